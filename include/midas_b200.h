@@ -1,0 +1,227 @@
+/*
+ * midas_b200.h — C-ABI of libmidas_b200.so, the B200 (sm_100a) drop-in for the
+ * per-sample pileup hot path of snayfach/MIDAS v1.3.0.
+ *
+ * The reference has no FFI layer of its own; the seam this ABI replaces is two
+ * Python call sites plus the third-party method beneath them (all paths are
+ * relative to the reference tree):
+ *
+ *   mb_snps_pileup*      <- midas/run/snps.py:219-244  pysam_pileup()
+ *                           midas/run/snps.py:164-216  species_pileup()   (counting + stats)
+ *                           midas/run/snps.py:141-162  keep_read()        (per-read filter)
+ *                           midas/run/snps.py:194-199  pysam count_coverage() call site
+ *   mb_genes_coverage*   <- midas/run/genes.py:171-203 count_mapped_bp()
+ *                           midas/run/genes.py:153-169 keep_read()
+ *   mb_pack_reads        <- what pysam/htslib hands to those loops (decoded BAM
+ *                           records), re-laid as the struct-of-arrays the GPU reads
+ *   mb_format_snps_tsv   <- midas/run/snps.py:179-182,201-210 (row text of <sp>.snps.gz)
+ *
+ * Conventions
+ *   - plain C, no C++/torch types; every function returns MB_OK (0) or a negative
+ *     mb_status; mb_last_error() gives a thread-local message for the last failure.
+ *     The library never calls exit()/abort() and never throws across the ABI
+ *     (contrast sys.exit in midas/utility.py:227-232).
+ *   - "host" pointers are caller-owned and only read/written during the call.
+ *     "dev" pointers are CUDA device pointers on the context's device (e.g. the
+ *     data_ptr() of a torch tensor); work on them is enqueued on the context's
+ *     stream (mb_ctx_set_stream) and is asynchronous unless stated otherwise.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point
+ *     fails with MB_ECUDA.
+ */
+#ifndef MIDAS_B200_H
+#define MIDAS_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------ status */
+typedef enum {
+  MB_OK = 0,
+  MB_EINVAL = -1,     /* bad argument; also: input on which the reference itself raises
+                         (missing NM tag -> KeyError snps.py:148; alen==0 or l_qseq==0 ->
+                         ZeroDivisionError snps.py:148/157; missing qualities -> np.mean(None)) */
+  MB_ECUDA = -2,      /* CUDA runtime error / no device */
+  MB_ENOMEM = -3,
+  MB_EOVERFLOW = -4,  /* a u32 counter or coordinate would overflow */
+  MB_EMALFORMED = -5, /* CIGAR/seq length mismatch, P op, read beyond contig start */
+  MB_EUNSORTED = -6   /* snps reads must be sorted by (layout order, pos) */
+} mb_status;
+
+const char* mb_version(void);
+const char* mb_last_error(void);
+
+/* positions per genome tile owned by one CTA; species regions are padded to it */
+#define MB_TILE 4096u
+/* bases per packed block (16 qualities = one 128-bit load, 16 x 2-bit = one u32) */
+#define MB_BLOCK 16u
+
+/* ----------------------------------------------------------------- filters */
+/* args['mapid','aln_cov','readq','mapq','baseq'] of the reference
+ * (scripts/run_midas.py:410-419 snps defaults 94.0/0.75/20/20/30,
+ *  scripts/run_midas.py:277-284 genes defaults 94.0/0.75/20/0, baseq unused). */
+typedef struct {
+  double mapid;    /* drop if 100*(alen-NM)/float(alen) < mapid      (snps.py:148) */
+  double aln_cov;  /* drop if alen/float(l_qseq)       < aln_cov    (snps.py:157) */
+  int32_t readq;   /* drop if mean(qual)               < readq      (snps.py:151) */
+  int32_t mapq;    /* drop if mapping_quality          < mapq       (snps.py:154) */
+  int32_t baseq;   /* per base: count only qual >= baseq; 0 disables the test (pysam) */
+  int32_t reserved;
+} mb_filters;
+
+/* ------------------------------------------------ plain (BAM-like) records */
+/* One decoded alignment per index, exactly the fields the reference loops read
+ * from pysam.AlignedSegment (snps.py:145-157, genes.py:154-166,180). */
+typedef struct {
+  uint64_t n_reads;
+  const int32_t* ref_id;      /* [n] index into mb_ref contigs (snps) / genes (genes) */
+  const int32_t* pos;         /* [n] 0-based leftmost reference position */
+  const uint8_t* mapq;        /* [n] */
+  const int32_t* nm;          /* [n] NM tag; negative = tag missing -> MB_EINVAL */
+  const int32_t* l_qseq;      /* [n] stored query length (soft clips included) */
+  const uint64_t* cigar_off;  /* [n+1] prefix offsets into cigar[] */
+  const uint32_t* cigar;      /* BAM encoding: len<<4 | op, op in MIDNSHP=X (0..8) */
+  const uint64_t* seq_off;    /* [n+1] prefix offsets (in bases) into seq[] and qual[] */
+  const uint8_t* seq;         /* one BAM 4-bit code per byte: =ACMGRSVTWYHKDBN (A=1,C=2,G=4,T=8) */
+  const uint8_t* qual;        /* raw Phred, one per base; 0xFF in the first byte = missing */
+} mb_plain_reads;
+
+/* -------------------------------------------------------- reference layout */
+/* Contigs of all selected species (snps.py:55-67 initialize_contigs). The
+ * library lays them out species-major in one padded global coordinate space:
+ * each species starts at a multiple of MB_TILE, contigs of a species are
+ * consecutive in the order given. */
+typedef struct {
+  uint32_t n_contigs;
+  uint32_t n_species;
+  const uint32_t* contig_len;      /* [n_contigs] */
+  const int32_t* contig_species;   /* [n_contigs] in [0, n_species) */
+} mb_ref;
+
+typedef struct mb_layout mb_layout;
+int mb_layout_create(const mb_ref* ref, mb_layout** out);
+void mb_layout_destroy(mb_layout* L);
+uint64_t mb_layout_gpad(const mb_layout* L);             /* padded genome size, multiple of MB_TILE */
+uint32_t mb_layout_n_tiles(const mb_layout* L);
+const uint32_t* mb_layout_contig_goff(const mb_layout* L);   /* [n_contigs] global offset of contig base 0 */
+const uint32_t* mb_layout_species_goff(const mb_layout* L);  /* [n_species+1] tile-aligned region starts */
+const uint64_t* mb_layout_species_len(const mb_layout* L);   /* [n_species] sum of contig lengths */
+
+/* --------------------------------------------------------- packed reads SoA */
+/* 16-byte per-read header. For snps `loc` is the global padded coordinate of the
+ * first aligned reference base; for genes it is the gene index. */
+typedef struct {
+  uint32_t loc;
+  uint16_t l_qseq;    /* query_length (snps.py:146) */
+  uint16_t alen;      /* len(query_alignment_sequence) = l_qseq - leading S - trailing S (snps.py:145) */
+  uint16_t q_start;   /* sum of leading soft clips = query index of the first aligned base */
+  uint16_t nm;        /* NM tag, saturated at 65535 */
+  uint16_t ref_span;  /* reference bases spanned, clipped at the contig end */
+  uint8_t mapq;
+  uint8_t flags;      /* MB_RF_* */
+} mb_read_hdr;
+
+#define MB_RF_SIMPLE 0x01u /* one aligned segment [q_start, q_start+ref_span) -> [loc, loc+ref_span): no CIGAR walk */
+#define MB_RF_NMSAT 0x02u  /* NM exceeded 65535 and was saturated */
+
+/* Struct of arrays, identical on host and in HBM (upload is a plain copy).
+ *   blk_off[i]..blk_off[i+1]  MB_BLOCK-base blocks of read i (ceil(l_qseq/16))
+ *   seq2[b]   16 bases x 2 bit, planar inside the block: bit k = low bit of base k,
+ *             bit 16+k = high bit of base k (A=0 C=1 G=2 T=3; non-ACGT and padding = 0)
+ *   qual[16b+k] bit 7 = base k is a literal A/C/G/T (countable), bits 0-6 = Phred;
+ *             padding bytes are 0
+ *   cplx[i]   for reads without MB_RF_SIMPLE: index into cigar[] of a record
+ *             {n_ops, op0, op1, ...} (BAM op words, contig-end overhang already
+ *             rewritten to a trailing soft clip); 0xFFFFFFFF for simple reads
+ */
+typedef struct {
+  uint64_t n_reads;
+  uint64_t n_blocks;
+  uint64_t n_cigar_words;
+  uint64_t total_bases;      /* sum of l_qseq (the Gbases numerator) */
+  uint32_t max_ref_span;
+  uint32_t sorted;           /* 1: hdr[].loc ascending (required by the snps path) */
+  const mb_read_hdr* hdr;    /* [n_reads] */
+  const uint32_t* blk_off;   /* [n_reads+1] */
+  const uint32_t* cplx;      /* [n_reads] */
+  const uint32_t* cigar;     /* [n_cigar_words] */
+  const uint32_t* seq2;      /* [n_blocks] */
+  const uint8_t* qual;       /* [n_blocks*16] */
+} mb_packed_reads;
+
+/* Host-side re-layout of decoded BAM records into the packed SoA (the step
+ * pysam/htslib performs for the reference before its loops see a record). Output
+ * buffers are library-owned (page-locked when `pinned` != 0 and a CUDA device is
+ * present) and released with mb_packed_free. mode 0 = snps (loc = global
+ * coordinate from the layout; `sort` != 0 stable-sorts by loc, otherwise unsorted
+ * input is MB_EUNSORTED), mode 1 = genes (loc = ref_id, file order preserved). */
+int mb_pack_reads(const mb_plain_reads* in, const mb_layout* L, int mode, int sort,
+                  int pinned, int n_threads, mb_packed_reads** out);
+void mb_packed_free(mb_packed_reads* p);
+
+/* ------------------------------------------------------------------ context */
+typedef struct mb_ctx mb_ctx;
+int mb_ctx_create(int device, mb_ctx** out);
+void mb_ctx_destroy(mb_ctx* ctx);
+int mb_ctx_set_stream(mb_ctx* ctx, void* cuda_stream); /* cudaStream_t; NULL = context-owned stream */
+int mb_ctx_sync(mb_ctx* ctx);
+int mb_ctx_device(const mb_ctx* ctx);
+/* kernels launched by this context since creation (for bench.py gpu_launches) */
+uint64_t mb_ctx_launch_count(const mb_ctx* ctx);
+/* device time (ms, CUDA events on the context stream) of the dominant pileup /
+ * coverage kernel of the most recent *_dev call; synchronises the stream. */
+int mb_ctx_last_kernel_ms(mb_ctx* ctx, float* ms);
+
+/* ------------------------------------------------- device-resident reads */
+typedef struct mb_dev_reads mb_dev_reads;
+int mb_reads_upload(mb_ctx* ctx, const mb_packed_reads* host, mb_dev_reads** out);
+void mb_reads_free(mb_ctx* ctx, mb_dev_reads* r);
+uint64_t mb_reads_bytes(const mb_dev_reads* r); /* bytes resident in HBM */
+
+/* -------------------------------------------------------------- snps path */
+/* per species: the aln_stats dict of species_pileup (snps.py:172-176, 211-213) */
+typedef struct {
+  uint64_t genome_length;
+  uint64_t covered_bases;
+  uint64_t total_depth;
+  uint64_t aligned_reads;
+  uint64_t mapped_reads;
+} mb_species_stats;
+
+/* Device-resident pileup. counts_dev: uint32 [4][gpad] (A,C,G,T planes, padded
+ * global coordinates; every element is written, no pre-zeroing needed).
+ * stats_dev: mb_species_stats [n_species] (overwritten). Asynchronous. */
+int mb_snps_pileup_dev(mb_ctx* ctx, const mb_dev_reads* reads, const mb_layout* L,
+                       const mb_filters* f, uint32_t* counts_dev, mb_species_stats* stats_dev);
+
+/* Host-buffer convenience = upload + mb_snps_pileup_dev + download; synchronous.
+ * counts_host: uint32 [4][gpad]; stats_host: [n_species]. */
+int mb_snps_pileup(mb_ctx* ctx, const mb_packed_reads* reads, const mb_layout* L,
+                   const mb_filters* f, uint32_t* counts_host, mb_species_stats* stats_host);
+
+/* ------------------------------------------------------------- genes path */
+/* per gene: Gene.{aligned_reads,mapped_reads,depth} of count_mapped_bp
+ * (genes.py:181-189); mapped_bp = sum of alen over kept reads, depth =
+ * mapped_bp / gene_len in fp64 (exact_order = 0) or the reference's running
+ * sum of alen/float(gene_len) in file order (exact_order = 1, bit-exact). */
+typedef struct {
+  uint32_t aligned_reads;
+  uint32_t mapped_reads;
+  uint64_t mapped_bp;
+  double depth;
+} mb_gene_out;
+
+int mb_genes_coverage_dev(mb_ctx* ctx, const mb_dev_reads* reads, const uint32_t* gene_len_dev,
+                          uint32_t n_genes, const mb_filters* f, int exact_order,
+                          mb_gene_out* out_dev);
+int mb_genes_coverage(mb_ctx* ctx, const mb_packed_reads* reads, const uint32_t* gene_len_host,
+                      uint32_t n_genes, const mb_filters* f, int exact_order,
+                      mb_gene_out* out_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MIDAS_B200_H */

@@ -1,0 +1,88 @@
+// Internal declarations shared by the translation units of libmidas_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include <atomic>
+#include <mutex>
+#include <unordered_map>
+
+#include "../../include/midas_b200.h"
+
+namespace mb {
+
+void set_error(const char* fmt, ...);
+int fail(int status, const char* fmt, ...);
+
+#define MB_CUDA_TRY(expr)                                                                   \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess)                                                                  \
+      return mb::fail(MB_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),   \
+                      __FILE__, __LINE__);                                                  \
+  } while (0)
+
+enum { OP_M = 0, OP_I = 1, OP_D = 2, OP_N = 3, OP_S = 4, OP_H = 5, OP_P = 6, OP_EQ = 7, OP_X = 8 };
+
+}  // namespace mb
+
+// --------------------------------------------------------------------------------------
+struct mb_layout {
+  uint64_t id;  // unique, for device-side caches
+  uint32_t n_contigs, n_species;
+  uint64_t gpad;
+  uint32_t n_tiles;
+  std::vector<uint32_t> contig_len, contig_goff;
+  std::vector<int32_t> contig_species;
+  std::vector<uint32_t> species_goff;  // [n_species+1]
+  std::vector<uint64_t> species_len;   // [n_species]
+  std::vector<int32_t> tile_species;   // [n_tiles], -1 for none
+};
+
+struct mb_packed_owner {  // allocation record behind a library-owned mb_packed_reads
+  mb_packed_reads pub;
+  bool pinned;
+  void* buf[6];
+};
+
+struct mb_dev_reads {
+  uint64_t n_reads, n_blocks, n_cigar_words, total_bases;
+  uint32_t max_ref_span, sorted;
+  mb_read_hdr* hdr;
+  uint32_t* blk_off;
+  uint32_t* cplx;
+  uint32_t* cigar;
+  uint32_t* seq2;
+  uint8_t* qual;
+  uint64_t bytes;
+};
+
+struct mb_dev_layout {  // device mirror of the parts of a layout the kernels read
+  int32_t* tile_species;
+  uint64_t* species_len;
+};
+
+struct mb_ctx {
+  int device;
+  int sm_count;
+  cudaStream_t own_stream;
+  cudaStream_t stream;
+  cudaEvent_t ev0, ev1;
+  bool ev_valid;
+  uint64_t launches;
+  bool pile_attr_set;
+  // scratch (grown on demand)
+  uint32_t* tile_rng;  // [2*n_tiles]
+  size_t tile_rng_cap;
+  uint32_t* sched;     // dynamic tile scheduler counters
+  std::unordered_map<uint64_t, mb_dev_layout> layouts;
+  // staging for the host-buffer convenience calls
+  void* stage[8];
+  size_t stage_cap[8];
+};
+
+namespace mb {
+int ctx_reserve(mb_ctx* ctx, int slot, size_t bytes, void** out);
+int get_dev_layout(mb_ctx* ctx, const mb_layout* L, mb_dev_layout* out);
+}  // namespace mb

@@ -1,0 +1,177 @@
+// Context, device-resident reads and device mirrors of the reference layout.
+#include <cstdio>
+#include <cstring>
+
+#include "common.h"
+
+namespace mb {
+
+int ctx_reserve(mb_ctx* ctx, int slot, size_t bytes, void** out) {
+  if (bytes == 0) bytes = 256;
+  if (ctx->stage_cap[slot] < bytes) {
+    if (ctx->stage[slot]) {
+      MB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+      MB_CUDA_TRY(cudaFree(ctx->stage[slot]));
+      ctx->stage[slot] = nullptr;
+      ctx->stage_cap[slot] = 0;
+    }
+    size_t cap = bytes + bytes / 8;
+    cap = (cap + 255) / 256 * 256;
+    MB_CUDA_TRY(cudaMalloc(&ctx->stage[slot], cap));
+    ctx->stage_cap[slot] = cap;
+  }
+  *out = ctx->stage[slot];
+  return MB_OK;
+}
+
+int get_dev_layout(mb_ctx* ctx, const mb_layout* L, mb_dev_layout* out) {
+  auto it = ctx->layouts.find(L->id);
+  if (it != ctx->layouts.end()) { *out = it->second; return MB_OK; }
+  mb_dev_layout d{};
+  size_t nt = L->n_tiles ? L->n_tiles : 1, ns = L->n_species ? L->n_species : 1;
+  MB_CUDA_TRY(cudaMalloc(&d.tile_species, sizeof(int32_t) * nt));
+  MB_CUDA_TRY(cudaMalloc(&d.species_len, sizeof(uint64_t) * ns));
+  if (L->n_tiles)
+    MB_CUDA_TRY(cudaMemcpyAsync(d.tile_species, L->tile_species.data(), sizeof(int32_t) * L->n_tiles,
+                                cudaMemcpyHostToDevice, ctx->stream));
+  if (L->n_species)
+    MB_CUDA_TRY(cudaMemcpyAsync(d.species_len, L->species_len.data(), sizeof(uint64_t) * L->n_species,
+                                cudaMemcpyHostToDevice, ctx->stream));
+  // the host vectors outlive the copy only if the layout does: make the upload complete now
+  MB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  ctx->layouts[L->id] = d;
+  *out = d;
+  return MB_OK;
+}
+
+}  // namespace mb
+
+extern "C" int mb_ctx_create(int device, mb_ctx** out) {
+  if (!out) return mb::fail(MB_EINVAL, "mb_ctx_create: null argument");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return mb::fail(MB_ECUDA, "mb_ctx_create: no CUDA device (%s); libmidas_b200 has no CPU fallback",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  if (device < 0 || device >= n) return mb::fail(MB_EINVAL, "mb_ctx_create: device %d not in [0,%d)", device, n);
+  MB_CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  MB_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10)
+    return mb::fail(MB_ECUDA, "mb_ctx_create: device %d is sm_%d%d; this library is built for sm_100a only", device,
+                    prop.major, prop.minor);
+  mb_ctx* c = new mb_ctx();
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  c->ev_valid = false;
+  c->launches = 0;
+  c->pile_attr_set = false;
+  c->tile_rng = nullptr;
+  c->tile_rng_cap = 0;
+  c->sched = nullptr;
+  memset(c->stage, 0, sizeof(c->stage));
+  memset(c->stage_cap, 0, sizeof(c->stage_cap));
+  MB_CUDA_TRY(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+  c->stream = c->own_stream;
+  MB_CUDA_TRY(cudaEventCreate(&c->ev0));
+  MB_CUDA_TRY(cudaEventCreate(&c->ev1));
+  MB_CUDA_TRY(cudaMalloc(&c->sched, 256));
+  *out = c;
+  return MB_OK;
+}
+
+extern "C" void mb_ctx_destroy(mb_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  for (auto& kv : c->layouts) {
+    cudaFree(kv.second.tile_species);
+    cudaFree(kv.second.species_len);
+  }
+  for (int i = 0; i < 8; ++i)
+    if (c->stage[i]) cudaFree(c->stage[i]);
+  if (c->tile_rng) cudaFree(c->tile_rng);
+  if (c->sched) cudaFree(c->sched);
+  cudaEventDestroy(c->ev0);
+  cudaEventDestroy(c->ev1);
+  cudaStreamDestroy(c->own_stream);
+  delete c;
+}
+
+extern "C" int mb_ctx_set_stream(mb_ctx* c, void* s) {
+  if (!c) return mb::fail(MB_EINVAL, "mb_ctx_set_stream: null context");
+  MB_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  c->stream = s ? (cudaStream_t)s : c->own_stream;
+  return MB_OK;
+}
+
+extern "C" int mb_ctx_sync(mb_ctx* c) {
+  if (!c) return mb::fail(MB_EINVAL, "mb_ctx_sync: null context");
+  MB_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return MB_OK;
+}
+
+extern "C" int mb_ctx_device(const mb_ctx* c) { return c ? c->device : -1; }
+extern "C" uint64_t mb_ctx_launch_count(const mb_ctx* c) { return c ? c->launches : 0; }
+
+extern "C" int mb_ctx_last_kernel_ms(mb_ctx* c, float* ms) {
+  if (!c || !ms) return mb::fail(MB_EINVAL, "mb_ctx_last_kernel_ms: null argument");
+  if (!c->ev_valid) return mb::fail(MB_EINVAL, "mb_ctx_last_kernel_ms: no kernel has been timed yet");
+  MB_CUDA_TRY(cudaEventSynchronize(c->ev1));
+  MB_CUDA_TRY(cudaEventElapsedTime(ms, c->ev0, c->ev1));
+  return MB_OK;
+}
+
+// ------------------------------------------------------------------ device-resident reads
+extern "C" int mb_reads_upload(mb_ctx* c, const mb_packed_reads* h, mb_dev_reads** out) {
+  if (!c || !h || !out) return mb::fail(MB_EINVAL, "mb_reads_upload: null argument");
+  MB_CUDA_TRY(cudaSetDevice(c->device));
+  mb_dev_reads* d = new mb_dev_reads();
+  memset(d, 0, sizeof(*d));
+  d->n_reads = h->n_reads;
+  d->n_blocks = h->n_blocks;
+  d->n_cigar_words = h->n_cigar_words;
+  d->total_bases = h->total_bases;
+  d->max_ref_span = h->max_ref_span;
+  d->sorted = h->sorted;
+  struct Part { void** dst; const void* src; size_t bytes; } parts[6] = {
+      {(void**)&d->hdr, h->hdr, sizeof(mb_read_hdr) * (size_t)h->n_reads},
+      {(void**)&d->blk_off, h->blk_off, sizeof(uint32_t) * (size_t)(h->n_reads + 1)},
+      {(void**)&d->cplx, h->cplx, sizeof(uint32_t) * (size_t)h->n_reads},
+      {(void**)&d->cigar, h->cigar, sizeof(uint32_t) * (size_t)h->n_cigar_words},
+      {(void**)&d->seq2, h->seq2, sizeof(uint32_t) * (size_t)h->n_blocks},
+      {(void**)&d->qual, h->qual, (size_t)h->n_blocks * MB_BLOCK}};
+  for (auto& p : parts) {
+    // +256 B of zero slack so vectorised tail loads never leave the allocation
+    cudaError_t e = cudaMalloc(p.dst, p.bytes + 256);
+    if (e != cudaSuccess) {
+      mb_reads_free(c, d);
+      return mb::fail(MB_ENOMEM, "mb_reads_upload: cudaMalloc(%zu) failed: %s", p.bytes, cudaGetErrorString(e));
+    }
+    cudaMemsetAsync((char*)*p.dst + p.bytes, 0, 256, c->stream);
+    if (p.bytes) {
+      e = cudaMemcpyAsync(*p.dst, p.src, p.bytes, cudaMemcpyHostToDevice, c->stream);
+      if (e != cudaSuccess) {
+        mb_reads_free(c, d);
+        return mb::fail(MB_ECUDA, "mb_reads_upload: H2D copy failed: %s", cudaGetErrorString(e));
+      }
+    }
+    d->bytes += p.bytes;
+  }
+  *out = d;
+  return MB_OK;
+}
+
+extern "C" void mb_reads_free(mb_ctx* c, mb_dev_reads* d) {
+  if (!d) return;
+  if (c) { cudaSetDevice(c->device); cudaStreamSynchronize(c->stream); }
+  cudaFree(d->hdr);
+  cudaFree(d->blk_off);
+  cudaFree(d->cplx);
+  cudaFree(d->cigar);
+  cudaFree(d->seq2);
+  cudaFree(d->qual);
+  delete d;
+}
+
+extern "C" uint64_t mb_reads_bytes(const mb_dev_reads* d) { return d ? d->bytes : 0; }

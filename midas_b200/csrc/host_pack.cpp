@@ -1,0 +1,421 @@
+// Host side of the boundary: reference layout and the re-layout of decoded BAM
+// records (mb_plain_reads) into the packed struct-of-arrays the kernels stream.
+//
+// This is the step pysam/htslib performs for the reference before its loops see an
+// AlignedSegment (reference midas/run/snps.py:186,194; midas/run/genes.py:175-180):
+// it derives, per read, the two CIGAR-only quantities keep_read needs
+//   alen  = len(aln.query_alignment_sequence)   (snps.py:145, genes.py:154)
+//   qlen  = aln.query_length                    (snps.py:146)
+// and validates the inputs on which the reference would raise. No counting happens here.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <numeric>
+#include <thread>
+
+#include "common.h"
+
+namespace mb {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int fail(int status, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return status;
+}
+
+}  // namespace mb
+
+extern "C" const char* mb_version(void) { return "midas_b200 0.1.0 (sm_100a)"; }
+extern "C" const char* mb_last_error(void) { return mb::g_err; }
+
+// ------------------------------------------------------------------------------ layout
+static std::atomic<uint64_t> g_layout_id{1};
+
+extern "C" int mb_layout_create(const mb_ref* ref, mb_layout** out) {
+  if (!ref || !out) return mb::fail(MB_EINVAL, "mb_layout_create: null argument");
+  if (ref->n_species == 0 && ref->n_contigs != 0)
+    return mb::fail(MB_EINVAL, "mb_layout_create: contigs without species");
+  mb_layout* L = new mb_layout();
+  L->id = g_layout_id.fetch_add(1);
+  L->n_contigs = ref->n_contigs;
+  L->n_species = ref->n_species;
+  L->contig_len.assign(ref->contig_len, ref->contig_len + ref->n_contigs);
+  L->contig_species.assign(ref->contig_species, ref->contig_species + ref->n_contigs);
+  L->contig_goff.assign(ref->n_contigs, 0);
+  L->species_goff.assign(ref->n_species + 1, 0);
+  L->species_len.assign(ref->n_species, 0);
+  for (uint32_t c = 0; c < ref->n_contigs; ++c) {
+    int32_t s = ref->contig_species[c];
+    if (s < 0 || (uint32_t)s >= ref->n_species) {
+      delete L;
+      return mb::fail(MB_EINVAL, "mb_layout_create: contig %u has species %d outside [0,%u)", c, s,
+                      ref->n_species);
+    }
+    if (ref->contig_len[c] == 0) {  // pysam count_coverage raises ValueError("interval of size 0")
+      delete L;
+      return mb::fail(MB_EINVAL, "mb_layout_create: contig %u has length 0", c);
+    }
+    L->species_len[s] += ref->contig_len[c];
+  }
+  // species-major, each species region starts on a tile boundary
+  uint64_t cur = 0;
+  std::vector<uint64_t> next(ref->n_species);
+  for (uint32_t s = 0; s < ref->n_species; ++s) {
+    cur = (cur + MB_TILE - 1) / MB_TILE * MB_TILE;
+    L->species_goff[s] = (uint32_t)cur;
+    next[s] = cur;
+    cur += L->species_len[s];
+    if (cur > 0xFFFF0000ull) {
+      delete L;
+      return mb::fail(MB_EOVERFLOW, "mb_layout_create: padded genome exceeds 32-bit coordinates");
+    }
+  }
+  cur = (cur + MB_TILE - 1) / MB_TILE * MB_TILE;
+  L->species_goff[ref->n_species] = (uint32_t)cur;
+  L->gpad = cur;
+  L->n_tiles = (uint32_t)(cur / MB_TILE);
+  for (uint32_t c = 0; c < ref->n_contigs; ++c) {
+    int32_t s = ref->contig_species[c];
+    L->contig_goff[c] = (uint32_t)next[s];
+    next[s] += ref->contig_len[c];
+  }
+  L->tile_species.assign(L->n_tiles, -1);
+  for (uint32_t s = 0; s < ref->n_species; ++s) {
+    uint32_t t0 = L->species_goff[s] / MB_TILE;
+    uint32_t t1 = (uint32_t)((L->species_goff[s] + L->species_len[s] + MB_TILE - 1) / MB_TILE);
+    for (uint32_t t = t0; t < t1; ++t) L->tile_species[t] = (int32_t)s;
+  }
+  *out = L;
+  return MB_OK;
+}
+
+extern "C" void mb_layout_destroy(mb_layout* L) { delete L; }
+extern "C" uint64_t mb_layout_gpad(const mb_layout* L) { return L ? L->gpad : 0; }
+extern "C" uint32_t mb_layout_n_tiles(const mb_layout* L) { return L ? L->n_tiles : 0; }
+extern "C" const uint32_t* mb_layout_contig_goff(const mb_layout* L) { return L->contig_goff.data(); }
+extern "C" const uint32_t* mb_layout_species_goff(const mb_layout* L) { return L->species_goff.data(); }
+extern "C" const uint64_t* mb_layout_species_len(const mb_layout* L) { return L->species_len.data(); }
+
+// -------------------------------------------------------------------------------- pack
+namespace {
+
+struct ReadGeom {
+  uint32_t loc;
+  uint16_t alen, q_start, ref_span, nm;
+  uint8_t flags;
+  uint32_t n_blk;
+  uint32_t n_cplx_words;  // 0 for simple reads, else 1 + n_ops_after_clip
+};
+
+// Analyse one record. Returns MB_OK or an error (message set).
+int analyse(const mb_plain_reads* in, const mb_layout* L, int mode, uint64_t i, ReadGeom* g) {
+  const int64_t lq = in->l_qseq[i];
+  if (lq <= 0) return mb::fail(MB_EINVAL, "read %llu: l_qseq=%lld (reference: ZeroDivisionError snps.py:157)",
+                               (unsigned long long)i, (long long)lq);
+  if (lq > 65535) return mb::fail(MB_EOVERFLOW, "read %llu: l_qseq=%lld exceeds the 65535-base short-read limit",
+                                  (unsigned long long)i, (long long)lq);
+  if ((int64_t)(in->seq_off[i + 1] - in->seq_off[i]) != lq)
+    return mb::fail(MB_EMALFORMED, "read %llu: seq_off span != l_qseq", (unsigned long long)i);
+  if (in->nm[i] < 0)
+    return mb::fail(MB_EINVAL, "read %llu: NM tag missing (reference: KeyError snps.py:148)", (unsigned long long)i);
+  if (in->qual[in->seq_off[i]] == 0xFF)
+    return mb::fail(MB_EINVAL, "read %llu: qualities missing (reference: np.mean(None) snps.py:151)",
+                    (unsigned long long)i);
+  const uint32_t* cig = in->cigar + in->cigar_off[i];
+  const int64_t n_cig = (int64_t)(in->cigar_off[i + 1] - in->cigar_off[i]);
+  if (n_cig > 65535) return mb::fail(MB_EOVERFLOW, "read %llu: more than 65535 CIGAR ops", (unsigned long long)i);
+  int64_t qsum = 0, span = 0, n_match_ops = 0, n_other = 0;
+  for (int64_t k = 0; k < n_cig; ++k) {
+    uint32_t op = cig[k] & 0xF;
+    int64_t len = cig[k] >> 4;
+    if (op == mb::OP_P || op > mb::OP_X)
+      return mb::fail(MB_EMALFORMED, "read %llu: unsupported CIGAR op %u", (unsigned long long)i, op);
+    if (op == mb::OP_M || op == mb::OP_EQ || op == mb::OP_X) { qsum += len; span += len; ++n_match_ops; }
+    else if (op == mb::OP_I) { qsum += len; ++n_other; }
+    else if (op == mb::OP_S) { qsum += len; }
+    else if (op == mb::OP_D || op == mb::OP_N) { span += len; ++n_other; }
+  }
+  if (n_cig > 0 && qsum != lq)
+    return mb::fail(MB_EMALFORMED, "read %llu: CIGAR consumes %lld query bases, l_qseq=%lld", (unsigned long long)i,
+                    (long long)qsum, (long long)lq);
+  // pysam getQueryStart / getQueryEnd (the end walk never visits op 0)
+  int64_t lead = 0, trail = 0;
+  for (int64_t k = 0; k < n_cig; ++k) {
+    uint32_t op = cig[k] & 0xF;
+    if (op == mb::OP_H) continue;
+    if (op == mb::OP_S) lead += cig[k] >> 4; else break;
+  }
+  for (int64_t k = n_cig - 1; k >= 1; --k) {
+    uint32_t op = cig[k] & 0xF;
+    if (op == mb::OP_H) continue;
+    if (op == mb::OP_S) trail += cig[k] >> 4; else break;
+  }
+  int64_t alen = lq - lead - trail;
+  if (alen <= 0) return mb::fail(MB_EINVAL, "read %llu: aligned length 0 (reference: ZeroDivisionError snps.py:148)",
+                                 (unsigned long long)i);
+  g->alen = (uint16_t)alen;
+  g->flags = 0;
+  uint32_t nm = (uint32_t)in->nm[i];
+  if (nm > 65535u) { nm = 65535u; g->flags |= MB_RF_NMSAT; }
+  g->nm = (uint16_t)nm;
+  g->n_blk = (uint32_t)((lq + MB_BLOCK - 1) / MB_BLOCK);
+  g->n_cplx_words = 0;
+  const int32_t rid = in->ref_id[i];
+  if (mode == 1) {  // genes: loc = gene index, the pileup geometry is unused
+    if (rid < 0 || (uint32_t)rid >= L->n_contigs)
+      return mb::fail(MB_EINVAL, "read %llu: ref_id %d outside [0,%u) (reference: KeyError genes.py:180)",
+                      (unsigned long long)i, rid, L->n_contigs);
+    g->loc = (uint32_t)rid;
+    g->q_start = (uint16_t)lead;
+    g->ref_span = 0;
+    g->flags |= MB_RF_SIMPLE;
+    return MB_OK;
+  }
+  if (rid < 0 || (uint32_t)rid >= L->n_contigs)
+    return mb::fail(MB_EINVAL, "read %llu: ref_id %d outside [0,%u)", (unsigned long long)i, rid, L->n_contigs);
+  const int64_t pos = in->pos[i];
+  const int64_t clen = L->contig_len[rid];
+  if (pos < 0 || pos >= clen)
+    return mb::fail(MB_EMALFORMED, "read %llu: pos %lld outside contig of length %lld", (unsigned long long)i,
+                    (long long)pos, (long long)clen);
+  g->loc = L->contig_goff[rid] + (uint32_t)pos;
+  const bool simple = (n_other == 0 && n_match_ops <= 1);
+  int64_t span_clipped = std::min<int64_t>(span, clen - pos);  // pysam ignores refpos >= contig_len
+  if (span_clipped > 65535)
+    return mb::fail(MB_EOVERFLOW, "read %llu: reference span %lld exceeds 65535", (unsigned long long)i,
+                    (long long)span_clipped);
+  g->ref_span = (uint16_t)span_clipped;
+  if (simple) {
+    // query index of the first aligned base = all S before the single M-like op
+    int64_t qs = 0;
+    for (int64_t k = 0; k < n_cig; ++k) {
+      uint32_t op = cig[k] & 0xF;
+      if (op == mb::OP_S) qs += cig[k] >> 4;
+      else if (op != mb::OP_H) break;
+    }
+    g->q_start = (uint16_t)qs;
+    g->flags |= MB_RF_SIMPLE;
+  } else {
+    g->q_start = (uint16_t)lead;
+    g->n_cplx_words = 1 + (uint32_t)n_cig;  // upper bound; H ops and post-clip ops are dropped when written
+  }
+  return MB_OK;
+}
+
+// Write the {n_ops, ops...} record of a complex read, clipped at the contig end. Returns words written.
+uint32_t write_cplx(const uint32_t* cig, int64_t n_cig, int64_t room /* contig_len - pos */, uint32_t* dst) {
+  uint32_t n = 0;
+  int64_t r = 0;
+  for (int64_t k = 0; k < n_cig && r < room; ++k) {
+    uint32_t op = cig[k] & 0xF;
+    int64_t len = cig[k] >> 4;
+    if (op == mb::OP_H || len == 0) continue;
+    if (op == mb::OP_M || op == mb::OP_EQ || op == mb::OP_X || op == mb::OP_D || op == mb::OP_N) {
+      if (r + len > room) len = room - r;
+      r += len;
+    }
+    dst[1 + n++] = ((uint32_t)len << 4) | op;
+  }
+  dst[0] = n;
+  return 1 + n;
+}
+
+static const uint8_t kNib2Code[16] = {0, 0, 1, 0, 2, 0, 0, 0, 3, 0, 0, 0, 0, 0, 0, 0};
+static const uint8_t kNibIsAcgt[16] = {0, 1, 1, 0, 1, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0};
+
+template <class F>
+void parallel_for(uint64_t n, int n_threads, F f) {
+  if (n_threads <= 1 || n < 4096) { f(0, n, 0); return; }
+  std::vector<std::thread> th;
+  uint64_t per = (n + n_threads - 1) / n_threads;
+  for (int t = 0; t < n_threads; ++t) {
+    uint64_t lo = std::min<uint64_t>(n, per * t), hi = std::min<uint64_t>(n, lo + per);
+    if (lo >= hi) break;
+    th.emplace_back([=] { f(lo, hi, t); });
+  }
+  for (auto& x : th) x.join();
+}
+
+void* alloc_host(size_t bytes, bool pinned) {
+  if (bytes == 0) bytes = 16;
+  void* p = nullptr;
+  if (pinned) {
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) == cudaSuccess) return p;
+    cudaGetLastError();
+    return nullptr;
+  }
+  if (posix_memalign(&p, 256, bytes) != 0) return nullptr;
+  return p;
+}
+
+}  // namespace
+
+extern "C" void mb_packed_free(mb_packed_reads* p) {
+  if (!p) return;
+  mb_packed_owner* o = reinterpret_cast<mb_packed_owner*>(p);
+  for (void* b : o->buf) {
+    if (!b) continue;
+    if (o->pinned) cudaFreeHost(b); else free(b);
+  }
+  delete o;
+}
+
+extern "C" int mb_pack_reads(const mb_plain_reads* in, const mb_layout* L, int mode, int sort, int pinned,
+                             int n_threads, mb_packed_reads** out) {
+  if (!in || !L || !out) return mb::fail(MB_EINVAL, "mb_pack_reads: null argument");
+  if (mode != 0 && mode != 1) return mb::fail(MB_EINVAL, "mb_pack_reads: mode must be 0 (snps) or 1 (genes)");
+  const uint64_t n = in->n_reads;
+  if (n >= 0xFFFFFFFFull) return mb::fail(MB_EOVERFLOW, "mb_pack_reads: more than 2^32-2 reads in one batch");
+  if (n_threads <= 0) n_threads = (int)std::min<unsigned>(32, std::max(1u, std::thread::hardware_concurrency()));
+
+  std::vector<ReadGeom> geom(n);
+  std::vector<int> rc(n_threads + 1, MB_OK);
+  std::vector<std::string> msg(n_threads + 1);
+  parallel_for(n, n_threads, [&](uint64_t lo, uint64_t hi, int t) {
+    for (uint64_t i = lo; i < hi; ++i) {
+      int r = analyse(in, L, mode, i, &geom[i]);
+      if (r != MB_OK) { rc[t] = r; msg[t] = mb_last_error(); return; }
+    }
+  });
+  for (int t = 0; t <= n_threads; ++t)
+    if (rc[t] != MB_OK) return mb::fail(rc[t], "%s", msg[t].c_str());
+
+  // order
+  std::vector<uint32_t> perm;
+  bool is_sorted = true;
+  if (mode == 0) {
+    for (uint64_t i = 1; i < n; ++i)
+      if (geom[i].loc < geom[i - 1].loc) { is_sorted = false; break; }
+    if (!is_sorted) {
+      if (!sort) return mb::fail(MB_EUNSORTED, "mb_pack_reads: snps reads are not sorted by (layout order, pos)");
+      perm.resize(n);
+      std::iota(perm.begin(), perm.end(), 0u);
+      std::stable_sort(perm.begin(), perm.end(), [&](uint32_t a, uint32_t b) { return geom[a].loc < geom[b].loc; });
+    }
+  }
+  auto src = [&](uint64_t j) -> uint64_t { return perm.empty() ? j : perm[j]; };
+
+  // offsets
+  std::vector<uint32_t> blk_off(n + 1), cg_off(n + 1);
+  uint64_t nb = 0, ncw = 0, tot_bases = 0;
+  uint32_t max_span = 0;
+  for (uint64_t j = 0; j < n; ++j) {
+    const ReadGeom& g = geom[src(j)];
+    blk_off[j] = (uint32_t)nb;
+    cg_off[j] = (uint32_t)ncw;
+    nb += g.n_blk;
+    ncw += g.n_cplx_words;
+    tot_bases += (uint64_t)in->l_qseq[src(j)];
+    max_span = std::max<uint32_t>(max_span, g.ref_span);
+    if (nb > 0xFFFFFFF0ull || ncw > 0xFFFFFFF0ull)
+      return mb::fail(MB_EOVERFLOW, "mb_pack_reads: batch too large for 32-bit block offsets");
+  }
+  blk_off[n] = (uint32_t)nb;
+  cg_off[n] = (uint32_t)ncw;
+
+  mb_packed_owner* o = new mb_packed_owner();
+  memset(o, 0, sizeof(*o));
+  o->pinned = pinned != 0;
+  size_t sizes[6] = {sizeof(mb_read_hdr) * (size_t)n, sizeof(uint32_t) * (size_t)(n + 1), sizeof(uint32_t) * (size_t)n,
+                     sizeof(uint32_t) * (size_t)ncw, sizeof(uint32_t) * (size_t)nb, (size_t)nb * MB_BLOCK};
+  for (int k = 0; k < 6; ++k) {
+    o->buf[k] = alloc_host(sizes[k], o->pinned);
+    if (!o->buf[k] && o->pinned) {  // no device / pin failure: fall back to pageable memory
+      for (int q = 0; q < k; ++q) { cudaFreeHost(o->buf[q]); o->buf[q] = nullptr; }
+      o->pinned = false;
+      k = -1;
+      continue;
+    }
+    if (!o->buf[k]) { mb_packed_free(&o->pub); return mb::fail(MB_ENOMEM, "mb_pack_reads: out of host memory"); }
+  }
+  mb_read_hdr* hdr = (mb_read_hdr*)o->buf[0];
+  uint32_t* blk = (uint32_t*)o->buf[1];
+  uint32_t* cplx = (uint32_t*)o->buf[2];
+  uint32_t* cigar = (uint32_t*)o->buf[3];
+  uint32_t* seq2 = (uint32_t*)o->buf[4];
+  uint8_t* qual = (uint8_t*)o->buf[5];
+  memcpy(blk, blk_off.data(), sizeof(uint32_t) * (n + 1));
+
+  std::vector<int> rc2(n_threads + 1, MB_OK);
+  parallel_for(n, n_threads, [&](uint64_t lo, uint64_t hi, int t) {
+    for (uint64_t j = lo; j < hi; ++j) {
+      const uint64_t i = src(j);
+      const ReadGeom& g = geom[i];
+      mb_read_hdr h;
+      h.loc = g.loc;
+      h.l_qseq = (uint16_t)in->l_qseq[i];
+      h.alen = g.alen;
+      h.q_start = g.q_start;
+      h.nm = g.nm;
+      h.ref_span = g.ref_span;
+      h.mapq = in->mapq[i];
+      h.flags = g.flags;
+      hdr[j] = h;
+      if (g.n_cplx_words) {
+        const uint32_t* cig = in->cigar + in->cigar_off[i];
+        const int64_t n_cig = (int64_t)(in->cigar_off[i + 1] - in->cigar_off[i]);
+        const int64_t room = (int64_t)L->contig_len[in->ref_id[i]] - in->pos[i];
+        uint32_t w = write_cplx(cig, n_cig, room, cigar + cg_off[j]);
+        for (uint32_t q = w; q < g.n_cplx_words; ++q) cigar[cg_off[j] + q] = 0;
+        cplx[j] = cg_off[j];
+      } else {
+        cplx[j] = 0xFFFFFFFFu;
+      }
+      const uint8_t* s = in->seq + in->seq_off[i];
+      const uint8_t* q = in->qual + in->seq_off[i];
+      const uint32_t lq = h.l_qseq;
+      for (uint32_t b = 0; b < g.n_blk; ++b) {
+        uint32_t lo_bits = 0, hi_bits = 0;
+        uint8_t* qd = qual + ((uint64_t)blk_off[j] + b) * MB_BLOCK;
+        for (uint32_t k = 0; k < MB_BLOCK; ++k) {
+          uint32_t qi = b * MB_BLOCK + k;
+          if (qi < lq) {
+            uint8_t nib = s[qi] & 0xF;
+            uint8_t ph = q[qi];
+            if (ph > 127) { rc2[t] = MB_EINVAL; ph = 127; }
+            uint8_t code = kNib2Code[nib];
+            lo_bits |= (uint32_t)(code & 1) << k;
+            hi_bits |= (uint32_t)(code >> 1) << k;
+            qd[k] = (uint8_t)(ph | (kNibIsAcgt[nib] ? 0x80 : 0));
+          } else {
+            qd[k] = 0;
+          }
+        }
+        seq2[(uint64_t)blk_off[j] + b] = lo_bits | (hi_bits << 16);
+      }
+    }
+  });
+  for (int t = 0; t <= n_threads; ++t)
+    if (rc2[t] != MB_OK) {
+      mb_packed_free(&o->pub);
+      return mb::fail(MB_EINVAL, "mb_pack_reads: base quality above 127 is not representable");
+    }
+
+  o->pub.n_reads = n;
+  o->pub.n_blocks = nb;
+  o->pub.n_cigar_words = ncw;
+  o->pub.total_bases = tot_bases;
+  o->pub.max_ref_span = max_span;
+  o->pub.sorted = (mode == 0) ? 1u : 0u;
+  o->pub.hdr = hdr;
+  o->pub.blk_off = blk;
+  o->pub.cplx = cplx;
+  o->pub.cigar = cigar;
+  o->pub.seq2 = seq2;
+  o->pub.qual = qual;
+  *out = &o->pub;
+  return MB_OK;
+}

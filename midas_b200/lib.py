@@ -1,0 +1,316 @@
+"""ctypes binding of include/midas_b200.h (libmidas_b200.so).
+
+There is no CPU fallback: if the shared library is missing, or a compute entry point is
+called without a B200, this module raises (MidasB200Error / OSError) instead of degrading.
+Device buffers handed to the *_dev entry points are torch CUDA tensors (torch is plumbing
+for device memory and streams only).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from .soa import CFilters, Filters, PlainReads, RefSet
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmidas_b200.so")
+
+MB_TILE = 4096
+MB_BLOCK = 16
+STATUS = {0: "MB_OK", -1: "MB_EINVAL", -2: "MB_ECUDA", -3: "MB_ENOMEM", -4: "MB_EOVERFLOW",
+          -5: "MB_EMALFORMED", -6: "MB_EUNSORTED"}
+
+
+class MidasB200Error(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(f"{STATUS.get(status, status)}: {message}")
+        self.status = status
+
+
+class CRef(C.Structure):
+    _fields_ = [("n_contigs", C.c_uint32), ("n_species", C.c_uint32),
+                ("contig_len", C.c_void_p), ("contig_species", C.c_void_p)]
+
+
+class CPlainReads(C.Structure):
+    _fields_ = [("n_reads", C.c_uint64), ("ref_id", C.c_void_p), ("pos", C.c_void_p), ("mapq", C.c_void_p),
+                ("nm", C.c_void_p), ("l_qseq", C.c_void_p), ("cigar_off", C.c_void_p), ("cigar", C.c_void_p),
+                ("seq_off", C.c_void_p), ("seq", C.c_void_p), ("qual", C.c_void_p)]
+
+
+class CPackedReads(C.Structure):
+    _fields_ = [("n_reads", C.c_uint64), ("n_blocks", C.c_uint64), ("n_cigar_words", C.c_uint64),
+                ("total_bases", C.c_uint64), ("max_ref_span", C.c_uint32), ("sorted", C.c_uint32),
+                ("hdr", C.c_void_p), ("blk_off", C.c_void_p), ("cplx", C.c_void_p), ("cigar", C.c_void_p),
+                ("seq2", C.c_void_p), ("qual", C.c_void_p)]
+
+
+HDR_DTYPE = np.dtype([("loc", "<u4"), ("l_qseq", "<u2"), ("alen", "<u2"), ("q_start", "<u2"), ("nm", "<u2"),
+                      ("ref_span", "<u2"), ("mapq", "u1"), ("flags", "u1")])
+STATS_DTYPE = np.dtype([("genome_length", "<u8"), ("covered_bases", "<u8"), ("total_depth", "<u8"),
+                        ("aligned_reads", "<u8"), ("mapped_reads", "<u8")])
+GENE_OUT_DTYPE = np.dtype([("aligned_reads", "<u4"), ("mapped_reads", "<u4"), ("mapped_bp", "<u8"),
+                           ("depth", "<f8")])
+
+# every symbol include/midas_b200.h declares (tests/test_abi.py checks the .so exports them all)
+EXPORTS = [
+    "mb_version", "mb_last_error",
+    "mb_layout_create", "mb_layout_destroy", "mb_layout_gpad", "mb_layout_n_tiles", "mb_layout_contig_goff",
+    "mb_layout_species_goff", "mb_layout_species_len",
+    "mb_pack_reads", "mb_packed_free",
+    "mb_ctx_create", "mb_ctx_destroy", "mb_ctx_set_stream", "mb_ctx_sync", "mb_ctx_device",
+    "mb_ctx_launch_count", "mb_ctx_last_kernel_ms",
+    "mb_reads_upload", "mb_reads_free", "mb_reads_bytes",
+    "mb_snps_pileup_dev", "mb_snps_pileup", "mb_genes_coverage_dev", "mb_genes_coverage",
+]
+
+_lib = None
+
+
+def load():
+    """Load libmidas_b200.so or raise — the product path never silently degrades."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise OSError(f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                      f"or `make -C midas_b200/csrc`; there is no CPU fallback")
+    L = C.CDLL(LIB_PATH)
+    L.mb_version.restype = C.c_char_p
+    L.mb_last_error.restype = C.c_char_p
+    L.mb_layout_gpad.restype = C.c_uint64
+    L.mb_layout_gpad.argtypes = [C.c_void_p]
+    L.mb_layout_n_tiles.restype = C.c_uint32
+    L.mb_layout_n_tiles.argtypes = [C.c_void_p]
+    for name in ("mb_layout_contig_goff", "mb_layout_species_goff", "mb_layout_species_len"):
+        getattr(L, name).restype = C.c_void_p
+        getattr(L, name).argtypes = [C.c_void_p]
+    L.mb_layout_create.argtypes = [C.POINTER(CRef), C.POINTER(C.c_void_p)]
+    L.mb_layout_destroy.argtypes = [C.c_void_p]
+    L.mb_layout_destroy.restype = None
+    L.mb_pack_reads.argtypes = [C.POINTER(CPlainReads), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                C.POINTER(C.POINTER(CPackedReads))]
+    L.mb_packed_free.argtypes = [C.POINTER(CPackedReads)]
+    L.mb_packed_free.restype = None
+    L.mb_ctx_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+    L.mb_ctx_destroy.argtypes = [C.c_void_p]
+    L.mb_ctx_destroy.restype = None
+    L.mb_ctx_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+    L.mb_ctx_sync.argtypes = [C.c_void_p]
+    L.mb_ctx_device.argtypes = [C.c_void_p]
+    L.mb_ctx_launch_count.argtypes = [C.c_void_p]
+    L.mb_ctx_launch_count.restype = C.c_uint64
+    L.mb_ctx_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+    L.mb_reads_upload.argtypes = [C.c_void_p, C.POINTER(CPackedReads), C.POINTER(C.c_void_p)]
+    L.mb_reads_free.argtypes = [C.c_void_p, C.c_void_p]
+    L.mb_reads_free.restype = None
+    L.mb_reads_bytes.argtypes = [C.c_void_p]
+    L.mb_reads_bytes.restype = C.c_uint64
+    L.mb_snps_pileup_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(CFilters), C.c_void_p, C.c_void_p]
+    L.mb_snps_pileup.argtypes = [C.c_void_p, C.POINTER(CPackedReads), C.c_void_p, C.POINTER(CFilters),
+                                 C.c_void_p, C.c_void_p]
+    L.mb_genes_coverage_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(CFilters),
+                                        C.c_int, C.c_void_p]
+    L.mb_genes_coverage.argtypes = [C.c_void_p, C.POINTER(CPackedReads), C.c_void_p, C.c_uint32,
+                                    C.POINTER(CFilters), C.c_int, C.c_void_p]
+    _lib = L
+    return L
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise MidasB200Error(rc, load().mb_last_error().decode(errors="replace"))
+
+
+def version() -> str:
+    return load().mb_version().decode()
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Layout:
+    """Padded, species-major global coordinate space (mb_layout)."""
+
+    def __init__(self, contig_len, contig_species, n_species: int):
+        L = load()
+        self.contig_len = np.ascontiguousarray(contig_len, np.uint32)
+        self.contig_species = np.ascontiguousarray(contig_species, np.int32)
+        self.n_contigs = int(self.contig_len.shape[0])
+        self.n_species = int(n_species)
+        cref = CRef(self.n_contigs, self.n_species, _ptr(self.contig_len), _ptr(self.contig_species))
+        h = C.c_void_p()
+        _check(L.mb_layout_create(C.byref(cref), C.byref(h)))
+        self._h = h
+        self.gpad = int(L.mb_layout_gpad(h))
+        self.n_tiles = int(L.mb_layout_n_tiles(h))
+
+        def arr(fn, n, dt):
+            p = fn(h)
+            if n == 0:
+                return np.zeros(0, dt)
+            return np.ctypeslib.as_array(C.cast(p, C.POINTER(np.ctypeslib.as_ctypes_type(dt))), (n,)).copy()
+
+        self.contig_goff = arr(L.mb_layout_contig_goff, self.n_contigs, np.dtype("<u4"))
+        self.species_goff = arr(L.mb_layout_species_goff, self.n_species + 1, np.dtype("<u4"))
+        self.species_len = arr(L.mb_layout_species_len, self.n_species, np.dtype("<u8"))
+
+    @staticmethod
+    def of(ref: RefSet) -> "Layout":
+        return Layout(ref.contig_len, ref.contig_species, ref.n_species)
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h and _lib is not None:
+            _lib.mb_layout_destroy(h)
+
+    def contig_counts(self, counts: np.ndarray, c: int) -> np.ndarray:
+        """View [4][contig_len[c]] of a [4][gpad] count array."""
+        o = int(self.contig_goff[c])
+        return counts[:, o:o + int(self.contig_len[c])]
+
+    def unpad(self, counts: np.ndarray) -> np.ndarray:
+        """[4][gpad] -> [4][sum(contig_len)] in the given contig order (the oracle's layout)."""
+        return np.concatenate([self.contig_counts(counts, c) for c in range(self.n_contigs)], axis=1) \
+            if self.n_contigs else counts[:, :0]
+
+
+class PackedReads:
+    """Library-owned packed struct-of-arrays (mb_packed_reads), host side."""
+
+    def __init__(self, reads: PlainReads, layout: Layout, mode: str = "snps", sort: bool = False,
+                 pinned: bool = False, threads: int = 0):
+        L = load()
+        self._keep = reads  # keep the source arrays alive during the call
+        cin = CPlainReads(reads.n_reads, _ptr(reads.ref_id), _ptr(reads.pos), _ptr(reads.mapq), _ptr(reads.nm),
+                          _ptr(reads.l_qseq), _ptr(reads.cigar_off), _ptr(reads.cigar), _ptr(reads.seq_off),
+                          _ptr(reads.seq), _ptr(reads.qual))
+        out = C.POINTER(CPackedReads)()
+        _check(L.mb_pack_reads(C.byref(cin), layout._h, {"snps": 0, "genes": 1}[mode], int(sort), int(pinned),
+                               int(threads), C.byref(out)))
+        self._p = out
+        self._keep = None
+        self.mode = mode
+
+    def __del__(self):
+        p, self._p = getattr(self, "_p", None), None
+        if p and _lib is not None:
+            _lib.mb_packed_free(p)
+
+    @property
+    def c(self) -> CPackedReads:
+        return self._p.contents
+
+    n_reads = property(lambda s: int(s.c.n_reads))
+    n_blocks = property(lambda s: int(s.c.n_blocks))
+    total_bases = property(lambda s: int(s.c.total_bases))
+    max_ref_span = property(lambda s: int(s.c.max_ref_span))
+
+    @property
+    def nbytes(self) -> int:
+        c = self.c
+        return int(16 * c.n_reads + 4 * (c.n_reads + 1) + 4 * c.n_reads + 4 * c.n_cigar_words + 4 * c.n_blocks
+                   + 16 * c.n_blocks)
+
+    def _view(self, ptr, n, dt):
+        if n == 0:
+            return np.zeros(0, dt)
+        buf = (C.c_char * (n * np.dtype(dt).itemsize)).from_address(ptr)
+        return np.frombuffer(buf, dtype=dt, count=n)
+
+    # numpy views of the packed arrays (valid while this object lives)
+    hdr = property(lambda s: s._view(s.c.hdr, s.n_reads, HDR_DTYPE))
+    blk_off = property(lambda s: s._view(s.c.blk_off, s.n_reads + 1, np.dtype("<u4")))
+    cplx = property(lambda s: s._view(s.c.cplx, s.n_reads, np.dtype("<u4")))
+    cigar = property(lambda s: s._view(s.c.cigar, int(s.c.n_cigar_words), np.dtype("<u4")))
+    seq2 = property(lambda s: s._view(s.c.seq2, s.n_blocks, np.dtype("<u4")))
+    qual = property(lambda s: s._view(s.c.qual, s.n_blocks * MB_BLOCK, np.dtype("u1")))
+
+
+class DevReads:
+    def __init__(self, ctx: "Context", packed: PackedReads):
+        h = C.c_void_p()
+        _check(load().mb_reads_upload(ctx._h, packed._p, C.byref(h)))
+        self._h, self._ctx = h, ctx
+        self.n_reads, self.total_bases, self.n_blocks = packed.n_reads, packed.total_bases, packed.n_blocks
+        self.nbytes = int(load().mb_reads_bytes(h))
+
+    def free(self):
+        h, self._h = self._h, None
+        if h and _lib is not None and self._ctx._h:
+            _lib.mb_reads_free(self._ctx._h, h)
+
+    __del__ = free
+
+
+class Context:
+    """One CUDA context/stream on one B200 (mb_ctx). Not re-entrant."""
+
+    def __init__(self, device: int = 0, use_torch_stream: bool = True):
+        L = load()
+        h = C.c_void_p()
+        _check(L.mb_ctx_create(int(device), C.byref(h)))
+        self._h = h
+        self.device = int(device)
+        if use_torch_stream:
+            import torch
+            self.set_stream(torch.cuda.current_stream(device).cuda_stream)
+
+    def close(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h and _lib is not None:
+            _lib.mb_ctx_destroy(h)
+
+    __del__ = close
+
+    def set_stream(self, cuda_stream: int | None):
+        _check(load().mb_ctx_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
+
+    def sync(self):
+        _check(load().mb_ctx_sync(self._h))
+
+    @property
+    def launch_count(self) -> int:
+        return int(load().mb_ctx_launch_count(self._h))
+
+    def last_kernel_ms(self) -> float:
+        ms = C.c_float()
+        _check(load().mb_ctx_last_kernel_ms(self._h, C.byref(ms)))
+        return float(ms.value)
+
+    def upload(self, packed: PackedReads) -> DevReads:
+        return DevReads(self, packed)
+
+    # ---- snps
+    def snps_pileup_dev(self, reads: DevReads, layout: Layout, filters: Filters, counts, stats):
+        """counts: torch int32/uint32 CUDA tensor [4, gpad]; stats: torch int64 CUDA tensor [n_species, 5]."""
+        f = CFilters.of(filters)
+        _check(load().mb_snps_pileup_dev(self._h, reads._h, layout._h, C.byref(f),
+                                         C.c_void_p(counts.data_ptr()), C.c_void_p(stats.data_ptr())))
+
+    def snps_pileup(self, packed: PackedReads, layout: Layout, filters: Filters,
+                    counts_out: np.ndarray | None = None):
+        """Host buffers in, host buffers out. Returns (counts uint32 [4][gpad], stats STATS_DTYPE [n_species])."""
+        counts = counts_out if counts_out is not None else np.empty((4, layout.gpad), np.uint32)
+        assert counts.dtype == np.uint32 and counts.shape == (4, layout.gpad) and counts.flags.c_contiguous
+        stats = np.zeros(layout.n_species, STATS_DTYPE)
+        f = CFilters.of(filters)
+        _check(load().mb_snps_pileup(self._h, packed._p, layout._h, C.byref(f), _ptr(counts), _ptr(stats)))
+        return counts, stats
+
+    # ---- genes
+    def genes_coverage_dev(self, reads: DevReads, gene_len, n_genes: int, filters: Filters, out, exact_order=False):
+        f = CFilters.of(filters)
+        _check(load().mb_genes_coverage_dev(self._h, reads._h, C.c_void_p(gene_len.data_ptr()), int(n_genes),
+                                            C.byref(f), int(exact_order), C.c_void_p(out.data_ptr())))
+
+    def genes_coverage(self, packed: PackedReads, gene_len: np.ndarray, filters: Filters, exact_order=False):
+        gene_len = np.ascontiguousarray(gene_len, np.uint32)
+        out = np.zeros(len(gene_len), GENE_OUT_DTYPE)
+        f = CFilters.of(filters)
+        _check(load().mb_genes_coverage(self._h, packed._p, _ptr(gene_len), len(gene_len), C.byref(f),
+                                        int(exact_order), _ptr(out)))
+        return out

@@ -1,0 +1,21 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a real B200 (run by the driver with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def ctx():
+    """One libmidas_b200 context on cuda:0 for the whole GPU session (fails loudly without a GPU)."""
+    from midas_b200 import lib
+    c = lib.Context(0)
+    yield c
+    c.close()

@@ -14,7 +14,6 @@
  *                           midas/run/genes.py:153-169 keep_read()
  *   mb_pack_reads        <- what pysam/htslib hands to those loops (decoded BAM
  *                           records), re-laid as the struct-of-arrays the GPU reads
- *   mb_format_snps_tsv   <- midas/run/snps.py:179-182,201-210 (row text of <sp>.snps.gz)
  *
  * Conventions
  *   - plain C, no C++/torch types; every function returns MB_OK (0) or a negative
@@ -174,6 +173,10 @@ uint64_t mb_ctx_launch_count(const mb_ctx* ctx);
 /* device time (ms, CUDA events on the context stream) of the dominant pileup /
  * coverage kernel of the most recent *_dev call; synchronises the stream. */
 int mb_ctx_last_kernel_ms(mb_ctx* ctx, float* ms);
+/* accumulated device time of that kernel over every *_dev call since the last reset
+ * (event pairs recorded on the context stream; reading synchronises the stream) */
+int mb_ctx_timing_reset(mb_ctx* ctx);
+int mb_ctx_timing_read(mb_ctx* ctx, double* total_ms, uint64_t* n_calls);
 
 /* ------------------------------------------------- device-resident reads */
 typedef struct mb_dev_reads mb_dev_reads;

@@ -68,8 +68,12 @@ struct mb_ctx {
   int sm_count;
   cudaStream_t own_stream;
   cudaStream_t stream;
-  cudaEvent_t ev0, ev1;
-  bool ev_valid;
+  // ring of event pairs bracketing the dominant kernel of each *_dev call
+  static constexpr int kRing = 64;
+  cudaEvent_t ring[kRing][2];
+  uint64_t ring_n;        // pairs recorded since the last timing reset
+  double ring_acc_ms;     // elapsed time of pairs already folded out of the ring
+  uint64_t ring_acc_n;
   uint64_t launches;
   bool pile_attr_set;
   // scratch (grown on demand)
@@ -78,11 +82,14 @@ struct mb_ctx {
   uint32_t* sched;     // dynamic tile scheduler counters
   std::unordered_map<uint64_t, mb_dev_layout> layouts;
   // staging for the host-buffer convenience calls
-  void* stage[8];
-  size_t stage_cap[8];
+  void* stage[16];
+  size_t stage_cap[16];
 };
 
 namespace mb {
+int timing_begin(mb_ctx* ctx);  // records the start event of the next pair on ctx->stream
+int timing_end(mb_ctx* ctx);
+int upload_reads(mb_ctx* ctx, const mb_packed_reads* h, mb_dev_reads* d, bool staged);
 int ctx_reserve(mb_ctx* ctx, int slot, size_t bytes, void** out);
 int get_dev_layout(mb_ctx* ctx, const mb_layout* L, mb_dev_layout* out);
 }  // namespace mb

@@ -44,6 +44,26 @@ int get_dev_layout(mb_ctx* ctx, const mb_layout* L, mb_dev_layout* out) {
   return MB_OK;
 }
 
+int timing_begin(mb_ctx* c) {
+  const int slot = (int)(c->ring_n % mb_ctx::kRing);
+  if (c->ring_n >= (uint64_t)mb_ctx::kRing) {  // fold the pair about to be overwritten
+    float ms = 0.f;
+    MB_CUDA_TRY(cudaEventSynchronize(c->ring[slot][1]));
+    MB_CUDA_TRY(cudaEventElapsedTime(&ms, c->ring[slot][0], c->ring[slot][1]));
+    c->ring_acc_ms += ms;
+    c->ring_acc_n += 1;
+  }
+  MB_CUDA_TRY(cudaEventRecord(c->ring[slot][0], c->stream));
+  return MB_OK;
+}
+
+int timing_end(mb_ctx* c) {
+  const int slot = (int)(c->ring_n % mb_ctx::kRing);
+  MB_CUDA_TRY(cudaEventRecord(c->ring[slot][1], c->stream));
+  c->ring_n += 1;
+  return MB_OK;
+}
+
 }  // namespace mb
 
 extern "C" int mb_ctx_create(int device, mb_ctx** out) {
@@ -63,7 +83,9 @@ extern "C" int mb_ctx_create(int device, mb_ctx** out) {
   mb_ctx* c = new mb_ctx();
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
-  c->ev_valid = false;
+  c->ring_n = 0;
+  c->ring_acc_ms = 0.0;
+  c->ring_acc_n = 0;
   c->launches = 0;
   c->pile_attr_set = false;
   c->tile_rng = nullptr;
@@ -73,8 +95,10 @@ extern "C" int mb_ctx_create(int device, mb_ctx** out) {
   memset(c->stage_cap, 0, sizeof(c->stage_cap));
   MB_CUDA_TRY(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
   c->stream = c->own_stream;
-  MB_CUDA_TRY(cudaEventCreate(&c->ev0));
-  MB_CUDA_TRY(cudaEventCreate(&c->ev1));
+  for (int i = 0; i < mb_ctx::kRing; ++i) {
+    MB_CUDA_TRY(cudaEventCreate(&c->ring[i][0]));
+    MB_CUDA_TRY(cudaEventCreate(&c->ring[i][1]));
+  }
   MB_CUDA_TRY(cudaMalloc(&c->sched, 256));
   *out = c;
   return MB_OK;
@@ -88,12 +112,14 @@ extern "C" void mb_ctx_destroy(mb_ctx* c) {
     cudaFree(kv.second.tile_species);
     cudaFree(kv.second.species_len);
   }
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < 16; ++i)
     if (c->stage[i]) cudaFree(c->stage[i]);
   if (c->tile_rng) cudaFree(c->tile_rng);
   if (c->sched) cudaFree(c->sched);
-  cudaEventDestroy(c->ev0);
-  cudaEventDestroy(c->ev1);
+  for (int i = 0; i < mb_ctx::kRing; ++i) {
+    cudaEventDestroy(c->ring[i][0]);
+    cudaEventDestroy(c->ring[i][1]);
+  }
   cudaStreamDestroy(c->own_stream);
   delete c;
 }
@@ -116,17 +142,45 @@ extern "C" uint64_t mb_ctx_launch_count(const mb_ctx* c) { return c ? c->launche
 
 extern "C" int mb_ctx_last_kernel_ms(mb_ctx* c, float* ms) {
   if (!c || !ms) return mb::fail(MB_EINVAL, "mb_ctx_last_kernel_ms: null argument");
-  if (!c->ev_valid) return mb::fail(MB_EINVAL, "mb_ctx_last_kernel_ms: no kernel has been timed yet");
-  MB_CUDA_TRY(cudaEventSynchronize(c->ev1));
-  MB_CUDA_TRY(cudaEventElapsedTime(ms, c->ev0, c->ev1));
+  if (c->ring_n == 0) return mb::fail(MB_EINVAL, "mb_ctx_last_kernel_ms: no kernel has been timed yet");
+  const int slot = (int)((c->ring_n - 1) % mb_ctx::kRing);
+  MB_CUDA_TRY(cudaEventSynchronize(c->ring[slot][1]));
+  MB_CUDA_TRY(cudaEventElapsedTime(ms, c->ring[slot][0], c->ring[slot][1]));
+  return MB_OK;
+}
+
+extern "C" int mb_ctx_timing_reset(mb_ctx* c) {
+  if (!c) return mb::fail(MB_EINVAL, "mb_ctx_timing_reset: null context");
+  MB_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  c->ring_n = 0;
+  c->ring_acc_ms = 0.0;
+  c->ring_acc_n = 0;
+  return MB_OK;
+}
+
+extern "C" int mb_ctx_timing_read(mb_ctx* c, double* total_ms, uint64_t* n) {
+  if (!c || !total_ms || !n) return mb::fail(MB_EINVAL, "mb_ctx_timing_read: null argument");
+  MB_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  double acc = c->ring_acc_ms;
+  uint64_t cnt = c->ring_acc_n;
+  const uint64_t live = c->ring_n < (uint64_t)mb_ctx::kRing ? c->ring_n : (uint64_t)mb_ctx::kRing;
+  for (uint64_t k = 0; k < live; ++k) {
+    const int slot = (int)((c->ring_n - 1 - k) % mb_ctx::kRing);
+    float ms = 0.f;
+    MB_CUDA_TRY(cudaEventElapsedTime(&ms, c->ring[slot][0], c->ring[slot][1]));
+    acc += ms;
+    cnt += 1;
+  }
+  *total_ms = acc;
+  *n = cnt;
   return MB_OK;
 }
 
 // ------------------------------------------------------------------ device-resident reads
-extern "C" int mb_reads_upload(mb_ctx* c, const mb_packed_reads* h, mb_dev_reads** out) {
-  if (!c || !h || !out) return mb::fail(MB_EINVAL, "mb_reads_upload: null argument");
-  MB_CUDA_TRY(cudaSetDevice(c->device));
-  mb_dev_reads* d = new mb_dev_reads();
+namespace mb {
+// Copy a packed batch to the device. staged: into context-owned buffers that are reused by the
+// next host-buffer call (no cudaMalloc/cudaFree on the e2e path); otherwise fresh allocations.
+int upload_reads(mb_ctx* c, const mb_packed_reads* h, mb_dev_reads* d, bool staged) {
   memset(d, 0, sizeof(*d));
   d->n_reads = h->n_reads;
   d->n_blocks = h->n_blocks;
@@ -141,23 +195,31 @@ extern "C" int mb_reads_upload(mb_ctx* c, const mb_packed_reads* h, mb_dev_reads
       {(void**)&d->cigar, h->cigar, sizeof(uint32_t) * (size_t)h->n_cigar_words},
       {(void**)&d->seq2, h->seq2, sizeof(uint32_t) * (size_t)h->n_blocks},
       {(void**)&d->qual, h->qual, (size_t)h->n_blocks * MB_BLOCK}};
+  int slot = 8;
   for (auto& p : parts) {
     // +256 B of zero slack so vectorised tail loads never leave the allocation
-    cudaError_t e = cudaMalloc(p.dst, p.bytes + 256);
-    if (e != cudaSuccess) {
-      mb_reads_free(c, d);
-      return mb::fail(MB_ENOMEM, "mb_reads_upload: cudaMalloc(%zu) failed: %s", p.bytes, cudaGetErrorString(e));
+    if (staged) {
+      int rc = ctx_reserve(c, slot++, p.bytes + 256, p.dst);
+      if (rc) return rc;
+    } else {
+      cudaError_t e = cudaMalloc(p.dst, p.bytes + 256);
+      if (e != cudaSuccess)
+        return mb::fail(MB_ENOMEM, "mb_reads_upload: cudaMalloc(%zu) failed: %s", p.bytes, cudaGetErrorString(e));
     }
-    cudaMemsetAsync((char*)*p.dst + p.bytes, 0, 256, c->stream);
-    if (p.bytes) {
-      e = cudaMemcpyAsync(*p.dst, p.src, p.bytes, cudaMemcpyHostToDevice, c->stream);
-      if (e != cudaSuccess) {
-        mb_reads_free(c, d);
-        return mb::fail(MB_ECUDA, "mb_reads_upload: H2D copy failed: %s", cudaGetErrorString(e));
-      }
-    }
+    MB_CUDA_TRY(cudaMemsetAsync((char*)*p.dst + p.bytes, 0, 256, c->stream));
+    if (p.bytes) MB_CUDA_TRY(cudaMemcpyAsync(*p.dst, p.src, p.bytes, cudaMemcpyHostToDevice, c->stream));
     d->bytes += p.bytes;
   }
+  return MB_OK;
+}
+}  // namespace mb
+
+extern "C" int mb_reads_upload(mb_ctx* c, const mb_packed_reads* h, mb_dev_reads** out) {
+  if (!c || !h || !out) return mb::fail(MB_EINVAL, "mb_reads_upload: null argument");
+  MB_CUDA_TRY(cudaSetDevice(c->device));
+  mb_dev_reads* d = new mb_dev_reads();
+  int rc = mb::upload_reads(c, h, d, false);
+  if (rc) { mb_reads_free(c, d); return rc; }
   *out = d;
   return MB_OK;
 }

@@ -122,15 +122,14 @@ extern "C" int mb_genes_coverage_dev(mb_ctx* ctx, const mb_dev_reads* reads, con
   p.aln_cov = f->aln_cov;
   p.readq = f->readq;
   p.mapq = f->mapq;
-  MB_CUDA_TRY(cudaEventRecord(ctx->ev0, st));
+  { int trc = mb::timing_begin(ctx); if (trc) return trc; }
   if (reads->n_reads) {
     uint64_t want = (reads->n_reads + GENE_THREADS - 1) / GENE_THREADS;
     uint32_t grid = (uint32_t)std::min<uint64_t>(want, (uint64_t)ctx->sm_count * 8);
     k_genes_v1<<<grid, GENE_THREADS, 0, st>>>(p);
     ctx->launches++;
   }
-  MB_CUDA_TRY(cudaEventRecord(ctx->ev1, st));
-  ctx->ev_valid = true;
+  { int trc = mb::timing_end(ctx); if (trc) return trc; }
   if (n_genes) {
     k_genes_finalize<<<(n_genes + 255) / 256, 256, 0, st>>>(p.out, gene_len_dev, n_genes);
     ctx->launches++;
@@ -143,8 +142,10 @@ extern "C" int mb_genes_coverage(mb_ctx* ctx, const mb_packed_reads* reads, cons
                                  uint32_t n_genes, const mb_filters* f, int exact_order, mb_gene_out* out_host) {
   if (!ctx || !reads || !gene_len_host || !f || !out_host)
     return mb::fail(MB_EINVAL, "mb_genes_coverage: null argument");
-  mb_dev_reads* d = nullptr;
-  int rc = mb_reads_upload(ctx, reads, &d);
+  MB_CUDA_TRY(cudaSetDevice(ctx->device));
+  mb_dev_reads dr;
+  mb_dev_reads* d = &dr;
+  int rc = mb::upload_reads(ctx, reads, d, /*staged=*/true);
   if (rc) return rc;
   void *gl = nullptr, *out = nullptr;
   rc = mb::ctx_reserve(ctx, 2, sizeof(uint32_t) * (size_t)n_genes, &gl);
@@ -162,6 +163,5 @@ extern "C" int mb_genes_coverage(mb_ctx* ctx, const mb_packed_reads* reads, cons
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) rc = mb::fail(MB_ECUDA, "mb_genes_coverage: %s", cudaGetErrorString(e));
   }
-  mb_reads_free(ctx, d);
   return rc;
 }

@@ -304,10 +304,9 @@ extern "C" int mb_snps_pileup_dev(mb_ctx* ctx, const mb_dev_reads* reads, const 
   p.mapq = f->mapq;
   p.qthr = 0x80u + (uint32_t)f->baseq;
   const uint32_t grid = min(n_tiles, (uint32_t)ctx->sm_count * 2u);
-  MB_CUDA_TRY(cudaEventRecord(ctx->ev0, st));
+  { int trc = mb::timing_begin(ctx); if (trc) return trc; }
   k_pileup_v1<<<grid, PILE_THREADS, kPileSmem, st>>>(p);
-  MB_CUDA_TRY(cudaEventRecord(ctx->ev1, st));
-  ctx->ev_valid = true;
+  { int trc = mb::timing_end(ctx); if (trc) return trc; }
   ctx->launches++;
   MB_CUDA_TRY(cudaGetLastError());
   return MB_OK;
@@ -317,8 +316,10 @@ extern "C" int mb_snps_pileup(mb_ctx* ctx, const mb_packed_reads* reads, const m
                               uint32_t* counts_host, mb_species_stats* stats_host) {
   if (!ctx || !reads || !L || !f || !counts_host || !stats_host)
     return mb::fail(MB_EINVAL, "mb_snps_pileup: null argument");
-  mb_dev_reads* d = nullptr;
-  int rc = mb_reads_upload(ctx, reads, &d);
+  MB_CUDA_TRY(cudaSetDevice(ctx->device));
+  mb_dev_reads dr;
+  mb_dev_reads* d = &dr;
+  int rc = mb::upload_reads(ctx, reads, d, /*staged=*/true);
   if (rc) return rc;
   void *counts = nullptr, *stats = nullptr;
   const size_t cbytes = sizeof(uint32_t) * 4 * (size_t)L->gpad, sbytes = sizeof(mb_species_stats) * (size_t)L->n_species;
@@ -331,6 +332,5 @@ extern "C" int mb_snps_pileup(mb_ctx* ctx, const mb_packed_reads* reads, const m
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) rc = mb::fail(MB_ECUDA, "mb_snps_pileup: %s", cudaGetErrorString(e));
   }
-  mb_reads_free(ctx, d);
   return rc;
 }

@@ -61,7 +61,7 @@ EXPORTS = [
     "mb_layout_species_goff", "mb_layout_species_len",
     "mb_pack_reads", "mb_packed_free",
     "mb_ctx_create", "mb_ctx_destroy", "mb_ctx_set_stream", "mb_ctx_sync", "mb_ctx_device",
-    "mb_ctx_launch_count", "mb_ctx_last_kernel_ms",
+    "mb_ctx_launch_count", "mb_ctx_last_kernel_ms", "mb_ctx_timing_reset", "mb_ctx_timing_read",
     "mb_reads_upload", "mb_reads_free", "mb_reads_bytes",
     "mb_snps_pileup_dev", "mb_snps_pileup", "mb_genes_coverage_dev", "mb_genes_coverage",
 ]
@@ -103,6 +103,8 @@ def load():
     L.mb_ctx_launch_count.argtypes = [C.c_void_p]
     L.mb_ctx_launch_count.restype = C.c_uint64
     L.mb_ctx_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+    L.mb_ctx_timing_reset.argtypes = [C.c_void_p]
+    L.mb_ctx_timing_read.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
     L.mb_reads_upload.argtypes = [C.c_void_p, C.POINTER(CPackedReads), C.POINTER(C.c_void_p)]
     L.mb_reads_free.argtypes = [C.c_void_p, C.c_void_p]
     L.mb_reads_free.restype = None
@@ -257,7 +259,9 @@ class Context:
         self.device = int(device)
         if use_torch_stream:
             import torch
-            self.set_stream(torch.cuda.current_stream(device).cuda_stream)
+            # torch's default stream has handle 0, which this ABI reads as "context-owned stream":
+            # name it explicitly as cudaStreamLegacy (0x1) so torch events bracket our kernels
+            self.set_stream(torch.cuda.current_stream(device).cuda_stream or 1)
 
     def close(self):
         h, self._h = getattr(self, "_h", None), None
@@ -280,6 +284,15 @@ class Context:
         ms = C.c_float()
         _check(load().mb_ctx_last_kernel_ms(self._h, C.byref(ms)))
         return float(ms.value)
+
+    def timing_reset(self):
+        _check(load().mb_ctx_timing_reset(self._h))
+
+    def timing_read(self):
+        """(total_ms, n_calls) of the dominant kernel since timing_reset(); synchronises."""
+        ms, n = C.c_double(), C.c_uint64()
+        _check(load().mb_ctx_timing_read(self._h, C.byref(ms), C.byref(n)))
+        return float(ms.value), int(n.value)
 
     def upload(self, packed: PackedReads) -> DevReads:
         return DevReads(self, packed)

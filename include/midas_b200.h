@@ -53,7 +53,8 @@ typedef enum {
 const char* mb_version(void);
 const char* mb_last_error(void);
 
-/* positions per genome tile owned by one CTA; species regions are padded to it */
+/* species regions of the padded coordinate space start on multiples of MB_TILE positions
+ * (a multiple of the kernel's tile, so no tile ever holds two species) */
 #define MB_TILE 4096u
 /* bases per packed block (16 qualities = one 128-bit load, 16 x 2-bit = one u32) */
 #define MB_BLOCK 16u
@@ -125,6 +126,11 @@ typedef struct {
 
 #define MB_RF_SIMPLE 0x01u /* one aligned segment [q_start, q_start+ref_span) -> [loc, loc+ref_span): no CIGAR walk */
 #define MB_RF_NMSAT 0x02u  /* NM exceeded 65535 and was saturated */
+#define MB_RF_LONG 0x04u   /* snps: the read does not fit a row of `row_words` 32-position words
+                              (reference span or query length too long); it is listed in long_idx[]
+                              and counted by the long-read kernel instead of the tile kernel */
+/* widest bit-plane row the tile kernel stages (32-position words per read) */
+#define MB_ROW_WORDS_MAX 16u
 
 /* Struct of arrays, identical on host and in HBM (upload is a plain copy).
  *   blk_off[i]..blk_off[i+1]  MB_BLOCK-base blocks of read i (ceil(l_qseq/16))
@@ -143,6 +149,11 @@ typedef struct {
   uint64_t total_bases;      /* sum of l_qseq (the Gbases numerator) */
   uint32_t max_ref_span;
   uint32_t sorted;           /* 1: hdr[].loc ascending (required by the snps path) */
+  uint32_t row_words;        /* snps: 32-position words per staged read row, chosen by the packer so
+                                that at most 0.1 % of the reads need more (those carry MB_RF_LONG);
+                                2..MB_ROW_WORDS_MAX; 0 in genes mode */
+  uint32_t n_long;           /* number of MB_RF_LONG reads */
+  const uint32_t* long_idx;  /* [n_long] ascending indices of the MB_RF_LONG reads */
   const mb_read_hdr* hdr;    /* [n_reads] */
   const uint32_t* blk_off;   /* [n_reads+1] */
   const uint32_t* cplx;      /* [n_reads] */

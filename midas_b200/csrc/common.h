@@ -43,12 +43,13 @@ struct mb_layout {
 struct mb_packed_owner {  // allocation record behind a library-owned mb_packed_reads
   mb_packed_reads pub;
   bool pinned;
-  void* buf[6];
+  void* buf[7];
 };
 
 struct mb_dev_reads {
   uint64_t n_reads, n_blocks, n_cigar_words, total_bases;
-  uint32_t max_ref_span, sorted;
+  uint32_t max_ref_span, sorted, row_words, n_long;
+  uint32_t* long_idx;
   mb_read_hdr* hdr;
   uint32_t* blk_off;
   uint32_t* cplx;
@@ -75,7 +76,8 @@ struct mb_ctx {
   double ring_acc_ms;     // elapsed time of pairs already folded out of the ring
   uint64_t ring_acc_n;
   uint64_t launches;
-  bool pile_attr_set;
+  size_t pile_smem;   // dynamic shared memory per CTA of the pileup kernel (0 = not configured yet)
+  int pile_occ;       // resident CTAs per SM at that size
   // scratch (grown on demand)
   uint32_t* tile_rng;  // [2*n_tiles]
   size_t tile_rng_cap;

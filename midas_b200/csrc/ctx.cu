@@ -87,7 +87,8 @@ extern "C" int mb_ctx_create(int device, mb_ctx** out) {
   c->ring_acc_ms = 0.0;
   c->ring_acc_n = 0;
   c->launches = 0;
-  c->pile_attr_set = false;
+  c->pile_smem = 0;
+  c->pile_occ = 1;
   c->tile_rng = nullptr;
   c->tile_rng_cap = 0;
   c->sched = nullptr;
@@ -188,7 +189,10 @@ int upload_reads(mb_ctx* c, const mb_packed_reads* h, mb_dev_reads* d, bool stag
   d->total_bases = h->total_bases;
   d->max_ref_span = h->max_ref_span;
   d->sorted = h->sorted;
-  struct Part { void** dst; const void* src; size_t bytes; } parts[6] = {
+  d->row_words = h->row_words;
+  d->n_long = h->n_long;
+  struct Part { void** dst; const void* src; size_t bytes; } parts[7] = {
+      {(void**)&d->long_idx, h->long_idx, sizeof(uint32_t) * (size_t)h->n_long},
       {(void**)&d->hdr, h->hdr, sizeof(mb_read_hdr) * (size_t)h->n_reads},
       {(void**)&d->blk_off, h->blk_off, sizeof(uint32_t) * (size_t)(h->n_reads + 1)},
       {(void**)&d->cplx, h->cplx, sizeof(uint32_t) * (size_t)h->n_reads},
@@ -233,6 +237,7 @@ extern "C" void mb_reads_free(mb_ctx* c, mb_dev_reads* d) {
   cudaFree(d->cigar);
   cudaFree(d->seq2);
   cudaFree(d->qual);
+  cudaFree(d->long_idx);
   delete d;
 }
 

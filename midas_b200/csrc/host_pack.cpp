@@ -118,6 +118,7 @@ struct ReadGeom {
   uint8_t flags;
   uint32_t n_blk;
   uint32_t n_cplx_words;  // 0 for simple reads, else 1 + n_ops_after_clip
+  uint8_t need_words;     // snps: 32-position words a staged row of this read needs (saturated at 255)
 };
 
 // Analyse one record. Returns MB_OK or an error (message set).
@@ -181,6 +182,7 @@ int analyse(const mb_plain_reads* in, const mb_layout* L, int mode, uint64_t i, 
     g->loc = (uint32_t)rid;
     g->q_start = (uint16_t)lead;
     g->ref_span = 0;
+    g->need_words = 0;
     g->flags |= MB_RF_SIMPLE;
     return MB_OK;
   }
@@ -198,6 +200,11 @@ int analyse(const mb_plain_reads* in, const mb_layout* L, int mode, uint64_t i, 
     return mb::fail(MB_EOVERFLOW, "read %llu: reference span %lld exceeds 65535", (unsigned long long)i,
                     (long long)span_clipped);
   g->ref_span = (uint16_t)span_clipped;
+  {  // row words: the aligned span placed at bit (loc & 31), and one lane per 32 query bases
+    const int64_t by_span = (((int64_t)(g->loc & 31u)) + span_clipped + 31) / 32;
+    const int64_t by_query = (lq + 31) / 32;
+    g->need_words = (uint8_t)std::min<int64_t>(255, std::max(by_span, by_query));
+  }
   if (simple) {
     // query index of the first aligned base = all S before the single M-like op
     int64_t qs = 0;
@@ -326,12 +333,31 @@ extern "C" int mb_pack_reads(const mb_plain_reads* in, const mb_layout* L, int m
   blk_off[n] = (uint32_t)nb;
   cg_off[n] = (uint32_t)ncw;
 
+  // row width of the tile kernel: the smallest W that all but 0.1 % of the reads fit
+  uint32_t row_words = 0;
+  uint64_t n_long = 0;
+  if (mode == 0) {
+    uint64_t hist[256] = {0};
+    for (uint64_t i = 0; i < n; ++i) hist[geom[i].need_words]++;
+    uint64_t above = 0;
+    for (int w = 255; w > (int)MB_ROW_WORDS_MAX; --w) above += hist[w];
+    row_words = MB_ROW_WORDS_MAX;
+    for (uint32_t w = MB_ROW_WORDS_MAX; w > 2; --w) {  // try shrinking to w-1
+      if (above + hist[w] > n / 1000) break;
+      above += hist[w];
+      row_words = w - 1;
+    }
+    for (uint64_t i = 0; i < n; ++i)
+      if (geom[i].need_words > row_words) { geom[i].flags |= MB_RF_LONG; ++n_long; }
+  }
+
   mb_packed_owner* o = new mb_packed_owner();
   memset(o, 0, sizeof(*o));
   o->pinned = pinned != 0;
-  size_t sizes[6] = {sizeof(mb_read_hdr) * (size_t)n, sizeof(uint32_t) * (size_t)(n + 1), sizeof(uint32_t) * (size_t)n,
-                     sizeof(uint32_t) * (size_t)ncw, sizeof(uint32_t) * (size_t)nb, (size_t)nb * MB_BLOCK};
-  for (int k = 0; k < 6; ++k) {
+  size_t sizes[7] = {sizeof(mb_read_hdr) * (size_t)n, sizeof(uint32_t) * (size_t)(n + 1), sizeof(uint32_t) * (size_t)n,
+                     sizeof(uint32_t) * (size_t)ncw, sizeof(uint32_t) * (size_t)nb, (size_t)nb * MB_BLOCK,
+                     sizeof(uint32_t) * (size_t)n_long};
+  for (int k = 0; k < 7; ++k) {
     o->buf[k] = alloc_host(sizes[k], o->pinned);
     if (!o->buf[k] && o->pinned) {  // no device / pin failure: fall back to pageable memory
       for (int q = 0; q < k; ++q) { cudaFreeHost(o->buf[q]); o->buf[q] = nullptr; }
@@ -347,7 +373,13 @@ extern "C" int mb_pack_reads(const mb_plain_reads* in, const mb_layout* L, int m
   uint32_t* cigar = (uint32_t*)o->buf[3];
   uint32_t* seq2 = (uint32_t*)o->buf[4];
   uint8_t* qual = (uint8_t*)o->buf[5];
+  uint32_t* long_idx = (uint32_t*)o->buf[6];
   memcpy(blk, blk_off.data(), sizeof(uint32_t) * (n + 1));
+  if (n_long) {
+    uint64_t k = 0;
+    for (uint64_t j = 0; j < n; ++j)
+      if (geom[src(j)].flags & MB_RF_LONG) long_idx[k++] = (uint32_t)j;
+  }
 
   std::vector<int> rc2(n_threads + 1, MB_OK);
   parallel_for(n, n_threads, [&](uint64_t lo, uint64_t hi, int t) {
@@ -410,6 +442,9 @@ extern "C" int mb_pack_reads(const mb_plain_reads* in, const mb_layout* L, int m
   o->pub.total_bases = tot_bases;
   o->pub.max_ref_span = max_span;
   o->pub.sorted = (mode == 0) ? 1u : 0u;
+  o->pub.row_words = row_words;
+  o->pub.n_long = (uint32_t)n_long;
+  o->pub.long_idx = long_idx;
   o->pub.hdr = hdr;
   o->pub.blk_off = blk;
   o->pub.cplx = cplx;

@@ -4,25 +4,56 @@
 //   midas/run/snps.py:141-162  keep_read        -> header filters + mean-quality test, fused
 //   midas/run/snps.py:194-199  count_coverage   -> CIGAR walk + per-base quality test + count
 //   midas/run/snps.py:201-213  per-position loop -> depth / covered_bases / total_depth, fused
-//                                                  into the tile flush (no second pass)
+//                                                  into the tile write-out (no second pass)
 //
-// Data-parallel decomposition: the padded genome is cut into MB_TILE-position tiles. Reads are
-// sorted by global coordinate, so the reads overlapping a tile are one contiguous index range.
-// A CTA owns a tile: it accumulates the tile's four count planes in shared memory (ATOMS),
-// then writes them to HBM with plain coalesced 128-bit stores. No global atomics on counters,
-// no pre-zeroing of the output, every output element written exactly once. Reads that straddle
-// a tile boundary are visited by both tiles, each counting only its own positions; the tile
-// containing the read's start "owns" it for aligned_reads/mapped_reads.
+// The count is integer and HBM-bound (about 1.4 B per base in, 16 B per position out), so the
+// design removes every per-base atomic and every per-base scalar operation that it can:
+//
+//   * the padded genome is cut into KT-position tiles; reads are sorted by coordinate, so the reads
+//     overlapping a tile are one contiguous index range (k_tile_ranges) and a CTA owns a tile;
+//   * STAGE: groups of W lanes turn one read each into a *bit-plane row in reference coordinates*:
+//     lane j converts 32 qualities into a 32-bit "countable" mask (byte-SIMD compare + multiply
+//     gather, no per-base branch), takes the two 2-bit sequence planes as they lie in HBM, and the
+//     CIGAR is applied once per 32-base word with warp shuffles + funnel shifts. The row is stored
+//     in shared memory as W x {A,C,G,T} 32-bit masks aligned to the global 32-position grid;
+//   * COUNT: a lane owns a 32-position column and adds the rows covering it with carry-save adders
+//     into bit-sliced ("vertical") counters held in registers: one LOP3 works on 32 positions at
+//     once, ~0.6 instructions per aligned base instead of one shared-memory atomic per base;
+//     KSUB lanes share a column (rows strided) and are merged by a shuffle butterfly of bit-sliced
+//     adders into shared-memory vertical counters;
+//   * EXPAND: the vertical counters are transposed to u32 counts (4 positions per thread, multiply
+//     spread), depth / covered_bases / total_depth are reduced on the way, and the four planes are
+//     written with coalesced 128-bit stores. Every output element is written exactly once, no
+//     pre-zeroing, no global atomics on counters.
+//
+// Reads that straddle a tile boundary are staged by both tiles (each counts only its own columns);
+// the tile containing a read's start owns it for aligned_reads / mapped_reads. Reads that do not
+// fit a W-word row (MB_RF_LONG, at most 0.1 % by construction of W) are counted by k_long_reads
+// with global atomics and the position stats are then recomputed by k_restat.
 #include <cstdio>
+#include <cstdlib>
 
 #include "common.h"
 
 namespace {
 
-constexpr uint32_t TILE = MB_TILE;
-constexpr int PILE_THREADS = 512;
-constexpr int PILE_WARPS = PILE_THREADS / 32;
-constexpr int CHUNK = 1024;  // reads whose header filters are evaluated per phase
+constexpr int KT = 2048;                 // positions per kernel tile (divides MB_TILE)
+constexpr int NCOL = KT / 32;            // 32-position columns per tile
+constexpr int KSUB = 4;                  // lanes sharing a column
+constexpr int NT = NCOL * KSUB;          // threads per CTA
+constexpr int NWARP = NT / 32;
+constexpr int NLEV = 9;                  // register vertical-counter levels (per-lane count <= 511)
+constexpr int XLEV = NLEV + 2;           // levels after merging KSUB = 4 lanes
+constexpr int VCL = 16;                  // shared-memory vertical-counter levels (<= 65535 rows per pass)
+constexpr int WMAX = MB_ROW_WORDS_MAX;
+constexpr uint32_t PASS_ROWS = 65528;    // rows folded into the shared counters before they are expanded
+constexpr int LANE_ROWS_MAX = 248;       // rows one lane may take in one round (keeps its count <= 511)
+constexpr int FIRST_N = NCOL + WMAX + 1;
+
+static_assert(MB_TILE % KT == 0, "kernel tile must divide the layout tile");
+static_assert(KSUB == 4, "the merge butterfly is written for 4 lanes per column");
+
+enum : uint32_t { F_NEEDQ = 1u, F_OVL = 2u, F_OWNER = 4u, F_SIMPLE = 8u };
 
 struct PileParams {
   const uint4* hdr;
@@ -30,28 +61,63 @@ struct PileParams {
   const uint32_t* cplx;
   const uint32_t* cigar;
   const uint32_t* seq2;
-  const uint8_t* qual;
-  const uint32_t* tile_rng;
-  const int32_t* tile_species;
+  const uint4* qual;          // 16 qualities per element
+  const uint32_t* tile_rng;   // [2 * n_ktiles]
+  const int32_t* tile_species;  // per MB_TILE tile
   uint32_t* counts;
   unsigned long long* stats;
   uint32_t* sched;
   uint64_t gpad;
-  uint32_t n_tiles;
+  uint32_t n_ktiles;
+  uint32_t W;                 // row words
+  uint32_t G;                 // reads per warp iteration = 32 / W
+  uint32_t rmax;              // rows staged per round
   double mapid, aln_cov;
   int readq, mapq;
-  uint32_t qthr;  // 0x80 + baseq: byte >= qthr <=> literal ACGT and Phred >= baseq
+  uint32_t qadd;              // (0x80 - baseq) * 0x01010101
+  uint32_t defer_restat;      // 1: long reads follow, position stats are recomputed afterwards
 };
-
-// Shared-memory index of tile-relative position x inside a plane. Within each block of 128
-// positions the 4x32 matrix is transposed, so that lanes holding positions x0+4*lane+k (k fixed)
-// hit 32 distinct banks.
-__device__ __forceinline__ uint32_t swz(uint32_t x) { return (x & ~127u) | ((x & 3u) << 5) | ((x >> 2) & 31u); }
 
 __device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
+}
+
+// carry-save adder on 32 bit-sliced positions: (sum, carry) of three one-bit addends
+#define CSA(s, c, a, b, d)                          \
+  do {                                              \
+    const uint32_t _a = (a), _b = (b), _d = (d);    \
+    (s) = _a ^ _b ^ _d;                             \
+    (c) = (_a & _b) | ((_a ^ _b) & _d);             \
+  } while (0)
+
+// 16 quality bytes (bit 7 = literal A/C/G/T, bits 0-6 = Phred) -> 2 bytes whose low bytes are the
+// 8 + 8 "countable" bits (Phred >= baseq and A/C/G/T); the Phred sum is accumulated into qsum.
+// Per 4 bases: mask, dot-product-accumulate, add, and, multiply-high (bit gather).
+__device__ __forceinline__ void conv16(const uint4 q, const uint32_t qadd, uint32_t& qsum, uint32_t& b01,
+                                       uint32_t& b23) {
+  constexpr uint32_t MUL0 = (1u << 25) | (1u << 18) | (1u << 11) | (1u << 4);  // bits 7,15,23,31 -> 32..35
+  constexpr uint32_t MUL4 = MUL0 << 4;                                         //                 -> 36..39
+  const uint32_t m0 = q.x & 0x7f7f7f7fu, m1 = q.y & 0x7f7f7f7fu, m2 = q.z & 0x7f7f7f7fu, m3 = q.w & 0x7f7f7f7fu;
+  qsum = __dp4a(m0, 0x01010101u, qsum);
+  qsum = __dp4a(m1, 0x01010101u, qsum);
+  qsum = __dp4a(m2, 0x01010101u, qsum);
+  qsum = __dp4a(m3, 0x01010101u, qsum);
+  const uint32_t t0 = (m0 + qadd) & q.x & 0x80808080u;
+  const uint32_t t1 = (m1 + qadd) & q.y & 0x80808080u;
+  const uint32_t t2 = (m2 + qadd) & q.z & 0x80808080u;
+  const uint32_t t3 = (m3 + qadd) & q.w & 0x80808080u;
+  const uint32_t n0 = __umulhi(t0, MUL0), n1 = __umulhi(t1, MUL4);
+  const uint32_t n2 = __umulhi(t2, MUL0), n3 = __umulhi(t3, MUL4);
+  b01 = (n0 & 0x0fu) | (n1 & ~0x0fu);  // low byte: bases 0-7 (higher bytes hold gather by-products)
+  b23 = (n2 & 0x0fu) | (n3 & ~0x0fu);  // low byte: bases 8-15
+}
+
+__device__ __forceinline__ uint32_t bit_range_mask(int lo, int hi) {  // bits [lo, hi) of a word, 0 <= lo < hi <= 32
+  const uint32_t up = 0xffffffffu << lo;
+  const uint32_t dn = 0xffffffffu >> (32 - hi);
+  return up & dn;
 }
 
 __global__ void k_init_stats(unsigned long long* stats, const uint64_t* species_len, uint32_t n_species,
@@ -67,14 +133,14 @@ __global__ void k_init_stats(unsigned long long* stats, const uint64_t* species_
   }
 }
 
-// For every tile the contiguous range of reads that can overlap it. Conservative lower end
-// (tile_start - max_ref_span); the pileup kernel skips non-overlapping reads by header.
-__global__ void k_tile_ranges(const uint4* __restrict__ hdr, uint32_t n_reads, uint32_t max_span, uint32_t n_tiles,
+// For every kernel tile the contiguous range of reads that can overlap it: a read that fits a W-word
+// row and overlaps [ts, ts+KT) starts after ts - 32 W; the pileup kernel skips the rest by header.
+__global__ void k_tile_ranges(const uint4* __restrict__ hdr, uint32_t n_reads, uint32_t back, uint32_t n_tiles,
                               uint32_t* __restrict__ rng) {
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_tiles) return;
-  const uint32_t ts = t * TILE, te = ts + TILE;
-  const uint32_t lo_key = ts > max_span ? ts - max_span : 0u;
+  const uint32_t ts = t * KT, te = ts + KT;
+  const uint32_t lo_key = ts > back ? ts - back : 0u;
   uint32_t lo = 0, hi = n_reads;
   while (lo < hi) {
     uint32_t mid = lo + ((hi - lo) >> 1);
@@ -90,149 +156,318 @@ __global__ void k_tile_ranges(const uint4* __restrict__ hdr, uint32_t n_reads, u
   rng[2 * t + 1] = lo;
 }
 
-__global__ void __launch_bounds__(PILE_THREADS, 2) k_pileup_v1(const PileParams p) {
+__global__ void __launch_bounds__(NT, 2) k_pileup_v2(const PileParams p) {
   extern __shared__ __align__(16) uint32_t smem[];
-  uint32_t* hist = smem;                                         // [4][TILE]
-  uint32_t* s_blk = hist + 4 * TILE;                             // [CHUNK]
-  uint8_t* s_hk = reinterpret_cast<uint8_t*>(s_blk + CHUNK);     // [CHUNK]
-  __shared__ unsigned long long s_red[4];                        // covered, depth, aligned, mapped
-  __shared__ uint32_t s_tile;
+  const uint32_t W = p.W;
+  uint4* s_vc = reinterpret_cast<uint4*>(smem);                       // [VCL][NCOL] x {A,C,G,T}
+  uint4* s_meta = s_vc + VCL * NCOL;                                  // [rmax]
+  uint4* s_rows = s_meta + p.rmax;                                    // [rmax][W] x {A,C,G,T}
+  __shared__ uint32_t s_first[FIRST_N];
+  __shared__ unsigned long long s_red[4];                             // covered, depth, aligned, mapped
+  __shared__ uint32_t s_tile, s_nmax;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int col = tid >> 2, ksub = tid & 3;                           // COUNT role
+  const int grp = lane / (int)W, gj = lane - grp * (int)W;            // STAGE role
+  const int gbase = grp * (int)W;
+  const bool lane_ok = grp < (int)p.G;
+  const uint32_t reduce_steps = W > 8 ? 4 : (W > 4 ? 3 : (W > 2 ? 2 : 1));
+
+  for (int i = tid; i < VCL * NCOL; i += NT) s_vc[i] = make_uint4(0, 0, 0, 0);
 
   for (;;) {
     __syncthreads();
-    if (tid == 0) s_tile = atomicAdd(p.sched, 1u);
+    if (tid == 0) { s_tile = atomicAdd(p.sched, 1u); s_nmax = 0; }
+    if (tid < 4) s_red[tid] = 0;
     __syncthreads();
     const uint32_t tile = s_tile;
-    if (tile >= p.n_tiles) break;
-    const uint32_t ts = tile * TILE;
+    if (tile >= p.n_ktiles) break;
+    const uint32_t ts = tile * KT;
     const uint32_t r0 = p.tile_rng[2 * tile], r1 = p.tile_rng[2 * tile + 1];
+    const uint32_t slot_c = ((ts >> 5) + (uint32_t)col) % W;          // where my column's word sits in a row
 
-    for (int i = tid; i < (int)TILE; i += PILE_THREADS) reinterpret_cast<uint4*>(hist)[i] = make_uint4(0, 0, 0, 0);
-    if (tid < 4) s_red[tid] = 0;
-    uint32_t my_aligned = 0, my_mapped = 0;
-
-    for (uint32_t c0 = r0; c0 < r1; c0 += CHUNK) {
-      const int n = (int)min((uint32_t)CHUNK, r1 - c0);
-      __syncthreads();
-      // ---- phase 0: header-only filters, one thread per read (snps.py:148,154,157)
-      for (int i = tid; i < n; i += PILE_THREADS) {
-        const uint4 h = __ldg(&p.hdr[c0 + i]);
-        const uint32_t loc = h.x, lq = h.y & 0xffffu, alen = h.y >> 16, nm = h.z >> 16;
-        const uint32_t span = h.w & 0xffffu, mq = (h.w >> 16) & 0xffu, fl = h.w >> 24;
-        uint32_t code;
-        if (loc < ts && loc + span <= ts) {
-          code = 2;  // neither owned by nor overlapping this tile
-        } else {
-          double pid = __ddiv_rn((double)(100 * ((int)alen - (int)nm)), (double)alen);
-          if (fl & MB_RF_NMSAT) pid = -__longlong_as_double(0x7ff0000000000000ll);
-          bool ok = !(pid < p.mapid);
-          ok = ok && !((int)mq < p.mapq);
-          ok = ok && !(__ddiv_rn((double)alen, (double)lq) < p.aln_cov);
-          code = ok ? 1u : 0u;
-        }
-        s_hk[i] = (uint8_t)code;
-        s_blk[i] = __ldg(&p.blk_off[c0 + i]);
-      }
-      __syncthreads();
-      // ---- phase 1: one warp per read
-      for (int i = warp; i < n; i += PILE_WARPS) {
-        const uint32_t code = s_hk[i];
-        if (code & 2u) continue;
-        const uint4 h = __ldg(&p.hdr[c0 + i]);
-        const uint32_t loc = h.x, lq = h.y & 0xffffu, qstart = h.z & 0xffffu;
-        const uint32_t span = h.w & 0xffffu, fl = h.w >> 24;
-        const uint32_t blk0 = s_blk[i];
-        const uint32_t nwords = ((lq + 15u) >> 4) << 2;
-        const uint32_t* __restrict__ qw = reinterpret_cast<const uint32_t*>(p.qual) + (size_t)blk0 * 4;
-        const bool owner = loc >= ts;
-        if (!(code & 1u)) {  // failed a header filter: the qualities are never needed
-          if (lane == 0 && owner) ++my_aligned;
-          continue;
-        }
-        // mean-quality filter (snps.py:151): mean(q) < readq  <=>  sum(q) < readq * l_qseq (exact)
-        uint32_t w0 = (uint32_t)lane < nwords ? __ldg(qw + lane) : 0u;
-        uint32_t w1 = (uint32_t)lane + 32u < nwords ? __ldg(qw + lane + 32) : 0u;
-        uint32_t s = __vsadu4(w0 & 0x7f7f7f7fu, 0u) + __vsadu4(w1 & 0x7f7f7f7fu, 0u);
-        for (uint32_t j = lane + 64; j < nwords; j += 32) s += __vsadu4(__ldg(qw + j) & 0x7f7f7f7fu, 0u);
-        s = warp_sum(s);
-        const bool keep = (long long)s >= (long long)p.readq * (long long)lq;
-        if (lane == 0 && owner) { ++my_aligned; my_mapped += keep ? 1u : 0u; }
-        if (!keep) continue;
-        const int x0 = (int)(loc - ts);  // tile-relative position of the first aligned base (may be < 0)
-        if (fl & MB_RF_SIMPLE) {
-          for (uint32_t j = lane; j < nwords; j += 32) {
-            const uint32_t w = j < 32 ? w0 : (j < 64 ? w1 : __ldg(qw + j));
-            const uint32_t sw = __ldg(p.seq2 + blk0 + (j >> 2));
-            const uint32_t sub = (j & 3u) << 2;
+    uint32_t cnt[4][NLEV];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const int rel = (int)(4 * j + k) - (int)qstart;
-              const int x = x0 + rel;
-              const uint32_t qb = (w >> (8 * k)) & 0xffu;
-              if ((uint32_t)rel < span && (uint32_t)x < TILE && qb >= p.qthr) {
-                const uint32_t bi = sub + k;
-                const uint32_t cd = ((sw >> bi) & 1u) | (((sw >> (16 + bi)) & 1u) << 1);
-                atomicAdd(&hist[cd * TILE + swz((uint32_t)x)], 1u);
-              }
-            }
-          }
-        } else {
-          const uint32_t* __restrict__ rec = p.cigar + __ldg(p.cplx + c0 + i);
-          const uint32_t n_ops = __ldg(rec);
-          int qpos = 0, rpos = x0;
-          for (uint32_t o = 0; o < n_ops; ++o) {
-            const uint32_t cw = __ldg(rec + 1 + o);
-            const uint32_t op = cw & 0xfu;
-            const int len = (int)(cw >> 4);
-            if (op == mb::OP_M || op == mb::OP_EQ || op == mb::OP_X) {
-              for (int q = qpos + lane; q < qpos + len; q += 32) {
-                const int x = rpos + (q - qpos);
-                if ((uint32_t)x < TILE) {
-                  const uint32_t qb = __ldg(p.qual + (size_t)blk0 * 16 + q);
-                  if (qb >= p.qthr) {
-                    const uint32_t sw = __ldg(p.seq2 + blk0 + (q >> 4));
-                    const uint32_t bi = q & 15;
-                    const uint32_t cd = ((sw >> bi) & 1u) | (((sw >> (16 + bi)) & 1u) << 1);
-                    atomicAdd(&hist[cd * TILE + swz((uint32_t)x)], 1u);
-                  }
-                }
-              }
-              qpos += len;
-              rpos += len;
-            } else if (op == mb::OP_I || op == mb::OP_S) {
-              qpos += len;
-            } else if (op == mb::OP_D || op == mb::OP_N) {
-              rpos += len;
-            }
-          }
-        }
-      }
-    }
-    __syncthreads();
-    // ---- flush: smem planes -> HBM (coalesced 128-bit stores) + fused per-position epilogue
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+      for (int l = 0; l < NLEV; ++l) cnt[c][l] = 0;
+    uint32_t n_lane = 0;        // rows (padded to blocks of 8) folded into cnt
+    uint32_t col_rows = 0;      // rows of my column folded since the last expansion
+    uint32_t my_aligned = 0, my_mapped = 0;
     uint32_t covered = 0;
     unsigned long long depth_sum = 0;
-    for (uint32_t x4 = tid * 4; x4 < TILE; x4 += PILE_THREADS * 4) {
-      const uint32_t base = (x4 & ~127u) | ((x4 >> 2) & 31u);
-      uint32_t d[4] = {0, 0, 0, 0};
+
+    // merge the KSUB lanes of each column (shuffle butterfly of bit-sliced adders) and add the
+    // result into the shared vertical counters; lane ksub folds class ksub
+    auto flush = [&]() {
+      uint32_t x[4][XLEV];
 #pragma unroll
-      for (int pl = 0; pl < 4; ++pl) {
-        uint4 v;
-        v.x = hist[pl * TILE + base];
-        v.y = hist[pl * TILE + base + 32];
-        v.z = hist[pl * TILE + base + 64];
-        v.w = hist[pl * TILE + base + 96];
-        d[0] += v.x; d[1] += v.y; d[2] += v.z; d[3] += v.w;
-        *reinterpret_cast<uint4*>(p.counts + (size_t)pl * p.gpad + ts + x4) = v;
+      for (int c = 0; c < 4; ++c) {
+#pragma unroll
+        for (int l = 0; l < NLEV; ++l) x[c][l] = cnt[c][l];
+#pragma unroll
+        for (int step = 0; step < 2; ++step) {
+          uint32_t carry = 0;
+#pragma unroll
+          for (int l = 0; l < NLEV + step; ++l) {
+            const uint32_t y = __shfl_xor_sync(0xffffffffu, x[c][l], 1 << step);
+            CSA(x[c][l], carry, x[c][l], y, carry);
+          }
+          x[c][NLEV + step] = carry;
+        }
+      }
+      uint32_t mine[VCL];
+#pragma unroll
+      for (int l = 0; l < VCL; ++l)
+        mine[l] = l >= XLEV ? 0u : (ksub == 0 ? x[0][l < XLEV ? l : 0] : (ksub == 1 ? x[1][l < XLEV ? l : 0]
+                                   : (ksub == 2 ? x[2][l < XLEV ? l : 0] : x[3][l < XLEV ? l : 0])));
+      uint32_t* vc = reinterpret_cast<uint32_t*>(s_vc) + col * 4 + ksub;
+      uint32_t carry = 0;
+#pragma unroll
+      for (int l = 0; l < VCL; ++l) {
+        if (l >= XLEV && !__any_sync(0xffffffffu, carry != 0)) break;
+        const uint32_t a = vc[l * NCOL * 4];
+        uint32_t sum;
+        CSA(sum, carry, a, mine[l], carry);
+        vc[l * NCOL * 4] = sum;
       }
 #pragma unroll
-      for (int k = 0; k < 4; ++k) { covered += d[k] > 0; depth_sum += d[k]; }  // snps.py:204,212-213
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int l = 0; l < NLEV; ++l) cnt[c][l] = 0;
+      n_lane = 0;
+    };
+
+    // transpose the shared vertical counters to u32 counts and write the tile (or add to it)
+    auto expand = [&](const bool accumulate, const bool last) {
+      __syncthreads();
+      if (ksub == 0 && col_rows) atomicMax(&s_nmax, col_rows);
+      __syncthreads();
+      const int nl = 32 - __clz(s_nmax);
+      const int nlo = nl < 8 ? nl : 8;
+      for (int q = tid; q < KT / 4; q += NT) {
+        const int c4 = q >> 3, sh = (q & 7) * 4;
+        uint32_t lo[4] = {0, 0, 0, 0}, hi[4] = {0, 0, 0, 0};
+        for (int l = 0; l < nlo; ++l) {
+          const uint4 w = s_vc[l * NCOL + c4];
+          lo[0] += ((((w.x >> sh) & 15u) * 0x00204081u) & 0x01010101u) << l;
+          lo[1] += ((((w.y >> sh) & 15u) * 0x00204081u) & 0x01010101u) << l;
+          lo[2] += ((((w.z >> sh) & 15u) * 0x00204081u) & 0x01010101u) << l;
+          lo[3] += ((((w.w >> sh) & 15u) * 0x00204081u) & 0x01010101u) << l;
+        }
+        for (int l = 8; l < nl; ++l) {
+          const uint4 w = s_vc[l * NCOL + c4];
+          hi[0] += ((((w.x >> sh) & 15u) * 0x00204081u) & 0x01010101u) << (l - 8);
+          hi[1] += ((((w.y >> sh) & 15u) * 0x00204081u) & 0x01010101u) << (l - 8);
+          hi[2] += ((((w.z >> sh) & 15u) * 0x00204081u) & 0x01010101u) << (l - 8);
+          hi[3] += ((((w.w >> sh) & 15u) * 0x00204081u) & 0x01010101u) << (l - 8);
+        }
+        uint32_t d[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint4 v;
+          v.x = (lo[c] & 0xffu) | ((hi[c] & 0xffu) << 8);
+          v.y = ((lo[c] >> 8) & 0xffu) | (((hi[c] >> 8) & 0xffu) << 8);
+          v.z = ((lo[c] >> 16) & 0xffu) | (((hi[c] >> 16) & 0xffu) << 8);
+          v.w = (lo[c] >> 24) | ((hi[c] >> 24) << 8);
+          uint4* dst = reinterpret_cast<uint4*>(p.counts + (size_t)c * p.gpad + ts + 4 * q);
+          if (accumulate) {
+            const uint4 o = *dst;
+            v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+          }
+          *dst = v;
+          d[0] += v.x; d[1] += v.y; d[2] += v.z; d[3] += v.w;
+        }
+        if (last) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) { covered += d[k] > 0; depth_sum += d[k]; }  // snps.py:204,212-213
+        }
+      }
+      __syncthreads();
+      for (int i = tid; i < (nl < VCL ? nl + 1 : VCL) * NCOL; i += NT) s_vc[i] = make_uint4(0, 0, 0, 0);
+      if (tid == 0) s_nmax = 0;
+      col_rows = 0;
+    };
+
+    uint32_t pass_rows = 0;
+    bool accumulate = false;
+    for (uint32_t rb = r0; rb < r1; rb += p.rmax) {
+      const int n = (int)min(p.rmax, r1 - rb);
+      if (pass_rows + (uint32_t)n > PASS_ROWS) {  // keep the shared counters below 2^VCL
+        flush();
+        expand(accumulate, false);
+        accumulate = true;
+        pass_rows = 0;
+      }
+      pass_rows += (uint32_t)n;
+      __syncthreads();
+      // ---- META: one thread per read: header filters (snps.py:148,154,157), geometry, row index table
+      for (int i = tid; i < n; i += NT) {
+        const uint32_t r = rb + (uint32_t)i;
+        const uint4 h = __ldg(&p.hdr[r]);
+        const uint32_t b0 = __ldg(&p.blk_off[r]);
+        const uint32_t loc = h.x, lq = h.y & 0xffffu, alen = h.y >> 16, qstart = h.z & 0xffffu, nm = h.z >> 16;
+        const uint32_t span = h.w & 0xffffu, mq = (h.w >> 16) & 0xffu, fl = h.w >> 24;
+        uint32_t flags = 0;
+        if (!(fl & MB_RF_LONG)) {
+          const bool owner = loc >= ts;
+          const bool ovl = span > 0 && loc + span > ts;
+          double pid = __ddiv_rn((double)(100 * ((int)alen - (int)nm)), (double)alen);
+          if (fl & MB_RF_NMSAT) pid = -__longlong_as_double(0x7ff0000000000000ll);
+          bool hk = !(pid < p.mapid);
+          hk = hk && !((int)mq < p.mapq);
+          hk = hk && !(__ddiv_rn((double)alen, (double)lq) < p.aln_cov);
+          if (owner) ++my_aligned;                                       // snps.py:143
+          if (hk && (ovl || owner)) flags |= F_NEEDQ;
+          if (ovl) flags |= F_OVL;
+          if (owner) flags |= F_OWNER;
+          if (fl & MB_RF_SIMPLE) flags |= F_SIMPLE;
+        }
+        const uint32_t gc = loc >> 5;
+        s_meta[i] = make_uint4(loc, b0, lq | (qstart << 16), span | (flags << 16) | ((gc % W) << 24));
+        // s_first[x] = first row of this round whose start column + (W-1) >= x
+        const int kmax = NCOL + (int)W - 1;
+        int xi = (int)gc - (int)(ts >> 5) + (int)W - 1;
+        xi = xi < 0 ? 0 : (xi > kmax ? kmax : xi);
+        int xlo = 0;
+        if (i > 0) {
+          int xp = (int)(__ldg(&p.hdr[r - 1].x) >> 5) - (int)(ts >> 5) + (int)W - 1;
+          xp = xp < 0 ? 0 : (xp > kmax ? kmax : xp);
+          xlo = xp + 1;
+        }
+        for (int x = xlo; x <= xi; ++x) s_first[x] = (uint32_t)i;
+        if (i == n - 1)
+          for (int x = xi + 1; x <= kmax + 1; ++x) s_first[x] = (uint32_t)n;
+      }
+      __syncthreads();
+      // ---- STAGE: W lanes per read build its bit-plane row
+      for (int it = warp; it * (int)p.G < n; it += NWARP) {
+        const int i = it * (int)p.G + grp;
+        const bool rowok = lane_ok && i < n;
+        uint4 m = make_uint4(0, 0, 0, 0);
+        if (rowok) m = s_meta[i];
+        const uint32_t loc = m.x, b0 = m.y, lq = m.z & 0xffffu, qstart = m.z >> 16;
+        const uint32_t span = m.w & 0xffffu, flags = (m.w >> 16) & 0xffu, slot0 = m.w >> 24;
+        const bool needq = (flags & F_NEEDQ) != 0;
+        const uint32_t nblk = (lq + 15u) >> 4;
+        // this lane's 32 query bases = blocks 2j and 2j+1
+        uint4 qa = make_uint4(0, 0, 0, 0), qb = make_uint4(0, 0, 0, 0);
+        uint32_t sa = 0, sb = 0;
+        const uint32_t bi = 2u * (uint32_t)gj;
+        if (needq && bi < nblk) { qa = __ldg(p.qual + b0 + bi); sa = __ldg(p.seq2 + b0 + bi); }
+        if (needq && bi + 1 < nblk) { qb = __ldg(p.qual + b0 + bi + 1); sb = __ldg(p.seq2 + b0 + bi + 1); }
+        uint32_t qsum = 0, a01, a23, c01, c23;
+        conv16(qa, p.qadd, qsum, a01, a23);
+        conv16(qb, p.qadd, qsum, c01, c23);
+        const uint32_t qv = __byte_perm(__byte_perm(a01, a23, 0x0040), __byte_perm(c01, c23, 0x0040), 0x5410);
+        const uint32_t ql = __byte_perm(sa, sb, 0x5410);   // low bits of the 2-bit base codes, 32 bases
+        const uint32_t qh = __byte_perm(sa, sb, 0x7632);   // high bits
+        // mean-quality filter (snps.py:151): mean(q) < readq  <=>  sum(q) < readq * l_qseq (exact)
+        uint32_t tot = qsum;
+        for (uint32_t s = 0, d = 1; s < reduce_steps; ++s, d <<= 1) {
+          const uint32_t t = __shfl_down_sync(0xffffffffu, tot, d);
+          if (gj + (int)d < (int)W) tot += t;
+        }
+        tot = __shfl_sync(0xffffffffu, tot, gbase & 31);
+        const bool keep = needq && ((long long)tot >= (long long)p.readq * (long long)lq);
+        if (gj == 0 && keep && (flags & F_OWNER)) ++my_mapped;               // snps.py:161
+        const bool place = rowok && keep && (flags & F_OVL);
+        // ---- CIGAR: every M/=/X run is one shifted, masked copy of the query planes
+        const bool simple = (flags & F_SIMPLE) != 0;
+        const uint32_t* __restrict__ rec = p.cigar;
+        uint32_t n_ops = 0;
+        if (place) {
+          if (simple) n_ops = 1;
+          else { rec = p.cigar + __ldg(p.cplx + rb + (uint32_t)i); n_ops = __ldg(rec); }
+        }
+        const uint32_t max_ops = __reduce_max_sync(0xffffffffu, n_ops);
+        int qpos = simple ? (int)qstart : 0, xpos = 0;
+        uint32_t rl = 0, rh = 0, rv = 0;
+        for (uint32_t o = 0; o < max_ops; ++o) {
+          uint32_t cw = 0;
+          const bool act = o < n_ops;
+          if (act) cw = simple ? (span << 4) : __ldg(rec + 1 + o);
+          const uint32_t op = cw & 0xfu;
+          const int len = (int)(cw >> 4);
+          const bool mlike = act && (op == mb::OP_M || op == mb::OP_EQ || op == mb::OP_X);
+          if (__any_sync(0xffffffffu, mlike)) {
+            const int p0 = (int)(loc & 31u) + xpos;          // row bit of the run's first base
+            const int qs = qpos + 32 * gj - p0;              // query index of bit 0 of my row word
+            const int a = qs >> 5, sh = qs & 31;
+            const bool ok0 = a >= 0 && a < (int)W, ok1 = a + 1 >= 0 && a + 1 < (int)W;
+            const int src0 = (gbase + a) & 31, src1 = (gbase + a + 1) & 31;
+            uint32_t l0 = __shfl_sync(0xffffffffu, ql, src0), l1 = __shfl_sync(0xffffffffu, ql, src1);
+            uint32_t h0 = __shfl_sync(0xffffffffu, qh, src0), h1 = __shfl_sync(0xffffffffu, qh, src1);
+            uint32_t v0 = __shfl_sync(0xffffffffu, qv, src0), v1 = __shfl_sync(0xffffffffu, qv, src1);
+            if (!ok0) { l0 = 0; h0 = 0; v0 = 0; }
+            if (!ok1) { l1 = 0; h1 = 0; v1 = 0; }
+            const int lo_b = max(0, p0 - 32 * gj), hi_b = min(32, p0 + len - 32 * gj);
+            if (mlike && hi_b > lo_b) {
+              const uint32_t msk = bit_range_mask(lo_b, hi_b);
+              rl |= __funnelshift_r(l0, l1, sh) & msk;
+              rh |= __funnelshift_r(h0, h1, sh) & msk;
+              rv |= __funnelshift_r(v0, v1, sh) & msk;
+            }
+          }
+          if (mlike) { qpos += len; xpos += len; }
+          else if (op == mb::OP_I || op == mb::OP_S) qpos += len;
+          else if (op == mb::OP_D || op == mb::OP_N) xpos += len;
+        }
+        if (rowok) {
+          uint32_t slot = slot0 + (uint32_t)gj;
+          if (slot >= W) slot -= W;
+          s_rows[(uint32_t)i * W + slot] = make_uint4(rv & ~rh & ~rl, rv & ~rh & rl, rv & rh & ~rl, rv & rh & rl);
+        }
+      }
+      __syncthreads();
+      // ---- COUNT: my column's rows of this round, KSUB-strided, 8 rows per carry-save tree
+      {
+        const uint32_t lo = s_first[col], hi = s_first[col + (int)W];
+        if (ksub == 0) col_rows += hi - lo;
+        const uint4* __restrict__ base = s_rows + slot_c;
+        for (uint32_t r = lo + (uint32_t)ksub; r < hi; r += 8 * KSUB) {
+          uint4 mrow[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const uint32_t rr = r + (uint32_t)(u * KSUB);
+            mrow[u] = rr < hi ? base[rr * W] : make_uint4(0, 0, 0, 0);
+          }
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint32_t in[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+              in[u] = c == 0 ? mrow[u].x : (c == 1 ? mrow[u].y : (c == 2 ? mrow[u].z : mrow[u].w));
+            uint32_t t0, t1, t2, t3, f0, f1, e;
+            CSA(cnt[c][0], t0, cnt[c][0], in[0], in[1]);
+            CSA(cnt[c][0], t1, cnt[c][0], in[2], in[3]);
+            CSA(cnt[c][1], f0, cnt[c][1], t0, t1);
+            CSA(cnt[c][0], t2, cnt[c][0], in[4], in[5]);
+            CSA(cnt[c][0], t3, cnt[c][0], in[6], in[7]);
+            CSA(cnt[c][1], f1, cnt[c][1], t2, t3);
+            CSA(cnt[c][2], e, cnt[c][2], f0, f1);
+#pragma unroll
+            for (int l = 3; l < NLEV; ++l) {
+              const uint32_t t = cnt[c][l] & e;
+              cnt[c][l] ^= e;
+              e = t;
+            }
+          }
+          n_lane += 8;
+        }
+      }
+      // a lane takes at most LANE_ROWS_MAX (+7 padding) rows per round: merge before 511 can be passed
+      if (__any_sync(0xffffffffu, n_lane > 511u - (LANE_ROWS_MAX + 8))) flush();
     }
+    flush();
+    expand(accumulate, true);
+
+    // ---- per-tile stats -> per-species stats
     covered = warp_sum(covered);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) depth_sum += __shfl_xor_sync(0xffffffffu, depth_sum, o);
+    my_aligned = warp_sum(my_aligned);
+    my_mapped = warp_sum(my_mapped);
     if (lane == 0) {
       if (covered) atomicAdd(&s_red[0], (unsigned long long)covered);
       if (depth_sum) atomicAdd(&s_red[1], depth_sum);
@@ -241,14 +476,122 @@ __global__ void __launch_bounds__(PILE_THREADS, 2) k_pileup_v1(const PileParams 
     }
     __syncthreads();
     if (tid < 4) {
-      const int sp = p.tile_species[tile];
+      const int sp = p.tile_species[tile / (MB_TILE / KT)];
       const unsigned long long v = s_red[tid];
-      if (sp >= 0 && v) atomicAdd(&p.stats[5 * sp + 1 + tid], v);
+      if (sp >= 0 && v && !(p.defer_restat && tid < 2)) atomicAdd(&p.stats[5 * sp + 1 + tid], v);
     }
   }
 }
 
-constexpr size_t kPileSmem = sizeof(uint32_t) * 4 * TILE + sizeof(uint32_t) * CHUNK + CHUNK;
+// ---- reads that do not fit a W-word row: one warp per read, global atomics (rare by construction)
+struct LongParams {
+  const uint4* hdr;
+  const uint32_t* blk_off;
+  const uint32_t* cplx;
+  const uint32_t* cigar;
+  const uint32_t* seq2;
+  const uint8_t* qual;
+  const uint32_t* long_idx;
+  const int32_t* tile_species;
+  uint32_t* counts;
+  unsigned long long* stats;
+  uint64_t gpad;
+  uint32_t n_long;
+  double mapid, aln_cov;
+  int readq, mapq;
+  uint32_t qthr;  // 0x80 + baseq
+};
+
+__global__ void __launch_bounds__(256) k_long_reads(const LongParams p) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t k = wg; k < p.n_long; k += nw) {
+    const uint32_t r = __ldg(p.long_idx + k);
+    const uint4 h = __ldg(&p.hdr[r]);
+    const uint32_t loc = h.x, lq = h.y & 0xffffu, alen = h.y >> 16, qstart = h.z & 0xffffu, nm = h.z >> 16;
+    const uint32_t span = h.w & 0xffffu, mq = (h.w >> 16) & 0xffu, fl = h.w >> 24;
+    const int sp = p.tile_species[loc / MB_TILE];
+    double pid = __ddiv_rn((double)(100 * ((int)alen - (int)nm)), (double)alen);
+    if (fl & MB_RF_NMSAT) pid = -__longlong_as_double(0x7ff0000000000000ll);
+    bool keep = !(pid < p.mapid) && !((int)mq < p.mapq) && !(__ddiv_rn((double)alen, (double)lq) < p.aln_cov);
+    const uint32_t b0 = __ldg(&p.blk_off[r]);
+    const uint8_t* __restrict__ q = p.qual + (size_t)b0 * 16;
+    if (keep) {
+      uint32_t s = 0;
+      for (uint32_t i = lane; i < lq; i += 32) s += __ldg(q + i) & 0x7fu;
+      s = warp_sum(s);
+      keep = (long long)s >= (long long)p.readq * (long long)lq;
+    }
+    if (lane == 0 && sp >= 0) {
+      atomicAdd(&p.stats[5 * sp + 3], 1ull);
+      if (keep) atomicAdd(&p.stats[5 * sp + 4], 1ull);
+    }
+    if (!keep) continue;
+    const bool simple = (fl & MB_RF_SIMPLE) != 0;
+    const uint32_t* __restrict__ rec = simple ? p.cigar : p.cigar + __ldg(p.cplx + r);
+    const uint32_t n_ops = simple ? 1u : __ldg(rec);
+    uint32_t qpos = simple ? qstart : 0u, x = loc;
+    for (uint32_t o = 0; o < n_ops; ++o) {
+      const uint32_t cw = simple ? (span << 4) : __ldg(rec + 1 + o);
+      const uint32_t op = cw & 0xfu, len = cw >> 4;
+      if (op == mb::OP_M || op == mb::OP_EQ || op == mb::OP_X) {
+        for (uint32_t i = lane; i < len; i += 32) {
+          const uint32_t qi = qpos + i;
+          if (__ldg(q + qi) >= p.qthr) {
+            const uint32_t sw = __ldg(p.seq2 + b0 + (qi >> 4)), bi = qi & 15u;
+            const uint32_t cd = ((sw >> bi) & 1u) | (((sw >> (16 + bi)) & 1u) << 1);
+            atomicAdd(p.counts + (size_t)cd * p.gpad + x + i, 1u);
+          }
+        }
+        qpos += len;
+        x += len;
+      } else if (op == mb::OP_I || op == mb::OP_S) {
+        qpos += len;
+      } else if (op == mb::OP_D || op == mb::OP_N) {
+        x += len;
+      }
+    }
+  }
+}
+
+// covered_bases / total_depth from finished counts (snps.py:204,212-213), one block per MB_TILE tile
+__global__ void __launch_bounds__(256) k_restat(const uint32_t* __restrict__ counts, uint64_t gpad, uint32_t n_tiles,
+                                                const int32_t* __restrict__ tile_species,
+                                                unsigned long long* stats) {
+  __shared__ unsigned long long s_red[2];
+  for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    if (threadIdx.x < 2) s_red[threadIdx.x] = 0;
+    __syncthreads();
+    uint32_t covered = 0;
+    unsigned long long depth = 0;
+    for (uint32_t x4 = threadIdx.x * 4; x4 < MB_TILE; x4 += blockDim.x * 4) {
+      const size_t o = (size_t)t * MB_TILE + x4;
+      const uint4 a = *reinterpret_cast<const uint4*>(counts + o);
+      const uint4 c = *reinterpret_cast<const uint4*>(counts + gpad + o);
+      const uint4 g = *reinterpret_cast<const uint4*>(counts + 2 * gpad + o);
+      const uint4 tt = *reinterpret_cast<const uint4*>(counts + 3 * gpad + o);
+      const uint32_t d0 = a.x + c.x + g.x + tt.x, d1 = a.y + c.y + g.y + tt.y;
+      const uint32_t d2 = a.z + c.z + g.z + tt.z, d3 = a.w + c.w + g.w + tt.w;
+      covered += (d0 > 0) + (d1 > 0) + (d2 > 0) + (d3 > 0);
+      depth += (unsigned long long)d0 + d1 + d2 + d3;
+    }
+    covered = warp_sum(covered);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) depth += __shfl_xor_sync(0xffffffffu, depth, o);
+    if ((threadIdx.x & 31) == 0) {
+      if (covered) atomicAdd(&s_red[0], (unsigned long long)covered);
+      if (depth) atomicAdd(&s_red[1], depth);
+    }
+    __syncthreads();
+    const int sp = tile_species[t];
+    if (threadIdx.x < 2 && sp >= 0 && s_red[threadIdx.x]) atomicAdd(&stats[5 * sp + 1 + threadIdx.x], s_red[threadIdx.x]);
+    __syncthreads();
+  }
+}
+
+size_t pile_smem_bytes(uint32_t W, uint32_t rmax) {
+  return sizeof(uint4) * ((size_t)VCL * NCOL + rmax + (size_t)rmax * W);
+}
 
 }  // namespace
 
@@ -258,31 +601,42 @@ extern "C" int mb_snps_pileup_dev(mb_ctx* ctx, const mb_dev_reads* reads, const 
     return mb::fail(MB_EINVAL, "mb_snps_pileup_dev: null argument");
   if (!reads->sorted) return mb::fail(MB_EUNSORTED, "mb_snps_pileup_dev: reads were not packed in snps (sorted) mode");
   if (f->baseq < 0 || f->baseq > 127) return mb::fail(MB_EINVAL, "mb_snps_pileup_dev: baseq %d outside [0,127]", f->baseq);
+  const uint32_t W = reads->row_words;
+  if (W < 2 || W > (uint32_t)WMAX) return mb::fail(MB_EINVAL, "mb_snps_pileup_dev: row_words %u outside [2,%d]", W, WMAX);
   MB_CUDA_TRY(cudaSetDevice(ctx->device));
   mb_dev_layout dl;
   int rc = mb::get_dev_layout(ctx, L, &dl);
   if (rc) return rc;
-  const uint32_t n_tiles = L->n_tiles;
-  if (ctx->tile_rng_cap < (size_t)2 * n_tiles + 2) {
+  const uint32_t n_ktiles = L->n_tiles * (MB_TILE / KT);
+  if (ctx->tile_rng_cap < (size_t)2 * n_ktiles + 2) {
     if (ctx->tile_rng) { MB_CUDA_TRY(cudaStreamSynchronize(ctx->stream)); MB_CUDA_TRY(cudaFree(ctx->tile_rng)); }
     ctx->tile_rng = nullptr;
     ctx->tile_rng_cap = 0;
-    MB_CUDA_TRY(cudaMalloc(&ctx->tile_rng, sizeof(uint32_t) * ((size_t)2 * n_tiles + 2)));
-    ctx->tile_rng_cap = (size_t)2 * n_tiles + 2;
+    MB_CUDA_TRY(cudaMalloc(&ctx->tile_rng, sizeof(uint32_t) * ((size_t)2 * n_ktiles + 2)));
+    ctx->tile_rng_cap = (size_t)2 * n_ktiles + 2;
   }
-  if (!ctx->pile_attr_set) {
-    MB_CUDA_TRY(cudaFuncSetAttribute(k_pileup_v1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPileSmem));
-    ctx->pile_attr_set = true;
+  // shared memory per CTA: two CTAs per SM (override with MB_PILE_SMEM_KB for experiments)
+  if (!ctx->pile_smem) {
+    size_t kb = 100;
+    if (const char* e = getenv("MB_PILE_SMEM_KB")) { long v = atol(e); if (v >= 32 && v <= 220) kb = (size_t)v; }
+    ctx->pile_smem = kb * 1024;
+    MB_CUDA_TRY(cudaFuncSetAttribute(k_pileup_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->pile_smem));
+    int occ = 0;
+    MB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pileup_v2, NT, ctx->pile_smem));
+    ctx->pile_occ = occ > 0 ? occ : 1;
   }
+  const size_t fixed = sizeof(uint4) * (size_t)VCL * NCOL;
+  uint32_t rmax = (uint32_t)((ctx->pile_smem - fixed) / (sizeof(uint4) * (W + 1)));
+  if (rmax > (uint32_t)LANE_ROWS_MAX * KSUB) rmax = LANE_ROWS_MAX * KSUB;
+  rmax &= ~7u;
   cudaStream_t st = ctx->stream;
   const uint32_t ns = L->n_species;
   k_init_stats<<<ns ? (ns + 255) / 256 : 1, 256, 0, st>>>(
       reinterpret_cast<unsigned long long*>(stats_dev), dl.species_len, ns, ctx->sched);
   ctx->launches++;
-  if (n_tiles == 0) { MB_CUDA_TRY(cudaGetLastError()); return MB_OK; }
-  k_tile_ranges<<<(n_tiles + 255) / 256, 256, 0, st>>>(reinterpret_cast<const uint4*>(reads->hdr),
-                                                       (uint32_t)reads->n_reads, reads->max_ref_span, n_tiles,
-                                                       ctx->tile_rng);
+  if (n_ktiles == 0) { MB_CUDA_TRY(cudaGetLastError()); return MB_OK; }
+  k_tile_ranges<<<(n_ktiles + 255) / 256, 256, 0, st>>>(reinterpret_cast<const uint4*>(reads->hdr),
+                                                        (uint32_t)reads->n_reads, 32u * W, n_ktiles, ctx->tile_rng);
   ctx->launches++;
   PileParams p;
   p.hdr = reinterpret_cast<const uint4*>(reads->hdr);
@@ -290,24 +644,47 @@ extern "C" int mb_snps_pileup_dev(mb_ctx* ctx, const mb_dev_reads* reads, const 
   p.cplx = reads->cplx;
   p.cigar = reads->cigar;
   p.seq2 = reads->seq2;
-  p.qual = reads->qual;
+  p.qual = reinterpret_cast<const uint4*>(reads->qual);
   p.tile_rng = ctx->tile_rng;
   p.tile_species = dl.tile_species;
   p.counts = counts_dev;
   p.stats = reinterpret_cast<unsigned long long*>(stats_dev);
   p.sched = ctx->sched;
   p.gpad = L->gpad;
-  p.n_tiles = n_tiles;
+  p.n_ktiles = n_ktiles;
+  p.W = W;
+  p.G = 32u / W;
+  p.rmax = rmax;
   p.mapid = f->mapid;
   p.aln_cov = f->aln_cov;
   p.readq = f->readq;
   p.mapq = f->mapq;
-  p.qthr = 0x80u + (uint32_t)f->baseq;
-  const uint32_t grid = min(n_tiles, (uint32_t)ctx->sm_count * 2u);
+  p.qadd = (0x80u - (uint32_t)f->baseq) * 0x01010101u;
+  p.defer_restat = reads->n_long ? 1u : 0u;
+  const uint32_t grid = min(n_ktiles, (uint32_t)(ctx->sm_count * ctx->pile_occ));
   { int trc = mb::timing_begin(ctx); if (trc) return trc; }
-  k_pileup_v1<<<grid, PILE_THREADS, kPileSmem, st>>>(p);
+  k_pileup_v2<<<grid, NT, pile_smem_bytes(W, rmax), st>>>(p);
   { int trc = mb::timing_end(ctx); if (trc) return trc; }
   ctx->launches++;
+  if (reads->n_long) {
+    LongParams lp;
+    lp.hdr = p.hdr; lp.blk_off = p.blk_off; lp.cplx = p.cplx; lp.cigar = p.cigar; lp.seq2 = p.seq2;
+    lp.qual = reads->qual;
+    lp.long_idx = reads->long_idx;
+    lp.tile_species = dl.tile_species;
+    lp.counts = counts_dev;
+    lp.stats = p.stats;
+    lp.gpad = L->gpad;
+    lp.n_long = reads->n_long;
+    lp.mapid = f->mapid; lp.aln_cov = f->aln_cov; lp.readq = f->readq; lp.mapq = f->mapq;
+    lp.qthr = 0x80u + (uint32_t)f->baseq;
+    const uint32_t lgrid = min((reads->n_long + 7u) / 8u, (uint32_t)ctx->sm_count * 8u);
+    k_long_reads<<<lgrid, 256, 0, st>>>(lp);
+    ctx->launches++;
+    k_restat<<<min(L->n_tiles, (uint32_t)ctx->sm_count * 8u), 256, 0, st>>>(counts_dev, L->gpad, L->n_tiles,
+                                                                            dl.tile_species, p.stats);
+    ctx->launches++;
+  }
   MB_CUDA_TRY(cudaGetLastError());
   return MB_OK;
 }

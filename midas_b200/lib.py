@@ -43,6 +43,7 @@ class CPlainReads(C.Structure):
 class CPackedReads(C.Structure):
     _fields_ = [("n_reads", C.c_uint64), ("n_blocks", C.c_uint64), ("n_cigar_words", C.c_uint64),
                 ("total_bases", C.c_uint64), ("max_ref_span", C.c_uint32), ("sorted", C.c_uint32),
+                ("row_words", C.c_uint32), ("n_long", C.c_uint32), ("long_idx", C.c_void_p),
                 ("hdr", C.c_void_p), ("blk_off", C.c_void_p), ("cplx", C.c_void_p), ("cigar", C.c_void_p),
                 ("seq2", C.c_void_p), ("qual", C.c_void_p)]
 
@@ -210,12 +211,14 @@ class PackedReads:
     n_blocks = property(lambda s: int(s.c.n_blocks))
     total_bases = property(lambda s: int(s.c.total_bases))
     max_ref_span = property(lambda s: int(s.c.max_ref_span))
+    row_words = property(lambda s: int(s.c.row_words))
+    n_long = property(lambda s: int(s.c.n_long))
 
     @property
     def nbytes(self) -> int:
         c = self.c
         return int(16 * c.n_reads + 4 * (c.n_reads + 1) + 4 * c.n_reads + 4 * c.n_cigar_words + 4 * c.n_blocks
-                   + 16 * c.n_blocks)
+                   + 16 * c.n_blocks + 4 * c.n_long)
 
     def _view(self, ptr, n, dt):
         if n == 0:
@@ -230,6 +233,7 @@ class PackedReads:
     cigar = property(lambda s: s._view(s.c.cigar, int(s.c.n_cigar_words), np.dtype("<u4")))
     seq2 = property(lambda s: s._view(s.c.seq2, s.n_blocks, np.dtype("<u4")))
     qual = property(lambda s: s._view(s.c.qual, s.n_blocks * MB_BLOCK, np.dtype("u1")))
+    long_idx = property(lambda s: s._view(s.c.long_idx, s.n_long, np.dtype("<u4")))
 
 
 class DevReads:

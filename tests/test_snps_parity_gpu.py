@@ -7,6 +7,9 @@ from midas_b200 import lib, synth
 from midas_b200.soa import Filters
 from oracle import oracle
 
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
 pytestmark = pytest.mark.gpu
 
 
@@ -50,3 +53,51 @@ def test_filter_settings(ctx, filters):
     ref, reads = synth.synth_snps(seed=21, n_species=2, contigs_per_species=2, contig_len=8_000, n_reads=25_000,
                                   len_jitter=0.2)
     _check(ctx, ref, reads, filters)
+
+
+# ---- arbitrary CIGARs (clips, =/X, N skips, long deletions -> long-read kernel, contig-end overhang)
+@pytest.mark.parametrize("seed,n_species,cps,lo,hi,n_reads,max_len", [
+    (101, 3, 2, 500, 6000, 3000, 300),
+    (102, 1, 1, 5000, 5000, 4000, 150),
+    (103, 2, 3, 40, 900, 2500, 120),        # contigs shorter than reads
+    (104, 1, 1, 70000, 70000, 20000, 100),  # many tiles
+    (105, 4, 1, 3000, 9000, 6000, 520),     # query longer than a 16-word row
+])
+def test_random_cigars(ctx, seed, n_species, cps, lo, hi, n_reads, max_len):
+    import gen
+    rng = np.random.default_rng(seed)
+    ref = gen.make_ref(rng, n_species, cps, lo, hi)
+    reads = gen.random_reads(seed, ref, n_reads, max_len=max_len)
+    for filters in (Filters(), Filters(mapid=0.0, aln_cov=0.0, readq=0, mapq=0, baseq=0),
+                    Filters(mapid=90.0, aln_cov=0.5, readq=25, mapq=10, baseq=20)):
+        _check(ctx, ref, reads, filters)
+
+
+def test_unsorted_input_is_sorted_by_the_packer(ctx):
+    import gen
+    rng = np.random.default_rng(7)
+    ref = gen.make_ref(rng, 2, 2, 2000, 4000)
+    reads = gen.random_reads(8, ref, 3000, max_len=160, sort=False)
+    _check(ctx, ref, reads, Filters(mapid=0.0, aln_cov=0.0, readq=0, mapq=0, baseq=10))
+
+
+@pytest.mark.parametrize("n_reads,frac", [(9000, 0.9), (80000, 0.97)])
+def test_deep_pile(ctx, n_reads, frac):
+    """Thousands of reads on one locus: register counters are merged early (> 511 rows per lane) and,
+    past 65 528 rows per tile, the shared counters are expanded in several passes."""
+    import gen
+    rng = np.random.default_rng(5)
+    ref = gen.make_ref(rng, 1, 2, 3000, 5000)
+    reads = gen.random_reads(9, ref, n_reads, max_len=60, min_len=20, pos_hot=(1, 2040, frac), long_del_frac=0.0)
+    _check(ctx, ref, reads, Filters(mapid=0.0, aln_cov=0.0, readq=0, mapq=0, baseq=0))
+    _check(ctx, ref, reads, Filters())
+
+
+def test_empty_and_tiny(ctx):
+    import gen
+    rng = np.random.default_rng(3)
+    ref = gen.make_ref(rng, 2, 1, 100, 5000)
+    empty = gen.random_reads(1, ref, 0)
+    _check(ctx, ref, empty, Filters())
+    one = gen.random_reads(2, ref, 1, max_len=50)
+    _check(ctx, ref, one, Filters(mapid=0.0, aln_cov=0.0, readq=0, mapq=0, baseq=0))

@@ -138,9 +138,10 @@ typedef struct {
  *             bit 16+k = high bit of base k (A=0 C=1 G=2 T=3; non-ACGT and padding = 0)
  *   qual[16b+k] bit 7 = base k is a literal A/C/G/T (countable), bits 0-6 = Phred;
  *             padding bytes are 0
- *   cplx[i]   for reads without MB_RF_SIMPLE: index into cigar[] of a record
- *             {n_ops, op0, op1, ...} (BAM op words, contig-end overhang already
- *             rewritten to a trailing soft clip); 0xFFFFFFFF for simple reads
+ *   cplx[i]   for reads without MB_RF_SIMPLE: index into cigar[] of a run record
+ *             {n_runs, (q0 | len << 16, x0) per M/=/X run}: query index of the run's first
+ *             base, run length, reference offset from the read's start (I/S/D/N/H folded in,
+ *             clipped at the contig end); 0xFFFFFFFF for simple reads
  */
 typedef struct {
   uint64_t n_reads;

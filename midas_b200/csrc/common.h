@@ -82,6 +82,10 @@ struct mb_ctx {
   uint32_t* tile_rng;  // [2*n_tiles]
   size_t tile_rng_cap;
   uint32_t* sched;     // dynamic tile scheduler counters
+  // exact integer thresholds of the two floating-point read filters, per alen / l_qseq (see ctx.cu)
+  int32_t* ftab;       // device: [2][65536]
+  double ftab_mapid, ftab_cov;
+  bool ftab_valid;
   std::unordered_map<uint64_t, mb_dev_layout> layouts;
   // staging for the host-buffer convenience calls
   void* stage[16];
@@ -94,4 +98,5 @@ int timing_end(mb_ctx* ctx);
 int upload_reads(mb_ctx* ctx, const mb_packed_reads* h, mb_dev_reads* d, bool staged);
 int ctx_reserve(mb_ctx* ctx, int slot, size_t bytes, void** out);
 int get_dev_layout(mb_ctx* ctx, const mb_layout* L, mb_dev_layout* out);
+int get_filter_tables(mb_ctx* ctx, const mb_filters* f, const int32_t** t_pid, const int32_t** t_cov);
 }  // namespace mb

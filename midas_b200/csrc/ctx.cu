@@ -1,6 +1,7 @@
 // Context, device-resident reads and device mirrors of the reference layout.
 #include <cstdio>
 #include <cstring>
+#include <climits>
 
 #include "common.h"
 
@@ -41,6 +42,61 @@ int get_dev_layout(mb_ctx* ctx, const mb_layout* L, mb_dev_layout* out) {
   MB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   ctx->layouts[L->id] = d;
   *out = d;
+  return MB_OK;
+}
+
+// The reference's two floating-point read filters compare an IEEE-754 double quotient of small
+// integers with a user threshold (snps.py:148,157):
+//     100*(alen-NM)/float(alen) < mapid        alen/float(l_qseq) < aln_cov
+// Both quotients are monotone in their integer numerator, so for every denominator there is one
+// smallest numerator that passes. The host finds it with the same correctly-rounded division the
+// reference's interpreter performs, and the kernels compare integers:
+//     t_pid[alen] = min num  with (double)num / alen  >= mapid   -> keep iff 100*(alen-NM) >= t_pid[alen]
+//     t_cov[lq]   = min alen with (double)alen / lq   >= aln_cov -> keep iff alen >= t_cov[lq]
+int get_filter_tables(mb_ctx* c, const mb_filters* f, const int32_t** t_pid, const int32_t** t_cov) {
+  const int N = 65536;
+  if (!c->ftab) MB_CUDA_TRY(cudaMalloc(&c->ftab, sizeof(int32_t) * 2 * N));
+  const bool same = c->ftab_valid && memcmp(&c->ftab_mapid, &f->mapid, sizeof(double)) == 0 &&
+                    memcmp(&c->ftab_cov, &f->aln_cov, sizeof(double)) == 0;
+  if (!same) {
+    std::vector<int32_t> h(2 * N);
+    const double mapid = f->mapid, cov = f->aln_cov;
+    h[0] = INT32_MAX;  // alen = 0 never reaches the kernels (MB_EINVAL at pack time)
+    h[N] = INT32_MAX;
+    for (int d = 1; d < N; ++d) {
+      const double dd = (double)d;
+      {  // numerators 100*(alen-NM), NM in [0,65535]
+        const long long lo = 100LL * (d - 65535), hi = 100LL * d;
+        int32_t t;
+        if (mapid != mapid || (double)lo / dd >= mapid) t = INT32_MIN;
+        else if (!((double)hi / dd >= mapid)) t = INT32_MAX;
+        else {
+          long long a = lo, b = hi;  // a fails, b passes
+          while (b - a > 1) { const long long m = a + (b - a) / 2; if ((double)m / dd >= mapid) b = m; else a = m; }
+          t = (int32_t)b;
+        }
+        h[d] = t;
+      }
+      {  // numerators alen in [0,65535]
+        int32_t t;
+        if (cov != cov || 0.0 / dd >= cov) t = 0;
+        else if (!(65535.0 / dd >= cov)) t = INT32_MAX;
+        else {
+          long long a = 0, b = 65535;
+          while (b - a > 1) { const long long m = a + (b - a) / 2; if ((double)m / dd >= cov) b = m; else a = m; }
+          t = (int32_t)b;
+        }
+        h[N + d] = t;
+      }
+    }
+    MB_CUDA_TRY(cudaStreamSynchronize(c->stream));  // a previous launch may still read the old tables
+    MB_CUDA_TRY(cudaMemcpy(c->ftab, h.data(), sizeof(int32_t) * 2 * N, cudaMemcpyHostToDevice));
+    c->ftab_mapid = f->mapid;
+    c->ftab_cov = f->aln_cov;
+    c->ftab_valid = true;
+  }
+  *t_pid = c->ftab;
+  *t_cov = c->ftab + N;
   return MB_OK;
 }
 
@@ -92,6 +148,8 @@ extern "C" int mb_ctx_create(int device, mb_ctx** out) {
   c->tile_rng = nullptr;
   c->tile_rng_cap = 0;
   c->sched = nullptr;
+  c->ftab = nullptr;
+  c->ftab_valid = false;
   memset(c->stage, 0, sizeof(c->stage));
   memset(c->stage_cap, 0, sizeof(c->stage_cap));
   MB_CUDA_TRY(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
@@ -117,6 +175,7 @@ extern "C" void mb_ctx_destroy(mb_ctx* c) {
     if (c->stage[i]) cudaFree(c->stage[i]);
   if (c->tile_rng) cudaFree(c->tile_rng);
   if (c->sched) cudaFree(c->sched);
+  if (c->ftab) cudaFree(c->ftab);
   for (int i = 0; i < mb_ctx::kRing; ++i) {
     cudaEventDestroy(c->ring[i][0]);
     cudaEventDestroy(c->ring[i][1]);

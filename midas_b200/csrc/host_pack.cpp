@@ -217,27 +217,37 @@ int analyse(const mb_plain_reads* in, const mb_layout* L, int mode, uint64_t i, 
     g->flags |= MB_RF_SIMPLE;
   } else {
     g->q_start = (uint16_t)lead;
-    g->n_cplx_words = 1 + (uint32_t)n_cig;  // upper bound; H ops and post-clip ops are dropped when written
+    g->n_cplx_words = 1 + 2 * (uint32_t)n_match_ops;  // upper bound; runs past the contig end are dropped
   }
   return MB_OK;
 }
 
-// Write the {n_ops, ops...} record of a complex read, clipped at the contig end. Returns words written.
+// Write the run record of a complex read: {n_runs, then per M/=/X run two words
+// (q0 | len << 16, x0)} = query index of the run's first base, its length, and its reference
+// offset from the read's start; clipped at the contig end. Returns words written.
 uint32_t write_cplx(const uint32_t* cig, int64_t n_cig, int64_t room /* contig_len - pos */, uint32_t* dst) {
   uint32_t n = 0;
-  int64_t r = 0;
+  int64_t q = 0, r = 0;
   for (int64_t k = 0; k < n_cig && r < room; ++k) {
     uint32_t op = cig[k] & 0xF;
     int64_t len = cig[k] >> 4;
-    if (op == mb::OP_H || len == 0) continue;
-    if (op == mb::OP_M || op == mb::OP_EQ || op == mb::OP_X || op == mb::OP_D || op == mb::OP_N) {
-      if (r + len > room) len = room - r;
+    if (op == mb::OP_M || op == mb::OP_EQ || op == mb::OP_X) {
+      int64_t take = std::min<int64_t>(len, room - r);
+      if (take > 0) {
+        dst[1 + 2 * n] = (uint32_t)q | ((uint32_t)take << 16);
+        dst[2 + 2 * n] = (uint32_t)r;
+        ++n;
+      }
+      q += len;
+      r += len;
+    } else if (op == mb::OP_I || op == mb::OP_S) {
+      q += len;
+    } else if (op == mb::OP_D || op == mb::OP_N) {
       r += len;
     }
-    dst[1 + n++] = ((uint32_t)len << 4) | op;
   }
   dst[0] = n;
-  return 1 + n;
+  return 1 + 2 * n;
 }
 
 static const uint8_t kNib2Code[16] = {0, 0, 1, 0, 2, 0, 0, 0, 3, 0, 0, 0, 0, 0, 0, 0};

@@ -32,6 +32,7 @@
 // with global atomics and the position stats are then recomputed by k_restat.
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
 
 #include "common.h"
 
@@ -42,12 +43,12 @@ constexpr int NCOL = KT / 32;            // 32-position columns per tile
 constexpr int KSUB = 4;                  // lanes sharing a column
 constexpr int NT = NCOL * KSUB;          // threads per CTA
 constexpr int NWARP = NT / 32;
-constexpr int NLEV = 9;                  // register vertical-counter levels (per-lane count <= 511)
+constexpr int NLEV = 8;                  // register vertical-counter levels (per-lane count <= 255 per round)
 constexpr int XLEV = NLEV + 2;           // levels after merging KSUB = 4 lanes
 constexpr int VCL = 16;                  // shared-memory vertical-counter levels (<= 65535 rows per pass)
 constexpr int WMAX = MB_ROW_WORDS_MAX;
 constexpr uint32_t PASS_ROWS = 65528;    // rows folded into the shared counters before they are expanded
-constexpr int LANE_ROWS_MAX = 248;       // rows one lane may take in one round (keeps its count <= 511)
+constexpr int LANE_ROWS_MAX = 248;       // rows one lane may take in one round (keeps its count <= 255)
 constexpr int FIRST_N = NCOL + WMAX + 1;
 
 static_assert(MB_TILE % KT == 0, "kernel tile must divide the layout tile");
@@ -72,8 +73,11 @@ struct PileParams {
   uint32_t W;                 // row words
   uint32_t G;                 // reads per warp iteration = 32 / W
   uint32_t rmax;              // rows staged per round
-  double mapid, aln_cov;
-  int readq, mapq;
+  const int32_t* t_pid;       // [65536] smallest 100*(alen-NM) that passes mapid, per alen
+  const int32_t* t_cov;       // [65536] smallest alen that passes aln_cov, per l_qseq
+  uint32_t pid_always;        // mapid is -inf or NaN (reads with a saturated NM pass only then)
+  uint32_t readq_eff;         // readq clamped to [0,128]
+  int mapq;
   uint32_t qadd;              // (0x80 - baseq) * 0x01010101
   uint32_t defer_restat;      // 1: long reads follow, position stats are recomputed afterwards
 };
@@ -156,24 +160,38 @@ __global__ void k_tile_ranges(const uint4* __restrict__ hdr, uint32_t n_reads, u
   rng[2 * t + 1] = lo;
 }
 
+// One staged read of the STAGE pipeline: everything a lane fetches from HBM for its 32 query bases
+struct StageIn {
+  uint4 m;        // s_meta entry
+  uint4 qa, qb;   // 2 x 16 qualities
+  uint32_t sa, sb;  // 2 x 16 two-bit bases
+  uint32_t r0a, r0b, r1a, r1b;  // first two runs of a complex read
+};
+
 __global__ void __launch_bounds__(NT, 2) k_pileup_v2(const PileParams p) {
   extern __shared__ __align__(16) uint32_t smem[];
   const uint32_t W = p.W;
   uint4* s_vc = reinterpret_cast<uint4*>(smem);                       // [VCL][NCOL] x {A,C,G,T}
   uint4* s_meta = s_vc + VCL * NCOL;                                  // [rmax]
   uint4* s_rows = s_meta + p.rmax;                                    // [rmax][W] x {A,C,G,T}
+  uint32_t* s_cplx = reinterpret_cast<uint32_t*>(s_rows + (size_t)p.rmax * W);  // [rmax]
   __shared__ uint32_t s_first[FIRST_N];
   __shared__ unsigned long long s_red[4];                             // covered, depth, aligned, mapped
   __shared__ uint32_t s_tile, s_nmax;
+  __shared__ uint8_t s_mod[NCOL + 2 * WMAX + 1];                      // x % W for small x
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int col = tid >> 2, ksub = tid & 3;                           // COUNT role
   const int grp = lane / (int)W, gj = lane - grp * (int)W;            // STAGE role
   const int gbase = grp * (int)W;
   const bool lane_ok = grp < (int)p.G;
-  const uint32_t reduce_steps = W > 8 ? 4 : (W > 4 ? 3 : (W > 2 ? 2 : 1));
+  const uint32_t bi = 2u * (uint32_t)gj;                              // my first 16-base block of a read
+  const uint4* __restrict__ qual_j = p.qual + bi;
+  const uint32_t* __restrict__ seq_j = p.seq2 + bi;
+  const int istep = NWARP * (int)p.G;
 
   for (int i = tid; i < VCL * NCOL; i += NT) s_vc[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < NCOL + 2 * WMAX + 1; i += NT) s_mod[i] = (uint8_t)((uint32_t)i % W);
 
   for (;;) {
     __syncthreads();
@@ -184,59 +202,14 @@ __global__ void __launch_bounds__(NT, 2) k_pileup_v2(const PileParams p) {
     if (tile >= p.n_ktiles) break;
     const uint32_t ts = tile * KT;
     const uint32_t r0 = p.tile_rng[2 * tile], r1 = p.tile_rng[2 * tile + 1];
-    const uint32_t slot_c = ((ts >> 5) + (uint32_t)col) % W;          // where my column's word sits in a row
+    const uint32_t tcol = ts >> 5, tb = tcol % W;
+    const uint32_t slot_c = s_mod[tb + (uint32_t)col];                // where my column's word sits in a row
+    const uint32_t loc_base = ts - 32u * WMAX;                        // row coordinates are stored relative to it (wraps for ts = 0: no read starts before 0)
 
-    uint32_t cnt[4][NLEV];
-#pragma unroll
-    for (int c = 0; c < 4; ++c)
-#pragma unroll
-      for (int l = 0; l < NLEV; ++l) cnt[c][l] = 0;
-    uint32_t n_lane = 0;        // rows (padded to blocks of 8) folded into cnt
     uint32_t col_rows = 0;      // rows of my column folded since the last expansion
     uint32_t my_aligned = 0, my_mapped = 0;
     uint32_t covered = 0;
     unsigned long long depth_sum = 0;
-
-    // merge the KSUB lanes of each column (shuffle butterfly of bit-sliced adders) and add the
-    // result into the shared vertical counters; lane ksub folds class ksub
-    auto flush = [&]() {
-      uint32_t x[4][XLEV];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-#pragma unroll
-        for (int l = 0; l < NLEV; ++l) x[c][l] = cnt[c][l];
-#pragma unroll
-        for (int step = 0; step < 2; ++step) {
-          uint32_t carry = 0;
-#pragma unroll
-          for (int l = 0; l < NLEV + step; ++l) {
-            const uint32_t y = __shfl_xor_sync(0xffffffffu, x[c][l], 1 << step);
-            CSA(x[c][l], carry, x[c][l], y, carry);
-          }
-          x[c][NLEV + step] = carry;
-        }
-      }
-      uint32_t mine[VCL];
-#pragma unroll
-      for (int l = 0; l < VCL; ++l)
-        mine[l] = l >= XLEV ? 0u : (ksub == 0 ? x[0][l < XLEV ? l : 0] : (ksub == 1 ? x[1][l < XLEV ? l : 0]
-                                   : (ksub == 2 ? x[2][l < XLEV ? l : 0] : x[3][l < XLEV ? l : 0])));
-      uint32_t* vc = reinterpret_cast<uint32_t*>(s_vc) + col * 4 + ksub;
-      uint32_t carry = 0;
-#pragma unroll
-      for (int l = 0; l < VCL; ++l) {
-        if (l >= XLEV && !__any_sync(0xffffffffu, carry != 0)) break;
-        const uint32_t a = vc[l * NCOL * 4];
-        uint32_t sum;
-        CSA(sum, carry, a, mine[l], carry);
-        vc[l * NCOL * 4] = sum;
-      }
-#pragma unroll
-      for (int c = 0; c < 4; ++c)
-#pragma unroll
-        for (int l = 0; l < NLEV; ++l) cnt[c][l] = 0;
-      n_lane = 0;
-    };
 
     // transpose the shared vertical counters to u32 counts and write the tile (or add to it)
     auto expand = [&](const bool accumulate, const bool last) {
@@ -294,7 +267,6 @@ __global__ void __launch_bounds__(NT, 2) k_pileup_v2(const PileParams p) {
     for (uint32_t rb = r0; rb < r1; rb += p.rmax) {
       const int n = (int)min(p.rmax, r1 - rb);
       if (pass_rows + (uint32_t)n > PASS_ROWS) {  // keep the shared counters below 2^VCL
-        flush();
         expand(accumulate, false);
         accumulate = true;
         pass_rows = 0;
@@ -312,26 +284,28 @@ __global__ void __launch_bounds__(NT, 2) k_pileup_v2(const PileParams p) {
         if (!(fl & MB_RF_LONG)) {
           const bool owner = loc >= ts;
           const bool ovl = span > 0 && loc + span > ts;
-          double pid = __ddiv_rn((double)(100 * ((int)alen - (int)nm)), (double)alen);
-          if (fl & MB_RF_NMSAT) pid = -__longlong_as_double(0x7ff0000000000000ll);
-          bool hk = !(pid < p.mapid);
-          hk = hk && !((int)mq < p.mapq);
-          hk = hk && !(__ddiv_rn((double)alen, (double)lq) < p.aln_cov);
-          if (owner) ++my_aligned;                                       // snps.py:143
+          // exact integer forms of the two double-precision tests (tables built in ctx.cu)
+          bool hk = (fl & MB_RF_NMSAT) ? (p.pid_always != 0)
+                                       : (100 * ((int)alen - (int)nm) >= __ldg(p.t_pid + alen));   // snps.py:148
+          hk = hk && (int)mq >= p.mapq;                                                             // snps.py:154
+          hk = hk && (int)alen >= __ldg(p.t_cov + lq);                                              // snps.py:157
+          if (owner) ++my_aligned;                                                                  // snps.py:143
           if (hk && (ovl || owner)) flags |= F_NEEDQ;
           if (ovl) flags |= F_OVL;
           if (owner) flags |= F_OWNER;
           if (fl & MB_RF_SIMPLE) flags |= F_SIMPLE;
+          else if ((flags & F_NEEDQ) && ovl) s_cplx[i] = __ldg(p.cplx + r);
         }
-        const uint32_t gc = loc >> 5;
-        s_meta[i] = make_uint4(loc, b0, lq | (qstart << 16), span | (flags << 16) | ((gc % W) << 24));
+        const int rel = (int)(loc >> 5) - (int)tcol;                      // start column, in [-W, NCOL)
+        const uint32_t slot0 = s_mod[(int)tb + rel + (int)W];
+        s_meta[i] = make_uint4((loc - loc_base) | (span << 16), b0, lq | (qstart << 16), flags | (slot0 << 8));
         // s_first[x] = first row of this round whose start column + (W-1) >= x
         const int kmax = NCOL + (int)W - 1;
-        int xi = (int)gc - (int)(ts >> 5) + (int)W - 1;
+        int xi = rel + (int)W - 1;
         xi = xi < 0 ? 0 : (xi > kmax ? kmax : xi);
         int xlo = 0;
         if (i > 0) {
-          int xp = (int)(__ldg(&p.hdr[r - 1].x) >> 5) - (int)(ts >> 5) + (int)W - 1;
+          int xp = (int)(__ldg(&p.hdr[r - 1].x) >> 5) - (int)tcol + (int)W - 1;
           xp = xp < 0 ? 0 : (xp > kmax ? kmax : xp);
           xlo = xp + 1;
         }
@@ -340,126 +314,168 @@ __global__ void __launch_bounds__(NT, 2) k_pileup_v2(const PileParams p) {
           for (int x = xi + 1; x <= kmax + 1; ++x) s_first[x] = (uint32_t)n;
       }
       __syncthreads();
-      // ---- STAGE: W lanes per read build its bit-plane row
-      for (int it = warp; it * (int)p.G < n; it += NWARP) {
-        const int i = it * (int)p.G + grp;
+      // ---- STAGE: W lanes per read build its bit-plane row; the loads of the next read are issued
+      // before the current one is converted (two reads in flight per lane group)
+      auto fetch = [&](const int i, StageIn& in) {
+        in.m = make_uint4(0, 0, 0, 0);
+        in.qa = make_uint4(0, 0, 0, 0);
+        in.qb = make_uint4(0, 0, 0, 0);
+        in.sa = 0; in.sb = 0;
+        in.r0a = 0; in.r0b = 0; in.r1a = 0; in.r1b = 0;
+        if (lane_ok && i < n) {
+          in.m = s_meta[i];
+          const uint32_t fl = in.m.w;
+          if (fl & F_NEEDQ) {
+            const uint32_t nblk = ((in.m.z & 0xffffu) + 15u) >> 4;
+            if (bi < nblk) { in.qa = __ldg(qual_j + in.m.y); in.sa = __ldg(seq_j + in.m.y); }
+            if (bi + 1 < nblk) { in.qb = __ldg(qual_j + in.m.y + 1); in.sb = __ldg(seq_j + in.m.y + 1); }
+            if (!(fl & F_SIMPLE) && (fl & F_OVL)) {
+              const uint32_t* __restrict__ rec = p.cigar + s_cplx[i];
+              in.r0a = __ldg(rec);       // n_runs
+              in.r0b = __ldg(rec + 1);
+              in.r1a = __ldg(rec + 2);
+              in.r1b = __ldg(rec + 3);   // may belong to the next record when n_runs == 1 (ignored then)
+            }
+          }
+        }
+      };
+      StageIn cur;
+      fetch(warp * (int)p.G + grp, cur);
+      for (int i = warp * (int)p.G + grp; i - grp < n; i += istep) {
+        StageIn nxt;
+        fetch(i + istep, nxt);
         const bool rowok = lane_ok && i < n;
-        uint4 m = make_uint4(0, 0, 0, 0);
-        if (rowok) m = s_meta[i];
-        const uint32_t loc = m.x, b0 = m.y, lq = m.z & 0xffffu, qstart = m.z >> 16;
-        const uint32_t span = m.w & 0xffffu, flags = (m.w >> 16) & 0xffu, slot0 = m.w >> 24;
+        const uint4 m = cur.m;
+        const uint32_t lq = m.z & 0xffffu, flags = m.w;
         const bool needq = (flags & F_NEEDQ) != 0;
-        const uint32_t nblk = (lq + 15u) >> 4;
-        // this lane's 32 query bases = blocks 2j and 2j+1
-        uint4 qa = make_uint4(0, 0, 0, 0), qb = make_uint4(0, 0, 0, 0);
-        uint32_t sa = 0, sb = 0;
-        const uint32_t bi = 2u * (uint32_t)gj;
-        if (needq && bi < nblk) { qa = __ldg(p.qual + b0 + bi); sa = __ldg(p.seq2 + b0 + bi); }
-        if (needq && bi + 1 < nblk) { qb = __ldg(p.qual + b0 + bi + 1); sb = __ldg(p.seq2 + b0 + bi + 1); }
         uint32_t qsum = 0, a01, a23, c01, c23;
-        conv16(qa, p.qadd, qsum, a01, a23);
-        conv16(qb, p.qadd, qsum, c01, c23);
+        conv16(cur.qa, p.qadd, qsum, a01, a23);
+        conv16(cur.qb, p.qadd, qsum, c01, c23);
         const uint32_t qv = __byte_perm(__byte_perm(a01, a23, 0x0040), __byte_perm(c01, c23, 0x0040), 0x5410);
-        const uint32_t ql = __byte_perm(sa, sb, 0x5410);   // low bits of the 2-bit base codes, 32 bases
-        const uint32_t qh = __byte_perm(sa, sb, 0x7632);   // high bits
+        const uint32_t ql = __byte_perm(cur.sa, cur.sb, 0x5410);   // low bits of the 2-bit base codes, 32 bases
+        const uint32_t qh = __byte_perm(cur.sa, cur.sb, 0x7632);   // high bits
         // mean-quality filter (snps.py:151): mean(q) < readq  <=>  sum(q) < readq * l_qseq (exact)
         uint32_t tot = qsum;
-        for (uint32_t s = 0, d = 1; s < reduce_steps; ++s, d <<= 1) {
+        for (uint32_t d = 1; d < W; d <<= 1) {
           const uint32_t t = __shfl_down_sync(0xffffffffu, tot, d);
           if (gj + (int)d < (int)W) tot += t;
         }
-        tot = __shfl_sync(0xffffffffu, tot, gbase & 31);
-        const bool keep = needq && ((long long)tot >= (long long)p.readq * (long long)lq);
+        tot = __shfl_sync(0xffffffffu, tot, gbase);
+        const bool keep = needq && tot >= p.readq_eff * lq;
         if (gj == 0 && keep && (flags & F_OWNER)) ++my_mapped;               // snps.py:161
-        const bool place = rowok && keep && (flags & F_OVL);
-        // ---- CIGAR: every M/=/X run is one shifted, masked copy of the query planes
+        const bool place = keep && (flags & F_OVL);
+        // ---- CIGAR: every M/=/X run is one shifted, masked copy of the query planes. Bits that
+        // survive a run's mask come from query words of this read, so no lane guards are needed.
         const bool simple = (flags & F_SIMPLE) != 0;
-        const uint32_t* __restrict__ rec = p.cigar;
-        uint32_t n_ops = 0;
+        uint32_t n_runs = 0;
+        uint32_t w0 = (m.z >> 16) | (m.x & 0xffff0000u), w1 = 0;   // simple read: q0 = q_start, len = span, x0 = 0
         if (place) {
-          if (simple) n_ops = 1;
-          else { rec = p.cigar + __ldg(p.cplx + rb + (uint32_t)i); n_ops = __ldg(rec); }
+          n_runs = 1;
+          if (!simple) { n_runs = cur.r0a; w0 = cur.r0b; w1 = cur.r1a; }
         }
-        const uint32_t max_ops = __reduce_max_sync(0xffffffffu, n_ops);
-        int qpos = simple ? (int)qstart : 0, xpos = 0;
+        const uint32_t max_runs = __reduce_max_sync(0xffffffffu, n_runs);
+        const int o32 = (int)(m.x & 31u) - 32 * gj;            // row bit of the read's first base, relative to my word
         uint32_t rl = 0, rh = 0, rv = 0;
-        for (uint32_t o = 0; o < max_ops; ++o) {
-          uint32_t cw = 0;
-          const bool act = o < n_ops;
-          if (act) cw = simple ? (span << 4) : __ldg(rec + 1 + o);
-          const uint32_t op = cw & 0xfu;
-          const int len = (int)(cw >> 4);
-          const bool mlike = act && (op == mb::OP_M || op == mb::OP_EQ || op == mb::OP_X);
-          if (__any_sync(0xffffffffu, mlike)) {
-            const int p0 = (int)(loc & 31u) + xpos;          // row bit of the run's first base
-            const int qs = qpos + 32 * gj - p0;              // query index of bit 0 of my row word
-            const int a = qs >> 5, sh = qs & 31;
-            const bool ok0 = a >= 0 && a < (int)W, ok1 = a + 1 >= 0 && a + 1 < (int)W;
-            const int src0 = (gbase + a) & 31, src1 = (gbase + a + 1) & 31;
-            uint32_t l0 = __shfl_sync(0xffffffffu, ql, src0), l1 = __shfl_sync(0xffffffffu, ql, src1);
-            uint32_t h0 = __shfl_sync(0xffffffffu, qh, src0), h1 = __shfl_sync(0xffffffffu, qh, src1);
-            uint32_t v0 = __shfl_sync(0xffffffffu, qv, src0), v1 = __shfl_sync(0xffffffffu, qv, src1);
-            if (!ok0) { l0 = 0; h0 = 0; v0 = 0; }
-            if (!ok1) { l1 = 0; h1 = 0; v1 = 0; }
-            const int lo_b = max(0, p0 - 32 * gj), hi_b = min(32, p0 + len - 32 * gj);
-            if (mlike && hi_b > lo_b) {
-              const uint32_t msk = bit_range_mask(lo_b, hi_b);
-              rl |= __funnelshift_r(l0, l1, sh) & msk;
-              rh |= __funnelshift_r(h0, h1, sh) & msk;
-              rv |= __funnelshift_r(v0, v1, sh) & msk;
-            }
+        for (uint32_t k = 0; k < max_runs; ++k) {
+          if (k >= 1 && k < n_runs) {
+            const uint32_t* __restrict__ rec = p.cigar + s_cplx[i];
+            if (k == 1) { w0 = cur.r1b; w1 = __ldg(rec + 4); }
+            else { w0 = __ldg(rec + 1 + 2 * k); w1 = __ldg(rec + 2 + 2 * k); }
           }
-          if (mlike) { qpos += len; xpos += len; }
-          else if (op == mb::OP_I || op == mb::OP_S) qpos += len;
-          else if (op == mb::OP_D || op == mb::OP_N) xpos += len;
+          const int q0 = (int)(w0 & 0xffffu), len = (int)(w0 >> 16);
+          const int p0 = o32 + (int)w1;                        // row bit of the run's first base (my word = 0)
+          const int qs = q0 - p0;                              // query index of bit 0 of my row word
+          const int a = gbase + (qs >> 5), sh = qs & 31;
+          const uint32_t l0 = __shfl_sync(0xffffffffu, ql, a), l1 = __shfl_sync(0xffffffffu, ql, a + 1);
+          const uint32_t h0 = __shfl_sync(0xffffffffu, qh, a), h1 = __shfl_sync(0xffffffffu, qh, a + 1);
+          const uint32_t v0 = __shfl_sync(0xffffffffu, qv, a), v1 = __shfl_sync(0xffffffffu, qv, a + 1);
+          const int lo_b = max(0, p0), hi_b = min(32, p0 + len);
+          if (k < n_runs && hi_b > lo_b) {
+            const uint32_t msk = bit_range_mask(lo_b, hi_b);
+            rl |= __funnelshift_r(l0, l1, sh) & msk;
+            rh |= __funnelshift_r(h0, h1, sh) & msk;
+            rv |= __funnelshift_r(v0, v1, sh) & msk;
+          }
         }
         if (rowok) {
-          uint32_t slot = slot0 + (uint32_t)gj;
+          uint32_t slot = ((flags >> 8) & 0xffu) + (uint32_t)gj;
           if (slot >= W) slot -= W;
           s_rows[(uint32_t)i * W + slot] = make_uint4(rv & ~rh & ~rl, rv & ~rh & rl, rv & rh & ~rl, rv & rh & rl);
         }
+        cur = nxt;
       }
       __syncthreads();
-      // ---- COUNT: my column's rows of this round, KSUB-strided, 8 rows per carry-save tree
+      // ---- COUNT: my column's rows of this round, KSUB-strided, 8 rows per carry-save tree into
+      // bit-sliced register counters; then the KSUB lanes of a column are merged by a shuffle
+      // butterfly of bit-sliced adders and lane ksub folds class ksub into the shared counters
       {
         const uint32_t lo = s_first[col], hi = s_first[col + (int)W];
-        if (ksub == 0) col_rows += hi - lo;
-        const uint4* __restrict__ base = s_rows + slot_c;
-        for (uint32_t r = lo + (uint32_t)ksub; r < hi; r += 8 * KSUB) {
-          uint4 mrow[8];
+        if (__any_sync(0xffffffffu, hi > lo)) {
+          if (ksub == 0) col_rows += hi - lo;
+          uint32_t cnt[4][XLEV];
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const uint32_t rr = r + (uint32_t)(u * KSUB);
-            mrow[u] = rr < hi ? base[rr * W] : make_uint4(0, 0, 0, 0);
+          for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int l = 0; l < NLEV; ++l) cnt[c][l] = 0;
+          const uint4* __restrict__ base = s_rows + slot_c;
+          for (uint32_t r = lo + (uint32_t)ksub; r < hi; r += 8 * KSUB) {
+            uint4 mrow[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const uint32_t rr = r + (uint32_t)(u * KSUB);
+              mrow[u] = rr < hi ? base[rr * W] : make_uint4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              uint32_t in[8];
+#pragma unroll
+              for (int u = 0; u < 8; ++u)
+                in[u] = c == 0 ? mrow[u].x : (c == 1 ? mrow[u].y : (c == 2 ? mrow[u].z : mrow[u].w));
+              uint32_t t0, t1, t2, t3, f0, f1, e;
+              CSA(cnt[c][0], t0, cnt[c][0], in[0], in[1]);
+              CSA(cnt[c][0], t1, cnt[c][0], in[2], in[3]);
+              CSA(cnt[c][1], f0, cnt[c][1], t0, t1);
+              CSA(cnt[c][0], t2, cnt[c][0], in[4], in[5]);
+              CSA(cnt[c][0], t3, cnt[c][0], in[6], in[7]);
+              CSA(cnt[c][1], f1, cnt[c][1], t2, t3);
+              CSA(cnt[c][2], e, cnt[c][2], f0, f1);
+#pragma unroll
+              for (int l = 3; l < NLEV; ++l) {
+                const uint32_t t = cnt[c][l] & e;
+                cnt[c][l] ^= e;
+                e = t;
+              }
+            }
           }
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
-            uint32_t in[8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u)
-              in[u] = c == 0 ? mrow[u].x : (c == 1 ? mrow[u].y : (c == 2 ? mrow[u].z : mrow[u].w));
-            uint32_t t0, t1, t2, t3, f0, f1, e;
-            CSA(cnt[c][0], t0, cnt[c][0], in[0], in[1]);
-            CSA(cnt[c][0], t1, cnt[c][0], in[2], in[3]);
-            CSA(cnt[c][1], f0, cnt[c][1], t0, t1);
-            CSA(cnt[c][0], t2, cnt[c][0], in[4], in[5]);
-            CSA(cnt[c][0], t3, cnt[c][0], in[6], in[7]);
-            CSA(cnt[c][1], f1, cnt[c][1], t2, t3);
-            CSA(cnt[c][2], e, cnt[c][2], f0, f1);
+            for (int step = 0; step < 2; ++step) {
+              uint32_t carry = 0;
 #pragma unroll
-            for (int l = 3; l < NLEV; ++l) {
-              const uint32_t t = cnt[c][l] & e;
-              cnt[c][l] ^= e;
-              e = t;
+              for (int l = 0; l < NLEV + step; ++l) {
+                const uint32_t y = __shfl_xor_sync(0xffffffffu, cnt[c][l], 1 << step);
+                CSA(cnt[c][l], carry, cnt[c][l], y, carry);
+              }
+              cnt[c][NLEV + step] = carry;
             }
           }
-          n_lane += 8;
+          uint32_t* vc = reinterpret_cast<uint32_t*>(s_vc) + col * 4 + ksub;
+          uint32_t carry = 0;
+#pragma unroll
+          for (int l = 0; l < VCL; ++l) {
+            if (l >= XLEV && !__any_sync(0xffffffffu, carry != 0)) break;
+            const uint32_t mine = l >= XLEV ? 0u : (ksub == 0 ? cnt[0][l < XLEV ? l : 0]
+                                  : (ksub == 1 ? cnt[1][l < XLEV ? l : 0]
+                                  : (ksub == 2 ? cnt[2][l < XLEV ? l : 0] : cnt[3][l < XLEV ? l : 0])));
+            const uint32_t a = vc[l * NCOL * 4];
+            uint32_t sum;
+            CSA(sum, carry, a, mine, carry);
+            vc[l * NCOL * 4] = sum;
+          }
         }
       }
-      // a lane takes at most LANE_ROWS_MAX (+7 padding) rows per round: merge before 511 can be passed
-      if (__any_sync(0xffffffffu, n_lane > 511u - (LANE_ROWS_MAX + 8))) flush();
     }
-    flush();
     expand(accumulate, true);
 
     // ---- per-tile stats -> per-species stats
@@ -529,26 +545,18 @@ __global__ void __launch_bounds__(256) k_long_reads(const LongParams p) {
     if (!keep) continue;
     const bool simple = (fl & MB_RF_SIMPLE) != 0;
     const uint32_t* __restrict__ rec = simple ? p.cigar : p.cigar + __ldg(p.cplx + r);
-    const uint32_t n_ops = simple ? 1u : __ldg(rec);
-    uint32_t qpos = simple ? qstart : 0u, x = loc;
-    for (uint32_t o = 0; o < n_ops; ++o) {
-      const uint32_t cw = simple ? (span << 4) : __ldg(rec + 1 + o);
-      const uint32_t op = cw & 0xfu, len = cw >> 4;
-      if (op == mb::OP_M || op == mb::OP_EQ || op == mb::OP_X) {
-        for (uint32_t i = lane; i < len; i += 32) {
-          const uint32_t qi = qpos + i;
-          if (__ldg(q + qi) >= p.qthr) {
-            const uint32_t sw = __ldg(p.seq2 + b0 + (qi >> 4)), bi = qi & 15u;
-            const uint32_t cd = ((sw >> bi) & 1u) | (((sw >> (16 + bi)) & 1u) << 1);
-            atomicAdd(p.counts + (size_t)cd * p.gpad + x + i, 1u);
-          }
+    const uint32_t n_runs = simple ? 1u : __ldg(rec);
+    for (uint32_t o = 0; o < n_runs; ++o) {
+      const uint32_t w0 = simple ? (qstart | (span << 16)) : __ldg(rec + 1 + 2 * o);
+      const uint32_t x0 = simple ? 0u : __ldg(rec + 2 + 2 * o);
+      const uint32_t q0 = w0 & 0xffffu, len = w0 >> 16;
+      for (uint32_t i = lane; i < len; i += 32) {
+        const uint32_t qi = q0 + i;
+        if (__ldg(q + qi) >= p.qthr) {
+          const uint32_t sw = __ldg(p.seq2 + b0 + (qi >> 4)), bb = qi & 15u;
+          const uint32_t cd = ((sw >> bb) & 1u) | (((sw >> (16 + bb)) & 1u) << 1);
+          atomicAdd(p.counts + (size_t)cd * p.gpad + loc + x0 + i, 1u);
         }
-        qpos += len;
-        x += len;
-      } else if (op == mb::OP_I || op == mb::OP_S) {
-        qpos += len;
-      } else if (op == mb::OP_D || op == mb::OP_N) {
-        x += len;
       }
     }
   }
@@ -590,7 +598,7 @@ __global__ void __launch_bounds__(256) k_restat(const uint32_t* __restrict__ cou
 }
 
 size_t pile_smem_bytes(uint32_t W, uint32_t rmax) {
-  return sizeof(uint4) * ((size_t)VCL * NCOL + rmax + (size_t)rmax * W);
+  return sizeof(uint4) * ((size_t)VCL * NCOL + rmax + (size_t)rmax * W) + sizeof(uint32_t) * rmax;
 }
 
 }  // namespace
@@ -626,7 +634,7 @@ extern "C" int mb_snps_pileup_dev(mb_ctx* ctx, const mb_dev_reads* reads, const 
     ctx->pile_occ = occ > 0 ? occ : 1;
   }
   const size_t fixed = sizeof(uint4) * (size_t)VCL * NCOL;
-  uint32_t rmax = (uint32_t)((ctx->pile_smem - fixed) / (sizeof(uint4) * (W + 1)));
+  uint32_t rmax = (uint32_t)((ctx->pile_smem - fixed) / (sizeof(uint4) * (W + 1) + sizeof(uint32_t)));
   if (rmax > (uint32_t)LANE_ROWS_MAX * KSUB) rmax = LANE_ROWS_MAX * KSUB;
   rmax &= ~7u;
   cudaStream_t st = ctx->stream;
@@ -655,9 +663,10 @@ extern "C" int mb_snps_pileup_dev(mb_ctx* ctx, const mb_dev_reads* reads, const 
   p.W = W;
   p.G = 32u / W;
   p.rmax = rmax;
-  p.mapid = f->mapid;
-  p.aln_cov = f->aln_cov;
-  p.readq = f->readq;
+  rc = mb::get_filter_tables(ctx, f, &p.t_pid, &p.t_cov);
+  if (rc) return rc;
+  p.pid_always = (f->mapid != f->mapid || f->mapid == -HUGE_VAL) ? 1u : 0u;
+  p.readq_eff = f->readq <= 0 ? 0u : (f->readq > 128 ? 128u : (uint32_t)f->readq);
   p.mapq = f->mapq;
   p.qadd = (0x80u - (uint32_t)f->baseq) * 0x01010101u;
   p.defer_restat = reads->n_long ? 1u : 0u;

@@ -12,6 +12,7 @@
  *                           midas/run/snps.py:194-199  pysam count_coverage() call site
  *   mb_genes_coverage*   <- midas/run/genes.py:171-203 count_mapped_bp()
  *                           midas/run/genes.py:153-169 keep_read()
+ *   mb_format_snps_rows  <- midas/run/snps.py:179-182,201-210 (row text of <species>.snps.gz)
  *   mb_pack_reads        <- what pysam/htslib hands to those loops (decoded BAM
  *                           records), re-laid as the struct-of-arrays the GPU reads
  *
@@ -177,7 +178,8 @@ void mb_packed_free(mb_packed_reads* p);
 typedef struct mb_ctx mb_ctx;
 int mb_ctx_create(int device, mb_ctx** out);
 void mb_ctx_destroy(mb_ctx* ctx);
-int mb_ctx_set_stream(mb_ctx* ctx, void* cuda_stream); /* cudaStream_t; NULL = context-owned stream */
+int mb_ctx_set_stream(mb_ctx* ctx, void* cuda_stream); /* cudaStream_t; NULL = context-owned stream
+                                                          (pass cudaStreamLegacy, (void*)1, for the default stream) */
 int mb_ctx_sync(mb_ctx* ctx);
 int mb_ctx_device(const mb_ctx* ctx);
 /* kernels launched by this context since creation (for bench.py gpu_launches) */
@@ -235,6 +237,17 @@ int mb_genes_coverage_dev(mb_ctx* ctx, const mb_dev_reads* reads, const uint32_t
 int mb_genes_coverage(mb_ctx* ctx, const mb_packed_reads* reads, const uint32_t* gene_len_host,
                       uint32_t n_genes, const mb_filters* f, int exact_order,
                       mb_gene_out* out_host);
+
+/* ------------------------------------------------------------- text output */
+/* Rows of <species>.snps.gz for n_rows consecutive positions of one contig, starting at 0-based
+ * position first_pos0 (reference midas/run/snps.py:201-210):
+ *   ref_id \t ref_pos \t ref_allele \t depth \t count_a \t count_c \t count_g \t count_t \n
+ * count_x point at the first of the n_rows counters of each plane, ref_bases at the upper-cased
+ * reference characters. Returns the number of bytes written (< 0: mb_status). Host only. */
+uint64_t mb_format_snps_bound(uint64_t name_len, uint64_t n_rows);
+int64_t mb_format_snps_rows(const char* contig_name, const uint8_t* ref_bases, uint64_t first_pos0,
+                            uint64_t n_rows, const uint32_t* count_a, const uint32_t* count_c,
+                            const uint32_t* count_g, const uint32_t* count_t, char* out, uint64_t cap);
 
 #ifdef __cplusplus
 }

@@ -11,6 +11,8 @@
 //   B. the qualities of the reads that survived A are summed 16 lanes per read with 128-bit loads
 //      (mean-quality test genes.py:160; exact integer form sum(q) >= readq*l_qseq);
 //   C. lane i issues read i's atomics: (aligned,mapped) as one packed u64 add, mapped_bp as another.
+#include <cub/device/device_radix_sort.cuh>
+
 #include "common.h"
 
 namespace {
@@ -23,6 +25,8 @@ struct GeneParams {
   const uint8_t* qual;
   uint64_t n_reads;
   unsigned long long* out;  // mb_gene_out as 3 x u64: [aligned|mapped<<32], mapped_bp, depth bits
+  uint32_t* key;            // exact order: per read, gene index if kept else 0xFFFFFFFF (may be null)
+  uint32_t* val;            // exact order: per read, aligned length
   uint32_t n_genes;
   double mapid, aln_cov;
   int readq, mapq;
@@ -86,6 +90,10 @@ __global__ void __launch_bounds__(GENE_THREADS) k_genes_v1(const GeneParams p) {
       unsigned long long* o = p.out + (size_t)gene * 3;
       atomicAdd(o, 1ull | ((unsigned long long)(keep ? 1u : 0u) << 32));  // genes.py:181-182,187-188
       if (keep) atomicAdd(o + 1, (unsigned long long)alen);                  // numerator of genes.py:189
+      if (p.key) { p.key[r] = keep ? gene : 0xFFFFFFFFu; p.val[r] = alen; }
+    } else if (valid && p.key) {
+      p.key[r] = 0xFFFFFFFFu;
+      p.val[r] = 0;
     }
   }
 }
@@ -99,6 +107,25 @@ __global__ void k_genes_finalize(unsigned long long* out, const uint32_t* __rest
   out[(size_t)g * 3 + 2] = (unsigned long long)__double_as_longlong(depth);
 }
 
+// exact_order: the reference adds len(query_alignment_sequence)/float(gene.length) to gene.depth
+// once per kept record in BAM file order (genes.py:178-189). After a stable sort by gene the kept
+// reads of a gene are contiguous and still in file order; one thread per gene repeats the same
+// sequence of IEEE-754 double divisions and additions.
+__global__ void k_genes_exact(const uint32_t* __restrict__ key, const uint32_t* __restrict__ val, uint64_t n_reads,
+                              unsigned long long* out, const uint32_t* __restrict__ gene_len, uint32_t n_genes) {
+  uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_genes) return;
+  uint64_t lo = 0, hi = n_reads;
+  while (lo < hi) {
+    const uint64_t mid = lo + ((hi - lo) >> 1);
+    if (key[mid] < g) lo = mid + 1; else hi = mid;
+  }
+  const double gl = (double)gene_len[g];
+  double depth = 0.0;
+  for (uint64_t i = lo; i < n_reads && key[i] == g; ++i) depth = __dadd_rn(depth, __ddiv_rn((double)val[i], gl));
+  out[(size_t)g * 3 + 2] = (unsigned long long)__double_as_longlong(depth);
+}
+
 }  // namespace
 
 static_assert(sizeof(mb_gene_out) == 24, "mb_gene_out must be 24 bytes");
@@ -107,9 +134,23 @@ extern "C" int mb_genes_coverage_dev(mb_ctx* ctx, const mb_dev_reads* reads, con
                                      uint32_t n_genes, const mb_filters* f, int exact_order, mb_gene_out* out_dev) {
   if (!ctx || !reads || !gene_len_dev || !f || !out_dev)
     return mb::fail(MB_EINVAL, "mb_genes_coverage_dev: null argument");
-  if (exact_order) return mb::fail(MB_EINVAL, "mb_genes_coverage_dev: exact_order=1 is not implemented yet");
   MB_CUDA_TRY(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
+  uint32_t *key = nullptr, *val = nullptr, *key2 = nullptr, *val2 = nullptr;
+  void* tmp = nullptr;
+  size_t tmp_bytes = 0;
+  const uint64_t n = reads->n_reads;
+  if (exact_order && n) {
+    if (n > 0x7fffffffull) return mb::fail(MB_EOVERFLOW, "mb_genes_coverage_dev: exact_order supports < 2^31 reads");
+    void* b[4];
+    for (int k = 0; k < 4; ++k) { int rc = mb::ctx_reserve(ctx, 4 + k, sizeof(uint32_t) * n, &b[k]); if (rc) return rc; }
+    key = (uint32_t*)b[0]; val = (uint32_t*)b[1]; key2 = (uint32_t*)b[2]; val2 = (uint32_t*)b[3];
+    MB_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, key, key2, val, val2, (int)n, 0, 32, st));
+    void* t = nullptr;
+    int rc = mb::ctx_reserve(ctx, 15, tmp_bytes, &t);
+    if (rc) return rc;
+    tmp = t;
+  }
   MB_CUDA_TRY(cudaMemsetAsync(out_dev, 0, sizeof(mb_gene_out) * (size_t)n_genes, st));
   GeneParams p;
   p.hdr = reinterpret_cast<const uint4*>(reads->hdr);
@@ -117,6 +158,8 @@ extern "C" int mb_genes_coverage_dev(mb_ctx* ctx, const mb_dev_reads* reads, con
   p.qual = reads->qual;
   p.n_reads = reads->n_reads;
   p.out = reinterpret_cast<unsigned long long*>(out_dev);
+  p.key = key;
+  p.val = val;
   p.n_genes = n_genes;
   p.mapid = f->mapid;
   p.aln_cov = f->aln_cov;
@@ -133,6 +176,11 @@ extern "C" int mb_genes_coverage_dev(mb_ctx* ctx, const mb_dev_reads* reads, con
   if (n_genes) {
     k_genes_finalize<<<(n_genes + 255) / 256, 256, 0, st>>>(p.out, gene_len_dev, n_genes);
     ctx->launches++;
+    if (exact_order && n) {
+      MB_CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, key, key2, val, val2, (int)n, 0, 32, st));
+      k_genes_exact<<<(n_genes + 127) / 128, 128, 0, st>>>(key2, val2, n, p.out, gene_len_dev, n_genes);
+      ctx->launches++;
+    }
   }
   MB_CUDA_TRY(cudaGetLastError());
   return MB_OK;

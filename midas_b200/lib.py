@@ -65,6 +65,7 @@ EXPORTS = [
     "mb_ctx_launch_count", "mb_ctx_last_kernel_ms", "mb_ctx_timing_reset", "mb_ctx_timing_read",
     "mb_reads_upload", "mb_reads_free", "mb_reads_bytes",
     "mb_snps_pileup_dev", "mb_snps_pileup", "mb_genes_coverage_dev", "mb_genes_coverage",
+    "mb_format_snps_bound", "mb_format_snps_rows",
 ]
 
 _lib = None
@@ -118,6 +119,11 @@ def load():
                                         C.c_int, C.c_void_p]
     L.mb_genes_coverage.argtypes = [C.c_void_p, C.POINTER(CPackedReads), C.c_void_p, C.c_uint32,
                                     C.POINTER(CFilters), C.c_int, C.c_void_p]
+    L.mb_format_snps_bound.restype = C.c_uint64
+    L.mb_format_snps_bound.argtypes = [C.c_uint64, C.c_uint64]
+    L.mb_format_snps_rows.restype = C.c_int64
+    L.mb_format_snps_rows.argtypes = [C.c_char_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
     _lib = L
     return L
 
@@ -331,3 +337,21 @@ class Context:
         _check(load().mb_genes_coverage(self._h, packed._p, _ptr(gene_len), len(gene_len), C.byref(f),
                                         int(exact_order), _ptr(out)))
         return out
+
+
+def format_snps_rows(contig_name: str, ref_bases: np.ndarray, first_pos0: int, counts4: np.ndarray) -> bytes:
+    """Text rows of <species>.snps.gz (reference snps.py:201-210) for counts4 = uint32 [4][n] of one
+    contig starting at 0-based position first_pos0; ref_bases = uint8 [n] upper-cased characters."""
+    L = load()
+    n = int(counts4.shape[1])
+    assert counts4.dtype == np.uint32 and counts4.shape[0] == 4 and ref_bases.dtype == np.uint8 and len(ref_bases) == n
+    planes = [np.ascontiguousarray(counts4[k]) for k in range(4)]
+    ref_bases = np.ascontiguousarray(ref_bases)
+    name = contig_name.encode()
+    cap = int(L.mb_format_snps_bound(len(name), n))
+    buf = C.create_string_buffer(max(cap, 1))
+    w = L.mb_format_snps_rows(name, _ptr(ref_bases), int(first_pos0), n, _ptr(planes[0]), _ptr(planes[1]),
+                              _ptr(planes[2]), _ptr(planes[3]), buf, cap)
+    if w < 0:
+        _check(int(w))
+    return buf.raw[:w]

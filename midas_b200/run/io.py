@@ -1,0 +1,69 @@
+"""File helpers shared by the run mirrors: the reference's iopen (midas/utility.py:194-206), a FASTA
+reader with Bio.SeqIO.parse(handle, 'fasta') semantics (record id = first whitespace token), and a
+multi-member gzip writer (only the decompressed bytes are part of the on-disk contract)."""
+from __future__ import annotations
+
+import bz2
+import gzip
+import io
+import zlib
+from concurrent.futures import ThreadPoolExecutor
+
+
+def iopen(inpath, mode="r"):
+    """Open by extension, text mode (reference midas/utility.py:194-206, Python 3 branch)."""
+    ext = inpath.split(".")[-1]
+    if ext == "gz":
+        return io.TextIOWrapper(gzip.open(inpath, mode))
+    if ext == "bz2":
+        return bz2.open(inpath, mode + "t" if "t" not in mode and "b" not in mode else mode)
+    return open(inpath, mode)
+
+
+def read_fasta(path):
+    """Yield (id, sequence) like Bio.SeqIO.parse(handle, 'fasta') (reference snps.py:59-62, genes.py:68-71)."""
+    fh = iopen(path)
+    title, chunks = None, []
+    for line in fh:
+        if line.startswith(">"):
+            if title is not None:
+                yield (title.split(None, 1)[0] if title.split() else ""), "".join(chunks)
+            title, chunks = line[1:].rstrip("\r\n"), []
+        elif title is not None:
+            chunks.append(line.strip().replace(" ", ""))
+    if title is not None:
+        yield (title.split(None, 1)[0] if title.split() else ""), "".join(chunks)
+    fh.close()
+
+
+def _member(data: bytes, level: int) -> bytes:
+    co = zlib.compressobj(level, zlib.DEFLATED, 31)   # wbits 31 = gzip container
+    return co.compress(data) + co.flush()
+
+
+class GzipMembersWriter:
+    """Writes a .gz file as a sequence of independently compressed members, compressing up to
+    `threads` chunks at a time (zlib releases the GIL). `gzip.open(path).read()` sees one stream."""
+
+    def __init__(self, path, level=6, threads=8):
+        self.fh = open(path, "wb")
+        self.level = level
+        self.pool = ThreadPoolExecutor(max(1, threads))
+        self.pending = []
+        self.max_pending = 2 * max(1, threads)
+
+    def write(self, data: bytes):
+        if not data:
+            return
+        self.pending.append(self.pool.submit(_member, data, self.level))
+        while len(self.pending) > self.max_pending:
+            self.fh.write(self.pending.pop(0).result())
+
+    def close(self):
+        for f in self.pending:
+            self.fh.write(f.result())
+        self.pending = []
+        self.pool.shutdown()
+        if self.fh.tell() == 0:
+            self.fh.write(_member(b"", self.level))
+        self.fh.close()

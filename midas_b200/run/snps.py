@@ -1,0 +1,222 @@
+"""`run_midas.py snps` pileup stage on the B200 — mirror of the reference's midas/run/snps.py.
+
+Same names and meaning as the reference module:
+  Species, Contig, initialize_species (snps.py:38-53), initialize_contigs (:55-67),
+  index_bam (:130-139, a no-op here), pysam_pileup (:219-244), snps_summary (:247-262),
+  run_pipeline (:268-306).
+`pysam_pileup(args, species, contigs)` keeps its signature and side effects (per-species
+`<outdir>/snps/output/<species>.snps.gz`, Species.{genome_length, covered_bases, total_depth,
+aligned_reads, mapped_reads, fraction_covered, mean_coverage}), but instead of one forked worker per
+species walking pysam (utility.parallel, midas/utility.py:81-107) it decodes the BAM once, packs
+the reads of all species into one struct-of-arrays and makes ONE call into libmidas_b200.so
+(mb_snps_pileup) from the parent process. There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import sys
+from time import time
+
+import numpy as np
+
+from .. import bam, lib
+from ..soa import Filters, RefSet
+from . import io as mio
+
+CHUNK_ROWS = 1 << 18
+
+
+class Species:
+    """Base class for species (reference snps.py:12-31)."""
+
+    def __init__(self, id):
+        self.id = id
+        self.paths = {}
+        self.aligned_reads = 0
+        self.mapped_reads = 0
+        self.genome_length = 0
+        self.covered_bases = 0
+        self.total_depth = 0
+        self.fraction_covered = 0
+        self.mean_coverage = 0
+
+    def fetch_paths(self, ref_db):
+        indir = "%s/rep_genomes/%s" % (ref_db, self.id)
+        for ext in ["", ".gz"]:
+            for type in ["fna", "features"]:
+                path = "%s/genome.%s%s" % (indir, type, ext)
+                if os.path.isfile(path):
+                    self.paths[type] = path
+
+
+class Contig:
+    """Base class for contig (reference snps.py:33-36)."""
+
+    def __init__(self, id):
+        self.id = id
+
+
+def initialize_species(args):
+    """reference snps.py:38-53; species selection from a species profile (--build_db) is upstream of
+    the hot path and not part of this package."""
+    species = {}
+    splist = "%s/snps/species.txt" % args["outdir"]
+    if args.get("build_db"):
+        sys.exit("\nError: the --build_db stage (species selection, bowtie2-build) is not part of midas_b200; "
+                 "run it with the reference and re-enter with --pileup")
+    elif os.path.isfile(splist):
+        for line in open(splist):
+            id = line.rstrip()
+            species[id] = Species(id)
+    for sp in species.values():
+        sp.fetch_paths(ref_db=args["db"])
+    return species
+
+
+def initialize_contigs(species):
+    """reference snps.py:55-67 (dict keyed by contig id across all species; later ids overwrite)."""
+    contigs = {}
+    for sp in species.values():
+        for rec_id, seq in mio.read_fasta(sp.paths["fna"]):
+            contig = Contig(rec_id)
+            contig.seq = seq.upper()
+            contig.length = len(contig.seq)
+            contig.species_id = sp.id
+            contigs[contig.id] = contig
+    return contigs
+
+
+def index_bam(args):
+    """reference snps.py:130-139 runs `samtools index`; the GPU path buckets reads by reference id
+    itself and needs no index."""
+    return None
+
+
+def _filters(args) -> Filters:
+    return Filters(float(args["mapid"]), float(args["aln_cov"]), int(args["readq"]), int(args["mapq"]),
+                   int(args["baseq"]))
+
+
+def build_refset(species, contigs):
+    """Contigs in the order species_pileup visits them (sorted ids, snps.py:187), grouped by species."""
+    sp_ids = list(species.keys())
+    sp_index = {s: k for k, s in enumerate(sp_ids)}
+    ids = [cid for cid in sorted(contigs.keys()) if contigs[cid].species_id in sp_index]
+    if any(contigs[c].length == 0 for c in ids):
+        raise lib.MidasB200Error(-1, "a reference contig has length 0 (pysam: ValueError, interval of size 0)")
+    ref = RefSet(ids, np.array([contigs[c].length for c in ids], np.uint32),
+                 np.array([sp_index[contigs[c].species_id] for c in ids], np.int32), sp_ids, None)
+    return ref
+
+
+def load_alignments(bampath, ref: RefSet):
+    """Decode the BAM and re-index its reference ids onto `ref` (records on references that are not
+    contigs of a selected species are never fetched by the reference, snps.py:190-199)."""
+    names, lens, reads = bam.read_bam(bampath)
+    index = {n: k for k, n in enumerate(ref.contig_names)}
+    tid_map = np.array([index.get(n, -1) for n in names], np.int32) if names else np.zeros(0, np.int32)
+    for n, l in zip(names, lens):
+        k = index.get(n)
+        if k is not None and int(ref.contig_len[k]) != int(l):
+            raise lib.MidasB200Error(-5, f"BAM header length of {n} ({l}) != FASTA length ({int(ref.contig_len[k])})")
+    new_id = tid_map[reads.ref_id] if reads.n_reads else reads.ref_id
+    keep = np.nonzero(new_id >= 0)[0]
+    if len(keep) != reads.n_reads:
+        reads = reads.select(keep)
+        new_id = new_id[keep]
+    reads.ref_id = np.ascontiguousarray(new_id, np.int32)
+    return reads
+
+
+def write_species_tsv(path, ref: RefSet, contigs, layout, counts, species_index, threads=8):
+    """<species>.snps.gz (reference snps.py:179-182 header, :201-210 rows)."""
+    out = mio.GzipMembersWriter(path, threads=threads)
+    out.write(b"ref_id\tref_pos\tref_allele\tdepth\tcount_a\tcount_c\tcount_g\tcount_t\n")
+    for c, cid in enumerate(ref.contig_names):
+        if int(ref.contig_species[c]) != species_index:
+            continue
+        seq = np.frombuffer(contigs[cid].seq.encode("latin-1"), np.uint8)
+        view = layout.contig_counts(counts, c)
+        n = int(ref.contig_len[c])
+        for lo in range(0, n, CHUNK_ROWS):
+            hi = min(n, lo + CHUNK_ROWS)
+            out.write(lib.format_snps_rows(cid, seq[lo:hi], lo, view[:, lo:hi]))
+    out.close()
+
+
+def pysam_pileup(args, species, contigs, ctx=None):
+    """reference snps.py:219-244. One GPU call for all species; fills the Species stats and writes
+    one <species>.snps.gz per species."""
+    start = time()
+    print("\nCounting alleles")
+    args["log"].write("\nCounting alleles\n")
+    own_ctx = ctx is None
+    if own_ctx:
+        ctx = lib.Context(int(args.get("device", 0)), use_torch_stream=False)
+    try:
+        ref = build_refset(species, contigs)
+        bampath = "%s/snps/temp/genomes.bam" % args["outdir"]
+        reads = load_alignments(bampath, ref)
+        layout = lib.Layout.of(ref)
+        packed = lib.PackedReads(reads, layout, "snps", sort=True, pinned=False)
+        counts, stats = ctx.snps_pileup(packed, layout, _filters(args))
+        threads = int(args.get("threads", 1) or 1)
+        for k, species_id in enumerate(ref.species_ids):
+            out_path = "%s/snps/output/%s.snps.gz" % (args["outdir"], species_id)
+            write_species_tsv(out_path, ref, contigs, layout, counts, k, threads=threads)
+            sp = species[species_id]
+            sp.genome_length = int(stats["genome_length"][k])
+            sp.covered_bases = int(stats["covered_bases"][k])
+            sp.total_depth = int(stats["total_depth"][k])
+            sp.aligned_reads = int(stats["aligned_reads"][k])
+            sp.mapped_reads = int(stats["mapped_reads"][k])
+            if sp.genome_length > 0:
+                sp.fraction_covered = sp.covered_bases / float(sp.genome_length)
+            if sp.covered_bases > 0:
+                sp.mean_coverage = sp.total_depth / float(sp.covered_bases)
+    finally:
+        if own_ctx:
+            ctx.close()
+    print("  %s minutes" % round((time() - start) / 60, 2))
+
+
+def snps_summary(args, species):
+    """reference snps.py:247-262 (numbers formatted with str(), as there)."""
+    fields = ["species_id", "genome_length", "covered_bases", "fraction_covered", "mean_coverage",
+              "aligned_reads", "mapped_reads"]
+    outfile = open(args["outdir"] + "/snps/summary.txt", "w")
+    outfile.write("\t".join(fields) + "\n")
+    for sp in species.values():
+        outfile.write(sp.id + "\t")
+        outfile.write(str(sp.genome_length) + "\t")
+        outfile.write(str(sp.covered_bases) + "\t")
+        outfile.write(str(sp.fraction_covered) + "\t")
+        outfile.write(str(sp.mean_coverage) + "\t")
+        outfile.write(str(sp.aligned_reads) + "\t")
+        outfile.write(str(sp.mapped_reads) + "\n")
+    outfile.close()
+
+
+def remove_tmp(args):
+    shutil.rmtree("/".join([args["outdir"], "snps/temp"]))
+
+
+def run_pipeline(args):
+    """reference snps.py:268-306. Only the pileup stage (args['call']) runs here; bowtie2-build /
+    bowtie2 alignment stay with the reference (host-side, out of scope)."""
+    print("\nReading reference data")
+    start = time()
+    species = initialize_species(args)
+    contigs = initialize_contigs(species)
+    print("  %s minutes" % round((time() - start) / 60, 2))
+    if args.get("align"):
+        sys.exit("\nError: the --align stage (bowtie2 | samtools) is not part of midas_b200; "
+                 "run it with the reference and re-enter with --pileup")
+    if args.get("call"):
+        index_bam(args)
+        pysam_pileup(args, species, contigs)
+        snps_summary(args, species)
+    if args.get("remove_temp"):
+        remove_tmp(args)
+    return species

@@ -1,0 +1,126 @@
+"""CPU: the host packer (mb_pack_reads) - geometry fields, block encoding, run records, row width,
+ordering, and the inputs on which the reference itself raises."""
+import numpy as np
+import pytest
+
+import gen
+from midas_b200 import lib, synth
+from midas_b200.soa import PlainReads, cigar_tuples, OP_M, OP_I, OP_D, OP_N, OP_S, OP_H, OP_EQ, OP_X, OP_P
+
+
+def _one(cigar, seq=None, qual=None, pos=10, nm=0, mapq=30, lq=None):
+    lq = lq if lq is not None else sum(l for o, l in cigar if o in (OP_M, OP_I, OP_S, OP_EQ, OP_X))
+    seq = seq if seq is not None else [1, 2, 4, 8] * (lq // 4) + [1] * (lq % 4)
+    qual = qual if qual is not None else [30] * lq
+    return PlainReads.from_records([dict(ref_id=0, pos=pos, mapq=mapq, nm=nm, cigar=cigar, seq=seq, qual=qual)])
+
+
+LAY = None
+
+
+def lay():
+    global LAY
+    if LAY is None:
+        LAY = lib.Layout([1000], [0], 1)
+    return LAY
+
+
+def test_geometry_fields_follow_pysam_query_alignment():
+    r = _one([(OP_H, 3), (OP_S, 5), (OP_M, 20), (OP_I, 2), (OP_M, 10), (OP_D, 4), (OP_M, 8), (OP_S, 7), (OP_H, 2)])
+    pk = lib.PackedReads(r, lay(), "snps")
+    h = pk.hdr[0]
+    assert h["l_qseq"] == 52 and h["q_start"] == 5 and h["alen"] == 40       # snps.py:145-146
+    assert h["ref_span"] == 42 and h["loc"] == 10 and not (h["flags"] & 1)
+    rec = pk.cigar[int(pk.cplx[0]):]
+    assert rec[0] == 3
+    runs = [(int(rec[1 + 2 * k]) & 0xFFFF, int(rec[1 + 2 * k]) >> 16, int(rec[2 + 2 * k])) for k in range(3)]
+    assert runs == [(5, 20, 0), (27, 10, 20), (37, 8, 34)]                   # (q0, len, x0)
+
+
+def test_simple_reads_and_soft_clips():
+    pk = lib.PackedReads(_one([(OP_S, 4), (OP_EQ, 30), (OP_S, 2)]), lay(), "snps")
+    h = pk.hdr[0]
+    assert h["flags"] & 1 and h["q_start"] == 4 and h["alen"] == 30 and h["ref_span"] == 30
+    assert pk.cplx[0] == 0xFFFFFFFF and pk.row_words >= 2
+
+
+def test_contig_end_overhang_is_clipped():
+    pk = lib.PackedReads(_one([(OP_M, 50)], pos=980), lay(), "snps")
+    assert pk.hdr[0]["ref_span"] == 20 and pk.hdr[0]["alen"] == 50
+    pk = lib.PackedReads(_one([(OP_M, 30), (OP_D, 5), (OP_M, 20)], pos=960), lay(), "snps")
+    rec = pk.cigar[int(pk.cplx[0]):]
+    assert rec[0] == 2 and (int(rec[3]) >> 16) == 5 and rec[4] == 35 and pk.hdr[0]["ref_span"] == 40
+
+
+def test_block_encoding_round_trips():
+    ref, reads = synth.synth_snps(seed=5, n_species=1, contigs_per_species=1, contig_len=5000, n_reads=300, read_len=77)
+    pk = lib.PackedReads(reads, lib.Layout.of(ref), "snps")
+    assert pk.n_reads == 300 and pk.total_bases == 300 * 77
+    blk, seq2, qual = pk.blk_off, pk.seq2, pk.qual
+    nib = np.array([1, 2, 4, 8])
+    for i in (0, 17, 299):
+        s0 = int(reads.seq_off[i])
+        for q in range(77):
+            w = int(seq2[int(blk[i]) + q // 16])
+            code = ((w >> (q % 16)) & 1) | (((w >> (16 + q % 16)) & 1) << 1)
+            qb = int(qual[int(blk[i]) * 16 + q])
+            src = int(reads.seq[s0 + q])
+            assert (qb & 0x7F) == int(reads.qual[s0 + q])
+            assert bool(qb & 0x80) == (src in (1, 2, 4, 8))
+            if src in (1, 2, 4, 8):
+                assert nib[code] == src
+        # padding of the last block is zero
+        assert not qual[int(blk[i]) * 16 + 77:int(blk[i + 1]) * 16].any()
+
+
+def test_row_width_and_long_reads():
+    ref, reads = synth.synth_snps(seed=6, n_species=1, contigs_per_species=1, contig_len=30000, n_reads=4000)
+    pk = lib.PackedReads(reads, lib.Layout.of(ref), "snps")
+    assert pk.row_words == 6 and pk.n_long == 0                              # 150 bp + <= 3 bp deletion
+    extra = _one([(OP_M, 40), (OP_D, 900), (OP_M, 40)], pos=100)
+    extra.ref_id[:] = 0
+    both = PlainReads.concat([reads, extra])
+    pk = lib.PackedReads(both, lib.Layout.of(ref), "snps", sort=True)
+    assert pk.row_words == 6 and pk.n_long == 1
+    assert pk.hdr[int(pk.long_idx[0])]["flags"] & 4
+
+
+def test_sorting_and_unsorted_rejection():
+    rng = np.random.default_rng(1)
+    ref = gen.make_ref(rng, 2, 2, 500, 900)
+    reads = gen.random_reads(3, ref, 500, max_len=80, sort=False)
+    L = lib.Layout.of(ref)
+    with pytest.raises(lib.MidasB200Error) as e:
+        lib.PackedReads(reads, L, "snps", sort=False)
+    assert e.value.status == -6
+    pk = lib.PackedReads(reads, L, "snps", sort=True)
+    loc = pk.hdr["loc"]
+    assert (np.diff(loc.astype(np.int64)) >= 0).all()
+    # stable: equal keys keep input order -> same multiset of (loc, l_qseq) as a stable numpy sort
+    key = L.contig_goff[reads.ref_id].astype(np.int64) + reads.pos
+    order = np.argsort(key, kind="stable")
+    assert np.array_equal(pk.hdr["l_qseq"], reads.l_qseq[order].astype(np.uint16))
+
+
+@pytest.mark.parametrize("kw,status", [
+    (dict(nm=-1), -1),                        # KeyError 'NM' (snps.py:148)
+    (dict(cigar=[(OP_S, 10)]), -1),           # aligned length 0 -> ZeroDivisionError (snps.py:148)
+    (dict(cigar=[(OP_M, 5), (OP_P, 1), (OP_M, 5)]), -5),
+    (dict(cigar=[(OP_M, 9)], lq=10), -5),     # CIGAR does not consume the query
+    (dict(qual=[0xFF] + [30] * 9, cigar=[(OP_M, 10)]), -1),   # qualities missing -> np.mean(None)
+    (dict(pos=1000, cigar=[(OP_M, 10)]), -5),
+])
+def test_inputs_on_which_the_reference_raises(kw, status):
+    kw.setdefault("cigar", [(OP_M, 10)])
+    r = _one(**kw)
+    with pytest.raises(lib.MidasB200Error) as e:
+        lib.PackedReads(r, lay(), "snps")
+    assert e.value.status == status
+
+
+def test_genes_mode_keeps_file_order_and_gene_index():
+    gref, greads, _ = synth.synth_genes(seed=9, n_species=2, genes_per_species=30, n_reads=500, read_len=100)
+    pk = lib.PackedReads(greads, lib.Layout.of(gref), "genes")
+    assert np.array_equal(pk.hdr["loc"], greads.ref_id.astype(np.uint32))
+    assert pk.row_words == 0 and pk.n_long == 0
+    assert np.array_equal(pk.hdr["mapq"], greads.mapq)

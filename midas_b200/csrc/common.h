@@ -78,9 +78,12 @@ struct mb_ctx {
   uint64_t launches;
   size_t pile_smem;   // dynamic shared memory per CTA of the pileup kernel (0 = not configured yet)
   int pile_occ;       // resident CTAs per SM at that size
+  uint32_t pile_attr_mask;  // row widths whose kernel instance already has its shared-memory attribute set
   // scratch (grown on demand)
   uint32_t* tile_rng;  // [2*n_tiles]
   size_t tile_rng_cap;
+  const mb_dev_reads* rng_for;  // resident batch the tile index in tile_rng was built for (null: none)
+  uint32_t rng_W, rng_ntiles;
   uint32_t* sched;     // dynamic tile scheduler counters
   // exact integer thresholds of the two floating-point read filters, per alen / l_qseq (see ctx.cu)
   int32_t* ftab;       // device: [2][65536]

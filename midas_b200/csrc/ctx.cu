@@ -145,8 +145,12 @@ extern "C" int mb_ctx_create(int device, mb_ctx** out) {
   c->launches = 0;
   c->pile_smem = 0;
   c->pile_occ = 1;
+  c->pile_attr_mask = 0;
   c->tile_rng = nullptr;
   c->tile_rng_cap = 0;
+  c->rng_for = nullptr;
+  c->rng_W = 0;
+  c->rng_ntiles = 0;
   c->sched = nullptr;
   c->ftab = nullptr;
   c->ftab_valid = false;
@@ -289,7 +293,7 @@ extern "C" int mb_reads_upload(mb_ctx* c, const mb_packed_reads* h, mb_dev_reads
 
 extern "C" void mb_reads_free(mb_ctx* c, mb_dev_reads* d) {
   if (!d) return;
-  if (c) { cudaSetDevice(c->device); cudaStreamSynchronize(c->stream); }
+  if (c) { cudaSetDevice(c->device); cudaStreamSynchronize(c->stream); if (c->rng_for == d) c->rng_for = nullptr; }
   cudaFree(d->hdr);
   cudaFree(d->blk_off);
   cudaFree(d->cplx);

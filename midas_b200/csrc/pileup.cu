@@ -71,7 +71,6 @@ struct PileParams {
   uint64_t gpad;
   uint32_t n_ktiles;
   uint32_t W;                 // row words
-  uint32_t G;                 // reads per warp iteration = 32 / W
   uint32_t rmax;              // rows staged per round
   const int32_t* t_pid;       // [65536] smallest 100*(alen-NM) that passes mapid, per alen
   const int32_t* t_cov;       // [65536] smallest alen that passes aln_cov, per l_qseq
@@ -168,9 +167,11 @@ struct StageIn {
   uint32_t r0a, r0b, r1a, r1b;  // first two runs of a complex read
 };
 
+template <int WT>
 __global__ void __launch_bounds__(NT, 2) k_pileup_v2(const PileParams p) {
   extern __shared__ __align__(16) uint32_t smem[];
-  const uint32_t W = p.W;
+  constexpr uint32_t W = (uint32_t)WT;          // row words (compile time: every per-lane loop below unrolls)
+  constexpr int G = 32 / WT;                    // reads per warp step
   uint4* s_vc = reinterpret_cast<uint4*>(smem);                       // [VCL][NCOL] x {A,C,G,T}
   uint4* s_meta = s_vc + VCL * NCOL;                                  // [rmax]
   uint4* s_rows = s_meta + p.rmax;                                    // [rmax][W] x {A,C,G,T}
@@ -184,11 +185,11 @@ __global__ void __launch_bounds__(NT, 2) k_pileup_v2(const PileParams p) {
   const int col = tid >> 2, ksub = tid & 3;                           // COUNT role
   const int grp = lane / (int)W, gj = lane - grp * (int)W;            // STAGE role
   const int gbase = grp * (int)W;
-  const bool lane_ok = grp < (int)p.G;
+  const bool lane_ok = grp < G;
   const uint32_t bi = 2u * (uint32_t)gj;                              // my first 16-base block of a read
   const uint4* __restrict__ qual_j = p.qual + bi;
   const uint32_t* __restrict__ seq_j = p.seq2 + bi;
-  const int istep = NWARP * (int)p.G;
+  constexpr int istep = NWARP * G;
 
   for (int i = tid; i < VCL * NCOL; i += NT) s_vc[i] = make_uint4(0, 0, 0, 0);
   for (int i = tid; i < NCOL + 2 * WMAX + 1; i += NT) s_mod[i] = (uint8_t)((uint32_t)i % W);
@@ -339,11 +340,7 @@ __global__ void __launch_bounds__(NT, 2) k_pileup_v2(const PileParams p) {
           }
         }
       };
-      StageIn cur;
-      fetch(warp * (int)p.G + grp, cur);
-      for (int i = warp * (int)p.G + grp; i - grp < n; i += istep) {
-        StageIn nxt;
-        fetch(i + istep, nxt);
+      auto process = [&](const int i, const StageIn& cur) {
         const bool rowok = lane_ok && i < n;
         const uint4 m = cur.m;
         const uint32_t lq = m.z & 0xffffu, flags = m.w;
@@ -356,6 +353,7 @@ __global__ void __launch_bounds__(NT, 2) k_pileup_v2(const PileParams p) {
         const uint32_t qh = __byte_perm(cur.sa, cur.sb, 0x7632);   // high bits
         // mean-quality filter (snps.py:151): mean(q) < readq  <=>  sum(q) < readq * l_qseq (exact)
         uint32_t tot = qsum;
+        #pragma unroll
         for (uint32_t d = 1; d < W; d <<= 1) {
           const uint32_t t = __shfl_down_sync(0xffffffffu, tot, d);
           if (gj + (int)d < (int)W) tot += t;
@@ -376,12 +374,7 @@ __global__ void __launch_bounds__(NT, 2) k_pileup_v2(const PileParams p) {
         const uint32_t max_runs = __reduce_max_sync(0xffffffffu, n_runs);
         const int o32 = (int)(m.x & 31u) - 32 * gj;            // row bit of the read's first base, relative to my word
         uint32_t rl = 0, rh = 0, rv = 0;
-        for (uint32_t k = 0; k < max_runs; ++k) {
-          if (k >= 1 && k < n_runs) {
-            const uint32_t* __restrict__ rec = p.cigar + s_cplx[i];
-            if (k == 1) { w0 = cur.r1b; w1 = __ldg(rec + 4); }
-            else { w0 = __ldg(rec + 1 + 2 * k); w1 = __ldg(rec + 2 + 2 * k); }
-          }
+        auto run = [&](const uint32_t k) {                     // all 32 lanes call it together
           const int q0 = (int)(w0 & 0xffffu), len = (int)(w0 >> 16);
           const int p0 = o32 + (int)w1;                        // row bit of the run's first base (my word = 0)
           const int qs = q0 - p0;                              // query index of bit 0 of my row word
@@ -396,13 +389,38 @@ __global__ void __launch_bounds__(NT, 2) k_pileup_v2(const PileParams p) {
             rh |= __funnelshift_r(h0, h1, sh) & msk;
             rv |= __funnelshift_r(v0, v1, sh) & msk;
           }
+        };
+        if (max_runs) run(0);
+        if (max_runs > 1) {                                    // some read of this step has an indel / skip
+          for (uint32_t k = 1; k < max_runs; ++k) {
+            if (k < n_runs) {
+              const uint32_t* __restrict__ rec = p.cigar + s_cplx[i];
+              if (k == 1) { w0 = cur.r1b; w1 = __ldg(rec + 4); }
+              else { w0 = __ldg(rec + 1 + 2 * k); w1 = __ldg(rec + 2 + 2 * k); }
+            }
+            run(k);
+          }
         }
         if (rowok) {
           uint32_t slot = ((flags >> 8) & 0xffu) + (uint32_t)gj;
           if (slot >= W) slot -= W;
           s_rows[(uint32_t)i * W + slot] = make_uint4(rv & ~rh & ~rl, rv & ~rh & rl, rv & rh & ~rl, rv & rh & rl);
         }
-        cur = nxt;
+      };
+      {
+        StageIn sa_, sb_;                                       // ping-pong: no register copies between steps
+        int i = warp * G + grp;
+        fetch(i, sa_);
+        while (true) {
+          fetch(i + istep, sb_);
+          process(i, sa_);
+          i += istep;
+          if (i - grp >= n) break;
+          fetch(i + istep, sa_);
+          process(i, sb_);
+          i += istep;
+          if (i - grp >= n) break;
+        }
       }
       __syncthreads();
       // ---- COUNT: my column's rows of this round, KSUB-strided, 8 rows per carry-save tree into
@@ -597,6 +615,17 @@ __global__ void __launch_bounds__(256) k_restat(const uint32_t* __restrict__ cou
   }
 }
 
+// the row widths the tile kernel is instantiated for; a batch runs at the smallest one >= its row_words
+struct PileKernel { uint32_t W; void (*fn)(const PileParams); };
+PileKernel pick_kernel(uint32_t row_words) {
+  static const PileKernel k[] = {{3, k_pileup_v2<3>},   {4, k_pileup_v2<4>},   {5, k_pileup_v2<5>},  {6, k_pileup_v2<6>},
+                                 {7, k_pileup_v2<7>},   {8, k_pileup_v2<8>},   {10, k_pileup_v2<10>}, {12, k_pileup_v2<12>},
+                                 {16, k_pileup_v2<16>}};
+  for (const PileKernel& e : k)
+    if (e.W >= row_words) return e;
+  return k[sizeof(k) / sizeof(k[0]) - 1];
+}
+
 size_t pile_smem_bytes(uint32_t W, uint32_t rmax) {
   return sizeof(uint4) * ((size_t)VCL * NCOL + rmax + (size_t)rmax * W) + sizeof(uint32_t) * rmax;
 }
@@ -609,8 +638,8 @@ extern "C" int mb_snps_pileup_dev(mb_ctx* ctx, const mb_dev_reads* reads, const 
     return mb::fail(MB_EINVAL, "mb_snps_pileup_dev: null argument");
   if (!reads->sorted) return mb::fail(MB_EUNSORTED, "mb_snps_pileup_dev: reads were not packed in snps (sorted) mode");
   if (f->baseq < 0 || f->baseq > 127) return mb::fail(MB_EINVAL, "mb_snps_pileup_dev: baseq %d outside [0,127]", f->baseq);
-  const uint32_t W = reads->row_words;
-  if (W < 2 || W > (uint32_t)WMAX) return mb::fail(MB_EINVAL, "mb_snps_pileup_dev: row_words %u outside [2,%d]", W, WMAX);
+  if (reads->row_words < 2 || reads->row_words > (uint32_t)WMAX)
+    return mb::fail(MB_EINVAL, "mb_snps_pileup_dev: row_words %u outside [2,%d]", reads->row_words, WMAX);
   MB_CUDA_TRY(cudaSetDevice(ctx->device));
   mb_dev_layout dl;
   int rc = mb::get_dev_layout(ctx, L, &dl);
@@ -620,18 +649,24 @@ extern "C" int mb_snps_pileup_dev(mb_ctx* ctx, const mb_dev_reads* reads, const 
     if (ctx->tile_rng) { MB_CUDA_TRY(cudaStreamSynchronize(ctx->stream)); MB_CUDA_TRY(cudaFree(ctx->tile_rng)); }
     ctx->tile_rng = nullptr;
     ctx->tile_rng_cap = 0;
+    ctx->rng_for = nullptr;
     MB_CUDA_TRY(cudaMalloc(&ctx->tile_rng, sizeof(uint32_t) * ((size_t)2 * n_ktiles + 2)));
     ctx->tile_rng_cap = (size_t)2 * n_ktiles + 2;
   }
   // shared memory per CTA: two CTAs per SM (override with MB_PILE_SMEM_KB for experiments)
+  const PileKernel kern = pick_kernel(reads->row_words);
+  const uint32_t W = kern.W;                                          // instantiated row width >= row_words
   if (!ctx->pile_smem) {
     size_t kb = 100;
     if (const char* e = getenv("MB_PILE_SMEM_KB")) { long v = atol(e); if (v >= 32 && v <= 220) kb = (size_t)v; }
     ctx->pile_smem = kb * 1024;
-    MB_CUDA_TRY(cudaFuncSetAttribute(k_pileup_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->pile_smem));
+  }
+  if (!(ctx->pile_attr_mask & (1u << W))) {
+    MB_CUDA_TRY(cudaFuncSetAttribute(kern.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->pile_smem));
     int occ = 0;
-    MB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pileup_v2, NT, ctx->pile_smem));
+    MB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern.fn, NT, ctx->pile_smem));
     ctx->pile_occ = occ > 0 ? occ : 1;
+    ctx->pile_attr_mask |= 1u << W;
   }
   const size_t fixed = sizeof(uint4) * (size_t)VCL * NCOL;
   uint32_t rmax = (uint32_t)((ctx->pile_smem - fixed) / (sizeof(uint4) * (W + 1) + sizeof(uint32_t)));
@@ -643,9 +678,15 @@ extern "C" int mb_snps_pileup_dev(mb_ctx* ctx, const mb_dev_reads* reads, const 
       reinterpret_cast<unsigned long long*>(stats_dev), dl.species_len, ns, ctx->sched);
   ctx->launches++;
   if (n_ktiles == 0) { MB_CUDA_TRY(cudaGetLastError()); return MB_OK; }
-  k_tile_ranges<<<(n_ktiles + 255) / 256, 256, 0, st>>>(reinterpret_cast<const uint4*>(reads->hdr),
-                                                        (uint32_t)reads->n_reads, 32u * W, n_ktiles, ctx->tile_rng);
-  ctx->launches++;
+  // the tile -> read-range index depends only on the resident batch: built once per (batch, row width)
+  if (ctx->rng_for != reads || ctx->rng_W != W || ctx->rng_ntiles != n_ktiles) {
+    k_tile_ranges<<<(n_ktiles + 255) / 256, 256, 0, st>>>(reinterpret_cast<const uint4*>(reads->hdr),
+                                                          (uint32_t)reads->n_reads, 32u * W, n_ktiles, ctx->tile_rng);
+    ctx->launches++;
+    ctx->rng_for = reads;
+    ctx->rng_W = W;
+    ctx->rng_ntiles = n_ktiles;
+  }
   PileParams p;
   p.hdr = reinterpret_cast<const uint4*>(reads->hdr);
   p.blk_off = reads->blk_off;
@@ -661,7 +702,6 @@ extern "C" int mb_snps_pileup_dev(mb_ctx* ctx, const mb_dev_reads* reads, const 
   p.gpad = L->gpad;
   p.n_ktiles = n_ktiles;
   p.W = W;
-  p.G = 32u / W;
   p.rmax = rmax;
   rc = mb::get_filter_tables(ctx, f, &p.t_pid, &p.t_cov);
   if (rc) return rc;
@@ -672,7 +712,7 @@ extern "C" int mb_snps_pileup_dev(mb_ctx* ctx, const mb_dev_reads* reads, const 
   p.defer_restat = reads->n_long ? 1u : 0u;
   const uint32_t grid = min(n_ktiles, (uint32_t)(ctx->sm_count * ctx->pile_occ));
   { int trc = mb::timing_begin(ctx); if (trc) return trc; }
-  k_pileup_v2<<<grid, NT, pile_smem_bytes(W, rmax), st>>>(p);
+  kern.fn<<<grid, NT, pile_smem_bytes(W, rmax), st>>>(p);
   { int trc = mb::timing_end(ctx); if (trc) return trc; }
   ctx->launches++;
   if (reads->n_long) {
@@ -711,7 +751,9 @@ extern "C" int mb_snps_pileup(mb_ctx* ctx, const mb_packed_reads* reads, const m
   const size_t cbytes = sizeof(uint32_t) * 4 * (size_t)L->gpad, sbytes = sizeof(mb_species_stats) * (size_t)L->n_species;
   rc = mb::ctx_reserve(ctx, 0, cbytes, &counts);
   if (!rc) rc = mb::ctx_reserve(ctx, 1, sbytes, &stats);
+  ctx->rng_for = nullptr;   // `dr` is a fresh batch in recycled staging buffers: rebuild the tile index
   if (!rc) rc = mb_snps_pileup_dev(ctx, d, L, f, (uint32_t*)counts, (mb_species_stats*)stats);
+  ctx->rng_for = nullptr;
   if (!rc && cbytes) {
     cudaError_t e = cudaMemcpyAsync(counts_host, counts, cbytes, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess && sbytes) e = cudaMemcpyAsync(stats_host, stats, sbytes, cudaMemcpyDeviceToHost, ctx->stream);

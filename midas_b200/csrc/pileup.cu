@@ -408,16 +408,21 @@ __global__ void __launch_bounds__(NT, 2) k_pileup_v2(const PileParams p) {
         }
       };
       {
-        StageIn sa_, sb_;                                       // ping-pong: no register copies between steps
+        StageIn sa_, sb_, sc_;                                  // three reads in flight per lane group, rotated without copies
         int i = warp * G + grp;
         fetch(i, sa_);
+        fetch(i + istep, sb_);
         while (true) {
-          fetch(i + istep, sb_);
+          fetch(i + 2 * istep, sc_);
           process(i, sa_);
           i += istep;
           if (i - grp >= n) break;
-          fetch(i + istep, sa_);
+          fetch(i + 2 * istep, sa_);
           process(i, sb_);
+          i += istep;
+          if (i - grp >= n) break;
+          fetch(i + 2 * istep, sb_);
+          process(i, sc_);
           i += istep;
           if (i - grp >= n) break;
         }

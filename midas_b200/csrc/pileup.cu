@@ -70,6 +70,7 @@ struct PileParams {
   uint32_t* sched;
   uint64_t gpad;
   uint32_t n_ktiles;
+  uint32_t n_blocks;          // 16-base blocks in seq2 / qual
   uint32_t W;                 // row words
   uint32_t rmax;              // rows staged per round
   const int32_t* t_pid;       // [65536] smallest 100*(alen-NM) that passes mapid, per alen
@@ -115,6 +116,14 @@ __device__ __forceinline__ void conv16(const uint4 q, const uint32_t qadd, uint3
   const uint32_t n2 = __umulhi(t2, MUL0), n3 = __umulhi(t3, MUL4);
   b01 = (n0 & 0x0fu) | (n1 & ~0x0fu);  // low byte: bases 0-7 (higher bytes hold gather by-products)
   b23 = (n2 & 0x0fu) | (n3 & ~0x0fu);  // low byte: bases 8-15
+}
+
+// Ask the copy engine to pull [ptr, ptr + bytes) into L2 (no registers, no shared memory, no wait):
+// the loads that follow a round later find their lines on chip instead of in HBM.
+__device__ __forceinline__ void l2_prefetch(const void* ptr, uint32_t bytes) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(ptr) & ~(uintptr_t)15;
+  const uint32_t n = (bytes + 31u) & ~15u;
+  if (n) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(n) : "memory");
 }
 
 __device__ __forceinline__ uint32_t bit_range_mask(int lo, int hi) {  // bits [lo, hi) of a word, 0 <= lo < hi <= 32
@@ -178,7 +187,7 @@ __global__ void __launch_bounds__(NT, 2) k_pileup_v2(const PileParams p) {
   uint32_t* s_cplx = reinterpret_cast<uint32_t*>(s_rows + (size_t)p.rmax * W);  // [rmax]
   __shared__ uint32_t s_first[FIRST_N];
   __shared__ unsigned long long s_red[4];                             // covered, depth, aligned, mapped
-  __shared__ uint32_t s_tile, s_nmax;
+  __shared__ uint32_t s_tile, s_next, s_nmax;
   __shared__ uint8_t s_mod[NCOL + 2 * WMAX + 1];                      // x % W for small x
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -194,15 +203,24 @@ __global__ void __launch_bounds__(NT, 2) k_pileup_v2(const PileParams p) {
   for (int i = tid; i < VCL * NCOL; i += NT) s_vc[i] = make_uint4(0, 0, 0, 0);
   for (int i = tid; i < NCOL + 2 * WMAX + 1; i += NT) s_mod[i] = (uint8_t)((uint32_t)i % W);
 
+  if (tid == 0) s_next = atomicAdd(p.sched, 1u);
   for (;;) {
     __syncthreads();
-    if (tid == 0) { s_tile = atomicAdd(p.sched, 1u); s_nmax = 0; }
+    if (tid == 0) { s_tile = s_next; s_next = atomicAdd(p.sched, 1u); s_nmax = 0; }   // one tile of look-ahead
     if (tid < 4) s_red[tid] = 0;
     __syncthreads();
     const uint32_t tile = s_tile;
     if (tile >= p.n_ktiles) break;
     const uint32_t ts = tile * KT;
     const uint32_t r0 = p.tile_rng[2 * tile], r1 = p.tile_rng[2 * tile + 1];
+    // thread 0: where the next tile's first round starts (used at this tile's last round; the loads
+    // are issued now so that their latency is long gone by then)
+    uint32_t nx_r0 = 0, nx_r1 = 0, nx_b0 = 0;
+    if (tid == 0 && s_next < p.n_ktiles) {
+      nx_r0 = __ldg(p.tile_rng + 2 * s_next);
+      nx_r1 = __ldg(p.tile_rng + 2 * s_next + 1);
+      nx_b0 = __ldg(p.blk_off + nx_r0);
+    }
     const uint32_t tcol = ts >> 5, tb = tcol % W;
     const uint32_t slot_c = s_mod[tb + (uint32_t)col];                // where my column's word sits in a row
     const uint32_t loc_base = ts - 32u * WMAX;                        // row coordinates are stored relative to it (wraps for ts = 0: no read starts before 0)
@@ -315,6 +333,24 @@ __global__ void __launch_bounds__(NT, 2) k_pileup_v2(const PileParams p) {
           for (int x = xi + 1; x <= kmax + 1; ++x) s_first[x] = (uint32_t)n;
       }
       __syncthreads();
+      if (tid == 0) {   // L2 prefetch of the round after this one (next rows of this tile, else the next tile's first rows)
+        const uint4 ml = s_meta[n - 1];
+        const uint32_t b_end = ml.y + (((ml.z & 0xffffu) + 15u) >> 4);     // one past this round's last block
+        const uint32_t b_beg = s_meta[0].y;
+        uint32_t pr0, pr1, pb0;
+        if (rb + (uint32_t)n < r1) { pr0 = rb + (uint32_t)n; pr1 = min(r1, pr0 + p.rmax); pb0 = b_end; }
+        else { pr0 = nx_r0; pr1 = min(nx_r1, nx_r0 + p.rmax); pb0 = nx_b0; }
+        if (pr1 > pr0) {
+          const uint32_t nrow = pr1 - pr0;
+          uint32_t nblk = (b_end - b_beg) / (uint32_t)n * nrow + 16u;        // as many blocks per read as this round had
+          nblk = pb0 < p.n_blocks ? min(nblk, p.n_blocks - pb0) : 0u;        // never past the arrays
+          l2_prefetch(p.hdr + pr0, nrow * 16u);
+          l2_prefetch(p.blk_off + pr0, nrow * 4u);
+          l2_prefetch(p.cplx + pr0, nrow * 4u);
+          l2_prefetch(p.qual + pb0, nblk * 16u);
+          l2_prefetch(p.seq2 + pb0, nblk * 4u);
+        }
+      }
       // ---- STAGE: W lanes per read build its bit-plane row; the loads of the next read are issued
       // before the current one is converted (two reads in flight per lane group)
       auto fetch = [&](const int i, StageIn& in) {
@@ -706,6 +742,7 @@ extern "C" int mb_snps_pileup_dev(mb_ctx* ctx, const mb_dev_reads* reads, const 
   p.sched = ctx->sched;
   p.gpad = L->gpad;
   p.n_ktiles = n_ktiles;
+  p.n_blocks = (uint32_t)reads->n_blocks;
   p.W = W;
   p.rmax = rmax;
   rc = mb::get_filter_tables(ctx, f, &p.t_pid, &p.t_cov);

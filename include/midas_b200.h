@@ -12,6 +12,7 @@
  *                           midas/run/snps.py:194-199  pysam count_coverage() call site
  *   mb_genes_coverage*   <- midas/run/genes.py:171-203 count_mapped_bp()
  *                           midas/run/genes.py:153-169 keep_read()
+ *   mb_bam_open          <- pysam.AlignmentFile(bam,'rb') at midas/run/snps.py:186, genes.py:175 (BAM decode)
  *   mb_format_snps_rows  <- midas/run/snps.py:179-182,201-210 (row text of <species>.snps.gz)
  *   mb_pack_reads        <- what pysam/htslib hands to those loops (decoded BAM
  *                           records), re-laid as the struct-of-arrays the GPU reads
@@ -237,6 +238,21 @@ int mb_genes_coverage_dev(mb_ctx* ctx, const mb_dev_reads* reads, const uint32_t
 int mb_genes_coverage(mb_ctx* ctx, const mb_packed_reads* reads, const uint32_t* gene_len_host,
                       uint32_t n_genes, const mb_filters* f, int exact_order,
                       mb_gene_out* out_host);
+
+/* ---------------------------------------------------------------- BAM ingest */
+/* Decode a BAM file (BGZF inflate + record parse on n_threads host threads, 0 = all) into the
+ * plain records above, in file order; records with refID < 0 are dropped. Replaces what
+ * pysam.AlignmentFile(path, 'rb') + fetch / count_coverage decode for the reference
+ * (midas/run/snps.py:186,194; midas/run/genes.py:175-180); no index (snps.py:130-139) is needed.
+ * The arrays behind mb_bam_reads() belong to the handle. Host only. */
+typedef struct mb_bam mb_bam;
+int mb_bam_open(const char* path, int n_threads, mb_bam** out);
+void mb_bam_close(mb_bam* b);
+uint32_t mb_bam_n_ref(const mb_bam* b);
+const char* mb_bam_ref_name(const mb_bam* b, uint32_t i);
+uint32_t mb_bam_ref_len(const mb_bam* b, uint32_t i);
+const mb_plain_reads* mb_bam_reads(const mb_bam* b);
+const uint16_t* mb_bam_flags(const mb_bam* b);   /* [n_reads] SAM flags (informational) */
 
 /* ------------------------------------------------------------- text output */
 /* Rows of <species>.snps.gz for n_rows consecutive positions of one contig, starting at 0-based

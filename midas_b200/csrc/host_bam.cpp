@@ -1,0 +1,239 @@
+// BAM -> decoded records (mb_plain_reads), natively: BGZF inflate on all host threads, then a
+// parallel record parse. This is the ingest step pysam/htslib performs for the reference when it
+// opens <outdir>/snps/temp/genomes.bam (midas/run/snps.py:186) or genes/temp/pangenomes.bam
+// (midas/run/genes.py:175-178); records come out in file order, unplaced records (refID < 0) are
+// dropped, no index is needed. Format: SAM/BAM specification v1, sections 4.1 (BGZF) and 4.2.
+#include <zlib.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "common.h"
+
+struct mb_bam {
+  std::vector<std::string> ref_name;
+  std::vector<uint32_t> ref_len;
+  std::vector<int32_t> ref_id, pos, nm, l_qseq;
+  std::vector<uint8_t> mapq, seq, qual;
+  std::vector<uint16_t> flag;
+  std::vector<uint64_t> cigar_off, seq_off;
+  std::vector<uint32_t> cigar;
+  mb_plain_reads pub;
+};
+
+namespace {
+
+inline uint32_t rd32(const uint8_t* p) { uint32_t v; memcpy(&v, p, 4); return v; }
+inline uint16_t rd16(const uint8_t* p) { uint16_t v; memcpy(&v, p, 2); return v; }
+
+template <class F>
+void pfor(size_t n, int n_threads, F f) {
+  if (n_threads <= 1 || n < 2) { f(0, n); return; }
+  std::vector<std::thread> th;
+  const size_t per = (n + n_threads - 1) / n_threads;
+  for (int t = 0; t < n_threads; ++t) {
+    const size_t lo = std::min(n, per * t), hi = std::min(n, lo + per);
+    if (lo >= hi) break;
+    th.emplace_back([=] { f(lo, hi); });
+  }
+  for (auto& x : th) x.join();
+}
+
+// integer value of the NM aux tag, or -1 when absent / malformed
+int32_t find_nm(const uint8_t* p, const uint8_t* end) {
+  while (p + 3 <= end) {
+    const uint8_t t0 = p[0], t1 = p[1], ty = p[2];
+    p += 3;
+    size_t sz = 0;
+    switch (ty) {
+      case 'A': case 'c': case 'C': sz = 1; break;
+      case 's': case 'S': sz = 2; break;
+      case 'i': case 'I': case 'f': sz = 4; break;
+      case 'd': sz = 8; break;
+      case 'Z': case 'H': {
+        const uint8_t* z = (const uint8_t*)memchr(p, 0, (size_t)(end - p));
+        if (!z) return -1;
+        p = z + 1;
+        continue;
+      }
+      case 'B': {
+        if (p + 5 > end) return -1;
+        const uint8_t sub = p[0];
+        const uint32_t cnt = rd32(p + 1);
+        size_t es = (sub == 'c' || sub == 'C') ? 1 : (sub == 's' || sub == 'S') ? 2 : 4;
+        p += 5 + (size_t)cnt * es;
+        continue;
+      }
+      default: return -1;
+    }
+    if (p + sz > end) return -1;
+    if (t0 == 'N' && t1 == 'M') {
+      switch (ty) {
+        case 'c': return (int8_t)p[0];
+        case 'C': return p[0];
+        case 's': return (int16_t)rd16(p);
+        case 'S': return rd16(p);
+        case 'i': return (int32_t)rd32(p);
+        case 'I': { const uint32_t v = rd32(p); return v > 0x7fffffffu ? 0x7fffffff : (int32_t)v; }
+        default: return -1;
+      }
+    }
+    p += sz;
+  }
+  return -1;
+}
+
+}  // namespace
+
+extern "C" int mb_bam_open(const char* path, int n_threads, mb_bam** out) {
+  if (!path || !out) return mb::fail(MB_EINVAL, "mb_bam_open: null argument");
+  if (n_threads <= 0) n_threads = (int)std::min<unsigned>(32, std::max(1u, std::thread::hardware_concurrency()));
+  FILE* fh = fopen(path, "rb");
+  if (!fh) return mb::fail(MB_EINVAL, "mb_bam_open: cannot open %s", path);
+  fseek(fh, 0, SEEK_END);
+  const long fsz = ftell(fh);
+  fseek(fh, 0, SEEK_SET);
+  std::vector<uint8_t> raw((size_t)std::max(0L, fsz));
+  if (fsz > 0 && fread(raw.data(), 1, (size_t)fsz, fh) != (size_t)fsz) { fclose(fh); return mb::fail(MB_EINVAL, "mb_bam_open: short read on %s", path); }
+  fclose(fh);
+  // 1. BGZF block table
+  struct Blk { size_t off, cbeg, clen; uint32_t isize; size_t dst; };
+  std::vector<Blk> blks;
+  size_t off = 0, total = 0;
+  while (off + 18 <= raw.size()) {
+    const uint8_t* b = raw.data() + off;
+    if (b[0] != 0x1f || b[1] != 0x8b || b[2] != 8 || !(b[3] & 4))
+      return mb::fail(MB_EMALFORMED, "mb_bam_open: %s: not a BGZF block at offset %zu", path, off);
+    const uint16_t xlen = rd16(b + 10);
+    size_t x = off + 12, xend = x + xlen, bsize = 0;
+    while (x + 4 <= xend && xend <= raw.size()) {
+      const uint16_t slen = rd16(raw.data() + x + 2);
+      if (raw[x] == 66 && raw[x + 1] == 67 && slen == 2) bsize = (size_t)rd16(raw.data() + x + 4) + 1;
+      x += 4 + slen;
+    }
+    if (!bsize || off + bsize > raw.size() || bsize < (size_t)xlen + 20)
+      return mb::fail(MB_EMALFORMED, "mb_bam_open: %s: bad BGZF block size at offset %zu", path, off);
+    Blk k;
+    k.off = off;
+    k.cbeg = xend;
+    k.clen = off + bsize - 8 - xend;
+    k.isize = rd32(raw.data() + off + bsize - 4);
+    k.dst = total;
+    total += k.isize;
+    blks.push_back(k);
+    off += bsize;
+  }
+  if (off != raw.size()) return mb::fail(MB_EMALFORMED, "mb_bam_open: %s: trailing bytes after the last BGZF block", path);
+  // 2. inflate in parallel
+  std::vector<uint8_t> data(total + 8);
+  std::vector<int> bad((size_t)n_threads + 1, 0);
+  pfor(blks.size(), n_threads, [&](size_t lo, size_t hi) {
+    for (size_t i = lo; i < hi; ++i) {
+      const Blk& k = blks[i];
+      if (!k.isize) continue;
+      z_stream zs;
+      memset(&zs, 0, sizeof(zs));
+      if (inflateInit2(&zs, -15) != Z_OK) { bad[0] = 1; return; }
+      zs.next_in = raw.data() + k.cbeg;
+      zs.avail_in = (uInt)k.clen;
+      zs.next_out = data.data() + k.dst;
+      zs.avail_out = k.isize;
+      const int rc = inflate(&zs, Z_FINISH);
+      const bool ok = rc == Z_STREAM_END && zs.total_out == k.isize &&
+                      (crc32(0L, data.data() + k.dst, k.isize) == rd32(raw.data() + k.off + (k.cbeg - k.off) + k.clen));
+      inflateEnd(&zs);
+      if (!ok) { bad[0] = 1; return; }
+    }
+  });
+  if (bad[0]) return mb::fail(MB_EMALFORMED, "mb_bam_open: %s: BGZF inflate / CRC failure", path);
+  raw.clear();
+  raw.shrink_to_fit();
+  // 3. header
+  const uint8_t* d = data.data();
+  if (total < 12 || memcmp(d, "BAM\1", 4) != 0) return mb::fail(MB_EMALFORMED, "mb_bam_open: %s: not a BAM file", path);
+  size_t o = 8 + (size_t)rd32(d + 4);
+  if (o + 4 > total) return mb::fail(MB_EMALFORMED, "mb_bam_open: %s: truncated header", path);
+  const uint32_t n_ref = rd32(d + o);
+  o += 4;
+  mb_bam* B = new mb_bam();
+  for (uint32_t i = 0; i < n_ref; ++i) {
+    if (o + 4 > total) { delete B; return mb::fail(MB_EMALFORMED, "mb_bam_open: %s: truncated reference list", path); }
+    const uint32_t ln = rd32(d + o);
+    if (o + 8 + ln > total || ln == 0) { delete B; return mb::fail(MB_EMALFORMED, "mb_bam_open: %s: truncated reference list", path); }
+    B->ref_name.emplace_back((const char*)d + o + 4, ln - 1);
+    B->ref_len.push_back(rd32(d + o + 4 + ln));
+    o += 8 + ln;
+  }
+  // 4. record table (sequential: 4 bytes per record decide the next offset)
+  std::vector<size_t> rec;
+  std::vector<uint64_t> coff(1, 0), soff(1, 0);
+  while (o + 4 <= total) {
+    const uint32_t bs = rd32(d + o);
+    if (bs < 32 || o + 4 + bs > total) { delete B; return mb::fail(MB_EMALFORMED, "mb_bam_open: %s: truncated record at %zu", path, o); }
+    const uint8_t* r = d + o + 4;
+    const int32_t rid = (int32_t)rd32(r);
+    const uint32_t l_name = r[8], n_cig = rd16(r + 12), l_seq = rd32(r + 16);
+    if (32 + (size_t)l_name + 4 * (size_t)n_cig + (l_seq + 1) / 2 + (size_t)l_seq > bs) {
+      delete B;
+      return mb::fail(MB_EMALFORMED, "mb_bam_open: %s: record fields exceed block_size at %zu", path, o);
+    }
+    if (rid >= 0) {
+      if ((uint32_t)rid >= n_ref) { delete B; return mb::fail(MB_EMALFORMED, "mb_bam_open: %s: refID %d out of range", path, rid); }
+      rec.push_back(o);
+      coff.push_back(coff.back() + n_cig);
+      soff.push_back(soff.back() + l_seq);
+    }
+    o += 4 + bs;
+  }
+  const size_t n = rec.size();
+  B->ref_id.resize(n); B->pos.resize(n); B->nm.resize(n); B->l_qseq.resize(n); B->mapq.resize(n); B->flag.resize(n);
+  B->cigar.resize(coff.back()); B->seq.resize(soff.back()); B->qual.resize(soff.back());
+  B->cigar_off = std::move(coff);
+  B->seq_off = std::move(soff);
+  // 5. parallel decode
+  pfor(n, n_threads, [&](size_t lo, size_t hi) {
+    for (size_t i = lo; i < hi; ++i) {
+      const uint8_t* r = d + rec[i] + 4;
+      const uint32_t bs = rd32(d + rec[i]);
+      const uint32_t l_name = r[8], n_cig = rd16(r + 12), l_seq = rd32(r + 16);
+      B->ref_id[i] = (int32_t)rd32(r);
+      B->pos[i] = (int32_t)rd32(r + 4);
+      B->mapq[i] = r[9];
+      B->flag[i] = rd16(r + 14);
+      B->l_qseq[i] = (int32_t)l_seq;
+      const uint8_t* q = r + 32 + l_name;
+      memcpy(B->cigar.data() + B->cigar_off[i], q, 4 * (size_t)n_cig);
+      q += 4 * (size_t)n_cig;
+      uint8_t* s = B->seq.data() + B->seq_off[i];
+      for (uint32_t k = 0; k < l_seq; ++k) s[k] = (k & 1) ? (q[k >> 1] & 15) : (q[k >> 1] >> 4);
+      q += (l_seq + 1) / 2;
+      memcpy(B->qual.data() + B->seq_off[i], q, l_seq);
+      q += l_seq;
+      B->nm[i] = find_nm(q, r + bs);
+    }
+  });
+  B->pub.n_reads = n;
+  B->pub.ref_id = B->ref_id.data();
+  B->pub.pos = B->pos.data();
+  B->pub.mapq = B->mapq.data();
+  B->pub.nm = B->nm.data();
+  B->pub.l_qseq = B->l_qseq.data();
+  B->pub.cigar_off = B->cigar_off.data();
+  B->pub.cigar = B->cigar.data();
+  B->pub.seq_off = B->seq_off.data();
+  B->pub.seq = B->seq.data();
+  B->pub.qual = B->qual.data();
+  *out = B;
+  return MB_OK;
+}
+
+extern "C" void mb_bam_close(mb_bam* B) { delete B; }
+extern "C" uint32_t mb_bam_n_ref(const mb_bam* B) { return B ? (uint32_t)B->ref_name.size() : 0; }
+extern "C" const char* mb_bam_ref_name(const mb_bam* B, uint32_t i) { return B && i < B->ref_name.size() ? B->ref_name[i].c_str() : ""; }
+extern "C" uint32_t mb_bam_ref_len(const mb_bam* B, uint32_t i) { return B && i < B->ref_len.size() ? B->ref_len[i] : 0; }
+extern "C" const mb_plain_reads* mb_bam_reads(const mb_bam* B) { return B ? &B->pub : nullptr; }
+extern "C" const uint16_t* mb_bam_flags(const mb_bam* B) { return B ? B->flag.data() : nullptr; }

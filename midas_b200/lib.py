@@ -66,6 +66,7 @@ EXPORTS = [
     "mb_reads_upload", "mb_reads_free", "mb_reads_bytes",
     "mb_snps_pileup_dev", "mb_snps_pileup", "mb_genes_coverage_dev", "mb_genes_coverage",
     "mb_format_snps_bound", "mb_format_snps_rows",
+    "mb_bam_open", "mb_bam_close", "mb_bam_n_ref", "mb_bam_ref_name", "mb_bam_ref_len", "mb_bam_reads", "mb_bam_flags",
 ]
 
 _lib = None
@@ -124,6 +125,19 @@ def load():
     L.mb_format_snps_rows.restype = C.c_int64
     L.mb_format_snps_rows.argtypes = [C.c_char_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+    L.mb_bam_open.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
+    L.mb_bam_close.argtypes = [C.c_void_p]
+    L.mb_bam_close.restype = None
+    L.mb_bam_n_ref.argtypes = [C.c_void_p]
+    L.mb_bam_n_ref.restype = C.c_uint32
+    L.mb_bam_ref_name.argtypes = [C.c_void_p, C.c_uint32]
+    L.mb_bam_ref_name.restype = C.c_char_p
+    L.mb_bam_ref_len.argtypes = [C.c_void_p, C.c_uint32]
+    L.mb_bam_ref_len.restype = C.c_uint32
+    L.mb_bam_reads.argtypes = [C.c_void_p]
+    L.mb_bam_reads.restype = C.POINTER(CPlainReads)
+    L.mb_bam_flags.argtypes = [C.c_void_p]
+    L.mb_bam_flags.restype = C.c_void_p
     _lib = L
     return L
 
@@ -355,3 +369,33 @@ def format_snps_rows(contig_name: str, ref_bases: np.ndarray, first_pos0: int, c
     if w < 0:
         _check(int(w))
     return buf.raw[:w]
+
+
+def read_bam(path: str, threads: int = 0):
+    """Native BAM decode (mb_bam_open): returns (ref_names, ref_lens, PlainReads) in file order, like
+    midas_b200.bam.read_bam (the pure-Python reader it must agree with)."""
+    L = load()
+    h = C.c_void_p()
+    _check(L.mb_bam_open(os.fsencode(path), int(threads), C.byref(h)))
+    try:
+        n_ref = int(L.mb_bam_n_ref(h))
+        names = [L.mb_bam_ref_name(h, i).decode() for i in range(n_ref)]
+        lens = [int(L.mb_bam_ref_len(h, i)) for i in range(n_ref)]
+        r = L.mb_bam_reads(h).contents
+        n = int(r.n_reads)
+
+        def arr(ptr, count, dt):
+            if count == 0:
+                return np.zeros(0, dt)
+            buf = (C.c_char * (count * np.dtype(dt).itemsize)).from_address(ptr)
+            return np.frombuffer(buf, dtype=dt, count=count).copy()
+
+        coff = arr(r.cigar_off, n + 1, np.uint64)
+        soff = arr(r.seq_off, n + 1, np.uint64)
+        reads = PlainReads(arr(r.ref_id, n, np.int32), arr(r.pos, n, np.int32), arr(r.mapq, n, np.uint8),
+                           arr(r.nm, n, np.int32), arr(r.l_qseq, n, np.int32), coff,
+                           arr(r.cigar, int(coff[-1]), np.uint32), soff, arr(r.seq, int(soff[-1]), np.uint8),
+                           arr(r.qual, int(soff[-1]), np.uint8), arr(L.mb_bam_flags(h), n, np.uint16))
+    finally:
+        L.mb_bam_close(h)
+    return names, lens, reads

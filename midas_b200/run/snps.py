@@ -113,7 +113,7 @@ def build_refset(species, contigs):
 def load_alignments(bampath, ref: RefSet):
     """Decode the BAM and re-index its reference ids onto `ref` (records on references that are not
     contigs of a selected species are never fetched by the reference, snps.py:190-199)."""
-    names, lens, reads = bam.read_bam(bampath)
+    names, lens, reads = lib.read_bam(bampath)
     index = {n: k for k, n in enumerate(ref.contig_names)}
     tid_map = np.array([index.get(n, -1) for n in names], np.int32) if names else np.zeros(0, np.int32)
     for n, l in zip(names, lens):

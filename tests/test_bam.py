@@ -50,3 +50,33 @@ def test_empty_bam(tmp_path):
     bam.write_bam(p, ["c1"], [100], empty)
     names, lens, back = bam.read_bam(p)
     assert names == ["c1"] and back.n_reads == 0
+
+
+def test_native_reader_agrees_with_python_reader(tmp_path):
+    from midas_b200 import lib
+    rng = np.random.default_rng(9)
+    ref = gen.make_ref(rng, 3, 2, 300, 3000)
+    reads = gen.random_reads(10, ref, 3000, max_len=200, sort=False)
+    reads.nm[::5] = 70000           # 32-bit NM
+    reads.ref_id[::97] = -1         # unplaced records are dropped by both readers
+    p = str(tmp_path / "n.bam")
+    bam.write_bam(p, ref.contig_names, ref.contig_len, reads)
+    n1, l1, r1 = bam.read_bam(p)
+    for threads in (1, 4):
+        n2, l2, r2 = lib.read_bam(p, threads)
+        assert n1 == n2 and [int(x) for x in l1] == l2
+        for f in ("ref_id", "pos", "mapq", "nm", "l_qseq", "cigar_off", "cigar", "seq_off", "seq", "qual", "flag"):
+            assert np.array_equal(getattr(r1, f), getattr(r2, f)), f
+    assert r1.n_reads == reads.n_reads - len(range(0, reads.n_reads, 97))
+
+
+def test_native_reader_rejects_garbage(tmp_path):
+    import pytest
+    from midas_b200 import lib
+    p = tmp_path / "bad.bam"
+    p.write_bytes(b"this is not a bam file at all, not even gzip")
+    with pytest.raises(lib.MidasB200Error) as e:
+        lib.read_bam(str(p))
+    assert e.value.status == -5
+    with pytest.raises(lib.MidasB200Error):
+        lib.read_bam(str(tmp_path / "missing.bam"))

@@ -13,6 +13,8 @@
 //   C. lane i issues read i's atomics: (aligned,mapped) as one packed u64 add, mapped_bp as another.
 #include <cub/device/device_radix_sort.cuh>
 
+#include <cmath>
+
 #include "common.h"
 
 namespace {
@@ -28,70 +30,57 @@ struct GeneParams {
   uint32_t* key;            // exact order: per read, gene index if kept else 0xFFFFFFFF (may be null)
   uint32_t* val;            // exact order: per read, aligned length
   uint32_t n_genes;
-  double mapid, aln_cov;
-  int readq, mapq;
+  const int32_t* t_pid;     // smallest 100*(alen-NM) that passes mapid, per alen (ctx.cu)
+  const int32_t* t_cov;     // smallest alen that passes aln_cov, per l_qseq
+  uint32_t pid_always, readq_eff;
+  int mapq;
 };
 
 __global__ void __launch_bounds__(GENE_THREADS) k_genes_v1(const GeneParams p) {
-  const int lane = threadIdx.x & 31;
-  const uint64_t warp_global = ((uint64_t)blockIdx.x * GENE_THREADS + threadIdx.x) >> 5;
-  const uint64_t n_warps = ((uint64_t)gridDim.x * GENE_THREADS) >> 5;
-  const int sub = lane >> 4, sl = lane & 15;  // two 16-lane groups
-  for (uint64_t base = warp_global * 32; base < p.n_reads; base += n_warps * 32) {
-    const uint64_t r = base + lane;
-    const bool valid = r < p.n_reads;
-    uint32_t gene = 0, lq = 0, alen = 0, blk0 = 0;
-    bool ok = false;
-    if (valid) {
-      const uint4 h = __ldg(&p.hdr[r]);
-      gene = h.x;
-      lq = h.y & 0xffffu;
-      alen = h.y >> 16;
-      const uint32_t nm = h.z >> 16, mq = (h.w >> 16) & 0xffu, fl = h.w >> 24;
-      blk0 = __ldg(&p.blk_off[r]);
-      double pid = __ddiv_rn((double)(100 * ((int)alen - (int)nm)), (double)alen);
-      if (fl & MB_RF_NMSAT) pid = -__longlong_as_double(0x7ff0000000000000ll);
-      ok = !(pid < p.mapid) && !((int)mq < p.mapq) && !(__ddiv_rn((double)alen, (double)lq) < p.aln_cov);
-    }
-    // B: quality sums, two reads per step
-    uint32_t need = __ballot_sync(0xffffffffu, ok);
-    uint32_t my_sum = 0;
-    while (need) {
-      // pick up to two reads: lowest set bits
-      const int i0 = __ffs(need) - 1;
-      need &= need - 1;
-      int i1 = -1;
-      if (need) { i1 = __ffs(need) - 1; need &= need - 1; }
-      const int src = sub == 0 ? i0 : i1;
-      const int srcc = src < 0 ? 0 : src;
-      const uint32_t b0 = __shfl_sync(0xffffffffu, blk0, srcc);
-      const uint32_t l = __shfl_sync(0xffffffffu, lq, srcc);
+  // One thread per read: its qualities are 10 independent 128-bit loads (all in flight at once);
+  // the 160-byte stride between lanes is absorbed by L1 (the kernel uses no shared memory).
+  const uint64_t stride = (uint64_t)gridDim.x * GENE_THREADS;
+  for (uint64_t r = (uint64_t)blockIdx.x * GENE_THREADS + threadIdx.x; r < p.n_reads; r += stride) {
+    const uint4 h = __ldg(&p.hdr[r]);
+    const uint32_t blk0 = __ldg(&p.blk_off[r]);
+    const uint32_t gene = h.x, lq = h.y & 0xffffu, alen = h.y >> 16;
+    const uint32_t nm = h.z >> 16, mq = (h.w >> 16) & 0xffu, fl = h.w >> 24;
+    // exact integer forms of the two double-precision tests of keep_read (tables built in ctx.cu)
+    bool ok = (fl & MB_RF_NMSAT) ? (p.pid_always != 0)
+                                 : (100 * ((int)alen - (int)nm) >= __ldg(p.t_pid + alen));   // genes.py:157
+    ok = ok && (int)mq >= p.mapq;                                                             // genes.py:163
+    ok = ok && (int)alen >= __ldg(p.t_cov + lq);                                              // genes.py:166
+    bool keep = false;
+    if (ok) {
+      // mean-quality test genes.py:160: mean(q) < readq  <=>  sum(q) < readq * l_qseq (exact)
+      const uint32_t nblk = (lq + 15u) >> 4;
+      const uint4* __restrict__ q = reinterpret_cast<const uint4*>(p.qual) + blk0;
       uint32_t s = 0;
-      if (src >= 0) {
-        const uint32_t nblk = (l + 15u) >> 4;
-        const uint4* __restrict__ q = reinterpret_cast<const uint4*>(p.qual) + b0;
-        for (uint32_t b = sl; b < nblk; b += 16) {
-          const uint4 v = __ldg(q + b);
-          s += __vsadu4(v.x & 0x7f7f7f7fu, 0u) + __vsadu4(v.y & 0x7f7f7f7fu, 0u) +
-               __vsadu4(v.z & 0x7f7f7f7fu, 0u) + __vsadu4(v.w & 0x7f7f7f7fu, 0u);
-        }
+      uint32_t b = 0;
+      for (; b + 4 <= nblk; b += 4) {
+        const uint4 v0 = __ldg(q + b), v1 = __ldg(q + b + 1), v2 = __ldg(q + b + 2), v3 = __ldg(q + b + 3);
+        s = __dp4a(v0.x & 0x7f7f7f7fu, 0x01010101u, s); s = __dp4a(v0.y & 0x7f7f7f7fu, 0x01010101u, s);
+        s = __dp4a(v0.z & 0x7f7f7f7fu, 0x01010101u, s); s = __dp4a(v0.w & 0x7f7f7f7fu, 0x01010101u, s);
+        s = __dp4a(v1.x & 0x7f7f7f7fu, 0x01010101u, s); s = __dp4a(v1.y & 0x7f7f7f7fu, 0x01010101u, s);
+        s = __dp4a(v1.z & 0x7f7f7f7fu, 0x01010101u, s); s = __dp4a(v1.w & 0x7f7f7f7fu, 0x01010101u, s);
+        s = __dp4a(v2.x & 0x7f7f7f7fu, 0x01010101u, s); s = __dp4a(v2.y & 0x7f7f7f7fu, 0x01010101u, s);
+        s = __dp4a(v2.z & 0x7f7f7f7fu, 0x01010101u, s); s = __dp4a(v2.w & 0x7f7f7f7fu, 0x01010101u, s);
+        s = __dp4a(v3.x & 0x7f7f7f7fu, 0x01010101u, s); s = __dp4a(v3.y & 0x7f7f7f7fu, 0x01010101u, s);
+        s = __dp4a(v3.z & 0x7f7f7f7fu, 0x01010101u, s); s = __dp4a(v3.w & 0x7f7f7f7fu, 0x01010101u, s);
       }
-#pragma unroll
-      for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      // hand the sums back to the owning lanes
-      const uint32_t s0 = __shfl_sync(0xffffffffu, s, 0);
-      const uint32_t s1 = __shfl_sync(0xffffffffu, s, 16);
-      if (lane == i0) my_sum = s0;
-      if (lane == i1) my_sum = s1;
+      for (; b < nblk; ++b) {
+        const uint4 v = __ldg(q + b);
+        s = __dp4a(v.x & 0x7f7f7f7fu, 0x01010101u, s); s = __dp4a(v.y & 0x7f7f7f7fu, 0x01010101u, s);
+        s = __dp4a(v.z & 0x7f7f7f7fu, 0x01010101u, s); s = __dp4a(v.w & 0x7f7f7f7fu, 0x01010101u, s);
+      }
+      keep = s >= p.readq_eff * lq;
     }
-    // C
-    if (valid && gene < p.n_genes) {
-      const bool keep = ok && ((long long)my_sum >= (long long)p.readq * (long long)lq);
+    if (gene < p.n_genes) {
       unsigned long long* o = p.out + (size_t)gene * 3;
       atomicAdd(o, 1ull | ((unsigned long long)(keep ? 1u : 0u) << 32));  // genes.py:181-182,187-188
       if (keep) atomicAdd(o + 1, (unsigned long long)alen);                  // numerator of genes.py:189
       if (p.key) { p.key[r] = keep ? gene : 0xFFFFFFFFu; p.val[r] = alen; }
-    } else if (valid && p.key) {
+    } else if (p.key) {
       p.key[r] = 0xFFFFFFFFu;
       p.val[r] = 0;
     }
@@ -161,9 +150,9 @@ extern "C" int mb_genes_coverage_dev(mb_ctx* ctx, const mb_dev_reads* reads, con
   p.key = key;
   p.val = val;
   p.n_genes = n_genes;
-  p.mapid = f->mapid;
-  p.aln_cov = f->aln_cov;
-  p.readq = f->readq;
+  { int frc = mb::get_filter_tables(ctx, f, &p.t_pid, &p.t_cov); if (frc) return frc; }
+  p.pid_always = (f->mapid != f->mapid || f->mapid == -HUGE_VAL) ? 1u : 0u;
+  p.readq_eff = f->readq <= 0 ? 0u : (f->readq > 128 ? 128u : (uint32_t)f->readq);
   p.mapq = f->mapq;
   { int trc = mb::timing_begin(ctx); if (trc) return trc; }
   if (reads->n_reads) {

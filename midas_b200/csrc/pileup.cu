@@ -168,23 +168,12 @@ __global__ void k_tile_ranges(const uint4* __restrict__ hdr, uint32_t n_reads, u
   rng[2 * t + 1] = lo;
 }
 
-// One staged read of the STAGE pipeline: everything a lane fetches from HBM for its 32 query bases
-struct StageIn {
-  uint4 m;        // s_meta entry
-  uint4 qa, qb;   // 2 x 16 qualities
-  uint32_t sa, sb;  // 2 x 16 two-bit bases
-  uint32_t r0a, r0b, r1a, r1b;  // first two runs of a complex read
-};
-
 template <int WT>
 __global__ void __launch_bounds__(NT, 2) k_pileup_v2(const PileParams p) {
   extern __shared__ __align__(16) uint32_t smem[];
   constexpr uint32_t W = (uint32_t)WT;          // row words (compile time: every per-lane loop below unrolls)
-  constexpr int G = 32 / WT;                    // reads per warp step
   uint4* s_vc = reinterpret_cast<uint4*>(smem);                       // [VCL][NCOL] x {A,C,G,T}
-  uint4* s_meta = s_vc + VCL * NCOL;                                  // [rmax]
-  uint4* s_rows = s_meta + p.rmax;                                    // [rmax][W] x {A,C,G,T}
-  uint32_t* s_cplx = reinterpret_cast<uint32_t*>(s_rows + (size_t)p.rmax * W);  // [rmax]
+  uint4* s_rows = s_vc + VCL * NCOL;                                  // [rmax][W] x {A,C,G,T}
   __shared__ uint32_t s_first[FIRST_N];
   __shared__ unsigned long long s_red[4];                             // covered, depth, aligned, mapped
   __shared__ uint32_t s_tile, s_next, s_nmax;
@@ -192,13 +181,6 @@ __global__ void __launch_bounds__(NT, 2) k_pileup_v2(const PileParams p) {
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int col = tid >> 2, ksub = tid & 3;                           // COUNT role
-  const int grp = lane / (int)W, gj = lane - grp * (int)W;            // STAGE role
-  const int gbase = grp * (int)W;
-  const bool lane_ok = grp < G;
-  const uint32_t bi = 2u * (uint32_t)gj;                              // my first 16-base block of a read
-  const uint4* __restrict__ qual_j = p.qual + bi;
-  const uint32_t* __restrict__ seq_j = p.seq2 + bi;
-  constexpr int istep = NWARP * G;
 
   for (int i = tid; i < VCL * NCOL; i += NT) s_vc[i] = make_uint4(0, 0, 0, 0);
   for (int i = tid; i < NCOL + 2 * WMAX + 1; i += NT) s_mod[i] = (uint8_t)((uint32_t)i % W);
@@ -292,175 +274,140 @@ __global__ void __launch_bounds__(NT, 2) k_pileup_v2(const PileParams p) {
       }
       pass_rows += (uint32_t)n;
       __syncthreads();
-      // ---- META: one thread per read: header filters (snps.py:148,154,157), geometry, row index table
+      // ---- STAGE: one thread per read, everything in registers: header filters (snps.py:148,154,157),
+      // row index table, 2W independent 128-bit quality loads (L1 absorbs the stride between lanes),
+      // conversion to bit planes, mean-quality filter, CIGAR placement, row store
       for (int i = tid; i < n; i += NT) {
         const uint32_t r = rb + (uint32_t)i;
         const uint4 h = __ldg(&p.hdr[r]);
         const uint32_t b0 = __ldg(&p.blk_off[r]);
         const uint32_t loc = h.x, lq = h.y & 0xffffu, alen = h.y >> 16, qstart = h.z & 0xffffu, nm = h.z >> 16;
         const uint32_t span = h.w & 0xffffu, mq = (h.w >> 16) & 0xffu, fl = h.w >> 24;
-        uint32_t flags = 0;
+        bool needq = false, ovl = false, owner = false;
         if (!(fl & MB_RF_LONG)) {
-          const bool owner = loc >= ts;
-          const bool ovl = span > 0 && loc + span > ts;
+          owner = loc >= ts;
+          ovl = span > 0 && loc + span > ts;
           // exact integer forms of the two double-precision tests (tables built in ctx.cu)
           bool hk = (fl & MB_RF_NMSAT) ? (p.pid_always != 0)
                                        : (100 * ((int)alen - (int)nm) >= __ldg(p.t_pid + alen));   // snps.py:148
           hk = hk && (int)mq >= p.mapq;                                                             // snps.py:154
           hk = hk && (int)alen >= __ldg(p.t_cov + lq);                                              // snps.py:157
           if (owner) ++my_aligned;                                                                  // snps.py:143
-          if (hk && (ovl || owner)) flags |= F_NEEDQ;
-          if (ovl) flags |= F_OVL;
-          if (owner) flags |= F_OWNER;
-          if (fl & MB_RF_SIMPLE) flags |= F_SIMPLE;
-          else if ((flags & F_NEEDQ) && ovl) s_cplx[i] = __ldg(p.cplx + r);
+          needq = hk && (ovl || owner);
         }
         const int rel = (int)(loc >> 5) - (int)tcol;                      // start column, in [-W, NCOL)
+        {  // s_first[x] = first row of this round whose start column + (W-1) >= x
+          const int kmax = NCOL + (int)W - 1;
+          int xi = rel + (int)W - 1;
+          xi = xi < 0 ? 0 : (xi > kmax ? kmax : xi);
+          int xlo = 0;
+          if (i > 0) {
+            int xp = (int)(__ldg(&p.hdr[r - 1].x) >> 5) - (int)tcol + (int)W - 1;
+            xp = xp < 0 ? 0 : (xp > kmax ? kmax : xp);
+            xlo = xp + 1;
+          }
+          for (int x = xlo; x <= xi; ++x) s_first[x] = (uint32_t)i;
+          if (i == n - 1)
+            for (int x = xi + 1; x <= kmax + 1; ++x) s_first[x] = (uint32_t)n;
+        }
+        // query bit planes, 32 bases per word: low / high bit of the base code, countable mask
+        uint32_t ql[WT + 1], qh[WT + 1], qv[WT + 1];
+#pragma unroll
+        for (int w = 0; w <= WT; ++w) { ql[w] = 0; qh[w] = 0; qv[w] = 0; }
+        bool keep = false;
+        if (needq) {
+          const uint32_t nblk = (lq + 15u) >> 4;
+          const uint4* __restrict__ qp = p.qual + b0;
+          const uint32_t* __restrict__ sp = p.seq2 + b0;
+          uint32_t qsum = 0;
+#pragma unroll
+          for (int w0 = 0; w0 < WT; w0 += 4) {              // 8 blocks = 8 independent 128-bit loads per step
+            uint4 qq[8];
+            uint32_t ss[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const uint32_t bidx = (uint32_t)(2 * w0 + u);
+              qq[u] = make_uint4(0, 0, 0, 0);
+              ss[u] = 0;
+              if (2 * w0 + u < 2 * WT && bidx < nblk) { qq[u] = __ldg(qp + bidx); ss[u] = __ldg(sp + bidx); }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              if (w0 + u < WT) {
+                uint32_t a01, a23, c01, c23;
+                conv16(qq[2 * u], p.qadd, qsum, a01, a23);
+                conv16(qq[2 * u + 1], p.qadd, qsum, c01, c23);
+                qv[w0 + u] = __byte_perm(__byte_perm(a01, a23, 0x0040), __byte_perm(c01, c23, 0x0040), 0x5410);
+                ql[w0 + u] = __byte_perm(ss[2 * u], ss[2 * u + 1], 0x5410);
+                qh[w0 + u] = __byte_perm(ss[2 * u], ss[2 * u + 1], 0x7632);
+              }
+            }
+          }
+          // mean-quality filter (snps.py:151): mean(q) < readq  <=>  sum(q) < readq * l_qseq (exact)
+          keep = qsum >= p.readq_eff * lq;
+          if (keep && owner) ++my_mapped;                                    // snps.py:161
+        }
+        // ---- CIGAR: every M/=/X run is one funnel-shifted, masked copy of the query planes
+        uint32_t rl[WT], rh[WT], rv[WT];
+#pragma unroll
+        for (int j = 0; j < WT; ++j) { rl[j] = 0; rh[j] = 0; rv[j] = 0; }
+        if (keep && ovl) {
+          const int o = (int)(loc & 31u);
+          // run (q0, x0, len): query bases [q0, q0+len) lie at row bits [o + x0, o + x0 + len); row word j
+          // takes query bits [32 j + dq, +32) with dq = q0 - o - x0 = 32 d + sh. d is -1 or 0 for
+          // all but heavily clipped reads: those two cases are selected without a branch.
+          const bool simple = (fl & MB_RF_SIMPLE) != 0;
+          const uint32_t* __restrict__ rec = p.cigar;
+          uint32_t n_runs = 1;
+          int wshift = 0;                                           // words the planes have been slid so far
+          if (!simple) { rec = p.cigar + __ldg(p.cplx + r); n_runs = __ldg(rec); }
+          for (uint32_t k = 0; k < n_runs; ++k) {
+            int q0 = (int)qstart, x0 = 0, len = (int)span;
+            if (!simple) {
+              const uint32_t w0 = __ldg(rec + 1 + 2 * k);
+              q0 = (int)(w0 & 0xffffu); len = (int)(w0 >> 16); x0 = (int)__ldg(rec + 2 + 2 * k);
+            }
+            const int p0 = o + x0, dq = q0 - p0;
+            int d = (dq >> 5) - wshift;
+            const int sh = dq & 31;
+            // heavily clipped reads / long indels: slide the planes by whole words (static register
+            // moves in a short loop) until the word offset is -1 or 0 again
+            while (d > 0) {
+#pragma unroll
+              for (int w = 0; w < WT; ++w) { ql[w] = ql[w + 1]; qh[w] = qh[w + 1]; qv[w] = qv[w + 1]; }
+              ql[WT] = 0; qh[WT] = 0; qv[WT] = 0;
+              --d; ++wshift;
+            }
+            while (d < -1) {
+#pragma unroll
+              for (int w = WT; w > 0; --w) { ql[w] = ql[w - 1]; qh[w] = qh[w - 1]; qv[w] = qv[w - 1]; }
+              ql[0] = 0; qh[0] = 0; qv[0] = 0;
+              ++d; --wshift;
+            }
+            const bool z = d == 0;
+#pragma unroll
+            for (int j = 0; j < WT; ++j) {
+              const int lo_b = max(0, p0 - 32 * j), hi_b = min(32, p0 + len - 32 * j);
+              if (hi_b > lo_b) {
+                const uint32_t msk = bit_range_mask(lo_b, hi_b);
+                const uint32_t l0 = z ? ql[j] : (j ? ql[j > 0 ? j - 1 : 0] : 0u), l1 = z ? ql[j + 1] : ql[j];
+                const uint32_t h0 = z ? qh[j] : (j ? qh[j > 0 ? j - 1 : 0] : 0u), h1 = z ? qh[j + 1] : qh[j];
+                const uint32_t v0 = z ? qv[j] : (j ? qv[j > 0 ? j - 1 : 0] : 0u), v1 = z ? qv[j + 1] : qv[j];
+                rl[j] |= __funnelshift_r(l0, l1, sh) & msk;
+                rh[j] |= __funnelshift_r(h0, h1, sh) & msk;
+                rv[j] |= __funnelshift_r(v0, v1, sh) & msk;
+              }
+            }
+          }
+        }
         const uint32_t slot0 = s_mod[(int)tb + rel + (int)W];
-        s_meta[i] = make_uint4((loc - loc_base) | (span << 16), b0, lq | (qstart << 16), flags | (slot0 << 8));
-        // s_first[x] = first row of this round whose start column + (W-1) >= x
-        const int kmax = NCOL + (int)W - 1;
-        int xi = rel + (int)W - 1;
-        xi = xi < 0 ? 0 : (xi > kmax ? kmax : xi);
-        int xlo = 0;
-        if (i > 0) {
-          int xp = (int)(__ldg(&p.hdr[r - 1].x) >> 5) - (int)tcol + (int)W - 1;
-          xp = xp < 0 ? 0 : (xp > kmax ? kmax : xp);
-          xlo = xp + 1;
-        }
-        for (int x = xlo; x <= xi; ++x) s_first[x] = (uint32_t)i;
-        if (i == n - 1)
-          for (int x = xi + 1; x <= kmax + 1; ++x) s_first[x] = (uint32_t)n;
-      }
-      __syncthreads();
-      if (tid == 0) {   // L2 prefetch of the round after this one (next rows of this tile, else the next tile's first rows)
-        const uint4 ml = s_meta[n - 1];
-        const uint32_t b_end = ml.y + (((ml.z & 0xffffu) + 15u) >> 4);     // one past this round's last block
-        const uint32_t b_beg = s_meta[0].y;
-        uint32_t pr0, pr1, pb0;
-        if (rb + (uint32_t)n < r1) { pr0 = rb + (uint32_t)n; pr1 = min(r1, pr0 + p.rmax); pb0 = b_end; }
-        else { pr0 = nx_r0; pr1 = min(nx_r1, nx_r0 + p.rmax); pb0 = nx_b0; }
-        if (pr1 > pr0) {
-          const uint32_t nrow = pr1 - pr0;
-          uint32_t nblk = (b_end - b_beg) / (uint32_t)n * nrow + 16u;        // as many blocks per read as this round had
-          nblk = pb0 < p.n_blocks ? min(nblk, p.n_blocks - pb0) : 0u;        // never past the arrays
-          l2_prefetch(p.hdr + pr0, nrow * 16u);
-          l2_prefetch(p.blk_off + pr0, nrow * 4u);
-          l2_prefetch(p.cplx + pr0, nrow * 4u);
-          l2_prefetch(p.qual + pb0, nblk * 16u);
-          l2_prefetch(p.seq2 + pb0, nblk * 4u);
-        }
-      }
-      // ---- STAGE: W lanes per read build its bit-plane row; the loads of the next read are issued
-      // before the current one is converted (two reads in flight per lane group)
-      auto fetch = [&](const int i, StageIn& in) {
-        in.m = make_uint4(0, 0, 0, 0);
-        in.qa = make_uint4(0, 0, 0, 0);
-        in.qb = make_uint4(0, 0, 0, 0);
-        in.sa = 0; in.sb = 0;
-        in.r0a = 0; in.r0b = 0; in.r1a = 0; in.r1b = 0;
-        if (lane_ok && i < n) {
-          in.m = s_meta[i];
-          const uint32_t fl = in.m.w;
-          if (fl & F_NEEDQ) {
-            const uint32_t nblk = ((in.m.z & 0xffffu) + 15u) >> 4;
-            if (bi < nblk) { in.qa = __ldg(qual_j + in.m.y); in.sa = __ldg(seq_j + in.m.y); }
-            if (bi + 1 < nblk) { in.qb = __ldg(qual_j + in.m.y + 1); in.sb = __ldg(seq_j + in.m.y + 1); }
-            if (!(fl & F_SIMPLE) && (fl & F_OVL)) {
-              const uint32_t* __restrict__ rec = p.cigar + s_cplx[i];
-              in.r0a = __ldg(rec);       // n_runs
-              in.r0b = __ldg(rec + 1);
-              in.r1a = __ldg(rec + 2);
-              in.r1b = __ldg(rec + 3);   // may belong to the next record when n_runs == 1 (ignored then)
-            }
-          }
-        }
-      };
-      auto process = [&](const int i, const StageIn& cur) {
-        const bool rowok = lane_ok && i < n;
-        const uint4 m = cur.m;
-        const uint32_t lq = m.z & 0xffffu, flags = m.w;
-        const bool needq = (flags & F_NEEDQ) != 0;
-        uint32_t qsum = 0, a01, a23, c01, c23;
-        conv16(cur.qa, p.qadd, qsum, a01, a23);
-        conv16(cur.qb, p.qadd, qsum, c01, c23);
-        const uint32_t qv = __byte_perm(__byte_perm(a01, a23, 0x0040), __byte_perm(c01, c23, 0x0040), 0x5410);
-        const uint32_t ql = __byte_perm(cur.sa, cur.sb, 0x5410);   // low bits of the 2-bit base codes, 32 bases
-        const uint32_t qh = __byte_perm(cur.sa, cur.sb, 0x7632);   // high bits
-        // mean-quality filter (snps.py:151): mean(q) < readq  <=>  sum(q) < readq * l_qseq (exact)
-        uint32_t tot = qsum;
-        #pragma unroll
-        for (uint32_t d = 1; d < W; d <<= 1) {
-          const uint32_t t = __shfl_down_sync(0xffffffffu, tot, d);
-          if (gj + (int)d < (int)W) tot += t;
-        }
-        tot = __shfl_sync(0xffffffffu, tot, gbase);
-        const bool keep = needq && tot >= p.readq_eff * lq;
-        if (gj == 0 && keep && (flags & F_OWNER)) ++my_mapped;               // snps.py:161
-        const bool place = keep && (flags & F_OVL);
-        // ---- CIGAR: every M/=/X run is one shifted, masked copy of the query planes. Bits that
-        // survive a run's mask come from query words of this read, so no lane guards are needed.
-        const bool simple = (flags & F_SIMPLE) != 0;
-        uint32_t n_runs = 0;
-        uint32_t w0 = (m.z >> 16) | (m.x & 0xffff0000u), w1 = 0;   // simple read: q0 = q_start, len = span, x0 = 0
-        if (place) {
-          n_runs = 1;
-          if (!simple) { n_runs = cur.r0a; w0 = cur.r0b; w1 = cur.r1a; }
-        }
-        const uint32_t max_runs = __reduce_max_sync(0xffffffffu, n_runs);
-        const int o32 = (int)(m.x & 31u) - 32 * gj;            // row bit of the read's first base, relative to my word
-        uint32_t rl = 0, rh = 0, rv = 0;
-        auto run = [&](const uint32_t k) {                     // all 32 lanes call it together
-          const int q0 = (int)(w0 & 0xffffu), len = (int)(w0 >> 16);
-          const int p0 = o32 + (int)w1;                        // row bit of the run's first base (my word = 0)
-          const int qs = q0 - p0;                              // query index of bit 0 of my row word
-          const int a = gbase + (qs >> 5), sh = qs & 31;
-          const uint32_t l0 = __shfl_sync(0xffffffffu, ql, a), l1 = __shfl_sync(0xffffffffu, ql, a + 1);
-          const uint32_t h0 = __shfl_sync(0xffffffffu, qh, a), h1 = __shfl_sync(0xffffffffu, qh, a + 1);
-          const uint32_t v0 = __shfl_sync(0xffffffffu, qv, a), v1 = __shfl_sync(0xffffffffu, qv, a + 1);
-          const int lo_b = max(0, p0), hi_b = min(32, p0 + len);
-          if (k < n_runs && hi_b > lo_b) {
-            const uint32_t msk = bit_range_mask(lo_b, hi_b);
-            rl |= __funnelshift_r(l0, l1, sh) & msk;
-            rh |= __funnelshift_r(h0, h1, sh) & msk;
-            rv |= __funnelshift_r(v0, v1, sh) & msk;
-          }
-        };
-        if (max_runs) run(0);
-        if (max_runs > 1) {                                    // some read of this step has an indel / skip
-          for (uint32_t k = 1; k < max_runs; ++k) {
-            if (k < n_runs) {
-              const uint32_t* __restrict__ rec = p.cigar + s_cplx[i];
-              if (k == 1) { w0 = cur.r1b; w1 = __ldg(rec + 4); }
-              else { w0 = __ldg(rec + 1 + 2 * k); w1 = __ldg(rec + 2 + 2 * k); }
-            }
-            run(k);
-          }
-        }
-        if (rowok) {
-          uint32_t slot = ((flags >> 8) & 0xffu) + (uint32_t)gj;
+        uint4* __restrict__ dst = s_rows + (uint32_t)i * W;
+#pragma unroll
+        for (int j = 0; j < WT; ++j) {
+          uint32_t slot = slot0 + (uint32_t)j;
           if (slot >= W) slot -= W;
-          s_rows[(uint32_t)i * W + slot] = make_uint4(rv & ~rh & ~rl, rv & ~rh & rl, rv & rh & ~rl, rv & rh & rl);
-        }
-      };
-      {
-        StageIn sa_, sb_, sc_;                                  // three reads in flight per lane group, rotated without copies
-        int i = warp * G + grp;
-        fetch(i, sa_);
-        fetch(i + istep, sb_);
-        while (true) {
-          fetch(i + 2 * istep, sc_);
-          process(i, sa_);
-          i += istep;
-          if (i - grp >= n) break;
-          fetch(i + 2 * istep, sa_);
-          process(i, sb_);
-          i += istep;
-          if (i - grp >= n) break;
-          fetch(i + 2 * istep, sb_);
-          process(i, sc_);
-          i += istep;
-          if (i - grp >= n) break;
+          dst[slot] = make_uint4(rv[j] & ~rh[j] & ~rl[j], rv[j] & ~rh[j] & rl[j], rv[j] & rh[j] & ~rl[j],
+                                 rv[j] & rh[j] & rl[j]);
         }
       }
       __syncthreads();
@@ -668,7 +615,7 @@ PileKernel pick_kernel(uint32_t row_words) {
 }
 
 size_t pile_smem_bytes(uint32_t W, uint32_t rmax) {
-  return sizeof(uint4) * ((size_t)VCL * NCOL + rmax + (size_t)rmax * W) + sizeof(uint32_t) * rmax;
+  return sizeof(uint4) * ((size_t)VCL * NCOL + (size_t)rmax * W);
 }
 
 }  // namespace
@@ -710,7 +657,7 @@ extern "C" int mb_snps_pileup_dev(mb_ctx* ctx, const mb_dev_reads* reads, const 
     ctx->pile_attr_mask |= 1u << W;
   }
   const size_t fixed = sizeof(uint4) * (size_t)VCL * NCOL;
-  uint32_t rmax = (uint32_t)((ctx->pile_smem - fixed) / (sizeof(uint4) * (W + 1) + sizeof(uint32_t)));
+  uint32_t rmax = (uint32_t)((ctx->pile_smem - fixed) / (sizeof(uint4) * W));
   if (rmax > (uint32_t)LANE_ROWS_MAX * KSUB) rmax = LANE_ROWS_MAX * KSUB;
   rmax &= ~7u;
   cudaStream_t st = ctx->stream;

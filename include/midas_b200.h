@@ -131,6 +131,9 @@ typedef struct {
 #define MB_RF_LONG 0x04u   /* snps: the read does not fit a row of `row_words` 32-position words
                               (reference span or query length too long); it is listed in long_idx[]
                               and counted by the long-read kernel instead of the tile kernel */
+#define MB_RF_RUNS2 0x08u  /* snps, not SIMPLE: exactly two M/=/X runs, the first starting at q_start and at
+                              the read's position; cplx[i] = len0 | inserted << 16 | deleted << 24
+                              (second run: q_start+len0+inserted, ref offset len0+deleted, to ref_span) */
 /* widest bit-plane row the tile kernel stages (32-position words per read) */
 #define MB_ROW_WORDS_MAX 16u
 
@@ -143,7 +146,8 @@ typedef struct {
  *   cplx[i]   for reads without MB_RF_SIMPLE: index into cigar[] of a run record
  *             {n_runs, (q0 | len << 16, x0) per M/=/X run}: query index of the run's first
  *             base, run length, reference offset from the read's start (I/S/D/N/H folded in,
- *             clipped at the contig end); 0xFFFFFFFF for simple reads
+ *             clipped at the contig end); 0xFFFFFFFF for simple reads; the two runs themselves
+ *             for MB_RF_RUNS2 reads
  */
 typedef struct {
   uint64_t n_reads;

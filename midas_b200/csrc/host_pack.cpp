@@ -410,9 +410,22 @@ extern "C" int mb_pack_reads(const mb_plain_reads* in, const mb_layout* L, int m
         const uint32_t* cig = in->cigar + in->cigar_off[i];
         const int64_t n_cig = (int64_t)(in->cigar_off[i + 1] - in->cigar_off[i]);
         const int64_t room = (int64_t)L->contig_len[in->ref_id[i]] - in->pos[i];
-        uint32_t w = write_cplx(cig, n_cig, room, cigar + cg_off[j]);
-        for (uint32_t q = w; q < g.n_cplx_words; ++q) cigar[cg_off[j] + q] = 0;
+        uint32_t* rec = cigar + cg_off[j];
+        uint32_t w = write_cplx(cig, n_cig, room, rec);
+        for (uint32_t q = w; q < g.n_cplx_words; ++q) rec[q] = 0;
         cplx[j] = cg_off[j];
+        // the common indel read = two runs: carried in the cplx word itself (no record fetch)
+        if (rec[0] == 2) {
+          const uint32_t q0 = rec[1] & 0xffffu, len0 = rec[1] >> 16, x0 = rec[2];
+          const uint32_t q1 = rec[3] & 0xffffu, len1 = rec[3] >> 16, x1 = rec[4];
+          const int64_t ins = (int64_t)q1 - (int64_t)(q0 + len0), del = (int64_t)x1 - (int64_t)len0;
+          if (q0 == g.q_start && x0 == 0 && ins >= 0 && ins <= 255 && del >= 0 && del <= 255 &&
+              x1 + len1 == g.ref_span) {
+            cplx[j] = len0 | ((uint32_t)ins << 16) | ((uint32_t)del << 24);
+            h.flags |= MB_RF_RUNS2;
+            hdr[j].flags = h.flags;
+          }
+        }
       } else {
         cplx[j] = 0xFFFFFFFFu;
       }

@@ -71,6 +71,7 @@ struct PileParams {
   uint64_t gpad;
   uint32_t n_ktiles;
   uint32_t n_blocks;          // 16-base blocks in seq2 / qual
+  uint32_t avg_blocks;        // blocks per read, rounded up (prefetch size estimate)
   uint32_t W;                 // row words
   uint32_t rmax;              // rows staged per round
   const int32_t* t_pid;       // [65536] smallest 100*(alen-NM) that passes mapid, per alen
@@ -195,14 +196,6 @@ __global__ void __launch_bounds__(NT, 2) k_pileup_v2(const PileParams p) {
     if (tile >= p.n_ktiles) break;
     const uint32_t ts = tile * KT;
     const uint32_t r0 = p.tile_rng[2 * tile], r1 = p.tile_rng[2 * tile + 1];
-    // thread 0: where the next tile's first round starts (used at this tile's last round; the loads
-    // are issued now so that their latency is long gone by then)
-    uint32_t nx_r0 = 0, nx_r1 = 0, nx_b0 = 0;
-    if (tid == 0 && s_next < p.n_ktiles) {
-      nx_r0 = __ldg(p.tile_rng + 2 * s_next);
-      nx_r1 = __ldg(p.tile_rng + 2 * s_next + 1);
-      nx_b0 = __ldg(p.blk_off + nx_r0);
-    }
     const uint32_t tcol = ts >> 5, tb = tcol % W;
     const uint32_t slot_c = s_mod[tb + (uint32_t)col];                // where my column's word sits in a row
     const uint32_t loc_base = ts - 32u * WMAX;                        // row coordinates are stored relative to it (wraps for ts = 0: no read starts before 0)
@@ -265,6 +258,9 @@ __global__ void __launch_bounds__(NT, 2) k_pileup_v2(const PileParams p) {
 
     uint32_t pass_rows = 0;
     bool accumulate = false;
+    bool pf_valid = false;                                            // thread 0: pf_b0 = first block of the next round
+    uint32_t pf_b0 = 0;
+    if (tid == 0 && r0 + p.rmax < r1) { pf_valid = true; pf_b0 = __ldg(p.blk_off + r0 + p.rmax); }
     for (uint32_t rb = r0; rb < r1; rb += p.rmax) {
       const int n = (int)min(p.rmax, r1 - rb);
       if (pass_rows + (uint32_t)n > PASS_ROWS) {  // keep the shared counters below 2^VCL
@@ -274,13 +270,43 @@ __global__ void __launch_bounds__(NT, 2) k_pileup_v2(const PileParams p) {
       }
       pass_rows += (uint32_t)n;
       __syncthreads();
+      if (tid == 0) {   // L2 prefetch (copy engine) of the rows after this round; their first block was fetched a round ago
+        const uint32_t pr0 = rb + (uint32_t)n, pr1 = min(r1, pr0 + p.rmax);
+        if (pr1 > pr0 && pf_valid) {
+          const uint32_t nrow = pr1 - pr0;
+          uint32_t nblk = nrow * p.avg_blocks + 16u;
+          nblk = pf_b0 < p.n_blocks ? min(nblk, p.n_blocks - pf_b0) : 0u;
+          l2_prefetch(p.hdr + pr0, nrow * 16u);
+          l2_prefetch(p.blk_off + pr0, nrow * 4u);
+          l2_prefetch(p.cplx + pr0, nrow * 4u);
+          l2_prefetch(p.qual + pf_b0, nblk * 16u);
+          l2_prefetch(p.seq2 + pf_b0, nblk * 4u);
+        }
+        const uint32_t nn0 = pr0 + p.rmax;                           // start of the round after the next one
+        pf_valid = nn0 < r1;
+        if (pf_valid) pf_b0 = __ldg(p.blk_off + nn0);
+      }
       // ---- STAGE: one thread per read, everything in registers: header filters (snps.py:148,154,157),
       // row index table, 2W independent 128-bit quality loads (L1 absorbs the stride between lanes),
       // conversion to bit planes, mean-quality filter, CIGAR placement, row store
+      uint4 nh = make_uint4(0, 0, 0, 0);                       // header, block offset, run word and predecessor
+      uint32_t nb0 = 0, ncw = 0, nprev = 0;                     // of this thread's next read: one step ahead
+      if (tid < n) {
+        nh = __ldg(&p.hdr[rb + tid]);
+        nb0 = __ldg(&p.blk_off[rb + tid]);
+        ncw = __ldg(&p.cplx[rb + tid]);
+        if (tid > 0) nprev = __ldg(&p.hdr[rb + tid - 1].x);
+      }
       for (int i = tid; i < n; i += NT) {
         const uint32_t r = rb + (uint32_t)i;
-        const uint4 h = __ldg(&p.hdr[r]);
-        const uint32_t b0 = __ldg(&p.blk_off[r]);
+        const uint4 h = nh;
+        const uint32_t b0 = nb0, cw = ncw, prev_loc = nprev;
+        if (i + NT < n) {
+          nh = __ldg(&p.hdr[r + NT]);
+          nb0 = __ldg(&p.blk_off[r + NT]);
+          ncw = __ldg(&p.cplx[r + NT]);
+          nprev = __ldg(&p.hdr[r + NT - 1].x);
+        }
         const uint32_t loc = h.x, lq = h.y & 0xffffu, alen = h.y >> 16, qstart = h.z & 0xffffu, nm = h.z >> 16;
         const uint32_t span = h.w & 0xffffu, mq = (h.w >> 16) & 0xffu, fl = h.w >> 24;
         bool needq = false, ovl = false, owner = false;
@@ -302,7 +328,7 @@ __global__ void __launch_bounds__(NT, 2) k_pileup_v2(const PileParams p) {
           xi = xi < 0 ? 0 : (xi > kmax ? kmax : xi);
           int xlo = 0;
           if (i > 0) {
-            int xp = (int)(__ldg(&p.hdr[r - 1].x) >> 5) - (int)tcol + (int)W - 1;
+            int xp = (int)(prev_loc >> 5) - (int)tcol + (int)W - 1;
             xp = xp < 0 ? 0 : (xp > kmax ? kmax : xp);
             xlo = xp + 1;
           }
@@ -360,10 +386,16 @@ __global__ void __launch_bounds__(NT, 2) k_pileup_v2(const PileParams p) {
           const uint32_t* __restrict__ rec = p.cigar;
           uint32_t n_runs = 1;
           int wshift = 0;                                           // words the planes have been slid so far
-          if (!simple) { rec = p.cigar + __ldg(p.cplx + r); n_runs = __ldg(rec); }
+          const bool runs2 = (fl & MB_RF_RUNS2) != 0;              // both runs are in the cplx word: no record fetch
+          if (runs2) n_runs = 2;
+          else if (!simple) { rec = p.cigar + cw; n_runs = __ldg(rec); }
           for (uint32_t k = 0; k < n_runs; ++k) {
             int q0 = (int)qstart, x0 = 0, len = (int)span;
-            if (!simple) {
+            if (runs2) {
+              const int len0 = (int)(cw & 0xffffu);
+              if (k == 0) len = len0;
+              else { x0 = len0 + (int)(cw >> 24); q0 = (int)qstart + len0 + (int)((cw >> 16) & 0xffu); len = (int)span - x0; }
+            } else if (!simple) {
               const uint32_t w0 = __ldg(rec + 1 + 2 * k);
               q0 = (int)(w0 & 0xffffu); len = (int)(w0 >> 16); x0 = (int)__ldg(rec + 2 + 2 * k);
             }
@@ -550,11 +582,18 @@ __global__ void __launch_bounds__(256) k_long_reads(const LongParams p) {
     }
     if (!keep) continue;
     const bool simple = (fl & MB_RF_SIMPLE) != 0;
-    const uint32_t* __restrict__ rec = simple ? p.cigar : p.cigar + __ldg(p.cplx + r);
-    const uint32_t n_runs = simple ? 1u : __ldg(rec);
+    const uint32_t* __restrict__ rec = (simple || (fl & MB_RF_RUNS2)) ? p.cigar : p.cigar + __ldg(p.cplx + r);
+    const bool runs2 = (fl & MB_RF_RUNS2) != 0;
+    const uint32_t cw = simple ? 0u : __ldg(p.cplx + r);
+    const uint32_t n_runs = simple ? 1u : (runs2 ? 2u : __ldg(rec));
     for (uint32_t o = 0; o < n_runs; ++o) {
-      const uint32_t w0 = simple ? (qstart | (span << 16)) : __ldg(rec + 1 + 2 * o);
-      const uint32_t x0 = simple ? 0u : __ldg(rec + 2 + 2 * o);
+      uint32_t w0, x0;
+      if (simple) { w0 = qstart | (span << 16); x0 = 0; }
+      else if (runs2) {
+        const uint32_t len0 = cw & 0xffffu, ins = (cw >> 16) & 0xffu, del = cw >> 24;
+        if (o == 0) { w0 = qstart | (len0 << 16); x0 = 0; }
+        else { x0 = len0 + del; w0 = (qstart + len0 + ins) | ((span - x0) << 16); }
+      } else { w0 = __ldg(rec + 1 + 2 * o); x0 = __ldg(rec + 2 + 2 * o); }
       const uint32_t q0 = w0 & 0xffffu, len = w0 >> 16;
       for (uint32_t i = lane; i < len; i += 32) {
         const uint32_t qi = q0 + i;
@@ -690,6 +729,7 @@ extern "C" int mb_snps_pileup_dev(mb_ctx* ctx, const mb_dev_reads* reads, const 
   p.gpad = L->gpad;
   p.n_ktiles = n_ktiles;
   p.n_blocks = (uint32_t)reads->n_blocks;
+  p.avg_blocks = (uint32_t)((reads->n_blocks + reads->n_reads - 1) / (reads->n_reads ? reads->n_reads : 1));
   p.W = W;
   p.rmax = rmax;
   rc = mb::get_filter_tables(ctx, f, &p.t_pid, &p.t_cov);

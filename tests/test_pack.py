@@ -48,8 +48,20 @@ def test_contig_end_overhang_is_clipped():
     pk = lib.PackedReads(_one([(OP_M, 50)], pos=980), lay(), "snps")
     assert pk.hdr[0]["ref_span"] == 20 and pk.hdr[0]["alen"] == 50
     pk = lib.PackedReads(_one([(OP_M, 30), (OP_D, 5), (OP_M, 20)], pos=960), lay(), "snps")
+    # two runs -> carried in the cplx word (MB_RF_RUNS2): len0 | inserted << 16 | deleted << 24; the second
+    # run is clipped at the contig end through ref_span (40 = 30 + 5 deleted + 5 of the 20 matched)
+    assert pk.hdr[0]["flags"] & 8 and pk.hdr[0]["ref_span"] == 40
+    cw = int(pk.cplx[0])
+    assert (cw & 0xFFFF, (cw >> 16) & 0xFF, cw >> 24) == (30, 0, 5)
+
+
+def test_two_run_reads_that_do_not_fit_the_run_word_keep_a_record():
+    pk = lib.PackedReads(_one([(OP_M, 30), (OP_D, 300), (OP_M, 20)], pos=100), lay(), "snps")
+    assert not (pk.hdr[0]["flags"] & 8)
     rec = pk.cigar[int(pk.cplx[0]):]
-    assert rec[0] == 2 and (int(rec[3]) >> 16) == 5 and rec[4] == 35 and pk.hdr[0]["ref_span"] == 40
+    assert rec[0] == 2 and rec[4] == 330
+    pk = lib.PackedReads(_one([(OP_D, 2), (OP_M, 30), (OP_I, 3), (OP_M, 20)], pos=100), lay(), "snps")
+    assert not (pk.hdr[0]["flags"] & 8)            # first run not at the read's position
 
 
 def test_block_encoding_round_trips():

@@ -72,6 +72,8 @@ struct PileParams {
   uint32_t n_ktiles;
   uint32_t n_blocks;          // 16-base blocks in seq2 / qual
   uint32_t avg_blocks;        // blocks per read, rounded up (prefetch size estimate)
+  uint32_t l2_prefetch;       // 1: bulk-prefetch the next round into L2
+  uint32_t row_prefetch;      // 1: each thread prefetches its next read's lines into L2
   uint32_t W;                 // row words
   uint32_t rmax;              // rows staged per round
   const int32_t* t_pid;       // [65536] smallest 100*(alen-NM) that passes mapid, per alen
@@ -272,7 +274,7 @@ __global__ void __launch_bounds__(NT, 2) k_pileup_v2(const PileParams p) {
       __syncthreads();
       if (tid == 0) {   // L2 prefetch (copy engine) of the rows after this round; their first block was fetched a round ago
         const uint32_t pr0 = rb + (uint32_t)n, pr1 = min(r1, pr0 + p.rmax);
-        if (pr1 > pr0 && pf_valid) {
+        if (pr1 > pr0 && pf_valid && p.l2_prefetch) {
           const uint32_t nrow = pr1 - pr0;
           uint32_t nblk = nrow * p.avg_blocks + 16u;
           nblk = pf_b0 < p.n_blocks ? min(nblk, p.n_blocks - pf_b0) : 0u;
@@ -301,6 +303,12 @@ __global__ void __launch_bounds__(NT, 2) k_pileup_v2(const PileParams p) {
         const uint32_t r = rb + (uint32_t)i;
         const uint4 h = nh;
         const uint32_t b0 = nb0, cw = ncw, prev_loc = nprev;
+        if (p.row_prefetch && i + NT < n) {                    // my next read's lines -> L2 while this one is converted
+          const char* q = reinterpret_cast<const char*>(p.qual + nb0);
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(q + 128));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(p.seq2 + nb0));
+        }
         if (i + NT < n) {
           nh = __ldg(&p.hdr[r + NT]);
           nb0 = __ldg(&p.blk_off[r + NT]);
@@ -698,6 +706,7 @@ extern "C" int mb_snps_pileup_dev(mb_ctx* ctx, const mb_dev_reads* reads, const 
   const size_t fixed = sizeof(uint4) * (size_t)VCL * NCOL;
   uint32_t rmax = (uint32_t)((ctx->pile_smem - fixed) / (sizeof(uint4) * W));
   if (rmax > (uint32_t)LANE_ROWS_MAX * KSUB) rmax = LANE_ROWS_MAX * KSUB;
+  if (rmax >= 2u * NT && !getenv("MB_PILE_RAGGED")) rmax = rmax / NT * NT;   // the same number of reads for every thread
   rmax &= ~7u;
   cudaStream_t st = ctx->stream;
   const uint32_t ns = L->n_species;
@@ -729,6 +738,8 @@ extern "C" int mb_snps_pileup_dev(mb_ctx* ctx, const mb_dev_reads* reads, const 
   p.gpad = L->gpad;
   p.n_ktiles = n_ktiles;
   p.n_blocks = (uint32_t)reads->n_blocks;
+  p.row_prefetch = getenv("MB_PILE_ROWPF") ? 1u : 0u;
+  p.l2_prefetch = getenv("MB_PILE_L2PF") ? 1u : 0u;   // measured slower on C2 (1.4x DRAM traffic): off unless asked for
   p.avg_blocks = (uint32_t)((reads->n_blocks + reads->n_reads - 1) / (reads->n_reads ? reads->n_reads : 1));
   p.W = W;
   p.rmax = rmax;

@@ -11,11 +11,12 @@
 //
 //   * the padded genome is cut into KT-position tiles; reads are sorted by coordinate, so the reads
 //     overlapping a tile are one contiguous index range (k_tile_ranges) and a CTA owns a tile;
-//   * STAGE: groups of W lanes turn one read each into a *bit-plane row in reference coordinates*:
-//     lane j converts 32 qualities into a 32-bit "countable" mask (byte-SIMD compare + multiply
-//     gather, no per-base branch), takes the two 2-bit sequence planes as they lie in HBM, and the
-//     CIGAR is applied once per 32-base word with warp shuffles + funnel shifts. The row is stored
-//     in shared memory as W x {A,C,G,T} 32-bit masks aligned to the global 32-position grid;
+//   * STAGE: one thread turns one read into a *bit-plane row in reference coordinates*, entirely in
+//     registers: its qualities arrive as up to 2W independent 128-bit loads, every 16 of them become
+//     a 16-bit "countable" mask (byte-SIMD compare + multiply gather, no per-base branch), the two
+//     2-bit sequence planes are taken as they lie in HBM, and each CIGAR run is applied with one
+//     funnel shift per plane per 32-position word. The row is stored in shared memory as
+//     W x {A,C,G,T} 32-bit masks aligned to the global 32-position grid;
 //   * COUNT: a lane owns a 32-position column and adds the rows covering it with carry-save adders
 //     into bit-sliced ("vertical") counters held in registers: one LOP3 works on 32 positions at
 //     once, ~0.6 instructions per aligned base instead of one shared-memory atomic per base;
@@ -345,9 +346,10 @@ __global__ void __launch_bounds__(NT, 2) k_pileup_v2(const PileParams p) {
             for (int x = xi + 1; x <= kmax + 1; ++x) s_first[x] = (uint32_t)n;
         }
         // query bit planes, 32 bases per word: low / high bit of the base code, countable mask
-        uint32_t ql[WT + 1], qh[WT + 1], qv[WT + 1];
+        // (query word w lives at index w + 1; index 0 is "word -1", zero until the planes are slid)
+        uint32_t ql[WT + 2], qh[WT + 2], qv[WT + 2];
 #pragma unroll
-        for (int w = 0; w <= WT; ++w) { ql[w] = 0; qh[w] = 0; qv[w] = 0; }
+        for (int w = 0; w <= WT + 1; ++w) { ql[w] = 0; qh[w] = 0; qv[w] = 0; }
         bool keep = false;
         if (needq) {
           const uint32_t nblk = (lq + 15u) >> 4;
@@ -371,9 +373,9 @@ __global__ void __launch_bounds__(NT, 2) k_pileup_v2(const PileParams p) {
                 uint32_t a01, a23, c01, c23;
                 conv16(qq[2 * u], p.qadd, qsum, a01, a23);
                 conv16(qq[2 * u + 1], p.qadd, qsum, c01, c23);
-                qv[w0 + u] = __byte_perm(__byte_perm(a01, a23, 0x0040), __byte_perm(c01, c23, 0x0040), 0x5410);
-                ql[w0 + u] = __byte_perm(ss[2 * u], ss[2 * u + 1], 0x5410);
-                qh[w0 + u] = __byte_perm(ss[2 * u], ss[2 * u + 1], 0x7632);
+                qv[w0 + u + 1] = __byte_perm(__byte_perm(a01, a23, 0x0040), __byte_perm(c01, c23, 0x0040), 0x5410);
+                ql[w0 + u + 1] = __byte_perm(ss[2 * u], ss[2 * u + 1], 0x5410);
+                qh[w0 + u + 1] = __byte_perm(ss[2 * u], ss[2 * u + 1], 0x7632);
               }
             }
           }
@@ -388,8 +390,9 @@ __global__ void __launch_bounds__(NT, 2) k_pileup_v2(const PileParams p) {
         if (keep && ovl) {
           const int o = (int)(loc & 31u);
           // run (q0, x0, len): query bases [q0, q0+len) lie at row bits [o + x0, o + x0 + len); row word j
-          // takes query bits [32 j + dq, +32) with dq = q0 - o - x0 = 32 d + sh. d is -1 or 0 for
-          // all but heavily clipped reads: those two cases are selected without a branch.
+          // takes query bits [32 j + dq, +32) with dq = q0 - o - x0 = 32 d + sh. d is -1 for an
+          // unclipped read that does not start on a word boundary; any other d first slides the
+          // planes by whole words (static register moves) so that the per-word code is branch-free.
           const bool simple = (fl & MB_RF_SIMPLE) != 0;
           const uint32_t* __restrict__ rec = p.cigar;
           uint32_t n_runs = 1;
@@ -412,30 +415,27 @@ __global__ void __launch_bounds__(NT, 2) k_pileup_v2(const PileParams p) {
             const int sh = dq & 31;
             // heavily clipped reads / long indels: slide the planes by whole words (static register
             // moves in a short loop) until the word offset is -1 or 0 again
-            while (d > 0) {
+            while (d > -1) {
 #pragma unroll
-              for (int w = 0; w < WT; ++w) { ql[w] = ql[w + 1]; qh[w] = qh[w + 1]; qv[w] = qv[w + 1]; }
-              ql[WT] = 0; qh[WT] = 0; qv[WT] = 0;
+              for (int w = 0; w <= WT; ++w) { ql[w] = ql[w + 1]; qh[w] = qh[w + 1]; qv[w] = qv[w + 1]; }
+              ql[WT + 1] = 0; qh[WT + 1] = 0; qv[WT + 1] = 0;
               --d; ++wshift;
             }
             while (d < -1) {
 #pragma unroll
-              for (int w = WT; w > 0; --w) { ql[w] = ql[w - 1]; qh[w] = qh[w - 1]; qv[w] = qv[w - 1]; }
+              for (int w = WT + 1; w > 0; --w) { ql[w] = ql[w - 1]; qh[w] = qh[w - 1]; qv[w] = qv[w - 1]; }
               ql[0] = 0; qh[0] = 0; qv[0] = 0;
               ++d; --wshift;
             }
-            const bool z = d == 0;
+            // now d == -1: row word j = query words (j-1 : j) funnel-shifted by sh
 #pragma unroll
             for (int j = 0; j < WT; ++j) {
               const int lo_b = max(0, p0 - 32 * j), hi_b = min(32, p0 + len - 32 * j);
               if (hi_b > lo_b) {
                 const uint32_t msk = bit_range_mask(lo_b, hi_b);
-                const uint32_t l0 = z ? ql[j] : (j ? ql[j > 0 ? j - 1 : 0] : 0u), l1 = z ? ql[j + 1] : ql[j];
-                const uint32_t h0 = z ? qh[j] : (j ? qh[j > 0 ? j - 1 : 0] : 0u), h1 = z ? qh[j + 1] : qh[j];
-                const uint32_t v0 = z ? qv[j] : (j ? qv[j > 0 ? j - 1 : 0] : 0u), v1 = z ? qv[j + 1] : qv[j];
-                rl[j] |= __funnelshift_r(l0, l1, sh) & msk;
-                rh[j] |= __funnelshift_r(h0, h1, sh) & msk;
-                rv[j] |= __funnelshift_r(v0, v1, sh) & msk;
+                rl[j] |= __funnelshift_r(ql[j], ql[j + 1], sh) & msk;
+                rh[j] |= __funnelshift_r(qh[j], qh[j + 1], sh) & msk;
+                rv[j] |= __funnelshift_r(qv[j], qv[j + 1], sh) & msk;
               }
             }
           }

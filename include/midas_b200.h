@@ -243,6 +243,33 @@ int mb_genes_coverage(mb_ctx* ctx, const mb_packed_reads* reads, const uint32_t*
                       uint32_t n_genes, const mb_filters* f, int exact_order,
                       mb_gene_out* out_host);
 
+/* ------------------------------------------------------------ merge (snps) */
+/* Pooled allele call across samples for every site of one species: the per-site arithmetic of
+ * GenomicSite in the reference's merge_midas.py snps (midas/merge/snps.py:42-104, driven from
+ * build_sharded_tables :324-360). counts_dev: uint32 [n_samples][4][n_sites] = the per-sample
+ * outputs of mb_snps_pileup stacked; mean_depth_dev: double [n_samples] (Sample mean_coverage,
+ * midas/merge/merge.py:66-74; must be > 0: the reference divides by it, snps.py:99).
+ * Outputs: pooled [4][n_sites] (saturating u32), call [n_sites] (bit field below), count_samples
+ * [n_sites] (samples passing site_depth / site_ratio), sample_depth [n_samples][n_sites]
+ * (major+minor count), sample_maf double [n_samples][n_sites]. Asynchronous on the context stream. */
+typedef struct {
+  double snp_freq;    /* --allele_freq (scripts/merge_midas.py:237) */
+  double site_ratio;  /* --site_ratio  (:245) */
+  int32_t site_depth; /* --site_depth  (:242) */
+  int32_t reserved;
+} mb_merge_params;
+/* call byte of a site: bits 0-1 major allele (index into ACGT), 2-3 minor allele, 4-6 snp_type
+ * (0 none, 1 mono, 2 bi, 3 tri, 4 quad), bit 7 = the site has a minor allele. A site has a major
+ * allele iff its pooled depth is > 0 (snps.py:52-63); otherwise the byte is 0. */
+#define MB_CALL_MAJOR(c) ((c) & 3u)
+#define MB_CALL_MINOR(c) (((c) >> 2) & 3u)
+#define MB_CALL_SNP_TYPE(c) (((c) >> 4) & 7u)
+#define MB_CALL_HAS_MINOR 0x80u
+int mb_merge_sites_dev(mb_ctx* ctx, const uint32_t* counts_dev, uint32_t n_samples, uint64_t n_sites,
+                       const double* mean_depth_dev, const mb_merge_params* mp, uint32_t* pooled_dev,
+                       uint8_t* call_dev, uint32_t* count_samples_dev, uint32_t* sample_depth_dev,
+                       double* sample_maf_dev);
+
 /* ---------------------------------------------------------------- BAM ingest */
 /* Decode a BAM file (BGZF inflate + record parse on n_threads host threads, 0 = all) into the
  * plain records above, in file order; records with refID < 0 are dropped. Replaces what

@@ -40,6 +40,11 @@ class CPlainReads(C.Structure):
                 ("seq_off", C.c_void_p), ("seq", C.c_void_p), ("qual", C.c_void_p)]
 
 
+class CMergeParams(C.Structure):
+    _fields_ = [("snp_freq", C.c_double), ("site_ratio", C.c_double), ("site_depth", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
 class CPackedReads(C.Structure):
     _fields_ = [("n_reads", C.c_uint64), ("n_blocks", C.c_uint64), ("n_cigar_words", C.c_uint64),
                 ("total_bases", C.c_uint64), ("max_ref_span", C.c_uint32), ("sorted", C.c_uint32),
@@ -66,6 +71,7 @@ EXPORTS = [
     "mb_reads_upload", "mb_reads_free", "mb_reads_bytes",
     "mb_snps_pileup_dev", "mb_snps_pileup", "mb_genes_coverage_dev", "mb_genes_coverage",
     "mb_format_snps_bound", "mb_format_snps_rows",
+    "mb_merge_sites_dev",
     "mb_bam_open", "mb_bam_close", "mb_bam_n_ref", "mb_bam_ref_name", "mb_bam_ref_len", "mb_bam_reads", "mb_bam_flags",
 ]
 
@@ -125,6 +131,8 @@ def load():
     L.mb_format_snps_rows.restype = C.c_int64
     L.mb_format_snps_rows.argtypes = [C.c_char_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+    L.mb_merge_sites_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p,
+                                     C.POINTER(CMergeParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.mb_bam_open.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
     L.mb_bam_close.argtypes = [C.c_void_p]
     L.mb_bam_close.restype = None
@@ -337,6 +345,33 @@ class Context:
         f = CFilters.of(filters)
         _check(load().mb_snps_pileup(self._h, packed._p, layout._h, C.byref(f), _ptr(counts), _ptr(stats)))
         return counts, stats
+
+    # ---- merge (snps)
+    def merge_sites(self, counts, mean_depth, snp_freq=0.01, site_depth=1, site_ratio=2.0):
+        """Pooled allele call across samples (reference midas/merge/snps.py GenomicSite).
+        counts: torch CUDA int32/uint32 [S, 4, G] (per-sample pileup outputs stacked); mean_depth: [S] float64.
+        Returns dict of torch CUDA tensors: pooled [4, G] int32 (bits of u32), call [G] uint8,
+        count_samples [G] int32, sample_depth [S, G] int32, sample_maf [S, G] float64."""
+        import torch
+        S, four, G = counts.shape
+        assert four == 4 and counts.is_contiguous() and counts.dtype in (torch.int32, torch.uint32)
+        dev = counts.device
+        md = torch.as_tensor(mean_depth, dtype=torch.float64, device=dev).contiguous()
+        if bool((md <= 0).any()):
+            raise MidasB200Error(-1, "mean_depth must be > 0 for every sample (reference: ZeroDivisionError snps.py:99)")
+        out = dict(pooled=torch.empty((4, G), dtype=torch.int32, device=dev),
+                   call=torch.empty(G, dtype=torch.uint8, device=dev),
+                   count_samples=torch.empty(G, dtype=torch.int32, device=dev),
+                   sample_depth=torch.empty((S, G), dtype=torch.int32, device=dev),
+                   sample_maf=torch.empty((S, G), dtype=torch.float64, device=dev))
+        mp = CMergeParams(float(snp_freq), float(site_ratio), int(site_depth), 0)
+        _check(load().mb_merge_sites_dev(self._h, C.c_void_p(counts.data_ptr()), int(S), int(G),
+                                         C.c_void_p(md.data_ptr()), C.byref(mp),
+                                         C.c_void_p(out["pooled"].data_ptr()), C.c_void_p(out["call"].data_ptr()),
+                                         C.c_void_p(out["count_samples"].data_ptr()),
+                                         C.c_void_p(out["sample_depth"].data_ptr()),
+                                         C.c_void_p(out["sample_maf"].data_ptr())))
+        return out
 
     # ---- genes
     def genes_coverage_dev(self, reads: DevReads, gene_len, n_genes: int, filters: Filters, out, exact_order=False):

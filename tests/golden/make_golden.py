@@ -80,6 +80,22 @@ def genes_case(name, ref, reads, marker, filters):
     shutil.rmtree(tmp)
 
 
+def merge_case(name, snp_freq, site_depth, site_ratio):
+    """Pooled allele call (merge_midas.py snps): the reference's unmodified GenomicSite per site."""
+    from oracle import merge_oracle as mo
+    counts, md = mo.synth_counts(5, 7, 600)
+    counts[:, :, 0] = 0                                   # no reads at all
+    counts[:, :, 1] = 3                                   # four-way tie
+    counts[:, :, 2] = 0
+    counts[0, 2, 2] = 5                                   # one allele in one sample
+    counts[:, :, 3] = [[4, 4, 0, 0]] * 7                  # A/C tie
+    ref = mo.run_reference_sites(counts, md, snp_freq, site_depth, site_ratio)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), counts=counts, mean_depth=md, snp_freq=snp_freq,
+                        site_depth=site_depth, site_ratio=site_ratio,
+                        **{("exp_" + k): v for k, v in ref.items() if k != "freq_text"},
+                        freq_text=np.array(ref["freq_text"]))
+
+
 def main():
     # 1. C2-shaped reads (90 % full matches, indels, clips), two species, default snps filters
     ref, reads = synth.synth_snps(seed=20260102, n_species=2, contigs_per_species=2, contig_len=2500, n_reads=2500,
@@ -98,6 +114,9 @@ def main():
     marker = marker.copy()
     marker[np.asarray(gref.contig_species) == 2] = -1
     genes_case("genes_c3_small", gref, greads, marker, Filters.genes_defaults())
+    # 5. merge_midas.py snps site arithmetic, default and strict parameters
+    merge_case("merge_small", 0.01, 1, 2.0)
+    merge_case("merge_small_strict", 0.2, 5, 1.2)
     print("golden vectors written under", HERE)
 
 

@@ -10,6 +10,8 @@
 
 namespace {
 
+constexpr int MERGE_THREADS = 128;
+
 struct MergeParams {
   const uint32_t* counts;        // [S][4][G]
   const double* mean_depth;      // [S]
@@ -24,14 +26,41 @@ struct MergeParams {
   double* sample_maf;            // [S][G]
 };
 
-__global__ void __launch_bounds__(256) k_merge_sites(const MergeParams p) {
+// One thread per site. STAGED = true: the site's n_samples x 4 counts are read from HBM once and kept
+// in a thread-private column of shared memory for the second (per-sample) pass; otherwise the second
+// pass re-reads them from HBM (any n_samples).
+template <bool STAGED>
+__global__ void __launch_bounds__(MERGE_THREADS) k_merge_sites(const MergeParams p) {
+  extern __shared__ uint32_t s_cnt[];          // [n_samples][4][MERGE_THREADS]
   const uint64_t G = p.n_sites;
-  for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < G; g += (uint64_t)gridDim.x * blockDim.x) {
+  const uint32_t S = p.n_samples;
+  for (uint64_t g = (uint64_t)blockIdx.x * MERGE_THREADS + threadIdx.x; g < G; g += (uint64_t)gridDim.x * MERGE_THREADS) {
     // pooled counts (snps.py:42-47)
     unsigned long long pc[4] = {0, 0, 0, 0};
-    for (uint32_t s = 0; s < p.n_samples; ++s) {
+    uint32_t s = 0;
+    for (; s + 4 <= S; s += 4) {
+      uint32_t v[4][4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t* c = p.counts + (size_t)(s + u) * 4 * G + g;
+        v[u][0] = c[0]; v[u][1] = c[G]; v[u][2] = c[2 * G]; v[u][3] = c[3 * G];
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          pc[k] += v[u][k];
+          if (STAGED) s_cnt[((s + u) * 4 + k) * MERGE_THREADS + threadIdx.x] = v[u][k];
+        }
+    }
+    for (; s < S; ++s) {
       const uint32_t* c = p.counts + (size_t)s * 4 * G + g;
-      pc[0] += c[0]; pc[1] += c[G]; pc[2] += c[2 * G]; pc[3] += c[3 * G];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t x = c[(size_t)k * G];
+        pc[k] += x;
+        if (STAGED) s_cnt[(s * 4 + k) * MERGE_THREADS + threadIdx.x] = x;
+      }
     }
     const unsigned long long depth = pc[0] + pc[1] + pc[2] + pc[3];
 #pragma unroll
@@ -63,22 +92,23 @@ __global__ void __launch_bounds__(256) k_merge_sites(const MergeParams p) {
     p.call[g] = (uint8_t)call;
     // compute_per_sample_mafs (snps.py:78-91) + compute_prevalence (snps.py:93-104)
     uint32_t pass = 0;
-    for (uint32_t s = 0; s < p.n_samples; ++s) {
-      const uint32_t* c = p.counts + (size_t)s * 4 * G + g;
+    for (uint32_t t = 0; t < S; ++t) {
       uint32_t sd = 0;
       double maf = 0.0;
       if (has_major) {
-        const uint32_t cm = c[(size_t)major * G];
+        const uint32_t cm = STAGED ? s_cnt[(t * 4 + major) * MERGE_THREADS + threadIdx.x]
+                                   : p.counts[(size_t)t * 4 * G + (size_t)major * G + g];
         if (!has_minor) sd = cm;
         else {
-          const uint32_t cn = c[(size_t)minor * G];
+          const uint32_t cn = STAGED ? s_cnt[(t * 4 + minor) * MERGE_THREADS + threadIdx.x]
+                                     : p.counts[(size_t)t * 4 * G + (size_t)minor * G + g];
           sd = cm + cn;
           maf = sd > 0 ? __ddiv_rn((double)cn, (double)sd) : 0.0;
         }
       }
-      p.sample_depth[(size_t)s * G + g] = sd;
-      p.sample_maf[(size_t)s * G + g] = maf;
-      const bool fail = ((int64_t)sd < (int64_t)p.site_depth) || (__ddiv_rn((double)sd, p.mean_depth[s]) > p.site_ratio);
+      p.sample_depth[(size_t)t * G + g] = sd;
+      p.sample_maf[(size_t)t * G + g] = maf;
+      const bool fail = ((int64_t)sd < (int64_t)p.site_depth) || (__ddiv_rn((double)sd, p.mean_depth[t]) > p.site_ratio);
       pass += fail ? 0u : 1u;
     }
     p.count_samples[g] = pass;
@@ -110,10 +140,22 @@ extern "C" int mb_merge_sites_dev(mb_ctx* ctx, const uint32_t* counts_dev, uint3
   p.count_samples = count_samples_dev;
   p.sample_depth = sample_depth_dev;
   p.sample_maf = sample_maf_dev;
-  const uint64_t want = (n_sites + 255) / 256;
-  const uint32_t grid = (uint32_t)std::min<uint64_t>(want, (uint64_t)ctx->sm_count * 8);
+  const uint64_t want = (n_sites + MERGE_THREADS - 1) / MERGE_THREADS;
+  const size_t smem = sizeof(uint32_t) * 4 * (size_t)n_samples * MERGE_THREADS;
+  // staging the counts in shared memory halves the HBM reads but leaves 4-8 warps per SM: measured 1.3-3x
+  // slower than re-reading (profiles/r01_merge_bench.json); kept for small sample counts only
+  const bool staged = smem <= 16 * 1024;
+  int occ = 1;
+  if (staged) {
+    MB_CUDA_TRY(cudaFuncSetAttribute(k_merge_sites<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_merge_sites<true>, MERGE_THREADS, smem));
+  } else {
+    MB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_merge_sites<false>, MERGE_THREADS, 0));
+  }
+  const uint32_t grid = (uint32_t)std::min<uint64_t>(want, (uint64_t)ctx->sm_count * (occ > 0 ? occ : 1));
   { int trc = mb::timing_begin(ctx); if (trc) return trc; }
-  k_merge_sites<<<grid, 256, 0, ctx->stream>>>(p);
+  if (staged) k_merge_sites<true><<<grid, MERGE_THREADS, smem, ctx->stream>>>(p);
+  else k_merge_sites<false><<<grid, MERGE_THREADS, 0, ctx->stream>>>(p);
   { int trc = mb::timing_end(ctx); if (trc) return trc; }
   ctx->launches++;
   MB_CUDA_TRY(cudaGetLastError());

@@ -46,3 +46,32 @@ def test_genes_pipeline_writes_the_reference_files(case, tmp_path):
         got = gzip.open(os.path.join(out, "genes", "output", sid + ".genes.gz"), "rb").read()
         assert got == exp[sid + ".genes.tsv"], sid
     assert open(os.path.join(out, "genes", "summary.txt"), "rb").read() == exp["summary.txt"]
+
+
+def test_cli_snps_and_genes(tmp_path):
+    """scripts/run_midas.py {snps --pileup, genes --call_genes} as a user runs them (subprocess)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cli = os.path.join(root, "scripts", "run_midas.py")
+    ref, reads, filters, extra = load_case("snps_c2_small")
+    db, out = fixtures.write_snps_fixture(str(tmp_path / "s"), ref, reads, lowercase_some=True)
+    r = subprocess.run([sys.executable, cli, "snps", out, "-d", db, "--pileup", "-t", "2"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    exp = expected("snps_c2_small")
+    for sid in ref.species_ids:
+        assert gzip.open(os.path.join(out, "snps", "output", sid + ".snps.gz"), "rb").read() == exp[sid + ".snps.tsv"]
+    assert open(os.path.join(out, "snps", "summary.txt"), "rb").read() == exp["summary.txt"]
+    assert os.path.isfile(os.path.join(out, "snps", "log.txt"))
+    # a missing BAM is a clean error, not a crash
+    os.remove(os.path.join(out, "snps", "temp", "genomes.bam"))
+    r = subprocess.run([sys.executable, cli, "snps", out, "-d", db, "--pileup"], capture_output=True, text=True)
+    assert r.returncode != 0 and "genomes.bam not found" in r.stderr
+    gref, greads, gfilters, gextra = load_case("genes_c3_small")
+    db2, out2 = fixtures.write_genes_fixture(str(tmp_path / "g"), gref, greads, np.array(gextra["marker"], np.int32))
+    r = subprocess.run([sys.executable, cli, "genes", out2, "-d", db2], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    gexp = expected("genes_c3_small")
+    for sid in gref.species_ids:
+        assert gzip.open(os.path.join(out2, "genes", "output", sid + ".genes.gz"), "rb").read() == gexp[sid + ".genes.tsv"]
+    assert open(os.path.join(out2, "genes", "summary.txt"), "rb").read() == gexp["summary.txt"]

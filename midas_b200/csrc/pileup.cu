@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(NT, 2) k_pileup_v2(const PileParams p) {
   uint4* s_rows = s_vc + VCL * NCOL;                                  // [rmax][W] x {A,C,G,T}
   __shared__ uint32_t s_first[FIRST_N];
   __shared__ unsigned long long s_red[4];                             // covered, depth, aligned, mapped
-  __shared__ uint32_t s_tile, s_next, s_nmax;
+  __shared__ uint32_t s_tile, s_nmax;
   __shared__ uint8_t s_mod[NCOL + 2 * WMAX + 1];                      // x % W for small x
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -189,14 +189,16 @@ __global__ void __launch_bounds__(NT, 2) k_pileup_v2(const PileParams p) {
   for (int i = tid; i < VCL * NCOL; i += NT) s_vc[i] = make_uint4(0, 0, 0, 0);
   for (int i = tid; i < NCOL + 2 * WMAX + 1; i += NT) s_mod[i] = (uint8_t)((uint32_t)i % W);
 
-  if (tid == 0) s_next = atomicAdd(p.sched, 1u);
+  uint32_t next_tile = 0;                                             // thread 0: the tile after the current one
+  if (tid == 0) next_tile = atomicAdd(p.sched, 1u);
   for (;;) {
     __syncthreads();
-    if (tid == 0) { s_tile = s_next; s_next = atomicAdd(p.sched, 1u); s_nmax = 0; }   // one tile of look-ahead
+    if (tid == 0) { s_tile = next_tile; s_nmax = 0; }
     if (tid < 4) s_red[tid] = 0;
     __syncthreads();
     const uint32_t tile = s_tile;
     if (tile >= p.n_ktiles) break;
+    if (tid == 0) next_tile = atomicAdd(p.sched, 1u);                 // its latency hides behind this tile's work
     const uint32_t ts = tile * KT;
     const uint32_t r0 = p.tile_rng[2 * tile], r1 = p.tile_rng[2 * tile + 1];
     const uint32_t tcol = ts >> 5, tb = tcol % W;

@@ -267,8 +267,8 @@ def main():
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = bases_all / float(te.item()) / 1e9
-    h2d = packed.nbytes
-    d2h = counts_np.nbytes + st_host.nbytes
+    h2d = packed.nbytes * world               # whole job: every rank copies its own species in and out
+    d2h = (counts_np.nbytes + st_host.nbytes) * world
     sampler.stop_flag = True
 
     # sanity: the device-resident and host-buffer paths agree, and something was counted

@@ -22,29 +22,34 @@ from ..soa import Filters, RefSet
 from . import io as mio
 
 
+_PAN_FILES = ("centroids.ffn", "cluster_info.txt", "gene_info.txt")
+
+
 class Species:
-    """reference genes.py:12-30"""
+    """Per-species record; attribute names are the reference's (genes.py:12-30), so its own epilogue
+    and merge code can consume these objects."""
 
     def __init__(self, id):
         self.id = id
         self.paths = {}
-        self.genes = []
+        self.genes = []                      # per-gene depths, filled by count_mapped_bp
         self.pangenome_size = 0
         self.aligned_reads = 0
         self.mapped_reads = 0
-        self.markers = defaultdict(float)
+        self.markers = defaultdict(float)    # marker_id -> summed depth
 
     def init_ref_db(self, ref_db):
-        self.dir = "%s/pan_genomes/%s" % (ref_db, self.id)
-        for ext in ["", ".gz"]:
-            for file in ["centroids.ffn", "cluster_info.txt", "gene_info.txt"]:
-                inpath = "%s/%s%s" % (self.dir, file, ext)
-                if os.path.isfile(inpath):
-                    self.paths[file] = inpath
+        """Locate <db>/pan_genomes/<species>/{centroids.ffn,cluster_info.txt,gene_info.txt}[.gz]; a .gz
+        file wins over a plain one, as in the reference (the later extension overwrites)."""
+        self.dir = os.path.join(ref_db, "pan_genomes", self.id).replace(os.sep, "/")
+        for name in _PAN_FILES:
+            for candidate in (self.dir + "/" + name, self.dir + "/" + name + ".gz"):
+                if os.path.isfile(candidate):
+                    self.paths[name] = candidate
 
 
 class Gene:
-    """reference genes.py:50-59"""
+    """Per-gene record (reference genes.py:50-59 attribute names)."""
 
     def __init__(self, id):
         self.id = id
@@ -57,36 +62,38 @@ class Gene:
 
 
 def initialize_species(args):
-    species = {}
-    splist = "%s/genes/species.txt" % args["outdir"]
+    """Species listed in <outdir>/genes/species.txt (reference genes.py:32-48). Selecting species from
+    a species profile (--build_db) is upstream of the hot path and not part of this package."""
     if args.get("build_db"):
         sys.exit("\nError: the --build_db stage is not part of midas_b200; run it with the reference and "
                  "re-enter with --call_genes")
-    elif os.path.isfile(splist):
-        for line in open(splist):
-            id = line.rstrip()
-            species[id] = Species(id)
+    species = {}
+    listing = "%s/genes/species.txt" % args["outdir"]
+    if os.path.isfile(listing):
+        with open(listing) as fh:
+            for line in fh:
+                sid = line.rstrip()
+                species[sid] = Species(sid)
     for sp in species.values():
         sp.init_ref_db(args["db"])
     return species
 
 
 def initialize_genes(args, species):
-    """reference genes.py:61-82"""
+    """Gene ids, owning species and lengths from each pangenome's centroids.ffn; marker ids from
+    <db>/marker_genes/phyeco.map for genes that exist (reference genes.py:61-82)."""
     genes = {}
     for sp in species.values():
-        for seq_id, seq in mio.read_fasta(sp.paths["centroids.ffn"]):
-            genes[seq_id] = Gene(seq_id)
-            genes[seq_id].species_id = sp.id
-            genes[seq_id].length = len(seq)
+        for gene_id, seq in mio.read_fasta(sp.paths["centroids.ffn"]):
+            g = Gene(gene_id)
+            g.species_id, g.length = sp.id, len(seq)
+            genes[gene_id] = g
             sp.pangenome_size += 1
-    path = "%s/marker_genes/phyeco.map" % args["db"]
-    file = mio.iopen(path)
-    reader = csv.DictReader(file, delimiter="\t")
-    for r in reader:
-        if r["gene_id"] in genes:
-            genes[r["gene_id"]].marker_id = r["marker_id"]
-    file.close()
+    with mio.iopen("%s/marker_genes/phyeco.map" % args["db"]) as fh:
+        for row in csv.DictReader(fh, delimiter="\t"):
+            g = genes.get(row["gene_id"])
+            if g is not None:
+                g.marker_id = row["marker_id"]
     return genes
 
 
@@ -135,52 +142,56 @@ def count_mapped_bp(args, species, genes, ctx=None):
         sp.mapped_reads += gene.mapped_reads
     print("  total aligned reads: %s" % sum([sp.aligned_reads for sp in species.values()]))
     print("  total mapped reads: %s" % sum([sp.mapped_reads for sp in species.values()]))
-    for gene in genes.values():
-        species[gene.species_id].genes.append(gene.depth)
+    # per-species summaries (genes.py:191-203): mean over covered genes in dict order (np.mean of a list)
+    for g in genes.values():
+        species[g.species_id].genes.append(g.depth)
     for sp in species.values():
-        non_zero_genes = [_ for _ in sp.genes if _ > 0]
-        sp.covered_genes = len(non_zero_genes)
-        sp.mean_coverage = np.mean(non_zero_genes) if len(non_zero_genes) > 0 else 0
+        covered = [d for d in sp.genes if d > 0]
+        sp.covered_genes = len(covered)
+        sp.mean_coverage = np.mean(covered) if covered else 0
         sp.fraction_covered = sp.covered_genes / float(sp.pangenome_size)
 
 
 def normalize(args, species, genes):
-    """reference genes.py:205-218 (np.median([]) -> nan for a species without marker genes, as there)."""
-    for gene in genes.values():
-        if gene.marker_id is not None:
-            species[gene.species_id].markers[gene.marker_id] += gene.depth
+    """Copy number = depth / median depth of the species' marker genes (reference genes.py:205-218).
+    A species without marker genes gets np.median([]) = nan (with numpy's warning), as there, and its
+    genes keep copies = 0.0 because nan > 0 is false."""
+    for g in genes.values():
+        if g.marker_id is not None:
+            species[g.species_id].markers[g.marker_id] += g.depth
     for sp in species.values():
         sp.marker_coverage = np.median(list(sp.markers.values()))
-    for gene in genes.values():
-        sp = species[gene.species_id]
-        if sp.marker_coverage > 0:
-            gene.copies = gene.depth / sp.marker_coverage
+    for g in genes.values():
+        cov = species[g.species_id].marker_coverage
+        if cov > 0:
+            g.copies = g.depth / cov
+
+
+GENES_HEADER = ("gene_id", "count_reads", "coverage", "copy_number")
+SUMMARY_HEADER = ("species_id", "pangenome_size", "covered_genes", "fraction_covered", "mean_coverage",
+                  "marker_coverage", "aligned_reads", "mapped_reads")
+
+
+def _tsv(values):
+    return "\t".join(str(v) for v in values) + "\n"          # numbers print with str(), as in the reference
 
 
 def write_results(args, species, genes):
-    """reference genes.py:220-245"""
-    header = ["gene_id", "count_reads", "coverage", "copy_number"]
-    for sp in species.values():
-        path = "/".join([args["outdir"], "genes/output/%s.genes.gz" % sp.id])
-        sp.out = mio.iopen(path, "w")
-        sp.out.write("\t".join(header) + "\n")
+    """<outdir>/genes/output/<species>.genes.gz (genes in sorted id order, genes.py:229) and
+    <outdir>/genes/summary.txt (genes.py:238-245)."""
+    rows = {sid: [_tsv(GENES_HEADER)] for sid in species}
     for gene_id in sorted(genes):
-        gene = genes[gene_id]
-        sp = species[gene.species_id]
-        values = [gene.id, gene.mapped_reads, gene.depth, gene.copies]
-        sp.out.write("\t".join([str(_) for _ in values]) + "\n")
-    for sp in species.values():
-        sp.out.close()
-    path = "/".join([args["outdir"], "genes/summary.txt"])
-    file = open(path, "w")
-    header = ["species_id", "pangenome_size", "covered_genes", "fraction_covered", "mean_coverage",
-              "marker_coverage", "aligned_reads", "mapped_reads"]
-    file.write("\t".join(header) + "\n")
-    for sp in species.values():
-        values = [sp.id, sp.pangenome_size, sp.covered_genes, sp.fraction_covered, sp.mean_coverage,
-                  sp.marker_coverage, sp.aligned_reads, sp.mapped_reads]
-        file.write("\t".join([str(_) for _ in values]) + "\n")
-    file.close()
+        g = genes[gene_id]
+        rows[g.species_id].append(_tsv((g.id, g.mapped_reads, g.depth, g.copies)))
+    for sid, lines in rows.items():
+        out = mio.iopen("%s/genes/output/%s.genes.gz" % (args["outdir"], sid), "w")
+        out.write("".join(lines))
+        out.close()
+    with open("%s/genes/summary.txt" % args["outdir"], "w") as fh:
+        fh.write(_tsv(SUMMARY_HEADER))
+        for sp in species.values():
+            fh.write(_tsv((sp.id, sp.pangenome_size, sp.covered_genes, sp.fraction_covered, sp.mean_coverage,
+                           sp.marker_coverage, sp.aligned_reads, sp.mapped_reads)))
 
 
 def remove_tmp(args):

@@ -181,21 +181,18 @@ def pysam_pileup(args, species, contigs, ctx=None):
     print("  %s minutes" % round((time() - start) / 60, 2))
 
 
+SUMMARY_FIELDS = ("species_id", "genome_length", "covered_bases", "fraction_covered", "mean_coverage",
+                  "aligned_reads", "mapped_reads")
+
+
 def snps_summary(args, species):
-    """reference snps.py:247-262 (numbers formatted with str(), as there)."""
-    fields = ["species_id", "genome_length", "covered_bases", "fraction_covered", "mean_coverage",
-              "aligned_reads", "mapped_reads"]
-    outfile = open(args["outdir"] + "/snps/summary.txt", "w")
-    outfile.write("\t".join(fields) + "\n")
-    for sp in species.values():
-        outfile.write(sp.id + "\t")
-        outfile.write(str(sp.genome_length) + "\t")
-        outfile.write(str(sp.covered_bases) + "\t")
-        outfile.write(str(sp.fraction_covered) + "\t")
-        outfile.write(str(sp.mean_coverage) + "\t")
-        outfile.write(str(sp.aligned_reads) + "\t")
-        outfile.write(str(sp.mapped_reads) + "\n")
-    outfile.close()
+    """<outdir>/snps/summary.txt (reference snps.py:247-262): one row per species, numbers printed
+    with str() (floats as shortest round-trip repr), species in dict order."""
+    with open("%s/snps/summary.txt" % args["outdir"], "w") as fh:
+        fh.write("\t".join(SUMMARY_FIELDS) + "\n")
+        for sp in species.values():
+            fh.write("\t".join(str(getattr(sp, name) if name != "species_id" else sp.id)
+                               for name in SUMMARY_FIELDS) + "\n")
 
 
 def remove_tmp(args):

@@ -101,3 +101,24 @@ def test_empty_and_tiny(ctx):
     _check(ctx, ref, empty, Filters())
     one = gen.random_reads(2, ref, 1, max_len=50)
     _check(ctx, ref, one, Filters(mapid=0.0, aln_cov=0.0, readq=0, mapq=0, baseq=0))
+
+
+def test_full_size_c2(ctx):
+    """BASELINE.json configs[1] at full size (5 M x 150 bp on 4 Mbp, the bench workload): every counter
+    and every stat against the oracle (run on all host threads), plus the size-independent identities
+    total_depth = sum of counters and covered_bases = #positions with depth > 0."""
+    import os
+    ref, reads = synth.synth_snps(seed=synth.SEED_C2, n_species=1, contigs_per_species=1, contig_len=4_000_000,
+                                  n_reads=5_000_000, read_len=150, keep_ref_seq=False)
+    lay = lib.Layout.of(ref)
+    pk = lib.PackedReads(reads, lay, "snps")
+    counts, stats = ctx.snps_pileup(pk, lay, Filters())
+    got = lay.unpad(counts)
+    depth = got.astype(np.uint64).sum(0)
+    assert int(stats["total_depth"][0]) == int(depth.sum())
+    assert int(stats["covered_bases"][0]) == int((depth > 0).sum())
+    assert int(stats["genome_length"][0]) == 4_000_000 and int(stats["aligned_reads"][0]) == 5_000_000
+    exp_counts, exp_stats = oracle.snps_pileup(reads, ref, Filters(), threads=os.cpu_count() or 1)
+    assert np.array_equal(got, exp_counts.astype(np.uint32))
+    for k, name in enumerate(lib.STATS_DTYPE.names):
+        assert int(stats[name][0]) == int(exp_stats[0, k]), name

@@ -130,6 +130,17 @@ __device__ __forceinline__ void l2_prefetch(const void* ptr, uint32_t bytes) {
   if (n) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(n) : "memory");
 }
 
+__device__ __forceinline__ uint32_t shl_clamp(uint32_t v, uint32_t n) {   // v << n, 0 for n >= 32
+  uint32_t r;
+  asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(n));
+  return r;
+}
+__device__ __forceinline__ uint32_t shr_clamp(uint32_t v, uint32_t n) {   // v >> n, 0 for n >= 32
+  uint32_t r;
+  asm("shr.u32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(n));
+  return r;
+}
+
 __device__ __forceinline__ uint32_t bit_range_mask(int lo, int hi) {  // bits [lo, hi) of a word, 0 <= lo < hi <= 32
   const uint32_t up = 0xffffffffu << lo;
   const uint32_t dn = 0xffffffffu >> (32 - hi);
@@ -430,15 +441,17 @@ __global__ void __launch_bounds__(NT, 2) k_pileup_v2(const PileParams p) {
               ++d; --wshift;
             }
             // now d == -1: row word j = query words (j-1 : j) funnel-shifted by sh
+            // mask of the run's bits inside word j = [p0 - 32 j, p0 + len - 32 j) clipped to [0, 32): built
+            // branch-free from clamped shifts (a PTX shift by >= 32 gives 0)
 #pragma unroll
             for (int j = 0; j < WT; ++j) {
-              const int lo_b = max(0, p0 - 32 * j), hi_b = min(32, p0 + len - 32 * j);
-              if (hi_b > lo_b) {
-                const uint32_t msk = bit_range_mask(lo_b, hi_b);
-                rl[j] |= __funnelshift_r(ql[j], ql[j + 1], sh) & msk;
-                rh[j] |= __funnelshift_r(qh[j], qh[j + 1], sh) & msk;
-                rv[j] |= __funnelshift_r(qv[j], qv[j + 1], sh) & msk;
-              }
+              const int r0b = p0 - 32 * j, r1b = r0b + len;
+              const uint32_t up = shl_clamp(0xffffffffu, (uint32_t)max(r0b, 0));
+              const uint32_t dn = shr_clamp(0xffffffffu, (uint32_t)(32 - min(max(r1b, 0), 32)));
+              const uint32_t msk = up & dn;
+              rl[j] |= __funnelshift_r(ql[j], ql[j + 1], sh) & msk;
+              rh[j] |= __funnelshift_r(qh[j], qh[j + 1], sh) & msk;
+              rv[j] |= __funnelshift_r(qv[j], qv[j + 1], sh) & msk;
             }
           }
         }

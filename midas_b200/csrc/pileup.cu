@@ -425,7 +425,8 @@ __global__ void __launch_bounds__(NT, 2) k_pileup_v2(const PileParams p) {
             }
             const int p0 = o + x0, dq = q0 - p0;
             int d = (dq >> 5) - wshift;
-            const int sh = dq & 31;
+            int sh = dq & 31;
+            if (d == 0 && sh == 0) { d = -1; sh = 32; }   // a read starting on a word boundary: shift by a whole word
             // heavily clipped reads / long indels: slide the planes by whole words (static register
             // moves in a short loop) until the word offset is -1 or 0 again
             while (d > -1) {
@@ -449,9 +450,9 @@ __global__ void __launch_bounds__(NT, 2) k_pileup_v2(const PileParams p) {
               const uint32_t up = shl_clamp(0xffffffffu, (uint32_t)max(r0b, 0));
               const uint32_t dn = shr_clamp(0xffffffffu, (uint32_t)(32 - min(max(r1b, 0), 32)));
               const uint32_t msk = up & dn;
-              rl[j] |= __funnelshift_r(ql[j], ql[j + 1], sh) & msk;
-              rh[j] |= __funnelshift_r(qh[j], qh[j + 1], sh) & msk;
-              rv[j] |= __funnelshift_r(qv[j], qv[j + 1], sh) & msk;
+              rl[j] |= __funnelshift_rc(ql[j], ql[j + 1], sh) & msk;   // clamped: sh = 32 selects the upper word
+              rh[j] |= __funnelshift_rc(qh[j], qh[j + 1], sh) & msk;
+              rv[j] |= __funnelshift_rc(qv[j], qv[j + 1], sh) & msk;
             }
           }
         }

@@ -58,8 +58,8 @@ const char* mb_last_error(void);
 /* species regions of the padded coordinate space start on multiples of MB_TILE positions
  * (a multiple of the kernel's tile, so no tile ever holds two species) */
 #define MB_TILE 4096u
-/* bases per packed block (16 qualities = one 128-bit load, 16 x 2-bit = one u32) */
-#define MB_BLOCK 16u
+/* bases per packed block: every per-base bit of 32 consecutive query bases is one 32-bit word */
+#define MB_BLOCK 32u
 
 /* ----------------------------------------------------------------- filters */
 /* args['mapid','aln_cov','readq','mapq','baseq'] of the reference
@@ -138,11 +138,19 @@ typedef struct {
 #define MB_ROW_WORDS_MAX 16u
 
 /* Struct of arrays, identical on host and in HBM (upload is a plain copy).
- *   blk_off[i]..blk_off[i+1]  MB_BLOCK-base blocks of read i (ceil(l_qseq/16))
- *   seq2[b]   16 bases x 2 bit, planar inside the block: bit k = low bit of base k,
- *             bit 16+k = high bit of base k (A=0 C=1 G=2 T=3; non-ACGT and padding = 0)
- *   qual[16b+k] bit 7 = base k is a literal A/C/G/T (countable), bits 0-6 = Phred;
- *             padding bytes are 0
+ * The per-base data of a read is bit-planar: the read is cut into MB_BLOCK-base blocks and every
+ * per-base bit of a block is one 32-bit word (bit k = base 32*b + k), so the kernels test and place
+ * 32 bases with one logic instruction. Block b of read i is the n_planes words at
+ *   planes[4*vec_off[i] + b*n_planes + p]            (the read's region is 16-byte aligned,
+ *                                                     ceil(l_qseq/32)*n_planes words, zero padded)
+ * snps mode (n_planes = 3 + q_planes):
+ *   p = 0, 1  low / high bit of the base code (A=0 C=1 G=2 T=3; anything else 0)
+ *   p = 2     "candidate": the base is a literal A/C/G/T, lies in an M/=/X run of the CIGAR and its
+ *             reference position is inside the contig: the only bases count_coverage can ever
+ *             count, whatever the filters are (soft clips, insertions, N never count)
+ *   p = 3+k   bit k of the base's Phred quality, k < q_planes
+ * genes mode (n_planes = q_planes): only the Phred bit planes (the path reads nothing else).
+ * q_planes is 6 when every quality of the batch is <= 63, else 7 (Phred <= 127 is required).
  *   cplx[i]   for reads without MB_RF_SIMPLE: index into cigar[] of a run record
  *             {n_runs, (q0 | len << 16, x0) per M/=/X run}: query index of the run's first
  *             base, run length, reference offset from the read's start (I/S/D/N/H folded in,
@@ -151,7 +159,7 @@ typedef struct {
  */
 typedef struct {
   uint64_t n_reads;
-  uint64_t n_blocks;
+  uint64_t n_vec;            /* 16-byte units in planes[] */
   uint64_t n_cigar_words;
   uint64_t total_bases;      /* sum of l_qseq (the Gbases numerator) */
   uint32_t max_ref_span;
@@ -160,13 +168,14 @@ typedef struct {
                                 that at most 0.1 % of the reads need more (those carry MB_RF_LONG);
                                 2..MB_ROW_WORDS_MAX; 0 in genes mode */
   uint32_t n_long;           /* number of MB_RF_LONG reads */
+  uint32_t q_planes;         /* Phred bit planes per block: 6 or 7 */
+  uint32_t n_planes;         /* words per block: 3 + q_planes (snps) or q_planes (genes) */
   const uint32_t* long_idx;  /* [n_long] ascending indices of the MB_RF_LONG reads */
   const mb_read_hdr* hdr;    /* [n_reads] */
-  const uint32_t* blk_off;   /* [n_reads+1] */
+  const uint32_t* vec_off;   /* [n_reads+1] first 16-byte unit of each read's region in planes[] */
   const uint32_t* cplx;      /* [n_reads] */
   const uint32_t* cigar;     /* [n_cigar_words] */
-  const uint32_t* seq2;      /* [n_blocks] */
-  const uint8_t* qual;       /* [n_blocks*16] */
+  const uint32_t* planes;    /* [4*n_vec] */
 } mb_packed_reads;
 
 /* Host-side re-layout of decoded BAM records into the packed SoA (the step

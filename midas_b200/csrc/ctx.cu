@@ -247,21 +247,22 @@ namespace mb {
 int upload_reads(mb_ctx* c, const mb_packed_reads* h, mb_dev_reads* d, bool staged) {
   memset(d, 0, sizeof(*d));
   d->n_reads = h->n_reads;
-  d->n_blocks = h->n_blocks;
+  d->n_vec = h->n_vec;
+  d->q_planes = h->q_planes;
+  d->n_planes = h->n_planes;
   d->n_cigar_words = h->n_cigar_words;
   d->total_bases = h->total_bases;
   d->max_ref_span = h->max_ref_span;
   d->sorted = h->sorted;
   d->row_words = h->row_words;
   d->n_long = h->n_long;
-  struct Part { void** dst; const void* src; size_t bytes; } parts[7] = {
+  struct Part { void** dst; const void* src; size_t bytes; } parts[6] = {
       {(void**)&d->long_idx, h->long_idx, sizeof(uint32_t) * (size_t)h->n_long},
       {(void**)&d->hdr, h->hdr, sizeof(mb_read_hdr) * (size_t)h->n_reads},
-      {(void**)&d->blk_off, h->blk_off, sizeof(uint32_t) * (size_t)(h->n_reads + 1)},
+      {(void**)&d->vec_off, h->vec_off, sizeof(uint32_t) * (size_t)(h->n_reads + 1)},
       {(void**)&d->cplx, h->cplx, sizeof(uint32_t) * (size_t)h->n_reads},
       {(void**)&d->cigar, h->cigar, sizeof(uint32_t) * (size_t)h->n_cigar_words},
-      {(void**)&d->seq2, h->seq2, sizeof(uint32_t) * (size_t)h->n_blocks},
-      {(void**)&d->qual, h->qual, (size_t)h->n_blocks * MB_BLOCK}};
+      {(void**)&d->planes, h->planes, (size_t)h->n_vec * 16}};
   int slot = 8;
   for (auto& p : parts) {
     // +256 B of zero slack so vectorised tail loads never leave the allocation
@@ -295,11 +296,10 @@ extern "C" void mb_reads_free(mb_ctx* c, mb_dev_reads* d) {
   if (!d) return;
   if (c) { cudaSetDevice(c->device); cudaStreamSynchronize(c->stream); if (c->rng_for == d) c->rng_for = nullptr; }
   cudaFree(d->hdr);
-  cudaFree(d->blk_off);
+  cudaFree(d->vec_off);
   cudaFree(d->cplx);
   cudaFree(d->cigar);
-  cudaFree(d->seq2);
-  cudaFree(d->qual);
+  cudaFree(d->planes);
   cudaFree(d->long_idx);
   delete d;
 }

@@ -5,12 +5,11 @@
 // gene, so the kernel is a streaming scan (16 B header + the read's qualities) followed by two
 // L2-resident atomics per read into the 24-byte per-gene record.
 //
-// Per warp, 32 consecutive reads at a time:
-//   A. lane i owns read i: coalesced header + block-offset loads, header-only filters
-//      (identity genes.py:157, mapq :163, alignment coverage :166), one thread per read;
-//   B. the qualities of the reads that survived A are summed 16 lanes per read with 128-bit loads
-//      (mean-quality test genes.py:160; exact integer form sum(q) >= readq*l_qseq);
-//   C. lane i issues read i's atomics: (aligned,mapped) as one packed u64 add, mapped_bp as another.
+// One thread per read: header-only filters (identity genes.py:157, mapq :163, alignment coverage :166),
+// then the Phred bit planes of the read (genes-mode packing holds nothing else) as independent 128-bit
+// loads: sum(q) = sum_k 2^k popc(plane k) (mean-quality test genes.py:160 in its exact integer form
+// sum(q) >= readq*l_qseq), then the read's atomics: (aligned,mapped) as one packed u64 add, mapped_bp
+// as another.
 #include <cub/device/device_radix_sort.cuh>
 
 #include <cmath>
@@ -23,8 +22,8 @@ constexpr int GENE_THREADS = 256;
 
 struct GeneParams {
   const uint4* hdr;
-  const uint32_t* blk_off;
-  const uint8_t* qual;
+  const uint32_t* vec_off;
+  const uint4* planes;      // genes-mode packing: q_planes words per 32-base block
   uint64_t n_reads;
   unsigned long long* out;  // mb_gene_out as 3 x u64: [aligned|mapped<<32], mapped_bp, depth bits
   uint32_t* key;            // exact order: per read, gene index if kept else 0xFFFFFFFF (may be null)
@@ -36,13 +35,14 @@ struct GeneParams {
   int mapq;
 };
 
-__global__ void __launch_bounds__(GENE_THREADS) k_genes_v1(const GeneParams p) {
-  // One thread per read: its qualities are 10 independent 128-bit loads (all in flight at once);
-  // the 160-byte stride between lanes is absorbed by L1 (the kernel uses no shared memory).
+template <int NQ>
+__global__ void __launch_bounds__(GENE_THREADS) k_genes_v2(const GeneParams p) {
+  // One thread per read: its Phred planes are up to 2 NQ independent 128-bit loads per step (a 150-base
+  // read is 8 of them, all in flight at once); the stride between lanes is absorbed by L1.
   const uint64_t stride = (uint64_t)gridDim.x * GENE_THREADS;
   for (uint64_t r = (uint64_t)blockIdx.x * GENE_THREADS + threadIdx.x; r < p.n_reads; r += stride) {
     const uint4 h = __ldg(&p.hdr[r]);
-    const uint32_t blk0 = __ldg(&p.blk_off[r]);
+    const uint32_t v0 = __ldg(&p.vec_off[r]);
     const uint32_t gene = h.x, lq = h.y & 0xffffu, alen = h.y >> 16;
     const uint32_t nm = h.z >> 16, mq = (h.w >> 16) & 0xffu, fl = h.w >> 24;
     // exact integer forms of the two double-precision tests of keep_read (tables built in ctx.cu)
@@ -53,26 +53,26 @@ __global__ void __launch_bounds__(GENE_THREADS) k_genes_v1(const GeneParams p) {
     bool keep = false;
     if (ok) {
       // mean-quality test genes.py:160: mean(q) < readq  <=>  sum(q) < readq * l_qseq (exact)
-      const uint32_t nblk = (lq + 15u) >> 4;
-      const uint4* __restrict__ q = reinterpret_cast<const uint4*>(p.qual) + blk0;
+      const uint32_t nvec = (((lq + 31u) >> 5) * (uint32_t)NQ + 3u) >> 2;
+      const uint4* __restrict__ q = p.planes + v0;
+      uint32_t pc[NQ];
+#pragma unroll
+      for (int k = 0; k < NQ; ++k) pc[k] = 0;
+      for (uint32_t b = 0; b < nvec; b += 2 * NQ) {       // 2 NQ vectors = 8 blocks: plane of word i is i % NQ
+        uint4 v[2 * NQ];
+#pragma unroll
+        for (int u = 0; u < 2 * NQ; ++u) v[u] = b + (uint32_t)u < nvec ? __ldg(q + b + u) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int u = 0; u < 2 * NQ; ++u) {
+          pc[(4 * u + 0) % NQ] += __popc(v[u].x);
+          pc[(4 * u + 1) % NQ] += __popc(v[u].y);
+          pc[(4 * u + 2) % NQ] += __popc(v[u].z);
+          pc[(4 * u + 3) % NQ] += __popc(v[u].w);
+        }
+      }
       uint32_t s = 0;
-      uint32_t b = 0;
-      for (; b + 4 <= nblk; b += 4) {
-        const uint4 v0 = __ldg(q + b), v1 = __ldg(q + b + 1), v2 = __ldg(q + b + 2), v3 = __ldg(q + b + 3);
-        s = __dp4a(v0.x & 0x7f7f7f7fu, 0x01010101u, s); s = __dp4a(v0.y & 0x7f7f7f7fu, 0x01010101u, s);
-        s = __dp4a(v0.z & 0x7f7f7f7fu, 0x01010101u, s); s = __dp4a(v0.w & 0x7f7f7f7fu, 0x01010101u, s);
-        s = __dp4a(v1.x & 0x7f7f7f7fu, 0x01010101u, s); s = __dp4a(v1.y & 0x7f7f7f7fu, 0x01010101u, s);
-        s = __dp4a(v1.z & 0x7f7f7f7fu, 0x01010101u, s); s = __dp4a(v1.w & 0x7f7f7f7fu, 0x01010101u, s);
-        s = __dp4a(v2.x & 0x7f7f7f7fu, 0x01010101u, s); s = __dp4a(v2.y & 0x7f7f7f7fu, 0x01010101u, s);
-        s = __dp4a(v2.z & 0x7f7f7f7fu, 0x01010101u, s); s = __dp4a(v2.w & 0x7f7f7f7fu, 0x01010101u, s);
-        s = __dp4a(v3.x & 0x7f7f7f7fu, 0x01010101u, s); s = __dp4a(v3.y & 0x7f7f7f7fu, 0x01010101u, s);
-        s = __dp4a(v3.z & 0x7f7f7f7fu, 0x01010101u, s); s = __dp4a(v3.w & 0x7f7f7f7fu, 0x01010101u, s);
-      }
-      for (; b < nblk; ++b) {
-        const uint4 v = __ldg(q + b);
-        s = __dp4a(v.x & 0x7f7f7f7fu, 0x01010101u, s); s = __dp4a(v.y & 0x7f7f7f7fu, 0x01010101u, s);
-        s = __dp4a(v.z & 0x7f7f7f7fu, 0x01010101u, s); s = __dp4a(v.w & 0x7f7f7f7fu, 0x01010101u, s);
-      }
+#pragma unroll
+      for (int k = 0; k < NQ; ++k) s += pc[k] << k;
       keep = s >= p.readq_eff * lq;
     }
     if (gene < p.n_genes) {
@@ -123,6 +123,8 @@ extern "C" int mb_genes_coverage_dev(mb_ctx* ctx, const mb_dev_reads* reads, con
                                      uint32_t n_genes, const mb_filters* f, int exact_order, mb_gene_out* out_dev) {
   if (!ctx || !reads || !gene_len_dev || !f || !out_dev)
     return mb::fail(MB_EINVAL, "mb_genes_coverage_dev: null argument");
+  if (reads->n_reads && (reads->n_planes != reads->q_planes || (reads->q_planes != 6 && reads->q_planes != 7)))
+    return mb::fail(MB_EINVAL, "mb_genes_coverage_dev: reads were not packed in genes mode (Phred planes only)");
   MB_CUDA_TRY(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   uint32_t *key = nullptr, *val = nullptr, *key2 = nullptr, *val2 = nullptr;
@@ -143,8 +145,8 @@ extern "C" int mb_genes_coverage_dev(mb_ctx* ctx, const mb_dev_reads* reads, con
   MB_CUDA_TRY(cudaMemsetAsync(out_dev, 0, sizeof(mb_gene_out) * (size_t)n_genes, st));
   GeneParams p;
   p.hdr = reinterpret_cast<const uint4*>(reads->hdr);
-  p.blk_off = reads->blk_off;
-  p.qual = reads->qual;
+  p.vec_off = reads->vec_off;
+  p.planes = reinterpret_cast<const uint4*>(reads->planes);
   p.n_reads = reads->n_reads;
   p.out = reinterpret_cast<unsigned long long*>(out_dev);
   p.key = key;
@@ -158,7 +160,8 @@ extern "C" int mb_genes_coverage_dev(mb_ctx* ctx, const mb_dev_reads* reads, con
   if (reads->n_reads) {
     uint64_t want = (reads->n_reads + GENE_THREADS - 1) / GENE_THREADS;
     uint32_t grid = (uint32_t)std::min<uint64_t>(want, (uint64_t)ctx->sm_count * 8);
-    k_genes_v1<<<grid, GENE_THREADS, 0, st>>>(p);
+    if (reads->q_planes == 6) k_genes_v2<6><<<grid, GENE_THREADS, 0, st>>>(p);
+    else k_genes_v2<7><<<grid, GENE_THREADS, 0, st>>>(p);
     ctx->launches++;
   }
   { int trc = mb::timing_end(ctx); if (trc) return trc; }

@@ -116,7 +116,8 @@ struct ReadGeom {
   uint32_t loc;
   uint16_t alen, q_start, ref_span, nm;
   uint8_t flags;
-  uint32_t n_blk;
+  uint8_t max_q;          // largest Phred of the read
+  uint32_t n_blk;         // MB_BLOCK-base blocks
   uint32_t n_cplx_words;  // 0 for simple reads, else 1 + n_ops_after_clip
   uint8_t need_words;     // snps: 32-position words a staged row of this read needs (saturated at 255)
 };
@@ -174,6 +175,15 @@ int analyse(const mb_plain_reads* in, const mb_layout* L, int mode, uint64_t i, 
   g->nm = (uint16_t)nm;
   g->n_blk = (uint32_t)((lq + MB_BLOCK - 1) / MB_BLOCK);
   g->n_cplx_words = 0;
+  {
+    const uint8_t* q = in->qual + in->seq_off[i];
+    uint8_t mx = 0;
+    for (int64_t k = 0; k < lq; ++k) mx = std::max(mx, q[k]);
+    if (mx > 127)
+      return mb::fail(MB_EINVAL, "read %llu: base quality %u above 127 is not representable", (unsigned long long)i,
+                      (unsigned)mx);
+    g->max_q = mx;
+  }
   const int32_t rid = in->ref_id[i];
   if (mode == 1) {  // genes: loc = gene index, the pileup geometry is unused
     if (rid < 0 || (uint32_t)rid >= L->n_contigs)
@@ -326,6 +336,11 @@ extern "C" int mb_pack_reads(const mb_plain_reads* in, const mb_layout* L, int m
   auto src = [&](uint64_t j) -> uint64_t { return perm.empty() ? j : perm[j]; };
 
   // offsets
+  uint8_t max_q = 0;
+  for (uint64_t i = 0; i < n; ++i) max_q = std::max(max_q, geom[i].max_q);
+  const uint32_t q_planes = max_q <= 63 ? 6u : 7u;
+  const uint32_t NP = mode == 0 ? 3u + q_planes : q_planes;     // words per block
+  const uint32_t P0 = mode == 0 ? 3u : 0u;                      // first Phred plane
   std::vector<uint32_t> blk_off(n + 1), cg_off(n + 1);
   uint64_t nb = 0, ncw = 0, tot_bases = 0;
   uint32_t max_span = 0;
@@ -333,7 +348,7 @@ extern "C" int mb_pack_reads(const mb_plain_reads* in, const mb_layout* L, int m
     const ReadGeom& g = geom[src(j)];
     blk_off[j] = (uint32_t)nb;
     cg_off[j] = (uint32_t)ncw;
-    nb += g.n_blk;
+    nb += ((uint64_t)g.n_blk * NP + 3) / 4;                     // 16-byte units of the read's region
     ncw += g.n_cplx_words;
     tot_bases += (uint64_t)in->l_qseq[src(j)];
     max_span = std::max<uint32_t>(max_span, g.ref_span);
@@ -365,7 +380,7 @@ extern "C" int mb_pack_reads(const mb_plain_reads* in, const mb_layout* L, int m
   memset(o, 0, sizeof(*o));
   o->pinned = pinned != 0;
   size_t sizes[7] = {sizeof(mb_read_hdr) * (size_t)n, sizeof(uint32_t) * (size_t)(n + 1), sizeof(uint32_t) * (size_t)n,
-                     sizeof(uint32_t) * (size_t)ncw, sizeof(uint32_t) * (size_t)nb, (size_t)nb * MB_BLOCK,
+                     sizeof(uint32_t) * (size_t)ncw, (size_t)nb * 16, 0,
                      sizeof(uint32_t) * (size_t)n_long};
   for (int k = 0; k < 7; ++k) {
     o->buf[k] = alloc_host(sizes[k], o->pinned);
@@ -381,8 +396,7 @@ extern "C" int mb_pack_reads(const mb_plain_reads* in, const mb_layout* L, int m
   uint32_t* blk = (uint32_t*)o->buf[1];
   uint32_t* cplx = (uint32_t*)o->buf[2];
   uint32_t* cigar = (uint32_t*)o->buf[3];
-  uint32_t* seq2 = (uint32_t*)o->buf[4];
-  uint8_t* qual = (uint8_t*)o->buf[5];
+  uint32_t* planes = (uint32_t*)o->buf[4];
   uint32_t* long_idx = (uint32_t*)o->buf[6];
   memcpy(blk, blk_off.data(), sizeof(uint32_t) * (n + 1));
   if (n_long) {
@@ -391,8 +405,7 @@ extern "C" int mb_pack_reads(const mb_plain_reads* in, const mb_layout* L, int m
       if (geom[src(j)].flags & MB_RF_LONG) long_idx[k++] = (uint32_t)j;
   }
 
-  std::vector<int> rc2(n_threads + 1, MB_OK);
-  parallel_for(n, n_threads, [&](uint64_t lo, uint64_t hi, int t) {
+  parallel_for(n, n_threads, [&](uint64_t lo, uint64_t hi, int) {
     for (uint64_t j = lo; j < hi; ++j) {
       const uint64_t i = src(j);
       const ReadGeom& g = geom[i];
@@ -432,48 +445,73 @@ extern "C" int mb_pack_reads(const mb_plain_reads* in, const mb_layout* L, int m
       const uint8_t* s = in->seq + in->seq_off[i];
       const uint8_t* q = in->qual + in->seq_off[i];
       const uint32_t lq = h.l_qseq;
+      uint32_t* reg = planes + (size_t)blk_off[j] * 4;
+      memset(reg, 0, ((size_t)blk_off[j + 1] - blk_off[j]) * 16);
       for (uint32_t b = 0; b < g.n_blk; ++b) {
-        uint32_t lo_bits = 0, hi_bits = 0;
-        uint8_t* qd = qual + ((uint64_t)blk_off[j] + b) * MB_BLOCK;
-        for (uint32_t k = 0; k < MB_BLOCK; ++k) {
-          uint32_t qi = b * MB_BLOCK + k;
-          if (qi < lq) {
-            uint8_t nib = s[qi] & 0xF;
-            uint8_t ph = q[qi];
-            if (ph > 127) { rc2[t] = MB_EINVAL; ph = 127; }
-            uint8_t code = kNib2Code[nib];
-            lo_bits |= (uint32_t)(code & 1) << k;
-            hi_bits |= (uint32_t)(code >> 1) << k;
-            qd[k] = (uint8_t)(ph | (kNibIsAcgt[nib] ? 0x80 : 0));
-          } else {
-            qd[k] = 0;
+        uint32_t w[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};        // lo, hi, acgt, Phred bits 0..6
+        const uint32_t nk = std::min<uint32_t>(MB_BLOCK, lq - b * MB_BLOCK);
+        for (uint32_t k = 0; k < nk; ++k) {
+          const uint32_t qi = b * MB_BLOCK + k;
+          const uint8_t nib = s[qi] & 0xF, ph = q[qi], code = kNib2Code[nib];
+          w[0] |= (uint32_t)(code & 1) << k;
+          w[1] |= (uint32_t)(code >> 1) << k;
+          w[2] |= (uint32_t)kNibIsAcgt[nib] << k;
+          w[3] |= (uint32_t)(ph & 1) << k;
+          w[4] |= (uint32_t)((ph >> 1) & 1) << k;
+          w[5] |= (uint32_t)((ph >> 2) & 1) << k;
+          w[6] |= (uint32_t)((ph >> 3) & 1) << k;
+          w[7] |= (uint32_t)((ph >> 4) & 1) << k;
+          w[8] |= (uint32_t)((ph >> 5) & 1) << k;
+          w[9] |= (uint32_t)((ph >> 6) & 1) << k;
+        }
+        uint32_t* d = reg + (size_t)b * NP;
+        if (mode == 0) { d[0] = w[0]; d[1] = w[1]; d[2] = w[2]; }
+        for (uint32_t k = 0; k < q_planes; ++k) d[P0 + k] = w[3 + k];
+      }
+      if (mode == 0) {
+        // candidate plane: keep only the bases of M/=/X runs whose reference position is inside the contig
+        // (S, I never count; pysam ignores refpos >= contig_len)
+        const uint32_t* cig = in->cigar + in->cigar_off[i];
+        const int64_t n_cig = (int64_t)(in->cigar_off[i + 1] - in->cigar_off[i]);
+        const int64_t room = (int64_t)L->contig_len[in->ref_id[i]] - in->pos[i];
+        uint32_t inrun[(65535 + 31) / 32 + 1];
+        for (uint32_t b = 0; b < g.n_blk; ++b) inrun[b] = 0;
+        int64_t qq = 0, rr = 0;
+        for (int64_t k = 0; k < n_cig; ++k) {
+          const uint32_t op = cig[k] & 0xF;
+          const int64_t len = cig[k] >> 4;
+          if (op == mb::OP_M || op == mb::OP_EQ || op == mb::OP_X) {
+            const int64_t take = std::max<int64_t>(0, std::min<int64_t>(len, room - rr));
+            for (int64_t x = qq; x < qq + take; ++x) inrun[x >> 5] |= 1u << (x & 31);
+            qq += len;
+            rr += len;
+          } else if (op == mb::OP_I || op == mb::OP_S) {
+            qq += len;
+          } else if (op == mb::OP_D || op == mb::OP_N) {
+            rr += len;
           }
         }
-        seq2[(uint64_t)blk_off[j] + b] = lo_bits | (hi_bits << 16);
+        for (uint32_t b = 0; b < g.n_blk; ++b) reg[(size_t)b * NP + 2] &= inrun[b];
       }
     }
   });
-  for (int t = 0; t <= n_threads; ++t)
-    if (rc2[t] != MB_OK) {
-      mb_packed_free(&o->pub);
-      return mb::fail(MB_EINVAL, "mb_pack_reads: base quality above 127 is not representable");
-    }
 
   o->pub.n_reads = n;
-  o->pub.n_blocks = nb;
+  o->pub.n_vec = nb;
   o->pub.n_cigar_words = ncw;
   o->pub.total_bases = tot_bases;
   o->pub.max_ref_span = max_span;
   o->pub.sorted = (mode == 0) ? 1u : 0u;
   o->pub.row_words = row_words;
   o->pub.n_long = (uint32_t)n_long;
+  o->pub.q_planes = q_planes;
+  o->pub.n_planes = NP;
   o->pub.long_idx = long_idx;
   o->pub.hdr = hdr;
-  o->pub.blk_off = blk;
+  o->pub.vec_off = blk;
   o->pub.cplx = cplx;
   o->pub.cigar = cigar;
-  o->pub.seq2 = seq2;
-  o->pub.qual = qual;
+  o->pub.planes = planes;
   *out = &o->pub;
   return MB_OK;
 }

@@ -12,11 +12,13 @@
 //   * the padded genome is cut into KT-position tiles; reads are sorted by coordinate, so the reads
 //     overlapping a tile are one contiguous index range (k_tile_ranges) and a CTA owns a tile;
 //   * STAGE: one thread turns one read into a *bit-plane row in reference coordinates*, entirely in
-//     registers: its qualities arrive as up to 2W independent 128-bit loads, every 16 of them become
-//     a 16-bit "countable" mask (byte-SIMD compare + multiply gather, no per-base branch), the two
-//     2-bit sequence planes are taken as they lie in HBM, and each CIGAR run is applied with one
-//     funnel shift per plane per 32-position word. The row is stored in shared memory as
-//     W x {A,C,G,T} 32-bit masks aligned to the global 32-position grid;
+//     registers: the read's bit planes (mb_packed_reads: 32 bases per word) arrive as independent
+//     128-bit loads, Phred >= baseq is a bit-sliced comparator (one LOP3 per Phred bit per 32 bases,
+//     no per-base work at all), the Phred sum is one POPC per plane word, the two sequence planes are
+//     taken as they lie in HBM, and each CIGAR run is one funnel shift per plane per 32-position
+//     word (the packer has already cleared the candidate bit of every base outside an M/=/X run, so
+//     single-run reads need no masks). The row is stored in shared memory as W x {A,C,G,T} 32-bit
+//     masks aligned to the global 32-position grid;
 //   * COUNT: a lane owns a 32-position column and adds the rows covering it with carry-save adders
 //     into bit-sliced ("vertical") counters held in registers: one LOP3 works on 32 positions at
 //     once, ~0.6 instructions per aligned base instead of one shared-memory atomic per base;
@@ -59,11 +61,10 @@ enum : uint32_t { F_NEEDQ = 1u, F_OVL = 2u, F_OWNER = 4u, F_SIMPLE = 8u };
 
 struct PileParams {
   const uint4* hdr;
-  const uint32_t* blk_off;
+  const uint32_t* vec_off;
   const uint32_t* cplx;
   const uint32_t* cigar;
-  const uint32_t* seq2;
-  const uint4* qual;          // 16 qualities per element
+  const uint4* planes;        // bit-planar read data, 16-byte units (mb_packed_reads)
   const uint32_t* tile_rng;   // [2 * n_ktiles]
   const int32_t* tile_species;  // per MB_TILE tile
   uint32_t* counts;
@@ -71,10 +72,6 @@ struct PileParams {
   uint32_t* sched;
   uint64_t gpad;
   uint32_t n_ktiles;
-  uint32_t n_blocks;          // 16-base blocks in seq2 / qual
-  uint32_t avg_blocks;        // blocks per read, rounded up (prefetch size estimate)
-  uint32_t l2_prefetch;       // 1: bulk-prefetch the next round into L2
-  uint32_t row_prefetch;      // 1: each thread prefetches its next read's lines into L2
   uint32_t W;                 // row words
   uint32_t rmax;              // rows staged per round
   const int32_t* t_pid;       // [65536] smallest 100*(alen-NM) that passes mapid, per alen
@@ -82,7 +79,7 @@ struct PileParams {
   uint32_t pid_always;        // mapid is -inf or NaN (reads with a saturated NM pass only then)
   uint32_t readq_eff;         // readq clamped to [0,128]
   int mapq;
-  uint32_t qadd;              // (0x80 - baseq) * 0x01010101
+  uint32_t baseq;             // per-base threshold (0: every candidate base counts)
   uint32_t defer_restat;      // 1: long reads follow, position stats are recomputed afterwards
 };
 
@@ -100,36 +97,6 @@ __device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
     (c) = (_a & _b) | ((_a ^ _b) & _d);             \
   } while (0)
 
-// 16 quality bytes (bit 7 = literal A/C/G/T, bits 0-6 = Phred) -> 2 bytes whose low bytes are the
-// 8 + 8 "countable" bits (Phred >= baseq and A/C/G/T); the Phred sum is accumulated into qsum.
-// Per 4 bases: mask, dot-product-accumulate, add, and, multiply-high (bit gather).
-__device__ __forceinline__ void conv16(const uint4 q, const uint32_t qadd, uint32_t& qsum, uint32_t& b01,
-                                       uint32_t& b23) {
-  constexpr uint32_t MUL0 = (1u << 25) | (1u << 18) | (1u << 11) | (1u << 4);  // bits 7,15,23,31 -> 32..35
-  constexpr uint32_t MUL4 = MUL0 << 4;                                         //                 -> 36..39
-  const uint32_t m0 = q.x & 0x7f7f7f7fu, m1 = q.y & 0x7f7f7f7fu, m2 = q.z & 0x7f7f7f7fu, m3 = q.w & 0x7f7f7f7fu;
-  qsum = __dp4a(m0, 0x01010101u, qsum);
-  qsum = __dp4a(m1, 0x01010101u, qsum);
-  qsum = __dp4a(m2, 0x01010101u, qsum);
-  qsum = __dp4a(m3, 0x01010101u, qsum);
-  const uint32_t t0 = (m0 + qadd) & q.x & 0x80808080u;
-  const uint32_t t1 = (m1 + qadd) & q.y & 0x80808080u;
-  const uint32_t t2 = (m2 + qadd) & q.z & 0x80808080u;
-  const uint32_t t3 = (m3 + qadd) & q.w & 0x80808080u;
-  const uint32_t n0 = __umulhi(t0, MUL0), n1 = __umulhi(t1, MUL4);
-  const uint32_t n2 = __umulhi(t2, MUL0), n3 = __umulhi(t3, MUL4);
-  b01 = (n0 & 0x0fu) | (n1 & ~0x0fu);  // low byte: bases 0-7 (higher bytes hold gather by-products)
-  b23 = (n2 & 0x0fu) | (n3 & ~0x0fu);  // low byte: bases 8-15
-}
-
-// Ask the copy engine to pull [ptr, ptr + bytes) into L2 (no registers, no shared memory, no wait):
-// the loads that follow a round later find their lines on chip instead of in HBM.
-__device__ __forceinline__ void l2_prefetch(const void* ptr, uint32_t bytes) {
-  const uintptr_t a = reinterpret_cast<uintptr_t>(ptr) & ~(uintptr_t)15;
-  const uint32_t n = (bytes + 31u) & ~15u;
-  if (n) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(n) : "memory");
-}
-
 __device__ __forceinline__ uint32_t shl_clamp(uint32_t v, uint32_t n) {   // v << n, 0 for n >= 32
   uint32_t r;
   asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(n));
@@ -139,12 +106,6 @@ __device__ __forceinline__ uint32_t shr_clamp(uint32_t v, uint32_t n) {   // v >
   uint32_t r;
   asm("shr.u32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(n));
   return r;
-}
-
-__device__ __forceinline__ uint32_t bit_range_mask(int lo, int hi) {  // bits [lo, hi) of a word, 0 <= lo < hi <= 32
-  const uint32_t up = 0xffffffffu << lo;
-  const uint32_t dn = 0xffffffffu >> (32 - hi);
-  return up & dn;
 }
 
 __global__ void k_init_stats(unsigned long long* stats, const uint64_t* species_len, uint32_t n_species,
@@ -183,10 +144,31 @@ __global__ void k_tile_ranges(const uint4* __restrict__ hdr, uint32_t n_reads, u
   rng[2 * t + 1] = lo;
 }
 
-template <int WT>
+// slide three register arrays of WT+2 words until the word offset d is -1 (static register moves in a
+// short loop; taken only by heavily clipped reads and by indels that push a run across a word boundary)
+#define MB_SLIDE(d, wshift, A, B, C)                                                        \
+  do {                                                                                      \
+    while ((d) > -1) {                                                                      \
+      _Pragma("unroll") for (int w = 0; w <= WT; ++w) { A[w] = A[w + 1]; B[w] = B[w + 1]; C[w] = C[w + 1]; } \
+      A[WT + 1] = 0; B[WT + 1] = 0; C[WT + 1] = 0;                                          \
+      --(d); ++(wshift);                                                                    \
+    }                                                                                       \
+    while ((d) < -1) {                                                                      \
+      _Pragma("unroll") for (int w = WT + 1; w > 0; --w) { A[w] = A[w - 1]; B[w] = B[w - 1]; C[w] = C[w - 1]; } \
+      A[0] = 0; B[0] = 0; C[0] = 0;                                                         \
+      ++(d); --(wshift);                                                                    \
+    }                                                                                       \
+  } while (0)
+
+template <int WT, int NQ>
 __global__ void __launch_bounds__(NT, 2) k_pileup_v2(const PileParams p) {
   extern __shared__ __align__(16) uint32_t smem[];
   constexpr uint32_t W = (uint32_t)WT;          // row words (compile time: every per-lane loop below unrolls)
+  constexpr int NP = 3 + NQ;                    // words per 32-base block: seq lo, seq hi, candidate, Phred bits
+  uint32_t tmk[NQ];                             // bit k of baseq, spread over a word (warp-uniform)
+#pragma unroll
+  for (int k = 0; k < NQ; ++k) tmk[k] = ((p.baseq >> k) & 1u) ? 0xffffffffu : 0u;
+  const uint32_t q_allow = (p.baseq >> NQ) ? 0u : 0xffffffffu;   // a threshold above every representable Phred
   uint4* s_vc = reinterpret_cast<uint4*>(smem);                       // [VCL][NCOL] x {A,C,G,T}
   uint4* s_rows = s_vc + VCL * NCOL;                                  // [rmax][W] x {A,C,G,T}
   __shared__ uint32_t s_first[FIRST_N];
@@ -274,9 +256,6 @@ __global__ void __launch_bounds__(NT, 2) k_pileup_v2(const PileParams p) {
 
     uint32_t pass_rows = 0;
     bool accumulate = false;
-    bool pf_valid = false;                                            // thread 0: pf_b0 = first block of the next round
-    uint32_t pf_b0 = 0;
-    if (tid == 0 && r0 + p.rmax < r1) { pf_valid = true; pf_b0 = __ldg(p.blk_off + r0 + p.rmax); }
     for (uint32_t rb = r0; rb < r1; rb += p.rmax) {
       const int n = (int)min(p.rmax, r1 - rb);
       if (pass_rows + (uint32_t)n > PASS_ROWS) {  // keep the shared counters below 2^VCL
@@ -286,30 +265,14 @@ __global__ void __launch_bounds__(NT, 2) k_pileup_v2(const PileParams p) {
       }
       pass_rows += (uint32_t)n;
       __syncthreads();
-      if (tid == 0) {   // L2 prefetch (copy engine) of the rows after this round; their first block was fetched a round ago
-        const uint32_t pr0 = rb + (uint32_t)n, pr1 = min(r1, pr0 + p.rmax);
-        if (pr1 > pr0 && pf_valid && p.l2_prefetch) {
-          const uint32_t nrow = pr1 - pr0;
-          uint32_t nblk = nrow * p.avg_blocks + 16u;
-          nblk = pf_b0 < p.n_blocks ? min(nblk, p.n_blocks - pf_b0) : 0u;
-          l2_prefetch(p.hdr + pr0, nrow * 16u);
-          l2_prefetch(p.blk_off + pr0, nrow * 4u);
-          l2_prefetch(p.cplx + pr0, nrow * 4u);
-          l2_prefetch(p.qual + pf_b0, nblk * 16u);
-          l2_prefetch(p.seq2 + pf_b0, nblk * 4u);
-        }
-        const uint32_t nn0 = pr0 + p.rmax;                           // start of the round after the next one
-        pf_valid = nn0 < r1;
-        if (pf_valid) pf_b0 = __ldg(p.blk_off + nn0);
-      }
       // ---- STAGE: one thread per read, everything in registers: header filters (snps.py:148,154,157),
-      // row index table, 2W independent 128-bit quality loads (L1 absorbs the stride between lanes),
-      // conversion to bit planes, mean-quality filter, CIGAR placement, row store
+      // row index table, the read's bit planes as independent 128-bit loads (L1 absorbs the stride
+      // between lanes), bit-sliced base-quality test, mean-quality filter, CIGAR placement, row store
       uint4 nh = make_uint4(0, 0, 0, 0);                       // header, block offset, run word and predecessor
       uint32_t nb0 = 0, ncw = 0, nprev = 0;                     // of this thread's next read: one step ahead
       if (tid < n) {
         nh = __ldg(&p.hdr[rb + tid]);
-        nb0 = __ldg(&p.blk_off[rb + tid]);
+        nb0 = __ldg(&p.vec_off[rb + tid]);
         ncw = __ldg(&p.cplx[rb + tid]);
         if (tid > 0) nprev = __ldg(&p.hdr[rb + tid - 1].x);
       }
@@ -317,15 +280,9 @@ __global__ void __launch_bounds__(NT, 2) k_pileup_v2(const PileParams p) {
         const uint32_t r = rb + (uint32_t)i;
         const uint4 h = nh;
         const uint32_t b0 = nb0, cw = ncw, prev_loc = nprev;
-        if (p.row_prefetch && i + NT < n) {                    // my next read's lines -> L2 while this one is converted
-          const char* q = reinterpret_cast<const char*>(p.qual + nb0);
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(q + 128));
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(p.seq2 + nb0));
-        }
         if (i + NT < n) {
           nh = __ldg(&p.hdr[r + NT]);
-          nb0 = __ldg(&p.blk_off[r + NT]);
+          nb0 = __ldg(&p.vec_off[r + NT]);
           ncw = __ldg(&p.cplx[r + NT]);
           nprev = __ldg(&p.hdr[r + NT - 1].x);
         }
@@ -365,94 +322,126 @@ __global__ void __launch_bounds__(NT, 2) k_pileup_v2(const PileParams p) {
         for (int w = 0; w <= WT + 1; ++w) { ql[w] = 0; qh[w] = 0; qv[w] = 0; }
         bool keep = false;
         if (needq) {
-          const uint32_t nblk = (lq + 15u) >> 4;
-          const uint4* __restrict__ qp = p.qual + b0;
-          const uint32_t* __restrict__ sp = p.seq2 + b0;
-          uint32_t qsum = 0;
+          const uint32_t nvec = (((lq + 31u) >> 5) * (uint32_t)NP + 3u) >> 2;
+          const uint4* __restrict__ vp = p.planes + b0;
+          uint32_t pc[NQ];
 #pragma unroll
-          for (int w0 = 0; w0 < WT; w0 += 4) {              // 8 blocks = 8 independent 128-bit loads per step
-            uint4 qq[8];
-            uint32_t ss[8];
+          for (int k = 0; k < NQ; ++k) pc[k] = 0;
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              const uint32_t bidx = (uint32_t)(2 * w0 + u);
-              qq[u] = make_uint4(0, 0, 0, 0);
-              ss[u] = 0;
-              if (2 * w0 + u < 2 * WT && bidx < nblk) { qq[u] = __ldg(qp + bidx); ss[u] = __ldg(sp + bidx); }
+          for (int s4 = 0; s4 < WT; s4 += 4) {              // 4 blocks = NP independent 128-bit loads per step
+            const int nb = WT - s4 < 4 ? WT - s4 : 4;
+            const int nv = (nb * NP + 3) / 4;
+            uint32_t raw[4 * NP];
+#pragma unroll
+            for (int u = 0; u < NP; ++u) {
+              uint4 t = make_uint4(0, 0, 0, 0);
+              if (u < nv && (uint32_t)(s4 / 4 * NP + u) < nvec) t = __ldg(vp + s4 / 4 * NP + u);
+              raw[4 * u] = t.x; raw[4 * u + 1] = t.y; raw[4 * u + 2] = t.z; raw[4 * u + 3] = t.w;
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              if (w0 + u < WT) {
-                uint32_t a01, a23, c01, c23;
-                conv16(qq[2 * u], p.qadd, qsum, a01, a23);
-                conv16(qq[2 * u + 1], p.qadd, qsum, c01, c23);
-                qv[w0 + u + 1] = __byte_perm(__byte_perm(a01, a23, 0x0040), __byte_perm(c01, c23, 0x0040), 0x5410);
-                ql[w0 + u + 1] = __byte_perm(ss[2 * u], ss[2 * u + 1], 0x5410);
-                qh[w0 + u + 1] = __byte_perm(ss[2 * u], ss[2 * u + 1], 0x7632);
+            for (int bl = 0; bl < 4; ++bl) {
+              if (bl < nb) {
+                // Phred >= baseq, bit-sliced over 32 bases: from the low bit up, "greater or equal so far"
+                uint32_t ge = 0xffffffffu;
+#pragma unroll
+                for (int k = 0; k < NQ; ++k) {
+                  const uint32_t pk = raw[bl * NP + 3 + k];
+                  ge = (pk & ge) | (~tmk[k] & (pk | ge));   // threshold bit set: and, clear: or (one LOP3)
+                  pc[k] += __popc(pk);
+                }
+                ql[s4 + bl + 1] = raw[bl * NP];
+                qh[s4 + bl + 1] = raw[bl * NP + 1];
+                qv[s4 + bl + 1] = raw[bl * NP + 2] & ge & q_allow;
               }
             }
           }
           // mean-quality filter (snps.py:151): mean(q) < readq  <=>  sum(q) < readq * l_qseq (exact)
+          uint32_t qsum = 0;
+#pragma unroll
+          for (int k = 0; k < NQ; ++k) qsum += pc[k] << k;
           keep = qsum >= p.readq_eff * lq;
           if (keep && owner) ++my_mapped;                                    // snps.py:161
         }
-        // ---- CIGAR: every M/=/X run is one funnel-shifted, masked copy of the query planes
+        // ---- CIGAR: every M/=/X run is one funnel-shifted copy of the query planes. Query bit q of a run
+        // (q0, x0) lies at row bit q - dq with dq = q0 - o - x0 = 32 d + sh, sh in [1, 32]: row word j is
+        // query words (j + d, j + d + 1) funnel-shifted by sh; d is -1 for every read that is not heavily
+        // clipped, other d first slide the planes by whole words so that the per-word code is static.
         uint32_t rl[WT], rh[WT], rv[WT];
 #pragma unroll
         for (int j = 0; j < WT; ++j) { rl[j] = 0; rh[j] = 0; rv[j] = 0; }
         if (keep && ovl) {
           const int o = (int)(loc & 31u);
-          // run (q0, x0, len): query bases [q0, q0+len) lie at row bits [o + x0, o + x0 + len); row word j
-          // takes query bits [32 j + dq, +32) with dq = q0 - o - x0 = 32 d + sh. d is -1 for an
-          // unclipped read that does not start on a word boundary; any other d first slides the
-          // planes by whole words (static register moves) so that the per-word code is branch-free.
           const bool simple = (fl & MB_RF_SIMPLE) != 0;
-          const uint32_t* __restrict__ rec = p.cigar;
-          uint32_t n_runs = 1;
-          int wshift = 0;                                           // words the planes have been slid so far
           const bool runs2 = (fl & MB_RF_RUNS2) != 0;              // both runs are in the cplx word: no record fetch
-          if (runs2) n_runs = 2;
-          else if (!simple) { rec = p.cigar + cw; n_runs = __ldg(rec); }
-          for (uint32_t k = 0; k < n_runs; ++k) {
-            int q0 = (int)qstart, x0 = 0, len = (int)span;
+          int wshift = 0;                                           // words the planes have been slid so far
+          if (simple || runs2) {
+            // run 1 starts at the read's position (x0 = 0). Bases outside the runs carry no candidate bit,
+            // so the run needs no mask of its own.
+            const int dq = (int)qstart - o;
+            int d = (dq - 1) >> 5;
+            const int sh = ((dq - 1) & 31) + 1;
+            MB_SLIDE(d, wshift, ql, qh, qv);
             if (runs2) {
-              const int len0 = (int)(cw & 0xffffu);
-              if (k == 0) len = len0;
-              else { x0 = len0 + (int)(cw >> 24); q0 = (int)qstart + len0 + (int)((cw >> 16) & 0xffu); len = (int)span - x0; }
-            } else if (!simple) {
+              // one indel: the candidate plane is split at query bit q_start + len0; the part above it is
+              // placed with the second run's shift (inserted bases carry no candidate bit)
+              const int len0 = (int)(cw & 0xffffu), ins = (int)((cw >> 16) & 0xffu), del = (int)(cw >> 24);
+              const int b1 = (int)qstart + len0 - 32 * (wshift - 1);        // split, relative to array word 0
+              uint32_t c2[WT + 2];
+#pragma unroll
+              for (int w = 0; w <= WT + 1; ++w) {
+                const uint32_t above = shl_clamp(0xffffffffu, (uint32_t)max(b1 - 32 * w, 0));
+                c2[w] = qv[w] & above;
+                qv[w] &= ~above;
+              }
+#pragma unroll
+              for (int j = 0; j < WT; ++j) {
+                rv[j] = __funnelshift_rc(qv[j], qv[j + 1], sh);
+                rl[j] = __funnelshift_rc(ql[j], ql[j + 1], sh);
+                rh[j] = __funnelshift_rc(qh[j], qh[j + 1], sh);
+              }
+              const int dq2 = dq + ins - del;
+              int d2 = ((dq2 - 1) >> 5) - wshift;
+              const int sh2 = ((dq2 - 1) & 31) + 1;
+              MB_SLIDE(d2, wshift, ql, qh, c2);
+#pragma unroll
+              for (int j = 0; j < WT; ++j) {
+                const uint32_t v2 = __funnelshift_rc(c2[j], c2[j + 1], sh2);
+                const uint32_t l2 = __funnelshift_rc(ql[j], ql[j + 1], sh2);
+                const uint32_t h2 = __funnelshift_rc(qh[j], qh[j + 1], sh2);
+                rl[j] = (rl[j] & rv[j]) | (l2 & ~rv[j]);             // bit select by the first run's support
+                rh[j] = (rh[j] & rv[j]) | (h2 & ~rv[j]);
+                rv[j] |= v2;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < WT; ++j) {
+                rv[j] = __funnelshift_rc(qv[j], qv[j + 1], sh);
+                rl[j] = __funnelshift_rc(ql[j], ql[j + 1], sh);
+                rh[j] = __funnelshift_rc(qh[j], qh[j + 1], sh);
+              }
+            }
+          } else {
+            // three or more runs: run records {n_runs, (q0 | len << 16, x0)...}, each run masked to its own
+            // row bits [o + x0, o + x0 + len) (clamped shifts: a PTX shift by >= 32 gives 0)
+            const uint32_t* __restrict__ rec = p.cigar + cw;
+            const uint32_t n_runs = __ldg(rec);
+            for (uint32_t k = 0; k < n_runs; ++k) {
               const uint32_t w0 = __ldg(rec + 1 + 2 * k);
-              q0 = (int)(w0 & 0xffffu); len = (int)(w0 >> 16); x0 = (int)__ldg(rec + 2 + 2 * k);
-            }
-            const int p0 = o + x0, dq = q0 - p0;
-            int d = (dq >> 5) - wshift;
-            int sh = dq & 31;
-            if (d == 0 && sh == 0) { d = -1; sh = 32; }   // a read starting on a word boundary: shift by a whole word
-            // heavily clipped reads / long indels: slide the planes by whole words (static register
-            // moves in a short loop) until the word offset is -1 or 0 again
-            while (d > -1) {
+              const int q0 = (int)(w0 & 0xffffu), len = (int)(w0 >> 16), x0 = (int)__ldg(rec + 2 + 2 * k);
+              const int p0 = o + x0, dq = q0 - p0;
+              int d = ((dq - 1) >> 5) - wshift;
+              const int sh = ((dq - 1) & 31) + 1;
+              MB_SLIDE(d, wshift, ql, qh, qv);
 #pragma unroll
-              for (int w = 0; w <= WT; ++w) { ql[w] = ql[w + 1]; qh[w] = qh[w + 1]; qv[w] = qv[w + 1]; }
-              ql[WT + 1] = 0; qh[WT + 1] = 0; qv[WT + 1] = 0;
-              --d; ++wshift;
-            }
-            while (d < -1) {
-#pragma unroll
-              for (int w = WT + 1; w > 0; --w) { ql[w] = ql[w - 1]; qh[w] = qh[w - 1]; qv[w] = qv[w - 1]; }
-              ql[0] = 0; qh[0] = 0; qv[0] = 0;
-              ++d; --wshift;
-            }
-            // now d == -1: row word j = query words (j-1 : j) funnel-shifted by sh
-            // mask of the run's bits inside word j = [p0 - 32 j, p0 + len - 32 j) clipped to [0, 32): built
-            // branch-free from clamped shifts (a PTX shift by >= 32 gives 0)
-#pragma unroll
-            for (int j = 0; j < WT; ++j) {
-              const int r0b = p0 - 32 * j, r1b = r0b + len;
-              const uint32_t up = shl_clamp(0xffffffffu, (uint32_t)max(r0b, 0));
-              const uint32_t dn = shr_clamp(0xffffffffu, (uint32_t)(32 - min(max(r1b, 0), 32)));
-              const uint32_t msk = up & dn;
-              rl[j] |= __funnelshift_rc(ql[j], ql[j + 1], sh) & msk;   // clamped: sh = 32 selects the upper word
-              rh[j] |= __funnelshift_rc(qh[j], qh[j + 1], sh) & msk;
-              rv[j] |= __funnelshift_rc(qv[j], qv[j + 1], sh) & msk;
+              for (int j = 0; j < WT; ++j) {
+                const int r0b = p0 - 32 * j, r1b = r0b + len;
+                const uint32_t up = shl_clamp(0xffffffffu, (uint32_t)max(r0b, 0));
+                const uint32_t dn = shr_clamp(0xffffffffu, (uint32_t)(32 - min(max(r1b, 0), 32)));
+                const uint32_t msk = up & dn;
+                rl[j] |= __funnelshift_rc(ql[j], ql[j + 1], sh) & msk;
+                rh[j] |= __funnelshift_rc(qh[j], qh[j + 1], sh) & msk;
+                rv[j] |= __funnelshift_rc(qv[j], qv[j + 1], sh) & msk;
+              }
             }
           }
         }
@@ -564,11 +553,10 @@ __global__ void __launch_bounds__(NT, 2) k_pileup_v2(const PileParams p) {
 // ---- reads that do not fit a W-word row: one warp per read, global atomics (rare by construction)
 struct LongParams {
   const uint4* hdr;
-  const uint32_t* blk_off;
+  const uint32_t* vec_off;
   const uint32_t* cplx;
   const uint32_t* cigar;
-  const uint32_t* seq2;
-  const uint8_t* qual;
+  const uint32_t* planes;
   const uint32_t* long_idx;
   const int32_t* tile_species;
   uint32_t* counts;
@@ -577,7 +565,8 @@ struct LongParams {
   uint32_t n_long;
   double mapid, aln_cov;
   int readq, mapq;
-  uint32_t qthr;  // 0x80 + baseq
+  uint32_t baseq;
+  uint32_t NQ, NP;  // Phred planes / words per 32-base block
 };
 
 __global__ void __launch_bounds__(256) k_long_reads(const LongParams p) {
@@ -592,11 +581,14 @@ __global__ void __launch_bounds__(256) k_long_reads(const LongParams p) {
     double pid = __ddiv_rn((double)(100 * ((int)alen - (int)nm)), (double)alen);
     if (fl & MB_RF_NMSAT) pid = -__longlong_as_double(0x7ff0000000000000ll);
     bool keep = !(pid < p.mapid) && !((int)mq < p.mapq) && !(__ddiv_rn((double)alen, (double)lq) < p.aln_cov);
-    const uint32_t b0 = __ldg(&p.blk_off[r]);
-    const uint8_t* __restrict__ q = p.qual + (size_t)b0 * 16;
+    const uint32_t* __restrict__ q = p.planes + (size_t)__ldg(&p.vec_off[r]) * 4;
     if (keep) {
       uint32_t s = 0;
-      for (uint32_t i = lane; i < lq; i += 32) s += __ldg(q + i) & 0x7fu;
+      const uint32_t nw = ((lq + 31u) >> 5) * p.NQ;
+      for (uint32_t i = lane; i < nw; i += 32) {
+        const uint32_t b = i / p.NQ, k = i - b * p.NQ;
+        s += (uint32_t)__popc(__ldg(q + b * p.NP + 3 + k)) << k;
+      }
       s = warp_sum(s);
       keep = (long long)s >= (long long)p.readq * (long long)lq;
     }
@@ -620,10 +612,12 @@ __global__ void __launch_bounds__(256) k_long_reads(const LongParams p) {
       } else { w0 = __ldg(rec + 1 + 2 * o); x0 = __ldg(rec + 2 + 2 * o); }
       const uint32_t q0 = w0 & 0xffffu, len = w0 >> 16;
       for (uint32_t i = lane; i < len; i += 32) {
-        const uint32_t qi = q0 + i;
-        if (__ldg(q + qi) >= p.qthr) {
-          const uint32_t sw = __ldg(p.seq2 + b0 + (qi >> 4)), bb = qi & 15u;
-          const uint32_t cd = ((sw >> bb) & 1u) | (((sw >> (16 + bb)) & 1u) << 1);
+        const uint32_t qi = q0 + i, bb = qi & 31u;
+        const uint32_t* __restrict__ blk = q + (qi >> 5) * p.NP;
+        uint32_t ph = 0;
+        for (uint32_t b = 0; b < p.NQ; ++b) ph |= ((__ldg(blk + 3 + b) >> bb) & 1u) << b;
+        if (((__ldg(blk + 2) >> bb) & 1u) && ph >= p.baseq) {     // candidate base with Phred >= baseq
+          const uint32_t cd = ((__ldg(blk) >> bb) & 1u) | (((__ldg(blk + 1) >> bb) & 1u) << 1);
           atomicAdd(p.counts + (size_t)cd * p.gpad + loc + x0 + i, 1u);
         }
       }
@@ -666,15 +660,20 @@ __global__ void __launch_bounds__(256) k_restat(const uint32_t* __restrict__ cou
   }
 }
 
-// the row widths the tile kernel is instantiated for; a batch runs at the smallest one >= its row_words
+// the row widths (and Phred plane counts) the tile kernel is instantiated for; a batch runs at the smallest
+// width >= its row_words
 struct PileKernel { uint32_t W; void (*fn)(const PileParams); };
-PileKernel pick_kernel(uint32_t row_words) {
-  static const PileKernel k[] = {{3, k_pileup_v2<3>},   {4, k_pileup_v2<4>},   {5, k_pileup_v2<5>},  {6, k_pileup_v2<6>},
-                                 {7, k_pileup_v2<7>},   {8, k_pileup_v2<8>},   {10, k_pileup_v2<10>}, {12, k_pileup_v2<12>},
-                                 {16, k_pileup_v2<16>}};
-  for (const PileKernel& e : k)
-    if (e.W >= row_words) return e;
-  return k[sizeof(k) / sizeof(k[0]) - 1];
+PileKernel pick_kernel(uint32_t row_words, uint32_t q_planes) {
+  static const PileKernel k6[] = {{3, k_pileup_v2<3, 6>},   {4, k_pileup_v2<4, 6>},   {5, k_pileup_v2<5, 6>},
+                                  {6, k_pileup_v2<6, 6>},   {7, k_pileup_v2<7, 6>},   {8, k_pileup_v2<8, 6>},
+                                  {10, k_pileup_v2<10, 6>}, {12, k_pileup_v2<12, 6>}, {16, k_pileup_v2<16, 6>}};
+  static const PileKernel k7[] = {{3, k_pileup_v2<3, 7>},   {4, k_pileup_v2<4, 7>},   {5, k_pileup_v2<5, 7>},
+                                  {6, k_pileup_v2<6, 7>},   {7, k_pileup_v2<7, 7>},   {8, k_pileup_v2<8, 7>},
+                                  {10, k_pileup_v2<10, 7>}, {12, k_pileup_v2<12, 7>}, {16, k_pileup_v2<16, 7>}};
+  const PileKernel* k = q_planes == 6 ? k6 : k7;
+  for (int i = 0; i < 9; ++i)
+    if (k[i].W >= row_words) return k[i];
+  return k[8];
 }
 
 size_t pile_smem_bytes(uint32_t W, uint32_t rmax) {
@@ -705,19 +704,24 @@ extern "C" int mb_snps_pileup_dev(mb_ctx* ctx, const mb_dev_reads* reads, const 
     ctx->tile_rng_cap = (size_t)2 * n_ktiles + 2;
   }
   // shared memory per CTA: two CTAs per SM (override with MB_PILE_SMEM_KB for experiments)
-  const PileKernel kern = pick_kernel(reads->row_words);
+  if (reads->n_planes != 3 + reads->q_planes || (reads->q_planes != 6 && reads->q_planes != 7))
+    return mb::fail(MB_EINVAL, "mb_snps_pileup_dev: reads were not packed in snps mode");
+  const PileKernel kern = pick_kernel(reads->row_words, reads->q_planes);
   const uint32_t W = kern.W;                                          // instantiated row width >= row_words
   if (!ctx->pile_smem) {
     size_t kb = 100;
     if (const char* e = getenv("MB_PILE_SMEM_KB")) { long v = atol(e); if (v >= 32 && v <= 220) kb = (size_t)v; }
     ctx->pile_smem = kb * 1024;
   }
-  if (!(ctx->pile_attr_mask & (1u << W))) {
+  const uint32_t attr_bit = 1u << (W + (reads->q_planes == 7 ? 16u : 0u));
+  if (!(ctx->pile_attr_mask & attr_bit)) {
     MB_CUDA_TRY(cudaFuncSetAttribute(kern.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->pile_smem));
+    ctx->pile_attr_mask |= attr_bit;
+  }
+  {
     int occ = 0;
     MB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern.fn, NT, ctx->pile_smem));
     ctx->pile_occ = occ > 0 ? occ : 1;
-    ctx->pile_attr_mask |= 1u << W;
   }
   const size_t fixed = sizeof(uint4) * (size_t)VCL * NCOL;
   uint32_t rmax = (uint32_t)((ctx->pile_smem - fixed) / (sizeof(uint4) * W));
@@ -741,11 +745,10 @@ extern "C" int mb_snps_pileup_dev(mb_ctx* ctx, const mb_dev_reads* reads, const 
   }
   PileParams p;
   p.hdr = reinterpret_cast<const uint4*>(reads->hdr);
-  p.blk_off = reads->blk_off;
+  p.vec_off = reads->vec_off;
   p.cplx = reads->cplx;
   p.cigar = reads->cigar;
-  p.seq2 = reads->seq2;
-  p.qual = reinterpret_cast<const uint4*>(reads->qual);
+  p.planes = reinterpret_cast<const uint4*>(reads->planes);
   p.tile_rng = ctx->tile_rng;
   p.tile_species = dl.tile_species;
   p.counts = counts_dev;
@@ -753,10 +756,6 @@ extern "C" int mb_snps_pileup_dev(mb_ctx* ctx, const mb_dev_reads* reads, const 
   p.sched = ctx->sched;
   p.gpad = L->gpad;
   p.n_ktiles = n_ktiles;
-  p.n_blocks = (uint32_t)reads->n_blocks;
-  p.row_prefetch = getenv("MB_PILE_ROWPF") ? 1u : 0u;
-  p.l2_prefetch = getenv("MB_PILE_L2PF") ? 1u : 0u;   // measured slower on C2 (1.4x DRAM traffic): off unless asked for
-  p.avg_blocks = (uint32_t)((reads->n_blocks + reads->n_reads - 1) / (reads->n_reads ? reads->n_reads : 1));
   p.W = W;
   p.rmax = rmax;
   rc = mb::get_filter_tables(ctx, f, &p.t_pid, &p.t_cov);
@@ -764,7 +763,7 @@ extern "C" int mb_snps_pileup_dev(mb_ctx* ctx, const mb_dev_reads* reads, const 
   p.pid_always = (f->mapid != f->mapid || f->mapid == -HUGE_VAL) ? 1u : 0u;
   p.readq_eff = f->readq <= 0 ? 0u : (f->readq > 128 ? 128u : (uint32_t)f->readq);
   p.mapq = f->mapq;
-  p.qadd = (0x80u - (uint32_t)f->baseq) * 0x01010101u;
+  p.baseq = (uint32_t)f->baseq;
   p.defer_restat = reads->n_long ? 1u : 0u;
   const uint32_t grid = min(n_ktiles, (uint32_t)(ctx->sm_count * ctx->pile_occ));
   { int trc = mb::timing_begin(ctx); if (trc) return trc; }
@@ -773,8 +772,7 @@ extern "C" int mb_snps_pileup_dev(mb_ctx* ctx, const mb_dev_reads* reads, const 
   ctx->launches++;
   if (reads->n_long) {
     LongParams lp;
-    lp.hdr = p.hdr; lp.blk_off = p.blk_off; lp.cplx = p.cplx; lp.cigar = p.cigar; lp.seq2 = p.seq2;
-    lp.qual = reads->qual;
+    lp.hdr = p.hdr; lp.vec_off = p.vec_off; lp.cplx = p.cplx; lp.cigar = p.cigar; lp.planes = reads->planes;
     lp.long_idx = reads->long_idx;
     lp.tile_species = dl.tile_species;
     lp.counts = counts_dev;
@@ -782,7 +780,8 @@ extern "C" int mb_snps_pileup_dev(mb_ctx* ctx, const mb_dev_reads* reads, const 
     lp.gpad = L->gpad;
     lp.n_long = reads->n_long;
     lp.mapid = f->mapid; lp.aln_cov = f->aln_cov; lp.readq = f->readq; lp.mapq = f->mapq;
-    lp.qthr = 0x80u + (uint32_t)f->baseq;
+    lp.baseq = (uint32_t)f->baseq;
+    lp.NQ = reads->q_planes; lp.NP = reads->n_planes;
     const uint32_t lgrid = min((reads->n_long + 7u) / 8u, (uint32_t)ctx->sm_count * 8u);
     k_long_reads<<<lgrid, 256, 0, st>>>(lp);
     ctx->launches++;

@@ -18,7 +18,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmidas_b200.so")
 
 MB_TILE = 4096
-MB_BLOCK = 16
+MB_BLOCK = 32
 STATUS = {0: "MB_OK", -1: "MB_EINVAL", -2: "MB_ECUDA", -3: "MB_ENOMEM", -4: "MB_EOVERFLOW",
           -5: "MB_EMALFORMED", -6: "MB_EUNSORTED"}
 
@@ -46,11 +46,12 @@ class CMergeParams(C.Structure):
 
 
 class CPackedReads(C.Structure):
-    _fields_ = [("n_reads", C.c_uint64), ("n_blocks", C.c_uint64), ("n_cigar_words", C.c_uint64),
+    _fields_ = [("n_reads", C.c_uint64), ("n_vec", C.c_uint64), ("n_cigar_words", C.c_uint64),
                 ("total_bases", C.c_uint64), ("max_ref_span", C.c_uint32), ("sorted", C.c_uint32),
-                ("row_words", C.c_uint32), ("n_long", C.c_uint32), ("long_idx", C.c_void_p),
-                ("hdr", C.c_void_p), ("blk_off", C.c_void_p), ("cplx", C.c_void_p), ("cigar", C.c_void_p),
-                ("seq2", C.c_void_p), ("qual", C.c_void_p)]
+                ("row_words", C.c_uint32), ("n_long", C.c_uint32), ("q_planes", C.c_uint32),
+                ("n_planes", C.c_uint32), ("long_idx", C.c_void_p),
+                ("hdr", C.c_void_p), ("vec_off", C.c_void_p), ("cplx", C.c_void_p), ("cigar", C.c_void_p),
+                ("planes", C.c_void_p)]
 
 
 HDR_DTYPE = np.dtype([("loc", "<u4"), ("l_qseq", "<u2"), ("alen", "<u2"), ("q_start", "<u2"), ("nm", "<u2"),
@@ -236,7 +237,9 @@ class PackedReads:
         return self._p.contents
 
     n_reads = property(lambda s: int(s.c.n_reads))
-    n_blocks = property(lambda s: int(s.c.n_blocks))
+    n_vec = property(lambda s: int(s.c.n_vec))
+    q_planes = property(lambda s: int(s.c.q_planes))
+    n_planes = property(lambda s: int(s.c.n_planes))
     total_bases = property(lambda s: int(s.c.total_bases))
     max_ref_span = property(lambda s: int(s.c.max_ref_span))
     row_words = property(lambda s: int(s.c.row_words))
@@ -245,8 +248,8 @@ class PackedReads:
     @property
     def nbytes(self) -> int:
         c = self.c
-        return int(16 * c.n_reads + 4 * (c.n_reads + 1) + 4 * c.n_reads + 4 * c.n_cigar_words + 4 * c.n_blocks
-                   + 16 * c.n_blocks + 4 * c.n_long)
+        return int(16 * c.n_reads + 4 * (c.n_reads + 1) + 4 * c.n_reads + 4 * c.n_cigar_words + 16 * c.n_vec
+                   + 4 * c.n_long)
 
     def _view(self, ptr, n, dt):
         if n == 0:
@@ -256,11 +259,10 @@ class PackedReads:
 
     # numpy views of the packed arrays (valid while this object lives)
     hdr = property(lambda s: s._view(s.c.hdr, s.n_reads, HDR_DTYPE))
-    blk_off = property(lambda s: s._view(s.c.blk_off, s.n_reads + 1, np.dtype("<u4")))
+    vec_off = property(lambda s: s._view(s.c.vec_off, s.n_reads + 1, np.dtype("<u4")))
     cplx = property(lambda s: s._view(s.c.cplx, s.n_reads, np.dtype("<u4")))
     cigar = property(lambda s: s._view(s.c.cigar, int(s.c.n_cigar_words), np.dtype("<u4")))
-    seq2 = property(lambda s: s._view(s.c.seq2, s.n_blocks, np.dtype("<u4")))
-    qual = property(lambda s: s._view(s.c.qual, s.n_blocks * MB_BLOCK, np.dtype("u1")))
+    planes = property(lambda s: s._view(s.c.planes, 4 * s.n_vec, np.dtype("<u4")))
     long_idx = property(lambda s: s._view(s.c.long_idx, s.n_long, np.dtype("<u4")))
 
 
@@ -269,7 +271,7 @@ class DevReads:
         h = C.c_void_p()
         _check(load().mb_reads_upload(ctx._h, packed._p, C.byref(h)))
         self._h, self._ctx = h, ctx
-        self.n_reads, self.total_bases, self.n_blocks = packed.n_reads, packed.total_bases, packed.n_blocks
+        self.n_reads, self.total_bases, self.n_vec = packed.n_reads, packed.total_bases, packed.n_vec
         self.nbytes = int(load().mb_reads_bytes(h))
 
     def free(self):

@@ -64,25 +64,78 @@ def test_two_run_reads_that_do_not_fit_the_run_word_keep_a_record():
     assert not (pk.hdr[0]["flags"] & 8)            # first run not at the read's position
 
 
+def _decode(pk, i):
+    """(base code, candidate bit, Phred) per query base of read i from the bit-planar blocks."""
+    hdr, off, planes = pk.hdr, pk.vec_off, pk.planes
+    lq, NP, NQ = int(hdr[i]["l_qseq"]), pk.n_planes, pk.q_planes
+    p0 = NP - NQ
+    reg = planes[4 * int(off[i]):4 * int(off[i + 1])]
+    assert len(reg) >= -(-lq // 32) * NP
+    code, cand, ph = [], [], []
+    for q in range(lq):
+        w = reg[(q // 32) * NP:(q // 32 + 1) * NP]
+        bit = q % 32
+        if p0:
+            code.append(((int(w[0]) >> bit) & 1) | (((int(w[1]) >> bit) & 1) << 1))
+            cand.append((int(w[2]) >> bit) & 1)
+        ph.append(sum(((int(w[p0 + k]) >> bit) & 1) << k for k in range(NQ)))
+    # everything after the last base of the read is zero padding
+    for q in range(lq, 32 * (-(-lq // 32))):
+        w = reg[(q // 32) * NP:(q // 32 + 1) * NP]
+        assert not any((int(x) >> (q % 32)) & 1 for x in w)
+    assert not reg[-(-lq // 32) * NP:].any()
+    return code, cand, ph
+
+
 def test_block_encoding_round_trips():
     ref, reads = synth.synth_snps(seed=5, n_species=1, contigs_per_species=1, contig_len=5000, n_reads=300, read_len=77)
     pk = lib.PackedReads(reads, lib.Layout.of(ref), "snps")
     assert pk.n_reads == 300 and pk.total_bases == 300 * 77
-    blk, seq2, qual = pk.blk_off, pk.seq2, pk.qual
+    assert pk.q_planes == 6 and pk.n_planes == 9                    # every synthetic Phred is <= 41
     nib = np.array([1, 2, 4, 8])
     for i in (0, 17, 299):
         s0 = int(reads.seq_off[i])
+        code, cand, ph = _decode(pk, i)
+        # which query bases sit in an M/=/X run (and inside the contig): only those may be candidates
+        in_run, q, r = [0] * 77, 0, 0
+        room = int(ref.contig_len[reads.ref_id[i]]) - int(reads.pos[i])
+        for c in reads.cigar[int(reads.cigar_off[i]):int(reads.cigar_off[i + 1])]:
+            op, ln = int(c) & 15, int(c) >> 4
+            if op in (OP_M, 7, 8):
+                for x in range(ln):
+                    in_run[q + x] = int(r + x < room)
+                q += ln; r += ln
+            elif op in (OP_I, 4):
+                q += ln
+            elif op in (OP_D, 3):
+                r += ln
         for q in range(77):
-            w = int(seq2[int(blk[i]) + q // 16])
-            code = ((w >> (q % 16)) & 1) | (((w >> (16 + q % 16)) & 1) << 1)
-            qb = int(qual[int(blk[i]) * 16 + q])
             src = int(reads.seq[s0 + q])
-            assert (qb & 0x7F) == int(reads.qual[s0 + q])
-            assert bool(qb & 0x80) == (src in (1, 2, 4, 8))
+            assert ph[q] == int(reads.qual[s0 + q])
+            assert cand[q] == int(src in (1, 2, 4, 8) and in_run[q])
             if src in (1, 2, 4, 8):
-                assert nib[code] == src
-        # padding of the last block is zero
-        assert not qual[int(blk[i]) * 16 + 77:int(blk[i + 1]) * 16].any()
+                assert nib[code[q]] == src
+
+
+def test_candidate_plane_excludes_clips_insertions_and_bases_past_the_contig_end():
+    seq = "ACGTN" * 8                                                # 40 bases, every fifth is N
+    pk = lib.PackedReads(_one([(4, 3), (OP_M, 10), (OP_I, 2), (OP_M, 20), (4, 5)], seq=seq, pos=985), lay(), "snps")
+    _, cand, _ = _decode(pk, 0)                                      # contig length 1000: 15 reference bases left
+    exp = [0] * 40
+    for q, r in [(3 + k, k) for k in range(10)] + [(15 + k, 10 + k) for k in range(20)]:
+        exp[q] = int(seq[q] != "N" and 985 + r < 1000)
+    assert cand == exp
+
+
+def test_seven_phred_planes_only_when_needed_and_genes_mode_holds_phred_planes_only():
+    pk = lib.PackedReads(_one([(OP_M, 40)], qual=[63] * 40), lay(), "snps")
+    assert (pk.q_planes, pk.n_planes) == (6, 9)
+    pk = lib.PackedReads(_one([(OP_M, 40)], qual=[64] + [3] * 39), lay(), "snps")
+    assert (pk.q_planes, pk.n_planes) == (7, 10)
+    assert _decode(pk, 0)[2] == [64] + [3] * 39
+    pk = lib.PackedReads(_one([(OP_M, 40)], qual=list(range(40))), lay(), "genes")
+    assert (pk.q_planes, pk.n_planes) == (6, 6) and pk.n_vec == 3    # 2 blocks x 6 words = 12 words
+    assert _decode(pk, 0)[2] == list(range(40))
 
 
 def test_row_width_and_long_reads():

@@ -48,6 +48,8 @@ def test_synthetic_default_filters(ctx, seed, n_species, cps, clen, n_reads, L):
     Filters(mapid=99.0, aln_cov=0.95, readq=36, mapq=40, baseq=41),
     Filters(mapid=94.0, aln_cov=0.75, readq=20, mapq=20, baseq=1),
     Filters(mapid=98.66666666666667, aln_cov=0.9866666666666667, readq=35, mapq=0, baseq=30),
+    Filters(mapid=0.0, aln_cov=0.0, readq=0, mapq=0, baseq=64),   # above every Phred a 6-plane batch can hold
+    Filters(mapid=0.0, aln_cov=0.0, readq=0, mapq=0, baseq=37),
 ])
 def test_filter_settings(ctx, filters):
     ref, reads = synth.synth_snps(seed=21, n_species=2, contigs_per_species=2, contig_len=8_000, n_reads=25_000,
@@ -69,7 +71,8 @@ def test_random_cigars(ctx, seed, n_species, cps, lo, hi, n_reads, max_len):
     ref = gen.make_ref(rng, n_species, cps, lo, hi)
     reads = gen.random_reads(seed, ref, n_reads, max_len=max_len)
     for filters in (Filters(), Filters(mapid=0.0, aln_cov=0.0, readq=0, mapq=0, baseq=0),
-                    Filters(mapid=90.0, aln_cov=0.5, readq=25, mapq=10, baseq=20)):
+                    Filters(mapid=90.0, aln_cov=0.5, readq=25, mapq=10, baseq=20),
+                    Filters(mapid=0.0, aln_cov=0.0, readq=0, mapq=0, baseq=70)):   # 7 Phred planes, top bit set
         _check(ctx, ref, reads, filters)
 
 

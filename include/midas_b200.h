@@ -141,7 +141,8 @@ typedef struct {
  * The per-base data of a read is bit-planar: the read is cut into MB_BLOCK-base blocks and every
  * per-base bit of a block is one 32-bit word (bit k = base 32*b + k), so the kernels test and place
  * 32 bases with one logic instruction. Block b of read i is the n_planes words at
- *   planes[4*vec_off[i] + b*n_planes + p]            (the read's region is 16-byte aligned,
+ *   planes[8*vec_off[i] + b*n_planes + p]            (the read's region is 32-byte aligned = one
+ *                                                     256-bit load per lane and sector,
  *                                                     ceil(l_qseq/32)*n_planes words, zero padded)
  * snps mode (n_planes = 3 + q_planes):
  *   p = 0, 1  low / high bit of the base code (A=0 C=1 G=2 T=3; anything else 0)
@@ -159,7 +160,7 @@ typedef struct {
  */
 typedef struct {
   uint64_t n_reads;
-  uint64_t n_vec;            /* 16-byte units in planes[] */
+  uint64_t n_vec;            /* 32-byte units in planes[] */
   uint64_t n_cigar_words;
   uint64_t total_bases;      /* sum of l_qseq (the Gbases numerator) */
   uint32_t max_ref_span;
@@ -172,10 +173,10 @@ typedef struct {
   uint32_t n_planes;         /* words per block: 3 + q_planes (snps) or q_planes (genes) */
   const uint32_t* long_idx;  /* [n_long] ascending indices of the MB_RF_LONG reads */
   const mb_read_hdr* hdr;    /* [n_reads] */
-  const uint32_t* vec_off;   /* [n_reads+1] first 16-byte unit of each read's region in planes[] */
+  const uint32_t* vec_off;   /* [n_reads+1] first 32-byte unit of each read's region in planes[] */
   const uint32_t* cplx;      /* [n_reads] */
   const uint32_t* cigar;     /* [n_cigar_words] */
-  const uint32_t* planes;    /* [4*n_vec] */
+  const uint32_t* planes;    /* [8*n_vec], 32-byte aligned */
 } mb_packed_reads;
 
 /* Host-side re-layout of decoded BAM records into the packed SoA (the step

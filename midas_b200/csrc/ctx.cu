@@ -262,7 +262,7 @@ int upload_reads(mb_ctx* c, const mb_packed_reads* h, mb_dev_reads* d, bool stag
       {(void**)&d->vec_off, h->vec_off, sizeof(uint32_t) * (size_t)(h->n_reads + 1)},
       {(void**)&d->cplx, h->cplx, sizeof(uint32_t) * (size_t)h->n_reads},
       {(void**)&d->cigar, h->cigar, sizeof(uint32_t) * (size_t)h->n_cigar_words},
-      {(void**)&d->planes, h->planes, (size_t)h->n_vec * 16}};
+      {(void**)&d->planes, h->planes, (size_t)h->n_vec * 32}};
   int slot = 8;
   for (auto& p : parts) {
     // +256 B of zero slack so vectorised tail loads never leave the allocation

@@ -348,7 +348,7 @@ extern "C" int mb_pack_reads(const mb_plain_reads* in, const mb_layout* L, int m
     const ReadGeom& g = geom[src(j)];
     blk_off[j] = (uint32_t)nb;
     cg_off[j] = (uint32_t)ncw;
-    nb += ((uint64_t)g.n_blk * NP + 3) / 4;                     // 16-byte units of the read's region
+    nb += ((uint64_t)g.n_blk * NP + 7) / 8;                     // 32-byte units of the read's region
     ncw += g.n_cplx_words;
     tot_bases += (uint64_t)in->l_qseq[src(j)];
     max_span = std::max<uint32_t>(max_span, g.ref_span);
@@ -380,7 +380,7 @@ extern "C" int mb_pack_reads(const mb_plain_reads* in, const mb_layout* L, int m
   memset(o, 0, sizeof(*o));
   o->pinned = pinned != 0;
   size_t sizes[7] = {sizeof(mb_read_hdr) * (size_t)n, sizeof(uint32_t) * (size_t)(n + 1), sizeof(uint32_t) * (size_t)n,
-                     sizeof(uint32_t) * (size_t)ncw, (size_t)nb * 16, 0,
+                     sizeof(uint32_t) * (size_t)ncw, (size_t)nb * 32, 0,
                      sizeof(uint32_t) * (size_t)n_long};
   for (int k = 0; k < 7; ++k) {
     o->buf[k] = alloc_host(sizes[k], o->pinned);
@@ -445,8 +445,8 @@ extern "C" int mb_pack_reads(const mb_plain_reads* in, const mb_layout* L, int m
       const uint8_t* s = in->seq + in->seq_off[i];
       const uint8_t* q = in->qual + in->seq_off[i];
       const uint32_t lq = h.l_qseq;
-      uint32_t* reg = planes + (size_t)blk_off[j] * 4;
-      memset(reg, 0, ((size_t)blk_off[j + 1] - blk_off[j]) * 16);
+      uint32_t* reg = planes + (size_t)blk_off[j] * 8;
+      memset(reg, 0, ((size_t)blk_off[j + 1] - blk_off[j]) * 32);
       for (uint32_t b = 0; b < g.n_blk; ++b) {
         uint32_t w[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};        // lo, hi, acgt, Phred bits 0..6
         const uint32_t nk = std::min<uint32_t>(MB_BLOCK, lq - b * MB_BLOCK);

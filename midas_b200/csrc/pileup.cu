@@ -64,7 +64,7 @@ struct PileParams {
   const uint32_t* vec_off;
   const uint32_t* cplx;
   const uint32_t* cigar;
-  const uint4* planes;        // bit-planar read data, 16-byte units (mb_packed_reads)
+  const uint32_t* planes;     // bit-planar read data (mb_packed_reads), regions in 32-byte units
   const uint32_t* tile_rng;   // [2 * n_ktiles]
   const int32_t* tile_species;  // per MB_TILE tile
   uint32_t* counts;
@@ -96,6 +96,13 @@ __device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
     (s) = _a ^ _b ^ _d;                             \
     (c) = (_a & _b) | ((_a ^ _b) & _d);             \
   } while (0)
+
+// one 256-bit load: a whole 32-byte sector per lane (the regions of the packed reads are 32-byte aligned)
+__device__ __forceinline__ void ldg256(const uint32_t* __restrict__ p, uint32_t* r) {
+  asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+      : "l"(p));
+}
 
 __device__ __forceinline__ uint32_t shl_clamp(uint32_t v, uint32_t n) {   // v << n, 0 for n >= 32
   uint32_t r;
@@ -160,7 +167,8 @@ __global__ void k_tile_ranges(const uint4* __restrict__ hdr, uint32_t n_reads, u
     }                                                                                       \
   } while (0)
 
-template <int WT, int NQ>
+// VAR: experiment switches (bit 0: 128-bit plane loads in steps of four blocks instead of 256-bit loads)
+template <int WT, int NQ, int VAR>
 __global__ void __launch_bounds__(NT, 2) k_pileup_v2(const PileParams p) {
   extern __shared__ __align__(16) uint32_t smem[];
   constexpr uint32_t W = (uint32_t)WT;          // row words (compile time: every per-lane loop below unrolls)
@@ -256,6 +264,8 @@ __global__ void __launch_bounds__(NT, 2) k_pileup_v2(const PileParams p) {
 
     uint32_t pass_rows = 0;
     bool accumulate = false;
+    uint4 nh = make_uint4(0, 0, 0, 0);                         // header, block offset, run word and predecessor
+    uint32_t nb0 = 0, ncw = 0, nprev = 0;                       // of this thread's next read: one step ahead
     for (uint32_t rb = r0; rb < r1; rb += p.rmax) {
       const int n = (int)min(p.rmax, r1 - rb);
       if (pass_rows + (uint32_t)n > PASS_ROWS) {  // keep the shared counters below 2^VCL
@@ -268,9 +278,10 @@ __global__ void __launch_bounds__(NT, 2) k_pileup_v2(const PileParams p) {
       // ---- STAGE: one thread per read, everything in registers: header filters (snps.py:148,154,157),
       // row index table, the read's bit planes as independent 128-bit loads (L1 absorbs the stride
       // between lanes), bit-sliced base-quality test, mean-quality filter, CIGAR placement, row store
-      uint4 nh = make_uint4(0, 0, 0, 0);                       // header, block offset, run word and predecessor
-      uint32_t nb0 = 0, ncw = 0, nprev = 0;                     // of this thread's next read: one step ahead
-      if (tid < n) {
+      if (rb == r0) {                                          // later rounds: requested before the previous COUNT
+        nh = make_uint4(0, 0, 0, 0); nb0 = 0; ncw = 0; nprev = 0;
+      }
+      if (rb == r0 && tid < n) {
         nh = __ldg(&p.hdr[rb + tid]);
         nb0 = __ldg(&p.vec_off[rb + tid]);
         ncw = __ldg(&p.cplx[rb + tid]);
@@ -322,37 +333,58 @@ __global__ void __launch_bounds__(NT, 2) k_pileup_v2(const PileParams p) {
         for (int w = 0; w <= WT + 1; ++w) { ql[w] = 0; qh[w] = 0; qv[w] = 0; }
         bool keep = false;
         if (needq) {
-          const uint32_t nvec = (((lq + 31u) >> 5) * (uint32_t)NP + 3u) >> 2;
-          const uint4* __restrict__ vp = p.planes + b0;
           uint32_t pc[NQ];
 #pragma unroll
           for (int k = 0; k < NQ; ++k) pc[k] = 0;
+          // one 32-base block -> query word w of the three planes
+          auto convert = [&](const int w, const uint32_t* __restrict__ blk) {
+            // Phred >= baseq, bit-sliced over 32 bases: from the low bit up, "greater or equal so far"
+            uint32_t ge = 0xffffffffu;
 #pragma unroll
-          for (int s4 = 0; s4 < WT; s4 += 4) {              // 4 blocks = NP independent 128-bit loads per step
-            const int nb = WT - s4 < 4 ? WT - s4 : 4;
-            const int nv = (nb * NP + 3) / 4;
-            uint32_t raw[4 * NP];
+            for (int k = 0; k < NQ; ++k) {
+              const uint32_t pk = blk[3 + k];
+              ge = (pk & ge) | (~tmk[k] & (pk | ge));       // threshold bit set: and, clear: or (one LOP3)
+              pc[k] += __popc(pk);
+            }
+            ql[w + 1] = blk[0];
+            qh[w + 1] = blk[1];
+            qv[w + 1] = blk[2] & ge & q_allow;
+          };
+          constexpr bool LD256 = WT <= 8 && !(VAR & 1);
+          if (LD256) {
+            // the whole read at once: ceil(9 W / 8) independent 256-bit loads, one full sector per lane each
+            constexpr int NV8 = (WT * NP + 7) / 8;
+            const uint32_t nv8 = (((lq + 31u) >> 5) * (uint32_t)NP + 7u) >> 3;
+            const uint32_t* __restrict__ vp = p.planes + (size_t)b0 * 8;
+            uint32_t raw[8 * NV8];
 #pragma unroll
-            for (int u = 0; u < NP; ++u) {
-              uint4 t = make_uint4(0, 0, 0, 0);
-              if (u < nv && (uint32_t)(s4 / 4 * NP + u) < nvec) t = __ldg(vp + s4 / 4 * NP + u);
-              raw[4 * u] = t.x; raw[4 * u + 1] = t.y; raw[4 * u + 2] = t.z; raw[4 * u + 3] = t.w;
+            for (int u = 0; u < NV8; ++u) {
+              if ((uint32_t)u < nv8) ldg256(vp + 8 * u, raw + 8 * u);
+              else {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) raw[8 * u + c] = 0;
+              }
             }
 #pragma unroll
-            for (int bl = 0; bl < 4; ++bl) {
-              if (bl < nb) {
-                // Phred >= baseq, bit-sliced over 32 bases: from the low bit up, "greater or equal so far"
-                uint32_t ge = 0xffffffffu;
+            for (int bl = 0; bl < WT; ++bl) convert(bl, raw + bl * NP);
+          } else {
+            // wide rows: steps of four blocks = NP independent 128-bit loads
+            const uint32_t nvec = (((lq + 31u) >> 5) * (uint32_t)NP + 3u) >> 2;
+            const uint4* __restrict__ vp = reinterpret_cast<const uint4*>(p.planes) + (size_t)b0 * 2;
 #pragma unroll
-                for (int k = 0; k < NQ; ++k) {
-                  const uint32_t pk = raw[bl * NP + 3 + k];
-                  ge = (pk & ge) | (~tmk[k] & (pk | ge));   // threshold bit set: and, clear: or (one LOP3)
-                  pc[k] += __popc(pk);
-                }
-                ql[s4 + bl + 1] = raw[bl * NP];
-                qh[s4 + bl + 1] = raw[bl * NP + 1];
-                qv[s4 + bl + 1] = raw[bl * NP + 2] & ge & q_allow;
+            for (int s4 = 0; s4 < WT; s4 += 4) {
+              const int nb = WT - s4 < 4 ? WT - s4 : 4;
+              const int nv = (nb * NP + 3) / 4;
+              uint32_t raw[4 * NP];
+#pragma unroll
+              for (int u = 0; u < NP; ++u) {
+                uint4 t = make_uint4(0, 0, 0, 0);
+                if (u < nv && (uint32_t)(s4 / 4 * NP + u) < nvec) t = __ldg(vp + s4 / 4 * NP + u);
+                raw[4 * u] = t.x; raw[4 * u + 1] = t.y; raw[4 * u + 2] = t.z; raw[4 * u + 3] = t.w;
               }
+#pragma unroll
+              for (int bl = 0; bl < 4; ++bl)
+                if (bl < nb) convert(s4 + bl, raw + bl * NP);
             }
           }
           // mean-quality filter (snps.py:151): mean(q) < readq  <=>  sum(q) < readq * l_qseq (exact)
@@ -453,6 +485,16 @@ __global__ void __launch_bounds__(NT, 2) k_pileup_v2(const PileParams p) {
           if (slot >= W) slot -= W;
           dst[slot] = make_uint4(rv[j] & ~rh[j] & ~rl[j], rv[j] & ~rh[j] & rl[j], rv[j] & rh[j] & ~rl[j],
                                  rv[j] & rh[j] & rl[j]);
+        }
+      }
+      if (rb + p.rmax < r1) {   // the first read of my next round: requested now, in flight during COUNT
+        const uint32_t nr = rb + p.rmax + (uint32_t)tid;
+        nh = make_uint4(0, 0, 0, 0); nb0 = 0; ncw = 0; nprev = 0;
+        if (nr < r1) {
+          nh = __ldg(&p.hdr[nr]);
+          nb0 = __ldg(&p.vec_off[nr]);
+          ncw = __ldg(&p.cplx[nr]);
+          if (tid > 0) nprev = __ldg(&p.hdr[nr - 1].x);
         }
       }
       __syncthreads();
@@ -581,7 +623,7 @@ __global__ void __launch_bounds__(256) k_long_reads(const LongParams p) {
     double pid = __ddiv_rn((double)(100 * ((int)alen - (int)nm)), (double)alen);
     if (fl & MB_RF_NMSAT) pid = -__longlong_as_double(0x7ff0000000000000ll);
     bool keep = !(pid < p.mapid) && !((int)mq < p.mapq) && !(__ddiv_rn((double)alen, (double)lq) < p.aln_cov);
-    const uint32_t* __restrict__ q = p.planes + (size_t)__ldg(&p.vec_off[r]) * 4;
+    const uint32_t* __restrict__ q = p.planes + (size_t)__ldg(&p.vec_off[r]) * 8;
     if (keep) {
       uint32_t s = 0;
       const uint32_t nw = ((lq + 31u) >> 5) * p.NQ;
@@ -664,12 +706,18 @@ __global__ void __launch_bounds__(256) k_restat(const uint32_t* __restrict__ cou
 // width >= its row_words
 struct PileKernel { uint32_t W; void (*fn)(const PileParams); };
 PileKernel pick_kernel(uint32_t row_words, uint32_t q_planes) {
-  static const PileKernel k6[] = {{3, k_pileup_v2<3, 6>},   {4, k_pileup_v2<4, 6>},   {5, k_pileup_v2<5, 6>},
-                                  {6, k_pileup_v2<6, 6>},   {7, k_pileup_v2<7, 6>},   {8, k_pileup_v2<8, 6>},
-                                  {10, k_pileup_v2<10, 6>}, {12, k_pileup_v2<12, 6>}, {16, k_pileup_v2<16, 6>}};
-  static const PileKernel k7[] = {{3, k_pileup_v2<3, 7>},   {4, k_pileup_v2<4, 7>},   {5, k_pileup_v2<5, 7>},
-                                  {6, k_pileup_v2<6, 7>},   {7, k_pileup_v2<7, 7>},   {8, k_pileup_v2<8, 7>},
-                                  {10, k_pileup_v2<10, 7>}, {12, k_pileup_v2<12, 7>}, {16, k_pileup_v2<16, 7>}};
+#define MB_PK(W, Q) {W, k_pileup_v2<W, Q, 0>}
+  static const PileKernel k6[] = {MB_PK(3, 6), MB_PK(4, 6), MB_PK(5, 6),  MB_PK(6, 6),  MB_PK(7, 6),
+                                  MB_PK(8, 6), MB_PK(10, 6), MB_PK(12, 6), MB_PK(16, 6)};
+  static const PileKernel k7[] = {MB_PK(3, 7), MB_PK(4, 7), MB_PK(5, 7),  MB_PK(6, 7),  MB_PK(7, 7),
+                                  MB_PK(8, 7), MB_PK(10, 7), MB_PK(12, 7), MB_PK(16, 7)};
+#undef MB_PK
+  // experiment switches (MB_PILE_VAR, W = 6 with 6 Phred planes only)
+  static const PileKernel kx[2] = {{6, k_pileup_v2<6, 6, 0>}, {6, k_pileup_v2<6, 6, 1>}};
+  if (const char* e = getenv("MB_PILE_VAR")) {
+    const long v = atol(e);
+    if (v > 0 && v < 2 && q_planes == 6 && row_words > 5 && row_words <= 6) return kx[v];
+  }
   const PileKernel* k = q_planes == 6 ? k6 : k7;
   for (int i = 0; i < 9; ++i)
     if (k[i].W >= row_words) return k[i];
@@ -714,7 +762,7 @@ extern "C" int mb_snps_pileup_dev(mb_ctx* ctx, const mb_dev_reads* reads, const 
     ctx->pile_smem = kb * 1024;
   }
   const uint32_t attr_bit = 1u << (W + (reads->q_planes == 7 ? 16u : 0u));
-  if (!(ctx->pile_attr_mask & attr_bit)) {
+  if (!(ctx->pile_attr_mask & attr_bit) || getenv("MB_PILE_VAR")) {
     MB_CUDA_TRY(cudaFuncSetAttribute(kern.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->pile_smem));
     ctx->pile_attr_mask |= attr_bit;
   }
@@ -748,7 +796,7 @@ extern "C" int mb_snps_pileup_dev(mb_ctx* ctx, const mb_dev_reads* reads, const 
   p.vec_off = reads->vec_off;
   p.cplx = reads->cplx;
   p.cigar = reads->cigar;
-  p.planes = reinterpret_cast<const uint4*>(reads->planes);
+  p.planes = reads->planes;
   p.tile_rng = ctx->tile_rng;
   p.tile_species = dl.tile_species;
   p.counts = counts_dev;

@@ -248,7 +248,7 @@ class PackedReads:
     @property
     def nbytes(self) -> int:
         c = self.c
-        return int(16 * c.n_reads + 4 * (c.n_reads + 1) + 4 * c.n_reads + 4 * c.n_cigar_words + 16 * c.n_vec
+        return int(16 * c.n_reads + 4 * (c.n_reads + 1) + 4 * c.n_reads + 4 * c.n_cigar_words + 32 * c.n_vec
                    + 4 * c.n_long)
 
     def _view(self, ptr, n, dt):
@@ -262,7 +262,7 @@ class PackedReads:
     vec_off = property(lambda s: s._view(s.c.vec_off, s.n_reads + 1, np.dtype("<u4")))
     cplx = property(lambda s: s._view(s.c.cplx, s.n_reads, np.dtype("<u4")))
     cigar = property(lambda s: s._view(s.c.cigar, int(s.c.n_cigar_words), np.dtype("<u4")))
-    planes = property(lambda s: s._view(s.c.planes, 4 * s.n_vec, np.dtype("<u4")))
+    planes = property(lambda s: s._view(s.c.planes, 8 * s.n_vec, np.dtype("<u4")))
     long_idx = property(lambda s: s._view(s.c.long_idx, s.n_long, np.dtype("<u4")))
 
 

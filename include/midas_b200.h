@@ -60,6 +60,8 @@ const char* mb_last_error(void);
 #define MB_TILE 4096u
 /* bases per packed block: every per-base bit of 32 consecutive query bases is one 32-bit word */
 #define MB_BLOCK 32u
+/* consecutive reads whose 32-byte units are interleaved in planes[] (one warp, one read per lane) */
+#define MB_GROUP 32u
 
 /* ----------------------------------------------------------------- filters */
 /* args['mapid','aln_cov','readq','mapq','baseq'] of the reference
@@ -140,10 +142,13 @@ typedef struct {
 /* Struct of arrays, identical on host and in HBM (upload is a plain copy).
  * The per-base data of a read is bit-planar: the read is cut into MB_BLOCK-base blocks and every
  * per-base bit of a block is one 32-bit word (bit k = base 32*b + k), so the kernels test and place
- * 32 bases with one logic instruction. Block b of read i is the n_planes words at
- *   planes[8*vec_off[i] + b*n_planes + p]            (the read's region is 32-byte aligned = one
- *                                                     256-bit load per lane and sector,
- *                                                     ceil(l_qseq/32)*n_planes words, zero padded)
+ * 32 bases with one logic instruction. The words of a read, block after block (n_planes words per
+ * block, zero padded to a multiple of 8), are cut into 32-byte units, and the units of MB_GROUP = 32
+ * consecutive reads are interleaved: unit u of read i lies at 32-byte unit vec_off[i] + 32*u of
+ * planes[], i.e. word w of read i is
+ *   planes[8*(vec_off[i] + 32*(w/8)) + w%8],   w = b*n_planes + p  (block b, plane p)
+ * so that the 32 lanes of a warp, one read each, fetch 1 KB of consecutive memory with every
+ * 256-bit load. A group holds max over its reads of ceil(words/8) units per read.
  * snps mode (n_planes = 3 + q_planes):
  *   p = 0, 1  low / high bit of the base code (A=0 C=1 G=2 T=3; anything else 0)
  *   p = 2     "candidate": the base is a literal A/C/G/T, lies in an M/=/X run of the CIGAR and its
@@ -173,7 +178,8 @@ typedef struct {
   uint32_t n_planes;         /* words per block: 3 + q_planes (snps) or q_planes (genes) */
   const uint32_t* long_idx;  /* [n_long] ascending indices of the MB_RF_LONG reads */
   const mb_read_hdr* hdr;    /* [n_reads] */
-  const uint32_t* vec_off;   /* [n_reads+1] first 32-byte unit of each read's region in planes[] */
+  const uint32_t* vec_off;   /* [n_reads+1] first 32-byte unit of each read in planes[] (its further units
+                                follow at a stride of MB_GROUP units); vec_off[n_reads] = n_vec */
   const uint32_t* cplx;      /* [n_reads] */
   const uint32_t* cigar;     /* [n_cigar_words] */
   const uint32_t* planes;    /* [8*n_vec], 32-byte aligned */

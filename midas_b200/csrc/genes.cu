@@ -20,6 +20,12 @@ namespace {
 
 constexpr int GENE_THREADS = 256;
 
+__device__ __forceinline__ void ldg256(const uint32_t* __restrict__ p, uint32_t* r) {
+  asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+      : "l"(p));
+}
+
 struct GeneParams {
   const uint4* hdr;
   const uint32_t* vec_off;
@@ -37,9 +43,9 @@ struct GeneParams {
 
 template <int NQ>
 __global__ void __launch_bounds__(GENE_THREADS) k_genes_v2(const GeneParams p) {
-  // One thread per read: its Phred planes are up to 2 NQ independent 128-bit loads per step (a 150-base
-  // read is 8 of them = one 128-byte line, all in flight at once; L1 turns them into one line fill - 256-bit
-  // loads, which skip L1, measured 8 % slower here).
+  // One thread per read: its Phred planes are up to NQ independent 256-bit loads per step (a 150-base
+  // read is 4 of them, all in flight at once); the units of 32 consecutive reads are interleaved in
+  // memory, so each of a warp's loads reads 1 KB of consecutive bytes.
   const uint64_t stride = (uint64_t)gridDim.x * GENE_THREADS;
   for (uint64_t r = (uint64_t)blockIdx.x * GENE_THREADS + threadIdx.x; r < p.n_reads; r += stride) {
     const uint4 h = __ldg(&p.hdr[r]);
@@ -54,22 +60,23 @@ __global__ void __launch_bounds__(GENE_THREADS) k_genes_v2(const GeneParams p) {
     bool keep = false;
     if (ok) {
       // mean-quality test genes.py:160: mean(q) < readq  <=>  sum(q) < readq * l_qseq (exact)
-      const uint32_t nvec = (((lq + 31u) >> 5) * (uint32_t)NQ + 3u) >> 2;
-      const uint4* __restrict__ q = reinterpret_cast<const uint4*>(p.planes) + (size_t)v0 * 2;
+      const uint32_t nv8 = (((lq + 31u) >> 5) * (uint32_t)NQ + 7u) >> 3;
+      const uint32_t* __restrict__ q = p.planes + (size_t)v0 * 8;
       uint32_t pc[NQ];
 #pragma unroll
       for (int k = 0; k < NQ; ++k) pc[k] = 0;
-      for (uint32_t b = 0; b < nvec; b += 2 * NQ) {       // 2 NQ vectors = 8 blocks: plane of word i is i % NQ
-        uint4 v[2 * NQ];
+      for (uint32_t b = 0; b < nv8; b += NQ) {            // NQ 256-bit loads = 8 blocks: plane of word i is i % NQ
+        uint32_t v[8 * NQ];
 #pragma unroll
-        for (int u = 0; u < 2 * NQ; ++u) v[u] = b + (uint32_t)u < nvec ? __ldg(q + b + u) : make_uint4(0, 0, 0, 0);
+        for (int u = 0; u < NQ; ++u) {
+          if (b + (uint32_t)u < nv8) ldg256(q + (size_t)(b + u) * (8 * MB_GROUP), v + 8 * u);
+          else {
 #pragma unroll
-        for (int u = 0; u < 2 * NQ; ++u) {
-          pc[(4 * u + 0) % NQ] += __popc(v[u].x);
-          pc[(4 * u + 1) % NQ] += __popc(v[u].y);
-          pc[(4 * u + 2) % NQ] += __popc(v[u].z);
-          pc[(4 * u + 3) % NQ] += __popc(v[u].w);
+            for (int c = 0; c < 8; ++c) v[8 * u + c] = 0;
+          }
         }
+#pragma unroll
+        for (int i = 0; i < 8 * NQ; ++i) pc[i % NQ] += __popc(v[i]);
       }
       uint32_t s = 0;
 #pragma unroll

@@ -344,16 +344,22 @@ extern "C" int mb_pack_reads(const mb_plain_reads* in, const mb_layout* L, int m
   std::vector<uint32_t> blk_off(n + 1), cg_off(n + 1);
   uint64_t nb = 0, ncw = 0, tot_bases = 0;
   uint32_t max_span = 0;
+  for (uint64_t j0 = 0; j0 < n; j0 += MB_GROUP) {               // groups of MB_GROUP reads, units interleaved
+    const uint64_t j1 = std::min<uint64_t>(n, j0 + MB_GROUP);
+    uint64_t units = 0;                                         // 32-byte units per read of this group
+    for (uint64_t j = j0; j < j1; ++j) units = std::max<uint64_t>(units, ((uint64_t)geom[src(j)].n_blk * NP + 7) / 8);
+    for (uint64_t j = j0; j < j1; ++j) blk_off[j] = (uint32_t)(nb + (j - j0));
+    nb += units * MB_GROUP;
+    if (nb > 0xFFFFFFF0ull) return mb::fail(MB_EOVERFLOW, "mb_pack_reads: batch too large for 32-bit unit offsets");
+  }
   for (uint64_t j = 0; j < n; ++j) {
     const ReadGeom& g = geom[src(j)];
-    blk_off[j] = (uint32_t)nb;
     cg_off[j] = (uint32_t)ncw;
-    nb += ((uint64_t)g.n_blk * NP + 7) / 8;                     // 32-byte units of the read's region
     ncw += g.n_cplx_words;
     tot_bases += (uint64_t)in->l_qseq[src(j)];
     max_span = std::max<uint32_t>(max_span, g.ref_span);
-    if (nb > 0xFFFFFFF0ull || ncw > 0xFFFFFFF0ull)
-      return mb::fail(MB_EOVERFLOW, "mb_pack_reads: batch too large for 32-bit block offsets");
+    if (ncw > 0xFFFFFFF0ull)
+      return mb::fail(MB_EOVERFLOW, "mb_pack_reads: batch too large for 32-bit run-record offsets");
   }
   blk_off[n] = (uint32_t)nb;
   cg_off[n] = (uint32_t)ncw;
@@ -399,6 +405,7 @@ extern "C" int mb_pack_reads(const mb_plain_reads* in, const mb_layout* L, int m
   uint32_t* planes = (uint32_t*)o->buf[4];
   uint32_t* long_idx = (uint32_t*)o->buf[6];
   memcpy(blk, blk_off.data(), sizeof(uint32_t) * (n + 1));
+  parallel_for(nb, n_threads, [&](uint64_t lo, uint64_t hi, int) { memset(planes + lo * 8, 0, (hi - lo) * 32); });
   if (n_long) {
     uint64_t k = 0;
     for (uint64_t j = 0; j < n; ++j)
@@ -445,8 +452,9 @@ extern "C" int mb_pack_reads(const mb_plain_reads* in, const mb_layout* L, int m
       const uint8_t* s = in->seq + in->seq_off[i];
       const uint8_t* q = in->qual + in->seq_off[i];
       const uint32_t lq = h.l_qseq;
+      // word w of this read: unit w/8 of the read, units of a group interleaved (stride MB_GROUP units)
       uint32_t* reg = planes + (size_t)blk_off[j] * 8;
-      memset(reg, 0, ((size_t)blk_off[j + 1] - blk_off[j]) * 32);
+      auto word = [&](uint32_t w) -> uint32_t& { return reg[(size_t)(w >> 3) * (8 * MB_GROUP) + (w & 7u)]; };
       for (uint32_t b = 0; b < g.n_blk; ++b) {
         uint32_t w[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};        // lo, hi, acgt, Phred bits 0..6
         const uint32_t nk = std::min<uint32_t>(MB_BLOCK, lq - b * MB_BLOCK);
@@ -464,9 +472,8 @@ extern "C" int mb_pack_reads(const mb_plain_reads* in, const mb_layout* L, int m
           w[8] |= (uint32_t)((ph >> 5) & 1) << k;
           w[9] |= (uint32_t)((ph >> 6) & 1) << k;
         }
-        uint32_t* d = reg + (size_t)b * NP;
-        if (mode == 0) { d[0] = w[0]; d[1] = w[1]; d[2] = w[2]; }
-        for (uint32_t k = 0; k < q_planes; ++k) d[P0 + k] = w[3 + k];
+        if (mode == 0) { word(b * NP) = w[0]; word(b * NP + 1) = w[1]; word(b * NP + 2) = w[2]; }
+        for (uint32_t k = 0; k < q_planes; ++k) word(b * NP + P0 + k) = w[3 + k];
       }
       if (mode == 0) {
         // candidate plane: keep only the bases of M/=/X runs whose reference position is inside the contig
@@ -491,7 +498,7 @@ extern "C" int mb_pack_reads(const mb_plain_reads* in, const mb_layout* L, int m
             rr += len;
           }
         }
-        for (uint32_t b = 0; b < g.n_blk; ++b) reg[(size_t)b * NP + 2] &= inrun[b];
+        for (uint32_t b = 0; b < g.n_blk; ++b) word(b * NP + 2) &= inrun[b];
       }
     }
   });

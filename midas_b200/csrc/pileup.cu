@@ -41,20 +41,17 @@
 
 namespace {
 
-constexpr int KT = 2048;                 // positions per kernel tile (divides MB_TILE)
-constexpr int NCOL = KT / 32;            // 32-position columns per tile
+// positions per kernel tile (divides MB_TILE), a kernel template choice: 2048 (256 threads, 2 CTAs per SM)
+// or 1024 (128 threads, 4 CTAs per SM: more independent barrier domains per SM)
 constexpr int KSUB = 4;                  // lanes sharing a column
-constexpr int NT = NCOL * KSUB;          // threads per CTA
-constexpr int NWARP = NT / 32;
 constexpr int NLEV = 8;                  // register vertical-counter levels (per-lane count <= 255 per round)
 constexpr int XLEV = NLEV + 2;           // levels after merging KSUB = 4 lanes
 constexpr int VCL = 16;                  // shared-memory vertical-counter levels (<= 65535 rows per pass)
 constexpr int WMAX = MB_ROW_WORDS_MAX;
 constexpr uint32_t PASS_ROWS = 65528;    // rows folded into the shared counters before they are expanded
 constexpr int LANE_ROWS_MAX = 248;       // rows one lane may take in one round (keeps its count <= 255)
-constexpr int FIRST_N = NCOL + WMAX + 1;
 
-static_assert(MB_TILE % KT == 0, "kernel tile must divide the layout tile");
+static_assert(MB_TILE % 2048 == 0, "kernel tile must divide the layout tile");
 static_assert(KSUB == 4, "the merge butterfly is written for 4 lanes per column");
 
 enum : uint32_t { F_NEEDQ = 1u, F_OVL = 2u, F_OWNER = 4u, F_SIMPLE = 8u };
@@ -131,10 +128,10 @@ __global__ void k_init_stats(unsigned long long* stats, const uint64_t* species_
 // For every kernel tile the contiguous range of reads that can overlap it: a read that fits a W-word
 // row and overlaps [ts, ts+KT) starts after ts - 32 W; the pileup kernel skips the rest by header.
 __global__ void k_tile_ranges(const uint4* __restrict__ hdr, uint32_t n_reads, uint32_t back, uint32_t n_tiles,
-                              uint32_t* __restrict__ rng) {
+                              uint32_t kt, uint32_t* __restrict__ rng) {
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_tiles) return;
-  const uint32_t ts = t * KT, te = ts + KT;
+  const uint32_t ts = t * kt, te = ts + kt;
   const uint32_t lo_key = ts > back ? ts - back : 0u;
   uint32_t lo = 0, hi = n_reads;
   while (lo < hi) {
@@ -167,9 +164,14 @@ __global__ void k_tile_ranges(const uint4* __restrict__ hdr, uint32_t n_reads, u
     }                                                                                       \
   } while (0)
 
-// VAR: experiment switches (bit 0: 128-bit plane loads in steps of four blocks instead of 256-bit loads)
+// VAR: bit 0: 128-bit plane loads in steps of four blocks instead of 256-bit loads (experiment switch);
+//      bit 1: 1024-position tiles, 128 threads, 4 CTAs per SM instead of 2048 / 256 / 2
 template <int WT, int NQ, int VAR>
-__global__ void __launch_bounds__(NT, 2) k_pileup_v2(const PileParams p) {
+__global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : 2) k_pileup_v2(const PileParams p) {
+  constexpr int KT = (VAR & 2) ? 1024 : 2048;
+  constexpr int NCOL = KT / 32;            // 32-position columns per tile
+  constexpr int NT = NCOL * KSUB;          // threads per CTA
+  constexpr int FIRST_N = NCOL + WMAX + 1;
   extern __shared__ __align__(16) uint32_t smem[];
   constexpr uint32_t W = (uint32_t)WT;          // row words (compile time: every per-lane loop below unrolls)
   constexpr int NP = 3 + NQ;                    // words per 32-base block: seq lo, seq hi, candidate, Phred bits
@@ -352,14 +354,15 @@ __global__ void __launch_bounds__(NT, 2) k_pileup_v2(const PileParams p) {
           };
           constexpr bool LD256 = WT <= 8 && !(VAR & 1);
           if (LD256) {
-            // the whole read at once: ceil(9 W / 8) independent 256-bit loads, one full sector per lane each
+            // the whole read at once: ceil(9 W / 8) independent 256-bit loads; the units of the 32 reads of a
+            // group are interleaved, so the lanes of a warp (consecutive reads) read consecutive sectors
             constexpr int NV8 = (WT * NP + 7) / 8;
             const uint32_t nv8 = (((lq + 31u) >> 5) * (uint32_t)NP + 7u) >> 3;
             const uint32_t* __restrict__ vp = p.planes + (size_t)b0 * 8;
             uint32_t raw[8 * NV8];
 #pragma unroll
             for (int u = 0; u < NV8; ++u) {
-              if ((uint32_t)u < nv8) ldg256(vp + 8 * u, raw + 8 * u);
+              if ((uint32_t)u < nv8) ldg256(vp + 8 * MB_GROUP * u, raw + 8 * u);
               else {
 #pragma unroll
                 for (int c = 0; c < 8; ++c) raw[8 * u + c] = 0;
@@ -370,7 +373,7 @@ __global__ void __launch_bounds__(NT, 2) k_pileup_v2(const PileParams p) {
           } else {
             // wide rows: steps of four blocks = NP independent 128-bit loads
             const uint32_t nvec = (((lq + 31u) >> 5) * (uint32_t)NP + 3u) >> 2;
-            const uint4* __restrict__ vp = reinterpret_cast<const uint4*>(p.planes) + (size_t)b0 * 2;
+            const uint32_t* __restrict__ vp = p.planes + (size_t)b0 * 8;
 #pragma unroll
             for (int s4 = 0; s4 < WT; s4 += 4) {
               const int nb = WT - s4 < 4 ? WT - s4 : 4;
@@ -379,7 +382,9 @@ __global__ void __launch_bounds__(NT, 2) k_pileup_v2(const PileParams p) {
 #pragma unroll
               for (int u = 0; u < NP; ++u) {
                 uint4 t = make_uint4(0, 0, 0, 0);
-                if (u < nv && (uint32_t)(s4 / 4 * NP + u) < nvec) t = __ldg(vp + s4 / 4 * NP + u);
+                const int v = s4 / 4 * NP + u;                    // 16-byte half of unit v / 2
+                if (u < nv && (uint32_t)v < nvec)
+                  t = __ldg(reinterpret_cast<const uint4*>(vp + (size_t)(v >> 1) * (8 * MB_GROUP)) + (v & 1));
                 raw[4 * u] = t.x; raw[4 * u + 1] = t.y; raw[4 * u + 2] = t.z; raw[4 * u + 3] = t.w;
               }
 #pragma unroll
@@ -611,6 +616,9 @@ struct LongParams {
   uint32_t NQ, NP;  // Phred planes / words per 32-base block
 };
 
+// word w of a read's planes: 32-byte unit w / 8 of the read, units of a group interleaved (mb_packed_reads)
+__device__ __forceinline__ size_t widx(uint32_t w) { return (size_t)(w >> 3) * (8 * MB_GROUP) + (w & 7u); }
+
 __global__ void __launch_bounds__(256) k_long_reads(const LongParams p) {
   const int lane = threadIdx.x & 31;
   const uint32_t wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
@@ -629,7 +637,7 @@ __global__ void __launch_bounds__(256) k_long_reads(const LongParams p) {
       const uint32_t nw = ((lq + 31u) >> 5) * p.NQ;
       for (uint32_t i = lane; i < nw; i += 32) {
         const uint32_t b = i / p.NQ, k = i - b * p.NQ;
-        s += (uint32_t)__popc(__ldg(q + b * p.NP + 3 + k)) << k;
+        s += (uint32_t)__popc(__ldg(q + widx(b * p.NP + 3 + k))) << k;
       }
       s = warp_sum(s);
       keep = (long long)s >= (long long)p.readq * (long long)lq;
@@ -655,11 +663,11 @@ __global__ void __launch_bounds__(256) k_long_reads(const LongParams p) {
       const uint32_t q0 = w0 & 0xffffu, len = w0 >> 16;
       for (uint32_t i = lane; i < len; i += 32) {
         const uint32_t qi = q0 + i, bb = qi & 31u;
-        const uint32_t* __restrict__ blk = q + (qi >> 5) * p.NP;
+        const uint32_t blk = (qi >> 5) * p.NP;                     // first word of the base's block
         uint32_t ph = 0;
-        for (uint32_t b = 0; b < p.NQ; ++b) ph |= ((__ldg(blk + 3 + b) >> bb) & 1u) << b;
-        if (((__ldg(blk + 2) >> bb) & 1u) && ph >= p.baseq) {     // candidate base with Phred >= baseq
-          const uint32_t cd = ((__ldg(blk) >> bb) & 1u) | (((__ldg(blk + 1) >> bb) & 1u) << 1);
+        for (uint32_t b = 0; b < p.NQ; ++b) ph |= ((__ldg(q + widx(blk + 3 + b)) >> bb) & 1u) << b;
+        if (((__ldg(q + widx(blk + 2)) >> bb) & 1u) && ph >= p.baseq) {     // candidate base with Phred >= baseq
+          const uint32_t cd = ((__ldg(q + widx(blk)) >> bb) & 1u) | (((__ldg(q + widx(blk + 1)) >> bb) & 1u) << 1);
           atomicAdd(p.counts + (size_t)cd * p.gpad + loc + x0 + i, 1u);
         }
       }
@@ -704,19 +712,20 @@ __global__ void __launch_bounds__(256) k_restat(const uint32_t* __restrict__ cou
 
 // the row widths (and Phred plane counts) the tile kernel is instantiated for; a batch runs at the smallest
 // width >= its row_words
-struct PileKernel { uint32_t W; void (*fn)(const PileParams); };
+struct PileKernel { uint32_t W; void (*fn)(const PileParams); uint32_t kt; };   // kt: positions per tile
 PileKernel pick_kernel(uint32_t row_words, uint32_t q_planes) {
-#define MB_PK(W, Q) {W, k_pileup_v2<W, Q, 0>}
+#define MB_PK(W, Q) {W, k_pileup_v2<W, Q, 0>, 2048}
   static const PileKernel k6[] = {MB_PK(3, 6), MB_PK(4, 6), MB_PK(5, 6),  MB_PK(6, 6),  MB_PK(7, 6),
                                   MB_PK(8, 6), MB_PK(10, 6), MB_PK(12, 6), MB_PK(16, 6)};
   static const PileKernel k7[] = {MB_PK(3, 7), MB_PK(4, 7), MB_PK(5, 7),  MB_PK(6, 7),  MB_PK(7, 7),
                                   MB_PK(8, 7), MB_PK(10, 7), MB_PK(12, 7), MB_PK(16, 7)};
 #undef MB_PK
   // experiment switches (MB_PILE_VAR, W = 6 with 6 Phred planes only)
-  static const PileKernel kx[2] = {{6, k_pileup_v2<6, 6, 0>}, {6, k_pileup_v2<6, 6, 1>}};
+  static const PileKernel kx[4] = {{6, k_pileup_v2<6, 6, 0>, 2048}, {6, k_pileup_v2<6, 6, 1>, 2048},
+                                   {6, k_pileup_v2<6, 6, 2>, 1024}, {6, k_pileup_v2<6, 6, 3>, 1024}};
   if (const char* e = getenv("MB_PILE_VAR")) {
     const long v = atol(e);
-    if (v > 0 && v < 2 && q_planes == 6 && row_words > 5 && row_words <= 6) return kx[v];
+    if (v > 0 && v < 4 && q_planes == 6 && row_words > 5 && row_words <= 6) return kx[v];
   }
   const PileKernel* k = q_planes == 6 ? k6 : k7;
   for (int i = 0; i < 9; ++i)
@@ -724,8 +733,8 @@ PileKernel pick_kernel(uint32_t row_words, uint32_t q_planes) {
   return k[8];
 }
 
-size_t pile_smem_bytes(uint32_t W, uint32_t rmax) {
-  return sizeof(uint4) * ((size_t)VCL * NCOL + (size_t)rmax * W);
+size_t pile_smem_bytes(uint32_t W, uint32_t rmax, uint32_t ncol) {
+  return sizeof(uint4) * ((size_t)VCL * ncol + (size_t)rmax * W);
 }
 
 }  // namespace
@@ -742,6 +751,12 @@ extern "C" int mb_snps_pileup_dev(mb_ctx* ctx, const mb_dev_reads* reads, const 
   mb_dev_layout dl;
   int rc = mb::get_dev_layout(ctx, L, &dl);
   if (rc) return rc;
+  // shared memory per CTA: two CTAs per SM (override with MB_PILE_SMEM_KB for experiments)
+  if (reads->n_planes != 3 + reads->q_planes || (reads->q_planes != 6 && reads->q_planes != 7))
+    return mb::fail(MB_EINVAL, "mb_snps_pileup_dev: reads were not packed in snps mode");
+  const PileKernel kern = pick_kernel(reads->row_words, reads->q_planes);
+  const uint32_t W = kern.W;                                          // instantiated row width >= row_words
+  const uint32_t KT = kern.kt, NCOL = KT / 32, NT = NCOL * KSUB;
   const uint32_t n_ktiles = L->n_tiles * (MB_TILE / KT);
   if (ctx->tile_rng_cap < (size_t)2 * n_ktiles + 2) {
     if (ctx->tile_rng) { MB_CUDA_TRY(cudaStreamSynchronize(ctx->stream)); MB_CUDA_TRY(cudaFree(ctx->tile_rng)); }
@@ -751,14 +766,9 @@ extern "C" int mb_snps_pileup_dev(mb_ctx* ctx, const mb_dev_reads* reads, const 
     MB_CUDA_TRY(cudaMalloc(&ctx->tile_rng, sizeof(uint32_t) * ((size_t)2 * n_ktiles + 2)));
     ctx->tile_rng_cap = (size_t)2 * n_ktiles + 2;
   }
-  // shared memory per CTA: two CTAs per SM (override with MB_PILE_SMEM_KB for experiments)
-  if (reads->n_planes != 3 + reads->q_planes || (reads->q_planes != 6 && reads->q_planes != 7))
-    return mb::fail(MB_EINVAL, "mb_snps_pileup_dev: reads were not packed in snps mode");
-  const PileKernel kern = pick_kernel(reads->row_words, reads->q_planes);
-  const uint32_t W = kern.W;                                          // instantiated row width >= row_words
-  if (!ctx->pile_smem) {
-    size_t kb = 100;
-    if (const char* e = getenv("MB_PILE_SMEM_KB")) { long v = atol(e); if (v >= 32 && v <= 220) kb = (size_t)v; }
+  {
+    size_t kb = KT == 2048 ? 100 : 50;                               // 2 / 4 CTAs per SM
+    if (const char* e = getenv("MB_PILE_SMEM_KB")) { long v = atol(e); if (v >= 24 && v <= 220) kb = (size_t)v; }
     ctx->pile_smem = kb * 1024;
   }
   const uint32_t attr_bit = 1u << (W + (reads->q_planes == 7 ? 16u : 0u));
@@ -785,7 +795,7 @@ extern "C" int mb_snps_pileup_dev(mb_ctx* ctx, const mb_dev_reads* reads, const 
   // the tile -> read-range index depends only on the resident batch: built once per (batch, row width)
   if (ctx->rng_for != reads || ctx->rng_W != W || ctx->rng_ntiles != n_ktiles) {
     k_tile_ranges<<<(n_ktiles + 255) / 256, 256, 0, st>>>(reinterpret_cast<const uint4*>(reads->hdr),
-                                                          (uint32_t)reads->n_reads, 32u * W, n_ktiles, ctx->tile_rng);
+                                                          (uint32_t)reads->n_reads, 32u * W, n_ktiles, KT, ctx->tile_rng);
     ctx->launches++;
     ctx->rng_for = reads;
     ctx->rng_W = W;
@@ -815,7 +825,7 @@ extern "C" int mb_snps_pileup_dev(mb_ctx* ctx, const mb_dev_reads* reads, const 
   p.defer_restat = reads->n_long ? 1u : 0u;
   const uint32_t grid = min(n_ktiles, (uint32_t)(ctx->sm_count * ctx->pile_occ));
   { int trc = mb::timing_begin(ctx); if (trc) return trc; }
-  kern.fn<<<grid, NT, pile_smem_bytes(W, rmax), st>>>(p);
+  kern.fn<<<grid, NT, pile_smem_bytes(W, rmax, NCOL), st>>>(p);
   { int trc = mb::timing_end(ctx); if (trc) return trc; }
   ctx->launches++;
   if (reads->n_long) {

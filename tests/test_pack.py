@@ -69,8 +69,9 @@ def _decode(pk, i):
     hdr, off, planes = pk.hdr, pk.vec_off, pk.planes
     lq, NP, NQ = int(hdr[i]["l_qseq"]), pk.n_planes, pk.q_planes
     p0 = NP - NQ
-    reg = planes[8 * int(off[i]):8 * int(off[i + 1])]
-    assert len(reg) >= -(-lq // 32) * NP
+    nw = -(-lq // 32) * NP
+    # word w of a read = unit w // 8 of the read; the units of 32 consecutive reads are interleaved
+    reg = np.array([planes[8 * (int(off[i]) + 32 * (w // 8)) + w % 8] for w in range(-(-nw // 8) * 8)])
     code, cand, ph = [], [], []
     for q in range(lq):
         w = reg[(q // 32) * NP:(q // 32 + 1) * NP]
@@ -134,7 +135,7 @@ def test_seven_phred_planes_only_when_needed_and_genes_mode_holds_phred_planes_o
     assert (pk.q_planes, pk.n_planes) == (7, 10)
     assert _decode(pk, 0)[2] == [64] + [3] * 39
     pk = lib.PackedReads(_one([(OP_M, 40)], qual=list(range(40))), lay(), "genes")
-    assert (pk.q_planes, pk.n_planes) == (6, 6) and pk.n_vec == 2    # 2 blocks x 6 words = 12 words = 2 x 32 B
+    assert (pk.q_planes, pk.n_planes) == (6, 6) and pk.n_vec == 64   # 2 blocks x 6 words = 2 units, group of 32
     assert _decode(pk, 0)[2] == list(range(40))
 
 

@@ -5,7 +5,7 @@
 // :49-76, compute_per_sample_mafs :78-91, compute_prevalence :93-104 (called per site from
 // build_sharded_tables :324-360). Input is the stack of per-sample count planes exactly as
 // mb_snps_pileup writes them: counts[s][plane][site]. Pure streaming, HBM-bound:
-// 16 B x n_samples read per site, 12 B x n_samples + 24 B written.
+// 16 B x n_samples read per site, 12 B x n_samples + 25 B written.
 #include "common.h"
 
 namespace {
@@ -24,14 +24,31 @@ struct MergeParams {
   uint32_t* count_samples;       // [G]
   uint32_t* sample_depth;        // [S][G]
   double* sample_maf;            // [S][G]
+  const unsigned long long* sd_max;   // [S] smallest per-sample depth that fails the site_ratio test (k_merge_thresholds)
 };
 
-// One thread per site. STAGED = true: the site's n_samples x 4 counts are read from HBM once and kept
-// in a thread-private column of shared memory for the second (per-sample) pass; otherwise the second
-// pass re-reads them from HBM (any n_samples).
-template <bool STAGED>
+// Per sample, the largest per-sample depth sd that still passes the ratio test of compute_prevalence
+// (snps.py:99-100: fail if sd / mean_depth > site_ratio). The quotient is a correctly rounded double
+// division, monotone in sd, so the threshold is found once per call with the same division and the site
+// kernel compares integers: exact, one division per sample instead of one per sample and site.
+__global__ void k_merge_thresholds(const double* __restrict__ mean_depth, uint32_t n_samples, double site_ratio,
+                                   unsigned long long* __restrict__ sd_max) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_samples) return;
+  const double md = mean_depth[t];
+  unsigned long long lo = 0, hi = 0x100000000ull;          // first sd in [0, 2^32] that fails
+  while (lo < hi) {
+    const unsigned long long mid = lo + ((hi - lo) >> 1);
+    if (__ddiv_rn((double)mid, md) > site_ratio) hi = mid; else lo = mid + 1;
+  }
+  sd_max[t] = lo;                                           // sd passes iff sd < sd_max[t]
+}
+
+// One thread per site, two passes over the site's n_samples x 4 counts: pooled counts and the allele
+// call, then per-sample depth / MAF / prevalence from the major and minor planes (re-read: they are the
+// lines this thread touched a moment ago). The second pass is unrolled four samples deep so that eight
+// loads are in flight per thread, and divides only where a sample has minor-allele reads.
 __global__ void __launch_bounds__(MERGE_THREADS) k_merge_sites(const MergeParams p) {
-  extern __shared__ uint32_t s_cnt[];          // [n_samples][4][MERGE_THREADS]
   const uint64_t G = p.n_sites;
   const uint32_t S = p.n_samples;
   for (uint64_t g = (uint64_t)blockIdx.x * MERGE_THREADS + threadIdx.x; g < G; g += (uint64_t)gridDim.x * MERGE_THREADS) {
@@ -43,74 +60,76 @@ __global__ void __launch_bounds__(MERGE_THREADS) k_merge_sites(const MergeParams
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const uint32_t* c = p.counts + (size_t)(s + u) * 4 * G + g;
-        v[u][0] = c[0]; v[u][1] = c[G]; v[u][2] = c[2 * G]; v[u][3] = c[3 * G];
+        v[u][0] = __ldg(c); v[u][1] = __ldg(c + G); v[u][2] = __ldg(c + 2 * G); v[u][3] = __ldg(c + 3 * G);
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u)
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          pc[k] += v[u][k];
-          if (STAGED) s_cnt[((s + u) * 4 + k) * MERGE_THREADS + threadIdx.x] = v[u][k];
-        }
+        for (int k = 0; k < 4; ++k) pc[k] += v[u][k];
     }
     for (; s < S; ++s) {
       const uint32_t* c = p.counts + (size_t)s * 4 * G + g;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const uint32_t x = c[(size_t)k * G];
-        pc[k] += x;
-        if (STAGED) s_cnt[(s * 4 + k) * MERGE_THREADS + threadIdx.x] = x;
-      }
+      for (int k = 0; k < 4; ++k) pc[k] += __ldg(c + (size_t)k * G);
     }
     const unsigned long long depth = pc[0] + pc[1] + pc[2] + pc[3];
 #pragma unroll
     for (int k = 0; k < 4; ++k) p.pooled[(size_t)k * G + g] = (uint32_t)(pc[k] > 0xffffffffull ? 0xffffffffull : pc[k]);
-    // call_alleles (snps.py:49-76): stable sort by frequency, descending (ties keep A<C<G<T)
-    int ord[4] = {0, 1, 2, 3};
+    // call_alleles (snps.py:49-76): stable sort by frequency, descending (ties keep A<C<G<T): a sorting
+    // network on keys count << 2 | (3 - allele), all in registers
+    unsigned long long key[4];
 #pragma unroll
-    for (int a = 1; a < 4; ++a)
-#pragma unroll
-      for (int b = a; b > 0; --b)
-        if (pc[ord[b]] > pc[ord[b - 1]]) { const int t = ord[b]; ord[b] = ord[b - 1]; ord[b - 1] = t; }
+    for (int k = 0; k < 4; ++k) key[k] = (pc[k] << 2) | (unsigned long long)(3 - k);
+#define MB_CSWAP(a, b) { const unsigned long long hi_ = key[a] > key[b] ? key[a] : key[b], lo_ = key[a] > key[b] ? key[b] : key[a]; key[a] = hi_; key[b] = lo_; }
+    MB_CSWAP(0, 1) MB_CSWAP(2, 3) MB_CSWAP(0, 2) MB_CSWAP(1, 3) MB_CSWAP(1, 2)
+#undef MB_CSWAP
     uint32_t call = 0;
     bool has_major = false, has_minor = false;
-    int major = 0, minor = 0;
+    uint32_t major = 0, minor = 0;
     if (depth > 0) {
       const double dd = (double)depth;
       double fr[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) fr[k] = __ddiv_rn((double)pc[ord[k]], dd);
-      if (fr[0] > 0) { has_major = true; major = ord[0]; }
-      if (fr[1] > 0) { has_minor = true; minor = ord[1]; }
+      for (int k = 0; k < 4; ++k) fr[k] = __ddiv_rn((double)(key[k] >> 2), dd);
+      if (fr[0] > 0) { has_major = true; major = 3u - (uint32_t)(key[0] & 3ull); }
+      if (fr[1] > 0) { has_minor = true; minor = 3u - (uint32_t)(key[1] & 3ull); }
       uint32_t snp = 0;                      // 0 none, 1 mono, 2 bi, 3 tri, 4 quad
       if (fr[3] >= p.snp_freq) snp = 4;
       else if (fr[2] >= p.snp_freq) snp = 3;
       else if (fr[1] >= p.snp_freq) snp = 2;
       else if (fr[0] >= p.snp_freq) snp = 1;
-      call = (uint32_t)major | ((uint32_t)minor << 2) | (snp << 4) | (has_minor ? MB_CALL_HAS_MINOR : 0u);
+      call = major | (minor << 2) | (snp << 4) | (has_minor ? MB_CALL_HAS_MINOR : 0u);
     }
     p.call[g] = (uint8_t)call;
     // compute_per_sample_mafs (snps.py:78-91) + compute_prevalence (snps.py:93-104)
     uint32_t pass = 0;
-    for (uint32_t t = 0; t < S; ++t) {
+    const uint32_t* cmaj = p.counts + (size_t)major * G + g;
+    const uint32_t* cmin = p.counts + (size_t)minor * G + g;
+    auto finish = [&](const uint32_t t, const uint32_t cm, const uint32_t cn) {
       uint32_t sd = 0;
       double maf = 0.0;
       if (has_major) {
-        const uint32_t cm = STAGED ? s_cnt[(t * 4 + major) * MERGE_THREADS + threadIdx.x]
-                                   : p.counts[(size_t)t * 4 * G + (size_t)major * G + g];
-        if (!has_minor) sd = cm;
-        else {
-          const uint32_t cn = STAGED ? s_cnt[(t * 4 + minor) * MERGE_THREADS + threadIdx.x]
-                                     : p.counts[(size_t)t * 4 * G + (size_t)minor * G + g];
-          sd = cm + cn;
-          maf = sd > 0 ? __ddiv_rn((double)cn, (double)sd) : 0.0;
-        }
+        sd = has_minor ? cm + cn : cm;
+        if (has_minor && cn > 0) maf = __ddiv_rn((double)cn, (double)sd);   // cn == 0: 0/sd = 0.0 exactly
       }
       p.sample_depth[(size_t)t * G + g] = sd;
       p.sample_maf[(size_t)t * G + g] = maf;
-      const bool fail = ((int64_t)sd < (int64_t)p.site_depth) || (__ddiv_rn((double)sd, p.mean_depth[t]) > p.site_ratio);
+      const bool fail = ((int64_t)sd < (int64_t)p.site_depth) || ((unsigned long long)sd >= __ldg(p.sd_max + t));
       pass += fail ? 0u : 1u;
+    };
+    uint32_t t = 0;
+    for (; t + 4 <= S; t += 4) {
+      uint32_t cm[4], cn[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        cm[u] = has_major ? __ldg(cmaj + (size_t)(t + u) * 4 * G) : 0u;
+        cn[u] = has_minor ? __ldg(cmin + (size_t)(t + u) * 4 * G) : 0u;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) finish(t + u, cm[u], cn[u]);
     }
+    for (; t < S; ++t)
+      finish(t, has_major ? __ldg(cmaj + (size_t)t * 4 * G) : 0u, has_minor ? __ldg(cmin + (size_t)t * 4 * G) : 0u);
     p.count_samples[g] = pass;
   }
 }
@@ -140,22 +159,18 @@ extern "C" int mb_merge_sites_dev(mb_ctx* ctx, const uint32_t* counts_dev, uint3
   p.count_samples = count_samples_dev;
   p.sample_depth = sample_depth_dev;
   p.sample_maf = sample_maf_dev;
+  void* thr = nullptr;
+  { int rc = mb::ctx_reserve(ctx, 14, sizeof(unsigned long long) * (size_t)n_samples, &thr); if (rc) return rc; }
+  p.sd_max = (const unsigned long long*)thr;
+  k_merge_thresholds<<<(n_samples + 127) / 128, 128, 0, ctx->stream>>>(mean_depth_dev, n_samples, mp->site_ratio,
+                                                                       (unsigned long long*)thr);
+  ctx->launches++;
   const uint64_t want = (n_sites + MERGE_THREADS - 1) / MERGE_THREADS;
-  const size_t smem = sizeof(uint32_t) * 4 * (size_t)n_samples * MERGE_THREADS;
-  // staging the counts in shared memory halves the HBM reads but leaves 4-8 warps per SM: measured 1.3-3x
-  // slower than re-reading (profiles/r01_merge_bench.json); kept for small sample counts only
-  const bool staged = smem <= 16 * 1024;
   int occ = 1;
-  if (staged) {
-    MB_CUDA_TRY(cudaFuncSetAttribute(k_merge_sites<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    MB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_merge_sites<true>, MERGE_THREADS, smem));
-  } else {
-    MB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_merge_sites<false>, MERGE_THREADS, 0));
-  }
+  MB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_merge_sites, MERGE_THREADS, 0));
   const uint32_t grid = (uint32_t)std::min<uint64_t>(want, (uint64_t)ctx->sm_count * (occ > 0 ? occ : 1));
   { int trc = mb::timing_begin(ctx); if (trc) return trc; }
-  if (staged) k_merge_sites<true><<<grid, MERGE_THREADS, smem, ctx->stream>>>(p);
-  else k_merge_sites<false><<<grid, MERGE_THREADS, 0, ctx->stream>>>(p);
+  k_merge_sites<<<grid, MERGE_THREADS, 0, ctx->stream>>>(p);
   { int trc = mb::timing_end(ctx); if (trc) return trc; }
   ctx->launches++;
   MB_CUDA_TRY(cudaGetLastError());

@@ -90,3 +90,87 @@ def write_genes_fixture(root, ref, reads, marker, seed=7):
             fh.write(sp + "\n")
     bam.write_bam(os.path.join(out, "genes", "temp", "pangenomes.bam"), ref.contig_names, ref.contig_len, reads)
     return db, out
+
+
+def write_merge_fixture(root, seed=20260105, n_samples=6):
+    """A database and run_midas.py sample directories for `merge_midas.py snps` (reference
+    midas/merge/merge.py:59-104, midas/merge/snps.py:225-259, midas/utility.py:244-294):
+      <db>/{species_info.txt,genome_info.txt}, <db>/rep_genomes/<sp>/{genome.fna.gz,genome.features}
+      <samples>/<id>/snps/{summary.txt,output/<sp>.snps.gz}
+    Two species; genes on both strands, overlapping and nested genes, a gene whose length is not a
+    multiple of three, a gene over an N, a non-coding gene; one sample below the depth cut for one
+    species, one sample directory without snps output. Returns (db, [sample dirs])."""
+    rng = np.random.default_rng(seed)
+    db, sroot = os.path.join(root, "db"), os.path.join(root, "samples")
+    genomes = {"Sp_alpha_1": [("alpha.c1", 1500), ("alpha.c2", 900)], "Sp_beta_2": [("beta.c1", 1200)]}
+    features = {
+        "Sp_alpha_1": [("a1", "alpha.c1", 31, 330, "+", "CDS"), ("a2", "alpha.c1", 301, 600, "-", "CDS"),
+                       ("a3", "alpha.c1", 350, 409, "+", "CDS"), ("a4", "alpha.c1", 700, 800, "+", "CDS"),
+                       ("a5", "alpha.c1", 900, 1019, "-", "CDS"), ("a6", "alpha.c1", 1100, 1180, "+", "tRNA"),
+                       ("a7", "alpha.c2", 10, 309, "+", "CDS"), ("a8", "alpha.c2", 600, 899, "-", "CDS")],
+        "Sp_beta_2": [("b1", "beta.c1", 100, 399, "-", "CDS"), ("b2", "beta.c1", 500, 799, "+", "CDS")],
+    }
+    os.makedirs(db, exist_ok=True)
+    with open(os.path.join(db, "species_info.txt"), "w") as fh:
+        fh.write("species_id\trep_genome\tcount_genomes\n")
+        for k, sp in enumerate(genomes):
+            fh.write(f"{sp}\tG{k}\t1\n")
+    with open(os.path.join(db, "genome_info.txt"), "w") as fh:
+        fh.write("genome_id\tgenome_name\tlength\tcontigs\n")
+        for k, (sp, ctgs) in enumerate(genomes.items()):
+            fh.write(f"G{k}\t{sp} strain\t{sum(l for _, l in ctgs)}\t{len(ctgs)}\n")
+    seqs = {}
+    for sp, ctgs in genomes.items():
+        d = os.path.join(db, "rep_genomes", sp)
+        os.makedirs(d, exist_ok=True)
+        with gzip.open(os.path.join(d, "genome.fna.gz"), "wt") as fh:
+            for cid, ln in ctgs:
+                s = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, ln)].tobytes().decode()
+                if cid == "alpha.c1":
+                    s = s[:949] + "N" + s[950:]                  # gene a5 runs over an N
+                seqs[cid] = s
+                fh.write(f">{cid} synthetic\n{_wrap(s.lower() if cid == 'beta.c1' else s)}\n")
+        with open(os.path.join(d, "genome.features"), "w") as fh:
+            fh.write("gene_id\tscaffold_id\tstart\tend\tstrand\tgene_type\tfunctions\n")
+            for g in features[sp]:
+                fh.write("\t".join(str(x) for x in g) + "\t\n")
+    dirs = []
+    for s in range(n_samples):
+        sdir = os.path.join(sroot, f"sample_{s:02d}")
+        dirs.append(sdir)
+        if s == n_samples - 1:                                   # a directory without snps output is skipped
+            os.makedirs(os.path.join(sdir, "genes"), exist_ok=True)
+            continue
+        os.makedirs(os.path.join(sdir, "snps", "output"), exist_ok=True)
+        rows = []
+        for sp, ctgs in genomes.items():
+            mean = float(rng.uniform(8, 30)) if not (sp == "Sp_beta_2" and s == 1) else 1.5
+            tot, cov, glen = 0, 0, 0
+            with gzip.open(os.path.join(sdir, "snps", "output", sp + ".snps.gz"), "wt") as fh:
+                fh.write("ref_id\tref_pos\tref_allele\tdepth\tcount_a\tcount_c\tcount_g\tcount_t\n")
+                for cid, ln in sorted(ctgs):
+                    ref = seqs[cid]
+                    # site-specific minor alleles shared by the samples (seeded per contig), plus noise
+                    srng = np.random.default_rng(sum(map(ord, cid)))
+                    is_snp = srng.random(ln) < 0.08
+                    minor = srng.integers(0, 4, ln)
+                    hot = srng.random(ln) < 0.01                 # abnormally deep sites (site_ratio filter)
+                    d = rng.poisson(mean, ln)
+                    d[rng.random(ln) < 0.05] = 0
+                    d = np.where(hot, d * 4, d)
+                    for i in range(ln):
+                        c = [0, 0, 0, 0]
+                        r = "ACGT".find(ref[i])
+                        maj = r if r >= 0 else int(minor[i])
+                        nmin = int(rng.binomial(d[i], 0.3)) if is_snp[i] else int(rng.binomial(d[i], 0.003))
+                        c[maj] += int(d[i]) - nmin
+                        c[int(minor[i])] += nmin
+                        dep = sum(c)
+                        fh.write(f"{cid}\t{i + 1}\t{ref[i]}\t{dep}\t{c[0]}\t{c[1]}\t{c[2]}\t{c[3]}\n")
+                        tot += dep; cov += dep > 0; glen += 1
+            rows.append((sp, glen, cov, cov / float(glen), tot / float(cov) if cov else 0.0, 1000 + s, 900 + s))
+        with open(os.path.join(sdir, "snps", "summary.txt"), "w") as fh:
+            fh.write("species_id\tgenome_length\tcovered_bases\tfraction_covered\tmean_coverage\taligned_reads\tmapped_reads\n")
+            for r in rows:
+                fh.write("\t".join(str(x) for x in r) + "\n")
+    return db, dirs

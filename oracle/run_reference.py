@@ -63,3 +63,24 @@ def run_genes(outdir, db, filters):
     genes = genes_mod.initialize_genes(args, species)
     genes_mod.pangenome_coverage(args, species, genes)
     return species, genes
+
+
+def merge_args(outdir, db, indirs, **over):
+    """args dict of scripts/merge_midas.py snps with the reference's defaults (:150-262)."""
+    args = {"outdir": outdir, "db": db, "indirs": list(indirs), "threads": 1, "species_id": None, "min_samples": 1,
+            "max_species": None, "sample_depth": 5.0, "fract_cov": 0.4, "max_samples": None, "all_samples": False,
+            "snp_type": ["bi"], "allele_freq": 0.01, "site_depth": 1, "site_ratio": 2.0, "site_prev": 0.95,
+            "max_sites": float("Inf")}
+    args.update(over)
+    return args
+
+
+def run_merge_snps(args):
+    """The reference's unmodified `merge_midas.py snps` pipeline (midas/merge/snps.py run_pipeline :469-508:
+    select_species, the temporary count matrices, the forked site shards, GenomicSite per site, annotation,
+    the three tables, snps_summary.txt). No pysam involved: only Bio.SeqIO comes from the shim."""
+    import contextlib
+    snps = _import("midas.merge.snps")
+    os.makedirs(args["outdir"], exist_ok=True)
+    with contextlib.redirect_stdout(io.StringIO()):
+        snps.run_pipeline(dict(args))

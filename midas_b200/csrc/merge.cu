@@ -6,6 +6,8 @@
 // build_sharded_tables :324-360). Input is the stack of per-sample count planes exactly as
 // mb_snps_pileup writes them: counts[s][plane][site]. Pure streaming, HBM-bound:
 // 16 B x n_samples read per site, 12 B x n_samples + 25 B written.
+#include <cstdlib>
+
 #include "common.h"
 
 namespace {
@@ -45,16 +47,44 @@ __global__ void k_merge_thresholds(const double* __restrict__ mean_depth, uint32
 }
 
 // One thread per site, two passes over the site's n_samples x 4 counts: pooled counts and the allele
-// call, then per-sample depth / MAF / prevalence from the major and minor planes (re-read: they are the
-// lines this thread touched a moment ago). The second pass is unrolled four samples deep so that eight
-// loads are in flight per thread, and divides only where a sample has minor-allele reads.
+// call, then per-sample depth / MAF / prevalence from the major and minor planes. The counts of the first
+// KS samples stay in registers between the passes, packed four 8-bit counts to a word (a site where any of
+// them exceeds 255 falls back to re-reading, like the samples past KS): the second pass then costs no HBM
+// traffic for them. Both passes are unrolled four samples deep (sixteen / eight loads in flight per thread)
+// and the MAF division is taken only where a sample has minor-allele reads.
+template <int KS>
 __global__ void __launch_bounds__(MERGE_THREADS) k_merge_sites(const MergeParams p) {
   const uint64_t G = p.n_sites;
   const uint32_t S = p.n_samples;
   for (uint64_t g = (uint64_t)blockIdx.x * MERGE_THREADS + threadIdx.x; g < G; g += (uint64_t)gridDim.x * MERGE_THREADS) {
     // pooled counts (snps.py:42-47)
     unsigned long long pc[4] = {0, 0, 0, 0};
-    uint32_t s = 0;
+    uint32_t kept[KS];
+    uint32_t wide = 0;                                   // or of the kept counts: > 255 means they do not fit
+#pragma unroll
+    for (int s0 = 0; s0 < KS; s0 += 4) {
+      if ((uint32_t)s0 < S) {
+        uint32_t v[4][4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const uint32_t* c = p.counts + (size_t)(s0 + u) * 4 * G + g;
+          const bool in = (uint32_t)(s0 + u) < S;
+          v[u][0] = in ? __ldg(c) : 0u; v[u][1] = in ? __ldg(c + G) : 0u;
+          v[u][2] = in ? __ldg(c + 2 * G) : 0u; v[u][3] = in ? __ldg(c + 3 * G) : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) pc[k] += v[u][k];
+          wide |= v[u][0] | v[u][1] | v[u][2] | v[u][3];
+          kept[s0 + u] = v[u][0] | (v[u][1] << 8) | (v[u][2] << 16) | (v[u][3] << 24);
+        }
+      } else {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) kept[s0 + u] = 0;
+      }
+    }
+    uint32_t s = KS;
     for (; s + 4 <= S; s += 4) {
       uint32_t v[4][4];
 #pragma unroll
@@ -72,6 +102,7 @@ __global__ void __launch_bounds__(MERGE_THREADS) k_merge_sites(const MergeParams
 #pragma unroll
       for (int k = 0; k < 4; ++k) pc[k] += __ldg(c + (size_t)k * G);
     }
+    const bool packed = wide < 256u;
     const unsigned long long depth = pc[0] + pc[1] + pc[2] + pc[3];
 #pragma unroll
     for (int k = 0; k < 4; ++k) p.pooled[(size_t)k * G + g] = (uint32_t)(pc[k] > 0xffffffffull ? 0xffffffffull : pc[k]);
@@ -117,7 +148,28 @@ __global__ void __launch_bounds__(MERGE_THREADS) k_merge_sites(const MergeParams
       const bool fail = ((int64_t)sd < (int64_t)p.site_depth) || ((unsigned long long)sd >= __ldg(p.sd_max + t));
       pass += fail ? 0u : 1u;
     };
-    uint32_t t = 0;
+    const uint32_t shm = 8u * major, shn = 8u * minor;
+#pragma unroll
+    for (int t0 = 0; t0 < KS; t0 += 4) {
+      if ((uint32_t)t0 < S) {
+        uint32_t cm[4], cn[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (packed) {
+            cm[u] = has_major ? (kept[t0 + u] >> shm) & 255u : 0u;
+            cn[u] = has_minor ? (kept[t0 + u] >> shn) & 255u : 0u;
+          } else {
+            const bool in = (uint32_t)(t0 + u) < S;
+            cm[u] = has_major && in ? __ldg(cmaj + (size_t)(t0 + u) * 4 * G) : 0u;
+            cn[u] = has_minor && in ? __ldg(cmin + (size_t)(t0 + u) * 4 * G) : 0u;
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if ((uint32_t)(t0 + u) < S) finish(t0 + u, cm[u], cn[u]);
+      }
+    }
+    uint32_t t = KS;
     for (; t + 4 <= S; t += 4) {
       uint32_t cm[4], cn[4];
 #pragma unroll
@@ -166,11 +218,16 @@ extern "C" int mb_merge_sites_dev(mb_ctx* ctx, const uint32_t* counts_dev, uint3
                                                                        (unsigned long long*)thr);
   ctx->launches++;
   const uint64_t want = (n_sites + MERGE_THREADS - 1) / MERGE_THREADS;
+  // 32 samples stay in registers between the passes (80 registers; 64 samples = 128 registers measured slower
+  // at every sample count). MB_MERGE_KS=4 selects the re-reading variant for comparison.
+  int ks = 32;
+  if (const char* e = getenv("MB_MERGE_KS")) { if (atoi(e) == 4) ks = 4; }
+  void (*fn)(const MergeParams) = ks == 4 ? k_merge_sites<4> : k_merge_sites<32>;
   int occ = 1;
-  MB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_merge_sites, MERGE_THREADS, 0));
+  MB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, MERGE_THREADS, 0));
   const uint32_t grid = (uint32_t)std::min<uint64_t>(want, (uint64_t)ctx->sm_count * (occ > 0 ? occ : 1));
   { int trc = mb::timing_begin(ctx); if (trc) return trc; }
-  k_merge_sites<<<grid, MERGE_THREADS, 0, ctx->stream>>>(p);
+  fn<<<grid, MERGE_THREADS, 0, ctx->stream>>>(p);
   { int trc = mb::timing_end(ctx); if (trc) return trc; }
   ctx->launches++;
   MB_CUDA_TRY(cudaGetLastError());

@@ -59,9 +59,13 @@ def test_kernel_matches_golden(ctx, case):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("seed,S,G", [(1, 3, 10_000), (2, 20, 50_001), (3, 1, 777), (4, 64, 4096)])
-def test_kernel_matches_oracle(ctx, seed, S, G):
-    counts, md = mo.synth_counts(seed, S, G, depth_mean=30.0, snp_frac=0.2)
+@pytest.mark.parametrize("seed,S,G,depth", [(1, 3, 10_000, 30.0), (2, 20, 50_001, 30.0), (3, 1, 777, 30.0),
+                                             (4, 64, 4096, 30.0), (5, 40, 3000, 180.0), (6, 100, 2000, 60.0),
+                                             (7, 33, 1500, 400.0)])
+def test_kernel_matches_oracle(ctx, seed, S, G, depth):
+    """depth 180-400: many sites hold counts above 255 and take the re-read path instead of the packed registers;
+    S = 100: samples past the register-resident 64."""
+    counts, md = mo.synth_counts(seed, S, G, depth_mean=depth, snp_frac=0.2)
     exp = mo.merge_sites(counts, md, 0.05, 3, 1.5)
     _gpu_check(ctx, counts, md, 0.05, 3, 1.5, exp)
 

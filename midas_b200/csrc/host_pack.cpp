@@ -8,6 +8,7 @@
 //   qlen  = aln.query_length                    (snps.py:146)
 // and validates the inputs on which the reference would raise. No counting happens here.
 #include <algorithm>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -176,13 +177,16 @@ int analyse(const mb_plain_reads* in, const mb_layout* L, int mode, uint64_t i, 
   g->n_blk = (uint32_t)((lq + MB_BLOCK - 1) / MB_BLOCK);
   g->n_cplx_words = 0;
   {
+    // or of all qualities, eight at a time: bit 7 set = a quality above 127, bits 6-7 clear = six planes suffice
     const uint8_t* q = in->qual + in->seq_off[i];
-    uint8_t mx = 0;
-    for (int64_t k = 0; k < lq; ++k) mx = std::max(mx, q[k]);
-    if (mx > 127)
-      return mb::fail(MB_EINVAL, "read %llu: base quality %u above 127 is not representable", (unsigned long long)i,
-                      (unsigned)mx);
-    g->max_q = mx;
+    uint64_t acc = 0;
+    int64_t k = 0;
+    for (; k + 8 <= lq; k += 8) { uint64_t w; memcpy(&w, q + k, 8); acc |= w; }
+    for (; k < lq; ++k) acc |= q[k];
+    acc |= acc >> 32; acc |= acc >> 16; acc |= acc >> 8;
+    if (acc & 0x80u)
+      return mb::fail(MB_EINVAL, "read %llu: a base quality above 127 is not representable", (unsigned long long)i);
+    g->max_q = (uint8_t)(acc & 0xffu);                      // an upper bound with the same leading bit as the maximum
   }
   const int32_t rid = in->ref_id[i];
   if (mode == 1) {  // genes: loc = gene index, the pileup geometry is unused
@@ -260,8 +264,12 @@ uint32_t write_cplx(const uint32_t* cig, int64_t n_cig, int64_t room /* contig_l
   return 1 + 2 * n;
 }
 
-static const uint8_t kNib2Code[16] = {0, 0, 1, 0, 2, 0, 0, 0, 3, 0, 0, 0, 0, 0, 0, 0};
-static const uint8_t kNibIsAcgt[16] = {0, 1, 1, 0, 1, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0};
+constexpr uint64_t kLsb = 0x0101010101010101ull;
+// bit 0 of each of eight bytes -> the eight low bits of the result (byte i -> bit i)
+static inline uint32_t gather8(uint64_t m) { return (uint32_t)((m * 0x0102040810204080ull) >> 56); }
+// 1 in bit 0 of every byte of v (bytes < 0x80) that is not zero
+static inline uint64_t nonzero_bytes(uint64_t v) { return (((v + 0x7f7f7f7f7f7f7f7full) | v) >> 7) & kLsb; }
+
 
 template <class F>
 void parallel_for(uint64_t n, int n_threads, F f) {
@@ -308,6 +316,10 @@ extern "C" int mb_pack_reads(const mb_plain_reads* in, const mb_layout* L, int m
   if (n >= 0xFFFFFFFFull) return mb::fail(MB_EOVERFLOW, "mb_pack_reads: more than 2^32-2 reads in one batch");
   if (n_threads <= 0) n_threads = (int)std::min<unsigned>(32, std::max(1u, std::thread::hardware_concurrency()));
 
+  const bool timing = getenv("MB_PACK_TIMING") != nullptr;
+  auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  double t_phase = now();
+  auto phase = [&](const char* name) { if (timing) { const double t = now(); fprintf(stderr, "mb_pack_reads: %-10s %8.1f ms\n", name, t - t_phase); t_phase = t; } };
   std::vector<ReadGeom> geom(n);
   std::vector<int> rc(n_threads + 1, MB_OK);
   std::vector<std::string> msg(n_threads + 1);
@@ -320,6 +332,7 @@ extern "C" int mb_pack_reads(const mb_plain_reads* in, const mb_layout* L, int m
   for (int t = 0; t <= n_threads; ++t)
     if (rc[t] != MB_OK) return mb::fail(rc[t], "%s", msg[t].c_str());
 
+  phase("analyse");
   // order
   std::vector<uint32_t> perm;
   bool is_sorted = true;
@@ -344,13 +357,25 @@ extern "C" int mb_pack_reads(const mb_plain_reads* in, const mb_layout* L, int m
   std::vector<uint32_t> blk_off(n + 1), cg_off(n + 1);
   uint64_t nb = 0, ncw = 0, tot_bases = 0;
   uint32_t max_span = 0;
-  for (uint64_t j0 = 0; j0 < n; j0 += MB_GROUP) {               // groups of MB_GROUP reads, units interleaved
-    const uint64_t j1 = std::min<uint64_t>(n, j0 + MB_GROUP);
-    uint64_t units = 0;                                         // 32-byte units per read of this group
-    for (uint64_t j = j0; j < j1; ++j) units = std::max<uint64_t>(units, ((uint64_t)geom[src(j)].n_blk * NP + 7) / 8);
-    for (uint64_t j = j0; j < j1; ++j) blk_off[j] = (uint32_t)(nb + (j - j0));
-    nb += units * MB_GROUP;
+  {  // groups of MB_GROUP reads, units interleaved: units per read of a group = the largest of its reads
+    const uint64_t n_groups = (n + MB_GROUP - 1) / MB_GROUP;
+    std::vector<uint32_t> g_units(n_groups);
+    parallel_for(n_groups, n_threads, [&](uint64_t lo, uint64_t hi, int) {
+      for (uint64_t gi = lo; gi < hi; ++gi) {
+        const uint64_t j1 = std::min<uint64_t>(n, (gi + 1) * MB_GROUP);
+        uint64_t units = 0;
+        for (uint64_t j = gi * MB_GROUP; j < j1; ++j)
+          units = std::max<uint64_t>(units, ((uint64_t)geom[src(j)].n_blk * NP + 7) / 8);
+        g_units[gi] = (uint32_t)units;
+      }
+    });
+    std::vector<uint64_t> g_off(n_groups + 1, 0);
+    for (uint64_t gi = 0; gi < n_groups; ++gi) g_off[gi + 1] = g_off[gi] + (uint64_t)g_units[gi] * MB_GROUP;
+    nb = g_off[n_groups];
     if (nb > 0xFFFFFFF0ull) return mb::fail(MB_EOVERFLOW, "mb_pack_reads: batch too large for 32-bit unit offsets");
+    parallel_for(n, n_threads, [&](uint64_t lo, uint64_t hi, int) {
+      for (uint64_t j = lo; j < hi; ++j) blk_off[j] = (uint32_t)(g_off[j / MB_GROUP] + j % MB_GROUP);
+    });
   }
   for (uint64_t j = 0; j < n; ++j) {
     const ReadGeom& g = geom[src(j)];
@@ -382,6 +407,7 @@ extern "C" int mb_pack_reads(const mb_plain_reads* in, const mb_layout* L, int m
       if (geom[i].need_words > row_words) { geom[i].flags |= MB_RF_LONG; ++n_long; }
   }
 
+  phase("offsets");
   mb_packed_owner* o = new mb_packed_owner();
   memset(o, 0, sizeof(*o));
   o->pinned = pinned != 0;
@@ -404,6 +430,7 @@ extern "C" int mb_pack_reads(const mb_plain_reads* in, const mb_layout* L, int m
   uint32_t* cigar = (uint32_t*)o->buf[3];
   uint32_t* planes = (uint32_t*)o->buf[4];
   uint32_t* long_idx = (uint32_t*)o->buf[6];
+  phase("alloc");
   memcpy(blk, blk_off.data(), sizeof(uint32_t) * (n + 1));
   parallel_for(nb, n_threads, [&](uint64_t lo, uint64_t hi, int) { memset(planes + lo * 8, 0, (hi - lo) * 32); });
   if (n_long) {
@@ -458,19 +485,23 @@ extern "C" int mb_pack_reads(const mb_plain_reads* in, const mb_layout* L, int m
       for (uint32_t b = 0; b < g.n_blk; ++b) {
         uint32_t w[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};        // lo, hi, acgt, Phred bits 0..6
         const uint32_t nk = std::min<uint32_t>(MB_BLOCK, lq - b * MB_BLOCK);
-        for (uint32_t k = 0; k < nk; ++k) {
-          const uint32_t qi = b * MB_BLOCK + k;
-          const uint8_t nib = s[qi] & 0xF, ph = q[qi], code = kNib2Code[nib];
-          w[0] |= (uint32_t)(code & 1) << k;
-          w[1] |= (uint32_t)(code >> 1) << k;
-          w[2] |= (uint32_t)kNibIsAcgt[nib] << k;
-          w[3] |= (uint32_t)(ph & 1) << k;
-          w[4] |= (uint32_t)((ph >> 1) & 1) << k;
-          w[5] |= (uint32_t)((ph >> 2) & 1) << k;
-          w[6] |= (uint32_t)((ph >> 3) & 1) << k;
-          w[7] |= (uint32_t)((ph >> 4) & 1) << k;
-          w[8] |= (uint32_t)((ph >> 5) & 1) << k;
-          w[9] |= (uint32_t)((ph >> 6) & 1) << k;
+        uint8_t sb[MB_BLOCK] = {0}, qb[MB_BLOCK] = {0};          // the block's bases, zero padded
+        memcpy(sb, s + b * MB_BLOCK, nk);
+        memcpy(qb, q + b * MB_BLOCK, nk);
+        for (uint32_t part = 0; part < 4; ++part) {              // eight bases at a time, byte-parallel in a u64
+          uint64_t sw, qw;
+          memcpy(&sw, sb + 8 * part, 8);
+          memcpy(&qw, qb + 8 * part, 8);
+          const uint32_t sh = 8 * part;
+          for (uint32_t k = 0; k < q_planes; ++k) w[3 + k] |= gather8((qw >> k) & kLsb) << sh;
+          // BAM nibble -> 2-bit code: A=1 C=2 G=4 T=8 are the nibbles with exactly one bit set
+          const uint64_t nib = sw & 0x0f0f0f0f0f0f0f0full;
+          const uint64_t t = nib & ((nib | 0x8080808080808080ull) - kLsb) & 0x0f0f0f0f0f0f0f0full;   // nib & (nib - 1)
+          const uint64_t acgt = nonzero_bytes(nib) & ~nonzero_bytes(t);
+          const uint64_t b1 = (nib >> 1) & kLsb, b2 = (nib >> 2) & kLsb, b3 = (nib >> 3) & kLsb;
+          w[0] |= gather8(acgt & (b1 | b3)) << sh;               // C, T
+          w[1] |= gather8(acgt & (b2 | b3)) << sh;               // G, T
+          w[2] |= gather8(acgt) << sh;
         }
         if (mode == 0) { word(b * NP) = w[0]; word(b * NP + 1) = w[1]; word(b * NP + 2) = w[2]; }
         for (uint32_t k = 0; k < q_planes; ++k) word(b * NP + P0 + k) = w[3 + k];
@@ -489,7 +520,11 @@ extern "C" int mb_pack_reads(const mb_plain_reads* in, const mb_layout* L, int m
           const int64_t len = cig[k] >> 4;
           if (op == mb::OP_M || op == mb::OP_EQ || op == mb::OP_X) {
             const int64_t take = std::max<int64_t>(0, std::min<int64_t>(len, room - rr));
-            for (int64_t x = qq; x < qq + take; ++x) inrun[x >> 5] |= 1u << (x & 31);
+            for (int64_t x = qq; x < qq + take;) {               // bits [qq, qq + take), a word at a time
+              const int64_t wi = x >> 5, lo_b = x & 31, n_b = std::min<int64_t>(32 - lo_b, qq + take - x);
+              inrun[wi] |= (n_b == 32 ? 0xffffffffu : ((1u << n_b) - 1u)) << lo_b;
+              x += n_b;
+            }
             qq += len;
             rr += len;
           } else if (op == mb::OP_I || op == mb::OP_S) {
@@ -503,6 +538,7 @@ extern "C" int mb_pack_reads(const mb_plain_reads* in, const mb_layout* L, int m
     }
   });
 
+  phase("fill");
   o->pub.n_reads = n;
   o->pub.n_vec = nb;
   o->pub.n_cigar_words = ncw;

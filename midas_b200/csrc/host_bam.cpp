@@ -14,14 +14,28 @@
 
 #include "common.h"
 
+// a buffer whose pages are first touched by the threads that fill it (std::vector would zero it on one thread)
+template <class T>
+struct RawBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  RawBuf() = default;
+  RawBuf(const RawBuf&) = delete;
+  RawBuf& operator=(const RawBuf&) = delete;
+  ~RawBuf() { free(p); }
+  bool resize(size_t k) { free(p); n = k; p = (T*)malloc((k ? k : 1) * sizeof(T)); return p != nullptr; }
+  T* data() { return p; }
+  const T* data() const { return p; }
+};
+
 struct mb_bam {
   std::vector<std::string> ref_name;
   std::vector<uint32_t> ref_len;
-  std::vector<int32_t> ref_id, pos, nm, l_qseq;
-  std::vector<uint8_t> mapq, seq, qual;
-  std::vector<uint16_t> flag;
+  RawBuf<int32_t> ref_id, pos, nm, l_qseq;
+  RawBuf<uint8_t> mapq, seq, qual;
+  RawBuf<uint16_t> flag;
   std::vector<uint64_t> cigar_off, seq_off;
-  std::vector<uint32_t> cigar;
+  RawBuf<uint32_t> cigar;
   mb_plain_reads pub;
 };
 
@@ -97,8 +111,10 @@ extern "C" int mb_bam_open(const char* path, int n_threads, mb_bam** out) {
   fseek(fh, 0, SEEK_END);
   const long fsz = ftell(fh);
   fseek(fh, 0, SEEK_SET);
-  std::vector<uint8_t> raw((size_t)std::max(0L, fsz));
-  if (fsz > 0 && fread(raw.data(), 1, (size_t)fsz, fh) != (size_t)fsz) { fclose(fh); return mb::fail(MB_EINVAL, "mb_bam_open: short read on %s", path); }
+  struct RawFile { RawBuf<uint8_t> b; const uint8_t* data() const { return b.data(); } size_t size() const { return b.n; }
+                   const uint8_t& operator[](size_t i) const { return b.p[i]; } } raw;
+  if (!raw.b.resize((size_t)std::max(0L, fsz))) { fclose(fh); return mb::fail(MB_ENOMEM, "mb_bam_open: out of memory"); }
+  if (fsz > 0 && fread(raw.b.data(), 1, (size_t)fsz, fh) != (size_t)fsz) { fclose(fh); return mb::fail(MB_EINVAL, "mb_bam_open: short read on %s", path); }
   fclose(fh);
   // 1. BGZF block table
   struct Blk { size_t off, cbeg, clen; uint32_t isize; size_t dst; };
@@ -129,7 +145,8 @@ extern "C" int mb_bam_open(const char* path, int n_threads, mb_bam** out) {
   }
   if (off != raw.size()) return mb::fail(MB_EMALFORMED, "mb_bam_open: %s: trailing bytes after the last BGZF block", path);
   // 2. inflate in parallel
-  std::vector<uint8_t> data(total + 8);
+  RawBuf<uint8_t> data;
+  if (!data.resize(total + 8)) return mb::fail(MB_ENOMEM, "mb_bam_open: out of memory");
   std::vector<int> bad((size_t)n_threads + 1, 0);
   pfor(blks.size(), n_threads, [&](size_t lo, size_t hi) {
     for (size_t i = lo; i < hi; ++i) {
@@ -138,7 +155,7 @@ extern "C" int mb_bam_open(const char* path, int n_threads, mb_bam** out) {
       z_stream zs;
       memset(&zs, 0, sizeof(zs));
       if (inflateInit2(&zs, -15) != Z_OK) { bad[0] = 1; return; }
-      zs.next_in = raw.data() + k.cbeg;
+      zs.next_in = const_cast<uint8_t*>(raw.data()) + k.cbeg;
       zs.avail_in = (uInt)k.clen;
       zs.next_out = data.data() + k.dst;
       zs.avail_out = k.isize;
@@ -150,10 +167,10 @@ extern "C" int mb_bam_open(const char* path, int n_threads, mb_bam** out) {
     }
   });
   if (bad[0]) return mb::fail(MB_EMALFORMED, "mb_bam_open: %s: BGZF inflate / CRC failure", path);
-  raw.clear();
-  raw.shrink_to_fit();
+  raw.b.resize(0);
   // 3. header
   const uint8_t* d = data.data();
+  memset(data.data() + total, 0, 8);
   if (total < 12 || memcmp(d, "BAM\1", 4) != 0) return mb::fail(MB_EMALFORMED, "mb_bam_open: %s: not a BAM file", path);
   size_t o = 8 + (size_t)rd32(d + 4);
   if (o + 4 > total) return mb::fail(MB_EMALFORMED, "mb_bam_open: %s: truncated header", path);
@@ -190,8 +207,11 @@ extern "C" int mb_bam_open(const char* path, int n_threads, mb_bam** out) {
     o += 4 + bs;
   }
   const size_t n = rec.size();
-  B->ref_id.resize(n); B->pos.resize(n); B->nm.resize(n); B->l_qseq.resize(n); B->mapq.resize(n); B->flag.resize(n);
-  B->cigar.resize(coff.back()); B->seq.resize(soff.back()); B->qual.resize(soff.back());
+  if (!(B->ref_id.resize(n) && B->pos.resize(n) && B->nm.resize(n) && B->l_qseq.resize(n) && B->mapq.resize(n) &&
+        B->flag.resize(n) && B->cigar.resize(coff.back()) && B->seq.resize(soff.back()) && B->qual.resize(soff.back()))) {
+    delete B;
+    return mb::fail(MB_ENOMEM, "mb_bam_open: out of memory");
+  }
   B->cigar_off = std::move(coff);
   B->seq_off = std::move(soff);
   // 5. parallel decode
@@ -200,11 +220,11 @@ extern "C" int mb_bam_open(const char* path, int n_threads, mb_bam** out) {
       const uint8_t* r = d + rec[i] + 4;
       const uint32_t bs = rd32(d + rec[i]);
       const uint32_t l_name = r[8], n_cig = rd16(r + 12), l_seq = rd32(r + 16);
-      B->ref_id[i] = (int32_t)rd32(r);
-      B->pos[i] = (int32_t)rd32(r + 4);
-      B->mapq[i] = r[9];
-      B->flag[i] = rd16(r + 14);
-      B->l_qseq[i] = (int32_t)l_seq;
+      B->ref_id.p[i] = (int32_t)rd32(r);
+      B->pos.p[i] = (int32_t)rd32(r + 4);
+      B->mapq.p[i] = r[9];
+      B->flag.p[i] = rd16(r + 14);
+      B->l_qseq.p[i] = (int32_t)l_seq;
       const uint8_t* q = r + 32 + l_name;
       memcpy(B->cigar.data() + B->cigar_off[i], q, 4 * (size_t)n_cig);
       q += 4 * (size_t)n_cig;
@@ -213,7 +233,7 @@ extern "C" int mb_bam_open(const char* path, int n_threads, mb_bam** out) {
       q += (l_seq + 1) / 2;
       memcpy(B->qual.data() + B->seq_off[i], q, l_seq);
       q += l_seq;
-      B->nm[i] = find_nm(q, r + bs);
+      B->nm.p[i] = find_nm(q, r + bs);
     }
   });
   B->pub.n_reads = n;

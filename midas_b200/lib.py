@@ -408,31 +408,43 @@ def format_snps_rows(contig_name: str, ref_bases: np.ndarray, first_pos0: int, c
     return buf.raw[:w]
 
 
+class _BamHandle:
+    """Keeps an mb_bam alive for as long as numpy views of its arrays exist."""
+
+    def __init__(self, h):
+        self.h = h
+
+    def __del__(self):
+        h, self.h = self.h, None
+        if h and _lib is not None:
+            _lib.mb_bam_close(h)
+
+
 def read_bam(path: str, threads: int = 0):
     """Native BAM decode (mb_bam_open): returns (ref_names, ref_lens, PlainReads) in file order, like
-    midas_b200.bam.read_bam (the pure-Python reader it must agree with)."""
+    midas_b200.bam.read_bam (the pure-Python reader it must agree with). The arrays are views of the
+    handle's buffers (no copy); the handle is closed when the last of them goes away."""
     L = load()
     h = C.c_void_p()
     _check(L.mb_bam_open(os.fsencode(path), int(threads), C.byref(h)))
-    try:
-        n_ref = int(L.mb_bam_n_ref(h))
-        names = [L.mb_bam_ref_name(h, i).decode() for i in range(n_ref)]
-        lens = [int(L.mb_bam_ref_len(h, i)) for i in range(n_ref)]
-        r = L.mb_bam_reads(h).contents
-        n = int(r.n_reads)
+    owner = _BamHandle(h)
+    n_ref = int(L.mb_bam_n_ref(h))
+    names = [L.mb_bam_ref_name(h, i).decode() for i in range(n_ref)]
+    lens = [int(L.mb_bam_ref_len(h, i)) for i in range(n_ref)]
+    r = L.mb_bam_reads(h).contents
+    n = int(r.n_reads)
 
-        def arr(ptr, count, dt):
-            if count == 0:
-                return np.zeros(0, dt)
-            buf = (C.c_char * (count * np.dtype(dt).itemsize)).from_address(ptr)
-            return np.frombuffer(buf, dtype=dt, count=count).copy()
+    def arr(ptr, count, dt):
+        if count == 0:
+            return np.zeros(0, dt)
+        buf = (C.c_char * (count * np.dtype(dt).itemsize)).from_address(ptr)
+        buf._owner = owner                      # numpy array -> ctypes buffer -> handle
+        return np.frombuffer(buf, dtype=dt, count=count)
 
-        coff = arr(r.cigar_off, n + 1, np.uint64)
-        soff = arr(r.seq_off, n + 1, np.uint64)
-        reads = PlainReads(arr(r.ref_id, n, np.int32), arr(r.pos, n, np.int32), arr(r.mapq, n, np.uint8),
-                           arr(r.nm, n, np.int32), arr(r.l_qseq, n, np.int32), coff,
-                           arr(r.cigar, int(coff[-1]), np.uint32), soff, arr(r.seq, int(soff[-1]), np.uint8),
-                           arr(r.qual, int(soff[-1]), np.uint8), arr(L.mb_bam_flags(h), n, np.uint16))
-    finally:
-        L.mb_bam_close(h)
+    coff = arr(r.cigar_off, n + 1, np.uint64)
+    soff = arr(r.seq_off, n + 1, np.uint64)
+    reads = PlainReads(arr(r.ref_id, n, np.int32), arr(r.pos, n, np.int32), arr(r.mapq, n, np.uint8),
+                       arr(r.nm, n, np.int32), arr(r.l_qseq, n, np.int32), coff,
+                       arr(r.cigar, int(coff[-1]), np.uint32), soff, arr(r.seq, int(soff[-1]), np.uint8),
+                       arr(r.qual, int(soff[-1]), np.uint8), arr(L.mb_bam_flags(h), n, np.uint16))
     return names, lens, reads

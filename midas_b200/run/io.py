@@ -59,6 +59,13 @@ class GzipMembersWriter:
         while len(self.pending) > self.max_pending:
             self.fh.write(self.pending.pop(0).result())
 
+    def write_deferred(self, make):
+        """Like write(make()), but make() itself (e.g. the native row formatter, which releases the GIL)
+        also runs on the pool; members are still written in submission order."""
+        self.pending.append(self.pool.submit(lambda: _member(make(), self.level)))
+        while len(self.pending) > self.max_pending:
+            self.fh.write(self.pending.pop(0).result())
+
     def close(self):
         for f in self.pending:
             self.fh.write(f.result())

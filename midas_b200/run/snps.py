@@ -24,7 +24,7 @@ from .. import bam, lib
 from ..soa import Filters, RefSet
 from . import io as mio
 
-CHUNK_ROWS = 1 << 18
+CHUNK_ROWS = 1 << 15          # rows per gzip member: ~1 MB of text, enough members to keep every host thread busy
 
 
 class Species:
@@ -141,7 +141,8 @@ def write_species_tsv(path, ref: RefSet, contigs, layout, counts, species_index,
         n = int(ref.contig_len[c])
         for lo in range(0, n, CHUNK_ROWS):
             hi = min(n, lo + CHUNK_ROWS)
-            out.write(lib.format_snps_rows(cid, seq[lo:hi], lo, view[:, lo:hi]))
+            out.write_deferred(lambda cid=cid, lo=lo, hi=hi, seq=seq, view=view:
+                               lib.format_snps_rows(cid, seq[lo:hi], lo, view[:, lo:hi]))
     out.close()
 
 
@@ -154,13 +155,26 @@ def pysam_pileup(args, species, contigs, ctx=None):
     own_ctx = ctx is None
     if own_ctx:
         ctx = lib.Context(int(args.get("device", 0)), use_torch_stream=False)
+    timing = args.get("timing")                     # optional dict: stage -> seconds (scripts/bench_pipeline.py)
+
+    def lap(stage, t0):
+        if timing is not None:
+            timing[stage] = timing.get(stage, 0.0) + (time() - t0)
+        return time()
+
     try:
+        t = time()
         ref = build_refset(species, contigs)
         bampath = "%s/snps/temp/genomes.bam" % args["outdir"]
         reads = load_alignments(bampath, ref)
+        if timing is not None:
+            timing["n_reads"], timing["n_bases"] = int(reads.n_reads), int(reads.l_qseq.sum(dtype=np.int64))
+        t = lap("bam_decode", t)
         layout = lib.Layout.of(ref)
         packed = lib.PackedReads(reads, layout, "snps", sort=True, pinned=False)
+        t = lap("pack", t)
         counts, stats = ctx.snps_pileup(packed, layout, _filters(args))
+        t = lap("gpu_h2d_kernels_d2h", t)
         threads = int(args.get("threads", 1) or 1)
         for k, species_id in enumerate(ref.species_ids):
             out_path = "%s/snps/output/%s.snps.gz" % (args["outdir"], species_id)
@@ -175,6 +189,7 @@ def pysam_pileup(args, species, contigs, ctx=None):
                 sp.fraction_covered = sp.covered_bases / float(sp.genome_length)
             if sp.covered_bases > 0:
                 sp.mean_coverage = sp.total_depth / float(sp.covered_bases)
+        lap("tsv_gzip", t)
     finally:
         if own_ctx:
             ctx.close()

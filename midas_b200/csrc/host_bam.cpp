@@ -10,6 +10,7 @@
 #include <cstring>
 #include <string>
 #include <thread>
+#include <chrono>
 #include <vector>
 
 #include "common.h"
@@ -106,6 +107,10 @@ int32_t find_nm(const uint8_t* p, const uint8_t* end) {
 extern "C" int mb_bam_open(const char* path, int n_threads, mb_bam** out) {
   if (!path || !out) return mb::fail(MB_EINVAL, "mb_bam_open: null argument");
   if (n_threads <= 0) n_threads = (int)std::min<unsigned>(32, std::max(1u, std::thread::hardware_concurrency()));
+  const bool timing = getenv("MB_BAM_TIMING") != nullptr;
+  auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  double t_phase = now();
+  auto phase = [&](const char* name) { if (timing) { const double t = now(); fprintf(stderr, "mb_bam_open: %-8s %8.1f ms\n", name, t - t_phase); t_phase = t; } };
   FILE* fh = fopen(path, "rb");
   if (!fh) return mb::fail(MB_EINVAL, "mb_bam_open: cannot open %s", path);
   fseek(fh, 0, SEEK_END);
@@ -116,6 +121,7 @@ extern "C" int mb_bam_open(const char* path, int n_threads, mb_bam** out) {
   if (!raw.b.resize((size_t)std::max(0L, fsz))) { fclose(fh); return mb::fail(MB_ENOMEM, "mb_bam_open: out of memory"); }
   if (fsz > 0 && fread(raw.b.data(), 1, (size_t)fsz, fh) != (size_t)fsz) { fclose(fh); return mb::fail(MB_EINVAL, "mb_bam_open: short read on %s", path); }
   fclose(fh);
+  phase("read");
   // 1. BGZF block table
   struct Blk { size_t off, cbeg, clen; uint32_t isize; size_t dst; };
   std::vector<Blk> blks;
@@ -144,6 +150,7 @@ extern "C" int mb_bam_open(const char* path, int n_threads, mb_bam** out) {
     off += bsize;
   }
   if (off != raw.size()) return mb::fail(MB_EMALFORMED, "mb_bam_open: %s: trailing bytes after the last BGZF block", path);
+  phase("blocks");
   // 2. inflate in parallel
   RawBuf<uint8_t> data;
   if (!data.resize(total + 8)) return mb::fail(MB_ENOMEM, "mb_bam_open: out of memory");
@@ -168,6 +175,7 @@ extern "C" int mb_bam_open(const char* path, int n_threads, mb_bam** out) {
   });
   if (bad[0]) return mb::fail(MB_EMALFORMED, "mb_bam_open: %s: BGZF inflate / CRC failure", path);
   raw.b.resize(0);
+  phase("inflate");
   // 3. header
   const uint8_t* d = data.data();
   memset(data.data() + total, 0, 8);
@@ -206,6 +214,7 @@ extern "C" int mb_bam_open(const char* path, int n_threads, mb_bam** out) {
     }
     o += 4 + bs;
   }
+  phase("records");
   const size_t n = rec.size();
   if (!(B->ref_id.resize(n) && B->pos.resize(n) && B->nm.resize(n) && B->l_qseq.resize(n) && B->mapq.resize(n) &&
         B->flag.resize(n) && B->cigar.resize(coff.back()) && B->seq.resize(soff.back()) && B->qual.resize(soff.back()))) {
@@ -236,6 +245,7 @@ extern "C" int mb_bam_open(const char* path, int n_threads, mb_bam** out) {
       B->nm.p[i] = find_nm(q, r + bs);
     }
   });
+  phase("decode");
   B->pub.n_reads = n;
   B->pub.ref_id = B->ref_id.data();
   B->pub.pos = B->pos.data();

@@ -118,6 +118,29 @@ def test_block_encoding_round_trips():
                 assert nib[code[q]] == src
 
 
+def test_ragged_reads_share_interleaved_groups():
+    """Reads of different lengths in one group of 32: every read decodes to its own bases, the group holds
+    max-over-its-reads units per read, and vec_off follows the interleaving rule."""
+    rng = np.random.default_rng(9)
+    ref = gen.make_ref(rng, 1, 1, 4000, 4000)
+    reads = gen.random_reads(10, ref, 100, max_len=200, min_len=5, long_del_frac=0.0)
+    pk = lib.PackedReads(reads, lib.Layout.of(ref), "snps")
+    lq = pk.hdr["l_qseq"].astype(np.int64)
+    assert lq.min() < 64 < 130 < lq.max()                            # genuinely ragged
+    units = (-(-lq // 32) * pk.n_planes + 7) // 8
+    off, base = pk.vec_off, 0
+    for g0 in range(0, 100, 32):
+        g1 = min(100, g0 + 32)
+        assert [int(x) for x in off[g0:g1]] == [base + k for k in range(g1 - g0)]
+        base += 32 * int(units[g0:g1].max())
+    assert int(off[100]) == base == pk.n_vec
+    assert np.array_equal(pk.hdr["loc"], reads.pos.astype(np.uint32))   # generator output is already sorted
+    for i in (0, 31, 32, 63, 99):
+        s0 = int(reads.seq_off[i])
+        _, _, ph = _decode(pk, i)
+        assert ph == [int(x) for x in reads.qual[s0:s0 + int(lq[i])]]
+
+
 def test_candidate_plane_excludes_clips_insertions_and_bases_past_the_contig_end():
     seq = "ACGTN" * 8                                                # 40 bases, every fifth is N
     pk = lib.PackedReads(_one([(4, 3), (OP_M, 10), (OP_I, 2), (OP_M, 20), (4, 5)], seq=seq, pos=985), lay(), "snps")

@@ -13,7 +13,8 @@
 //     overlapping a tile are one contiguous index range (k_tile_ranges) and a CTA owns a tile;
 //   * STAGE: one thread turns one read into a *bit-plane row in reference coordinates*, entirely in
 //     registers: the read's bit planes (mb_packed_reads: 32 bases per word) arrive as independent
-//     128-bit loads, Phred >= baseq is a bit-sliced comparator (one LOP3 per Phred bit per 32 bases,
+//     256-bit loads (the 32-byte units of 32 consecutive reads are interleaved, so each load of a warp
+//     is 1 KB of consecutive memory), Phred >= baseq is a bit-sliced comparator (one LOP3 per Phred bit per 32 bases,
 //     no per-base work at all), the Phred sum is one POPC per plane word, the two sequence planes are
 //     taken as they lie in HBM, and each CIGAR run is one funnel shift per plane per 32-position
 //     word (the packer has already cleared the candidate bit of every base outside an M/=/X run, so
@@ -41,8 +42,8 @@
 
 namespace {
 
-// positions per kernel tile (divides MB_TILE), a kernel template choice: 2048 (256 threads, 2 CTAs per SM)
-// or 1024 (128 threads, 4 CTAs per SM: more independent barrier domains per SM)
+// The positions per kernel tile (a divisor of MB_TILE) are a template choice of the kernel: 2048 (256
+// threads, 2 CTAs per SM; the one in use) or 1024 (128 threads, 4 CTAs per SM: measured 3 % slower).
 constexpr int KSUB = 4;                  // lanes sharing a column
 constexpr int NLEV = 8;                  // register vertical-counter levels (per-lane count <= 255 per round)
 constexpr int XLEV = NLEV + 2;           // levels after merging KSUB = 4 lanes
@@ -53,8 +54,6 @@ constexpr int LANE_ROWS_MAX = 248;       // rows one lane may take in one round 
 
 static_assert(MB_TILE % 2048 == 0, "kernel tile must divide the layout tile");
 static_assert(KSUB == 4, "the merge butterfly is written for 4 lanes per column");
-
-enum : uint32_t { F_NEEDQ = 1u, F_OVL = 2u, F_OWNER = 4u, F_SIMPLE = 8u };
 
 struct PileParams {
   const uint4* hdr;
@@ -186,7 +185,7 @@ __global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : 2) k_pi
   __shared__ uint32_t s_tile, s_nmax;
   __shared__ uint8_t s_mod[NCOL + 2 * WMAX + 1];                      // x % W for small x
 
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31;
   const int col = tid >> 2, ksub = tid & 3;                           // COUNT role
 
   for (int i = tid; i < VCL * NCOL; i += NT) s_vc[i] = make_uint4(0, 0, 0, 0);
@@ -206,7 +205,6 @@ __global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : 2) k_pi
     const uint32_t r0 = p.tile_rng[2 * tile], r1 = p.tile_rng[2 * tile + 1];
     const uint32_t tcol = ts >> 5, tb = tcol % W;
     const uint32_t slot_c = s_mod[tb + (uint32_t)col];                // where my column's word sits in a row
-    const uint32_t loc_base = ts - 32u * WMAX;                        // row coordinates are stored relative to it (wraps for ts = 0: no read starts before 0)
 
     uint32_t col_rows = 0;      // rows of my column folded since the last expansion
     uint32_t my_aligned = 0, my_mapped = 0;
@@ -278,8 +276,8 @@ __global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : 2) k_pi
       pass_rows += (uint32_t)n;
       __syncthreads();
       // ---- STAGE: one thread per read, everything in registers: header filters (snps.py:148,154,157),
-      // row index table, the read's bit planes as independent 128-bit loads (L1 absorbs the stride
-      // between lanes), bit-sliced base-quality test, mean-quality filter, CIGAR placement, row store
+      // row index table, the read's bit planes as independent 256-bit loads, bit-sliced base-quality test,
+      // mean-quality filter, CIGAR placement, row store
       if (rb == r0) {                                          // later rounds: requested before the previous COUNT
         nh = make_uint4(0, 0, 0, 0); nb0 = 0; ncw = 0; nprev = 0;
       }

@@ -27,6 +27,7 @@ struct MergeParams {
   uint32_t* sample_depth;        // [S][G]
   double* sample_maf;            // [S][G]
   const unsigned long long* sd_max;   // [S] smallest per-sample depth that fails the site_ratio test (k_merge_thresholds)
+  uint32_t n_shared;             // samples KS .. KS + n_shared - 1 keep their packed counts in shared memory
 };
 
 // Per sample, the largest per-sample depth sd that still passes the ratio test of compute_prevalence
@@ -52,8 +53,9 @@ __global__ void k_merge_thresholds(const double* __restrict__ mean_depth, uint32
 // them exceeds 255 falls back to re-reading, like the samples past KS): the second pass then costs no HBM
 // traffic for them. Both passes are unrolled four samples deep (sixteen / eight loads in flight per thread)
 // and the MAF division is taken only where a sample has minor-allele reads.
-template <int KS>
+template <int KS, bool SHARED>
 __global__ void __launch_bounds__(MERGE_THREADS) k_merge_sites(const MergeParams p) {
+  extern __shared__ uint32_t s_keep[];                       // [n_shared][MERGE_THREADS]
   const uint64_t G = p.n_sites;
   const uint32_t S = p.n_samples;
   for (uint64_t g = (uint64_t)blockIdx.x * MERGE_THREADS + threadIdx.x; g < G; g += (uint64_t)gridDim.x * MERGE_THREADS) {
@@ -84,6 +86,9 @@ __global__ void __launch_bounds__(MERGE_THREADS) k_merge_sites(const MergeParams
         for (int u = 0; u < 4; ++u) kept[s0 + u] = 0;
       }
     }
+    // samples past the registers: packed the same way into a thread-private column of shared memory
+    // (s_keep[sample - KS][thread]: conflict-free), as many as the launch reserved; the rest is re-read
+    const uint32_t s_end = SHARED ? KS + p.n_shared : KS;
     uint32_t s = KS;
     for (; s + 4 <= S; s += 4) {
       uint32_t v[4][4];
@@ -93,14 +98,24 @@ __global__ void __launch_bounds__(MERGE_THREADS) k_merge_sites(const MergeParams
         v[u][0] = __ldg(c); v[u][1] = __ldg(c + G); v[u][2] = __ldg(c + 2 * G); v[u][3] = __ldg(c + 3 * G);
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
+      for (int u = 0; u < 4; ++u) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) pc[k] += v[u][k];
+        if (SHARED && s + u < s_end) {
+          wide |= v[u][0] | v[u][1] | v[u][2] | v[u][3];
+          s_keep[(s + u - KS) * MERGE_THREADS + threadIdx.x] = v[u][0] | (v[u][1] << 8) | (v[u][2] << 16) | (v[u][3] << 24);
+        }
+      }
     }
     for (; s < S; ++s) {
       const uint32_t* c = p.counts + (size_t)s * 4 * G + g;
+      uint32_t v[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) pc[k] += __ldg(c + (size_t)k * G);
+      for (int k = 0; k < 4; ++k) { v[k] = __ldg(c + (size_t)k * G); pc[k] += v[k]; }
+      if (SHARED && s < s_end) {
+        wide |= v[0] | v[1] | v[2] | v[3];
+        s_keep[(s - KS) * MERGE_THREADS + threadIdx.x] = v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24);
+      }
     }
     const bool packed = wide < 256u;
     const unsigned long long depth = pc[0] + pc[1] + pc[2] + pc[3];
@@ -170,6 +185,13 @@ __global__ void __launch_bounds__(MERGE_THREADS) k_merge_sites(const MergeParams
       }
     }
     uint32_t t = KS;
+    if (SHARED && packed) {                                    // shared-memory samples: no HBM traffic
+      const uint32_t t_end = s_end < S ? s_end : S;
+      for (; t < t_end; ++t) {
+        const uint32_t w = s_keep[(t - KS) * MERGE_THREADS + threadIdx.x];
+        finish(t, has_major ? (w >> shm) & 255u : 0u, has_minor ? (w >> shn) & 255u : 0u);
+      }
+    }
     for (; t + 4 <= S; t += 4) {
       uint32_t cm[4], cn[4];
 #pragma unroll
@@ -222,12 +244,20 @@ extern "C" int mb_merge_sites_dev(mb_ctx* ctx, const uint32_t* counts_dev, uint3
   // at every sample count). MB_MERGE_KS=4 selects the re-reading variant for comparison.
   int ks = 32;
   if (const char* e = getenv("MB_MERGE_KS")) { if (atoi(e) == 4) ks = 4; }
-  void (*fn)(const MergeParams) = ks == 4 ? k_merge_sites<4> : k_merge_sites<32>;
+  void (*fn)(const MergeParams) = ks == 4 ? k_merge_sites<4, false>
+                                          : (n_samples > 32 ? k_merge_sites<32, true> : k_merge_sites<32, false>);
+  // samples past the 32 in registers keep their packed counts in shared memory: up to 96 of them (48 KB per
+  // CTA, four CTAs per SM); MB_MERGE_SHARED overrides the count (experiments)
+  uint32_t n_shared = (ks == 32 && n_samples > 32u) ? std::min<uint32_t>(n_samples - 32u, 96u) : 0u;
+  if (const char* e = getenv("MB_MERGE_SHARED")) n_shared = std::min<uint32_t>(n_shared, (uint32_t)std::max(0, atoi(e)));
+  p.n_shared = n_shared;
+  const size_t smem = sizeof(uint32_t) * (size_t)n_shared * MERGE_THREADS;
+  if (smem > 48 * 1024) MB_CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 1;
-  MB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, MERGE_THREADS, 0));
+  MB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, MERGE_THREADS, smem));
   const uint32_t grid = (uint32_t)std::min<uint64_t>(want, (uint64_t)ctx->sm_count * (occ > 0 ? occ : 1));
   { int trc = mb::timing_begin(ctx); if (trc) return trc; }
-  fn<<<grid, MERGE_THREADS, 0, ctx->stream>>>(p);
+  fn<<<grid, MERGE_THREADS, smem, ctx->stream>>>(p);
   { int trc = mb::timing_end(ctx); if (trc) return trc; }
   ctx->launches++;
   MB_CUDA_TRY(cudaGetLastError());

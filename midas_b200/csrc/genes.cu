@@ -87,9 +87,9 @@ __global__ void __launch_bounds__(GENE_THREADS) k_genes_v2(const GeneParams p) {
       unsigned long long* o = p.out + (size_t)gene * 3;
       atomicAdd(o, 1ull | ((unsigned long long)(keep ? 1u : 0u) << 32));  // genes.py:181-182,187-188
       if (keep) atomicAdd(o + 1, (unsigned long long)alen);                  // numerator of genes.py:189
-      if (p.key) { p.key[r] = keep ? gene : 0xFFFFFFFFu; p.val[r] = alen; }
+      if (p.key) { p.key[r] = keep ? gene : p.n_genes; p.val[r] = alen; }   // dropped reads sort behind every gene
     } else if (p.key) {
-      p.key[r] = 0xFFFFFFFFu;
+      p.key[r] = p.n_genes;
       p.val[r] = 0;
     }
   }
@@ -139,12 +139,14 @@ extern "C" int mb_genes_coverage_dev(mb_ctx* ctx, const mb_dev_reads* reads, con
   void* tmp = nullptr;
   size_t tmp_bytes = 0;
   const uint64_t n = reads->n_reads;
+  int key_bits = 1;                                   // sort keys are gene indices 0..n_genes (n_genes = dropped read)
+  while (key_bits < 32 && (n_genes >> key_bits)) ++key_bits;
   if (exact_order && n) {
     if (n > 0x7fffffffull) return mb::fail(MB_EOVERFLOW, "mb_genes_coverage_dev: exact_order supports < 2^31 reads");
     void* b[4];
     for (int k = 0; k < 4; ++k) { int rc = mb::ctx_reserve(ctx, 4 + k, sizeof(uint32_t) * n, &b[k]); if (rc) return rc; }
     key = (uint32_t*)b[0]; val = (uint32_t*)b[1]; key2 = (uint32_t*)b[2]; val2 = (uint32_t*)b[3];
-    MB_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, key, key2, val, val2, (int)n, 0, 32, st));
+    MB_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, key, key2, val, val2, (int)n, 0, key_bits, st));
     void* t = nullptr;
     int rc = mb::ctx_reserve(ctx, 15, tmp_bytes, &t);
     if (rc) return rc;
@@ -177,7 +179,7 @@ extern "C" int mb_genes_coverage_dev(mb_ctx* ctx, const mb_dev_reads* reads, con
     k_genes_finalize<<<(n_genes + 255) / 256, 256, 0, st>>>(p.out, gene_len_dev, n_genes);
     ctx->launches++;
     if (exact_order && n) {
-      MB_CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, key, key2, val, val2, (int)n, 0, 32, st));
+      MB_CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, key, key2, val, val2, (int)n, 0, key_bits, st));
       k_genes_exact<<<(n_genes + 127) / 128, 128, 0, st>>>(key2, val2, n, p.out, gene_len_dev, n_genes);
       ctx->launches++;
     }

@@ -176,7 +176,12 @@ __global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : 2) k_pi
   constexpr int NP = 3 + NQ;                    // words per 32-base block: seq lo, seq hi, candidate, Phred bits
   uint32_t tmk[NQ];                             // bit k of baseq, spread over a word (warp-uniform)
 #pragma unroll
-  for (int k = 0; k < NQ; ++k) tmk[k] = ((p.baseq >> k) & 1u) ? 0xffffffffu : 0u;
+  for (int k = 0; k < NQ; ++k) {
+    tmk[k] = ((p.baseq >> k) & 1u) ? 0xffffffffu : 0u;
+    // kept as a plain register operand: seen as a known-uniform value the compiler turns every comparator
+    // step into an AND plus a predicated OR (two instructions) instead of one three-input LOP3
+    asm volatile("mov.b32 %0, %0;" : "+r"(tmk[k]));
+  }
   const uint32_t q_allow = (p.baseq >> NQ) ? 0u : 0xffffffffu;   // a threshold above every representable Phred
   uint4* s_vc = reinterpret_cast<uint4*>(smem);                       // [VCL][NCOL] x {A,C,G,T}
   uint4* s_rows = s_vc + VCL * NCOL;                                  // [rmax][W] x {A,C,G,T}
@@ -343,7 +348,8 @@ __global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : 2) k_pi
 #pragma unroll
             for (int k = 0; k < NQ; ++k) {
               const uint32_t pk = blk[3 + k];
-              ge = (pk & ge) | (~tmk[k] & (pk | ge));       // threshold bit set: and, clear: or (one LOP3)
+              // threshold bit set: ge &= plane, clear: ge |= plane - one LOP3 (lut 0xD4 = c ? a & b : a | b)
+              asm("lop3.b32 %0, %1, %0, %2, 0xD4;" : "+r"(ge) : "r"(pk), "r"(tmk[k]));
               pc[k] += __popc(pk);
             }
             ql[w + 1] = blk[0];

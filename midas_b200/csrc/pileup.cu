@@ -333,10 +333,13 @@ __global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : 2) k_pi
         }
         // query bit planes, 32 bases per word: low / high bit of the base code, countable mask
         // (query word w lives at index w + 1; index 0 is "word -1", zero until the planes are slid)
+        // (words 1..WT are all written by the conversion below; the planes are only read under `keep`)
         uint32_t ql[WT + 2], qh[WT + 2], qv[WT + 2];
-#pragma unroll
-        for (int w = 0; w <= WT + 1; ++w) { ql[w] = 0; qh[w] = 0; qv[w] = 0; }
-        bool keep = false;
+        ql[0] = 0; qh[0] = 0; qv[0] = 0;
+        ql[WT + 1] = 0; qh[WT + 1] = 0; qv[WT + 1] = 0;
+        const uint32_t slot0 = s_mod[(int)tb + rel + (int)W];
+        uint4* __restrict__ dst = s_rows + (uint32_t)i * W;
+        bool keep = false, placed = false;
         if (needq) {
           uint32_t pc[NQ];
 #pragma unroll
@@ -366,7 +369,8 @@ __global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : 2) k_pi
             uint32_t raw[8 * NV8];
 #pragma unroll
             for (int u = 0; u < NV8; ++u) {
-              if ((uint32_t)u < nv8) ldg256(vp + 8 * MB_GROUP * u, raw + 8 * u);
+              // every read has a block, i.e. at least NP > 8 words: its first two units always exist
+              if (u < 2 || (uint32_t)u < nv8) ldg256(vp + 8 * MB_GROUP * u, raw + 8 * u);
               else {
 #pragma unroll
                 for (int c = 0; c < 8; ++c) raw[8 * u + c] = 0;
@@ -402,15 +406,12 @@ __global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : 2) k_pi
           for (int k = 0; k < NQ; ++k) qsum += pc[k] << k;
           keep = qsum >= p.readq_eff * lq;
           if (keep && owner) ++my_mapped;                                    // snps.py:161
-        }
         // ---- CIGAR: every M/=/X run is one funnel-shifted copy of the query planes. Query bit q of a run
         // (q0, x0) lies at row bit q - dq with dq = q0 - o - x0 = 32 d + sh, sh in [1, 32]: row word j is
         // query words (j + d, j + d + 1) funnel-shifted by sh; d is -1 for every read that is not heavily
         // clipped, other d first slide the planes by whole words so that the per-word code is static.
-        uint32_t rl[WT], rh[WT], rv[WT];
-#pragma unroll
-        for (int j = 0; j < WT; ++j) { rl[j] = 0; rh[j] = 0; rv[j] = 0; }
         if (keep && ovl) {
+          uint32_t rl[WT], rh[WT], rv[WT];
           const int o = (int)(loc & 31u);
           const bool simple = (fl & MB_RF_SIMPLE) != 0;
           const bool runs2 = (fl & MB_RF_RUNS2) != 0;              // both runs are in the cplx word: no record fetch
@@ -466,6 +467,8 @@ __global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : 2) k_pi
             // row bits [o + x0, o + x0 + len) (clamped shifts: a PTX shift by >= 32 gives 0)
             const uint32_t* __restrict__ rec = p.cigar + cw;
             const uint32_t n_runs = __ldg(rec);
+#pragma unroll
+            for (int j = 0; j < WT; ++j) { rl[j] = 0; rh[j] = 0; rv[j] = 0; }
             for (uint32_t k = 0; k < n_runs; ++k) {
               const uint32_t w0 = __ldg(rec + 1 + 2 * k);
               const int q0 = (int)(w0 & 0xffffu), len = (int)(w0 >> 16), x0 = (int)__ldg(rec + 2 + 2 * k);
@@ -485,15 +488,19 @@ __global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : 2) k_pi
               }
             }
           }
-        }
-        const uint32_t slot0 = s_mod[(int)tb + rel + (int)W];
-        uint4* __restrict__ dst = s_rows + (uint32_t)i * W;
 #pragma unroll
-        for (int j = 0; j < WT; ++j) {
-          uint32_t slot = slot0 + (uint32_t)j;
-          if (slot >= W) slot -= W;
-          dst[slot] = make_uint4(rv[j] & ~rh[j] & ~rl[j], rv[j] & ~rh[j] & rl[j], rv[j] & rh[j] & ~rl[j],
-                                 rv[j] & rh[j] & rl[j]);
+          for (int j = 0; j < WT; ++j) {
+            uint32_t slot = slot0 + (uint32_t)j;
+            if (slot >= W) slot -= W;
+            dst[slot] = make_uint4(rv[j] & ~rh[j] & ~rl[j], rv[j] & ~rh[j] & rl[j], rv[j] & rh[j] & ~rl[j],
+                                   rv[j] & rh[j] & rl[j]);
+          }
+          placed = true;
+        }
+        }
+        if (!placed) {                                          // filtered out, or not on this tile: an empty row
+#pragma unroll
+          for (int j = 0; j < WT; ++j) dst[j] = make_uint4(0, 0, 0, 0);
         }
       }
       if (rb + p.rmax < r1) {   // the first read of my next round: requested now, in flight during COUNT

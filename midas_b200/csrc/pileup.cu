@@ -194,6 +194,7 @@ __global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : 2) k_pi
   const int col = tid >> 2, ksub = tid & 3;                           // COUNT role
 
   for (int i = tid; i < VCL * NCOL; i += NT) s_vc[i] = make_uint4(0, 0, 0, 0);
+  if (tid < (int)W) s_rows[p.rmax * W + tid] = make_uint4(0, 0, 0, 0);   // row rmax stays empty: COUNT reads it for padding
   for (int i = tid; i < NCOL + 2 * WMAX + 1; i += NT) s_mod[i] = (uint8_t)((uint32_t)i % W);
 
   uint32_t next_tile = 0;                                             // thread 0: the tile after the current one
@@ -532,7 +533,7 @@ __global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : 2) k_pi
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
               const uint32_t rr = r + (uint32_t)(u * KSUB);
-              mrow[u] = rr < hi ? base[rr * W] : make_uint4(0, 0, 0, 0);
+              mrow[u] = base[(rr < hi ? rr : p.rmax) * W];          // past the end: the all-zero row behind the last one
             }
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
@@ -745,7 +746,7 @@ PileKernel pick_kernel(uint32_t row_words, uint32_t q_planes) {
 }
 
 size_t pile_smem_bytes(uint32_t W, uint32_t rmax, uint32_t ncol) {
-  return sizeof(uint4) * ((size_t)VCL * ncol + (size_t)rmax * W);
+  return sizeof(uint4) * ((size_t)VCL * ncol + ((size_t)rmax + 1) * W);   // + the empty padding row
 }
 
 }  // namespace
@@ -793,7 +794,7 @@ extern "C" int mb_snps_pileup_dev(mb_ctx* ctx, const mb_dev_reads* reads, const 
     ctx->pile_occ = occ > 0 ? occ : 1;
   }
   const size_t fixed = sizeof(uint4) * (size_t)VCL * NCOL;
-  uint32_t rmax = (uint32_t)((ctx->pile_smem - fixed) / (sizeof(uint4) * W));
+  uint32_t rmax = (uint32_t)((ctx->pile_smem - fixed) / (sizeof(uint4) * W)) - 1u;   // one row is the empty padding row
   if (rmax > (uint32_t)LANE_ROWS_MAX * KSUB) rmax = LANE_ROWS_MAX * KSUB;
   if (rmax >= 2u * NT && !getenv("MB_PILE_RAGGED")) rmax = rmax / NT * NT;   // the same number of reads for every thread
   rmax &= ~7u;

@@ -14,6 +14,8 @@
  *                           midas/run/genes.py:153-169 keep_read()
  *   mb_bam_open          <- pysam.AlignmentFile(bam,'rb') at midas/run/snps.py:186, genes.py:175 (BAM decode)
  *   mb_format_snps_rows  <- midas/run/snps.py:179-182,201-210 (row text of <species>.snps.gz)
+ *   mb_merge_sites_dev   <- midas/merge/snps.py:42-104 GenomicSite (per-site arithmetic of merge_midas.py snps)
+ *   mb_format_merge_*    <- midas/merge/snps.py:196-201 (row text of snps_freq.txt / snps_depth.txt)
  *   mb_pack_reads        <- what pysam/htslib hands to those loops (decoded BAM
  *                           records), re-laid as the struct-of-arrays the GPU reads
  *
@@ -311,6 +313,17 @@ uint64_t mb_format_snps_bound(uint64_t name_len, uint64_t n_rows);
 int64_t mb_format_snps_rows(const char* contig_name, const uint8_t* ref_bases, uint64_t first_pos0,
                             uint64_t n_rows, const uint32_t* count_a, const uint32_t* count_c,
                             const uint32_t* count_g, const uint32_t* count_t, char* out, uint64_t cap);
+
+/* Rows of snps_freq.txt / snps_depth.txt of merge_midas.py snps (reference midas/merge/snps.py:196-201) for
+ * n_rows kept sites: "site_id \t v(sample 0) \t v(sample 1) ... \n" with '{0:.3g}'.format(maf) resp.
+ * str(depth). maf / depth are the sample-major outputs of mb_merge_sites_dev copied to the host (`stride`
+ * sites per sample); row r is site site_index[r] (0-based), printed as site id site_index[r] + 1 (:352).
+ * Return the number of bytes written (< 0: mb_status). Host only. */
+uint64_t mb_format_merge_bound(uint64_t n_rows, uint32_t n_samples);
+int64_t mb_format_merge_freq_rows(const uint64_t* site_index, uint64_t n_rows, uint32_t n_samples, uint64_t stride,
+                                  const double* maf, char* out, uint64_t cap);
+int64_t mb_format_merge_depth_rows(const uint64_t* site_index, uint64_t n_rows, uint32_t n_samples, uint64_t stride,
+                                   const uint32_t* depth, char* out, uint64_t cap);
 
 #ifdef __cplusplus
 }

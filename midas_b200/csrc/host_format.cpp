@@ -3,6 +3,8 @@
 // The reference builds each row with '\t'.join(str(x)) in a per-position Python loop; integers
 // print the same in any language, so this formatter only has to be fast. Gzip framing is left to
 // the caller (any member layout is valid; only the decompressed bytes are compared).
+#include <cmath>
+#include <cstdio>
 #include <cstring>
 
 #include "common.h"
@@ -58,6 +60,54 @@ extern "C" int64_t mb_format_snps_rows(const char* contig_name, const uint8_t* r
     p = put_u32(p, g);
     *p++ = '\t';
     p = put_u32(p, t);
+    *p++ = '\n';
+  }
+  return (int64_t)(p - out);
+}
+
+// ---- rows of snps_freq.txt / snps_depth.txt of merge_midas.py snps (reference midas/merge/snps.py:196-201):
+//   site_id \t v(sample 0) \t v(sample 1) ... \n   with '{0:.3g}'.format(maf) resp. str(depth).
+// The values stay where the kernel wrote them (sample-major, `stride` sites per sample): row r is site
+// site_index[r] (0-based; the id printed is site_index[r] + 1, snps.py:352). printf's %.3g is the same
+// correctly rounded three-significant-digit conversion as Python's format (two-digit exponents included).
+extern "C" uint64_t mb_format_merge_bound(uint64_t n_rows, uint32_t n_samples) {
+  return n_rows * (21 + (uint64_t)n_samples * 17 + 1) + 32;
+}
+
+extern "C" int64_t mb_format_merge_freq_rows(const uint64_t* site_index, uint64_t n_rows, uint32_t n_samples,
+                                             uint64_t stride, const double* maf, char* out, uint64_t cap) {
+  if (!site_index || !maf || !out) return mb::fail(MB_EINVAL, "mb_format_merge_freq_rows: null argument");
+  if (cap < mb_format_merge_bound(n_rows, n_samples))
+    return mb::fail(MB_EINVAL, "mb_format_merge_freq_rows: output buffer smaller than mb_format_merge_bound");
+  char* p = out;
+  for (uint64_t r = 0; r < n_rows; ++r) {
+    const uint64_t g = site_index[r];
+    p = put_u64(p, g + 1);
+    for (uint32_t s = 0; s < n_samples; ++s) {
+      *p++ = '\t';
+      const double v = maf[(size_t)s * stride + g];
+      if (v == 0.0 && !std::signbit(v)) *p++ = '0';
+      else if (v == 1.0) *p++ = '1';
+      else p += snprintf(p, 17, "%.3g", v);
+    }
+    *p++ = '\n';
+  }
+  return (int64_t)(p - out);
+}
+
+extern "C" int64_t mb_format_merge_depth_rows(const uint64_t* site_index, uint64_t n_rows, uint32_t n_samples,
+                                              uint64_t stride, const uint32_t* depth, char* out, uint64_t cap) {
+  if (!site_index || !depth || !out) return mb::fail(MB_EINVAL, "mb_format_merge_depth_rows: null argument");
+  if (cap < mb_format_merge_bound(n_rows, n_samples))
+    return mb::fail(MB_EINVAL, "mb_format_merge_depth_rows: output buffer smaller than mb_format_merge_bound");
+  char* p = out;
+  for (uint64_t r = 0; r < n_rows; ++r) {
+    const uint64_t g = site_index[r];
+    p = put_u64(p, g + 1);
+    for (uint32_t s = 0; s < n_samples; ++s) {
+      *p++ = '\t';
+      p = put_u32(p, depth[(size_t)s * stride + g]);
+    }
     *p++ = '\n';
   }
   return (int64_t)(p - out);

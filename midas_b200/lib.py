@@ -72,7 +72,7 @@ EXPORTS = [
     "mb_reads_upload", "mb_reads_free", "mb_reads_bytes",
     "mb_snps_pileup_dev", "mb_snps_pileup", "mb_genes_coverage_dev", "mb_genes_coverage",
     "mb_format_snps_bound", "mb_format_snps_rows",
-    "mb_merge_sites_dev",
+    "mb_merge_sites_dev", "mb_format_merge_bound", "mb_format_merge_freq_rows", "mb_format_merge_depth_rows",
     "mb_bam_open", "mb_bam_close", "mb_bam_n_ref", "mb_bam_ref_name", "mb_bam_ref_len", "mb_bam_reads", "mb_bam_flags",
 ]
 
@@ -129,6 +129,11 @@ def load():
                                     C.POINTER(CFilters), C.c_int, C.c_void_p]
     L.mb_format_snps_bound.restype = C.c_uint64
     L.mb_format_snps_bound.argtypes = [C.c_uint64, C.c_uint64]
+    L.mb_format_merge_bound.restype = C.c_uint64
+    L.mb_format_merge_bound.argtypes = [C.c_uint64, C.c_uint32]
+    for name in ("mb_format_merge_freq_rows", "mb_format_merge_depth_rows"):
+        getattr(L, name).restype = C.c_int64
+        getattr(L, name).argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint64, C.c_void_p, C.c_char_p, C.c_uint64]
     L.mb_format_snps_rows.restype = C.c_int64
     L.mb_format_snps_rows.argtypes = [C.c_char_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
@@ -418,6 +423,28 @@ class _BamHandle:
         h, self.h = self.h, None
         if h and _lib is not None:
             _lib.mb_bam_close(h)
+
+
+def format_merge_rows(site_index: np.ndarray, maf: np.ndarray, depth: np.ndarray):
+    """Text rows of snps_freq.txt and snps_depth.txt (reference midas/merge/snps.py:196-201) for the kept sites
+    `site_index` (0-based, uint64): maf f64 [S][G] and depth u32 [S][G] as mb_merge_sites_dev wrote them.
+    Returns (freq_bytes, depth_bytes)."""
+    L = load()
+    site_index = np.ascontiguousarray(site_index, np.uint64)
+    maf = np.ascontiguousarray(maf, np.float64)
+    depth = np.ascontiguousarray(depth, np.uint32)
+    S, G = maf.shape
+    assert depth.shape == (S, G)
+    n = len(site_index)
+    cap = int(L.mb_format_merge_bound(n, S))
+    out = []
+    for fn, arr in ((L.mb_format_merge_freq_rows, maf), (L.mb_format_merge_depth_rows, depth)):
+        buf = C.create_string_buffer(max(cap, 1))
+        w = fn(_ptr(site_index), n, S, G, _ptr(arr), buf, cap)
+        if w < 0:
+            _check(int(w))
+        out.append(buf.raw[:w])
+    return out[0], out[1]
 
 
 def read_bam(path: str, threads: int = 0):

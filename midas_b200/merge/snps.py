@@ -34,6 +34,7 @@ CODON_TABLE = {a + b + c: aa for (a, b, c), aa in zip(
     ((x, y, z) for x in "TCAG" for y in "TCAG" for z in "TCAG"),
     "FFLLSSSSYY__CC_WLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG")}   # standard code, stop = '_' (utility.py:306-326)
 COMPLEMENT = {"A": "T", "T": "A", "G": "C", "C": "G"}
+ROWS_PER_CHUNK = 1 << 14                                             # kept sites per formatting task
 
 
 # ------------------------------------------------------------------------------------------ site engine
@@ -63,21 +64,25 @@ def gpu_site_engine(device=0):
 
 
 # ------------------------------------------------------------------------------------------ inputs
-def read_sample_counts(species_id, samples, max_sites=float("inf")):
+def read_sample_counts(species_id, samples, max_sites=float("inf"), threads=1):
     """The samples' `<dir>/snps/output/<species>.snps.gz` tables (reference read_run_midas_snps :225-231 +
     build_temp_count_matrix :233-259) as (ref_id [G], ref_pos [G], ref_allele [G], counts u32 [S][4][G]).
     Site identity comes from the first sample; the table ends with the shortest sample and at max_sites."""
     import pandas as pd
+    from concurrent.futures import ThreadPoolExecutor
     cols = ["ref_id", "ref_pos", "ref_allele", "depth", "count_a", "count_c", "count_g", "count_t"]
     nrows = None if max_sites == float("inf") else int(max_sites)
-    frames = []
-    for k, sample in enumerate(samples):
-        path = "%s/snps/output/%s.snps.gz" % (sample.dir, species_id)
-        use = cols if k == 0 else cols[4:]
-        frames.append(pd.read_csv(path, sep="\t", header=0, names=cols, usecols=use, nrows=nrows, keep_default_na=False,
-                                  dtype={"ref_id": str, "ref_pos": np.int64, "ref_allele": str, "count_a": np.uint32,
-                                         "count_c": np.uint32, "count_g": np.uint32, "count_t": np.uint32},
-                                  compression="gzip", engine="c"))
+
+    def table(k):
+        path = "%s/snps/output/%s.snps.gz" % (samples[k].dir, species_id)
+        return pd.read_csv(path, sep="\t", header=0, names=cols, usecols=cols if k == 0 else cols[4:], nrows=nrows,
+                           keep_default_na=False, compression="gzip", engine="c",
+                           dtype={"ref_id": str, "ref_pos": np.int64, "ref_allele": str, "count_a": np.uint32,
+                                  "count_c": np.uint32, "count_g": np.uint32, "count_t": np.uint32})
+
+    # one table per sample, parsed concurrently (inflate and the C parser release the GIL)
+    with ThreadPoolExecutor(max(1, min(int(threads or 1), len(samples) or 1))) as pool:
+        frames = list(pool.map(table, range(len(samples))))
     G = min(len(f) for f in frames) if frames else 0
     counts = np.empty((len(frames), 4, G), np.uint32)
     for s, f in enumerate(frames):
@@ -172,23 +177,31 @@ def write_tables(species, args, ref_id, ref_pos, ref_allele, res, keep, genes):
     header = "\t".join(["site_id"] + [s.id for s in species.samples]) + "\n"
     index = GeneIndex(genes)
     pooled, major, minor = res["pooled"], res["major"], res["minor"]
-    with open(outdir + "/snps_info.txt", "w") as f_info, open(outdir + "/snps_freq.txt", "w") as f_freq, \
-            open(outdir + "/snps_depth.txt", "w") as f_depth:
+    from concurrent.futures import ThreadPoolExecutor
+    from .. import lib
+    maf = np.ascontiguousarray(res["sample_maf"], np.float64)
+    dep = np.ascontiguousarray(res["sample_depth"]).astype(np.uint32, copy=False)
+    keep = np.ascontiguousarray(keep, np.uint64)
+    chunks = [keep[lo:lo + ROWS_PER_CHUNK] for lo in range(0, len(keep), ROWS_PER_CHUNK)]
+    with open(outdir + "/snps_info.txt", "w") as f_info, open(outdir + "/snps_freq.txt", "wb") as f_freq, \
+            open(outdir + "/snps_depth.txt", "wb") as f_depth, \
+            ThreadPoolExecutor(max(1, int(args.get("threads", 1) or 1))) as pool:
         f_info.write("\t".join(INFO_FIELDS) + "\n")
-        f_freq.write(header)
-        f_depth.write(header)
-        maf = res["sample_maf"][:, keep].T                          # [kept sites][samples]
-        dep = res["sample_depth"][:, keep].T
-        for row, g in enumerate(keep):
-            sid, rid, pos = str(int(g) + 1), str(ref_id[g]), int(ref_pos[g])
+        f_freq.write(header.encode())
+        f_depth.write(header.encode())
+        # the two matrices: native row formatter (mb_format_merge_*_rows), chunks formatted concurrently
+        texts = pool.map(lambda c: lib.format_merge_rows(c, maf, dep), chunks)
+        for g in keep.tolist():                                      # the annotated info rows, kept sites only
+            sid, rid, pos = str(g + 1), str(ref_id[g]), int(ref_pos[g])
             locus, gene_id, site_type, aas = annotate(rid, pos, index.find(rid, pos))
             info = [sid, rid, str(pos), str(ref_allele[g]),
                     ALLELES[major[g]] if major[g] >= 0 else None, ALLELES[minor[g]] if minor[g] >= 0 else None,
                     str(int(res["count_samples"][g]))] + [str(int(pooled[k][g])) for k in range(4)] + \
                    [locus, gene_id, SNP_TYPES[int(res["snp_type"][g])], site_type, aas]
             f_info.write("\t".join(_na(x) for x in info) + "\n")
-            f_freq.write(sid + "\t" + "\t".join("{0:.3g}".format(x) for x in maf[row].tolist()) + "\n")
-            f_depth.write(sid + "\t" + "\t".join(str(x) for x in dep[row].tolist()) + "\n")
+        for freq, depth in texts:
+            f_freq.write(freq)
+            f_depth.write(depth)
 
 
 def write_snps_readme(args, sp):
@@ -204,7 +217,8 @@ def write_snps_readme(args, sp):
 def merge_species(species, args, engine):
     """All sites of one species: parse, pooled call (GPU), filter (reference flag :106-114), annotate, write.
     Returns (n_sites, n_kept)."""
-    ref_id, ref_pos, ref_allele, counts = read_sample_counts(species.id, species.samples, args["max_sites"])
+    ref_id, ref_pos, ref_allele, counts = read_sample_counts(species.id, species.samples, args["max_sites"],
+                                                             threads=args.get("threads", 1))
     S, G = counts.shape[0], counts.shape[2]
     if G == 0:
         res = dict(pooled=np.zeros((4, 0), np.uint32), major=np.zeros(0, np.int8), minor=np.zeros(0, np.int8),

@@ -5,7 +5,8 @@ per-site arithmetic on the B200 (midas_b200/merge/snps.py -> mb_merge_sites_dev)
 
 Flags, defaults, presets and the files written under <outdir>/<species_id>/ follow the reference. What differs:
   * `species` and `genes` are not provided (outside the pileup path and its consumers, SURVEY §8);
-  * --threads is accepted and ignored: one GPU call per species replaces the forked site shards;
+  * --threads sets the host threads that parse the samples' tables and format the output rows; the site
+    arithmetic itself is one GPU call per species instead of forked site shards;
   * --device selects the CUDA device; readme.txt is this package's own wording.
 """
 import argparse
@@ -31,7 +32,7 @@ def snps_arguments(argv=None):
     p = argparse.ArgumentParser(usage="merge_midas.py snps <outdir> [options]")
     p.add_argument("program", help=argparse.SUPPRESS)
     p.add_argument("outdir", type=str, help="directory for output files; one subdirectory per species_id")
-    p.add_argument("--threads", type=int, default=1, help="accepted for compatibility (ignored)")
+    p.add_argument("--threads", type=int, default=1, help="host threads for parsing and formatting (1)")
     p.add_argument("--device", type=int, default=0, help="CUDA device (this package only)")
     p.add_argument("-i", type=str, dest="input", required=True, help="sample directories written by run_midas.py; see -t")
     p.add_argument("-t", choices=["list", "file", "dir"], dest="intype", required=True,

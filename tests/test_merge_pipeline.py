@@ -81,3 +81,22 @@ def test_cli_presets_follow_the_reference():
     assert (a["snp_type"], a["site_prev"], a["sample_depth"], a["fract_cov"]) == (["any"], 0.0, 0.0, 0.0)
     a = merge_midas.snps_arguments(["snps", "out", "-i", "x", "-t", "list", "--all_sites", "--core_snps"])
     assert (a["snp_type"], a["site_prev"]) == (["bi"], 0.95)      # later presets win, as in the reference
+
+
+def test_native_row_formatter_equals_python_format():
+    """mb_format_merge_{freq,depth}_rows against '{0:.3g}'.format / str (snps.py:196-201) on ratios of small
+    integers (what a MAF is), values that round across a digit boundary, tiny and exact values."""
+    import numpy as np
+    from midas_b200 import lib
+    rng = np.random.default_rng(11)
+    S, G = 7, 4000
+    num = rng.integers(0, 400, (S, G)).astype(np.float64)
+    den = num + rng.integers(0, 400, (S, G))
+    maf = np.where(den > 0, num / np.maximum(den, 1), 0.0)
+    maf[0, :12] = [0.0, 1.0, 0.5, 0.9995, 0.99949999, 0.0009995, 1e-5, 1.2345e-7, 0.1, 0.125, 0.3335, 0.33349999]
+    depth = rng.integers(0, 2 ** 32, (S, G), dtype=np.uint64).astype(np.uint32)
+    keep = np.sort(rng.choice(G, 1500, replace=False)).astype(np.uint64)
+    freq, dep = lib.format_merge_rows(keep, maf, depth)
+    exp_f = "".join(str(int(g) + 1) + "\t" + "\t".join("{0:.3g}".format(x) for x in maf[:, g].tolist()) + "\n" for g in keep)
+    exp_d = "".join(str(int(g) + 1) + "\t" + "\t".join(str(x) for x in depth[:, g].tolist()) + "\n" for g in keep)
+    assert freq.decode() == exp_f and dep.decode() == exp_d

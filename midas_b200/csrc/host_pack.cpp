@@ -337,8 +337,12 @@ extern "C" int mb_pack_reads(const mb_plain_reads* in, const mb_layout* L, int m
   std::vector<uint32_t> perm;
   bool is_sorted = true;
   if (mode == 0) {
-    for (uint64_t i = 1; i < n; ++i)
-      if (geom[i].loc < geom[i - 1].loc) { is_sorted = false; break; }
+    std::vector<int> unsorted(n_threads + 1, 0);
+    parallel_for(n, n_threads, [&](uint64_t lo, uint64_t hi, int t) {
+      for (uint64_t i = std::max<uint64_t>(lo, 1); i < hi; ++i)
+        if (geom[i].loc < geom[i - 1].loc) { unsorted[t] = 1; return; }
+    });
+    for (int t = 0; t <= n_threads; ++t) is_sorted = is_sorted && !unsorted[t];
     if (!is_sorted) {
       if (!sort) return mb::fail(MB_EUNSORTED, "mb_pack_reads: snps reads are not sorted by (layout order, pos)");
       perm.resize(n);
@@ -394,7 +398,15 @@ extern "C" int mb_pack_reads(const mb_plain_reads* in, const mb_layout* L, int m
   uint64_t n_long = 0;
   if (mode == 0) {
     uint64_t hist[256] = {0};
-    for (uint64_t i = 0; i < n; ++i) hist[geom[i].need_words]++;
+    {
+      std::vector<uint64_t> part((size_t)(n_threads + 1) * 256, 0);
+      parallel_for(n, n_threads, [&](uint64_t lo, uint64_t hi, int t) {
+        uint64_t* h = part.data() + (size_t)t * 256;
+        for (uint64_t i = lo; i < hi; ++i) h[geom[i].need_words]++;
+      });
+      for (int t = 0; t <= n_threads; ++t)
+        for (int w = 0; w < 256; ++w) hist[w] += part[(size_t)t * 256 + w];
+    }
     uint64_t above = 0;
     for (int w = 255; w > (int)MB_ROW_WORDS_MAX; --w) above += hist[w];
     row_words = MB_ROW_WORDS_MAX;
@@ -403,8 +415,12 @@ extern "C" int mb_pack_reads(const mb_plain_reads* in, const mb_layout* L, int m
       above += hist[w];
       row_words = w - 1;
     }
-    for (uint64_t i = 0; i < n; ++i)
-      if (geom[i].need_words > row_words) { geom[i].flags |= MB_RF_LONG; ++n_long; }
+    for (int w = (int)row_words + 1; w < 256; ++w) n_long += hist[w];
+    if (n_long)
+      parallel_for(n, n_threads, [&](uint64_t lo, uint64_t hi, int) {
+        for (uint64_t i = lo; i < hi; ++i)
+          if (geom[i].need_words > row_words) geom[i].flags |= MB_RF_LONG;
+      });
   }
 
   phase("offsets");

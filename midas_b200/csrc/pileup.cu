@@ -61,6 +61,7 @@ struct PileParams {
   const uint32_t* cplx;
   const uint32_t* cigar;
   const uint32_t* planes;     // bit-planar read data (mb_packed_reads), regions in 32-byte units
+  const uint32_t* zero_unit;  // 32 bytes of zeros (the slack behind planes[]): what a load past a read's end fetches
   const uint32_t* tile_rng;   // [2 * n_ktiles]
   const int32_t* tile_species;  // per MB_TILE tile
   uint32_t* counts;
@@ -370,12 +371,9 @@ __global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : 2) k_pi
             uint32_t raw[8 * NV8];
 #pragma unroll
             for (int u = 0; u < NV8; ++u) {
-              // every read has a block, i.e. at least NP > 8 words: its first two units always exist
-              if (u < 2 || (uint32_t)u < nv8) ldg256(vp + 8 * MB_GROUP * u, raw + 8 * u);
-              else {
-#pragma unroll
-                for (int c = 0; c < 8; ++c) raw[8 * u + c] = 0;
-              }
+              // every read has a block, i.e. at least NP > 8 words: its first two units always exist; units
+              // past the read's end come from one shared all-zero unit (no predicated loads, no zeroed defaults)
+              ldg256((u < 2 || (uint32_t)u < nv8) ? vp + 8 * MB_GROUP * u : p.zero_unit, raw + 8 * u);
             }
 #pragma unroll
             for (int bl = 0; bl < WT; ++bl) convert(bl, raw + bl * NP);
@@ -819,6 +817,7 @@ extern "C" int mb_snps_pileup_dev(mb_ctx* ctx, const mb_dev_reads* reads, const 
   p.cplx = reads->cplx;
   p.cigar = reads->cigar;
   p.planes = reads->planes;
+  p.zero_unit = reads->planes + (size_t)reads->n_vec * 8;       // upload_reads keeps 256 zero bytes behind every array
   p.tile_rng = ctx->tile_rng;
   p.tile_species = dl.tile_species;
   p.counts = counts_dev;

@@ -3,6 +3,10 @@
 // opens <outdir>/snps/temp/genomes.bam (midas/run/snps.py:186) or genes/temp/pangenomes.bam
 // (midas/run/genes.py:175-178); records come out in file order, unplaced records (refID < 0) are
 // dropped, no index is needed. Format: SAM/BAM specification v1, sections 4.1 (BGZF) and 4.2.
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <zlib.h>
 
 #include <algorithm>
@@ -111,16 +115,30 @@ extern "C" int mb_bam_open(const char* path, int n_threads, mb_bam** out) {
   auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   double t_phase = now();
   auto phase = [&](const char* name) { if (timing) { const double t = now(); fprintf(stderr, "mb_bam_open: %-8s %8.1f ms\n", name, t - t_phase); t_phase = t; } };
-  FILE* fh = fopen(path, "rb");
-  if (!fh) return mb::fail(MB_EINVAL, "mb_bam_open: cannot open %s", path);
-  fseek(fh, 0, SEEK_END);
-  const long fsz = ftell(fh);
-  fseek(fh, 0, SEEK_SET);
-  struct RawFile { RawBuf<uint8_t> b; const uint8_t* data() const { return b.data(); } size_t size() const { return b.n; }
-                   const uint8_t& operator[](size_t i) const { return b.p[i]; } } raw;
-  if (!raw.b.resize((size_t)std::max(0L, fsz))) { fclose(fh); return mb::fail(MB_ENOMEM, "mb_bam_open: out of memory"); }
-  if (fsz > 0 && fread(raw.b.data(), 1, (size_t)fsz, fh) != (size_t)fsz) { fclose(fh); return mb::fail(MB_EINVAL, "mb_bam_open: short read on %s", path); }
-  fclose(fh);
+  // the file is mapped, not copied: the inflate threads read the compressed blocks straight from the page cache
+  struct RawFile {
+    const uint8_t* p = nullptr;
+    size_t n = 0;
+    ~RawFile() { release(); }
+    void release() { if (p && n) munmap(const_cast<uint8_t*>(p), n); p = nullptr; n = 0; }
+    const uint8_t* data() const { return p; }
+    size_t size() const { return n; }
+    const uint8_t& operator[](size_t i) const { return p[i]; }
+  } raw;
+  {
+    const int fd = open(path, O_RDONLY);
+    if (fd < 0) return mb::fail(MB_EINVAL, "mb_bam_open: cannot open %s", path);
+    struct stat st;
+    if (fstat(fd, &st) != 0) { close(fd); return mb::fail(MB_EINVAL, "mb_bam_open: cannot stat %s", path); }
+    if (st.st_size > 0) {
+      void* m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+      if (m == MAP_FAILED) { close(fd); return mb::fail(MB_EINVAL, "mb_bam_open: cannot map %s", path); }
+      madvise(m, (size_t)st.st_size, MADV_WILLNEED);
+      raw.p = (const uint8_t*)m;
+      raw.n = (size_t)st.st_size;
+    }
+    close(fd);
+  }
   phase("read");
   // 1. BGZF block table
   struct Blk { size_t off, cbeg, clen; uint32_t isize; size_t dst; };
@@ -174,7 +192,7 @@ extern "C" int mb_bam_open(const char* path, int n_threads, mb_bam** out) {
     }
   });
   if (bad[0]) return mb::fail(MB_EMALFORMED, "mb_bam_open: %s: BGZF inflate / CRC failure", path);
-  raw.b.resize(0);
+  raw.release();
   phase("inflate");
   // 3. header
   const uint8_t* d = data.data();

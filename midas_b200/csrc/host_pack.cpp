@@ -358,7 +358,7 @@ extern "C" int mb_pack_reads(const mb_plain_reads* in, const mb_layout* L, int m
   const uint32_t q_planes = max_q <= 63 ? 6u : 7u;
   const uint32_t NP = mode == 0 ? 3u + q_planes : q_planes;     // words per block
   const uint32_t P0 = mode == 0 ? 3u : 0u;                      // first Phred plane
-  std::vector<uint32_t> blk_off(n + 1), cg_off(n + 1);
+  std::vector<uint32_t> unit_off(n + 1), cg_off(n + 1);
   uint64_t nb = 0, ncw = 0, tot_bases = 0;
   uint32_t max_span = 0;
   {  // groups of MB_GROUP reads, units interleaved: units per read of a group = the largest of its reads
@@ -378,7 +378,7 @@ extern "C" int mb_pack_reads(const mb_plain_reads* in, const mb_layout* L, int m
     nb = g_off[n_groups];
     if (nb > 0xFFFFFFF0ull) return mb::fail(MB_EOVERFLOW, "mb_pack_reads: batch too large for 32-bit unit offsets");
     parallel_for(n, n_threads, [&](uint64_t lo, uint64_t hi, int) {
-      for (uint64_t j = lo; j < hi; ++j) blk_off[j] = (uint32_t)(g_off[j / MB_GROUP] + j % MB_GROUP);
+      for (uint64_t j = lo; j < hi; ++j) unit_off[j] = (uint32_t)(g_off[j / MB_GROUP] + j % MB_GROUP);
     });
   }
   for (uint64_t j = 0; j < n; ++j) {
@@ -390,7 +390,7 @@ extern "C" int mb_pack_reads(const mb_plain_reads* in, const mb_layout* L, int m
     if (ncw > 0xFFFFFFF0ull)
       return mb::fail(MB_EOVERFLOW, "mb_pack_reads: batch too large for 32-bit run-record offsets");
   }
-  blk_off[n] = (uint32_t)nb;
+  unit_off[n] = (uint32_t)nb;
   cg_off[n] = (uint32_t)ncw;
 
   // row width of the tile kernel: the smallest W that all but 0.1 % of the reads fit
@@ -441,13 +441,13 @@ extern "C" int mb_pack_reads(const mb_plain_reads* in, const mb_layout* L, int m
     if (!o->buf[k]) { mb_packed_free(&o->pub); return mb::fail(MB_ENOMEM, "mb_pack_reads: out of host memory"); }
   }
   mb_read_hdr* hdr = (mb_read_hdr*)o->buf[0];
-  uint32_t* blk = (uint32_t*)o->buf[1];
+  uint32_t* voff = (uint32_t*)o->buf[1];
   uint32_t* cplx = (uint32_t*)o->buf[2];
   uint32_t* cigar = (uint32_t*)o->buf[3];
   uint32_t* planes = (uint32_t*)o->buf[4];
   uint32_t* long_idx = (uint32_t*)o->buf[6];
   phase("alloc");
-  memcpy(blk, blk_off.data(), sizeof(uint32_t) * (n + 1));
+  memcpy(voff, unit_off.data(), sizeof(uint32_t) * (n + 1));
   parallel_for(nb, n_threads, [&](uint64_t lo, uint64_t hi, int) { memset(planes + lo * 8, 0, (hi - lo) * 32); });
   if (n_long) {
     uint64_t k = 0;
@@ -496,7 +496,7 @@ extern "C" int mb_pack_reads(const mb_plain_reads* in, const mb_layout* L, int m
       const uint8_t* q = in->qual + in->seq_off[i];
       const uint32_t lq = h.l_qseq;
       // word w of this read: unit w/8 of the read, units of a group interleaved (stride MB_GROUP units)
-      uint32_t* reg = planes + (size_t)blk_off[j] * 8;
+      uint32_t* reg = planes + (size_t)unit_off[j] * 8;
       auto word = [&](uint32_t w) -> uint32_t& { return reg[(size_t)(w >> 3) * (8 * MB_GROUP) + (w & 7u)]; };
       for (uint32_t b = 0; b < g.n_blk; ++b) {
         uint32_t w[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};        // lo, hi, acgt, Phred bits 0..6
@@ -567,7 +567,7 @@ extern "C" int mb_pack_reads(const mb_plain_reads* in, const mb_layout* L, int m
   o->pub.n_planes = NP;
   o->pub.long_idx = long_idx;
   o->pub.hdr = hdr;
-  o->pub.vec_off = blk;
+  o->pub.vec_off = voff;
   o->pub.cplx = cplx;
   o->pub.cigar = cigar;
   o->pub.planes = planes;

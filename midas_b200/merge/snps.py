@@ -236,15 +236,22 @@ def merge_species(species, args, engine):
     return G, len(keep)
 
 
-def run_pipeline(args, engine=None):
-    """reference run_pipeline :469-508."""
+def run_pipeline(args, engine=None, shard=None):
+    """reference run_pipeline :469-508. Species are independent, so under `torchrun` (or with an explicit
+    shard = (rank, world)) every process selects the same species list and merges every world-th species on
+    its own GPU (LOCAL_RANK); no collective is needed, each species has its own output directory."""
     print("Identifying species and samples")
     species_list = merge.select_species(args, dtype="snps")
     for species in species_list:
         print("  %s" % species.id)
         print("    count samples: %s" % len(species.samples))
+    rank, world = shard if shard is not None else (int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")))
+    if world > 1:
+        species_list = species_list[rank::world]
+        print("\nRank %s of %s: %s species" % (rank, world, len(species_list)))
     if engine is None and species_list:
-        engine = gpu_site_engine(int(args.get("device", 0)))
+        device = args.get("device")
+        engine = gpu_site_engine(int(os.environ.get("LOCAL_RANK", "0")) if device is None else int(device))
     print("\nMerging snps")
     for species in species_list:
         print("  %s" % species.id)

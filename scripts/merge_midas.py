@@ -7,7 +7,8 @@ Flags, defaults, presets and the files written under <outdir>/<species_id>/ foll
   * `species` and `genes` are not provided (outside the pileup path and its consumers, SURVEY §8);
   * --threads sets the host threads that parse the samples' tables and format the output rows; the site
     arithmetic itself is one GPU call per species instead of forked site shards;
-  * --device selects the CUDA device; readme.txt is this package's own wording.
+  * --device selects the CUDA device; under torchrun every rank merges every WORLD_SIZE-th species on its own
+    GPU (species are independent: no collective); readme.txt is this package's own wording.
 """
 import argparse
 import os
@@ -33,7 +34,9 @@ def snps_arguments(argv=None):
     p.add_argument("program", help=argparse.SUPPRESS)
     p.add_argument("outdir", type=str, help="directory for output files; one subdirectory per species_id")
     p.add_argument("--threads", type=int, default=1, help="host threads for parsing and formatting (1)")
-    p.add_argument("--device", type=int, default=0, help="CUDA device (this package only)")
+    p.add_argument("--device", type=int, default=None,
+                   help="CUDA device (this package only; default: LOCAL_RANK, so that `torchrun --nproc-per-node N "
+                        "scripts/merge_midas.py snps ...` merges every N-th species on each of N GPUs)")
     p.add_argument("-i", type=str, dest="input", required=True, help="sample directories written by run_midas.py; see -t")
     p.add_argument("-t", choices=["list", "file", "dir"], dest="intype", required=True,
                    help="list: comma-separated paths; dir: directory of sample directories; file: one path per line")

@@ -100,3 +100,21 @@ def test_native_row_formatter_equals_python_format():
     exp_f = "".join(str(int(g) + 1) + "\t" + "\t".join("{0:.3g}".format(x) for x in maf[:, g].tolist()) + "\n" for g in keep)
     exp_d = "".join(str(int(g) + 1) + "\t" + "\t".join(str(x) for x in depth[:, g].tolist()) + "\n" for g in keep)
     assert freq.decode() == exp_f and dep.decode() == exp_d
+
+
+def test_species_shard_over_ranks_without_a_collective(tmp_path):
+    """Two ranks, each merging every second species into the same outdir: the union is the single-process result."""
+    case = "all_sites"
+    with open(os.path.join(GOLD, "cases", case, "args.json")) as fh:
+        over = json.load(fh)
+    db, dirs = _inputs()
+    args = merge_args(str(tmp_path / "out"), db, dirs, **over)
+    os.makedirs(args["outdir"])
+    done = []
+    for rank in (0, 1):
+        done += [sp.id for sp in msnps.run_pipeline(dict(args), engine=mo.merge_sites, shard=(rank, 2))]
+    assert sorted(done) == ["Sp_alpha_1", "Sp_beta_2"] and len(set(done)) == 2
+    for sp in done:
+        for fn in FILES:
+            with open(os.path.join(GOLD, "cases", case, sp, fn), "rb") as a, open(os.path.join(args["outdir"], sp, fn), "rb") as b:
+                assert a.read() == b.read(), (sp, fn)

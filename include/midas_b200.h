@@ -16,8 +16,10 @@
  *   mb_format_snps_rows  <- midas/run/snps.py:179-182,201-210 (row text of <species>.snps.gz)
  *   mb_merge_sites_dev   <- midas/merge/snps.py:42-104 GenomicSite (per-site arithmetic of merge_midas.py snps)
  *   mb_format_merge_*    <- midas/merge/snps.py:196-201 (row text of snps_freq.txt / snps_depth.txt)
- *   mb_pack_reads        <- what pysam/htslib hands to those loops (decoded BAM
- *                           records), re-laid as the struct-of-arrays the GPU reads
+ *   mb_reads_pack*       <- what pysam/htslib hands to those loops (decoded BAM records),
+ *   mb_*_plain              re-laid ON THE GPU (k_pack_* kernels) as the struct-of-arrays the
+ *                           pileup kernels read; mb_pack_reads is the host version of the same
+ *                           re-layout (kept as its checker and for unsorted input)
  *
  * Conventions
  *   - plain C, no C++/torch types; every function returns MB_OK (0) or a negative
@@ -90,9 +92,14 @@ typedef struct {
   const int32_t* l_qseq;      /* [n] stored query length (soft clips included) */
   const uint64_t* cigar_off;  /* [n+1] prefix offsets into cigar[] */
   const uint32_t* cigar;      /* BAM encoding: len<<4 | op, op in MIDNSHP=X (0..8) */
-  const uint64_t* seq_off;    /* [n+1] prefix offsets (in bases) into seq[] and qual[] */
-  const uint8_t* seq;         /* one BAM 4-bit code per byte: =ACMGRSVTWYHKDBN (A=1,C=2,G=4,T=8) */
+  const uint64_t* seq_off;    /* [n+1] offsets (in bases) into seq[] and qual[]: base k of read i is element
+                                 seq_off[i] + k; seq_off[i+1] - seq_off[i] >= l_qseq[i] (padding allowed) */
+  const uint8_t* seq;         /* BAM 4-bit codes =ACMGRSVTWYHKDBN (A=1,C=2,G=4,T=8): one per byte
+                                 (seq_nibbles = 0), or as they lie in a BAM record, two per byte with the
+                                 even element in the high nibble (seq_nibbles = 1; every seq_off[i] even) */
   const uint8_t* qual;        /* raw Phred, one per base; 0xFF in the first byte = missing */
+  uint32_t seq_nibbles;
+  uint32_t reserved;
 } mb_plain_reads;
 
 /* -------------------------------------------------------- reference layout */
@@ -109,6 +116,9 @@ typedef struct {
 
 typedef struct mb_layout mb_layout;
 int mb_layout_create(const mb_ref* ref, mb_layout** out);
+/* genes mode needs no coordinates (loc = gene index): a layout that only knows how many genes there
+ * are, without the 32-bit padded-genome limit of mb_layout_create */
+int mb_layout_create_genes(uint32_t n_genes, mb_layout** out);
 void mb_layout_destroy(mb_layout* L);
 uint64_t mb_layout_gpad(const mb_layout* L);             /* padded genome size, multiple of MB_TILE */
 uint32_t mb_layout_n_tiles(const mb_layout* L);
@@ -159,11 +169,10 @@ typedef struct {
  *   p = 3+k   bit k of the base's Phred quality, k < q_planes
  * genes mode (n_planes = q_planes): only the Phred bit planes (the path reads nothing else).
  * q_planes is 6 when every quality of the batch is <= 63, else 7 (Phred <= 127 is required).
- *   cplx[i]   for reads without MB_RF_SIMPLE: index into cigar[] of a run record
- *             {n_runs, (q0 | len << 16, x0) per M/=/X run}: query index of the run's first
- *             base, run length, reference offset from the read's start (I/S/D/N/H folded in,
- *             clipped at the contig end); 0xFFFFFFFF for simple reads; the two runs themselves
- *             for MB_RF_RUNS2 reads
+ *   cplx[i]   0xFFFFFFFF for MB_RF_SIMPLE reads; the two runs themselves for MB_RF_RUNS2 reads; for
+ *             every other read the index into cigar[] of the read's first raw BAM CIGAR word
+ *             (len << 4 | op): the kernels walk the ops until l_qseq query bases are consumed and
+ *             clip every M/=/X run at ref_span (= the contig end)
  */
 typedef struct {
   uint64_t n_reads;
@@ -178,7 +187,8 @@ typedef struct {
   uint32_t n_long;           /* number of MB_RF_LONG reads */
   uint32_t q_planes;         /* Phred bit planes per block: 6 or 7 */
   uint32_t n_planes;         /* words per block: 3 + q_planes (snps) or q_planes (genes) */
-  const uint32_t* long_idx;  /* [n_long] ascending indices of the MB_RF_LONG reads */
+  const uint32_t* long_idx;  /* [n_long] indices of the MB_RF_LONG reads (ascending from mb_pack_reads, any order
+                                from the device packer) */
   const mb_read_hdr* hdr;    /* [n_reads] */
   const uint32_t* vec_off;   /* [n_reads+1] first 32-byte unit of each read in planes[] (its further units
                                 follow at a stride of MB_GROUP units); vec_off[n_reads] = n_vec */
@@ -196,6 +206,10 @@ typedef struct {
 int mb_pack_reads(const mb_plain_reads* in, const mb_layout* L, int mode, int sort,
                   int pinned, int n_threads, mb_packed_reads** out);
 void mb_packed_free(mb_packed_reads* p);
+
+/* page-locked host memory for buffers that cross PCIe (cudaHostAlloc); MB_ECUDA without a device */
+int mb_host_alloc(size_t bytes, void** out);
+void mb_host_free(void* p);
 
 /* ------------------------------------------------------------------ context */
 typedef struct mb_ctx mb_ctx;
@@ -220,6 +234,24 @@ typedef struct mb_dev_reads mb_dev_reads;
 int mb_reads_upload(mb_ctx* ctx, const mb_packed_reads* host, mb_dev_reads** out);
 void mb_reads_free(mb_ctx* ctx, mb_dev_reads* r);
 uint64_t mb_reads_bytes(const mb_dev_reads* r); /* bytes resident in HBM */
+uint64_t mb_reads_total_bases(const mb_dev_reads* r);
+uint64_t mb_reads_n(const mb_dev_reads* r);
+
+/* The re-layout of decoded records into the packed SoA, on the GPU (csrc/pack.cu): CIGAR geometry,
+ * validation, candidate mask and the bit transposition of sequence / Phred bytes into planes run as
+ * kernels over the plain arrays. `plain` holds HOST pointers for mb_reads_pack (copied to the device
+ * first) and DEVICE pointers for mb_reads_pack_dev. mode 0 = snps: the records must be in BAM
+ * coordinate order (ref_id, then pos, ascending - what `samtools sort` writes, reference
+ * midas/run/snps.py:118); contigs are moved as whole blocks into the layout's order, no sort runs.
+ * Otherwise MB_EUNSORTED (use mb_pack_reads with sort). mode 1 = genes (file order kept).
+ * The result is resident in HBM and byte-identical to mb_reads_upload(mb_pack_reads(...)) up to the
+ * indexing of cigar[] / order of long_idx[]. Synchronises the context stream once. */
+int mb_reads_pack(mb_ctx* ctx, const mb_plain_reads* plain_host, const mb_layout* L, int mode, mb_dev_reads** out);
+int mb_reads_pack_dev(mb_ctx* ctx, const mb_plain_reads* plain_dev, const mb_layout* L, int mode, mb_dev_reads** out);
+/* host copy of a resident batch (for checking the device packer against mb_pack_reads); free with mb_packed_free */
+int mb_reads_download(mb_ctx* ctx, const mb_dev_reads* r, mb_packed_reads** out);
+/* device time (ms) of the k_pack_* kernels of the most recent mb_reads_pack* / mb_*_plain call */
+int mb_ctx_last_pack_ms(mb_ctx* ctx, float* ms);
 
 /* -------------------------------------------------------------- snps path */
 /* per species: the aln_stats dict of species_pileup (snps.py:172-176, 211-213) */
@@ -242,6 +274,23 @@ int mb_snps_pileup_dev(mb_ctx* ctx, const mb_dev_reads* reads, const mb_layout* 
 int mb_snps_pileup(mb_ctx* ctx, const mb_packed_reads* reads, const mb_layout* L,
                    const mb_filters* f, uint32_t* counts_host, mb_species_stats* stats_host);
 
+/* From decoded records in (pinned or pageable) host memory: H2D of the plain arrays + device re-layout
+ * + mb_snps_pileup_dev + D2H of counts and stats; staging buffers are owned by the context and reused.
+ * This is the host-buffer call of the path (what bench.py's e2e times and run/snps.py calls). */
+int mb_snps_pileup_plain(mb_ctx* ctx, const mb_plain_reads* plain_host, const mb_layout* L,
+                         const mb_filters* f, uint32_t* counts_host, mb_species_stats* stats_host);
+
+/* A batch in which a u32 counter would overflow (more than 2^32-1 reads counted on one position) makes
+ * mb_snps_pileup / mb_snps_pileup_plain return MB_EOVERFLOW; the counter saturates at 0xFFFFFFFF. After
+ * an asynchronous mb_snps_pileup_dev, ask with mb_ctx_overflowed (synchronises the stream). */
+int mb_ctx_overflowed(mb_ctx* ctx, int* flag);
+
+/* Multi-GPU (species sharded by rank, midas/run/snps.py:225-228): a device pointer in ANOTHER GPU's
+ * memory (peer / symmetric memory, e.g. rank 0's stats table) to which the kernel epilogue of every
+ * following mb_snps_pileup_dev also writes its mb_species_stats rows, so that no collective is needed
+ * to gather them. NULL switches the mirror off. */
+int mb_ctx_set_stats_mirror(mb_ctx* ctx, mb_species_stats* peer_rows);
+
 /* ------------------------------------------------------------- genes path */
 /* per gene: Gene.{aligned_reads,mapped_reads,depth} of count_mapped_bp
  * (genes.py:181-189); mapped_bp = sum of alen over kept reads, depth =
@@ -260,6 +309,9 @@ int mb_genes_coverage_dev(mb_ctx* ctx, const mb_dev_reads* reads, const uint32_t
 int mb_genes_coverage(mb_ctx* ctx, const mb_packed_reads* reads, const uint32_t* gene_len_host,
                       uint32_t n_genes, const mb_filters* f, int exact_order,
                       mb_gene_out* out_host);
+/* from decoded records in host memory (H2D + device re-layout + coverage + D2H), see mb_snps_pileup_plain */
+int mb_genes_coverage_plain(mb_ctx* ctx, const mb_plain_reads* plain_host, const uint32_t* gene_len_host,
+                            uint32_t n_genes, const mb_filters* f, int exact_order, mb_gene_out* out_host);
 
 /* ------------------------------------------------------------ merge (snps) */
 /* Pooled allele call across samples for every site of one species: the per-site arithmetic of
@@ -295,7 +347,9 @@ int mb_merge_sites_dev(mb_ctx* ctx, const uint32_t* counts_dev, uint32_t n_sampl
  * (midas/run/snps.py:186,194; midas/run/genes.py:175-180); no index (snps.py:130-139) is needed.
  * The arrays behind mb_bam_reads() belong to the handle. Host only. */
 typedef struct mb_bam mb_bam;
-int mb_bam_open(const char* path, int n_threads, mb_bam** out);
+#define MB_BAM_PINNED 1     /* the record arrays are page-locked (they are about to cross PCIe) */
+#define MB_BAM_SEQ_BYTES 2  /* seq expanded to one code per byte (default: as in the file, seq_nibbles = 1) */
+int mb_bam_open(const char* path, int n_threads, int flags, mb_bam** out);
 void mb_bam_close(mb_bam* b);
 uint32_t mb_bam_n_ref(const mb_bam* b);
 const char* mb_bam_ref_name(const mb_bam* b, uint32_t i);

@@ -75,6 +75,7 @@ def _reg2bin(beg: int, end: int) -> int:
 def write_bam(path: str, ref_names, ref_lens, reads: PlainReads, extra_tags: bool = True,
               header_text: str | None = None, level: int = 6) -> None:
     """Write `reads` as a BAM file (records in the given order)."""
+    reads = reads.unpacked()
     if header_text is None:
         header_text = "@HD\tVN:1.0\tSO:unsorted\n" + "".join(
             f"@SQ\tSN:{n}\tLN:{int(l)}\n" for n, l in zip(ref_names, ref_lens))

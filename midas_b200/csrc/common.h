@@ -30,6 +30,7 @@ enum { OP_M = 0, OP_I = 1, OP_D = 2, OP_N = 3, OP_S = 4, OP_H = 5, OP_P = 6, OP_
 // --------------------------------------------------------------------------------------
 struct mb_layout {
   uint64_t id;  // unique, for device-side caches
+  bool genes_only;  // mb_layout_create_genes: only n_contigs is meaningful
   uint32_t n_contigs, n_species;
   uint64_t gpad;
   uint32_t n_tiles;
@@ -38,6 +39,8 @@ struct mb_layout {
   std::vector<uint32_t> species_goff;  // [n_species+1]
   std::vector<uint64_t> species_len;   // [n_species]
   std::vector<int32_t> tile_species;   // [n_tiles], -1 for none
+  std::vector<uint32_t> order;         // [n_contigs] contig indices in layout (global coordinate) order
+  bool identity_order;                 // order[k] == k
 };
 
 struct mb_packed_owner {  // allocation record behind a library-owned mb_packed_reads
@@ -56,11 +59,15 @@ struct mb_dev_reads {
   uint32_t* cigar;
   uint32_t* planes;
   uint64_t bytes;
+  bool owned;  // the arrays are this object's own allocations (false: context staging buffers)
 };
 
 struct mb_dev_layout {  // device mirror of the parts of a layout the kernels read
   int32_t* tile_species;
   uint64_t* species_len;
+  uint32_t* contig_len;   // [n_contigs]
+  uint32_t* contig_goff;  // [n_contigs]
+  uint32_t* order;        // [n_contigs]
 };
 
 struct mb_ctx {
@@ -90,8 +97,19 @@ struct mb_ctx {
   bool ftab_valid;
   std::unordered_map<uint64_t, mb_dev_layout> layouts;
   // staging for the host-buffer convenience calls
-  void* stage[16];
-  size_t stage_cap[16];
+  static constexpr int kStage = 40;
+  void* stage[kStage];
+  size_t stage_cap[kStage];
+  // device packer (pack.cu)
+  void* pack_meta;        // device PackMeta
+  void* pack_meta_host;   // pinned mirror
+  cudaEvent_t pack_ev[2];
+  bool pack_timed;
+  // u32 counter overflow flag of the pileup kernels (device word + pinned mirror)
+  uint32_t* ovf;
+  uint32_t* ovf_host;
+  // peer-memory mirror of the stats rows (multi-GPU), or null
+  mb_species_stats* stats_mirror;
 };
 
 namespace mb {
@@ -101,4 +119,10 @@ int upload_reads(mb_ctx* ctx, const mb_packed_reads* h, mb_dev_reads* d, bool st
 int ctx_reserve(mb_ctx* ctx, int slot, size_t bytes, void** out);
 int get_dev_layout(mb_ctx* ctx, const mb_layout* L, mb_dev_layout* out);
 int get_filter_tables(mb_ctx* ctx, const mb_filters* f, const int32_t** t_pid, const int32_t** t_cov);
+// device packer: plain arrays already on the device -> packed batch `d`; staged: into context staging buffers
+int pack_on_device(mb_ctx* ctx, const mb_plain_reads* dev, const mb_layout* L, int mode, bool staged, mb_dev_reads* d);
+// copy the plain arrays of `host` into context staging buffers (slots from `slot0`), `dev` gets the device pointers
+int upload_plain(mb_ctx* ctx, const mb_plain_reads* host, mb_plain_reads* dev);
+void free_dev_reads_arrays(mb_dev_reads* d);
+int check_overflow(mb_ctx* ctx, const char* who);   // after a stream sync: MB_EOVERFLOW if the flag is set (and clears it)
 }  // namespace mb

@@ -29,9 +29,17 @@ int get_dev_layout(mb_ctx* ctx, const mb_layout* L, mb_dev_layout* out) {
   auto it = ctx->layouts.find(L->id);
   if (it != ctx->layouts.end()) { *out = it->second; return MB_OK; }
   mb_dev_layout d{};
-  size_t nt = L->n_tiles ? L->n_tiles : 1, ns = L->n_species ? L->n_species : 1;
+  size_t nt = L->n_tiles ? L->n_tiles : 1, ns = L->n_species ? L->n_species : 1, nc = L->n_contigs ? L->n_contigs : 1;
   MB_CUDA_TRY(cudaMalloc(&d.tile_species, sizeof(int32_t) * nt));
   MB_CUDA_TRY(cudaMalloc(&d.species_len, sizeof(uint64_t) * ns));
+  MB_CUDA_TRY(cudaMalloc(&d.contig_len, sizeof(uint32_t) * nc));
+  MB_CUDA_TRY(cudaMalloc(&d.contig_goff, sizeof(uint32_t) * nc));
+  MB_CUDA_TRY(cudaMalloc(&d.order, sizeof(uint32_t) * nc));
+  if (L->n_contigs && !L->genes_only) {
+    MB_CUDA_TRY(cudaMemcpyAsync(d.contig_len, L->contig_len.data(), sizeof(uint32_t) * L->n_contigs, cudaMemcpyHostToDevice, ctx->stream));
+    MB_CUDA_TRY(cudaMemcpyAsync(d.contig_goff, L->contig_goff.data(), sizeof(uint32_t) * L->n_contigs, cudaMemcpyHostToDevice, ctx->stream));
+    MB_CUDA_TRY(cudaMemcpyAsync(d.order, L->order.data(), sizeof(uint32_t) * L->n_contigs, cudaMemcpyHostToDevice, ctx->stream));
+  }
   if (L->n_tiles)
     MB_CUDA_TRY(cudaMemcpyAsync(d.tile_species, L->tile_species.data(), sizeof(int32_t) * L->n_tiles,
                                 cudaMemcpyHostToDevice, ctx->stream));
@@ -156,8 +164,22 @@ extern "C" int mb_ctx_create(int device, mb_ctx** out) {
   c->ftab_valid = false;
   memset(c->stage, 0, sizeof(c->stage));
   memset(c->stage_cap, 0, sizeof(c->stage_cap));
+  c->pack_meta = nullptr;
+  c->pack_meta_host = nullptr;
+  c->pack_timed = false;
+  c->ovf = nullptr;
+  c->ovf_host = nullptr;
+  c->stats_mirror = nullptr;
   MB_CUDA_TRY(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
   c->stream = c->own_stream;
+  MB_CUDA_TRY(cudaMalloc(&c->pack_meta, 2048));
+  MB_CUDA_TRY(cudaHostAlloc(&c->pack_meta_host, 2048, cudaHostAllocDefault));
+  MB_CUDA_TRY(cudaEventCreate(&c->pack_ev[0]));
+  MB_CUDA_TRY(cudaEventCreate(&c->pack_ev[1]));
+  MB_CUDA_TRY(cudaMalloc(&c->ovf, 256));
+  MB_CUDA_TRY(cudaMemset(c->ovf, 0, 256));
+  MB_CUDA_TRY(cudaHostAlloc((void**)&c->ovf_host, 256, cudaHostAllocDefault));
+  c->ovf_host[0] = 0;
   for (int i = 0; i < mb_ctx::kRing; ++i) {
     MB_CUDA_TRY(cudaEventCreate(&c->ring[i][0]));
     MB_CUDA_TRY(cudaEventCreate(&c->ring[i][1]));
@@ -174,9 +196,18 @@ extern "C" void mb_ctx_destroy(mb_ctx* c) {
   for (auto& kv : c->layouts) {
     cudaFree(kv.second.tile_species);
     cudaFree(kv.second.species_len);
+    cudaFree(kv.second.contig_len);
+    cudaFree(kv.second.contig_goff);
+    cudaFree(kv.second.order);
   }
-  for (int i = 0; i < 16; ++i)
+  for (int i = 0; i < mb_ctx::kStage; ++i)
     if (c->stage[i]) cudaFree(c->stage[i]);
+  if (c->pack_meta) cudaFree(c->pack_meta);
+  if (c->pack_meta_host) cudaFreeHost(c->pack_meta_host);
+  cudaEventDestroy(c->pack_ev[0]);
+  cudaEventDestroy(c->pack_ev[1]);
+  if (c->ovf) cudaFree(c->ovf);
+  if (c->ovf_host) cudaFreeHost(c->ovf_host);
   if (c->tile_rng) cudaFree(c->tile_rng);
   if (c->sched) cudaFree(c->sched);
   if (c->ftab) cudaFree(c->ftab);
@@ -202,6 +233,42 @@ extern "C" int mb_ctx_sync(mb_ctx* c) {
 }
 
 extern "C" int mb_ctx_device(const mb_ctx* c) { return c ? c->device : -1; }
+
+namespace mb {
+int check_overflow(mb_ctx* c, const char* who) {
+  MB_CUDA_TRY(cudaMemcpyAsync(c->ovf_host, c->ovf, 4, cudaMemcpyDeviceToHost, c->stream));
+  MB_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  if (c->ovf_host[0]) {
+    c->ovf_host[0] = 0;
+    MB_CUDA_TRY(cudaMemsetAsync(c->ovf, 0, 4, c->stream));
+    return mb::fail(MB_EOVERFLOW, "%s: a per-position u32 counter overflowed (saturated at 4294967295)", who);
+  }
+  return MB_OK;
+}
+}  // namespace mb
+
+extern "C" int mb_ctx_overflowed(mb_ctx* c, int* flag) {
+  if (!c || !flag) return mb::fail(MB_EINVAL, "mb_ctx_overflowed: null argument");
+  MB_CUDA_TRY(cudaSetDevice(c->device));
+  const int rc = mb::check_overflow(c, "mb_ctx_overflowed");
+  if (rc == MB_EOVERFLOW) { *flag = 1; return MB_OK; }
+  *flag = 0;
+  return rc;
+}
+
+extern "C" int mb_ctx_set_stats_mirror(mb_ctx* c, mb_species_stats* peer_rows) {
+  if (!c) return mb::fail(MB_EINVAL, "mb_ctx_set_stats_mirror: null context");
+  c->stats_mirror = peer_rows;
+  return MB_OK;
+}
+
+extern "C" int mb_host_alloc(size_t bytes, void** out) {
+  if (!out) return mb::fail(MB_EINVAL, "mb_host_alloc: null argument");
+  cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 16, cudaHostAllocDefault);
+  if (e != cudaSuccess) { cudaGetLastError(); return mb::fail(MB_ECUDA, "mb_host_alloc(%zu): %s", bytes, cudaGetErrorString(e)); }
+  return MB_OK;
+}
+extern "C" void mb_host_free(void* p) { if (p) cudaFreeHost(p); }
 extern "C" uint64_t mb_ctx_launch_count(const mb_ctx* c) { return c ? c->launches : 0; }
 
 extern "C" int mb_ctx_last_kernel_ms(mb_ctx* c, float* ms) {
@@ -246,6 +313,7 @@ namespace mb {
 // next host-buffer call (no cudaMalloc/cudaFree on the e2e path); otherwise fresh allocations.
 int upload_reads(mb_ctx* c, const mb_packed_reads* h, mb_dev_reads* d, bool staged) {
   memset(d, 0, sizeof(*d));
+  d->owned = !staged;
   d->n_reads = h->n_reads;
   d->n_vec = h->n_vec;
   d->q_planes = h->q_planes;
@@ -295,13 +363,10 @@ extern "C" int mb_reads_upload(mb_ctx* c, const mb_packed_reads* h, mb_dev_reads
 extern "C" void mb_reads_free(mb_ctx* c, mb_dev_reads* d) {
   if (!d) return;
   if (c) { cudaSetDevice(c->device); cudaStreamSynchronize(c->stream); if (c->rng_for == d) c->rng_for = nullptr; }
-  cudaFree(d->hdr);
-  cudaFree(d->vec_off);
-  cudaFree(d->cplx);
-  cudaFree(d->cigar);
-  cudaFree(d->planes);
-  cudaFree(d->long_idx);
+  mb::free_dev_reads_arrays(d);
   delete d;
 }
 
 extern "C" uint64_t mb_reads_bytes(const mb_dev_reads* d) { return d ? d->bytes : 0; }
+extern "C" uint64_t mb_reads_total_bases(const mb_dev_reads* d) { return d ? d->total_bases : 0; }
+extern "C" uint64_t mb_reads_n(const mb_dev_reads* d) { return d ? d->n_reads : 0; }

@@ -215,3 +215,36 @@ extern "C" int mb_genes_coverage(mb_ctx* ctx, const mb_packed_reads* reads, cons
   }
   return rc;
 }
+
+extern "C" int mb_genes_coverage_plain(mb_ctx* ctx, const mb_plain_reads* plain_host, const uint32_t* gene_len_host,
+                                       uint32_t n_genes, const mb_filters* f, int exact_order, mb_gene_out* out_host) {
+  if (!ctx || !plain_host || !gene_len_host || !f || !out_host)
+    return mb::fail(MB_EINVAL, "mb_genes_coverage_plain: null argument");
+  MB_CUDA_TRY(cudaSetDevice(ctx->device));
+  mb_layout* L = nullptr;
+  int rc = mb_layout_create_genes(n_genes, &L);
+  if (rc) return rc;
+  mb_plain_reads dev;
+  rc = mb::upload_plain(ctx, plain_host, &dev);                         // H2D of the decoded records
+  mb_dev_reads dr;
+  if (!rc) rc = mb::pack_on_device(ctx, &dev, L, 1, /*staged=*/true, &dr);   // the re-layout, on the GPU
+  mb_layout_destroy(L);
+  if (rc) return rc;
+  void *gl = nullptr, *out = nullptr;
+  rc = mb::ctx_reserve(ctx, 2, sizeof(uint32_t) * (size_t)n_genes, &gl);
+  if (!rc) rc = mb::ctx_reserve(ctx, 3, sizeof(mb_gene_out) * (size_t)n_genes, &out);
+  if (!rc && n_genes) {
+    cudaError_t e = cudaMemcpyAsync(gl, gene_len_host, sizeof(uint32_t) * (size_t)n_genes, cudaMemcpyHostToDevice,
+                                    ctx->stream);
+    if (e != cudaSuccess) rc = mb::fail(MB_ECUDA, "mb_genes_coverage_plain: %s", cudaGetErrorString(e));
+  }
+  if (!rc) rc = mb_genes_coverage_dev(ctx, &dr, (const uint32_t*)gl, n_genes, f, exact_order, (mb_gene_out*)out);
+  if (!rc) {
+    cudaError_t e = cudaSuccess;
+    if (n_genes)
+      e = cudaMemcpyAsync(out_host, out, sizeof(mb_gene_out) * (size_t)n_genes, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) rc = mb::fail(MB_ECUDA, "mb_genes_coverage_plain: %s", cudaGetErrorString(e));
+  }
+  return rc;
+}

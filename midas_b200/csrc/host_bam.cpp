@@ -24,11 +24,25 @@ template <class T>
 struct RawBuf {
   T* p = nullptr;
   size_t n = 0;
+  bool pinned = false;   // page-locked (cudaHostAlloc): the array is about to cross PCIe
   RawBuf() = default;
   RawBuf(const RawBuf&) = delete;
   RawBuf& operator=(const RawBuf&) = delete;
-  ~RawBuf() { free(p); }
-  bool resize(size_t k) { free(p); n = k; p = (T*)malloc((k ? k : 1) * sizeof(T)); return p != nullptr; }
+  ~RawBuf() { release(); }
+  void release() { if (p) { if (pinned) cudaFreeHost(p); else free(p); } p = nullptr; }
+  bool resize(size_t k, bool pin = false) {
+    release();
+    n = k;
+    const size_t bytes = (k ? k : 1) * sizeof(T) + 16;
+    pinned = false;
+    if (pin) {
+      void* q = nullptr;
+      if (cudaHostAlloc(&q, bytes, cudaHostAllocDefault) == cudaSuccess) { p = (T*)q; pinned = true; return true; }
+      cudaGetLastError();   // no device / pin failure: pageable memory
+    }
+    p = (T*)malloc(bytes);
+    return p != nullptr;
+  }
   T* data() { return p; }
   const T* data() const { return p; }
 };
@@ -39,7 +53,7 @@ struct mb_bam {
   RawBuf<int32_t> ref_id, pos, nm, l_qseq;
   RawBuf<uint8_t> mapq, seq, qual;
   RawBuf<uint16_t> flag;
-  std::vector<uint64_t> cigar_off, seq_off;
+  RawBuf<uint64_t> cigar_off, seq_off;
   RawBuf<uint32_t> cigar;
   mb_plain_reads pub;
 };
@@ -83,7 +97,9 @@ int32_t find_nm(const uint8_t* p, const uint8_t* end) {
         if (p + 5 > end) return -1;
         const uint8_t sub = p[0];
         const uint32_t cnt = rd32(p + 1);
-        size_t es = (sub == 'c' || sub == 'C') ? 1 : (sub == 's' || sub == 'S') ? 2 : 4;
+        const size_t es = (sub == 'c' || sub == 'C') ? 1 : (sub == 's' || sub == 'S') ? 2 : 4;
+        const size_t remaining = (size_t)(end - p);
+        if ((size_t)cnt > (remaining - 5) / es) return -1;   // the array would run past the record
         p += 5 + (size_t)cnt * es;
         continue;
       }
@@ -108,8 +124,9 @@ int32_t find_nm(const uint8_t* p, const uint8_t* end) {
 
 }  // namespace
 
-extern "C" int mb_bam_open(const char* path, int n_threads, mb_bam** out) {
+extern "C" int mb_bam_open(const char* path, int n_threads, int flags, mb_bam** out) {
   if (!path || !out) return mb::fail(MB_EINVAL, "mb_bam_open: null argument");
+  const bool pin = (flags & MB_BAM_PINNED) != 0, nib = !(flags & MB_BAM_SEQ_BYTES);
   if (n_threads <= 0) n_threads = (int)std::min<unsigned>(32, std::max(1u, std::thread::hardware_concurrency()));
   const bool timing = getenv("MB_BAM_TIMING") != nullptr;
   auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
@@ -152,7 +169,7 @@ extern "C" int mb_bam_open(const char* path, int n_threads, mb_bam** out) {
     size_t x = off + 12, xend = x + xlen, bsize = 0;
     while (x + 4 <= xend && xend <= raw.size()) {
       const uint16_t slen = rd16(raw.data() + x + 2);
-      if (raw[x] == 66 && raw[x + 1] == 67 && slen == 2) bsize = (size_t)rd16(raw.data() + x + 4) + 1;
+      if (raw[x] == 66 && raw[x + 1] == 67 && slen == 2 && x + 6 <= xend) bsize = (size_t)rd16(raw.data() + x + 4) + 1;
       x += 4 + slen;
     }
     if (!bsize || off + bsize > raw.size() || bsize < (size_t)xlen + 20)
@@ -162,6 +179,8 @@ extern "C" int mb_bam_open(const char* path, int n_threads, mb_bam** out) {
     k.cbeg = xend;
     k.clen = off + bsize - 8 - xend;
     k.isize = rd32(raw.data() + off + bsize - 4);
+    if (k.isize > 65536u)
+      return mb::fail(MB_EMALFORMED, "mb_bam_open: %s: BGZF block at offset %zu claims %u inflated bytes (> 64 KiB)", path, off, k.isize);
     k.dst = total;
     total += k.isize;
     blks.push_back(k);
@@ -172,14 +191,15 @@ extern "C" int mb_bam_open(const char* path, int n_threads, mb_bam** out) {
   // 2. inflate in parallel
   RawBuf<uint8_t> data;
   if (!data.resize(total + 8)) return mb::fail(MB_ENOMEM, "mb_bam_open: out of memory");
-  std::vector<int> bad((size_t)n_threads + 1, 0);
+  std::atomic<int> bad_flag{0};
+  std::atomic<int>* bad = &bad_flag;
   pfor(blks.size(), n_threads, [&](size_t lo, size_t hi) {
     for (size_t i = lo; i < hi; ++i) {
       const Blk& k = blks[i];
       if (!k.isize) continue;
       z_stream zs;
       memset(&zs, 0, sizeof(zs));
-      if (inflateInit2(&zs, -15) != Z_OK) { bad[0] = 1; return; }
+      if (inflateInit2(&zs, -15) != Z_OK) { bad->store(1); return; }
       zs.next_in = const_cast<uint8_t*>(raw.data()) + k.cbeg;
       zs.avail_in = (uInt)k.clen;
       zs.next_out = data.data() + k.dst;
@@ -188,10 +208,10 @@ extern "C" int mb_bam_open(const char* path, int n_threads, mb_bam** out) {
       const bool ok = rc == Z_STREAM_END && zs.total_out == k.isize &&
                       (crc32(0L, data.data() + k.dst, k.isize) == rd32(raw.data() + k.off + (k.cbeg - k.off) + k.clen));
       inflateEnd(&zs);
-      if (!ok) { bad[0] = 1; return; }
+      if (!ok) { bad->store(1); return; }
     }
   });
-  if (bad[0]) return mb::fail(MB_EMALFORMED, "mb_bam_open: %s: BGZF inflate / CRC failure", path);
+  if (bad->load()) return mb::fail(MB_EMALFORMED, "mb_bam_open: %s: BGZF inflate / CRC failure", path);
   raw.release();
   phase("inflate");
   // 3. header
@@ -228,19 +248,21 @@ extern "C" int mb_bam_open(const char* path, int n_threads, mb_bam** out) {
       if ((uint32_t)rid >= n_ref) { delete B; return mb::fail(MB_EMALFORMED, "mb_bam_open: %s: refID %d out of range", path, rid); }
       rec.push_back(o);
       coff.push_back(coff.back() + n_cig);
-      soff.push_back(soff.back() + l_seq);
+      soff.push_back(soff.back() + (nib ? ((uint64_t)l_seq + 1) & ~1ull : (uint64_t)l_seq));   // nibbles: whole bytes per read
     }
     o += 4 + bs;
   }
   phase("records");
   const size_t n = rec.size();
-  if (!(B->ref_id.resize(n) && B->pos.resize(n) && B->nm.resize(n) && B->l_qseq.resize(n) && B->mapq.resize(n) &&
-        B->flag.resize(n) && B->cigar.resize(coff.back()) && B->seq.resize(soff.back()) && B->qual.resize(soff.back()))) {
+  if (!(B->ref_id.resize(n, pin) && B->pos.resize(n, pin) && B->nm.resize(n, pin) && B->l_qseq.resize(n, pin) &&
+        B->mapq.resize(n, pin) && B->flag.resize(n) && B->cigar.resize(coff.back(), pin) &&
+        B->seq.resize(nib ? (soff.back() + 1) / 2 : soff.back(), pin) && B->qual.resize(soff.back(), pin) &&
+        B->cigar_off.resize(n + 1, pin) && B->seq_off.resize(n + 1, pin))) {
     delete B;
     return mb::fail(MB_ENOMEM, "mb_bam_open: out of memory");
   }
-  B->cigar_off = std::move(coff);
-  B->seq_off = std::move(soff);
+  memcpy(B->cigar_off.data(), coff.data(), sizeof(uint64_t) * (n + 1));
+  memcpy(B->seq_off.data(), soff.data(), sizeof(uint64_t) * (n + 1));
   // 5. parallel decode
   pfor(n, n_threads, [&](size_t lo, size_t hi) {
     for (size_t i = lo; i < hi; ++i) {
@@ -253,12 +275,17 @@ extern "C" int mb_bam_open(const char* path, int n_threads, mb_bam** out) {
       B->flag.p[i] = rd16(r + 14);
       B->l_qseq.p[i] = (int32_t)l_seq;
       const uint8_t* q = r + 32 + l_name;
-      memcpy(B->cigar.data() + B->cigar_off[i], q, 4 * (size_t)n_cig);
+      memcpy(B->cigar.data() + B->cigar_off.p[i], q, 4 * (size_t)n_cig);
       q += 4 * (size_t)n_cig;
-      uint8_t* s = B->seq.data() + B->seq_off[i];
-      for (uint32_t k = 0; k < l_seq; ++k) s[k] = (k & 1) ? (q[k >> 1] & 15) : (q[k >> 1] >> 4);
+      if (nib) {
+        memcpy(B->seq.data() + (B->seq_off.p[i] >> 1), q, (l_seq + 1) / 2);     // as in the file: two codes per byte
+      } else {
+        uint8_t* s = B->seq.data() + B->seq_off.p[i];
+        for (uint32_t k = 0; k < l_seq; ++k) s[k] = (k & 1) ? (q[k >> 1] & 15) : (q[k >> 1] >> 4);
+      }
       q += (l_seq + 1) / 2;
-      memcpy(B->qual.data() + B->seq_off[i], q, l_seq);
+      memcpy(B->qual.data() + B->seq_off.p[i], q, l_seq);
+      if (nib && (l_seq & 1)) B->qual.p[B->seq_off.p[i] + l_seq] = 0;            // the pad element of an odd read
       q += l_seq;
       B->nm.p[i] = find_nm(q, r + bs);
     }
@@ -275,6 +302,8 @@ extern "C" int mb_bam_open(const char* path, int n_threads, mb_bam** out) {
   B->pub.seq_off = B->seq_off.data();
   B->pub.seq = B->seq.data();
   B->pub.qual = B->qual.data();
+  B->pub.seq_nibbles = nib ? 1u : 0u;
+  B->pub.reserved = 0;
   *out = B;
   return MB_OK;
 }

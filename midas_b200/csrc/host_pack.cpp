@@ -51,6 +51,7 @@ extern "C" int mb_layout_create(const mb_ref* ref, mb_layout** out) {
     return mb::fail(MB_EINVAL, "mb_layout_create: contigs without species");
   mb_layout* L = new mb_layout();
   L->id = g_layout_id.fetch_add(1);
+  L->genes_only = false;
   L->n_contigs = ref->n_contigs;
   L->n_species = ref->n_species;
   L->contig_len.assign(ref->contig_len, ref->contig_len + ref->n_contigs);
@@ -93,12 +94,34 @@ extern "C" int mb_layout_create(const mb_ref* ref, mb_layout** out) {
     L->contig_goff[c] = (uint32_t)next[s];
     next[s] += ref->contig_len[c];
   }
+  // contigs in global-coordinate order (species-major, given order inside a species)
+  L->order.resize(ref->n_contigs);
+  std::iota(L->order.begin(), L->order.end(), 0u);
+  std::stable_sort(L->order.begin(), L->order.end(),
+                   [&](uint32_t a, uint32_t b) { return L->contig_species[a] < L->contig_species[b]; });
+  L->identity_order = true;
+  for (uint32_t c = 0; c < ref->n_contigs; ++c) L->identity_order = L->identity_order && L->order[c] == c;
   L->tile_species.assign(L->n_tiles, -1);
   for (uint32_t s = 0; s < ref->n_species; ++s) {
     uint32_t t0 = L->species_goff[s] / MB_TILE;
     uint32_t t1 = (uint32_t)((L->species_goff[s] + L->species_len[s] + MB_TILE - 1) / MB_TILE);
     for (uint32_t t = t0; t < t1; ++t) L->tile_species[t] = (int32_t)s;
   }
+  *out = L;
+  return MB_OK;
+}
+
+extern "C" int mb_layout_create_genes(uint32_t n_genes, mb_layout** out) {
+  if (!out) return mb::fail(MB_EINVAL, "mb_layout_create_genes: null argument");
+  mb_layout* L = new mb_layout();
+  L->id = g_layout_id.fetch_add(1);
+  L->genes_only = true;
+  L->n_contigs = n_genes;
+  L->n_species = 0;
+  L->gpad = 0;
+  L->n_tiles = 0;
+  L->identity_order = true;
+  L->species_goff.assign(1, 0);
   *out = L;
   return MB_OK;
 }
@@ -130,8 +153,10 @@ int analyse(const mb_plain_reads* in, const mb_layout* L, int mode, uint64_t i, 
                                (unsigned long long)i, (long long)lq);
   if (lq > 65535) return mb::fail(MB_EOVERFLOW, "read %llu: l_qseq=%lld exceeds the 65535-base short-read limit",
                                   (unsigned long long)i, (long long)lq);
-  if ((int64_t)(in->seq_off[i + 1] - in->seq_off[i]) != lq)
-    return mb::fail(MB_EMALFORMED, "read %llu: seq_off span != l_qseq", (unsigned long long)i);
+  if ((int64_t)(in->seq_off[i + 1] - in->seq_off[i]) < lq)
+    return mb::fail(MB_EMALFORMED, "read %llu: seq_off span < l_qseq", (unsigned long long)i);
+  if (in->seq_nibbles && (in->seq_off[i] & 1))
+    return mb::fail(MB_EMALFORMED, "read %llu: seq_off must be even with seq_nibbles", (unsigned long long)i);
   if (in->nm[i] < 0)
     return mb::fail(MB_EINVAL, "read %llu: NM tag missing (reference: KeyError snps.py:148)", (unsigned long long)i);
   if (in->qual[in->seq_off[i]] == 0xFF)
@@ -231,15 +256,15 @@ int analyse(const mb_plain_reads* in, const mb_layout* L, int mode, uint64_t i, 
     g->flags |= MB_RF_SIMPLE;
   } else {
     g->q_start = (uint16_t)lead;
-    g->n_cplx_words = 1 + 2 * (uint32_t)n_match_ops;  // upper bound; runs past the contig end are dropped
+    g->n_cplx_words = (uint32_t)n_cig;  // the raw CIGAR words: the kernels walk them
   }
   return MB_OK;
 }
 
-// Write the run record of a complex read: {n_runs, then per M/=/X run two words
-// (q0 | len << 16, x0)} = query index of the run's first base, its length, and its reference
-// offset from the read's start; clipped at the contig end. Returns words written.
-uint32_t write_cplx(const uint32_t* cig, int64_t n_cig, int64_t room /* contig_len - pos */, uint32_t* dst) {
+// The M/=/X runs of a read after clipping at the contig end: dst = {n_runs, then for the first two runs
+// (q0 | len << 16, x0)} = query index of the run's first base, its length, and its reference offset from
+// the read's start.
+void count_runs(const uint32_t* cig, int64_t n_cig, int64_t room /* contig_len - pos */, uint32_t* dst) {
   uint32_t n = 0;
   int64_t q = 0, r = 0;
   for (int64_t k = 0; k < n_cig && r < room; ++k) {
@@ -248,8 +273,10 @@ uint32_t write_cplx(const uint32_t* cig, int64_t n_cig, int64_t room /* contig_l
     if (op == mb::OP_M || op == mb::OP_EQ || op == mb::OP_X) {
       int64_t take = std::min<int64_t>(len, room - r);
       if (take > 0) {
-        dst[1 + 2 * n] = (uint32_t)q | ((uint32_t)take << 16);
-        dst[2 + 2 * n] = (uint32_t)r;
+        if (n < 2) {
+          dst[1 + 2 * n] = (uint32_t)q | ((uint32_t)take << 16);
+          dst[2 + 2 * n] = (uint32_t)r;
+        }
         ++n;
       }
       q += len;
@@ -261,7 +288,6 @@ uint32_t write_cplx(const uint32_t* cig, int64_t n_cig, int64_t room /* contig_l
     }
   }
   dst[0] = n;
-  return 1 + 2 * n;
 }
 
 constexpr uint64_t kLsb = 0x0101010101010101ull;
@@ -312,6 +338,7 @@ extern "C" int mb_pack_reads(const mb_plain_reads* in, const mb_layout* L, int m
                              int n_threads, mb_packed_reads** out) {
   if (!in || !L || !out) return mb::fail(MB_EINVAL, "mb_pack_reads: null argument");
   if (mode != 0 && mode != 1) return mb::fail(MB_EINVAL, "mb_pack_reads: mode must be 0 (snps) or 1 (genes)");
+  if (mode == 0 && L->genes_only) return mb::fail(MB_EINVAL, "mb_pack_reads: snps mode needs a layout with coordinates");
   const uint64_t n = in->n_reads;
   if (n >= 0xFFFFFFFFull) return mb::fail(MB_EOVERFLOW, "mb_pack_reads: more than 2^32-2 reads in one batch");
   if (n_threads <= 0) n_threads = (int)std::min<unsigned>(32, std::max(1u, std::thread::hardware_concurrency()));
@@ -473,11 +500,11 @@ extern "C" int mb_pack_reads(const mb_plain_reads* in, const mb_layout* L, int m
         const uint32_t* cig = in->cigar + in->cigar_off[i];
         const int64_t n_cig = (int64_t)(in->cigar_off[i + 1] - in->cigar_off[i]);
         const int64_t room = (int64_t)L->contig_len[in->ref_id[i]] - in->pos[i];
-        uint32_t* rec = cigar + cg_off[j];
-        uint32_t w = write_cplx(cig, n_cig, room, rec);
-        for (uint32_t q = w; q < g.n_cplx_words; ++q) rec[q] = 0;
+        memcpy(cigar + cg_off[j], cig, sizeof(uint32_t) * (size_t)n_cig);   // raw ops, walked by the kernels
         cplx[j] = cg_off[j];
-        // the common indel read = two runs: carried in the cplx word itself (no record fetch)
+        // the common indel read = two runs (after clipping at the contig end): carried in the cplx word itself
+        uint32_t rec[5] = {0, 0, 0, 0, 0};
+        count_runs(cig, n_cig, room, rec);
         if (rec[0] == 2) {
           const uint32_t q0 = rec[1] & 0xffffu, len0 = rec[1] >> 16, x0 = rec[2];
           const uint32_t q1 = rec[3] & 0xffffu, len1 = rec[3] >> 16, x1 = rec[4];
@@ -502,7 +529,12 @@ extern "C" int mb_pack_reads(const mb_plain_reads* in, const mb_layout* L, int m
         uint32_t w[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};        // lo, hi, acgt, Phred bits 0..6
         const uint32_t nk = std::min<uint32_t>(MB_BLOCK, lq - b * MB_BLOCK);
         uint8_t sb[MB_BLOCK] = {0}, qb[MB_BLOCK] = {0};          // the block's bases, zero padded
-        memcpy(sb, s + b * MB_BLOCK, nk);
+        if (in->seq_nibbles) {                                   // two codes per byte, even element in the high nibble
+          const uint8_t* s4 = in->seq + (in->seq_off[i] >> 1) + b * (MB_BLOCK / 2);
+          for (uint32_t k = 0; k < nk; ++k) sb[k] = (k & 1) ? (s4[k >> 1] & 15) : (s4[k >> 1] >> 4);
+        } else {
+          memcpy(sb, s + b * MB_BLOCK, nk);
+        }
         memcpy(qb, q + b * MB_BLOCK, nk);
         for (uint32_t part = 0; part < 4; ++part) {              // eight bases at a time, byte-parallel in a u64
           uint64_t sw, qw;

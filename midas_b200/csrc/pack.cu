@@ -1,0 +1,711 @@
+// Device packer: decoded BAM records (mb_plain_reads) -> the packed struct-of-arrays the pileup kernels
+// stream (mb_packed_reads layout, include/midas_b200.h), entirely on the GPU.
+//
+// This is the step pysam/htslib performs for the reference before its loops see an AlignedSegment
+// (reference midas/run/snps.py:186,194; midas/run/genes.py:175-180): per read the two CIGAR-only
+// quantities keep_read needs (alen = len(query_alignment_sequence) snps.py:145, query_length :146),
+// validation of the inputs on which the reference raises, and the re-layout. csrc/host_pack.cpp is the
+// host version of the same re-layout; tests/test_pack_gpu.py holds the two byte-identical.
+//
+//   k_pack_blocks    contig -> range of reads (binary search in the coordinate-sorted ref_id column) and
+//                    where that block goes in layout order: a BAM is sorted by (tid, pos), the layout is
+//                    species-major, so whole contigs move and nothing is sorted
+//   k_pack_analyse   one thread per record: CIGAR walk (alen, q_start, ref_span clipped at the contig end,
+//                    single-indel run word), validation, 16-byte header, need-words histogram
+//   k_pack_qor       OR of every quality byte (6 or 7 Phred planes; a byte above 127 is an error)
+//   k_pack_finish    row width of the tile kernel (all but 0.1 % of the reads fit), plane counts
+//   k_pack_units / k_pack_scan{1,2,3}  32-byte units per group of 32 reads -> vec_off (exclusive scan)
+//   k_pack_long      MB_RF_LONG flags + their index list
+//   k_pack_fill      one warp per read, one lane per base: every plane word of a 32-base block is one
+//                    __ballot_sync (sequence low / high bit, candidate, Phred bits), zero padding included
+#include <cstdio>
+#include <cstring>
+
+#include "common.h"
+
+namespace {
+
+enum PackErr : uint32_t {
+  PE_NONE = 0, PE_LQ0, PE_LQBIG, PE_SEQOFF, PE_NM, PE_NOQUAL, PE_NCIG, PE_OP, PE_QSUM, PE_ALEN0, PE_REFID, PE_POS,
+  PE_SPAN, PE_CIGOFF, PE_SEQALIGN
+};
+
+struct PackMeta {
+  unsigned long long err;          // min over failing records of (index << 8 | PackErr); ~0 = none
+  unsigned long long total_bases;
+  unsigned long long n_vec;
+  unsigned long long n_cig;        // cigar_off[n]
+  uint32_t unsorted, q_or, max_span, n_long, row_words, q_planes, n_planes, long_fill;
+  uint32_t hist[256];
+};
+
+struct Plain {  // device view of mb_plain_reads
+  uint64_t n;
+  const int32_t *ref_id, *pos, *nm, *l_qseq;
+  const uint8_t* mapq;
+  const uint64_t *cigar_off, *seq_off;
+  const uint32_t* cigar;
+  const uint8_t *seq, *qual;
+  uint32_t nib;
+};
+
+__device__ __forceinline__ void report(PackMeta* m, uint64_t i, uint32_t code) {
+  atomicMin(&m->err, (unsigned long long)((i << 8) | code));
+}
+
+// ---- contig blocks: source range of every contig and its destination in layout order (one block)
+__global__ void __launch_bounds__(1024) k_pack_blocks(const int32_t* __restrict__ ref_id, uint64_t n, uint32_t n_contigs,
+                                                      const uint32_t* __restrict__ order, uint32_t* blk_src,
+                                                      uint32_t* blk_dst) {
+  __shared__ unsigned long long s_scan[1024];
+  __shared__ unsigned long long s_carry;
+  for (uint32_t c = threadIdx.x; c < n_contigs; c += blockDim.x) {
+    uint64_t lo = 0, hi = n;
+    while (lo < hi) { const uint64_t mid = lo + ((hi - lo) >> 1); if (ref_id[mid] < (int32_t)c) lo = mid + 1; else hi = mid; }
+    const uint64_t a = lo;
+    hi = n;
+    while (lo < hi) { const uint64_t mid = lo + ((hi - lo) >> 1); if (ref_id[mid] <= (int32_t)c) lo = mid + 1; else hi = mid; }
+    blk_src[c] = (uint32_t)a;
+    blk_dst[c] = (uint32_t)(lo - a);   // count for now
+  }
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (uint32_t base = 0; base < n_contigs; base += blockDim.x) {
+    const uint32_t k = base + threadIdx.x;
+    const uint32_t c = k < n_contigs ? order[k] : 0u;
+    const unsigned long long v = k < n_contigs ? blk_dst[c] : 0ull;
+    s_scan[threadIdx.x] = v;
+    __syncthreads();
+    for (uint32_t o = 1; o < blockDim.x; o <<= 1) {
+      const unsigned long long t = threadIdx.x >= o ? s_scan[threadIdx.x - o] : 0ull;
+      __syncthreads();
+      s_scan[threadIdx.x] += t;
+      __syncthreads();
+    }
+    const unsigned long long incl = s_scan[threadIdx.x], carry = s_carry;
+    __syncthreads();
+    if (k < n_contigs) blk_dst[c] = (uint32_t)(carry + incl - v);
+    if (threadIdx.x == blockDim.x - 1) s_carry = carry + incl;
+    __syncthreads();
+  }
+}
+
+// ---- per record: geometry + validation (the checks and their order follow host_pack.cpp::analyse)
+template <int MODE>
+__global__ void __launch_bounds__(256) k_pack_analyse(const Plain in, const uint32_t n_contigs,
+                                                      const uint32_t* __restrict__ contig_len,
+                                                      const uint32_t* __restrict__ contig_goff,
+                                                      const uint32_t* __restrict__ blk_src,
+                                                      const uint32_t* __restrict__ blk_dst, uint4* hdr, uint32_t* cplx,
+                                                      uint32_t* src_of, uint16_t* nblk, uint8_t* need, PackMeta* meta) {
+  __shared__ uint32_t s_hist[256];
+  __shared__ unsigned long long s_bases;
+  __shared__ uint32_t s_span;
+  for (int k = threadIdx.x; k < 256; k += blockDim.x) s_hist[k] = 0;
+  if (threadIdx.x == 0) { s_bases = 0; s_span = 0; }
+  __syncthreads();
+  unsigned long long my_bases = 0;
+  uint32_t my_span = 0;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < in.n; i += stride) {
+    const int64_t lq = in.l_qseq[i];
+    const int32_t rid = in.ref_id[i];
+    const int64_t pos = in.pos[i];
+    if (MODE == 0 && i > 0) {   // BAM coordinate order
+      const int32_t prid = in.ref_id[i - 1];
+      if (prid > rid || (prid == rid && (int64_t)in.pos[i - 1] > pos)) meta->unsorted = 1;
+    }
+    if (lq <= 0) { report(meta, i, PE_LQ0); continue; }
+    if (lq > 65535) { report(meta, i, PE_LQBIG); continue; }
+    const uint64_t so = in.seq_off[i];
+    if ((int64_t)(in.seq_off[i + 1] - so) < lq) { report(meta, i, PE_SEQOFF); continue; }
+    if (in.nib && (so & 1)) { report(meta, i, PE_SEQALIGN); continue; }
+    const int32_t nm_raw = in.nm[i];
+    if (nm_raw < 0) { report(meta, i, PE_NM); continue; }
+    if (in.qual[so] == 0xFF) { report(meta, i, PE_NOQUAL); continue; }
+    const uint64_t co = in.cigar_off[i];
+    const int64_t n_cig = (int64_t)(in.cigar_off[i + 1] - co);
+    if (n_cig > 65535) { report(meta, i, PE_NCIG); continue; }
+    if (co + (uint64_t)n_cig > 0xFFFFFFF0ull) { report(meta, i, PE_CIGOFF); continue; }
+    const uint32_t* __restrict__ cig = in.cigar + co;
+    int64_t qsum = 0, span = 0, n_match = 0, n_other = 0, lead = 0;
+    bool bad_op = false, in_lead = true;
+    for (int64_t k = 0; k < n_cig; ++k) {
+      const uint32_t w = cig[k], op = w & 15u;
+      const int64_t len = w >> 4;
+      if (op == mb::OP_P || op > mb::OP_X) { bad_op = true; break; }
+      if (op == mb::OP_M || op == mb::OP_EQ || op == mb::OP_X) { qsum += len; span += len; ++n_match; }
+      else if (op == mb::OP_I) { qsum += len; ++n_other; }
+      else if (op == mb::OP_S) { qsum += len; }
+      else if (op == mb::OP_D || op == mb::OP_N) { span += len; ++n_other; }
+      // pysam getQueryStart: soft clips before the first op that is neither S nor H
+      if (in_lead) { if (op == mb::OP_S) lead += len; else if (op != mb::OP_H) in_lead = false; }
+    }
+    if (bad_op) { report(meta, i, PE_OP); continue; }
+    if (n_cig > 0 && qsum != lq) { report(meta, i, PE_QSUM); continue; }
+    int64_t trail = 0;   // pysam getQueryEnd: the walk from the end never visits op 0
+    for (int64_t k = n_cig - 1; k >= 1; --k) {
+      const uint32_t op = cig[k] & 15u;
+      if (op == mb::OP_H) continue;
+      if (op == mb::OP_S) trail += cig[k] >> 4; else break;
+    }
+    const int64_t alen = lq - lead - trail;
+    if (alen <= 0) { report(meta, i, PE_ALEN0); continue; }
+    uint32_t flags = 0;
+    uint32_t nm = (uint32_t)nm_raw;
+    if (nm > 65535u) { nm = 65535u; flags |= MB_RF_NMSAT; }
+    if (rid < 0 || (uint32_t)rid >= n_contigs) { report(meta, i, PE_REFID); continue; }
+    uint32_t loc, ref_span = 0, cw = 0xFFFFFFFFu, need_w = 0;
+    uint64_t j = i;
+    if (MODE == 1) {
+      loc = (uint32_t)rid;
+      flags |= MB_RF_SIMPLE;
+    } else {
+      const int64_t clen = contig_len[rid];
+      if (pos < 0 || pos >= clen) { report(meta, i, PE_POS); continue; }
+      loc = contig_goff[rid] + (uint32_t)pos;
+      const int64_t room = clen - pos;
+      const int64_t sc = span < room ? span : room;   // pysam ignores refpos >= contig_len
+      if (sc > 65535) { report(meta, i, PE_SPAN); continue; }
+      ref_span = (uint32_t)sc;
+      const int64_t by_span = ((int64_t)(loc & 31u) + sc + 31) / 32, by_query = (lq + 31) / 32;
+      const int64_t nw = by_span > by_query ? by_span : by_query;
+      need_w = (uint32_t)(nw > 255 ? 255 : nw);
+      if (n_other == 0 && n_match <= 1) {
+        flags |= MB_RF_SIMPLE;
+      } else {
+        // the runs after clipping at the contig end: exactly two of the single-indel shape ride in the word
+        int64_t q = 0, r = 0;
+        uint32_t n_runs = 0, q0 = 0, len0 = 0, x0 = 0, q1 = 0, len1 = 0, x1 = 0;
+        for (int64_t k = 0; k < n_cig && r < room; ++k) {
+          const uint32_t w = cig[k], op = w & 15u;
+          const int64_t len = w >> 4;
+          if (op == mb::OP_M || op == mb::OP_EQ || op == mb::OP_X) {
+            const int64_t take = len < room - r ? len : room - r;
+            if (take > 0) {
+              if (n_runs == 0) { q0 = (uint32_t)q; len0 = (uint32_t)take; x0 = (uint32_t)r; }
+              else if (n_runs == 1) { q1 = (uint32_t)q; len1 = (uint32_t)take; x1 = (uint32_t)r; }
+              ++n_runs;
+            }
+            q += len; r += len;
+          } else if (op == mb::OP_I || op == mb::OP_S) q += len;
+          else if (op == mb::OP_D || op == mb::OP_N) r += len;
+        }
+        cw = (uint32_t)co;
+        if (n_runs == 2) {
+          const int64_t ins = (int64_t)q1 - (int64_t)(q0 + len0), del = (int64_t)x1 - (int64_t)len0;
+          if (q0 == (uint32_t)lead && x0 == 0 && ins >= 0 && ins <= 255 && del >= 0 && del <= 255 &&
+              x1 + len1 == ref_span) {
+            cw = len0 | ((uint32_t)ins << 16) | ((uint32_t)del << 24);
+            flags |= MB_RF_RUNS2;
+          }
+        }
+      }
+      j = (uint64_t)blk_dst[rid] + (i - (uint64_t)blk_src[rid]);
+      if (j >= in.n) { meta->unsorted = 1; continue; }   // ref_id column not ascending: the block table is meaningless
+    }
+    hdr[j] = make_uint4(loc, (uint32_t)lq | ((uint32_t)alen << 16), (uint32_t)lead | (nm << 16),
+                        ref_span | ((uint32_t)in.mapq[i] << 16) | (flags << 24));
+    cplx[j] = cw;
+    src_of[j] = (uint32_t)i;
+    nblk[j] = (uint16_t)((lq + MB_BLOCK - 1) / MB_BLOCK);
+    if (MODE == 0) { need[j] = (uint8_t)need_w; atomicAdd(&s_hist[need_w], 1u); }
+    my_bases += (unsigned long long)lq;
+    my_span = max(my_span, ref_span);
+  }
+  atomicAdd(&s_bases, my_bases);
+  atomicMax(&s_span, my_span);
+  __syncthreads();
+  if (MODE == 0)
+    for (int k = threadIdx.x; k < 256; k += blockDim.x)
+      if (s_hist[k]) atomicAdd(&meta->hist[k], s_hist[k]);
+  if (threadIdx.x == 0) {
+    if (s_bases) atomicAdd(&meta->total_bases, s_bases);
+    if (s_span) atomicMax(&meta->max_span, s_span);
+  }
+}
+
+// ---- OR of every quality byte of every record: one warp per record, aligned 32-bit words, ends masked
+__global__ void __launch_bounds__(256) k_pack_qor(const Plain in, PackMeta* meta) {
+  const int lane = threadIdx.x & 31;
+  const uint64_t wg = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  uint32_t acc = 0;
+  for (uint64_t i = wg; i < in.n; i += nw) {
+    const int64_t lq = in.l_qseq[i];
+    if (lq <= 0 || lq > 65535) continue;
+    const uintptr_t a0 = (uintptr_t)(in.qual + in.seq_off[i]), a1 = a0 + (uintptr_t)lq;
+    const uintptr_t w0 = a0 & ~(uintptr_t)3, w1 = (a1 + 3) & ~(uintptr_t)3;
+    for (uintptr_t w = w0 + 4 * (uintptr_t)lane; w < w1; w += 128) {
+      uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(w));
+      if (w < a0) v &= 0xffffffffu << (8 * (uint32_t)(a0 - w));
+      if (w + 4 > a1) v &= 0xffffffffu >> (8 * (uint32_t)(w + 4 - a1));
+      acc |= v;
+    }
+  }
+  acc |= acc >> 16;
+  acc |= acc >> 8;
+  acc &= 0xffu;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc |= __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0 && acc) atomicOr(&meta->q_or, acc);
+}
+
+// ---- row width: the smallest W that all but 0.1 % of the reads fit (as host_pack.cpp); plane counts
+__global__ void k_pack_finish(PackMeta* meta, uint64_t n, int mode, const uint64_t* __restrict__ cigar_off) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  meta->n_cig = n ? cigar_off[n] : 0ull;
+  const uint32_t q_planes = (meta->q_or & 0x40u) ? 7u : 6u;
+  meta->q_planes = q_planes;
+  meta->n_planes = mode == 0 ? 3u + q_planes : q_planes;
+  uint32_t row_words = 0;
+  unsigned long long n_long = 0;
+  if (mode == 0) {
+    unsigned long long above = 0;
+    for (int w = 255; w > (int)MB_ROW_WORDS_MAX; --w) above += meta->hist[w];
+    row_words = MB_ROW_WORDS_MAX;
+    for (uint32_t w = MB_ROW_WORDS_MAX; w > 2; --w) {
+      if (above + meta->hist[w] > n / 1000) break;
+      above += meta->hist[w];
+      row_words = w - 1;
+    }
+    for (int w = (int)row_words + 1; w < 256; ++w) n_long += meta->hist[w];
+  }
+  meta->row_words = row_words;
+  meta->n_long = (uint32_t)n_long;
+}
+
+// ---- 32-byte units per read of a group (= the largest of its 32 reads): one warp per group
+__global__ void __launch_bounds__(256) k_pack_units(const uint16_t* __restrict__ nblk, uint64_t n, uint64_t n_groups,
+                                                    const PackMeta* __restrict__ meta, uint32_t* g_units) {
+  const uint32_t NP = meta->n_planes;
+  const int lane = threadIdx.x & 31;
+  const uint64_t wg = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for (uint64_t g = wg; g < n_groups; g += nw) {
+    const uint64_t j = g * MB_GROUP + lane;
+    uint32_t u = j < n ? ((uint32_t)nblk[j] * NP + 7u) / 8u : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) u = max(u, __shfl_xor_sync(0xffffffffu, u, o));
+    if (lane == 0) g_units[g] = u;
+  }
+}
+
+constexpr int SCAN_T = 1024, SCAN_PER = 4, SCAN_CHUNK = SCAN_T * SCAN_PER;
+
+__device__ __forceinline__ unsigned long long block_incl_scan(unsigned long long v, unsigned long long* s_warp) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += t;
+  }
+  if (lane == 31) s_warp[wid] = v;
+  __syncthreads();
+  if (wid == 0) {
+    unsigned long long w = lane < (int)(blockDim.x >> 5) ? s_warp[lane] : 0ull;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long t = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += t;
+    }
+    s_warp[lane] = w;
+  }
+  __syncthreads();
+  const unsigned long long r = v + (wid ? s_warp[wid - 1] : 0ull);
+  __syncthreads();
+  return r;
+}
+
+__global__ void __launch_bounds__(SCAN_T) k_pack_scan1(const uint32_t* __restrict__ g_units, uint64_t n_groups,
+                                                       unsigned long long* bsum) {
+  __shared__ unsigned long long s_warp[32];
+  const uint64_t base = (uint64_t)blockIdx.x * SCAN_CHUNK + (uint64_t)threadIdx.x * SCAN_PER;
+  unsigned long long v = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_PER; ++k) if (base + k < n_groups) v += g_units[base + k];
+  const unsigned long long incl = block_incl_scan(v, s_warp);
+  if (threadIdx.x == SCAN_T - 1) bsum[blockIdx.x] = incl;
+}
+
+__global__ void __launch_bounds__(SCAN_T) k_pack_scan2(unsigned long long* bsum, uint32_t n_blocks, PackMeta* meta) {
+  __shared__ unsigned long long s_warp[32];
+  __shared__ unsigned long long s_carry;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (uint32_t base = 0; base < n_blocks; base += SCAN_T) {
+    const uint32_t k = base + threadIdx.x;
+    const unsigned long long v = k < n_blocks ? bsum[k] : 0ull;
+    const unsigned long long incl = block_incl_scan(v, s_warp);
+    const unsigned long long carry = s_carry;
+    __syncthreads();
+    if (k < n_blocks) bsum[k] = carry + incl - v;
+    if (threadIdx.x == SCAN_T - 1) s_carry = carry + incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) meta->n_vec = s_carry * MB_GROUP;
+}
+
+// vec_off[j] = 32 * (units of all groups before j's) + j % 32; vec_off[n] = n_vec
+__global__ void __launch_bounds__(SCAN_T) k_pack_scan3(const uint32_t* __restrict__ g_units, uint64_t n_groups,
+                                                       const unsigned long long* __restrict__ bpre, uint64_t n,
+                                                       const PackMeta* __restrict__ meta, uint32_t* vec_off) {
+  __shared__ unsigned long long s_warp[32];
+  const uint64_t base = (uint64_t)blockIdx.x * SCAN_CHUNK + (uint64_t)threadIdx.x * SCAN_PER;
+  unsigned long long u[SCAN_PER], v = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_PER; ++k) { u[k] = base + k < n_groups ? g_units[base + k] : 0u; v += u[k]; }
+  unsigned long long excl = block_incl_scan(v, s_warp) - v + bpre[blockIdx.x];
+#pragma unroll
+  for (int k = 0; k < SCAN_PER; ++k) {
+    const uint64_t g = base + k;
+    if (g < n_groups) {
+      const uint64_t j0 = g * MB_GROUP, j1 = min(n, j0 + MB_GROUP);
+      for (uint64_t j = j0; j < j1; ++j) vec_off[j] = (uint32_t)(excl * MB_GROUP + (j - j0));
+    }
+    excl += u[k];
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) vec_off[n] = (uint32_t)meta->n_vec;
+}
+
+__global__ void __launch_bounds__(256) k_pack_long(const uint8_t* __restrict__ need, uint64_t n, PackMeta* meta,
+                                                   uint4* hdr, uint32_t* long_idx) {
+  const uint32_t rw = meta->row_words;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+    if (need[j] > rw) {
+      hdr[j].w |= (uint32_t)MB_RF_LONG << 24;
+      long_idx[atomicAdd(&meta->long_fill, 1u)] = (uint32_t)j;
+    }
+  }
+}
+
+// ---- the planes: one warp per read, one lane per base of a 32-base block, one ballot per plane word
+template <int MODE>
+__global__ void __launch_bounds__(256) k_pack_fill(const Plain in, const uint4* __restrict__ hdr,
+                                                   const uint32_t* __restrict__ src_of,
+                                                   const uint32_t* __restrict__ vec_off, uint64_t n,
+                                                   const PackMeta* __restrict__ meta, uint32_t* planes) {
+  const uint32_t NQ = meta->q_planes, NP = meta->n_planes, P0 = MODE == 0 ? 3u : 0u;
+  const uint32_t n_vec = (uint32_t)meta->n_vec;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint64_t wg = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for (uint64_t j = wg; j < n; j += nw) {
+    const uint4 h = __ldg(&hdr[j]);
+    const uint64_t i = src_of[j];
+    const uint32_t lq = h.y & 0xffffu, qstart = h.z & 0xffffu, span = h.w & 0xffffu, fl = h.w >> 24;
+    const uint32_t n_blk = (lq + MB_BLOCK - 1) / MB_BLOCK;
+    const uint64_t g0 = (j / MB_GROUP) * MB_GROUP, g1 = g0 + MB_GROUP;
+    const uint32_t units = ((g1 < n ? __ldg(&vec_off[g1]) : n_vec) - __ldg(&vec_off[g0])) / MB_GROUP;
+    uint32_t* __restrict__ reg = planes + (size_t)__ldg(&vec_off[j]) * 8;
+    const uint64_t so = in.seq_off[i];
+    const uint8_t* __restrict__ qp = in.qual + so;
+    const uint32_t* __restrict__ cig = in.cigar + in.cigar_off[i];
+    const bool simple = (fl & MB_RF_SIMPLE) != 0;
+    for (uint32_t b = 0; b < n_blk; ++b) {
+      const uint32_t k = b * MB_BLOCK + lane;
+      const bool valid = k < lq;
+      uint32_t q = 0, nibv = 0;
+      if (valid) {
+        q = qp[k];
+        if (MODE == 0) {
+          const uint64_t e = so + k;
+          nibv = in.nib ? ((uint32_t)in.seq[e >> 1] >> ((e & 1) ? 0 : 4)) & 15u : (uint32_t)in.seq[e] & 15u;
+        }
+      }
+      uint32_t mine = 0;   // lane p keeps plane word p of this block
+      if (MODE == 0) {
+        // BAM nibble -> 2-bit code: A=1 C=2 G=4 T=8 are the nibbles with exactly one bit set
+        const bool acgt = nibv != 0 && (nibv & (nibv - 1)) == 0;
+        bool inrun;
+        if (simple) {
+          inrun = k >= qstart && k < qstart + span;
+        } else {
+          // M/=/X runs, clipped where the reference position reaches ref_span (= the contig end)
+          inrun = false;
+          uint32_t qq = 0, rr = 0;
+          for (uint32_t c = 0; qq < lq; ++c) {
+            const uint32_t w = __ldg(cig + c), op = w & 15u, len = w >> 4;
+            if (op == mb::OP_M || op == mb::OP_EQ || op == mb::OP_X) {
+              const uint32_t take = rr < span ? min(len, span - rr) : 0u;
+              inrun = inrun || (k >= qq && k < qq + take);
+              qq += len; rr += len;
+            } else if (op == mb::OP_I || op == mb::OP_S) qq += len;
+            else if (op == mb::OP_D || op == mb::OP_N) rr += len;
+          }
+        }
+        const uint32_t w0 = __ballot_sync(0xffffffffu, acgt && (nibv & 0xAu));    // C, T
+        const uint32_t w1 = __ballot_sync(0xffffffffu, acgt && (nibv & 0xCu));    // G, T
+        const uint32_t w2 = __ballot_sync(0xffffffffu, acgt && inrun);
+        mine = lane == 0 ? w0 : (lane == 1 ? w1 : (lane == 2 ? w2 : 0u));
+      }
+      for (uint32_t pl = 0; pl < NQ; ++pl) {
+        const uint32_t w = __ballot_sync(0xffffffffu, (q >> pl) & 1u);
+        if (lane == P0 + pl) mine = w;
+      }
+      if (lane < NP) {
+        const uint32_t w = b * NP + lane;
+        reg[(size_t)(w >> 3) * (8 * MB_GROUP) + (w & 7u)] = mine;
+      }
+    }
+    for (uint32_t w = n_blk * NP + lane; w < units * 8; w += 32)      // padding up to the group's units
+      reg[(size_t)(w >> 3) * (8 * MB_GROUP) + (w & 7u)] = 0u;
+  }
+}
+
+const char* pack_err_text(uint32_t code, int* status) {
+  switch (code) {
+    case PE_LQ0: *status = MB_EINVAL; return "l_qseq <= 0 (reference: ZeroDivisionError snps.py:157)";
+    case PE_LQBIG: *status = MB_EOVERFLOW; return "l_qseq exceeds the 65535-base short-read limit";
+    case PE_SEQOFF: *status = MB_EMALFORMED; return "seq_off span < l_qseq";
+    case PE_SEQALIGN: *status = MB_EMALFORMED; return "seq_off must be even with seq_nibbles";
+    case PE_NM: *status = MB_EINVAL; return "NM tag missing (reference: KeyError snps.py:148)";
+    case PE_NOQUAL: *status = MB_EINVAL; return "qualities missing (reference: np.mean(None) snps.py:151)";
+    case PE_NCIG: *status = MB_EOVERFLOW; return "more than 65535 CIGAR ops";
+    case PE_OP: *status = MB_EMALFORMED; return "unsupported CIGAR op";
+    case PE_QSUM: *status = MB_EMALFORMED; return "CIGAR query length != l_qseq";
+    case PE_ALEN0: *status = MB_EINVAL; return "aligned length 0 (reference: ZeroDivisionError snps.py:148)";
+    case PE_REFID: *status = MB_EINVAL; return "ref_id outside the layout";
+    case PE_POS: *status = MB_EMALFORMED; return "pos outside its contig";
+    case PE_SPAN: *status = MB_EOVERFLOW; return "reference span exceeds 65535";
+    case PE_CIGOFF: *status = MB_EOVERFLOW; return "batch too large for 32-bit CIGAR offsets";
+    default: *status = MB_EINVAL; return "invalid record";
+  }
+}
+
+// array `slot` of the packed batch: an own allocation (+256 B of zero slack) or a context staging buffer
+int pack_alloc(mb_ctx* c, bool staged, int slot, size_t bytes, void** out) {
+  if (staged) {
+    int rc = mb::ctx_reserve(c, slot, bytes + 256, out);
+    if (rc) return rc;
+  } else {
+    cudaError_t e = cudaMalloc(out, bytes + 256);
+    if (e != cudaSuccess) return mb::fail(MB_ENOMEM, "mb_reads_pack: cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+  }
+  MB_CUDA_TRY(cudaMemsetAsync((char*)*out + bytes, 0, 256, c->stream));
+  return MB_OK;
+}
+
+}  // namespace
+
+namespace mb {
+
+void free_dev_reads_arrays(mb_dev_reads* d) {
+  if (!d || !d->owned) return;
+  cudaFree(d->hdr); cudaFree(d->vec_off); cudaFree(d->cplx); cudaFree(d->cigar); cudaFree(d->planes); cudaFree(d->long_idx);
+  d->hdr = nullptr; d->vec_off = nullptr; d->cplx = nullptr; d->cigar = nullptr; d->planes = nullptr; d->long_idx = nullptr;
+}
+
+int upload_plain(mb_ctx* c, const mb_plain_reads* h, mb_plain_reads* d) {
+  const uint64_t n = h->n_reads;
+  *d = *h;
+  if (n == 0) return MB_OK;
+  const uint64_t n_cig = h->cigar_off[n], n_el = h->seq_off[n];
+  const size_t seq_bytes = h->seq_nibbles ? (size_t)((n_el + 1) / 2) : (size_t)n_el;
+  struct Part { const void** dst; const void* src; size_t bytes; } parts[10] = {
+      {(const void**)&d->ref_id, h->ref_id, 4 * (size_t)n},       {(const void**)&d->pos, h->pos, 4 * (size_t)n},
+      {(const void**)&d->mapq, h->mapq, (size_t)n},               {(const void**)&d->nm, h->nm, 4 * (size_t)n},
+      {(const void**)&d->l_qseq, h->l_qseq, 4 * (size_t)n},       {(const void**)&d->cigar_off, h->cigar_off, 8 * (size_t)(n + 1)},
+      {(const void**)&d->cigar, h->cigar, 4 * (size_t)n_cig},     {(const void**)&d->seq_off, h->seq_off, 8 * (size_t)(n + 1)},
+      {(const void**)&d->seq, h->seq, seq_bytes},                 {(const void**)&d->qual, h->qual, (size_t)n_el}};
+  int slot = 16;
+  for (auto& p : parts) {
+    void* buf = nullptr;
+    int rc = ctx_reserve(c, slot++, p.bytes + 256, &buf);
+    if (rc) return rc;
+    MB_CUDA_TRY(cudaMemsetAsync((char*)buf + p.bytes, 0, 256, c->stream));
+    if (p.bytes) MB_CUDA_TRY(cudaMemcpyAsync(buf, p.src, p.bytes, cudaMemcpyHostToDevice, c->stream));
+    *p.dst = buf;
+  }
+  return MB_OK;
+}
+
+int pack_on_device(mb_ctx* c, const mb_plain_reads* in, const mb_layout* L, int mode, bool staged, mb_dev_reads* d) {
+  memset(d, 0, sizeof(*d));
+  d->owned = !staged;
+  const uint64_t n = in->n_reads;
+  if (n >= 0xFFFFFFFFull) return mb::fail(MB_EOVERFLOW, "mb_reads_pack: more than 2^32-2 reads in one batch");
+  if (mode == 0 && L->genes_only) return mb::fail(MB_EINVAL, "mb_reads_pack: snps mode needs a layout with coordinates");
+  cudaStream_t st = c->stream;
+  PackMeta* meta = (PackMeta*)c->pack_meta;
+  PackMeta* hm = (PackMeta*)c->pack_meta_host;
+  MB_CUDA_TRY(cudaEventRecord(c->pack_ev[0], st));
+  c->pack_timed = true;
+  const uint64_t n_groups = (n + MB_GROUP - 1) / MB_GROUP;
+  const uint32_t n_sblocks = (uint32_t)((n_groups + SCAN_CHUNK - 1) / SCAN_CHUNK);
+  void *src_of = nullptr, *nblk = nullptr, *need = nullptr, *blk_src = nullptr, *blk_dst = nullptr, *g_units = nullptr,
+       *bsum = nullptr;
+  int rc = ctx_reserve(c, 26, 4 * (size_t)n, &src_of);
+  if (!rc) rc = ctx_reserve(c, 27, 2 * (size_t)n, &nblk);
+  if (!rc) rc = ctx_reserve(c, 28, (size_t)n, &need);
+  if (!rc) rc = ctx_reserve(c, 29, 4 * (size_t)L->n_contigs, &blk_src);
+  if (!rc) rc = ctx_reserve(c, 30, 4 * (size_t)L->n_contigs, &blk_dst);
+  if (!rc) rc = ctx_reserve(c, 31, 4 * (size_t)n_groups, &g_units);
+  if (!rc) rc = ctx_reserve(c, 32, 8 * (size_t)(n_sblocks + 1), &bsum);
+  if (!rc) rc = pack_alloc(c, staged, 33, sizeof(mb_read_hdr) * (size_t)n, (void**)&d->hdr);
+  if (!rc) rc = pack_alloc(c, staged, 34, 4 * (size_t)(n + 1), (void**)&d->vec_off);
+  if (!rc) rc = pack_alloc(c, staged, 35, 4 * (size_t)n, (void**)&d->cplx);
+  if (rc) return rc;
+  PackMeta init;
+  memset(&init, 0, sizeof(init));
+  init.err = ~0ull;
+  *hm = init;   // pinned: the async copy below reads it before anything overwrites it (stream order + the sync below)
+  MB_CUDA_TRY(cudaMemcpyAsync(meta, hm, sizeof(PackMeta), cudaMemcpyHostToDevice, st));
+  Plain P;
+  P.n = n;
+  P.ref_id = in->ref_id; P.pos = in->pos; P.nm = in->nm; P.l_qseq = in->l_qseq; P.mapq = in->mapq;
+  P.cigar_off = in->cigar_off; P.seq_off = in->seq_off; P.cigar = in->cigar; P.seq = in->seq; P.qual = in->qual;
+  P.nib = in->seq_nibbles ? 1u : 0u;
+  mb_dev_layout dl{};
+  if (mode == 0) { rc = get_dev_layout(c, L, &dl); if (rc) return rc; }
+  const uint32_t grid = (uint32_t)std::min<uint64_t>((n + 255) / 256, (uint64_t)c->sm_count * 8);
+  const uint32_t wgrid = (uint32_t)std::min<uint64_t>((n + 7) / 8, (uint64_t)c->sm_count * 8);
+  if (n) {
+    if (mode == 0) {
+      k_pack_blocks<<<1, 1024, 0, st>>>(P.ref_id, n, L->n_contigs, dl.order, (uint32_t*)blk_src, (uint32_t*)blk_dst);
+      k_pack_analyse<0><<<grid, 256, 0, st>>>(P, L->n_contigs, dl.contig_len, dl.contig_goff, (uint32_t*)blk_src,
+                                              (uint32_t*)blk_dst, (uint4*)d->hdr, d->cplx, (uint32_t*)src_of,
+                                              (uint16_t*)nblk, (uint8_t*)need, meta);
+      c->launches += 2;
+    } else {
+      k_pack_analyse<1><<<grid, 256, 0, st>>>(P, L->n_contigs, nullptr, nullptr, nullptr, nullptr, (uint4*)d->hdr, d->cplx,
+                                              (uint32_t*)src_of, (uint16_t*)nblk, (uint8_t*)need, meta);
+      c->launches += 1;
+    }
+    k_pack_qor<<<wgrid, 256, 0, st>>>(P, meta);
+    c->launches += 1;
+  }
+  k_pack_finish<<<1, 32, 0, st>>>(meta, n, mode, P.cigar_off);
+  c->launches += 1;
+  if (n) {
+    k_pack_units<<<(uint32_t)std::min<uint64_t>((n_groups + 7) / 8, (uint64_t)c->sm_count * 8), 256, 0, st>>>(
+        (const uint16_t*)nblk, n, n_groups, meta, (uint32_t*)g_units);
+    k_pack_scan1<<<n_sblocks, SCAN_T, 0, st>>>((const uint32_t*)g_units, n_groups, (unsigned long long*)bsum);
+    k_pack_scan2<<<1, SCAN_T, 0, st>>>((unsigned long long*)bsum, n_sblocks, meta);
+    c->launches += 3;
+  }
+  MB_CUDA_TRY(cudaMemcpyAsync(hm, meta, sizeof(PackMeta), cudaMemcpyDeviceToHost, st));
+  MB_CUDA_TRY(cudaStreamSynchronize(st));
+  MB_CUDA_TRY(cudaGetLastError());
+  if (hm->err != ~0ull) {
+    int status = MB_EINVAL;
+    const char* text = pack_err_text((uint32_t)(hm->err & 0xffu), &status);
+    return mb::fail(status, "read %llu: %s", (unsigned long long)(hm->err >> 8), text);
+  }
+  if (hm->q_or & 0x80u) return mb::fail(MB_EINVAL, "mb_reads_pack: a base quality above 127 is not representable");
+  if (hm->unsorted)
+    return mb::fail(MB_EUNSORTED, "mb_reads_pack: snps records are not in BAM coordinate order (ref_id, pos); "
+                                  "use mb_pack_reads with sort");
+  if (hm->n_vec > 0xFFFFFFF0ull) return mb::fail(MB_EOVERFLOW, "mb_reads_pack: batch too large for 32-bit unit offsets");
+  d->n_reads = n;
+  d->n_vec = hm->n_vec;
+  d->total_bases = hm->total_bases;
+  d->max_ref_span = hm->max_span;
+  d->sorted = mode == 0 ? 1u : 0u;
+  d->row_words = hm->row_words;
+  d->n_long = hm->n_long;
+  d->q_planes = hm->q_planes;
+  d->n_planes = hm->n_planes;
+  rc = pack_alloc(c, staged, 36, (size_t)d->n_vec * 32, (void**)&d->planes);
+  if (!rc) rc = pack_alloc(c, staged, 37, 4 * (size_t)d->n_long, (void**)&d->long_idx);
+  if (rc) return rc;
+  // the raw CIGAR words are part of the packed batch (cplx[] indexes them): a resident batch owns a copy
+  const uint64_t n_cig = hm->n_cig;
+  d->n_cigar_words = n_cig;
+  if (staged) {
+    d->cigar = const_cast<uint32_t*>(in->cigar);
+  } else {
+    rc = pack_alloc(c, false, 38, 4 * (size_t)n_cig, (void**)&d->cigar);
+    if (rc) return rc;
+    if (n_cig) MB_CUDA_TRY(cudaMemcpyAsync(d->cigar, in->cigar, 4 * (size_t)n_cig, cudaMemcpyDeviceToDevice, st));
+  }
+  if (n) {
+    k_pack_scan3<<<n_sblocks, SCAN_T, 0, st>>>((const uint32_t*)g_units, n_groups, (const unsigned long long*)bsum, n, meta,
+                                               d->vec_off);
+    c->launches += 1;
+    if (d->n_long) {
+      k_pack_long<<<grid, 256, 0, st>>>((const uint8_t*)need, n, meta, (uint4*)d->hdr, d->long_idx);
+      c->launches += 1;
+    }
+    if (mode == 0)
+      k_pack_fill<0><<<wgrid, 256, 0, st>>>(P, (const uint4*)d->hdr, (const uint32_t*)src_of, d->vec_off, n, meta, d->planes);
+    else
+      k_pack_fill<1><<<wgrid, 256, 0, st>>>(P, (const uint4*)d->hdr, (const uint32_t*)src_of, d->vec_off, n, meta, d->planes);
+    c->launches += 1;
+  } else {
+    MB_CUDA_TRY(cudaMemsetAsync(d->vec_off, 0, 4, st));
+  }
+  MB_CUDA_TRY(cudaEventRecord(c->pack_ev[1], st));
+  MB_CUDA_TRY(cudaGetLastError());
+  d->bytes = sizeof(mb_read_hdr) * n + 4 * (n + 1) + 4 * n + 4 * n_cig + (uint64_t)d->n_vec * 32 + 4 * (uint64_t)d->n_long;
+  return MB_OK;
+}
+
+}  // namespace mb
+
+extern "C" int mb_reads_pack_dev(mb_ctx* c, const mb_plain_reads* plain_dev, const mb_layout* L, int mode,
+                                 mb_dev_reads** out) {
+  if (!c || !plain_dev || !L || !out) return mb::fail(MB_EINVAL, "mb_reads_pack_dev: null argument");
+  if (mode != 0 && mode != 1) return mb::fail(MB_EINVAL, "mb_reads_pack_dev: mode must be 0 (snps) or 1 (genes)");
+  MB_CUDA_TRY(cudaSetDevice(c->device));
+  mb_dev_reads* d = new mb_dev_reads();
+  int rc = mb::pack_on_device(c, plain_dev, L, mode, false, d);
+  if (rc) { cudaStreamSynchronize(c->stream); mb::free_dev_reads_arrays(d); delete d; return rc; }
+  *out = d;
+  return MB_OK;
+}
+
+extern "C" int mb_reads_pack(mb_ctx* c, const mb_plain_reads* plain_host, const mb_layout* L, int mode,
+                             mb_dev_reads** out) {
+  if (!c || !plain_host || !L || !out) return mb::fail(MB_EINVAL, "mb_reads_pack: null argument");
+  MB_CUDA_TRY(cudaSetDevice(c->device));
+  mb_plain_reads dev;
+  int rc = mb::upload_plain(c, plain_host, &dev);
+  if (rc) return rc;
+  return mb_reads_pack_dev(c, &dev, L, mode, out);
+}
+
+extern "C" int mb_ctx_last_pack_ms(mb_ctx* c, float* ms) {
+  if (!c || !ms) return mb::fail(MB_EINVAL, "mb_ctx_last_pack_ms: null argument");
+  if (!c->pack_timed) return mb::fail(MB_EINVAL, "mb_ctx_last_pack_ms: the device packer has not run yet");
+  MB_CUDA_TRY(cudaEventSynchronize(c->pack_ev[1]));
+  MB_CUDA_TRY(cudaEventElapsedTime(ms, c->pack_ev[0], c->pack_ev[1]));
+  return MB_OK;
+}
+
+extern "C" int mb_reads_download(mb_ctx* c, const mb_dev_reads* r, mb_packed_reads** out) {
+  if (!c || !r || !out) return mb::fail(MB_EINVAL, "mb_reads_download: null argument");
+  MB_CUDA_TRY(cudaSetDevice(c->device));
+  MB_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  mb_packed_owner* o = new mb_packed_owner();
+  memset(o, 0, sizeof(*o));
+  o->pinned = false;
+  const size_t sizes[7] = {sizeof(mb_read_hdr) * (size_t)r->n_reads, 4 * (size_t)(r->n_reads + 1), 4 * (size_t)r->n_reads,
+                           4 * (size_t)r->n_cigar_words, (size_t)r->n_vec * 32, 0, 4 * (size_t)r->n_long};
+  const void* src[7] = {r->hdr, r->vec_off, r->cplx, r->cigar, r->planes, nullptr, r->long_idx};
+  for (int k = 0; k < 7; ++k) {
+    void* b = nullptr;
+    if (posix_memalign(&b, 256, sizes[k] ? sizes[k] : 16) != 0) { mb_packed_free(&o->pub); return mb::fail(MB_ENOMEM, "mb_reads_download: out of host memory"); }
+    o->buf[k] = b;
+    if (sizes[k] && src[k]) {
+      cudaError_t e = cudaMemcpy(b, src[k], sizes[k], cudaMemcpyDeviceToHost);
+      if (e != cudaSuccess) { mb_packed_free(&o->pub); return mb::fail(MB_ECUDA, "mb_reads_download: %s", cudaGetErrorString(e)); }
+    }
+  }
+  o->pub.n_reads = r->n_reads;
+  o->pub.n_vec = r->n_vec;
+  o->pub.n_cigar_words = r->n_cigar_words;
+  o->pub.total_bases = r->total_bases;
+  o->pub.max_ref_span = r->max_ref_span;
+  o->pub.sorted = r->sorted;
+  o->pub.row_words = r->row_words;
+  o->pub.n_long = r->n_long;
+  o->pub.q_planes = r->q_planes;
+  o->pub.n_planes = r->n_planes;
+  o->pub.hdr = (mb_read_hdr*)o->buf[0];
+  o->pub.vec_off = (uint32_t*)o->buf[1];
+  o->pub.cplx = (uint32_t*)o->buf[2];
+  o->pub.cigar = (uint32_t*)o->buf[3];
+  o->pub.planes = (uint32_t*)o->buf[4];
+  o->pub.long_idx = (uint32_t*)o->buf[6];
+  *out = &o->pub;
+  return MB_OK;
+}

@@ -78,6 +78,9 @@ struct PileParams {
   int mapq;
   uint32_t baseq;             // per-base threshold (0: every candidate base counts)
   uint32_t defer_restat;      // 1: long reads follow, position stats are recomputed afterwards
+  uint32_t* ovf;              // set to 1 when a u32 counter saturates (MB_EOVERFLOW)
+  unsigned long long* mirror; // peer-memory copy of the stats rows (multi-GPU), written by the last CTA; or null
+  uint32_t n_species;
 };
 
 __device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
@@ -115,7 +118,7 @@ __device__ __forceinline__ uint32_t shr_clamp(uint32_t v, uint32_t n) {   // v >
 __global__ void k_init_stats(unsigned long long* stats, const uint64_t* species_len, uint32_t n_species,
                              uint32_t* sched) {
   uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s == 0) sched[0] = 0;
+  if (s == 0) { sched[0] = 0; sched[1] = 0; }
   if (s < n_species) {
     stats[5 * s + 0] = species_len[s];  // genome_length (snps.py:211)
     stats[5 * s + 1] = 0;
@@ -251,9 +254,16 @@ __global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : 2) k_pi
           v.z = ((lo[c] >> 16) & 0xffu) | (((hi[c] >> 16) & 0xffu) << 8);
           v.w = (lo[c] >> 24) | ((hi[c] >> 24) << 8);
           uint4* dst = reinterpret_cast<uint4*>(p.counts + (size_t)c * p.gpad + ts + 4 * q);
-          if (accumulate) {
+          if (accumulate) {   // a column deeper than PASS_ROWS rows: u32 sums saturate and raise MB_EOVERFLOW
             const uint4 o = *dst;
             v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+            if (v.x < o.x || v.y < o.y || v.z < o.z || v.w < o.w) {
+              if (v.x < o.x) v.x = 0xffffffffu;
+              if (v.y < o.y) v.y = 0xffffffffu;
+              if (v.z < o.z) v.z = 0xffffffffu;
+              if (v.w < o.w) v.w = 0xffffffffu;
+              *p.ovf = 1u;
+            }
           }
           *dst = v;
           d[0] += v.x; d[1] += v.y; d[2] += v.z; d[3] += v.w;
@@ -462,29 +472,38 @@ __global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : 2) k_pi
               }
             }
           } else {
-            // three or more runs: run records {n_runs, (q0 | len << 16, x0)...}, each run masked to its own
-            // row bits [o + x0, o + x0 + len) (clamped shifts: a PTX shift by >= 32 gives 0)
-            const uint32_t* __restrict__ rec = p.cigar + cw;
-            const uint32_t n_runs = __ldg(rec);
+            // three or more runs: the read's raw CIGAR words (len << 4 | op) are walked until l_qseq query bases
+            // are consumed; every M/=/X run is clipped at ref_span (the contig end) and masked to its own row
+            // bits [o + x0, o + x0 + len) (clamped shifts: a PTX shift by >= 32 gives 0)
+            const uint32_t* __restrict__ ops = p.cigar + cw;
 #pragma unroll
             for (int j = 0; j < WT; ++j) { rl[j] = 0; rh[j] = 0; rv[j] = 0; }
-            for (uint32_t k = 0; k < n_runs; ++k) {
-              const uint32_t w0 = __ldg(rec + 1 + 2 * k);
-              const int q0 = (int)(w0 & 0xffffu), len = (int)(w0 >> 16), x0 = (int)__ldg(rec + 2 + 2 * k);
-              const int p0 = o + x0, dq = q0 - p0;
-              int d = ((dq - 1) >> 5) - wshift;
-              const int sh = ((dq - 1) & 31) + 1;
-              MB_SLIDE(d, wshift, ql, qh, qv);
+            for (int q0 = 0, x0 = 0; q0 < (int)lq;) {
+              const uint32_t opw = __ldg(ops++);
+              const uint32_t op = opw & 15u;
+              const int oplen = (int)(opw >> 4);
+              if (op == mb::OP_I || op == mb::OP_S) { q0 += oplen; continue; }
+              if (op == mb::OP_D || op == mb::OP_N) { x0 += oplen; continue; }
+              if (op != mb::OP_M && op != mb::OP_EQ && op != mb::OP_X) continue;       // H
+              const int len = min(oplen, (int)span - x0);
+              if (len > 0) {
+                const int p0 = o + x0, dq = q0 - p0;
+                int d = ((dq - 1) >> 5) - wshift;
+                const int sh = ((dq - 1) & 31) + 1;
+                MB_SLIDE(d, wshift, ql, qh, qv);
 #pragma unroll
-              for (int j = 0; j < WT; ++j) {
-                const int r0b = p0 - 32 * j, r1b = r0b + len;
-                const uint32_t up = shl_clamp(0xffffffffu, (uint32_t)max(r0b, 0));
-                const uint32_t dn = shr_clamp(0xffffffffu, (uint32_t)(32 - min(max(r1b, 0), 32)));
-                const uint32_t msk = up & dn;
-                rl[j] |= __funnelshift_rc(ql[j], ql[j + 1], sh) & msk;
-                rh[j] |= __funnelshift_rc(qh[j], qh[j + 1], sh) & msk;
-                rv[j] |= __funnelshift_rc(qv[j], qv[j + 1], sh) & msk;
+                for (int j = 0; j < WT; ++j) {
+                  const int r0b = p0 - 32 * j, r1b = r0b + len;
+                  const uint32_t up = shl_clamp(0xffffffffu, (uint32_t)max(r0b, 0));
+                  const uint32_t dn = shr_clamp(0xffffffffu, (uint32_t)(32 - min(max(r1b, 0), 32)));
+                  const uint32_t msk = up & dn;
+                  rl[j] |= __funnelshift_rc(ql[j], ql[j + 1], sh) & msk;
+                  rh[j] |= __funnelshift_rc(qh[j], qh[j + 1], sh) & msk;
+                  rv[j] |= __funnelshift_rc(qv[j], qv[j + 1], sh) & msk;
+                }
               }
+              q0 += oplen;
+              x0 += oplen;
             }
           }
 #pragma unroll
@@ -605,6 +624,25 @@ __global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : 2) k_pi
       if (sp >= 0 && v && !(p.defer_restat && tid < 2)) atomicAdd(&p.stats[5 * sp + 1 + tid], v);
     }
   }
+  // ---- multi-GPU: the last CTA to finish copies the finished stats rows into the peer buffer (e.g. rank 0's
+  // table over NVLink), so gathering the per-species rows needs no collective
+  if (p.mirror) {
+    __shared__ uint32_t s_last;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = atomicAdd(p.sched + 1, 1u) == gridDim.x - 1 ? 1u : 0u;
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      for (uint32_t i = tid; i < 5u * p.n_species; i += NT) p.mirror[i] = __ldcg(p.stats + i);
+      __threadfence_system();
+    }
+  }
+}
+
+__global__ void k_mirror_stats(const unsigned long long* __restrict__ stats, unsigned long long* mirror, uint32_t n) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) mirror[i] = stats[i];
+  __threadfence_system();
 }
 
 // ---- reads that do not fit a W-word row: one warp per read, global atomics (rare by construction)
@@ -620,6 +658,7 @@ struct LongParams {
   unsigned long long* stats;
   uint64_t gpad;
   uint32_t n_long;
+  uint32_t* ovf;
   double mapid, aln_cov;
   int readq, mapq;
   uint32_t baseq;
@@ -658,19 +697,10 @@ __global__ void __launch_bounds__(256) k_long_reads(const LongParams p) {
     }
     if (!keep) continue;
     const bool simple = (fl & MB_RF_SIMPLE) != 0;
-    const uint32_t* __restrict__ rec = (simple || (fl & MB_RF_RUNS2)) ? p.cigar : p.cigar + __ldg(p.cplx + r);
     const bool runs2 = (fl & MB_RF_RUNS2) != 0;
     const uint32_t cw = simple ? 0u : __ldg(p.cplx + r);
-    const uint32_t n_runs = simple ? 1u : (runs2 ? 2u : __ldg(rec));
-    for (uint32_t o = 0; o < n_runs; ++o) {
-      uint32_t w0, x0;
-      if (simple) { w0 = qstart | (span << 16); x0 = 0; }
-      else if (runs2) {
-        const uint32_t len0 = cw & 0xffffu, ins = (cw >> 16) & 0xffu, del = cw >> 24;
-        if (o == 0) { w0 = qstart | (len0 << 16); x0 = 0; }
-        else { x0 = len0 + del; w0 = (qstart + len0 + ins) | ((span - x0) << 16); }
-      } else { w0 = __ldg(rec + 1 + 2 * o); x0 = __ldg(rec + 2 + 2 * o); }
-      const uint32_t q0 = w0 & 0xffffu, len = w0 >> 16;
+    // one run: query bases [q0, q0 + len) on reference offsets [x0, x0 + len)
+    auto count_run = [&](const uint32_t q0, const uint32_t len, const uint32_t x0) {
       for (uint32_t i = lane; i < len; i += 32) {
         const uint32_t qi = q0 + i, bb = qi & 31u;
         const uint32_t blk = (qi >> 5) * p.NP;                     // first word of the base's block
@@ -678,8 +708,31 @@ __global__ void __launch_bounds__(256) k_long_reads(const LongParams p) {
         for (uint32_t b = 0; b < p.NQ; ++b) ph |= ((__ldg(q + widx(blk + 3 + b)) >> bb) & 1u) << b;
         if (((__ldg(q + widx(blk + 2)) >> bb) & 1u) && ph >= p.baseq) {     // candidate base with Phred >= baseq
           const uint32_t cd = ((__ldg(q + widx(blk)) >> bb) & 1u) | (((__ldg(q + widx(blk + 1)) >> bb) & 1u) << 1);
-          atomicAdd(p.counts + (size_t)cd * p.gpad + loc + x0 + i, 1u);
+          const uint32_t old = atomicAdd(p.counts + (size_t)cd * p.gpad + loc + x0 + i, 1u);
+          if (old == 0xffffffffu) {                                 // wrapped: saturate and flag (MB_EOVERFLOW)
+            atomicExch(p.counts + (size_t)cd * p.gpad + loc + x0 + i, 0xffffffffu);
+            *p.ovf = 1u;
+          }
         }
+      }
+    };
+    if (simple) {
+      count_run(qstart, span, 0u);
+    } else if (runs2) {
+      const uint32_t len0 = cw & 0xffffu, ins = (cw >> 16) & 0xffu, del = cw >> 24;
+      count_run(qstart, len0, 0u);
+      count_run(qstart + len0 + ins, span - (len0 + del), len0 + del);
+    } else {
+      // raw CIGAR words, walked until l_qseq query bases are consumed; runs clipped at ref_span
+      const uint32_t* __restrict__ ops = p.cigar + cw;
+      for (uint32_t q0 = 0, x0 = 0; q0 < lq;) {
+        const uint32_t opw = __ldg(ops++), op = opw & 15u, oplen = opw >> 4;
+        if (op == mb::OP_I || op == mb::OP_S) { q0 += oplen; continue; }
+        if (op == mb::OP_D || op == mb::OP_N) { x0 += oplen; continue; }
+        if (op != mb::OP_M && op != mb::OP_EQ && op != mb::OP_X) continue;
+        if (x0 < span) count_run(q0, min(oplen, span - x0), x0);
+        q0 += oplen;
+        x0 += oplen;
       }
     }
   }
@@ -801,7 +854,15 @@ extern "C" int mb_snps_pileup_dev(mb_ctx* ctx, const mb_dev_reads* reads, const 
   k_init_stats<<<ns ? (ns + 255) / 256 : 1, 256, 0, st>>>(
       reinterpret_cast<unsigned long long*>(stats_dev), dl.species_len, ns, ctx->sched);
   ctx->launches++;
-  if (n_ktiles == 0) { MB_CUDA_TRY(cudaGetLastError()); return MB_OK; }
+  if (n_ktiles == 0) {
+    if (ctx->stats_mirror && ns) {
+      k_mirror_stats<<<1, 256, 0, st>>>(reinterpret_cast<unsigned long long*>(stats_dev),
+                                        reinterpret_cast<unsigned long long*>(ctx->stats_mirror), 5u * ns);
+      ctx->launches++;
+    }
+    MB_CUDA_TRY(cudaGetLastError());
+    return MB_OK;
+  }
   // the tile -> read-range index depends only on the resident batch: built once per (batch, row width)
   if (ctx->rng_for != reads || ctx->rng_W != W || ctx->rng_ntiles != n_ktiles) {
     k_tile_ranges<<<(n_ktiles + 255) / 256, 256, 0, st>>>(reinterpret_cast<const uint4*>(reads->hdr),
@@ -834,6 +895,9 @@ extern "C" int mb_snps_pileup_dev(mb_ctx* ctx, const mb_dev_reads* reads, const 
   p.mapq = f->mapq;
   p.baseq = (uint32_t)f->baseq;
   p.defer_restat = reads->n_long ? 1u : 0u;
+  p.ovf = ctx->ovf;
+  p.mirror = reads->n_long ? nullptr : reinterpret_cast<unsigned long long*>(ctx->stats_mirror);
+  p.n_species = ns;
   const uint32_t grid = min(n_ktiles, (uint32_t)(ctx->sm_count * ctx->pile_occ));
   { int trc = mb::timing_begin(ctx); if (trc) return trc; }
   kern.fn<<<grid, NT, pile_smem_bytes(W, rmax, NCOL), st>>>(p);
@@ -848,6 +912,7 @@ extern "C" int mb_snps_pileup_dev(mb_ctx* ctx, const mb_dev_reads* reads, const 
     lp.stats = p.stats;
     lp.gpad = L->gpad;
     lp.n_long = reads->n_long;
+    lp.ovf = ctx->ovf;
     lp.mapid = f->mapid; lp.aln_cov = f->aln_cov; lp.readq = f->readq; lp.mapq = f->mapq;
     lp.baseq = (uint32_t)f->baseq;
     lp.NQ = reads->q_planes; lp.NP = reads->n_planes;
@@ -857,6 +922,10 @@ extern "C" int mb_snps_pileup_dev(mb_ctx* ctx, const mb_dev_reads* reads, const 
     k_restat<<<min(L->n_tiles, (uint32_t)ctx->sm_count * 8u), 256, 0, st>>>(counts_dev, L->gpad, L->n_tiles,
                                                                             dl.tile_species, p.stats);
     ctx->launches++;
+    if (ctx->stats_mirror && ns) {
+      k_mirror_stats<<<1, 256, 0, st>>>(p.stats, reinterpret_cast<unsigned long long*>(ctx->stats_mirror), 5u * ns);
+      ctx->launches++;
+    }
   }
   MB_CUDA_TRY(cudaGetLastError());
   return MB_OK;
@@ -881,8 +950,35 @@ extern "C" int mb_snps_pileup(mb_ctx* ctx, const mb_packed_reads* reads, const m
   if (!rc && cbytes) {
     cudaError_t e = cudaMemcpyAsync(counts_host, counts, cbytes, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess && sbytes) e = cudaMemcpyAsync(stats_host, stats, sbytes, cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) rc = mb::fail(MB_ECUDA, "mb_snps_pileup: %s", cudaGetErrorString(e));
   }
+  if (!rc) rc = mb::check_overflow(ctx, "mb_snps_pileup");   // synchronises the stream
+  return rc;
+}
+
+extern "C" int mb_snps_pileup_plain(mb_ctx* ctx, const mb_plain_reads* plain_host, const mb_layout* L,
+                                    const mb_filters* f, uint32_t* counts_host, mb_species_stats* stats_host) {
+  if (!ctx || !plain_host || !L || !f || !counts_host || !stats_host)
+    return mb::fail(MB_EINVAL, "mb_snps_pileup_plain: null argument");
+  MB_CUDA_TRY(cudaSetDevice(ctx->device));
+  mb_plain_reads dev;
+  int rc = mb::upload_plain(ctx, plain_host, &dev);                     // H2D of the decoded records
+  if (rc) return rc;
+  mb_dev_reads dr;
+  rc = mb::pack_on_device(ctx, &dev, L, 0, /*staged=*/true, &dr);       // k_pack_*: the re-layout, on the GPU
+  if (rc) return rc;
+  void *counts = nullptr, *stats = nullptr;
+  const size_t cbytes = sizeof(uint32_t) * 4 * (size_t)L->gpad, sbytes = sizeof(mb_species_stats) * (size_t)L->n_species;
+  rc = mb::ctx_reserve(ctx, 0, cbytes, &counts);
+  if (!rc) rc = mb::ctx_reserve(ctx, 1, sbytes, &stats);
+  ctx->rng_for = nullptr;
+  if (!rc) rc = mb_snps_pileup_dev(ctx, &dr, L, f, (uint32_t*)counts, (mb_species_stats*)stats);
+  ctx->rng_for = nullptr;
+  if (!rc && cbytes) {
+    cudaError_t e = cudaMemcpyAsync(counts_host, counts, cbytes, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess && sbytes) e = cudaMemcpyAsync(stats_host, stats, sbytes, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e != cudaSuccess) rc = mb::fail(MB_ECUDA, "mb_snps_pileup_plain: %s", cudaGetErrorString(e));
+  }
+  if (!rc) rc = mb::check_overflow(ctx, "mb_snps_pileup_plain");
   return rc;
 }

@@ -37,7 +37,15 @@ class CRef(C.Structure):
 class CPlainReads(C.Structure):
     _fields_ = [("n_reads", C.c_uint64), ("ref_id", C.c_void_p), ("pos", C.c_void_p), ("mapq", C.c_void_p),
                 ("nm", C.c_void_p), ("l_qseq", C.c_void_p), ("cigar_off", C.c_void_p), ("cigar", C.c_void_p),
-                ("seq_off", C.c_void_p), ("seq", C.c_void_p), ("qual", C.c_void_p)]
+                ("seq_off", C.c_void_p), ("seq", C.c_void_p), ("qual", C.c_void_p),
+                ("seq_nibbles", C.c_uint32), ("reserved", C.c_uint32)]
+
+    @staticmethod
+    def of(reads: PlainReads) -> "CPlainReads":
+        """View of host numpy arrays (the caller keeps `reads` alive for the duration of the call)."""
+        return CPlainReads(reads.n_reads, _ptr(reads.ref_id), _ptr(reads.pos), _ptr(reads.mapq), _ptr(reads.nm),
+                           _ptr(reads.l_qseq), _ptr(reads.cigar_off), _ptr(reads.cigar), _ptr(reads.seq_off),
+                           _ptr(reads.seq), _ptr(reads.qual), int(bool(reads.seq_nibbles)), 0)
 
 
 class CMergeParams(C.Structure):
@@ -64,13 +72,15 @@ GENE_OUT_DTYPE = np.dtype([("aligned_reads", "<u4"), ("mapped_reads", "<u4"), ("
 # every symbol include/midas_b200.h declares (tests/test_abi.py checks the .so exports them all)
 EXPORTS = [
     "mb_version", "mb_last_error",
-    "mb_layout_create", "mb_layout_destroy", "mb_layout_gpad", "mb_layout_n_tiles", "mb_layout_contig_goff",
+    "mb_layout_create", "mb_layout_create_genes", "mb_layout_destroy", "mb_layout_gpad", "mb_layout_n_tiles", "mb_layout_contig_goff",
     "mb_layout_species_goff", "mb_layout_species_len",
-    "mb_pack_reads", "mb_packed_free",
+    "mb_pack_reads", "mb_packed_free", "mb_host_alloc", "mb_host_free",
     "mb_ctx_create", "mb_ctx_destroy", "mb_ctx_set_stream", "mb_ctx_sync", "mb_ctx_device",
     "mb_ctx_launch_count", "mb_ctx_last_kernel_ms", "mb_ctx_timing_reset", "mb_ctx_timing_read",
-    "mb_reads_upload", "mb_reads_free", "mb_reads_bytes",
-    "mb_snps_pileup_dev", "mb_snps_pileup", "mb_genes_coverage_dev", "mb_genes_coverage",
+    "mb_reads_upload", "mb_reads_free", "mb_reads_bytes", "mb_reads_total_bases", "mb_reads_n",
+    "mb_reads_pack", "mb_reads_pack_dev", "mb_reads_download", "mb_ctx_last_pack_ms",
+    "mb_snps_pileup_dev", "mb_snps_pileup", "mb_snps_pileup_plain", "mb_ctx_overflowed", "mb_ctx_set_stats_mirror",
+    "mb_genes_coverage_dev", "mb_genes_coverage", "mb_genes_coverage_plain",
     "mb_format_snps_bound", "mb_format_snps_rows",
     "mb_merge_sites_dev", "mb_format_merge_bound", "mb_format_merge_freq_rows", "mb_format_merge_depth_rows",
     "mb_bam_open", "mb_bam_close", "mb_bam_n_ref", "mb_bam_ref_name", "mb_bam_ref_len", "mb_bam_reads", "mb_bam_flags",
@@ -98,8 +108,25 @@ def load():
         getattr(L, name).restype = C.c_void_p
         getattr(L, name).argtypes = [C.c_void_p]
     L.mb_layout_create.argtypes = [C.POINTER(CRef), C.POINTER(C.c_void_p)]
+    L.mb_layout_create_genes.argtypes = [C.c_uint32, C.POINTER(C.c_void_p)]
     L.mb_layout_destroy.argtypes = [C.c_void_p]
     L.mb_layout_destroy.restype = None
+    L.mb_host_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]
+    L.mb_host_free.argtypes = [C.c_void_p]
+    L.mb_host_free.restype = None
+    for name in ("mb_reads_total_bases", "mb_reads_n"):
+        getattr(L, name).argtypes = [C.c_void_p]
+        getattr(L, name).restype = C.c_uint64
+    L.mb_reads_pack.argtypes = [C.c_void_p, C.POINTER(CPlainReads), C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
+    L.mb_reads_pack_dev.argtypes = [C.c_void_p, C.POINTER(CPlainReads), C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
+    L.mb_reads_download.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.POINTER(CPackedReads))]
+    L.mb_ctx_last_pack_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+    L.mb_snps_pileup_plain.argtypes = [C.c_void_p, C.POINTER(CPlainReads), C.c_void_p, C.POINTER(CFilters),
+                                       C.c_void_p, C.c_void_p]
+    L.mb_ctx_overflowed.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
+    L.mb_ctx_set_stats_mirror.argtypes = [C.c_void_p, C.c_void_p]
+    L.mb_genes_coverage_plain.argtypes = [C.c_void_p, C.POINTER(CPlainReads), C.c_void_p, C.c_uint32,
+                                          C.POINTER(CFilters), C.c_int, C.c_void_p]
     L.mb_pack_reads.argtypes = [C.POINTER(CPlainReads), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                 C.POINTER(C.POINTER(CPackedReads))]
     L.mb_packed_free.argtypes = [C.POINTER(CPackedReads)]
@@ -139,7 +166,7 @@ def load():
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
     L.mb_merge_sites_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p,
                                      C.POINTER(CMergeParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
-    L.mb_bam_open.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
+    L.mb_bam_open.argtypes = [C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
     L.mb_bam_close.argtypes = [C.c_void_p]
     L.mb_bam_close.restype = None
     L.mb_bam_n_ref.argtypes = [C.c_void_p]
@@ -199,6 +226,20 @@ class Layout:
     def of(ref: RefSet) -> "Layout":
         return Layout(ref.contig_len, ref.contig_species, ref.n_species)
 
+    @staticmethod
+    def genes(n_genes: int) -> "Layout":
+        """Genes mode needs no coordinates (loc = gene index): no 32-bit padded-genome limit."""
+        self = Layout.__new__(Layout)
+        h = C.c_void_p()
+        _check(load().mb_layout_create_genes(int(n_genes), C.byref(h)))
+        self._h, self.n_contigs, self.n_species, self.gpad, self.n_tiles = h, int(n_genes), 0, 0, 0
+        self.contig_len = np.zeros(0, np.uint32)
+        self.contig_species = np.zeros(0, np.int32)
+        self.contig_goff = np.zeros(0, np.uint32)
+        self.species_goff = np.zeros(1, np.uint32)
+        self.species_len = np.zeros(0, np.uint64)
+        return self
+
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
         if h and _lib is not None:
@@ -222,15 +263,19 @@ class PackedReads:
                  pinned: bool = False, threads: int = 0):
         L = load()
         self._keep = reads  # keep the source arrays alive during the call
-        cin = CPlainReads(reads.n_reads, _ptr(reads.ref_id), _ptr(reads.pos), _ptr(reads.mapq), _ptr(reads.nm),
-                          _ptr(reads.l_qseq), _ptr(reads.cigar_off), _ptr(reads.cigar), _ptr(reads.seq_off),
-                          _ptr(reads.seq), _ptr(reads.qual))
+        cin = CPlainReads.of(reads)
         out = C.POINTER(CPackedReads)()
         _check(L.mb_pack_reads(C.byref(cin), layout._h, {"snps": 0, "genes": 1}[mode], int(sort), int(pinned),
                                int(threads), C.byref(out)))
         self._p = out
         self._keep = None
         self.mode = mode
+
+    @staticmethod
+    def _from_pointer(p, mode: str) -> "PackedReads":
+        self = PackedReads.__new__(PackedReads)
+        self._p, self._keep, self.mode = p, None, mode
+        return self
 
     def __del__(self):
         p, self._p = getattr(self, "_p", None), None
@@ -272,12 +317,24 @@ class PackedReads:
 
 
 class DevReads:
-    def __init__(self, ctx: "Context", packed: PackedReads):
-        h = C.c_void_p()
-        _check(load().mb_reads_upload(ctx._h, packed._p, C.byref(h)))
-        self._h, self._ctx = h, ctx
-        self.n_reads, self.total_bases, self.n_vec = packed.n_reads, packed.total_bases, packed.n_vec
-        self.nbytes = int(load().mb_reads_bytes(h))
+    """A packed batch resident in HBM (mb_dev_reads): uploaded from a host PackedReads, or packed on the
+    GPU from plain records (Context.pack / Context.pack_dev)."""
+
+    def __init__(self, ctx: "Context", packed: PackedReads | None = None, handle=None, mode: str | None = None):
+        if handle is None:
+            handle = C.c_void_p()
+            _check(load().mb_reads_upload(ctx._h, packed._p, C.byref(handle)))
+            mode = packed.mode
+        self._h, self._ctx, self.mode = handle, ctx, mode
+        L = load()
+        self.n_reads, self.total_bases = int(L.mb_reads_n(handle)), int(L.mb_reads_total_bases(handle))
+        self.nbytes = int(L.mb_reads_bytes(handle))
+
+    def download(self) -> PackedReads:
+        """Host copy of the resident arrays (to check the device packer against mb_pack_reads)."""
+        out = C.POINTER(CPackedReads)()
+        _check(load().mb_reads_download(self._ctx._h, self._h, C.byref(out)))
+        return PackedReads._from_pointer(out, self.mode)
 
     def free(self):
         h, self._h = self._h, None
@@ -336,6 +393,39 @@ class Context:
     def upload(self, packed: PackedReads) -> DevReads:
         return DevReads(self, packed)
 
+    def pack(self, reads: PlainReads, layout: Layout, mode: str = "snps") -> DevReads:
+        """Decoded records in host memory -> packed batch resident in HBM; the re-layout runs on the GPU
+        (mb_reads_pack). snps mode wants BAM coordinate order (MB_EUNSORTED otherwise)."""
+        cin = CPlainReads.of(reads)
+        h = C.c_void_p()
+        _check(load().mb_reads_pack(self._h, C.byref(cin), layout._h, {"snps": 0, "genes": 1}[mode], C.byref(h)))
+        return DevReads(self, handle=h, mode=mode)
+
+    def pack_dev(self, t: dict, layout: Layout, mode: str = "snps", seq_nibbles: bool = False) -> DevReads:
+        """Same, from records already on the device: `t` maps the mb_plain_reads field names to torch CUDA
+        tensors (ref_id/pos/nm/l_qseq int32, mapq/seq/qual uint8, cigar_off/seq_off int64, cigar int32)."""
+        n = int(t["ref_id"].shape[0])
+        cin = CPlainReads(n, *[C.c_void_p(t[k].data_ptr()) for k in
+                               ("ref_id", "pos", "mapq", "nm", "l_qseq", "cigar_off", "cigar", "seq_off", "seq", "qual")],
+                          int(bool(seq_nibbles)), 0)
+        h = C.c_void_p()
+        _check(load().mb_reads_pack_dev(self._h, C.byref(cin), layout._h, {"snps": 0, "genes": 1}[mode], C.byref(h)))
+        return DevReads(self, handle=h, mode=mode)
+
+    def last_pack_ms(self) -> float:
+        ms = C.c_float()
+        _check(load().mb_ctx_last_pack_ms(self._h, C.byref(ms)))
+        return float(ms.value)
+
+    def overflowed(self) -> bool:
+        flag = C.c_int()
+        _check(load().mb_ctx_overflowed(self._h, C.byref(flag)))
+        return bool(flag.value)
+
+    def set_stats_mirror(self, ptr: int | None):
+        """Device pointer in a peer GPU's memory that also receives the stats rows (None: off)."""
+        _check(load().mb_ctx_set_stats_mirror(self._h, C.c_void_p(ptr or 0)))
+
     # ---- snps
     def snps_pileup_dev(self, reads: DevReads, layout: Layout, filters: Filters, counts, stats):
         """counts: torch int32/uint32 CUDA tensor [4, gpad]; stats: torch int64 CUDA tensor [n_species, 5]."""
@@ -351,6 +441,18 @@ class Context:
         stats = np.zeros(layout.n_species, STATS_DTYPE)
         f = CFilters.of(filters)
         _check(load().mb_snps_pileup(self._h, packed._p, layout._h, C.byref(f), _ptr(counts), _ptr(stats)))
+        return counts, stats
+
+    def snps_pileup_plain(self, reads: PlainReads, layout: Layout, filters: Filters,
+                          counts_out: np.ndarray | None = None):
+        """Decoded records in host memory in, host buffers out: H2D + device re-layout + pileup + D2H
+        (mb_snps_pileup_plain). Returns (counts uint32 [4][gpad], stats STATS_DTYPE [n_species])."""
+        counts = counts_out if counts_out is not None else np.empty((4, layout.gpad), np.uint32)
+        assert counts.dtype == np.uint32 and counts.shape == (4, layout.gpad) and counts.flags.c_contiguous
+        stats = np.zeros(layout.n_species, STATS_DTYPE)
+        f = CFilters.of(filters)
+        cin = CPlainReads.of(reads)
+        _check(load().mb_snps_pileup_plain(self._h, C.byref(cin), layout._h, C.byref(f), _ptr(counts), _ptr(stats)))
         return counts, stats
 
     # ---- merge (snps)
@@ -385,6 +487,16 @@ class Context:
         f = CFilters.of(filters)
         _check(load().mb_genes_coverage_dev(self._h, reads._h, C.c_void_p(gene_len.data_ptr()), int(n_genes),
                                             C.byref(f), int(exact_order), C.c_void_p(out.data_ptr())))
+
+    def genes_coverage_plain(self, reads: PlainReads, gene_len: np.ndarray, filters: Filters, exact_order=False):
+        """Decoded records in host memory -> per-gene outputs (mb_genes_coverage_plain)."""
+        gene_len = np.ascontiguousarray(gene_len, np.uint32)
+        out = np.zeros(len(gene_len), GENE_OUT_DTYPE)
+        f = CFilters.of(filters)
+        cin = CPlainReads.of(reads)
+        _check(load().mb_genes_coverage_plain(self._h, C.byref(cin), _ptr(gene_len), len(gene_len), C.byref(f),
+                                              int(exact_order), _ptr(out)))
+        return out
 
     def genes_coverage(self, packed: PackedReads, gene_len: np.ndarray, filters: Filters, exact_order=False):
         gene_len = np.ascontiguousarray(gene_len, np.uint32)
@@ -447,13 +559,19 @@ def format_merge_rows(site_index: np.ndarray, maf: np.ndarray, depth: np.ndarray
     return out[0], out[1]
 
 
-def read_bam(path: str, threads: int = 0):
+MB_BAM_PINNED, MB_BAM_SEQ_BYTES = 1, 2
+
+
+def read_bam(path: str, threads: int = 0, pinned: bool = False, seq_bytes: bool = False):
     """Native BAM decode (mb_bam_open): returns (ref_names, ref_lens, PlainReads) in file order, like
-    midas_b200.bam.read_bam (the pure-Python reader it must agree with). The arrays are views of the
-    handle's buffers (no copy); the handle is closed when the last of them goes away."""
+    midas_b200.bam.read_bam (the pure-Python reader it must agree with). seq stays as in the file (two
+    codes per byte, PlainReads.seq_nibbles) unless seq_bytes; pinned = page-locked arrays (they are about
+    to cross PCIe). The arrays are views of the handle's buffers (no copy); the handle is closed when the
+    last of them goes away."""
     L = load()
     h = C.c_void_p()
-    _check(L.mb_bam_open(os.fsencode(path), int(threads), C.byref(h)))
+    _check(L.mb_bam_open(os.fsencode(path), int(threads),
+                         (MB_BAM_PINNED if pinned else 0) | (MB_BAM_SEQ_BYTES if seq_bytes else 0), C.byref(h)))
     owner = _BamHandle(h)
     n_ref = int(L.mb_bam_n_ref(h))
     names = [L.mb_bam_ref_name(h, i).decode() for i in range(n_ref)]
@@ -472,6 +590,42 @@ def read_bam(path: str, threads: int = 0):
     soff = arr(r.seq_off, n + 1, np.uint64)
     reads = PlainReads(arr(r.ref_id, n, np.int32), arr(r.pos, n, np.int32), arr(r.mapq, n, np.uint8),
                        arr(r.nm, n, np.int32), arr(r.l_qseq, n, np.int32), coff,
-                       arr(r.cigar, int(coff[-1]), np.uint32), soff, arr(r.seq, int(soff[-1]), np.uint8),
-                       arr(r.qual, int(soff[-1]), np.uint8), arr(L.mb_bam_flags(h), n, np.uint16))
+                       arr(r.cigar, int(coff[-1]), np.uint32), soff,
+                       arr(r.seq, (int(soff[-1]) + 1) // 2 if r.seq_nibbles else int(soff[-1]), np.uint8),
+                       arr(r.qual, int(soff[-1]), np.uint8), arr(L.mb_bam_flags(h), n, np.uint16),
+                       bool(r.seq_nibbles))
     return names, lens, reads
+
+
+class _Pinned:
+    def __init__(self, ptr):
+        self.ptr = ptr
+
+    def __del__(self):
+        p, self.ptr = self.ptr, None
+        if p and _lib is not None:
+            _lib.mb_host_free(p)
+
+
+def pinned_empty(n: int, dtype) -> np.ndarray:
+    """Page-locked host array (mb_host_alloc); freed when the array goes away."""
+    dt = np.dtype(dtype)
+    p = C.c_void_p()
+    _check(load().mb_host_alloc(max(1, int(n)) * dt.itemsize, C.byref(p)))
+    owner = _Pinned(p)
+    if n == 0:
+        return np.zeros(0, dt)
+    buf = (C.c_char * (int(n) * dt.itemsize)).from_address(p.value)
+    buf._owner = owner
+    return np.frombuffer(buf, dtype=dt, count=int(n))
+
+
+def pinned_reads(reads: PlainReads) -> PlainReads:
+    """Copy of `reads` whose arrays are page-locked (what the BAM reader hands out with pinned=True)."""
+    def pin(a):
+        out = pinned_empty(a.shape[0], a.dtype)
+        out[...] = a
+        return out
+    return PlainReads(pin(reads.ref_id), pin(reads.pos), pin(reads.mapq), pin(reads.nm), pin(reads.l_qseq),
+                      pin(reads.cigar_off), pin(reads.cigar), pin(reads.seq_off), pin(reads.seq), pin(reads.qual),
+                      reads.flag, reads.seq_nibbles)

@@ -106,7 +106,7 @@ def pangenome_coverage(args, species, genes, ctx=None):
 def count_mapped_bp(args, species, genes, ctx=None):
     """reference genes.py:171-203: per gene aligned/mapped reads and depth, per species summaries."""
     bam_path = "/".join([args["outdir"], "genes/temp/pangenomes.bam"])
-    names, lens, reads = lib.read_bam(bam_path)
+    names, lens, reads = lib.read_bam(bam_path, int(args.get("threads", 0) or 0), pinned=True)
     gene_ids = list(genes.keys())
     gindex = {g: k for k, g in enumerate(gene_ids)}
     missing = [n for n in set(names[t] for t in np.unique(reads.ref_id))
@@ -114,21 +114,22 @@ def count_mapped_bp(args, species, genes, ctx=None):
     if missing:
         raise KeyError(missing[0])                                   # genes[...] KeyError, genes.py:180
     tid_map = np.array([gindex.get(n, -1) for n in names], np.int32) if names else np.zeros(0, np.int32)
-    if reads.n_reads:
-        reads.ref_id = np.ascontiguousarray(tid_map[reads.ref_id], np.int32)
-    sp_ids = list(species.keys())
-    sp_index = {s: k for k, s in enumerate(sp_ids)}
+    if reads.n_reads and not np.array_equal(tid_map, np.arange(len(names), dtype=np.int32)):
+        reads.ref_id[...] = tid_map[reads.ref_id]
     gene_len = np.array([genes[g].length for g in gene_ids], np.uint32)
-    ref = RefSet(gene_ids, np.maximum(gene_len, 1), np.array([sp_index[genes[g].species_id] for g in gene_ids],
-                                                             np.int32), sp_ids, None)
+    if reads.n_reads:
+        hit = np.unique(reads.ref_id)
+        if (gene_len[hit] == 0).any():
+            raise ZeroDivisionError("float division by zero")    # alen / float(gene.length), genes.py:189
     own_ctx = ctx is None
     if own_ctx:
         ctx = lib.Context(int(args.get("device", 0)), use_torch_stream=False)
     try:
-        layout = lib.Layout.of(ref)
-        packed = lib.PackedReads(reads, layout, "genes")
+        # decoded records -> H2D -> re-layout on the GPU -> coverage kernel -> D2H. depth is one division of
+        # the integer sum (within 1e-12 of the reference's running float sum); --exact_order reproduces the
+        # running sum bit for bit at the price of a device sort
         f = Filters(float(args["mapid"]), float(args["aln_cov"]), int(args["readq"]), int(args["mapq"]), 0)
-        out = ctx.genes_coverage(packed, gene_len, f, exact_order=bool(args.get("exact_order", True)))
+        out = ctx.genes_coverage_plain(reads, gene_len, f, exact_order=bool(args.get("exact_order", False)))
     finally:
         if own_ctx:
             ctx.close()

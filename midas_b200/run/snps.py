@@ -7,9 +7,10 @@ Same names and meaning as the reference module:
 `pysam_pileup(args, species, contigs)` keeps its signature and side effects (per-species
 `<outdir>/snps/output/<species>.snps.gz`, Species.{genome_length, covered_bases, total_depth,
 aligned_reads, mapped_reads, fraction_covered, mean_coverage}), but instead of one forked worker per
-species walking pysam (utility.parallel, midas/utility.py:81-107) it decodes the BAM once, packs
-the reads of all species into one struct-of-arrays and makes ONE call into libmidas_b200.so
-(mb_snps_pileup) from the parent process. There is no CPU fallback.
+species walking pysam (utility.parallel, midas/utility.py:81-107) it decodes the BAM once into
+page-locked arrays and makes ONE call into libmidas_b200.so (mb_snps_pileup_plain: H2D, re-layout of the
+records on the GPU, pileup of all species, D2H) from the parent process. Under torchrun every rank takes
+the species shard.plan gives it on its own GPU. There is no CPU fallback.
 """
 from __future__ import annotations
 
@@ -98,11 +99,20 @@ def _filters(args) -> Filters:
                    int(args["baseq"]))
 
 
-def build_refset(species, contigs):
-    """Contigs in the order species_pileup visits them (sorted ids, snps.py:187), grouped by species."""
+def build_refset(species, contigs, bam_names=None):
+    """The contigs of the selected species as a RefSet. With the BAM header's reference names, contigs are
+    numbered in BAM tid order (so that the file's coordinate order is the batch's order and the device packer
+    only moves whole contigs); contigs the BAM does not name follow. species_pileup's own visiting order
+    (sorted ids, snps.py:187) is applied when the rows are written, not here."""
     sp_ids = list(species.keys())
     sp_index = {s: k for k, s in enumerate(sp_ids)}
-    ids = [cid for cid in sorted(contigs.keys()) if contigs[cid].species_id in sp_index]
+    known = {cid for cid in contigs if contigs[cid].species_id in sp_index}
+    ids, seen = [], set()
+    for n in (bam_names or []):
+        if n in known and n not in seen:
+            ids.append(n)
+            seen.add(n)
+    ids += [cid for cid in sorted(known) if cid not in seen]
     if any(contigs[c].length == 0 for c in ids):
         raise lib.MidasB200Error(-1, "a reference contig has length 0 (pysam: ValueError, interval of size 0)")
     ref = RefSet(ids, np.array([contigs[c].length for c in ids], np.uint32),
@@ -110,30 +120,38 @@ def build_refset(species, contigs):
     return ref
 
 
-def load_alignments(bampath, ref: RefSet):
-    """Decode the BAM and re-index its reference ids onto `ref` (records on references that are not
-    contigs of a selected species are never fetched by the reference, snps.py:190-199)."""
-    names, lens, reads = lib.read_bam(bampath)
+def load_alignments(bampath, species, contigs, threads=0, pinned=True):
+    """Decode the BAM (native reader, page-locked arrays, seq left as in the file) and number its records
+    on a RefSet in tid order. Records on references that are not contigs of a selected species are never
+    fetched by the reference (snps.py:190-199) and are dropped. Returns (RefSet, PlainReads)."""
+    names, lens, reads = lib.read_bam(bampath, threads, pinned=pinned)
+    ref = build_refset(species, contigs, names)
     index = {n: k for k, n in enumerate(ref.contig_names)}
     tid_map = np.array([index.get(n, -1) for n in names], np.int32) if names else np.zeros(0, np.int32)
     for n, l in zip(names, lens):
         k = index.get(n)
         if k is not None and int(ref.contig_len[k]) != int(l):
             raise lib.MidasB200Error(-5, f"BAM header length of {n} ({l}) != FASTA length ({int(ref.contig_len[k])})")
-    new_id = tid_map[reads.ref_id] if reads.n_reads else reads.ref_id
-    keep = np.nonzero(new_id >= 0)[0]
-    if len(keep) != reads.n_reads:
-        reads = reads.select(keep)
-        new_id = new_id[keep]
-    reads.ref_id = np.ascontiguousarray(new_id, np.int32)
-    return reads
+    if reads.n_reads and not np.array_equal(tid_map, np.arange(len(names), dtype=np.int32)):
+        new_id = tid_map[reads.ref_id]
+        keep = np.nonzero(new_id >= 0)[0]
+        if len(keep) != reads.n_reads:
+            reads = reads.select(keep)
+            new_id = new_id[keep]
+        if reads.ref_id.flags.writeable:
+            reads.ref_id[...] = new_id                       # in place: the array may be page-locked
+        else:
+            reads.ref_id = np.ascontiguousarray(new_id, np.int32)
+    return ref, reads
 
 
 def write_species_tsv(path, ref: RefSet, contigs, layout, counts, species_index, threads=8):
     """<species>.snps.gz (reference snps.py:179-182 header, :201-210 rows)."""
     out = mio.GzipMembersWriter(path, threads=threads)
     out.write(b"ref_id\tref_pos\tref_allele\tdepth\tcount_a\tcount_c\tcount_g\tcount_t\n")
-    for c, cid in enumerate(ref.contig_names):
+    index = {cid: c for c, cid in enumerate(ref.contig_names)}
+    for cid in sorted(index):                                      # species_pileup's order, snps.py:187
+        c = index[cid]
         if int(ref.contig_species[c]) != species_index:
             continue
         seq = np.frombuffer(contigs[cid].seq.encode("latin-1"), np.uint8)
@@ -164,18 +182,23 @@ def pysam_pileup(args, species, contigs, ctx=None):
 
     try:
         t = time()
-        ref = build_refset(species, contigs)
+        threads = int(args.get("threads", 1) or 1)
         bampath = "%s/snps/temp/genomes.bam" % args["outdir"]
-        reads = load_alignments(bampath, ref)
+        ref, reads = load_alignments(bampath, species, contigs, threads=threads)
         if timing is not None:
             timing["n_reads"], timing["n_bases"] = int(reads.n_reads), int(reads.l_qseq.sum(dtype=np.int64))
         t = lap("bam_decode", t)
         layout = lib.Layout.of(ref)
-        packed = lib.PackedReads(reads, layout, "snps", sort=True, pinned=False)
-        t = lap("pack", t)
-        counts, stats = ctx.snps_pileup(packed, layout, _filters(args))
-        t = lap("gpu_h2d_kernels_d2h", t)
-        threads = int(args.get("threads", 1) or 1)
+        try:
+            # decoded records -> H2D -> re-layout on the GPU (k_pack_*) -> pileup -> D2H
+            counts, stats = ctx.snps_pileup_plain(reads, layout, _filters(args))
+        except lib.MidasB200Error as e:
+            if e.status != -6:
+                raise
+            # a BAM that is not coordinate-sorted (the reference sorts it, snps.py:118): sort on the host
+            packed = lib.PackedReads(reads, layout, "snps", sort=True, pinned=False, threads=threads)
+            counts, stats = ctx.snps_pileup(packed, layout, _filters(args))
+        t = lap("gpu_h2d_pack_kernels_d2h", t)
         for k, species_id in enumerate(ref.species_ids):
             out_path = "%s/snps/output/%s.snps.gz" % (args["outdir"], species_id)
             write_species_tsv(out_path, ref, contigs, layout, counts, k, threads=threads)

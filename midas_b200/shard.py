@@ -91,15 +91,31 @@ def dominant_species(read_counts, n_ranks: int):
     return np.nonzero(read_counts * n_ranks > total)[0].astype(np.int32)
 
 
+def plan(read_counts, n_ranks: int):
+    """The sharding decision for a sample, from the per-species read counts alone (every rank computes the
+    same plan): dominant species (> 1/n_ranks of the reads) are split by read index over all ranks, the
+    others are owned by one rank each (LPT bin packing on what is left).
+    Returns (owner int32 [n_species], -1 for split species; dom int32 [n_dom] indices of the split species)."""
+    read_counts = np.asarray(read_counts, np.int64)
+    dom = dominant_species(read_counts, n_ranks)
+    rest = read_counts.copy()
+    rest[dom] = 0
+    owner = assign_species(rest, n_ranks)
+    owner[dom] = -1
+    return owner, dom
+
+
+def split_bounds(n: int, n_ranks: int) -> np.ndarray:
+    """Index ranges [b[r], b[r+1]) of a split species' reads (contiguous: they keep the sort order)."""
+    return np.linspace(0, int(n), n_ranks + 1).astype(np.int64)
+
+
 def shard_split(reads: PlainReads, ref: RefSet, rank: int, n_ranks: int):
     """Like shard(), but dominant species are split by read index over all ranks.
     Returns (sub RefSet, sub PlainReads, species_index, split_mask) where split_mask[k] is True for the
     rank's k-th species if it is a split (replicated) one that needs the count all-reduce."""
     counts = species_read_counts(reads, ref)
-    dom = dominant_species(counts, n_ranks)
-    rest = counts.copy()
-    rest[dom] = 0
-    owner = assign_species(rest, n_ranks)
+    owner, dom = plan(counts, n_ranks)
     sp_of_read = ref.contig_species[reads.ref_id] if reads.n_reads else np.zeros(0, np.int32)
     is_dom_sp = np.zeros(ref.n_species, bool)
     is_dom_sp[dom] = True
@@ -116,7 +132,7 @@ def shard_split(reads: PlainReads, ref: RefSet, rank: int, n_ranks: int):
         take = (~is_dom_sp[sp_of_read]) & (owner[sp_of_read] == rank)
         for s in dom:                                   # contiguous index ranges keep the sort order
             idx = np.nonzero(sp_of_read == s)[0]
-            b = np.linspace(0, len(idx), n_ranks + 1).astype(np.int64)
+            b = split_bounds(len(idx), n_ranks)
             take[idx[b[rank]:b[rank + 1]]] = True
         sel = np.nonzero(take)[0]
         sub_reads = reads.select(sel)

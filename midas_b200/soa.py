@@ -34,10 +34,11 @@ class PlainReads:
     l_qseq: np.ndarray      # int32 [n]
     cigar_off: np.ndarray   # uint64 [n+1]
     cigar: np.ndarray       # uint32 [sum n_cigar]  len<<4|op
-    seq_off: np.ndarray     # uint64 [n+1] (bases)
-    seq: np.ndarray         # uint8 [total bases] BAM 4-bit code per byte
-    qual: np.ndarray        # uint8 [total bases] raw Phred
+    seq_off: np.ndarray     # uint64 [n+1] element offsets into seq / qual (span >= l_qseq: padding allowed)
+    seq: np.ndarray         # uint8: BAM 4-bit codes, one per byte, or two per byte (seq_nibbles)
+    qual: np.ndarray        # uint8 [total elements] raw Phred
     flag: np.ndarray | None = None   # uint16 [n] SAM flag (carried for BAM round trips only)
+    seq_nibbles: bool = False        # seq as in a BAM record: element e in byte e >> 1, even e in the high nibble
 
     def __post_init__(self):
         self.ref_id = _c(self.ref_id, np.int32)
@@ -53,7 +54,56 @@ class PlainReads:
         n = self.n_reads
         assert self.pos.shape == (n,) and self.mapq.shape == (n,) and self.nm.shape == (n,)
         assert self.l_qseq.shape == (n,) and self.cigar_off.shape == (n + 1,) and self.seq_off.shape == (n + 1,)
-        assert self.seq.shape == self.qual.shape
+        if self.seq_nibbles:
+            assert self.seq.shape[0] == (self.qual.shape[0] + 1) // 2
+        else:
+            assert self.seq.shape == self.qual.shape
+
+    def unpacked(self) -> "PlainReads":
+        """One code per byte, spans exactly l_qseq (the form the oracle and the BAM writer take)."""
+        if not self.seq_nibbles:
+            if getattr(self, "_exact_spans", None) is None:     # checked once: the arrays are not resized in place
+                self._exact_spans = bool(np.array_equal((self.seq_off[1:] - self.seq_off[:-1]).astype(np.int64),
+                                                        self.l_qseq.astype(np.int64)))
+            if self._exact_spans:
+                return self
+        n = self.n_reads
+        lq = self.l_qseq.astype(np.int64)
+        soff = np.zeros(n + 1, np.uint64)
+        np.cumsum(lq, out=soff[1:])
+        total = int(soff[-1])
+        if total:
+            src = np.repeat(self.seq_off[:-1].astype(np.int64) - soff[:-1].astype(np.int64), lq) + np.arange(total, dtype=np.int64)
+            if self.seq_nibbles:
+                b = self.seq[src >> 1]
+                seq = np.where(src & 1, b & 15, b >> 4).astype(np.uint8)
+            else:
+                seq = self.seq[src]
+            qual = self.qual[src]
+        else:
+            seq, qual = np.zeros(0, np.uint8), np.zeros(0, np.uint8)
+        return PlainReads(self.ref_id, self.pos, self.mapq, self.nm, self.l_qseq, self.cigar_off, self.cigar, soff,
+                          seq, qual, self.flag)
+
+    def nibble_packed(self) -> "PlainReads":
+        """seq as in a BAM record (two codes per byte, every read on a byte boundary; qual padded alike)."""
+        if self.seq_nibbles:
+            return self
+        u = self.unpacked()
+        n = u.n_reads
+        lq = u.l_qseq.astype(np.int64)
+        span = (lq + 1) & ~1
+        soff = np.zeros(n + 1, np.uint64)
+        np.cumsum(span, out=soff[1:])
+        total = int(soff[-1])
+        codes = np.zeros(total, np.uint8)
+        qual = np.zeros(total, np.uint8)
+        if total:
+            dst = np.repeat(soff[:-1].astype(np.int64) - u.seq_off[:-1].astype(np.int64), lq) + np.arange(int(lq.sum()), dtype=np.int64)
+            codes[dst] = u.seq & 15
+            qual[dst] = u.qual
+        seq = ((codes[0::2] << 4) | codes[1::2]).astype(np.uint8)
+        return PlainReads(u.ref_id, u.pos, u.mapq, u.nm, u.l_qseq, u.cigar_off, u.cigar, soff, seq, qual, u.flag, True)
 
     @property
     def n_reads(self) -> int:
@@ -65,6 +115,8 @@ class PlainReads:
 
     def select(self, idx) -> "PlainReads":
         """Sub-select / reorder reads (idx: index array or slice)."""
+        if self.seq_nibbles:
+            return self.unpacked().select(idx).nibble_packed()
         idx = np.arange(self.n_reads)[idx] if isinstance(idx, slice) else np.asarray(idx, dtype=np.int64)
         ncig = (self.cigar_off[1:] - self.cigar_off[:-1]).astype(np.int64)[idx]
         nseq = (self.seq_off[1:] - self.seq_off[:-1]).astype(np.int64)[idx]
@@ -87,6 +139,8 @@ class PlainReads:
 
     @staticmethod
     def concat(parts: list["PlainReads"]) -> "PlainReads":
+        if any(p.seq_nibbles for p in parts):
+            parts = [p.unpacked() for p in parts]
         coffs, soffs = [np.zeros(1, np.uint64)], [np.zeros(1, np.uint64)]
         cb = sb = 0
         for p in parts:

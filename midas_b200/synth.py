@@ -182,6 +182,25 @@ def synth_snps(seed=SEED_C2, n_species=1, contigs_per_species=1, contig_len=4_00
     return ref, reads
 
 
+def genes_model(seed, n_species, genes_per_species, read_len, abundance="lognormal", n_markers=15):
+    """The pangenome of the C3 recipe: (gene_len int64 [n_genes], read weight per gene, gene_species, marker index
+    or -1). Gene length = clip(lognormal(ln 900, 0.6), 150, 20000); species abundance lognormal(sigma=1);
+    per-gene copy-number variation inside a species, 15 % of the genes absent."""
+    L = int(read_len)
+    rng = _rng(seed, 0)
+    n_genes = n_species * genes_per_species
+    glen = np.clip(rng.lognormal(np.log(900.0), 0.6, n_genes), max(150, L + 1), 20000).astype(np.int64)
+    gene_species = np.repeat(np.arange(n_species, dtype=np.int32), genes_per_species)
+    sp_w = _weights(abundance, n_species, rng)
+    gw = rng.lognormal(0, 0.5, n_genes) * (rng.random(n_genes) > 0.15) * glen
+    gw = sp_w[gene_species] * gw / np.bincount(gene_species, weights=gw, minlength=n_species)[gene_species]
+    marker = np.full(n_genes, -1, np.int32)
+    for s in range(n_species):
+        pick = rng.choice(genes_per_species, size=min(n_markers, genes_per_species), replace=False)
+        marker[s * genes_per_species + pick] = np.arange(len(pick), dtype=np.int32)
+    return glen, gw, gene_species, marker
+
+
 def synth_genes(seed=SEED_C3, n_species=100, genes_per_species=20_000, n_reads=50_000_000,
                 read_len=150, abundance="lognormal", chunk=500_000, threads=None, n_markers=15):
     """SURVEY §8d C3 recipe: reads in random (file) order over a multi-species pangenome.
@@ -192,19 +211,9 @@ def synth_genes(seed=SEED_C3, n_species=100, genes_per_species=20_000, n_reads=5
     marker_ids: int32 [n_genes] marker index or -1).
     """
     L = int(read_len)
-    rng = _rng(seed, 0)
     n_genes = n_species * genes_per_species
-    glen = np.clip(rng.lognormal(np.log(900.0), 0.6, n_genes), max(150, L + 1), 20000).astype(np.int64)
-    gene_species = np.repeat(np.arange(n_species, dtype=np.int32), genes_per_species)
-    sp_w = _weights(abundance, n_species, rng)
-    # per-gene copy-number variation inside a species, some genes absent
-    gw = rng.lognormal(0, 0.5, n_genes) * (rng.random(n_genes) > 0.15) * glen
-    gw = sp_w[gene_species] * gw / np.bincount(gene_species, weights=gw, minlength=n_species)[gene_species]
+    glen, gw, gene_species, marker = genes_model(seed, n_species, genes_per_species, L, abundance, n_markers)
     cdf = np.cumsum(gw / gw.sum())
-    marker = np.full(n_genes, -1, np.int32)
-    for s in range(n_species):
-        pick = rng.choice(genes_per_species, size=min(n_markers, genes_per_species), replace=False)
-        marker[s * genes_per_species + pick] = np.arange(len(pick), dtype=np.int32)
 
     bounds = list(range(0, n_reads, chunk)) + [n_reads]
     jobs = [(ci, bounds[ci], bounds[ci + 1]) for ci in range(len(bounds) - 1)]

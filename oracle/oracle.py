@@ -64,6 +64,7 @@ def snps_pileup(reads, ref, filters, threads=1, species_ranges=None):
     parallelism, one task per species (midas/run/snps.py:225-228).
     """
     L = lib()
+    reads = reads.unpacked()       # the C restatement reads one base code per byte
     g_total = int(ref.contig_len.sum(dtype=np.int64))
     n_sp = ref.n_species
     f = _of(filters)
@@ -110,6 +111,7 @@ def snps_pileup(reads, ref, filters, threads=1, species_ranges=None):
 def genes_coverage(reads, gene_len, filters):
     """Returns dict(aligned u64[n_genes], mapped u64[n_genes], mapped_bp u64[n_genes], depth f64[n_genes])."""
     L = lib()
+    reads = reads.unpacked()
     gene_len = np.ascontiguousarray(gene_len, np.uint32)
     ng = len(gene_len)
     al = np.zeros(ng, np.uint64); mp = np.zeros(ng, np.uint64); bp = np.zeros(ng, np.uint64)
@@ -166,6 +168,7 @@ def py_keep_read(cig, l_qseq, nm, mapq, qual, f):
 
 
 def py_snps_pileup(reads, ref, filters):
+    reads = reads.unpacked()
     g_total = int(ref.contig_len.sum(dtype=np.int64))
     coff = np.concatenate(([0], np.cumsum(ref.contig_len.astype(np.int64))))
     counts = np.zeros((4, g_total), np.uint64)

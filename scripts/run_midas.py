@@ -78,9 +78,10 @@ def gene_arguments():
     p.add_argument("--mapq", type=int, default=0)
     p.add_argument("--aln_cov", type=float, default=0.75)
     p.add_argument("--trim", type=int, default=0)
-    p.add_argument("--no_exact_order", dest="exact_order", action="store_false", default=True,
-                   help="sum mapped bp as an integer and divide once (faster; coverage within 1e-12 of the "
-                        "reference's running float sum instead of bit-equal)")
+    p.add_argument("--exact_order", dest="exact_order", action="store_true", default=False,
+                   help="reproduce the reference's running float sum of alen/gene_length in BAM order bit for bit "
+                        "(adds a device sort); default: sum mapped bp as an integer and divide once, coverage "
+                        "within 1e-12 of the reference")
     return vars(p.parse_args())
 
 

@@ -62,11 +62,19 @@ def test_native_reader_agrees_with_python_reader(tmp_path):
     p = str(tmp_path / "n.bam")
     bam.write_bam(p, ref.contig_names, ref.contig_len, reads)
     n1, l1, r1 = bam.read_bam(p)
+    fields = ("ref_id", "pos", "mapq", "nm", "l_qseq", "cigar_off", "cigar", "seq_off", "seq", "qual", "flag")
     for threads in (1, 4):
-        n2, l2, r2 = lib.read_bam(p, threads)
-        assert n1 == n2 and [int(x) for x in l1] == l2
-        for f in ("ref_id", "pos", "mapq", "nm", "l_qseq", "cigar_off", "cigar", "seq_off", "seq", "qual", "flag"):
+        n2, l2, r2 = lib.read_bam(p, threads, seq_bytes=True)
+        assert n1 == n2 and [int(x) for x in l1] == l2 and not r2.seq_nibbles
+        for f in fields:
             assert np.array_equal(getattr(r1, f), getattr(r2, f)), f
+        # default: seq as it lies in the file (two codes per byte, every read on a byte boundary)
+        _, _, r3 = lib.read_bam(p, threads)
+        assert r3.seq_nibbles and not np.any(r3.seq_off & np.uint64(1))
+        u = r3.unpacked()
+        for f in fields:
+            assert np.array_equal(getattr(r1, f), getattr(u, f)), f
+        assert np.array_equal(r1.nibble_packed().seq, r3.seq) and np.array_equal(r1.nibble_packed().qual, r3.qual)
     assert r1.n_reads == reads.n_reads - len(range(0, reads.n_reads, 97))
 
 

@@ -24,6 +24,10 @@ def _check(ctx, gref, greads, filters):
             assert np.array_equal(out["depth"].view(np.uint64), exp["depth"].view(np.uint64))
         else:
             assert np.allclose(out["depth"], exp["depth"], rtol=1e-12, atol=0)
+        # decoded records in, re-layout on the GPU: the same bits
+        for r in (greads, greads.nibble_packed()):
+            out2 = ctx.genes_coverage_plain(r, gref.contig_len, filters, exact_order=exact)
+            assert np.array_equal(out2.view(np.uint8), out.view(np.uint8))
 
 
 @pytest.mark.parametrize("seed,n_species,gps,n_reads,L", [

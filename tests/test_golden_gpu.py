@@ -40,12 +40,23 @@ def test_genes_pipeline_writes_the_reference_files(case, tmp_path):
     ref, reads, filters, extra = load_case(case)
     db, out = fixtures.write_genes_fixture(str(tmp_path), ref, reads, np.array(extra["marker"], np.int32))
     with pytest.warns(RuntimeWarning):
-        genes.run_pipeline(_args(out, db, filters))          # exact_order=True: bit-exact float text
+        genes.run_pipeline(_args(out, db, filters, exact_order=True))    # --exact_order: bit-exact float text
     exp = expected(case)
     for sid in ref.species_ids:
         got = gzip.open(os.path.join(out, "genes", "output", sid + ".genes.gz"), "rb").read()
         assert got == exp[sid + ".genes.tsv"], sid
     assert open(os.path.join(out, "genes", "summary.txt"), "rb").read() == exp["summary.txt"]
+    # the default (one division of the integer sum, no device sort): same counts, floats within 1e-12
+    with pytest.warns(RuntimeWarning):
+        genes.run_pipeline(_args(out, db, filters))
+    for sid in ref.species_ids:
+        got = gzip.open(os.path.join(out, "genes", "output", sid + ".genes.gz"), "rt").read().splitlines()
+        want = exp[sid + ".genes.tsv"].decode().splitlines()
+        assert got[0] == want[0] and len(got) == len(want)
+        for g, w in zip(got[1:], want[1:]):
+            g, w = g.split("\t"), w.split("\t")
+            assert g[:2] == w[:2]
+            assert np.allclose([float(g[2]), float(g[3])], [float(w[2]), float(w[3])], rtol=1e-12, atol=0)
 
 
 def test_cli_snps_and_genes(tmp_path):
@@ -69,7 +80,7 @@ def test_cli_snps_and_genes(tmp_path):
     assert r.returncode != 0 and "genomes.bam not found" in r.stderr
     gref, greads, gfilters, gextra = load_case("genes_c3_small")
     db2, out2 = fixtures.write_genes_fixture(str(tmp_path / "g"), gref, greads, np.array(gextra["marker"], np.int32))
-    r = subprocess.run([sys.executable, cli, "genes", out2, "-d", db2], capture_output=True, text=True)
+    r = subprocess.run([sys.executable, cli, "genes", out2, "-d", db2, "--exact_order"], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     gexp = expected("genes_c3_small")
     for sid in gref.species_ids:

@@ -31,10 +31,9 @@ def test_geometry_fields_follow_pysam_query_alignment():
     h = pk.hdr[0]
     assert h["l_qseq"] == 52 and h["q_start"] == 5 and h["alen"] == 40       # snps.py:145-146
     assert h["ref_span"] == 42 and h["loc"] == 10 and not (h["flags"] & 1)
+    # three runs: cplx points at the read's raw CIGAR words, which the kernels walk
     rec = pk.cigar[int(pk.cplx[0]):]
-    assert rec[0] == 3
-    runs = [(int(rec[1 + 2 * k]) & 0xFFFF, int(rec[1 + 2 * k]) >> 16, int(rec[2 + 2 * k])) for k in range(3)]
-    assert runs == [(5, 20, 0), (27, 10, 20), (37, 8, 34)]                   # (q0, len, x0)
+    assert [(int(w) & 15, int(w) >> 4) for w in rec[:9]] == cigar_tuples(r, 0)
 
 
 def test_simple_reads_and_soft_clips():
@@ -59,7 +58,7 @@ def test_two_run_reads_that_do_not_fit_the_run_word_keep_a_record():
     pk = lib.PackedReads(_one([(OP_M, 30), (OP_D, 300), (OP_M, 20)], pos=100), lay(), "snps")
     assert not (pk.hdr[0]["flags"] & 8)
     rec = pk.cigar[int(pk.cplx[0]):]
-    assert rec[0] == 2 and rec[4] == 330
+    assert [(int(w) & 15, int(w) >> 4) for w in rec[:3]] == [(OP_M, 30), (OP_D, 300), (OP_M, 20)]
     pk = lib.PackedReads(_one([(OP_D, 2), (OP_M, 30), (OP_I, 3), (OP_M, 20)], pos=100), lay(), "snps")
     assert not (pk.hdr[0]["flags"] & 8)            # first run not at the read's position
 
@@ -205,6 +204,30 @@ def test_inputs_on_which_the_reference_raises(kw, status):
     with pytest.raises(lib.MidasB200Error) as e:
         lib.PackedReads(r, lay(), "snps")
     assert e.value.status == status
+
+
+def test_nibble_packed_input_packs_identically():
+    """seq as it lies in a BAM record (two codes per byte, odd reads padded) gives the same packed batch."""
+    rng = np.random.default_rng(4)
+    ref = gen.make_ref(rng, 2, 2, 500, 900)
+    reads = gen.random_reads(5, ref, 400, max_len=90)
+    L = lib.Layout.of(ref)
+    a = lib.PackedReads(reads, L, "snps", sort=True)
+    nb = reads.nibble_packed()
+    assert nb.seq_nibbles and np.array_equal(nb.unpacked().seq, reads.seq)
+    b = lib.PackedReads(nb, L, "snps", sort=True)
+    for f in ("hdr", "vec_off", "cplx", "cigar", "planes", "long_idx"):
+        assert np.array_equal(getattr(a, f), getattr(b, f)), f
+
+
+def test_genes_layout_has_no_coordinate_limit():
+    L = lib.Layout.genes(3_000_000_000)          # more "positions" than a 32-bit padded genome could hold
+    r = _one([(OP_M, 10)])
+    r.ref_id[:] = 5
+    pk = lib.PackedReads(r, L, "genes")
+    assert pk.hdr[0]["loc"] == 5
+    with pytest.raises(lib.MidasB200Error):
+        lib.PackedReads(r, L, "snps")
 
 
 def test_genes_mode_keeps_file_order_and_gene_index():

@@ -28,6 +28,17 @@ def _check(ctx, ref, reads, filters):
     for c in range(lay.n_contigs):
         o = int(lay.contig_goff[c]); mask[o:o + int(lay.contig_len[c])] = False
     assert not counts[:, mask].any()
+    # the host-buffer call of the product path: decoded records in, re-layout on the GPU (k_pack_*)
+    key = (reads.ref_id.astype(np.int64) << 32) | reads.pos.astype(np.int64)
+    if bool(np.all(np.diff(key) >= 0)):                    # BAM coordinate order
+        for r in (reads, reads.nibble_packed()):
+            c2, s2 = ctx.snps_pileup_plain(r, lay, filters)
+            assert np.array_equal(c2, counts), "plain-record path differs from the host-packed path"
+            assert np.array_equal(s2, stats)
+    else:
+        with pytest.raises(lib.MidasB200Error) as e:
+            ctx.snps_pileup_plain(reads, lay, filters)
+        assert e.value.status == -6
 
 
 @pytest.mark.parametrize("seed,n_species,cps,clen,n_reads,L", [
@@ -114,8 +125,7 @@ def test_full_size_c2(ctx):
     ref, reads = synth.synth_snps(seed=synth.SEED_C2, n_species=1, contigs_per_species=1, contig_len=4_000_000,
                                   n_reads=5_000_000, read_len=150, keep_ref_seq=False)
     lay = lib.Layout.of(ref)
-    pk = lib.PackedReads(reads, lay, "snps")
-    counts, stats = ctx.snps_pileup(pk, lay, Filters())
+    counts, stats = ctx.snps_pileup_plain(reads, lay, Filters())
     got = lay.unpad(counts)
     depth = got.astype(np.uint64).sum(0)
     assert int(stats["total_depth"][0]) == int(depth.sum())

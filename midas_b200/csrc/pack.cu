@@ -388,14 +388,19 @@ __global__ void __launch_bounds__(256) k_pack_fill(const Plain in, const uint4* 
   const uint32_t n_vec = (uint32_t)meta->n_vec;
   const uint32_t lane = threadIdx.x & 31;
   const uint64_t wg = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-  for (uint64_t j = wg; j < n; j += nw) {
+  const uint64_t n_slots = (n + MB_GROUP - 1) / MB_GROUP * MB_GROUP;
+  for (uint64_t j = wg; j < n_slots; j += nw) {
+    const uint64_t g0 = (j / MB_GROUP) * MB_GROUP, g1 = g0 + MB_GROUP;
+    const uint32_t units = ((g1 < n ? __ldg(&vec_off[g1]) : n_vec) - __ldg(&vec_off[g0])) / MB_GROUP;
+    uint32_t* __restrict__ reg = planes + ((size_t)__ldg(&vec_off[g0]) + (j - g0)) * 8;
+    if (j >= n) {                                   // the unused slots of the last group: zeros, as the host packer
+      for (uint32_t w = lane; w < units * 8; w += 32) reg[(size_t)(w >> 3) * (8 * MB_GROUP) + (w & 7u)] = 0u;
+      continue;
+    }
     const uint4 h = __ldg(&hdr[j]);
     const uint64_t i = src_of[j];
     const uint32_t lq = h.y & 0xffffu, qstart = h.z & 0xffffu, span = h.w & 0xffffu, fl = h.w >> 24;
     const uint32_t n_blk = (lq + MB_BLOCK - 1) / MB_BLOCK;
-    const uint64_t g0 = (j / MB_GROUP) * MB_GROUP, g1 = g0 + MB_GROUP;
-    const uint32_t units = ((g1 < n ? __ldg(&vec_off[g1]) : n_vec) - __ldg(&vec_off[g0])) / MB_GROUP;
-    uint32_t* __restrict__ reg = planes + (size_t)__ldg(&vec_off[j]) * 8;
     const uint64_t so = in.seq_off[i];
     const uint8_t* __restrict__ qp = in.qual + so;
     const uint32_t* __restrict__ cig = in.cigar + in.cigar_off[i];

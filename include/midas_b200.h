@@ -187,6 +187,8 @@ typedef struct {
   uint32_t n_long;           /* number of MB_RF_LONG reads */
   uint32_t q_planes;         /* Phred bit planes per block: 6 or 7 */
   uint32_t n_planes;         /* words per block: 3 + q_planes (snps) or q_planes (genes) */
+  uint32_t max_units;        /* largest number of 32-byte units per read of any group */
+  uint32_t reserved;
   const uint32_t* long_idx;  /* [n_long] indices of the MB_RF_LONG reads (ascending from mb_pack_reads, any order
                                 from the device packer) */
   const mb_read_hdr* hdr;    /* [n_reads] */

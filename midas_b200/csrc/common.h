@@ -51,7 +51,7 @@ struct mb_packed_owner {  // allocation record behind a library-owned mb_packed_
 
 struct mb_dev_reads {
   uint64_t n_reads, n_vec, n_cigar_words, total_bases;
-  uint32_t max_ref_span, sorted, row_words, n_long, q_planes, n_planes;
+  uint32_t max_ref_span, sorted, row_words, n_long, q_planes, n_planes, max_units;
   uint32_t* long_idx;
   mb_read_hdr* hdr;
   uint32_t* vec_off;

@@ -318,6 +318,7 @@ int upload_reads(mb_ctx* c, const mb_packed_reads* h, mb_dev_reads* d, bool stag
   d->n_vec = h->n_vec;
   d->q_planes = h->q_planes;
   d->n_planes = h->n_planes;
+  d->max_units = h->max_units;
   d->n_cigar_words = h->n_cigar_words;
   d->total_bases = h->total_bases;
   d->max_ref_span = h->max_ref_span;

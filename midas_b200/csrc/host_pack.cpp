@@ -387,7 +387,7 @@ extern "C" int mb_pack_reads(const mb_plain_reads* in, const mb_layout* L, int m
   const uint32_t P0 = mode == 0 ? 3u : 0u;                      // first Phred plane
   std::vector<uint32_t> unit_off(n + 1), cg_off(n + 1);
   uint64_t nb = 0, ncw = 0, tot_bases = 0;
-  uint32_t max_span = 0;
+  uint32_t max_span = 0, max_units = 0;
   {  // groups of MB_GROUP reads, units interleaved: units per read of a group = the largest of its reads
     const uint64_t n_groups = (n + MB_GROUP - 1) / MB_GROUP;
     std::vector<uint32_t> g_units(n_groups);
@@ -402,6 +402,7 @@ extern "C" int mb_pack_reads(const mb_plain_reads* in, const mb_layout* L, int m
     });
     std::vector<uint64_t> g_off(n_groups + 1, 0);
     for (uint64_t gi = 0; gi < n_groups; ++gi) g_off[gi + 1] = g_off[gi] + (uint64_t)g_units[gi] * MB_GROUP;
+    for (uint64_t gi = 0; gi < n_groups; ++gi) max_units = std::max(max_units, g_units[gi]);
     nb = g_off[n_groups];
     if (nb > 0xFFFFFFF0ull) return mb::fail(MB_EOVERFLOW, "mb_pack_reads: batch too large for 32-bit unit offsets");
     parallel_for(n, n_threads, [&](uint64_t lo, uint64_t hi, int) {
@@ -597,6 +598,7 @@ extern "C" int mb_pack_reads(const mb_plain_reads* in, const mb_layout* L, int m
   o->pub.n_long = (uint32_t)n_long;
   o->pub.q_planes = q_planes;
   o->pub.n_planes = NP;
+  o->pub.max_units = max_units;
   o->pub.long_idx = long_idx;
   o->pub.hdr = hdr;
   o->pub.vec_off = voff;

@@ -35,7 +35,7 @@ struct PackMeta {
   unsigned long long total_bases;
   unsigned long long n_vec;
   unsigned long long n_cig;        // cigar_off[n]
-  uint32_t unsorted, q_or, max_span, n_long, row_words, q_planes, n_planes, long_fill;
+  uint32_t unsorted, q_or, max_span, n_long, row_words, q_planes, n_planes, long_fill, max_units, pad_;
   uint32_t hist[256];
 };
 
@@ -276,8 +276,9 @@ __global__ void k_pack_finish(PackMeta* meta, uint64_t n, int mode, const uint64
 
 // ---- 32-byte units per read of a group (= the largest of its 32 reads): one warp per group
 __global__ void __launch_bounds__(256) k_pack_units(const uint16_t* __restrict__ nblk, uint64_t n, uint64_t n_groups,
-                                                    const PackMeta* __restrict__ meta, uint32_t* g_units) {
+                                                    PackMeta* meta, uint32_t* g_units) {
   const uint32_t NP = meta->n_planes;
+  uint32_t umax = 0;
   const int lane = threadIdx.x & 31;
   const uint64_t wg = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((uint64_t)gridDim.x * blockDim.x) >> 5;
   for (uint64_t g = wg; g < n_groups; g += nw) {
@@ -286,7 +287,9 @@ __global__ void __launch_bounds__(256) k_pack_units(const uint16_t* __restrict__
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) u = max(u, __shfl_xor_sync(0xffffffffu, u, o));
     if (lane == 0) g_units[g] = u;
+    umax = max(umax, u);
   }
+  if (lane == 0 && umax) atomicMax(&meta->max_units, umax);
 }
 
 constexpr int SCAN_T = 1024, SCAN_PER = 4, SCAN_CHUNK = SCAN_T * SCAN_PER;
@@ -609,6 +612,7 @@ int pack_on_device(mb_ctx* c, const mb_plain_reads* in, const mb_layout* L, int 
   d->n_long = hm->n_long;
   d->q_planes = hm->q_planes;
   d->n_planes = hm->n_planes;
+  d->max_units = hm->max_units;
   rc = pack_alloc(c, staged, 36, (size_t)d->n_vec * 32, (void**)&d->planes);
   if (!rc) rc = pack_alloc(c, staged, 37, 4 * (size_t)d->n_long, (void**)&d->long_idx);
   if (rc) return rc;
@@ -705,6 +709,7 @@ extern "C" int mb_reads_download(mb_ctx* c, const mb_dev_reads* r, mb_packed_rea
   o->pub.n_long = r->n_long;
   o->pub.q_planes = r->q_planes;
   o->pub.n_planes = r->n_planes;
+  o->pub.max_units = r->max_units;
   o->pub.hdr = (mb_read_hdr*)o->buf[0];
   o->pub.vec_off = (uint32_t*)o->buf[1];
   o->pub.cplx = (uint32_t*)o->buf[2];

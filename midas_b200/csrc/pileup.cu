@@ -37,6 +37,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cmath>
+#include <algorithm>
 
 #include "common.h"
 
@@ -78,6 +79,8 @@ struct PileParams {
   int mapq;
   uint32_t baseq;             // per-base threshold (0: every candidate base counts)
   uint32_t defer_restat;      // 1: long reads follow, position stats are recomputed afterwards
+  uint32_t slot_units;        // TMA staging: 32-byte units per read a warp's shared-memory slot holds
+  uint32_t n_reads;
   uint32_t* ovf;              // set to 1 when a u32 counter saturates (MB_EOVERFLOW)
   unsigned long long* mirror; // peer-memory copy of the stats rows (multi-GPU), written by the last CTA; or null
   uint32_t n_species;
@@ -102,6 +105,37 @@ __device__ __forceinline__ void ldg256(const uint32_t* __restrict__ p, uint32_t*
   asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
       : "l"(p));
+}
+
+// ---- asynchronous staging (VAR & 4): one bulk copy (TMA, UBLKCP) per warp and group, completion on an mbarrier
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "MB_WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra MB_DONE_%=;\n"
+      "bra MB_WAIT_%=;\n"
+      "MB_DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void lds256(const uint32_t* p, uint32_t* r) {
+  const uint4 a = *reinterpret_cast<const uint4*>(p), b = *reinterpret_cast<const uint4*>(p + 4);
+  r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w; r[4] = b.x; r[5] = b.y; r[6] = b.z; r[7] = b.w;
 }
 
 __device__ __forceinline__ uint32_t shl_clamp(uint32_t v, uint32_t n) {   // v << n, 0 for n >= 32
@@ -175,7 +209,8 @@ __global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : 2) k_pi
   constexpr int NCOL = KT / 32;            // 32-position columns per tile
   constexpr int NT = NCOL * KSUB;          // threads per CTA
   constexpr int FIRST_N = NCOL + WMAX + 1;
-  extern __shared__ __align__(16) uint32_t smem[];
+  constexpr bool TMA = (VAR & 4) != 0;          // bit 2: the planes arrive by bulk copy into a per-warp slot
+  extern __shared__ __align__(128) uint32_t smem[];
   constexpr uint32_t W = (uint32_t)WT;          // row words (compile time: every per-lane loop below unrolls)
   constexpr int NP = 3 + NQ;                    // words per 32-base block: seq lo, seq hi, candidate, Phred bits
   uint32_t tmk[NQ];                             // bit k of baseq, spread over a word (warp-uniform)
@@ -193,6 +228,12 @@ __global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : 2) k_pi
   __shared__ unsigned long long s_red[4];                             // covered, depth, aligned, mapped
   __shared__ uint32_t s_tile, s_nmax;
   __shared__ uint8_t s_mod[NCOL + 2 * WMAX + 1];                      // x % W for small x
+  __shared__ __align__(8) unsigned long long s_mbar[NT / 32];         // TMA: one per warp
+  // TMA: slot of warp w = slot_units x {32 lanes x 32 bytes}, as the group lies in HBM; then one all-zero unit
+  uint32_t* const s_slots = reinterpret_cast<uint32_t*>(s_rows + ((size_t)p.rmax + 1) * W);
+  uint32_t* const my_slot = s_slots + (size_t)(threadIdx.x >> 5) * p.slot_units * (8 * MB_GROUP);
+  const uint32_t* const s_zero = s_slots + (size_t)(NT / 32) * p.slot_units * (8 * MB_GROUP);
+  uint32_t mb_phase = 0;                                               // parity of my warp's next wait
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int col = tid >> 2, ksub = tid & 3;                           // COUNT role
@@ -200,6 +241,11 @@ __global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : 2) k_pi
   for (int i = tid; i < VCL * NCOL; i += NT) s_vc[i] = make_uint4(0, 0, 0, 0);
   if (tid < (int)W) s_rows[p.rmax * W + tid] = make_uint4(0, 0, 0, 0);   // row rmax stays empty: COUNT reads it for padding
   for (int i = tid; i < NCOL + 2 * WMAX + 1; i += NT) s_mod[i] = (uint8_t)((uint32_t)i % W);
+  if (TMA) {
+    if (tid < NT / 32) mbar_init(&s_mbar[tid], 1);
+    if (tid < 8) const_cast<uint32_t*>(s_zero)[tid] = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
 
   uint32_t next_tile = 0;                                             // thread 0: the tile after the current one
   if (tid == 0) next_tile = atomicAdd(p.sched, 1u);
@@ -213,6 +259,16 @@ __global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : 2) k_pi
     if (tid == 0) next_tile = atomicAdd(p.sched, 1u);                 // its latency hides behind this tile's work
     const uint32_t ts = tile * KT;
     const uint32_t r0 = p.tile_rng[2 * tile], r1 = p.tile_rng[2 * tile + 1];
+    const uint32_t r0a = TMA ? (r0 & ~31u) : r0;                       // TMA: rounds start on a group boundary
+    const uint32_t n_groups = r1 > r0a ? (r1 - r0a + 31u) >> 5 : 0u;   // (the leading reads end before the tile: empty rows)
+    const uint32_t GR = p.rmax >> 5;                                   // groups per round
+    if (TMA && lane == 0 && (uint32_t)(tid >> 5) < n_groups) {         // my warp's first group of this tile
+      const uint32_t ra = r0a + 32u * (uint32_t)(tid >> 5);
+      const uint32_t v0 = __ldg(&p.vec_off[ra]), v1 = __ldg(&p.vec_off[min(ra + 32u, p.n_reads)]);
+      const uint32_t units = min((v1 - v0) >> 5, p.slot_units);
+      mbar_expect_tx(&s_mbar[tid >> 5], units * 1024u);
+      bulk_g2s(my_slot, p.planes + (size_t)v0 * 8, units * 1024u, &s_mbar[tid >> 5]);
+    }
     const uint32_t tcol = ts >> 5, tb = tcol % W;
     const uint32_t slot_c = s_mod[tb + (uint32_t)col];                // where my column's word sits in a row
 
@@ -279,41 +335,10 @@ __global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : 2) k_pi
       col_rows = 0;
     };
 
-    uint32_t pass_rows = 0;
-    bool accumulate = false;
-    uint4 nh = make_uint4(0, 0, 0, 0);                         // header, block offset, run word and predecessor
-    uint32_t nb0 = 0, ncw = 0, nprev = 0;                       // of this thread's next read: one step ahead
-    for (uint32_t rb = r0; rb < r1; rb += p.rmax) {
-      const int n = (int)min(p.rmax, r1 - rb);
-      if (pass_rows + (uint32_t)n > PASS_ROWS) {  // keep the shared counters below 2^VCL
-        expand(accumulate, false);
-        accumulate = true;
-        pass_rows = 0;
-      }
-      pass_rows += (uint32_t)n;
-      __syncthreads();
-      // ---- STAGE: one thread per read, everything in registers: header filters (snps.py:148,154,157),
-      // row index table, the read's bit planes as independent 256-bit loads, bit-sliced base-quality test,
-      // mean-quality filter, CIGAR placement, row store
-      if (rb == r0) {                                          // later rounds: requested before the previous COUNT
-        nh = make_uint4(0, 0, 0, 0); nb0 = 0; ncw = 0; nprev = 0;
-      }
-      if (rb == r0 && tid < n) {
-        nh = __ldg(&p.hdr[rb + tid]);
-        nb0 = __ldg(&p.vec_off[rb + tid]);
-        ncw = __ldg(&p.cplx[rb + tid]);
-        if (tid > 0) nprev = __ldg(&p.hdr[rb + tid - 1].x);
-      }
-      for (int i = tid; i < n; i += NT) {
-        const uint32_t r = rb + (uint32_t)i;
-        const uint4 h = nh;
-        const uint32_t b0 = nb0, cw = ncw, prev_loc = nprev;
-        if (i + NT < n) {
-          nh = __ldg(&p.hdr[r + NT]);
-          nb0 = __ldg(&p.vec_off[r + NT]);
-          ncw = __ldg(&p.cplx[r + NT]);
-          nprev = __ldg(&p.hdr[r + NT - 1].x);
-        }
+    // ---- STAGE of one read (row i of a round of n rows): header filters (snps.py:148,154,157), row index
+    // table, the read's bit planes, bit-sliced base-quality test, mean-quality filter, CIGAR placement, row store
+    auto stage_one = [&](const int i, const int n, const uint4 h, const uint32_t b0, const uint32_t cw,
+                         const uint32_t prev_loc) {
         const uint32_t loc = h.x, lq = h.y & 0xffffu, alen = h.y >> 16, qstart = h.z & 0xffffu, nm = h.z >> 16;
         const uint32_t span = h.w & 0xffffu, mq = (h.w >> 16) & 0xffu, fl = h.w >> 24;
         bool needq = false, ovl = false, owner = false;
@@ -383,7 +408,10 @@ __global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : 2) k_pi
             for (int u = 0; u < NV8; ++u) {
               // every read has a block, i.e. at least NP > 8 words: its first two units always exist; units
               // past the read's end come from one shared all-zero unit (no predicated loads, no zeroed defaults)
-              ldg256((u < 2 || (uint32_t)u < nv8) ? vp + 8 * MB_GROUP * u : p.zero_unit, raw + 8 * u);
+              if (TMA)   // my units of the group's slot: unit u of lane l at (32 u + l) x 32 bytes
+                lds256((u < 2 || (uint32_t)u < nv8) ? my_slot + (8 * MB_GROUP) * u + 8 * lane : s_zero, raw + 8 * u);
+              else
+                ldg256((u < 2 || (uint32_t)u < nv8) ? vp + 8 * MB_GROUP * u : p.zero_unit, raw + 8 * u);
             }
 #pragma unroll
             for (int bl = 0; bl < WT; ++bl) convert(bl, raw + bl * NP);
@@ -520,6 +548,77 @@ __global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : 2) k_pi
 #pragma unroll
           for (int j = 0; j < WT; ++j) dst[j] = make_uint4(0, 0, 0, 0);
         }
+    };
+
+    uint32_t pass_rows = 0;
+    bool accumulate = false;
+    uint4 nh = make_uint4(0, 0, 0, 0);                         // header, block offset, run word and predecessor
+    uint32_t nb0 = 0, ncw = 0, nprev = 0;                       // of this thread's next read: one step ahead
+    for (uint32_t rb = r0a; rb < r1; rb += p.rmax) {
+      const int n = (int)min(p.rmax, r1 - rb);
+      if (pass_rows + (uint32_t)n > PASS_ROWS) {  // keep the shared counters below 2^VCL
+        expand(accumulate, false);
+        accumulate = true;
+        pass_rows = 0;
+      }
+      pass_rows += (uint32_t)n;
+      __syncthreads();
+      // ---- STAGE: one thread per read, everything in registers: header filters (snps.py:148,154,157),
+      // row index table, the read's bit planes as independent 256-bit loads, bit-sliced base-quality test,
+      // mean-quality filter, CIGAR placement, row store
+      if (TMA) {
+        // one aligned group of 32 reads per warp and step; the group's units are one contiguous block in HBM and
+        // arrive by one bulk copy issued a whole group (>= 500 instructions per lane) before they are needed
+        const int wid = tid >> 5;
+        const uint32_t gq = (rb - r0a) >> 5;                                  // first group of this round
+        for (uint32_t g = gq + (uint32_t)wid; g < gq + GR && g < n_groups; g += NT / 32) {
+          const uint32_t r = r0a + 32u * g + (uint32_t)lane;
+          const int i = (int)(r - rb);
+          uint4 h = make_uint4(0, 0, 0, 0);
+          uint32_t cw = 0, prev_loc = 0;
+          if (i < n) {
+            h = __ldg(&p.hdr[r]);
+            cw = __ldg(&p.cplx[r]);
+            if (lane == 0 && i > 0) prev_loc = __ldg(&p.hdr[r - 1].x);
+          }
+          {
+            const uint32_t up = __shfl_up_sync(0xffffffffu, h.x, 1);
+            if (lane > 0) prev_loc = up;
+          }
+          mbar_wait(&s_mbar[wid], mb_phase);                                   // this group's units have landed
+          mb_phase ^= 1u;
+          if (i < n) stage_one(i, n, h, 0u, cw, prev_loc);
+          __syncwarp();
+          if (lane == 0 && g + NT / 32 < n_groups) {                           // my next group, into the same slot
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            const uint32_t ra = r0a + 32u * (g + NT / 32);
+            const uint32_t v0 = __ldg(&p.vec_off[ra]), v1 = __ldg(&p.vec_off[min(ra + 32u, p.n_reads)]);
+            const uint32_t units = min((v1 - v0) >> 5, p.slot_units);
+            mbar_expect_tx(&s_mbar[wid], units * 1024u);
+            bulk_g2s(my_slot, p.planes + (size_t)v0 * 8, units * 1024u, &s_mbar[wid]);
+          }
+        }
+      } else {
+      if (rb == r0) {                                          // later rounds: requested before the previous COUNT
+        nh = make_uint4(0, 0, 0, 0); nb0 = 0; ncw = 0; nprev = 0;
+      }
+      if (rb == r0 && tid < n) {
+        nh = __ldg(&p.hdr[rb + tid]);
+        nb0 = __ldg(&p.vec_off[rb + tid]);
+        ncw = __ldg(&p.cplx[rb + tid]);
+        if (tid > 0) nprev = __ldg(&p.hdr[rb + tid - 1].x);
+      }
+      for (int i = tid; i < n; i += NT) {
+        const uint32_t r = rb + (uint32_t)i;
+        const uint4 h = nh;
+        const uint32_t b0 = nb0, cw = ncw, prev_loc = nprev;
+        if (i + NT < n) {
+          nh = __ldg(&p.hdr[r + NT]);
+          nb0 = __ldg(&p.vec_off[r + NT]);
+          ncw = __ldg(&p.cplx[r + NT]);
+          nprev = __ldg(&p.hdr[r + NT - 1].x);
+        }
+        stage_one(i, n, h, b0, cw, prev_loc);
       }
       if (rb + p.rmax < r1) {   // the first read of my next round: requested now, in flight during COUNT
         const uint32_t nr = rb + p.rmax + (uint32_t)tid;
@@ -530,6 +629,7 @@ __global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : 2) k_pi
           ncw = __ldg(&p.cplx[nr]);
           if (tid > 0) nprev = __ldg(&p.hdr[nr - 1].x);
         }
+      }
       }
       __syncthreads();
       // ---- COUNT: my column's rows of this round, KSUB-strided, 8 rows per carry-save tree into
@@ -775,17 +875,26 @@ __global__ void __launch_bounds__(256) k_restat(const uint32_t* __restrict__ cou
 
 // the row widths (and Phred plane counts) the tile kernel is instantiated for; a batch runs at the smallest
 // width >= its row_words
-struct PileKernel { uint32_t W; void (*fn)(const PileParams); uint32_t kt; };   // kt: positions per tile
-PileKernel pick_kernel(uint32_t row_words, uint32_t q_planes) {
-#define MB_PK(W, Q) {W, k_pileup_v2<W, Q, 0>, 2048}
+struct PileKernel { uint32_t W; void (*fn)(const PileParams); uint32_t kt; bool tma; };   // kt: positions per tile
+PileKernel pick_kernel(uint32_t row_words, uint32_t q_planes, bool want_tma) {
+#define MB_PT(W, Q) {W, k_pileup_v2<W, Q, 4>, 2048, true}
+  static const PileKernel t6[] = {MB_PT(3, 6), MB_PT(4, 6), MB_PT(5, 6), MB_PT(6, 6), MB_PT(7, 6), MB_PT(8, 6)};
+  static const PileKernel t7[] = {MB_PT(3, 7), MB_PT(4, 7), MB_PT(5, 7), MB_PT(6, 7), MB_PT(7, 7), MB_PT(8, 7)};
+#undef MB_PT
+  if (want_tma && row_words <= 8) {
+    const PileKernel* k = q_planes == 6 ? t6 : t7;
+    for (int i = 0; i < 6; ++i)
+      if (k[i].W >= row_words) return k[i];
+  }
+#define MB_PK(W, Q) {W, k_pileup_v2<W, Q, 0>, 2048, false}
   static const PileKernel k6[] = {MB_PK(3, 6), MB_PK(4, 6), MB_PK(5, 6),  MB_PK(6, 6),  MB_PK(7, 6),
                                   MB_PK(8, 6), MB_PK(10, 6), MB_PK(12, 6), MB_PK(16, 6)};
   static const PileKernel k7[] = {MB_PK(3, 7), MB_PK(4, 7), MB_PK(5, 7),  MB_PK(6, 7),  MB_PK(7, 7),
                                   MB_PK(8, 7), MB_PK(10, 7), MB_PK(12, 7), MB_PK(16, 7)};
 #undef MB_PK
   // experiment switches (MB_PILE_VAR, W = 6 with 6 Phred planes only)
-  static const PileKernel kx[4] = {{6, k_pileup_v2<6, 6, 0>, 2048}, {6, k_pileup_v2<6, 6, 1>, 2048},
-                                   {6, k_pileup_v2<6, 6, 2>, 1024}, {6, k_pileup_v2<6, 6, 3>, 1024}};
+  static const PileKernel kx[4] = {{6, k_pileup_v2<6, 6, 0>, 2048, false}, {6, k_pileup_v2<6, 6, 1>, 2048, false},
+                                   {6, k_pileup_v2<6, 6, 2>, 1024, false}, {6, k_pileup_v2<6, 6, 3>, 1024, false}};
   if (const char* e = getenv("MB_PILE_VAR")) {
     const long v = atol(e);
     if (v > 0 && v < 4 && q_planes == 6 && row_words > 5 && row_words <= 6) return kx[v];
@@ -796,8 +905,9 @@ PileKernel pick_kernel(uint32_t row_words, uint32_t q_planes) {
   return k[8];
 }
 
-size_t pile_smem_bytes(uint32_t W, uint32_t rmax, uint32_t ncol) {
-  return sizeof(uint4) * ((size_t)VCL * ncol + ((size_t)rmax + 1) * W);   // + the empty padding row
+size_t pile_smem_bytes(uint32_t W, uint32_t rmax, uint32_t ncol, uint32_t slot_units, uint32_t n_warps) {
+  return sizeof(uint4) * ((size_t)VCL * ncol + ((size_t)rmax + 1) * W)     // + the empty padding row
+         + (slot_units ? (size_t)n_warps * slot_units * 1024 + 32 : 0);    // TMA: one slot per warp + a zero unit
 }
 
 }  // namespace
@@ -817,7 +927,11 @@ extern "C" int mb_snps_pileup_dev(mb_ctx* ctx, const mb_dev_reads* reads, const 
   // shared memory per CTA: two CTAs per SM (override with MB_PILE_SMEM_KB for experiments)
   if (reads->n_planes != 3 + reads->q_planes || (reads->q_planes != 6 && reads->q_planes != 7))
     return mb::fail(MB_EINVAL, "mb_snps_pileup_dev: reads were not packed in snps mode");
-  const PileKernel kern = pick_kernel(reads->row_words, reads->q_planes);
+  // staging variant: bulk copies into per-warp shared-memory slots (MB_PILE_TMA=0 selects the register path)
+  bool want_tma = true;
+  if (const char* e = getenv("MB_PILE_TMA")) want_tma = atol(e) != 0;
+  if (getenv("MB_PILE_VAR")) want_tma = false;
+  const PileKernel kern = pick_kernel(reads->row_words, reads->q_planes, want_tma);
   const uint32_t W = kern.W;                                          // instantiated row width >= row_words
   const uint32_t KT = kern.kt, NCOL = KT / 32, NT = NCOL * KSUB;
   const uint32_t n_ktiles = L->n_tiles * (MB_TILE / KT);
@@ -830,12 +944,12 @@ extern "C" int mb_snps_pileup_dev(mb_ctx* ctx, const mb_dev_reads* reads, const 
     ctx->tile_rng_cap = (size_t)2 * n_ktiles + 2;
   }
   {
-    size_t kb = KT == 2048 ? 100 : 50;                               // 2 / 4 CTAs per SM
+    size_t kb = kern.tma ? 113 : (KT == 2048 ? 100 : 50);            // 2 / 4 CTAs per SM
     if (const char* e = getenv("MB_PILE_SMEM_KB")) { long v = atol(e); if (v >= 24 && v <= 220) kb = (size_t)v; }
     ctx->pile_smem = kb * 1024;
   }
-  const uint32_t attr_bit = 1u << (W + (reads->q_planes == 7 ? 16u : 0u));
-  if (!(ctx->pile_attr_mask & attr_bit) || getenv("MB_PILE_VAR")) {
+  const uint32_t attr_bit = 1u << (W + (reads->q_planes == 7 ? 16u : 0u) + (kern.tma ? 8u : 0u));
+  if (!(ctx->pile_attr_mask & attr_bit) || getenv("MB_PILE_VAR") || getenv("MB_PILE_SMEM_KB")) {
     MB_CUDA_TRY(cudaFuncSetAttribute(kern.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->pile_smem));
     ctx->pile_attr_mask |= attr_bit;
   }
@@ -845,10 +959,26 @@ extern "C" int mb_snps_pileup_dev(mb_ctx* ctx, const mb_dev_reads* reads, const 
     ctx->pile_occ = occ > 0 ? occ : 1;
   }
   const size_t fixed = sizeof(uint4) * (size_t)VCL * NCOL;
-  uint32_t rmax = (uint32_t)((ctx->pile_smem - fixed) / (sizeof(uint4) * W)) - 1u;   // one row is the empty padding row
-  if (rmax > (uint32_t)LANE_ROWS_MAX * KSUB) rmax = LANE_ROWS_MAX * KSUB;
-  if (rmax >= 2u * NT && !getenv("MB_PILE_RAGGED")) rmax = rmax / NT * NT;   // the same number of reads for every thread
-  rmax &= ~7u;
+  uint32_t rmax, slot_units = 0;
+  if (kern.tma) {
+    // per warp one slot of slot_units x 1 KB (the units of a group of 32 reads, as they lie in HBM); what is left
+    // of the shared memory holds the rows of a round, a whole number of groups per warp
+    const uint32_t nv8 = (W * (3u + reads->q_planes) + 7u) / 8u;
+    slot_units = reads->max_units ? std::min(nv8, reads->max_units) : nv8;
+    if (slot_units < 2) slot_units = 2;
+    const size_t slots = (size_t)(NT / 32) * slot_units * 1024 + 32;
+    const size_t left = ctx->pile_smem > fixed + slots ? ctx->pile_smem - fixed - slots : 0;
+    rmax = (uint32_t)(left / (sizeof(uint4) * W));
+    rmax = rmax > 0 ? rmax - 1u : 0u;
+    if (rmax > (uint32_t)LANE_ROWS_MAX * KSUB) rmax = LANE_ROWS_MAX * KSUB;
+    rmax = rmax / NT * NT;
+    if (rmax == 0) return mb::fail(MB_EINVAL, "mb_snps_pileup_dev: no shared memory left for rows (W=%u)", W);
+  } else {
+    rmax = (uint32_t)((ctx->pile_smem - fixed) / (sizeof(uint4) * W)) - 1u;   // one row is the empty padding row
+    if (rmax > (uint32_t)LANE_ROWS_MAX * KSUB) rmax = LANE_ROWS_MAX * KSUB;
+    if (rmax >= 2u * NT && !getenv("MB_PILE_RAGGED")) rmax = rmax / NT * NT;   // the same number of reads for every thread
+    rmax &= ~7u;
+  }
   cudaStream_t st = ctx->stream;
   const uint32_t ns = L->n_species;
   k_init_stats<<<ns ? (ns + 255) / 256 : 1, 256, 0, st>>>(
@@ -895,12 +1025,14 @@ extern "C" int mb_snps_pileup_dev(mb_ctx* ctx, const mb_dev_reads* reads, const 
   p.mapq = f->mapq;
   p.baseq = (uint32_t)f->baseq;
   p.defer_restat = reads->n_long ? 1u : 0u;
+  p.slot_units = slot_units;
+  p.n_reads = (uint32_t)reads->n_reads;
   p.ovf = ctx->ovf;
   p.mirror = reads->n_long ? nullptr : reinterpret_cast<unsigned long long*>(ctx->stats_mirror);
   p.n_species = ns;
   const uint32_t grid = min(n_ktiles, (uint32_t)(ctx->sm_count * ctx->pile_occ));
   { int trc = mb::timing_begin(ctx); if (trc) return trc; }
-  kern.fn<<<grid, NT, pile_smem_bytes(W, rmax, NCOL), st>>>(p);
+  kern.fn<<<grid, NT, pile_smem_bytes(W, rmax, NCOL, slot_units, NT / 32), st>>>(p);
   { int trc = mb::timing_end(ctx); if (trc) return trc; }
   ctx->launches++;
   if (reads->n_long) {

@@ -57,7 +57,8 @@ class CPackedReads(C.Structure):
     _fields_ = [("n_reads", C.c_uint64), ("n_vec", C.c_uint64), ("n_cigar_words", C.c_uint64),
                 ("total_bases", C.c_uint64), ("max_ref_span", C.c_uint32), ("sorted", C.c_uint32),
                 ("row_words", C.c_uint32), ("n_long", C.c_uint32), ("q_planes", C.c_uint32),
-                ("n_planes", C.c_uint32), ("long_idx", C.c_void_p),
+                ("n_planes", C.c_uint32), ("max_units", C.c_uint32), ("reserved", C.c_uint32),
+                ("long_idx", C.c_void_p),
                 ("hdr", C.c_void_p), ("vec_off", C.c_void_p), ("cplx", C.c_void_p), ("cigar", C.c_void_p),
                 ("planes", C.c_void_p)]
 
@@ -294,6 +295,7 @@ class PackedReads:
     max_ref_span = property(lambda s: int(s.c.max_ref_span))
     row_words = property(lambda s: int(s.c.row_words))
     n_long = property(lambda s: int(s.c.n_long))
+    max_units = property(lambda s: int(s.c.max_units))
 
     @property
     def nbytes(self) -> int:

@@ -225,6 +225,33 @@ __global__ void __launch_bounds__(256) k_pack_analyse(const Plain in, const uint
   }
 }
 
+// ---- OR of the whole quality array [seq_off[0], seq_off[n]) as one flat stream (padding elements included: they
+// are zero from every producer in this repository; if a foreign producer left garbage there, bits 6-7 show up
+// and the exact per-record pass below decides)
+__global__ void __launch_bounds__(256) k_pack_qor_flat(const Plain in, PackMeta* meta) {
+  const uintptr_t a0 = (uintptr_t)(in.qual + in.seq_off[0]), a1 = (uintptr_t)(in.qual + in.seq_off[in.n]);
+  const uintptr_t v0 = (a0 + 15) & ~(uintptr_t)15, v1 = a1 & ~(uintptr_t)15;
+  uint32_t acc = 0;
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, nt = (uint64_t)gridDim.x * blockDim.x;
+  if (v1 > v0) {
+    const uint4* __restrict__ p = reinterpret_cast<const uint4*>(v0);
+    const uint64_t nv = (v1 - v0) >> 4;
+    for (uint64_t k = t; k < nv; k += nt) { const uint4 w = __ldg(p + k); acc |= w.x | w.y | w.z | w.w; }
+    if (t < 32) {                                   // the unaligned ends, byte by byte
+      for (uintptr_t b = a0 + t; b < v0 && b < a1; b += 32) acc |= *reinterpret_cast<const uint8_t*>(b);
+      for (uintptr_t b = v1 + t; b < a1; b += 32) acc |= *reinterpret_cast<const uint8_t*>(b);
+    }
+  } else if (t < 32) {
+    for (uintptr_t b = a0 + t; b < a1; b += 32) acc |= *reinterpret_cast<const uint8_t*>(b);
+  }
+  acc |= acc >> 16;
+  acc |= acc >> 8;
+  acc &= 0xffu;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc |= __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0 && acc) atomicOr(&meta->q_or, acc);
+}
+
 // ---- OR of every quality byte of every record: one warp per record, aligned 32-bit words, ends masked
 __global__ void __launch_bounds__(256) k_pack_qor(const Plain in, PackMeta* meta) {
   const int lane = threadIdx.x & 31;
@@ -381,81 +408,127 @@ __global__ void __launch_bounds__(256) k_pack_long(const uint8_t* __restrict__ n
   }
 }
 
-// ---- the planes: one warp per read, one lane per base of a 32-base block, one ballot per plane word
-template <int MODE>
+// ---- the planes: one warp per group of 32 reads. The lanes first fetch the 32 reads' metadata side by side (one
+// latency chain per group); then read after read, eight 32-base blocks at a time. Lane l loads base l of every
+// block of the chunk and packs one byte (quality) or one nibble (sequence class) per block into a 32-bit word;
+// the warp's 32 words are a 32 x 32 bit matrix, and ONE warp-level bit transposition (5 shuffle steps) turns it
+// into plane words: lane 8 s + k then holds Phred bit k of block s, lane 4 s + k the sequence plane k of block s.
+// Padding words and the unused slots of the last group are written as zeros.
+__device__ __forceinline__ uint32_t warp_transpose32(uint32_t x, const uint32_t lane) {
+  // 32 x 32 bit matrix over the lanes of a warp: on return bit l of lane j = bit j of lane l on entry
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) {
+    const uint32_t m = d == 16 ? 0x0000ffffu : d == 8 ? 0x00ff00ffu : d == 4 ? 0x0f0f0f0fu : d == 2 ? 0x33333333u : 0x55555555u;
+    const uint32_t y = __shfl_xor_sync(0xffffffffu, x, d);
+    x = (lane & d) ? (((y >> d) & m) | (x & ~m)) : ((x & m) | ((y << d) & ~m));
+  }
+  return x;
+}
+
+__device__ __forceinline__ uint32_t range_mask(int lo, int hi) {   // bits [lo, hi) of a word, clamped to [0, 32)
+  lo = max(lo, 0);
+  hi = min(max(hi, 0), 32);
+  uint32_t up, dn;
+  asm("shl.b32 %0, %1, %2;" : "=r"(up) : "r"(0xffffffffu), "r"((uint32_t)lo));
+  asm("shr.u32 %0, %1, %2;" : "=r"(dn) : "r"(0xffffffffu), "r"((uint32_t)(32 - hi)));
+  return hi > lo ? (up & dn) : 0u;
+}
+
+template <int MODE, int NQ>
 __global__ void __launch_bounds__(256) k_pack_fill(const Plain in, const uint4* __restrict__ hdr,
                                                    const uint32_t* __restrict__ src_of,
                                                    const uint32_t* __restrict__ vec_off, uint64_t n,
                                                    const PackMeta* __restrict__ meta, uint32_t* planes) {
-  const uint32_t NQ = meta->q_planes, NP = meta->n_planes, P0 = MODE == 0 ? 3u : 0u;
+  constexpr uint32_t P0 = MODE == 0 ? 3u : 0u, NP = P0 + NQ;
   const uint32_t n_vec = (uint32_t)meta->n_vec;
   const uint32_t lane = threadIdx.x & 31;
   const uint64_t wg = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-  const uint64_t n_slots = (n + MB_GROUP - 1) / MB_GROUP * MB_GROUP;
-  for (uint64_t j = wg; j < n_slots; j += nw) {
-    const uint64_t g0 = (j / MB_GROUP) * MB_GROUP, g1 = g0 + MB_GROUP;
-    const uint32_t units = ((g1 < n ? __ldg(&vec_off[g1]) : n_vec) - __ldg(&vec_off[g0])) / MB_GROUP;
-    uint32_t* __restrict__ reg = planes + ((size_t)__ldg(&vec_off[g0]) + (j - g0)) * 8;
-    if (j >= n) {                                   // the unused slots of the last group: zeros, as the host packer
-      for (uint32_t w = lane; w < units * 8; w += 32) reg[(size_t)(w >> 3) * (8 * MB_GROUP) + (w & 7u)] = 0u;
-      continue;
+  const uint64_t n_groups = (n + MB_GROUP - 1) / MB_GROUP;
+  const uint32_t qs = lane >> 3, qk = lane & 7u;      // after a quality transposition: block qs of four, Phred bit qk
+  const uint32_t ss = lane >> 2, sk = lane & 3u;      // after a sequence transposition: block ss of eight, plane sk
+  for (uint64_t g = wg; g < n_groups; g += nw) {
+    const uint64_t g0 = g * MB_GROUP, g1 = g0 + MB_GROUP;
+    const uint32_t v0 = __ldg(&vec_off[g0]);
+    const uint32_t units = ((g1 < n ? __ldg(&vec_off[g1]) : n_vec) - v0) / MB_GROUP;
+    // my read's metadata (lane l <-> read g0 + l)
+    const uint64_t jm = g0 + lane;
+    uint4 hm = make_uint4(0, 0, 0, 0);
+    uint64_t so_m = 0, co_m = 0;
+    if (jm < n) {
+      hm = __ldg(&hdr[jm]);
+      const uint64_t im = src_of[jm];
+      so_m = in.seq_off[im];
+      co_m = in.cigar_off[im];
     }
-    const uint4 h = __ldg(&hdr[j]);
-    const uint64_t i = src_of[j];
-    const uint32_t lq = h.y & 0xffffu, qstart = h.z & 0xffffu, span = h.w & 0xffffu, fl = h.w >> 24;
-    const uint32_t n_blk = (lq + MB_BLOCK - 1) / MB_BLOCK;
-    const uint64_t so = in.seq_off[i];
-    const uint8_t* __restrict__ qp = in.qual + so;
-    const uint32_t* __restrict__ cig = in.cigar + in.cigar_off[i];
-    const bool simple = (fl & MB_RF_SIMPLE) != 0;
-    for (uint32_t b = 0; b < n_blk; ++b) {
-      const uint32_t k = b * MB_BLOCK + lane;
-      const bool valid = k < lq;
-      uint32_t q = 0, nibv = 0;
-      if (valid) {
-        q = qp[k];
-        if (MODE == 0) {
-          const uint64_t e = so + k;
-          nibv = in.nib ? ((uint32_t)in.seq[e >> 1] >> ((e & 1) ? 0 : 4)) & 15u : (uint32_t)in.seq[e] & 15u;
-        }
+    for (uint32_t rr = 0; rr < MB_GROUP; ++rr) {
+      uint32_t* __restrict__ reg = planes + ((size_t)v0 + rr) * 8;
+      auto word = [&](const uint32_t w) -> uint32_t& { return reg[(size_t)(w >> 3) * (8 * MB_GROUP) + (w & 7u)]; };
+      if (g0 + rr >= n) {                              // the unused slots of the last group: zeros, as the host packer
+        for (uint32_t w = lane; w < units * 8; w += 32) word(w) = 0u;
+        continue;
       }
-      uint32_t mine = 0;   // lane p keeps plane word p of this block
-      if (MODE == 0) {
-        // BAM nibble -> 2-bit code: A=1 C=2 G=4 T=8 are the nibbles with exactly one bit set
-        const bool acgt = nibv != 0 && (nibv & (nibv - 1)) == 0;
-        bool inrun;
-        if (simple) {
-          inrun = k >= qstart && k < qstart + span;
-        } else {
-          // M/=/X runs, clipped where the reference position reaches ref_span (= the contig end)
-          inrun = false;
-          uint32_t qq = 0, rr = 0;
-          for (uint32_t c = 0; qq < lq; ++c) {
-            const uint32_t w = __ldg(cig + c), op = w & 15u, len = w >> 4;
-            if (op == mb::OP_M || op == mb::OP_EQ || op == mb::OP_X) {
-              const uint32_t take = rr < span ? min(len, span - rr) : 0u;
-              inrun = inrun || (k >= qq && k < qq + take);
-              qq += len; rr += len;
-            } else if (op == mb::OP_I || op == mb::OP_S) qq += len;
-            else if (op == mb::OP_D || op == mb::OP_N) rr += len;
+      const uint32_t hy = __shfl_sync(0xffffffffu, hm.y, rr), hz = __shfl_sync(0xffffffffu, hm.z, rr);
+      const uint32_t hw = __shfl_sync(0xffffffffu, hm.w, rr);
+      const uint64_t so = __shfl_sync(0xffffffffu, so_m, rr), co = __shfl_sync(0xffffffffu, co_m, rr);
+      const uint32_t lq = hy & 0xffffu, qstart = hz & 0xffffu, span = hw & 0xffffu, fl = hw >> 24;
+      const uint32_t n_blk = (lq + MB_BLOCK - 1) / MB_BLOCK;
+      const uint8_t* __restrict__ qp = in.qual + so;
+      const bool simple = (fl & MB_RF_SIMPLE) != 0;
+      for (uint32_t b0 = 0; b0 < n_blk; b0 += 8) {
+        // ---- loads: base `lane` of each of the chunk's eight blocks, all in flight at once
+        uint32_t qa = 0, qb = 0, sn = 0;
+#pragma unroll
+        for (int s8 = 0; s8 < 8; ++s8) {
+          const uint32_t k = (b0 + s8) * MB_BLOCK + lane;
+          if (k < lq) {
+            const uint32_t q = qp[k];
+            if (s8 < 4) qa |= q << (8 * s8); else qb |= q << (8 * (s8 - 4));
+            if (MODE == 0) {
+              const uint64_t e = so + k;
+              const uint32_t nib = in.nib ? ((uint32_t)in.seq[e >> 1] >> ((e & 1) ? 0 : 4)) & 15u : (uint32_t)in.seq[e] & 15u;
+              // BAM nibble -> {low bit, high bit, is A/C/G/T}: A=1 C=2 G=4 T=8 -> 4, 5, 6, 7; anything else 0
+              const uint32_t cls = nib == 8u ? 7u : (nib < 8u ? (0x00060540u >> (4 * nib)) & 7u : 0u);
+              sn |= cls << (4 * s8);
+            }
           }
         }
-        const uint32_t w0 = __ballot_sync(0xffffffffu, acgt && (nibv & 0xAu));    // C, T
-        const uint32_t w1 = __ballot_sync(0xffffffffu, acgt && (nibv & 0xCu));    // G, T
-        const uint32_t w2 = __ballot_sync(0xffffffffu, acgt && inrun);
-        mine = lane == 0 ? w0 : (lane == 1 ? w1 : (lane == 2 ? w2 : 0u));
+        // ---- quality planes: lane 8 s + k <- Phred bit k of block b0 + s (first four blocks), b0 + 4 + s (last four)
+        qa = warp_transpose32(qa, lane);
+        if (qk < (uint32_t)NQ && b0 + qs < n_blk) word((b0 + qs) * NP + P0 + qk) = qa;
+        if (b0 + 4 < n_blk) {
+          qb = warp_transpose32(qb, lane);
+          if (qk < (uint32_t)NQ && b0 + 4 + qs < n_blk) word((b0 + 4 + qs) * NP + P0 + qk) = qb;
+        }
+        if (MODE == 0) {
+          // ---- sequence planes: lane 4 s + k <- plane k of block b0 + s; the candidate plane (k = 2) keeps only the
+          // bases of M/=/X runs whose reference position is inside the contig (clipped where it reaches ref_span)
+          sn = warp_transpose32(sn, lane);
+          const uint32_t blk = b0 + ss;
+          if (sk == 2u && blk < n_blk) {
+            const int base = (int)(blk * MB_BLOCK);
+            uint32_t inrun = 0;
+            if (simple) {
+              inrun = range_mask((int)qstart - base, (int)(qstart + span) - base);
+            } else {
+              const uint32_t* __restrict__ cig = in.cigar + co;
+              uint32_t qq = 0, rx = 0;
+              for (uint32_t ci = 0; qq < lq; ++ci) {
+                const uint32_t w = __ldg(cig + ci), op = w & 15u, len = w >> 4;
+                if (op == mb::OP_M || op == mb::OP_EQ || op == mb::OP_X) {
+                  const uint32_t take = rx < span ? min(len, span - rx) : 0u;
+                  inrun |= range_mask((int)qq - base, (int)(qq + take) - base);
+                  qq += len; rx += len;
+                } else if (op == mb::OP_I || op == mb::OP_S) qq += len;
+                else if (op == mb::OP_D || op == mb::OP_N) rx += len;
+              }
+            }
+            sn &= inrun;
+          }
+          if (sk < 3u && blk < n_blk) word(blk * NP + sk) = sn;
+        }
       }
-      for (uint32_t pl = 0; pl < NQ; ++pl) {
-        const uint32_t w = __ballot_sync(0xffffffffu, (q >> pl) & 1u);
-        if (lane == P0 + pl) mine = w;
-      }
-      if (lane < NP) {
-        const uint32_t w = b * NP + lane;
-        reg[(size_t)(w >> 3) * (8 * MB_GROUP) + (w & 7u)] = mine;
-      }
+      for (uint32_t w = n_blk * NP + lane; w < units * 8; w += 32) word(w) = 0u;   // padding up to the group's units
     }
-    for (uint32_t w = n_blk * NP + lane; w < units * 8; w += 32)      // padding up to the group's units
-      reg[(size_t)(w >> 3) * (8 * MB_GROUP) + (w & 7u)] = 0u;
   }
 }
 
@@ -578,21 +651,32 @@ int pack_on_device(mb_ctx* c, const mb_plain_reads* in, const mb_layout* L, int 
                                               (uint32_t*)src_of, (uint16_t*)nblk, (uint8_t*)need, meta);
       c->launches += 1;
     }
-    k_pack_qor<<<wgrid, 256, 0, st>>>(P, meta);
+  }
+  for (int pass = 0; pass < 2; ++pass) {
+    if (n) {
+      if (pass == 0) {
+        k_pack_qor_flat<<<(uint32_t)c->sm_count * 8, 256, 0, st>>>(P, meta);
+      } else {   // Phred > 63 somewhere (or garbage in padding): the exact per-record pass decides
+        MB_CUDA_TRY(cudaMemsetAsync(&meta->q_or, 0, sizeof(uint32_t), st));
+        MB_CUDA_TRY(cudaMemsetAsync(&meta->max_units, 0, sizeof(uint32_t), st));
+        k_pack_qor<<<wgrid, 256, 0, st>>>(P, meta);
+      }
+      c->launches += 1;
+    }
+    k_pack_finish<<<1, 32, 0, st>>>(meta, n, mode, P.cigar_off);
     c->launches += 1;
+    if (n) {
+      k_pack_units<<<(uint32_t)std::min<uint64_t>((n_groups + 7) / 8, (uint64_t)c->sm_count * 8), 256, 0, st>>>(
+          (const uint16_t*)nblk, n, n_groups, meta, (uint32_t*)g_units);
+      k_pack_scan1<<<n_sblocks, SCAN_T, 0, st>>>((const uint32_t*)g_units, n_groups, (unsigned long long*)bsum);
+      k_pack_scan2<<<1, SCAN_T, 0, st>>>((unsigned long long*)bsum, n_sblocks, meta);
+      c->launches += 3;
+    }
+    MB_CUDA_TRY(cudaMemcpyAsync(hm, meta, sizeof(PackMeta), cudaMemcpyDeviceToHost, st));
+    MB_CUDA_TRY(cudaStreamSynchronize(st));
+    MB_CUDA_TRY(cudaGetLastError());
+    if (hm->err != ~0ull || !(hm->q_or & 0xC0u) || n == 0) break;
   }
-  k_pack_finish<<<1, 32, 0, st>>>(meta, n, mode, P.cigar_off);
-  c->launches += 1;
-  if (n) {
-    k_pack_units<<<(uint32_t)std::min<uint64_t>((n_groups + 7) / 8, (uint64_t)c->sm_count * 8), 256, 0, st>>>(
-        (const uint16_t*)nblk, n, n_groups, meta, (uint32_t*)g_units);
-    k_pack_scan1<<<n_sblocks, SCAN_T, 0, st>>>((const uint32_t*)g_units, n_groups, (unsigned long long*)bsum);
-    k_pack_scan2<<<1, SCAN_T, 0, st>>>((unsigned long long*)bsum, n_sblocks, meta);
-    c->launches += 3;
-  }
-  MB_CUDA_TRY(cudaMemcpyAsync(hm, meta, sizeof(PackMeta), cudaMemcpyDeviceToHost, st));
-  MB_CUDA_TRY(cudaStreamSynchronize(st));
-  MB_CUDA_TRY(cudaGetLastError());
   if (hm->err != ~0ull) {
     int status = MB_EINVAL;
     const char* text = pack_err_text((uint32_t)(hm->err & 0xffu), &status);
@@ -634,10 +718,13 @@ int pack_on_device(mb_ctx* c, const mb_plain_reads* in, const mb_layout* L, int 
       k_pack_long<<<grid, 256, 0, st>>>((const uint8_t*)need, n, meta, (uint4*)d->hdr, d->long_idx);
       c->launches += 1;
     }
-    if (mode == 0)
-      k_pack_fill<0><<<wgrid, 256, 0, st>>>(P, (const uint4*)d->hdr, (const uint32_t*)src_of, d->vec_off, n, meta, d->planes);
-    else
-      k_pack_fill<1><<<wgrid, 256, 0, st>>>(P, (const uint4*)d->hdr, (const uint32_t*)src_of, d->vec_off, n, meta, d->planes);
+    {
+      const uint32_t fgrid = (uint32_t)std::min<uint64_t>((n_groups + 7) / 8, (uint64_t)c->sm_count * 8);
+      void (*fill)(const Plain, const uint4*, const uint32_t*, const uint32_t*, uint64_t, const PackMeta*, uint32_t*) =
+          mode == 0 ? (d->q_planes == 6 ? k_pack_fill<0, 6> : k_pack_fill<0, 7>)
+                    : (d->q_planes == 6 ? k_pack_fill<1, 6> : k_pack_fill<1, 7>);
+      fill<<<fgrid, 256, 0, st>>>(P, (const uint4*)d->hdr, (const uint32_t*)src_of, d->vec_off, n, meta, d->planes);
+    }
     c->launches += 1;
   } else {
     MB_CUDA_TRY(cudaMemsetAsync(d->vec_off, 0, 4, st));

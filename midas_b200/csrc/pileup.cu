@@ -48,9 +48,9 @@ namespace {
 constexpr int KSUB = 4;                  // lanes sharing a column
 constexpr int NLEV = 8;                  // register vertical-counter levels (per-lane count <= 255 per round)
 constexpr int XLEV = NLEV + 2;           // levels after merging KSUB = 4 lanes
-constexpr int VCL = 16;                  // shared-memory vertical-counter levels (<= 65535 rows per pass)
+constexpr int VCL = 15;                  // shared-memory vertical-counter levels (<= 32767 rows per pass)
 constexpr int WMAX = MB_ROW_WORDS_MAX;
-constexpr uint32_t PASS_ROWS = 65528;    // rows folded into the shared counters before they are expanded
+constexpr uint32_t PASS_ROWS = 32760;    // rows folded into the shared counters before they are expanded
 constexpr int LANE_ROWS_MAX = 248;       // rows one lane may take in one round (keeps its count <= 255)
 
 static_assert(MB_TILE % 2048 == 0, "kernel tile must divide the layout tile");
@@ -164,25 +164,32 @@ __global__ void k_init_stats(unsigned long long* stats, const uint64_t* species_
 
 // For every kernel tile the contiguous range of reads that can overlap it: a read that fits a W-word
 // row and overlaps [ts, ts+KT) starts after ts - 32 W; the pileup kernel skips the rest by header.
-__global__ void k_tile_ranges(const uint4* __restrict__ hdr, uint32_t n_reads, uint32_t back, uint32_t n_tiles,
-                              uint32_t kt, uint32_t* __restrict__ rng) {
-  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+// One warp per tile, 32-ary search: every level is one coalesced-ish probe per lane and a ballot (5 dependent
+// levels for 5 M reads instead of the 22 of a binary search).
+__device__ __forceinline__ uint32_t warp_lower_bound(const uint4* __restrict__ hdr, uint32_t lo, uint32_t hi, uint32_t key,
+                                                     const uint32_t lane) {
+  // first index in [lo, hi) whose loc is >= key
+  while (hi - lo > 32u) {
+    const uint32_t step = (hi - lo + 31u) / 32u;
+    const uint32_t probe = lo + (lane + 1u) * step - 1u;             // last element of my sub-range
+    const bool below = probe < hi ? __ldg(&hdr[probe].x) < key : false;
+    const uint32_t k = (uint32_t)__popc(__ballot_sync(0xffffffffu, below));   // sub-ranges entirely below the key
+    lo += k * step;
+    hi = min(hi, lo + step);
+  }
+  const bool below = lo + lane < hi ? __ldg(&hdr[lo + lane].x) < key : false;
+  return lo + (uint32_t)__popc(__ballot_sync(0xffffffffu, below));
+}
+
+__global__ void __launch_bounds__(256) k_tile_ranges(const uint4* __restrict__ hdr, uint32_t n_reads, uint32_t back,
+                                                     uint32_t n_tiles, uint32_t kt, uint32_t* __restrict__ rng) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (t >= n_tiles) return;
   const uint32_t ts = t * kt, te = ts + kt;
-  const uint32_t lo_key = ts > back ? ts - back : 0u;
-  uint32_t lo = 0, hi = n_reads;
-  while (lo < hi) {
-    uint32_t mid = lo + ((hi - lo) >> 1);
-    if (__ldg(&hdr[mid].x) < lo_key) lo = mid + 1; else hi = mid;
-  }
-  const uint32_t r0 = lo;
-  hi = n_reads;
-  while (lo < hi) {
-    uint32_t mid = lo + ((hi - lo) >> 1);
-    if (__ldg(&hdr[mid].x) < te) lo = mid + 1; else hi = mid;
-  }
-  rng[2 * t] = r0;
-  rng[2 * t + 1] = lo;
+  const uint32_t r0 = warp_lower_bound(hdr, 0u, n_reads, ts > back ? ts - back : 0u, lane);
+  const uint32_t r1 = warp_lower_bound(hdr, r0, n_reads, te, lane);
+  if (lane == 0) { rng[2 * t] = r0; rng[2 * t + 1] = r1; }
 }
 
 // slide three register arrays of WT+2 words until the word offset d is -1 (static register moves in a
@@ -210,6 +217,9 @@ __global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : 2) k_pi
   constexpr int NT = NCOL * KSUB;          // threads per CTA
   constexpr int FIRST_N = NCOL + WMAX + 1;
   constexpr bool TMA = (VAR & 4) != 0;          // bit 2: the planes arrive by bulk copy into a per-warp slot
+  constexpr bool PFL2 = (VAR & 8) != 0;         // bit 3: the next round's arrays are prefetched into L2 during COUNT
+  constexpr bool SORTED = (VAR & 16) != 0;      // bit 4: the rows of a round are dealt to the threads by class (below)
+  constexpr int KMAX = 3;                       // SORTED: rows per thread and round (rmax <= KMAX * NT)
   extern __shared__ __align__(128) uint32_t smem[];
   constexpr uint32_t W = (uint32_t)WT;          // row words (compile time: every per-lane loop below unrolls)
   constexpr int NP = 3 + NQ;                    // words per 32-base block: seq lo, seq hi, candidate, Phred bits
@@ -229,11 +239,21 @@ __global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : 2) k_pi
   __shared__ uint32_t s_tile, s_nmax;
   __shared__ uint8_t s_mod[NCOL + 2 * WMAX + 1];                      // x % W for small x
   __shared__ __align__(8) unsigned long long s_mbar[NT / 32];         // TMA: one per warp
+  __shared__ uint32_t s_pf[4];                                         // PFL2: first read, last read, first unit, units
   // TMA: slot of warp w = slot_units x {32 lanes x 32 bytes}, as the group lies in HBM; then one all-zero unit
   uint32_t* const s_slots = reinterpret_cast<uint32_t*>(s_rows + ((size_t)p.rmax + 1) * W);
   uint32_t* const my_slot = s_slots + (size_t)(threadIdx.x >> 5) * p.slot_units * (8 * MB_GROUP);
   const uint32_t* const s_zero = s_slots + (size_t)(NT / 32) * p.slot_units * (8 * MB_GROUP);
   uint32_t mb_phase = 0;                                               // parity of my warp's next wait
+  // SORTED: the round's headers (bit 31 of .w = the read passed the header filters and touches the tile), the
+  // rows in processing order, the unit offsets of the round's groups
+  uint4* const s_hdr = reinterpret_cast<uint4*>(const_cast<uint32_t*>(s_zero) + 8);
+  uint16_t* const s_perm = reinterpret_cast<uint16_t*>(s_hdr + p.rmax);
+  uint32_t* const s_goff = reinterpret_cast<uint32_t*>(s_perm + p.rmax);
+  __shared__ uint32_t s_cnt[2];                                        // SORTED: simple / complex rows of the round
+  uint4 hq[KMAX];                                                      // SORTED: my rows' headers of the coming round
+  uint32_t hq_base = 0xffffffffu;                                      //   ... and the round (first read) they belong to
+  if (SORTED && threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int col = tid >> 2, ksub = tid & 3;                           // COUNT role
@@ -262,12 +282,17 @@ __global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : 2) k_pi
     const uint32_t r0a = TMA ? (r0 & ~31u) : r0;                       // TMA: rounds start on a group boundary
     const uint32_t n_groups = r1 > r0a ? (r1 - r0a + 31u) >> 5 : 0u;   // (the leading reads end before the tile: empty rows)
     const uint32_t GR = p.rmax >> 5;                                   // groups per round
+    uint32_t nv0 = 0, nv1 = 0;                                         // TMA, lane 0: unit range of my warp's next group
     if (TMA && lane == 0 && (uint32_t)(tid >> 5) < n_groups) {         // my warp's first group of this tile
       const uint32_t ra = r0a + 32u * (uint32_t)(tid >> 5);
       const uint32_t v0 = __ldg(&p.vec_off[ra]), v1 = __ldg(&p.vec_off[min(ra + 32u, p.n_reads)]);
       const uint32_t units = min((v1 - v0) >> 5, p.slot_units);
       mbar_expect_tx(&s_mbar[tid >> 5], units * 1024u);
       bulk_g2s(my_slot, p.planes + (size_t)v0 * 8, units * 1024u, &s_mbar[tid >> 5]);
+      if ((uint32_t)(tid >> 5) + NT / 32 < n_groups) {
+        nv0 = __ldg(&p.vec_off[ra + 256u]);
+        nv1 = __ldg(&p.vec_off[min(ra + 288u, p.n_reads)]);
+      }
     }
     const uint32_t tcol = ts >> 5, tb = tcol % W;
     const uint32_t slot_c = s_mod[tb + (uint32_t)col];                // where my column's word sits in a row
@@ -338,11 +363,18 @@ __global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : 2) k_pi
     // ---- STAGE of one read (row i of a round of n rows): header filters (snps.py:148,154,157), row index
     // table, the read's bit planes, bit-sliced base-quality test, mean-quality filter, CIGAR placement, row store
     auto stage_one = [&](const int i, const int n, const uint4 h, const uint32_t b0, const uint32_t cw,
-                         const uint32_t prev_loc) {
+                         const uint32_t prev_loc, const uint32_t* __restrict__ raw_in) {
         const uint32_t loc = h.x, lq = h.y & 0xffffu, alen = h.y >> 16, qstart = h.z & 0xffffu, nm = h.z >> 16;
-        const uint32_t span = h.w & 0xffffu, mq = (h.w >> 16) & 0xffu, fl = h.w >> 24;
+        const uint32_t span = h.w & 0xffffu, mq = (h.w >> 16) & 0xffu, fl = (h.w >> 24) & 0x7fu;
         bool needq = false, ovl = false, owner = false;
-        if (!(fl & MB_RF_LONG)) {
+        if (SORTED) {                              // classified before (bit 31 of the stashed header)
+          if (!(fl & MB_RF_LONG)) {
+            owner = loc >= ts;
+            ovl = span > 0 && loc + span > ts;
+            if (owner) ++my_aligned;                                                                // snps.py:143
+            needq = (h.w >> 31) != 0;
+          }
+        } else if (!(fl & MB_RF_LONG)) {
           owner = loc >= ts;
           ovl = span > 0 && loc + span > ts;
           // exact integer forms of the two double-precision tests (tables built in ctx.cu)
@@ -403,16 +435,16 @@ __global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : 2) k_pi
             constexpr int NV8 = (WT * NP + 7) / 8;
             const uint32_t nv8 = (((lq + 31u) >> 5) * (uint32_t)NP + 7u) >> 3;
             const uint32_t* __restrict__ vp = p.planes + (size_t)b0 * 8;
-            uint32_t raw[8 * NV8];
+            uint32_t raw_ld[TMA ? 1 : 8 * NV8];
+            if (!TMA) {
 #pragma unroll
-            for (int u = 0; u < NV8; ++u) {
-              // every read has a block, i.e. at least NP > 8 words: its first two units always exist; units
-              // past the read's end come from one shared all-zero unit (no predicated loads, no zeroed defaults)
-              if (TMA)   // my units of the group's slot: unit u of lane l at (32 u + l) x 32 bytes
-                lds256((u < 2 || (uint32_t)u < nv8) ? my_slot + (8 * MB_GROUP) * u + 8 * lane : s_zero, raw + 8 * u);
-              else
-                ldg256((u < 2 || (uint32_t)u < nv8) ? vp + 8 * MB_GROUP * u : p.zero_unit, raw + 8 * u);
+              for (int u = 0; u < NV8; ++u) {
+                // every read has a block, i.e. at least NP > 8 words: its first two units always exist; units
+                // past the read's end come from one shared all-zero unit (no predicated loads, no zeroed defaults)
+                ldg256((u < 2 || (uint32_t)u < nv8) ? vp + 8 * MB_GROUP * u : p.zero_unit, raw_ld + 8 * u);
+              }
             }
+            const uint32_t* __restrict__ raw = TMA ? raw_in : raw_ld;   // TMA: already copied out of the warp's slot
 #pragma unroll
             for (int bl = 0; bl < WT; ++bl) convert(bl, raw + bl * NP);
           } else {
@@ -554,6 +586,14 @@ __global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : 2) k_pi
     bool accumulate = false;
     uint4 nh = make_uint4(0, 0, 0, 0);                         // header, block offset, run word and predecessor
     uint32_t nb0 = 0, ncw = 0, nprev = 0;                       // of this thread's next read: one step ahead
+    if (TMA) {                                                  // my read of the warp's first group of this tile
+      const uint32_t rf = r0a + 32u * (uint32_t)(tid >> 5) + (uint32_t)lane;
+      if ((uint32_t)(tid >> 5) < n_groups && rf < r1) {
+        nh = __ldg(&p.hdr[rf]);
+        ncw = __ldg(&p.cplx[rf]);
+        if (lane == 0 && rf > r0a) nprev = __ldg(&p.hdr[rf - 1].x);
+      }
+    }
     for (uint32_t rb = r0a; rb < r1; rb += p.rmax) {
       const int n = (int)min(p.rmax, r1 - rb);
       if (pass_rows + (uint32_t)n > PASS_ROWS) {  // keep the shared counters below 2^VCL
@@ -574,30 +614,140 @@ __global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : 2) k_pi
         for (uint32_t g = gq + (uint32_t)wid; g < gq + GR && g < n_groups; g += NT / 32) {
           const uint32_t r = r0a + 32u * g + (uint32_t)lane;
           const int i = (int)(r - rb);
-          uint4 h = make_uint4(0, 0, 0, 0);
-          uint32_t cw = 0, prev_loc = 0;
-          if (i < n) {
-            h = __ldg(&p.hdr[r]);
-            cw = __ldg(&p.cplx[r]);
-            if (lane == 0 && i > 0) prev_loc = __ldg(&p.hdr[r - 1].x);
-          }
+          const uint4 h = nh;                                                  // requested one group ago
+          const uint32_t cw = ncw;
+          uint32_t prev_loc = nprev;
           {
             const uint32_t up = __shfl_up_sync(0xffffffffu, h.x, 1);
             if (lane > 0) prev_loc = up;
           }
           mbar_wait(&s_mbar[wid], mb_phase);                                   // this group's units have landed
           mb_phase ^= 1u;
-          if (i < n) stage_one(i, n, h, 0u, cw, prev_loc);
+          // my units out of the slot (unit u of lane l at (32 u + l) x 32 bytes), so that the slot is free for the
+          // next group while this one is converted and placed
+          constexpr int NV8T = (WT * NP + 7) / 8;
+          uint32_t raw[8 * NV8T];
+          {
+            const uint32_t nv8 = i < n ? min(((((h.y & 0xffffu) + 31u) >> 5) * (uint32_t)NP + 7u) >> 3, p.slot_units) : 0u;
+#pragma unroll
+            for (int u = 0; u < NV8T; ++u)
+              lds256((uint32_t)u < nv8 ? my_slot + (8 * MB_GROUP) * u + 8 * lane : s_zero, raw + 8 * u);
+          }
           __syncwarp();
           if (lane == 0 && g + NT / 32 < n_groups) {                           // my next group, into the same slot
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            const uint32_t ra = r0a + 32u * (g + NT / 32);
-            const uint32_t v0 = __ldg(&p.vec_off[ra]), v1 = __ldg(&p.vec_off[min(ra + 32u, p.n_reads)]);
-            const uint32_t units = min((v1 - v0) >> 5, p.slot_units);
+            const uint32_t units = min((nv1 - nv0) >> 5, p.slot_units);
             mbar_expect_tx(&s_mbar[wid], units * 1024u);
-            bulk_g2s(my_slot, p.planes + (size_t)v0 * 8, units * 1024u, &s_mbar[wid]);
+            bulk_g2s(my_slot, p.planes + (size_t)nv0 * 8, units * 1024u, &s_mbar[wid]);
+            if (g + 2 * (NT / 32) < n_groups) {                                // and the unit range of the one after it
+              const uint32_t ra = r0a + 32u * (g + 2 * (NT / 32));
+              nv0 = __ldg(&p.vec_off[ra]);
+              nv1 = __ldg(&p.vec_off[min(ra + 32u, p.n_reads)]);
+            }
+          }
+          // header and run word of my read of the warp's next group: in flight during this group's work
+          const uint4 h_cur = h;
+          const uint32_t cw_cur = cw, prev_cur = prev_loc;
+          if (g + NT / 32 < n_groups) {
+            const uint32_t rn = r + 8u * 32u;
+            if (rn < r1) {
+              nh = __ldg(&p.hdr[rn]);
+              ncw = __ldg(&p.cplx[rn]);
+              if (lane == 0) nprev = __ldg(&p.hdr[rn - 1].x);
+            }
+          }
+          if (i < n) stage_one(i, n, h_cur, 0u, cw_cur, prev_cur, raw);
+        }
+      } else {
+      uint32_t pf_r0 = 0, pf_r1 = 0, pf_u0 = 0, pf_u1 = 0;
+      if ((PFL2 || SORTED) && tid == 0) {
+        // the reads of the next round (or of the next tile's first round) and their unit range: asked for now,
+        // needed when this round's STAGE ends
+        pf_r0 = rb + p.rmax;
+        pf_r1 = min(pf_r0 + p.rmax, r1);
+        if (pf_r0 >= r1) {
+          pf_r0 = pf_r1 = 0;
+          if (next_tile < p.n_ktiles) {
+            pf_r0 = __ldg(&p.tile_rng[2 * next_tile]);
+            pf_r1 = min(pf_r0 + p.rmax, __ldg(&p.tile_rng[2 * next_tile + 1]));
           }
         }
+        if (pf_r1 > pf_r0) {
+          pf_u0 = __ldg(&p.vec_off[pf_r0 & ~31u]);
+          pf_u1 = __ldg(&p.vec_off[min((pf_r1 + 31u) & ~31u, p.n_reads)]);
+        }
+      }
+      if (SORTED) {
+        // ---- phase A: my rows' headers (requested before the previous COUNT) are classified - simple (one run),
+        // complex (an indel or more: the long placement code), or nothing to stage - and stashed; rows to stage
+        // go into s_perm, simple ones from the front, complex ones from the back, so that phase B's warps each
+        // run one kind of read: no lane idles through a conversion it does not need, and the few warps that hold
+        // the complex reads are the only ones that execute the indel code
+        if (hq_base != rb) {
+#pragma unroll
+          for (int k = 0; k < KMAX; ++k) {
+            const int i = tid + k * NT;
+            hq[k] = i < n ? __ldg(&p.hdr[rb + (uint32_t)i]) : make_uint4(0, 0, 0, 0);
+          }
+        }
+        if ((uint32_t)tid <= (p.rmax >> 5) + 1u)
+          s_goff[tid] = __ldg(&p.vec_off[min((rb & ~31u) + 32u * (uint32_t)tid, p.n_reads)]);
+        uint32_t skip_mask = 0;
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) {
+          const int i = tid + k * NT;
+          uint4 h = hq[k];
+          int cls = 2;                                                       // 0 simple, 1 complex, 2 nothing to stage
+          if (i < n) {
+            const uint32_t loc = h.x, lq = h.y & 0xffffu, alen = h.y >> 16, nm = h.z >> 16;
+            const uint32_t span = h.w & 0xffffu, mq = (h.w >> 16) & 0xffu, fl = h.w >> 24;
+            if (!(fl & MB_RF_LONG)) {
+              const bool owner = loc >= ts, ovl = span > 0 && loc + span > ts;
+              bool hk = (fl & MB_RF_NMSAT) ? (p.pid_always != 0)
+                                           : (100 * ((int)alen - (int)nm) >= __ldg(p.t_pid + alen));   // snps.py:148
+              hk = hk && (int)mq >= p.mapq;                                                             // snps.py:154
+              hk = hk && (int)alen >= __ldg(p.t_cov + lq);                                              // snps.py:157
+              if (hk && (ovl || owner)) {
+                cls = (fl & MB_RF_SIMPLE) ? 0 : 1;
+                h.w |= 0x80000000u;
+              }
+            }
+            s_hdr[i] = h;
+            if (cls == 2) skip_mask |= 1u << k;
+          }
+          const uint32_t m0 = __ballot_sync(0xffffffffu, cls == 0), m1 = __ballot_sync(0xffffffffu, cls == 1);
+          uint32_t b0 = 0, b1 = 0;
+          if (lane == 0) {
+            if (m0) b0 = atomicAdd(&s_cnt[0], (uint32_t)__popc(m0));
+            if (m1) b1 = atomicAdd(&s_cnt[1], (uint32_t)__popc(m1));
+          }
+          b0 = __shfl_sync(0xffffffffu, b0, 0);
+          b1 = __shfl_sync(0xffffffffu, b1, 0);
+          const uint32_t below = (1u << lane) - 1u;
+          if (cls == 0) s_perm[b0 + (uint32_t)__popc(m0 & below)] = (uint16_t)i;
+          if (cls == 1) s_perm[p.rmax - 1u - (b1 + (uint32_t)__popc(m1 & below))] = (uint16_t)i;
+        }
+        __syncthreads();
+        // ---- phase B
+        const uint32_t n_s = s_cnt[0], n_c = s_cnt[1];
+        const uint32_t g_first = rb >> 5;
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) {                                     // my rows with nothing to stage: index table, empty row
+          if (skip_mask & (1u << k)) {
+            const int i = tid + k * NT;
+            stage_one(i, n, s_hdr[i], 0u, 0u, i > 0 ? s_hdr[i - 1].x : 0u, nullptr);
+          }
+        }
+        for (uint32_t slot = (uint32_t)tid; slot < p.rmax; slot += NT) {
+          if (slot >= n_s && slot < p.rmax - n_c) continue;
+          const int i = (int)s_perm[slot];
+          const uint4 h = s_hdr[i];
+          const uint32_t r = rb + (uint32_t)i;
+          const uint32_t b0 = s_goff[(r >> 5) - g_first] + (r & 31u);
+          const uint32_t cw = ((h.w >> 24) & MB_RF_SIMPLE) ? 0xffffffffu : __ldg(&p.cplx[r]);
+          stage_one(i, n, h, b0, cw, i > 0 ? s_hdr[i - 1].x : 0u, nullptr);
+        }
+        if (tid == 0) { s_pf[0] = pf_r0; s_pf[1] = pf_r1; s_pf[2] = pf_u0; s_pf[3] = pf_u1 > pf_u0 ? pf_u1 - pf_u0 : 0u; }
       } else {
       if (rb == r0) {                                          // later rounds: requested before the previous COUNT
         nh = make_uint4(0, 0, 0, 0); nb0 = 0; ncw = 0; nprev = 0;
@@ -618,7 +768,7 @@ __global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : 2) k_pi
           ncw = __ldg(&p.cplx[r + NT]);
           nprev = __ldg(&p.hdr[r + NT - 1].x);
         }
-        stage_one(i, n, h, b0, cw, prev_loc);
+        stage_one(i, n, h, b0, cw, prev_loc, nullptr);
       }
       if (rb + p.rmax < r1) {   // the first read of my next round: requested now, in flight during COUNT
         const uint32_t nr = rb + p.rmax + (uint32_t)tid;
@@ -630,8 +780,39 @@ __global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : 2) k_pi
           if (tid > 0) nprev = __ldg(&p.hdr[nr - 1].x);
         }
       }
+      if (PFL2 && tid == 0) { s_pf[0] = pf_r0; s_pf[1] = pf_r1; s_pf[2] = pf_u0; s_pf[3] = pf_u1 > pf_u0 ? pf_u1 - pf_u0 : 0u; }
+      }
       }
       __syncthreads();
+      if (SORTED) {
+        // my rows' headers of the coming round (this tile's next round or the next tile's first one): in flight
+        // during COUNT; the class counters are free again
+        const uint32_t a = s_pf[0], b = s_pf[1];
+        hq_base = b > a ? a : 0xffffffffu;
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) {
+          const uint32_t rr = a + (uint32_t)(tid + k * NT);
+          hq[k] = rr < b ? __ldg(&p.hdr[rr]) : make_uint4(0, 0, 0, 0);
+        }
+        if (tid < 2) s_cnt[tid] = 0;
+      }
+      if (PFL2 && !TMA) {
+        // HBM -> L2 traffic of the next round runs under this round's COUNT: 8 KB pieces of the plane range, then the
+        // headers, unit offsets and run words
+        const uint32_t a = s_pf[0], b = s_pf[1], u0 = s_pf[2], nu = s_pf[3];
+        const uint32_t n_pl = (nu + 255u) >> 8;                               // 256 units = 8 KB
+        if ((uint32_t)tid < n_pl) {
+          const uint32_t units = min(256u, nu - 256u * (uint32_t)tid);
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.planes + ((size_t)u0 + 256u * (uint32_t)tid) * 8),
+                       "r"(units * 32u) : "memory");
+        } else if (b > a && (uint32_t)tid < n_pl + 3u) {
+          const uint32_t k = (uint32_t)tid - n_pl;
+          const uint32_t a16 = a & ~3u, nb = ((b - a16 + 3u) & ~3u);          // 16-byte aligned element ranges
+          if (k == 0) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.hdr + a16), "r"(nb * 16u) : "memory");
+          else if (k == 1) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.vec_off + a16), "r"(nb * 4u) : "memory");
+          else asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.cplx + a16), "r"(nb * 4u) : "memory");
+        }
+      }
       // ---- COUNT: my column's rows of this round, KSUB-strided, 8 rows per carry-save tree into
       // bit-sliced register counters; then the KSUB lanes of a column are merged by a shuffle
       // butterfly of bit-sliced adders and lane ksub folds class ksub into the shared counters
@@ -875,9 +1056,9 @@ __global__ void __launch_bounds__(256) k_restat(const uint32_t* __restrict__ cou
 
 // the row widths (and Phred plane counts) the tile kernel is instantiated for; a batch runs at the smallest
 // width >= its row_words
-struct PileKernel { uint32_t W; void (*fn)(const PileParams); uint32_t kt; bool tma; };   // kt: positions per tile
+struct PileKernel { uint32_t W; void (*fn)(const PileParams); uint32_t kt; bool tma; bool sorted; };   // kt: positions per tile
 PileKernel pick_kernel(uint32_t row_words, uint32_t q_planes, bool want_tma) {
-#define MB_PT(W, Q) {W, k_pileup_v2<W, Q, 4>, 2048, true}
+#define MB_PT(W, Q) {W, k_pileup_v2<W, Q, 4>, 2048, true, false}
   static const PileKernel t6[] = {MB_PT(3, 6), MB_PT(4, 6), MB_PT(5, 6), MB_PT(6, 6), MB_PT(7, 6), MB_PT(8, 6)};
   static const PileKernel t7[] = {MB_PT(3, 7), MB_PT(4, 7), MB_PT(5, 7), MB_PT(6, 7), MB_PT(7, 7), MB_PT(8, 7)};
 #undef MB_PT
@@ -886,18 +1067,22 @@ PileKernel pick_kernel(uint32_t row_words, uint32_t q_planes, bool want_tma) {
     for (int i = 0; i < 6; ++i)
       if (k[i].W >= row_words) return k[i];
   }
-#define MB_PK(W, Q) {W, k_pileup_v2<W, Q, 0>, 2048, false}
+#define MB_PK(W, Q) {W, k_pileup_v2<W, Q, 8>, 2048, false, false}
   static const PileKernel k6[] = {MB_PK(3, 6), MB_PK(4, 6), MB_PK(5, 6),  MB_PK(6, 6),  MB_PK(7, 6),
                                   MB_PK(8, 6), MB_PK(10, 6), MB_PK(12, 6), MB_PK(16, 6)};
   static const PileKernel k7[] = {MB_PK(3, 7), MB_PK(4, 7), MB_PK(5, 7),  MB_PK(6, 7),  MB_PK(7, 7),
                                   MB_PK(8, 7), MB_PK(10, 7), MB_PK(12, 7), MB_PK(16, 7)};
 #undef MB_PK
   // experiment switches (MB_PILE_VAR, W = 6 with 6 Phred planes only)
-  static const PileKernel kx[4] = {{6, k_pileup_v2<6, 6, 0>, 2048, false}, {6, k_pileup_v2<6, 6, 1>, 2048, false},
-                                   {6, k_pileup_v2<6, 6, 2>, 1024, false}, {6, k_pileup_v2<6, 6, 3>, 1024, false}};
+  static const PileKernel kx[4] = {{6, k_pileup_v2<6, 6, 0>, 2048, false, false}, {6, k_pileup_v2<6, 6, 1>, 2048, false, false},
+                                   {6, k_pileup_v2<6, 6, 2>, 1024, false, false}, {6, k_pileup_v2<6, 6, 3>, 1024, false, false}};
+  static const PileKernel kpf = {6, k_pileup_v2<6, 6, 8>, 2048, false, false};
+  static const PileKernel kso = {6, k_pileup_v2<6, 6, 24>, 2048, false, true};
   if (const char* e = getenv("MB_PILE_VAR")) {
     const long v = atol(e);
-    if (v > 0 && v < 4 && q_planes == 6 && row_words > 5 && row_words <= 6) return kx[v];
+    if (v >= 0 && v < 4 && q_planes == 6 && row_words > 5 && row_words <= 6) return kx[v];
+    if (v == 8 && q_planes == 6 && row_words > 5 && row_words <= 6) return kpf;
+    if (v == 24 && q_planes == 6 && row_words > 5 && row_words <= 6) return kso;
   }
   const PileKernel* k = q_planes == 6 ? k6 : k7;
   for (int i = 0; i < 9; ++i)
@@ -905,9 +1090,11 @@ PileKernel pick_kernel(uint32_t row_words, uint32_t q_planes, bool want_tma) {
   return k[8];
 }
 
-size_t pile_smem_bytes(uint32_t W, uint32_t rmax, uint32_t ncol, uint32_t slot_units, uint32_t n_warps) {
+size_t sorted_smem_bytes(uint32_t rmax) { return (size_t)rmax * 18 + 4 * ((size_t)(rmax >> 5) + 4) + 32; }
+size_t pile_smem_bytes(uint32_t W, uint32_t rmax, uint32_t ncol, uint32_t slot_units, uint32_t n_warps, bool sorted) {
   return sizeof(uint4) * ((size_t)VCL * ncol + ((size_t)rmax + 1) * W)     // + the empty padding row
-         + (slot_units ? (size_t)n_warps * slot_units * 1024 + 32 : 0);    // TMA: one slot per warp + a zero unit
+         + (slot_units ? (size_t)n_warps * slot_units * 1024 : 0) + 32     // TMA: one slot per warp; a zero unit
+         + (sorted ? sorted_smem_bytes(rmax) : 0);                         // SORTED: header stash, order, group offsets
 }
 
 }  // namespace
@@ -927,8 +1114,10 @@ extern "C" int mb_snps_pileup_dev(mb_ctx* ctx, const mb_dev_reads* reads, const 
   // shared memory per CTA: two CTAs per SM (override with MB_PILE_SMEM_KB for experiments)
   if (reads->n_planes != 3 + reads->q_planes || (reads->q_planes != 6 && reads->q_planes != 7))
     return mb::fail(MB_EINVAL, "mb_snps_pileup_dev: reads were not packed in snps mode");
-  // staging variant: bulk copies into per-warp shared-memory slots (MB_PILE_TMA=0 selects the register path)
-  bool want_tma = true;
+  // staging variant. Default: register path (256-bit loads) with the next round's arrays prefetched into L2 under
+  // COUNT. MB_PILE_TMA=1 selects the bulk-copy variant (per-warp shared-memory slots, mbarrier completion): measured
+  // 17 % slower on C2 (profiles/r02_k_pileup_variants.md), kept as a switch
+  bool want_tma = false;
   if (const char* e = getenv("MB_PILE_TMA")) want_tma = atol(e) != 0;
   if (getenv("MB_PILE_VAR")) want_tma = false;
   const PileKernel kern = pick_kernel(reads->row_words, reads->q_planes, want_tma);
@@ -944,7 +1133,7 @@ extern "C" int mb_snps_pileup_dev(mb_ctx* ctx, const mb_dev_reads* reads, const 
     ctx->tile_rng_cap = (size_t)2 * n_ktiles + 2;
   }
   {
-    size_t kb = kern.tma ? 113 : (KT == 2048 ? 100 : 50);            // 2 / 4 CTAs per SM
+    size_t kb = (kern.tma || kern.sorted) ? 112 : (KT == 2048 ? 100 : 50);            // 2 / 4 CTAs per SM
     if (const char* e = getenv("MB_PILE_SMEM_KB")) { long v = atol(e); if (v >= 24 && v <= 220) kb = (size_t)v; }
     ctx->pile_smem = kb * 1024;
   }
@@ -973,6 +1162,9 @@ extern "C" int mb_snps_pileup_dev(mb_ctx* ctx, const mb_dev_reads* reads, const 
     if (rmax > (uint32_t)LANE_ROWS_MAX * KSUB) rmax = LANE_ROWS_MAX * KSUB;
     rmax = rmax / NT * NT;
     if (rmax == 0) return mb::fail(MB_EINVAL, "mb_snps_pileup_dev: no shared memory left for rows (W=%u)", W);
+  } else if (kern.sorted) {
+    rmax = 3u * NT;                                                              // KMAX rows per thread
+    while (rmax > NT && pile_smem_bytes(W, rmax, NCOL, 0, NT / 32, true) > ctx->pile_smem) rmax -= NT;
   } else {
     rmax = (uint32_t)((ctx->pile_smem - fixed) / (sizeof(uint4) * W)) - 1u;   // one row is the empty padding row
     if (rmax > (uint32_t)LANE_ROWS_MAX * KSUB) rmax = LANE_ROWS_MAX * KSUB;
@@ -995,7 +1187,7 @@ extern "C" int mb_snps_pileup_dev(mb_ctx* ctx, const mb_dev_reads* reads, const 
   }
   // the tile -> read-range index depends only on the resident batch: built once per (batch, row width)
   if (ctx->rng_for != reads || ctx->rng_W != W || ctx->rng_ntiles != n_ktiles) {
-    k_tile_ranges<<<(n_ktiles + 255) / 256, 256, 0, st>>>(reinterpret_cast<const uint4*>(reads->hdr),
+    k_tile_ranges<<<(n_ktiles + 7) / 8, 256, 0, st>>>(reinterpret_cast<const uint4*>(reads->hdr),
                                                           (uint32_t)reads->n_reads, 32u * W, n_ktiles, KT, ctx->tile_rng);
     ctx->launches++;
     ctx->rng_for = reads;
@@ -1032,7 +1224,7 @@ extern "C" int mb_snps_pileup_dev(mb_ctx* ctx, const mb_dev_reads* reads, const 
   p.n_species = ns;
   const uint32_t grid = min(n_ktiles, (uint32_t)(ctx->sm_count * ctx->pile_occ));
   { int trc = mb::timing_begin(ctx); if (trc) return trc; }
-  kern.fn<<<grid, NT, pile_smem_bytes(W, rmax, NCOL, slot_units, NT / 32), st>>>(p);
+  kern.fn<<<grid, NT, pile_smem_bytes(W, rmax, NCOL, slot_units, NT / 32, kern.sorted), st>>>(p);
   { int trc = mb::timing_end(ctx); if (trc) return trc; }
   ctx->launches++;
   if (reads->n_long) {

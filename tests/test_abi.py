@@ -30,7 +30,7 @@ def test_every_declared_symbol_is_exported():
 def test_version_and_struct_sizes():
     assert "sm_100a" in lib.version()
     assert lib.HDR_DTYPE.itemsize == 16 and lib.STATS_DTYPE.itemsize == 40 and lib.GENE_OUT_DTYPE.itemsize == 24
-    assert C.sizeof(lib.CPackedReads) == 8 * 4 + 4 * 4 + 8 * 7
+    assert C.sizeof(lib.CPackedReads) == 8 * 4 + 4 * 8 + 8 * 6
 
 
 def test_no_cpu_fallback():

@@ -164,12 +164,39 @@ def write_species_tsv(path, ref: RefSet, contigs, layout, counts, species_index,
     out.close()
 
 
+def _world():
+    """(rank, world_size) of an initialised torch.distributed job (torchrun), else (0, 1)."""
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank(), dist.get_world_size()
+    except ImportError:
+        pass
+    return 0, 1
+
+
+def _run_batch(ctx, reads, layout, filters, threads):
+    """Decoded records -> counts + stats through the C-ABI (H2D, re-layout on the GPU, pileup, D2H)."""
+    try:
+        return ctx.snps_pileup_plain(reads, layout, filters)
+    except lib.MidasB200Error as e:
+        if e.status != -6:
+            raise
+        # a BAM that is not coordinate-sorted (the reference sorts it, snps.py:118): sort on the host
+        packed = lib.PackedReads(reads, layout, "snps", sort=True, pinned=False, threads=threads)
+        return ctx.snps_pileup(packed, layout, filters)
+
+
 def pysam_pileup(args, species, contigs, ctx=None):
-    """reference snps.py:219-244. One GPU call for all species; fills the Species stats and writes
-    one <species>.snps.gz per species."""
+    """reference snps.py:219-244. One GPU call for all species of this rank; fills the Species stats and writes
+    one <species>.snps.gz per species. Under torchrun (one process per GPU) the species are dealt to the ranks
+    by shard.plan - the reference's own unit of parallelism, one worker per species (snps.py:225-228) - a species
+    holding more than 1/world of the reads is split by read index and its planes are all-reduced; the stats rows
+    are gathered so that every rank (rank 0 writes summary.txt) sees all species."""
     start = time()
     print("\nCounting alleles")
     args["log"].write("\nCounting alleles\n")
+    rank, world = _world()
     own_ctx = ctx is None
     if own_ctx:
         ctx = lib.Context(int(args.get("device", 0)), use_torch_stream=False)
@@ -188,26 +215,38 @@ def pysam_pileup(args, species, contigs, ctx=None):
         if timing is not None:
             timing["n_reads"], timing["n_bases"] = int(reads.n_reads), int(reads.l_qseq.sum(dtype=np.int64))
         t = lap("bam_decode", t)
-        layout = lib.Layout.of(ref)
-        try:
-            # decoded records -> H2D -> re-layout on the GPU (k_pack_*) -> pileup -> D2H
-            counts, stats = ctx.snps_pileup_plain(reads, layout, _filters(args))
-        except lib.MidasB200Error as e:
-            if e.status != -6:
-                raise
-            # a BAM that is not coordinate-sorted (the reference sorts it, snps.py:118): sort on the host
-            packed = lib.PackedReads(reads, layout, "snps", sort=True, pinned=False, threads=threads)
-            counts, stats = ctx.snps_pileup(packed, layout, _filters(args))
-        t = lap("gpu_h2d_pack_kernels_d2h", t)
-        for k, species_id in enumerate(ref.species_ids):
-            out_path = "%s/snps/output/%s.snps.gz" % (args["outdir"], species_id)
-            write_species_tsv(out_path, ref, contigs, layout, counts, k, threads=threads)
+        filters = _filters(args)
+        if world == 1:
+            layout = lib.Layout.of(ref)
+            counts, stats = _run_batch(ctx, reads, layout, filters, threads)
+            t = lap("gpu_h2d_pack_kernels_d2h", t)
+            mine, writes = np.arange(ref.n_species), np.ones(ref.n_species, bool)
+            sub_ref = ref
+            rows = np.stack([stats[name].astype(np.int64) for name in lib.STATS_DTYPE.names], 1)
+        else:
+            import torch
+            from .. import shard
+            sub_ref, sub_reads, mine, split = shard.shard_split(reads, ref, rank, world)
+            layout = lib.Layout.of(sub_ref)
+            counts, stats = _run_batch(ctx, sub_reads, layout, filters, threads)
+            local = np.stack([stats[name].astype(np.int64) for name in lib.STATS_DTYPE.names], 1)
+            dev = torch.device("cuda", ctx.device)
+            if split.any():     # the one real exchange step of the path: sum the replicas of the split species
+                ct = torch.from_numpy(counts.view(np.int32)).to(dev)
+                st = torch.from_numpy(local).to(dev)
+                shard.allreduce_split_counts(ct, st, layout, split)
+                counts = ct.cpu().numpy().view(np.uint32)
+                local = st.cpu().numpy()
+            rows = shard.allreduce_stats(local, mine, ref.n_species, device=dev, split_mask=split)
+            writes = ~split | (rank == 0)                       # a split species is written once, by rank 0
+            t = lap("gpu_h2d_pack_kernels_d2h", t)
+        for k, g in enumerate(mine):
+            if writes[k]:
+                out_path = "%s/snps/output/%s.snps.gz" % (args["outdir"], ref.species_ids[g])
+                write_species_tsv(out_path, sub_ref, contigs, layout, counts, k, threads=threads)
+        for g, species_id in enumerate(ref.species_ids):
             sp = species[species_id]
-            sp.genome_length = int(stats["genome_length"][k])
-            sp.covered_bases = int(stats["covered_bases"][k])
-            sp.total_depth = int(stats["total_depth"][k])
-            sp.aligned_reads = int(stats["aligned_reads"][k])
-            sp.mapped_reads = int(stats["mapped_reads"][k])
+            sp.genome_length, sp.covered_bases, sp.total_depth, sp.aligned_reads, sp.mapped_reads = (int(x) for x in rows[g])
             if sp.genome_length > 0:
                 sp.fraction_covered = sp.covered_bases / float(sp.genome_length)
             if sp.covered_bases > 0:
@@ -251,7 +290,8 @@ def run_pipeline(args):
     if args.get("call"):
         index_bam(args)
         pysam_pileup(args, species, contigs)
-        snps_summary(args, species)
-    if args.get("remove_temp"):
+        if _world()[0] == 0:
+            snps_summary(args, species)
+    if args.get("remove_temp") and _world()[0] == 0:
         remove_tmp(args)
     return species

@@ -158,8 +158,8 @@ def allreduce_split_counts(counts, stats, layout, split_mask):
             dist.all_reduce(region)
             dist.all_reduce(am)
         counts[:, lo:hi] = region
-        depth = region.to(torch.int64).sum(0)
-        stats[k, 1] = int((depth > 0).sum())
-        stats[k, 2] = int(depth.sum())
+        depth = (region.to(torch.int64) & 0xFFFFFFFF).sum(0)          # the planes hold u32 bit patterns
+        stats[k, 1] = (depth > 0).sum()                               # tensor assignments: no host synchronisation
+        stats[k, 2] = depth.sum()
         stats[k, 3:5] = am
     return counts, stats

@@ -10,6 +10,11 @@ Flags, defaults, directory layout, log.txt and the on-disk outputs follow the re
   * -1 is not required for those stages (reference :391 requires it even for --pileup).
   * utility.add_executables (midas/utility.py:109-150) is not called: no samtools / bowtie2 needed.
   * `species` is not provided (alignment-bound, upstream of the hot path).
+  * multi-GPU: `torchrun --nproc-per-node N scripts/run_midas.py snps OUT -d DB --pileup` runs one process per GPU;
+    the species are dealt to the ranks (midas_b200.shard.plan: the reference's own unit of parallelism, one worker
+    per species, midas/run/snps.py:225-228), every rank writes its species' .snps.gz, rank 0 writes summary.txt,
+    log.txt and readme.txt. Without torchrun, --device picks the GPU.
+log.txt (opened 'w', parameter block) and readme.txt follow the reference (:432-481, :290-336, :630-746).
 """
 import argparse
 import os
@@ -85,28 +90,62 @@ def gene_arguments():
     return vars(p.parse_args())
 
 
+def init_distributed(args):
+    """Under torchrun: one process per GPU, NCCL for the small exchanges of the path. Returns (rank, world)."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world <= 1:
+        return 0, 1
+    import torch
+    import torch.distributed as dist
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    args["device"] = local
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return dist.get_rank(), world
+
+
 def main():
     program = get_program()
     args = snp_arguments() if program == "snps" else gene_arguments()
     stage = "call" if program == "snps" else "cov"
+    if args["species_id"]:
+        args["species_id"] = args["species_id"].split(",")
     if not (args["build_db"] or args["align"] or args[stage]):
         args[stage] = True
+        if args["m1"]:
+            sys.stderr.write("Note: this package runs the %s stage only; reads given with -1 are not aligned here - run "
+                             "--build_db / --align with the reference first\n" % ("--pileup" if program == "snps" else "--call_genes"))
     if args["db"] is None or not os.path.isdir(args["db"]):
         sys.exit("\nError: No reference database specified (-d / MIDAS_DB)\n")
+    rank, world = init_distributed(args)
+    if world > 1 and program != "snps":
+        sys.exit("\nError: multi-GPU runs are provided for `snps --pileup` (species shard by rank)\n")
     for d in ("", program, program + "/output", program + "/temp"):
         os.makedirs(os.path.join(args["outdir"], d), exist_ok=True)
     bam = os.path.join(args["outdir"], program, "temp", "genomes.bam" if program == "snps" else "pangenomes.bam")
     if args[stage] and not (args["build_db"] or args["align"]) and not os.path.isfile(bam):
         sys.exit("\nError: %s not found; run the --build_db and --align stages with the reference first\n" % bam)
-    args["log"] = open(os.path.join(args["outdir"], program, "log.txt"), "a")
-    args["log"].write("\nMIDAS (midas_b200): %s stage on CUDA device %d\n" % (program, args["device"]))
+    from midas_b200.run import cli_text
+    if rank == 0:
+        args["log"] = open(os.path.join(args["outdir"], program, "log.txt"), "w")     # reference :30-33
+        args["log"].write("\nMIDAS hot path on B200 (midas_b200): %s stage, %d GPU%s\n" % (program, world, "s" if world > 1 else ""))
+        cli_text.print_arguments(program, args)
+    else:
+        args["log"] = open(os.devnull, "w")
+        sys.stdout = open(os.devnull, "w")
     if program == "snps":
         from midas_b200.run import snps
         snps.run_pipeline(args)
     else:
         from midas_b200.run import genes
         genes.run_pipeline(args)
+    if rank == 0:
+        cli_text.write_readme(program, args)
     args["log"].close()
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -73,7 +73,11 @@ def test_cli_snps_and_genes(tmp_path):
     for sid in ref.species_ids:
         assert gzip.open(os.path.join(out, "snps", "output", sid + ".snps.gz"), "rb").read() == exp[sid + ".snps.tsv"]
     assert open(os.path.join(out, "snps", "summary.txt"), "rb").read() == exp["summary.txt"]
-    assert os.path.isfile(os.path.join(out, "snps", "log.txt"))
+    log = open(os.path.join(out, "snps", "log.txt")).read()
+    assert "===========Parameters===========" in log and "minimum base quality score: 30" in log
+    assert "Counting alleles" in log
+    readme = open(os.path.join(out, "snps", "readme.txt")).read()
+    assert "output/{SPECIES_ID}.snps.gz" in readme and readme.rstrip().endswith("/rep_genomes")
     # a missing BAM is a clean error, not a crash
     os.remove(os.path.join(out, "snps", "temp", "genomes.bam"))
     r = subprocess.run([sys.executable, cli, "snps", out, "-d", db, "--pileup"], capture_output=True, text=True)

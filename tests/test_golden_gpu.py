@@ -90,3 +90,32 @@ def test_cli_snps_and_genes(tmp_path):
     for sid in gref.species_ids:
         assert gzip.open(os.path.join(out2, "genes", "output", sid + ".genes.gz"), "rb").read() == gexp[sid + ".genes.tsv"]
     assert open(os.path.join(out2, "genes", "summary.txt"), "rb").read() == gexp["summary.txt"]
+
+
+def test_cli_snps_under_torchrun_two_gpus(tmp_path):
+    """torchrun --nproc-per-node 2 scripts/run_midas.py snps --pileup: species dealt to two ranks (one GPU each),
+    every rank writes its species, rank 0 the summary - byte for byte the reference's files. Needs two GPUs."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cli = os.path.join(root, "scripts", "run_midas.py")
+    for case in SNPS_CASES:
+        ref, reads, filters, extra = load_case(case)
+        if len(ref.species_ids) < 2:
+            continue
+        db, out = fixtures.write_snps_fixture(str(tmp_path / case), ref, reads,
+                                              lowercase_some=extra.get("lowercase_some", False))
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+               "127.0.0.1", "--master-port", "29731", cli, "snps", out, "-d", db, "--pileup", "-t", "2",
+               "--mapid", str(filters.mapid), "--mapq", str(filters.mapq), "--baseq", str(filters.baseq),
+               "--readq", str(filters.readq), "--aln_cov", str(filters.aln_cov)]
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-3000:]
+        exp = expected(case)
+        for sid in ref.species_ids:
+            got = gzip.open(os.path.join(out, "snps", "output", sid + ".snps.gz"), "rb").read()
+            assert got == exp[sid + ".snps.tsv"], (case, sid)
+        assert open(os.path.join(out, "snps", "summary.txt"), "rb").read() == exp["summary.txt"]

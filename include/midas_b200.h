@@ -373,13 +373,14 @@ int64_t mb_format_snps_rows(const char* contig_name, const uint8_t* ref_bases, u
 /* Rows of snps_freq.txt / snps_depth.txt of merge_midas.py snps (reference midas/merge/snps.py:196-201) for
  * n_rows kept sites: "site_id \t v(sample 0) \t v(sample 1) ... \n" with '{0:.3g}'.format(maf) resp.
  * str(depth). maf / depth are the sample-major outputs of mb_merge_sites_dev copied to the host (`stride`
- * sites per sample); row r is site site_index[r] (0-based), printed as site id site_index[r] + 1 (:352).
+ * sites per sample); row r is site site_index[r] (0-based within the arrays), printed as site id
+ * id_base + site_index[r] + 1 (:352; id_base = first site of the chunk the arrays hold).
  * Return the number of bytes written (< 0: mb_status). Host only. */
 uint64_t mb_format_merge_bound(uint64_t n_rows, uint32_t n_samples);
 int64_t mb_format_merge_freq_rows(const uint64_t* site_index, uint64_t n_rows, uint32_t n_samples, uint64_t stride,
-                                  const double* maf, char* out, uint64_t cap);
+                                  const double* maf, uint64_t id_base, char* out, uint64_t cap);
 int64_t mb_format_merge_depth_rows(const uint64_t* site_index, uint64_t n_rows, uint32_t n_samples, uint64_t stride,
-                                   const uint32_t* depth, char* out, uint64_t cap);
+                                   const uint32_t* depth, uint64_t id_base, char* out, uint64_t cap);
 
 #ifdef __cplusplus
 }

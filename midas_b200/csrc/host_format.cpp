@@ -75,14 +75,15 @@ extern "C" uint64_t mb_format_merge_bound(uint64_t n_rows, uint32_t n_samples) {
 }
 
 extern "C" int64_t mb_format_merge_freq_rows(const uint64_t* site_index, uint64_t n_rows, uint32_t n_samples,
-                                             uint64_t stride, const double* maf, char* out, uint64_t cap) {
+                                             uint64_t stride, const double* maf, uint64_t id_base, char* out,
+                                             uint64_t cap) {
   if (!site_index || !maf || !out) return mb::fail(MB_EINVAL, "mb_format_merge_freq_rows: null argument");
   if (cap < mb_format_merge_bound(n_rows, n_samples))
     return mb::fail(MB_EINVAL, "mb_format_merge_freq_rows: output buffer smaller than mb_format_merge_bound");
   char* p = out;
   for (uint64_t r = 0; r < n_rows; ++r) {
     const uint64_t g = site_index[r];
-    p = put_u64(p, g + 1);
+    p = put_u64(p, id_base + g + 1);
     for (uint32_t s = 0; s < n_samples; ++s) {
       *p++ = '\t';
       const double v = maf[(size_t)s * stride + g];
@@ -96,14 +97,15 @@ extern "C" int64_t mb_format_merge_freq_rows(const uint64_t* site_index, uint64_
 }
 
 extern "C" int64_t mb_format_merge_depth_rows(const uint64_t* site_index, uint64_t n_rows, uint32_t n_samples,
-                                              uint64_t stride, const uint32_t* depth, char* out, uint64_t cap) {
+                                              uint64_t stride, const uint32_t* depth, uint64_t id_base, char* out,
+                                              uint64_t cap) {
   if (!site_index || !depth || !out) return mb::fail(MB_EINVAL, "mb_format_merge_depth_rows: null argument");
   if (cap < mb_format_merge_bound(n_rows, n_samples))
     return mb::fail(MB_EINVAL, "mb_format_merge_depth_rows: output buffer smaller than mb_format_merge_bound");
   char* p = out;
   for (uint64_t r = 0; r < n_rows; ++r) {
     const uint64_t g = site_index[r];
-    p = put_u64(p, g + 1);
+    p = put_u64(p, id_base + g + 1);
     for (uint32_t s = 0; s < n_samples; ++s) {
       *p++ = '\t';
       p = put_u32(p, depth[(size_t)s * stride + g]);

@@ -472,32 +472,38 @@ __global__ void __launch_bounds__(256) k_pack_fill(const Plain in, const uint4* 
       const uint64_t so = __shfl_sync(0xffffffffu, so_m, rr), co = __shfl_sync(0xffffffffu, co_m, rr);
       const uint32_t lq = hy & 0xffffu, qstart = hz & 0xffffu, span = hw & 0xffffu, fl = hw >> 24;
       const uint32_t n_blk = (lq + MB_BLOCK - 1) / MB_BLOCK;
-      const uint8_t* __restrict__ qp = in.qual + so;
+      // my base of every block: quality byte at qb[32 b], sequence nibble in byte sb[16 b] (seq_off is even with nibble
+      // packing, so the nibble within the byte depends on the lane alone)
+      const uint8_t* __restrict__ qb = in.qual + so + lane;
+      const uint8_t* __restrict__ sb = in.nib ? in.seq + ((so + lane) >> 1) : in.seq + so + lane;
+      const uint32_t sb_step = in.nib ? 16u : 32u, nib_shift = (in.nib && !(lane & 1u)) ? 4u : 0u;
       const bool simple = (fl & MB_RF_SIMPLE) != 0;
       for (uint32_t b0 = 0; b0 < n_blk; b0 += 8) {
-        // ---- loads: base `lane` of each of the chunk's eight blocks, all in flight at once
-        uint32_t qa = 0, qb = 0, sn = 0;
+        // ---- loads: base `lane` of each of the chunk's (up to eight) blocks, all in flight at once
+        uint32_t qa = 0, qb4 = 0, sn = 0;
+        const uint8_t* __restrict__ qc = qb + (size_t)b0 * MB_BLOCK;
+        const uint8_t* __restrict__ sc = sb + (size_t)b0 * sb_step;
 #pragma unroll
         for (int s8 = 0; s8 < 8; ++s8) {
-          const uint32_t k = (b0 + s8) * MB_BLOCK + lane;
-          if (k < lq) {
-            const uint32_t q = qp[k];
-            if (s8 < 4) qa |= q << (8 * s8); else qb |= q << (8 * (s8 - 4));
+          if (b0 + s8 >= n_blk) break;                                     // uniform: the read has no such block
+          if ((b0 + s8) * MB_BLOCK + lane < lq) {
+            const uint32_t q = qc[s8 * (int)MB_BLOCK];
+            if (s8 < 4) qa |= q << (8 * s8); else qb4 |= q << (8 * (s8 - 4));
             if (MODE == 0) {
-              const uint64_t e = so + k;
-              const uint32_t nib = in.nib ? ((uint32_t)in.seq[e >> 1] >> ((e & 1) ? 0 : 4)) & 15u : (uint32_t)in.seq[e] & 15u;
+              const uint32_t nib = ((uint32_t)sc[s8 * sb_step] >> nib_shift) & 15u;
               // BAM nibble -> {low bit, high bit, is A/C/G/T}: A=1 C=2 G=4 T=8 -> 4, 5, 6, 7; anything else 0
               const uint32_t cls = nib == 8u ? 7u : (nib < 8u ? (0x00060540u >> (4 * nib)) & 7u : 0u);
               sn |= cls << (4 * s8);
             }
           }
         }
+        uint32_t qb_ = qb4;
         // ---- quality planes: lane 8 s + k <- Phred bit k of block b0 + s (first four blocks), b0 + 4 + s (last four)
         qa = warp_transpose32(qa, lane);
         if (qk < (uint32_t)NQ && b0 + qs < n_blk) word((b0 + qs) * NP + P0 + qk) = qa;
         if (b0 + 4 < n_blk) {
-          qb = warp_transpose32(qb, lane);
-          if (qk < (uint32_t)NQ && b0 + 4 + qs < n_blk) word((b0 + 4 + qs) * NP + P0 + qk) = qb;
+          qb_ = warp_transpose32(qb_, lane);
+          if (qk < (uint32_t)NQ && b0 + 4 + qs < n_blk) word((b0 + 4 + qs) * NP + P0 + qk) = qb_;
         }
         if (MODE == 0) {
           // ---- sequence planes: lane 4 s + k <- plane k of block b0 + s; the candidate plane (k = 2) keeps only the

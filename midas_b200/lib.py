@@ -161,7 +161,8 @@ def load():
     L.mb_format_merge_bound.argtypes = [C.c_uint64, C.c_uint32]
     for name in ("mb_format_merge_freq_rows", "mb_format_merge_depth_rows"):
         getattr(L, name).restype = C.c_int64
-        getattr(L, name).argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint64, C.c_void_p, C.c_char_p, C.c_uint64]
+        getattr(L, name).argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint64, C.c_void_p, C.c_uint64, C.c_char_p,
+                                     C.c_uint64]
     L.mb_format_snps_rows.restype = C.c_int64
     L.mb_format_snps_rows.argtypes = [C.c_char_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
@@ -539,10 +540,10 @@ class _BamHandle:
             _lib.mb_bam_close(h)
 
 
-def format_merge_rows(site_index: np.ndarray, maf: np.ndarray, depth: np.ndarray):
+def format_merge_rows(site_index: np.ndarray, maf: np.ndarray, depth: np.ndarray, first_site: int = 0):
     """Text rows of snps_freq.txt and snps_depth.txt (reference midas/merge/snps.py:196-201) for the kept sites
-    `site_index` (0-based, uint64): maf f64 [S][G] and depth u32 [S][G] as mb_merge_sites_dev wrote them.
-    Returns (freq_bytes, depth_bytes)."""
+    `site_index` (0-based within the chunk, uint64): maf f64 [S][G] and depth u32 [S][G] as mb_merge_sites_dev wrote
+    them; the printed site id is first_site + index + 1. Returns (freq_bytes, depth_bytes)."""
     L = load()
     site_index = np.ascontiguousarray(site_index, np.uint64)
     maf = np.ascontiguousarray(maf, np.float64)
@@ -554,7 +555,7 @@ def format_merge_rows(site_index: np.ndarray, maf: np.ndarray, depth: np.ndarray
     out = []
     for fn, arr in ((L.mb_format_merge_freq_rows, maf), (L.mb_format_merge_depth_rows, depth)):
         buf = C.create_string_buffer(max(cap, 1))
-        w = fn(_ptr(site_index), n, S, G, _ptr(arr), buf, cap)
+        w = fn(_ptr(site_index), n, S, G, _ptr(arr), int(first_site), buf, cap)
         if w < 0:
             _check(int(w))
         out.append(buf.raw[:w])

@@ -7,9 +7,12 @@ snp_type, per-sample depth and minor-allele frequency, prevalence (:42-104), the
 :106-114), the gene annotation of the sites that are kept (`annotate` :116-172) and three text rows
 (`write` :174-201); finally the shards are concatenated (merge_sharded_tables :388-407).
 
-Here the count columns of all samples are parsed straight into one `uint32 [samples][4][sites]` array, the
-whole per-site arithmetic is ONE call into libmidas_b200.so (`mb_merge_sites_dev`, csrc/merge.cu), and only the
-sites that survive the filter are annotated and formatted on the host. Same outputs, byte for byte:
+Here the sites of a species are processed in fixed-size chunks (a few hundred thousand rows, sized so that a chunk
+of all samples stays near 1 GB: the reference streams one row at a time at O(samples) memory and is run on thousands
+of samples, so nothing here may scale with samples x genome): the count columns of all samples are parsed straight
+into one `uint32 [samples][4][chunk]` array, the per-site arithmetic of the chunk is ONE call into
+libmidas_b200.so (`mb_merge_sites_dev`, csrc/merge.cu), and only the sites that survive the filter are annotated
+and formatted on the host, appended to the three tables. Same outputs, byte for byte:
 `<outdir>/<species>/snps_{info,freq,depth,summary}.txt` (readme.txt is this package's own wording).
 Site ids are the 1-based row numbers of the samples' tables, as in the reference (:352).
 
@@ -64,33 +67,72 @@ def gpu_site_engine(device=0):
 
 
 # ------------------------------------------------------------------------------------------ inputs
-def read_sample_counts(species_id, samples, max_sites=float("inf"), threads=1):
+CHUNK_TARGET_BYTES = 1 << 30          # counts in + depth / maf out of one chunk of all samples (28 B per sample and site)
+
+
+def chunk_rows_for(n_samples: int) -> int:
+    return int(min(1 << 20, max(1 << 14, CHUNK_TARGET_BYTES // (28 * max(1, n_samples)))))
+
+
+def iter_sample_counts(species_id, samples, max_sites=float("inf"), threads=1, chunk_rows=None):
     """The samples' `<dir>/snps/output/<species>.snps.gz` tables (reference read_run_midas_snps :225-231 +
-    build_temp_count_matrix :233-259) as (ref_id [G], ref_pos [G], ref_allele [G], counts u32 [S][4][G]).
-    Site identity comes from the first sample; the table ends with the shortest sample and at max_sites."""
+    build_temp_count_matrix :233-259), `chunk_rows` sites at a time: yields (first_site, ref_id [g], ref_pos [g],
+    ref_allele [g], counts u32 [S][4][g]). Site identity comes from the first sample; the table ends with the
+    shortest sample and at max_sites. Memory is O(samples x chunk_rows), whatever the genome size."""
     import pandas as pd
     from concurrent.futures import ThreadPoolExecutor
     cols = ["ref_id", "ref_pos", "ref_allele", "depth", "count_a", "count_c", "count_g", "count_t"]
     nrows = None if max_sites == float("inf") else int(max_sites)
+    chunk_rows = int(chunk_rows or chunk_rows_for(len(samples)))
 
-    def table(k):
+    def reader(k):
         path = "%s/snps/output/%s.snps.gz" % (samples[k].dir, species_id)
         return pd.read_csv(path, sep="\t", header=0, names=cols, usecols=cols if k == 0 else cols[4:], nrows=nrows,
-                           keep_default_na=False, compression="gzip", engine="c",
+                           keep_default_na=False, compression="gzip", engine="c", chunksize=chunk_rows,
                            dtype={"ref_id": str, "ref_pos": np.int64, "ref_allele": str, "count_a": np.uint32,
                                   "count_c": np.uint32, "count_g": np.uint32, "count_t": np.uint32})
 
-    # one table per sample, parsed concurrently (inflate and the C parser release the GIL)
-    with ThreadPoolExecutor(max(1, min(int(threads or 1), len(samples) or 1))) as pool:
-        frames = list(pool.map(table, range(len(samples))))
-    G = min(len(f) for f in frames) if frames else 0
-    counts = np.empty((len(frames), 4, G), np.uint32)
-    for s, f in enumerate(frames):
-        for k, c in enumerate(cols[4:]):
-            counts[s, k] = f[c].to_numpy()[:G]
-    first = frames[0]
-    return (first["ref_id"].to_numpy()[:G], first["ref_pos"].to_numpy()[:G], first["ref_allele"].to_numpy()[:G],
-            counts)
+    readers = [reader(k) for k in range(len(samples))]
+    if not readers:
+        return
+
+    def pull(r):
+        try:
+            return next(r)
+        except StopIteration:
+            return None
+
+    first_site = 0
+    # one chunk per sample, parsed concurrently (inflate and the C parser release the GIL)
+    with ThreadPoolExecutor(max(1, min(int(threads or 1), len(samples)))) as pool:
+        while True:
+            frames = list(pool.map(pull, readers))
+            if any(f is None for f in frames):
+                break
+            g = min(len(f) for f in frames)
+            if g == 0:
+                break
+            counts = np.empty((len(frames), 4, g), np.uint32)
+            for s_, f in enumerate(frames):
+                for k, c in enumerate(cols[4:]):
+                    counts[s_, k] = f[c].to_numpy()[:g]
+            first = frames[0]
+            yield (first_site, first["ref_id"].to_numpy()[:g], first["ref_pos"].to_numpy()[:g],
+                   first["ref_allele"].to_numpy()[:g], counts)
+            first_site += g
+            if any(len(f) != g for f in frames) or g < chunk_rows:      # the shortest sample ended inside this chunk
+                break
+    for r in readers:
+        r.close()
+
+
+def read_sample_counts(species_id, samples, max_sites=float("inf"), threads=1):
+    """Whole-table form of iter_sample_counts (small inputs / tests): (ref_id, ref_pos, ref_allele, counts [S][4][G])."""
+    parts = list(iter_sample_counts(species_id, samples, max_sites, threads))
+    if not parts:
+        return np.zeros(0, object), np.zeros(0, np.int64), np.zeros(0, object), np.zeros((len(samples), 4, 0), np.uint32)
+    return (np.concatenate([p[1] for p in parts]), np.concatenate([p[2] for p in parts]),
+            np.concatenate([p[3] for p in parts]), np.concatenate([p[4] for p in parts], axis=2))
 
 
 def read_genes(species_id, db):
@@ -171,37 +213,50 @@ def _na(x):
     return "NA" if x is None else x
 
 
-def write_tables(species, args, ref_id, ref_pos, ref_allele, res, keep, genes):
-    """snps_info.txt / snps_freq.txt / snps_depth.txt (reference write_merge_midas :276-322, write :174-201)."""
-    outdir = "%s/%s" % (args["outdir"], species.id)
-    header = "\t".join(["site_id"] + [s.id for s in species.samples]) + "\n"
-    index = GeneIndex(genes)
-    pooled, major, minor = res["pooled"], res["major"], res["minor"]
-    from concurrent.futures import ThreadPoolExecutor
-    from .. import lib
-    maf = np.ascontiguousarray(res["sample_maf"], np.float64)
-    dep = np.ascontiguousarray(res["sample_depth"]).astype(np.uint32, copy=False)
-    keep = np.ascontiguousarray(keep, np.uint64)
-    chunks = [keep[lo:lo + ROWS_PER_CHUNK] for lo in range(0, len(keep), ROWS_PER_CHUNK)]
-    with open(outdir + "/snps_info.txt", "w") as f_info, open(outdir + "/snps_freq.txt", "wb") as f_freq, \
-            open(outdir + "/snps_depth.txt", "wb") as f_depth, \
-            ThreadPoolExecutor(max(1, int(args.get("threads", 1) or 1))) as pool:
-        f_info.write("\t".join(INFO_FIELDS) + "\n")
-        f_freq.write(header.encode())
-        f_depth.write(header.encode())
-        # the two matrices: native row formatter (mb_format_merge_*_rows), chunks formatted concurrently
-        texts = pool.map(lambda c: lib.format_merge_rows(c, maf, dep), chunks)
+class TableWriter:
+    """snps_info.txt / snps_freq.txt / snps_depth.txt (reference write_merge_midas :276-322, write :174-201),
+    appended chunk by chunk."""
+
+    def __init__(self, species, args, genes):
+        from concurrent.futures import ThreadPoolExecutor
+        outdir = "%s/%s" % (args["outdir"], species.id)
+        header = "\t".join(["site_id"] + [s.id for s in species.samples]) + "\n"
+        self.index = GeneIndex(genes)
+        self.f_info = open(outdir + "/snps_info.txt", "w")
+        self.f_freq = open(outdir + "/snps_freq.txt", "wb")
+        self.f_depth = open(outdir + "/snps_depth.txt", "wb")
+        self.pool = ThreadPoolExecutor(max(1, int(args.get("threads", 1) or 1)))
+        self.f_info.write("\t".join(INFO_FIELDS) + "\n")
+        self.f_freq.write(header.encode())
+        self.f_depth.write(header.encode())
+
+    def write_chunk(self, first_site, ref_id, ref_pos, ref_allele, res, keep):
+        """`keep`: indices (within the chunk) of the sites that passed the filter; site ids are 1-based row numbers
+        of the samples' tables (:352), i.e. first_site + index + 1."""
+        from .. import lib
+        pooled, major, minor = res["pooled"], res["major"], res["minor"]
+        maf = np.ascontiguousarray(res["sample_maf"], np.float64)
+        dep = np.ascontiguousarray(res["sample_depth"]).astype(np.uint32, copy=False)
+        keep = np.ascontiguousarray(keep, np.uint64)
+        chunks = [keep[lo:lo + ROWS_PER_CHUNK] for lo in range(0, len(keep), ROWS_PER_CHUNK)]
+        # the two matrices: native row formatter (mb_format_merge_*_rows), pieces formatted concurrently
+        texts = self.pool.map(lambda c: lib.format_merge_rows(c, maf, dep, first_site), chunks)
         for g in keep.tolist():                                      # the annotated info rows, kept sites only
-            sid, rid, pos = str(g + 1), str(ref_id[g]), int(ref_pos[g])
-            locus, gene_id, site_type, aas = annotate(rid, pos, index.find(rid, pos))
+            sid, rid, pos = str(first_site + g + 1), str(ref_id[g]), int(ref_pos[g])
+            locus, gene_id, site_type, aas = annotate(rid, pos, self.index.find(rid, pos))
             info = [sid, rid, str(pos), str(ref_allele[g]),
                     ALLELES[major[g]] if major[g] >= 0 else None, ALLELES[minor[g]] if minor[g] >= 0 else None,
                     str(int(res["count_samples"][g]))] + [str(int(pooled[k][g])) for k in range(4)] + \
                    [locus, gene_id, SNP_TYPES[int(res["snp_type"][g])], site_type, aas]
-            f_info.write("\t".join(_na(x) for x in info) + "\n")
+            self.f_info.write("\t".join(_na(x) for x in info) + "\n")
         for freq, depth in texts:
-            f_freq.write(freq)
-            f_depth.write(depth)
+            self.f_freq.write(freq)
+            self.f_depth.write(depth)
+
+    def close(self):
+        self.pool.shutdown()
+        for f in (self.f_info, self.f_freq, self.f_depth):
+            f.close()
 
 
 def write_snps_readme(args, sp):
@@ -214,26 +269,29 @@ def write_snps_readme(args, sp):
 
 
 # ------------------------------------------------------------------------------------------ pipeline
-def merge_species(species, args, engine):
-    """All sites of one species: parse, pooled call (GPU), filter (reference flag :106-114), annotate, write.
-    Returns (n_sites, n_kept)."""
-    ref_id, ref_pos, ref_allele, counts = read_sample_counts(species.id, species.samples, args["max_sites"],
-                                                             threads=args.get("threads", 1))
-    S, G = counts.shape[0], counts.shape[2]
-    if G == 0:
-        res = dict(pooled=np.zeros((4, 0), np.uint32), major=np.zeros(0, np.int8), minor=np.zeros(0, np.int8),
-                   snp_type=np.zeros(0, np.int8), count_samples=np.zeros(0, np.int64),
-                   sample_depth=np.zeros((S, 0), np.uint32), sample_maf=np.zeros((S, 0)))
-    else:
-        res = engine(counts, species.sample_depth, args["allele_freq"], args["site_depth"], args["site_ratio"])
-    prevalence = np.asarray(res["count_samples"], np.int64) / float(S)           # compute_prevalence :104
-    ok = ~(prevalence < args["site_prev"])
-    if "any" not in args["snp_type"]:
-        wanted = [t for t in range(1, 5) if SNP_TYPES[t] in args["snp_type"]]
-        ok &= np.isin(res["snp_type"], wanted)
-    keep = np.flatnonzero(ok)
-    write_tables(species, args, ref_id, ref_pos, ref_allele, res, keep, read_genes(species.id, args["db"]))
-    return G, len(keep)
+def merge_species(species, args, engine, chunk_rows=None):
+    """All sites of one species, a chunk of sites at a time: parse, pooled call (GPU), filter (reference flag
+    :106-114), annotate, append. Returns (n_sites, n_kept)."""
+    S = len(species.samples)
+    writer = TableWriter(species, args, read_genes(species.id, args["db"]))
+    n_sites = n_kept = 0
+    try:
+        for first_site, ref_id, ref_pos, ref_allele, counts in iter_sample_counts(
+                species.id, species.samples, args["max_sites"], threads=args.get("threads", 1), chunk_rows=chunk_rows):
+            res = engine(counts, species.sample_depth, args["allele_freq"], args["site_depth"], args["site_ratio"])
+            del counts
+            prevalence = np.asarray(res["count_samples"], np.int64) / float(S)           # compute_prevalence :104
+            ok = ~(prevalence < args["site_prev"])
+            if "any" not in args["snp_type"]:
+                wanted = [t for t in range(1, 5) if SNP_TYPES[t] in args["snp_type"]]
+                ok &= np.isin(res["snp_type"], wanted)
+            keep = np.flatnonzero(ok)
+            writer.write_chunk(first_site, ref_id, ref_pos, ref_allele, res, keep)
+            n_sites += len(ref_pos)
+            n_kept += len(keep)
+    finally:
+        writer.close()
+    return n_sites, n_kept
 
 
 def run_pipeline(args, engine=None, shard=None):
@@ -255,7 +313,7 @@ def run_pipeline(args, engine=None, shard=None):
     print("\nMerging snps")
     for species in species_list:
         print("  %s" % species.id)
-        n_sites, n_kept = merge_species(species, args, engine)
+        n_sites, n_kept = merge_species(species, args, engine, chunk_rows=args.get("chunk_rows"))
         print("    %s sites, %s written" % (n_sites, n_kept))
         write_snps_readme(args, species)
         species.write_sample_info(dtype="snps", outdir=args["outdir"])

@@ -61,10 +61,13 @@ def test_kernel_matches_golden(ctx, case):
 @pytest.mark.gpu
 @pytest.mark.parametrize("seed,S,G,depth", [(1, 3, 10_000, 30.0), (2, 20, 50_001, 30.0), (3, 1, 777, 30.0),
                                              (4, 64, 4096, 30.0), (5, 40, 3000, 180.0), (6, 100, 2000, 60.0),
-                                             (7, 33, 1500, 400.0)])
+                                             (7, 33, 1500, 400.0), (8, 129, 1500, 20.0), (9, 200, 1200, 25.0),
+                                             (10, 129, 900, 300.0), (11, 200, 700, 350.0)])
 def test_kernel_matches_oracle(ctx, seed, S, G, depth):
-    """depth 180-400: many sites hold counts above 255 and take the re-read path instead of the packed registers;
-    S = 100: samples past the register-resident 64."""
+    """depth 180-400: many sites hold counts above 255 and take the re-read path instead of the packed (8-bit)
+    registers. S = 33..128: samples past the 32 register-resident ones live in the shared-memory column;
+    S = 129, 200: the samples past the 128th take the separate re-read branch of both passes (low depth = packed
+    sites, high depth = wide sites)."""
     counts, md = mo.synth_counts(seed, S, G, depth_mean=depth, snp_frac=0.2)
     exp = mo.merge_sites(counts, md, 0.05, 3, 1.5)
     _gpu_check(ctx, counts, md, 0.05, 3, 1.5, exp)

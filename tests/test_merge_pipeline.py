@@ -53,6 +53,23 @@ def test_pipeline_files_match_the_reference_on_the_gpu(case, tmp_path):
     _run_and_compare(case, tmp_path, None)
 
 
+@pytest.mark.parametrize("chunk_rows", [1, 37, 500])
+def test_site_chunks_of_any_size_give_the_same_files(chunk_rows, tmp_path):
+    """The sites are processed a chunk at a time (memory O(samples x chunk), not O(samples x genome)): whatever the
+    chunk size - one row, a size that leaves a ragged last chunk, larger than a table - the files are the reference's."""
+    case = "all_sites"
+    with open(os.path.join(GOLD, "cases", case, "args.json")) as fh:
+        over = json.load(fh)
+    db, dirs = _inputs()
+    args = merge_args(str(tmp_path / "out"), db, dirs, chunk_rows=chunk_rows, **over)
+    os.makedirs(args["outdir"])
+    msnps.run_pipeline(args, engine=mo.merge_sites)
+    for sp in sorted(d for d in os.listdir(os.path.join(GOLD, "cases", case)) if d != "args.json"):
+        for fn in FILES:
+            with open(os.path.join(GOLD, "cases", case, sp, fn), "rb") as a, open(os.path.join(args["outdir"], sp, fn), "rb") as b:
+                assert a.read() == b.read(), (sp, fn)
+
+
 def test_gene_lookup_equals_the_reference_pointer_walk():
     """GeneIndex.find against a direct restatement of the pointer walk of annotate (snps.py:121-139)."""
     db, _ = _inputs()
@@ -100,6 +117,10 @@ def test_native_row_formatter_equals_python_format():
     exp_f = "".join(str(int(g) + 1) + "\t" + "\t".join("{0:.3g}".format(x) for x in maf[:, g].tolist()) + "\n" for g in keep)
     exp_d = "".join(str(int(g) + 1) + "\t" + "\t".join(str(x) for x in depth[:, g].tolist()) + "\n" for g in keep)
     assert freq.decode() == exp_f and dep.decode() == exp_d
+    # a chunk that starts at site 123456: the printed ids are offset, the data indices are not
+    freq2, dep2 = lib.format_merge_rows(keep[:5], maf, depth, first_site=123456)
+    assert freq2.decode().split("\n")[0].split("\t")[0] == str(123456 + int(keep[0]) + 1)
+    assert freq2.decode().split("\t", 1)[1].split("\n")[0] == exp_f.split("\t", 1)[1].split("\n")[0]
 
 
 def test_species_shard_over_ranks_without_a_collective(tmp_path):

@@ -110,6 +110,10 @@ struct mb_ctx {
   uint32_t* ovf_host;
   // peer-memory mirror of the stats rows (multi-GPU), or null
   mb_species_stats* stats_mirror;
+  // overlapped host-buffer path: the bulk arrays cross PCIe on a second stream, a chunk of reads at a time
+  static constexpr int kChunks = 8;
+  cudaStream_t copy_stream;
+  cudaEvent_t chunk_ev[kChunks + 1];
 };
 
 namespace mb {
@@ -123,6 +127,12 @@ int get_filter_tables(mb_ctx* ctx, const mb_filters* f, const int32_t** t_pid, c
 int pack_on_device(mb_ctx* ctx, const mb_plain_reads* dev, const mb_layout* L, int mode, bool staged, mb_dev_reads* d);
 // copy the plain arrays of `host` into context staging buffers (slots from `slot0`), `dev` gets the device pointers
 int upload_plain(mb_ctx* ctx, const mb_plain_reads* host, mb_plain_reads* dev);
+// host records -> packed batch in context staging buffers with the transfer of seq / qual overlapped with the
+// re-layout (chunks of reads). *done = false: the batch does not qualify (small, or contigs must move), nothing was done.
+// *respec = true after the final stream sync means: Phred > 63 seen, the caller must re-pack with pack_on_device.
+int pack_from_host_overlapped(mb_ctx* ctx, const mb_plain_reads* host, const mb_layout* L, int mode, mb_plain_reads* dev,
+                              mb_dev_reads* d, bool* done);
+int pack_overlapped_verdict(mb_ctx* ctx, bool* respec);   // after a stream sync: errors / re-pack needed
 void free_dev_reads_arrays(mb_dev_reads* d);
 int check_overflow(mb_ctx* ctx, const char* who);   // after a stream sync: MB_EOVERFLOW if the flag is set (and clears it)
 }  // namespace mb

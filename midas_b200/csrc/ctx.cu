@@ -172,6 +172,8 @@ extern "C" int mb_ctx_create(int device, mb_ctx** out) {
   c->stats_mirror = nullptr;
   MB_CUDA_TRY(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
   c->stream = c->own_stream;
+  MB_CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  for (int i = 0; i <= mb_ctx::kChunks; ++i) MB_CUDA_TRY(cudaEventCreateWithFlags(&c->chunk_ev[i], cudaEventDisableTiming));
   MB_CUDA_TRY(cudaMalloc(&c->pack_meta, 2048));
   MB_CUDA_TRY(cudaHostAlloc(&c->pack_meta_host, 2048, cudaHostAllocDefault));
   MB_CUDA_TRY(cudaEventCreate(&c->pack_ev[0]));
@@ -202,6 +204,8 @@ extern "C" void mb_ctx_destroy(mb_ctx* c) {
   }
   for (int i = 0; i < mb_ctx::kStage; ++i)
     if (c->stage[i]) cudaFree(c->stage[i]);
+  cudaStreamDestroy(c->copy_stream);
+  for (int i = 0; i <= mb_ctx::kChunks; ++i) cudaEventDestroy(c->chunk_ev[i]);
   if (c->pack_meta) cudaFree(c->pack_meta);
   if (c->pack_meta_host) cudaFreeHost(c->pack_meta_host);
   cudaEventDestroy(c->pack_ev[0]);

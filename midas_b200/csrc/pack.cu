@@ -47,7 +47,15 @@ struct Plain {  // device view of mb_plain_reads
   const uint32_t* cigar;
   const uint8_t *seq, *qual;
   uint32_t nib;
+  uint32_t qual_later;   // 1: the quality bytes are still in flight (overlapped transfer): k_pack_fill checks for 0xFF
 };
+
+__global__ void k_pack_meta_init(PackMeta* m) {   // a kernel, not a copy: nothing of the packer queues behind bulk transfers
+  uint32_t* w = reinterpret_cast<uint32_t*>(m);
+  for (uint32_t i = threadIdx.x; i < sizeof(PackMeta) / 4; i += blockDim.x) w[i] = 0;
+  __syncthreads();
+  if (threadIdx.x == 0) m->err = ~0ull;
+}
 
 __device__ __forceinline__ void report(PackMeta* m, uint64_t i, uint32_t code) {
   atomicMin(&m->err, (unsigned long long)((i << 8) | code));
@@ -122,7 +130,7 @@ __global__ void __launch_bounds__(256) k_pack_analyse(const Plain in, const uint
     if (in.nib && (so & 1)) { report(meta, i, PE_SEQALIGN); continue; }
     const int32_t nm_raw = in.nm[i];
     if (nm_raw < 0) { report(meta, i, PE_NM); continue; }
-    if (in.qual[so] == 0xFF) { report(meta, i, PE_NOQUAL); continue; }
+    if (!in.qual_later && in.qual[so] == 0xFF) { report(meta, i, PE_NOQUAL); continue; }
     const uint64_t co = in.cigar_off[i];
     const int64_t n_cig = (int64_t)(in.cigar_off[i + 1] - co);
     if (n_cig > 65535) { report(meta, i, PE_NCIG); continue; }
@@ -228,8 +236,8 @@ __global__ void __launch_bounds__(256) k_pack_analyse(const Plain in, const uint
 // ---- OR of the whole quality array [seq_off[0], seq_off[n]) as one flat stream (padding elements included: they
 // are zero from every producer in this repository; if a foreign producer left garbage there, bits 6-7 show up
 // and the exact per-record pass below decides)
-__global__ void __launch_bounds__(256) k_pack_qor_flat(const Plain in, PackMeta* meta) {
-  const uintptr_t a0 = (uintptr_t)(in.qual + in.seq_off[0]), a1 = (uintptr_t)(in.qual + in.seq_off[in.n]);
+__global__ void __launch_bounds__(256) k_pack_qor_flat(const Plain in, PackMeta* meta, uint64_t r_lo, uint64_t r_hi) {
+  const uintptr_t a0 = (uintptr_t)(in.qual + in.seq_off[r_lo]), a1 = (uintptr_t)(in.qual + in.seq_off[r_hi]);
   const uintptr_t v0 = (a0 + 15) & ~(uintptr_t)15, v1 = a1 & ~(uintptr_t)15;
   uint32_t acc = 0;
   const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, nt = (uint64_t)gridDim.x * blockDim.x;
@@ -438,15 +446,14 @@ template <int MODE, int NQ>
 __global__ void __launch_bounds__(256) k_pack_fill(const Plain in, const uint4* __restrict__ hdr,
                                                    const uint32_t* __restrict__ src_of,
                                                    const uint32_t* __restrict__ vec_off, uint64_t n,
-                                                   const PackMeta* __restrict__ meta, uint32_t* planes) {
+                                                   PackMeta* meta, uint32_t* planes, uint64_t g_lo, uint64_t g_hi) {
   constexpr uint32_t P0 = MODE == 0 ? 3u : 0u, NP = P0 + NQ;
   const uint32_t n_vec = (uint32_t)meta->n_vec;
   const uint32_t lane = threadIdx.x & 31;
   const uint64_t wg = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-  const uint64_t n_groups = (n + MB_GROUP - 1) / MB_GROUP;
   const uint32_t qs = lane >> 3, qk = lane & 7u;      // after a quality transposition: block qs of four, Phred bit qk
   const uint32_t ss = lane >> 2, sk = lane & 3u;      // after a sequence transposition: block ss of eight, plane sk
-  for (uint64_t g = wg; g < n_groups; g += nw) {
+  for (uint64_t g = g_lo + wg; g < g_hi; g += nw) {
     const uint64_t g0 = g * MB_GROUP, g1 = g0 + MB_GROUP;
     const uint32_t v0 = __ldg(&vec_off[g0]);
     const uint32_t units = ((g1 < n ? __ldg(&vec_off[g1]) : n_vec) - v0) / MB_GROUP;
@@ -474,6 +481,7 @@ __global__ void __launch_bounds__(256) k_pack_fill(const Plain in, const uint4* 
       const uint32_t n_blk = (lq + MB_BLOCK - 1) / MB_BLOCK;
       // my base of every block: quality byte at qb[32 b], sequence nibble in byte sb[16 b] (seq_off is even with nibble
       // packing, so the nibble within the byte depends on the lane alone)
+      if (in.qual_later && lane == 0 && in.qual[so] == 0xFF) report(meta, src_of[g0 + rr], PE_NOQUAL);
       const uint8_t* __restrict__ qb = in.qual + so + lane;
       const uint8_t* __restrict__ sb = in.nib ? in.seq + ((so + lane) >> 1) : in.seq + so + lane;
       const uint32_t sb_step = in.nib ? 16u : 32u, nib_shift = (in.nib && !(lane & 1u)) ? 4u : 0u;
@@ -537,6 +545,9 @@ __global__ void __launch_bounds__(256) k_pack_fill(const Plain in, const uint4* 
     }
   }
 }
+
+typedef void (*FillFn)(const Plain, const uint4*, const uint32_t*, const uint32_t*, uint64_t, PackMeta*, uint32_t*, uint64_t,
+                       uint64_t);
 
 const char* pack_err_text(uint32_t code, int* status) {
   switch (code) {
@@ -631,16 +642,13 @@ int pack_on_device(mb_ctx* c, const mb_plain_reads* in, const mb_layout* L, int 
   if (!rc) rc = pack_alloc(c, staged, 34, 4 * (size_t)(n + 1), (void**)&d->vec_off);
   if (!rc) rc = pack_alloc(c, staged, 35, 4 * (size_t)n, (void**)&d->cplx);
   if (rc) return rc;
-  PackMeta init;
-  memset(&init, 0, sizeof(init));
-  init.err = ~0ull;
-  *hm = init;   // pinned: the async copy below reads it before anything overwrites it (stream order + the sync below)
-  MB_CUDA_TRY(cudaMemcpyAsync(meta, hm, sizeof(PackMeta), cudaMemcpyHostToDevice, st));
+  k_pack_meta_init<<<1, 256, 0, st>>>(meta);
   Plain P;
   P.n = n;
   P.ref_id = in->ref_id; P.pos = in->pos; P.nm = in->nm; P.l_qseq = in->l_qseq; P.mapq = in->mapq;
   P.cigar_off = in->cigar_off; P.seq_off = in->seq_off; P.cigar = in->cigar; P.seq = in->seq; P.qual = in->qual;
   P.nib = in->seq_nibbles ? 1u : 0u;
+  P.qual_later = 0;
   mb_dev_layout dl{};
   if (mode == 0) { rc = get_dev_layout(c, L, &dl); if (rc) return rc; }
   const uint32_t grid = (uint32_t)std::min<uint64_t>((n + 255) / 256, (uint64_t)c->sm_count * 8);
@@ -661,7 +669,7 @@ int pack_on_device(mb_ctx* c, const mb_plain_reads* in, const mb_layout* L, int 
   for (int pass = 0; pass < 2; ++pass) {
     if (n) {
       if (pass == 0) {
-        k_pack_qor_flat<<<(uint32_t)c->sm_count * 8, 256, 0, st>>>(P, meta);
+        k_pack_qor_flat<<<(uint32_t)c->sm_count * 8, 256, 0, st>>>(P, meta, 0, n);
       } else {   // Phred > 63 somewhere (or garbage in padding): the exact per-record pass decides
         MB_CUDA_TRY(cudaMemsetAsync(&meta->q_or, 0, sizeof(uint32_t), st));
         MB_CUDA_TRY(cudaMemsetAsync(&meta->max_units, 0, sizeof(uint32_t), st));
@@ -726,10 +734,10 @@ int pack_on_device(mb_ctx* c, const mb_plain_reads* in, const mb_layout* L, int 
     }
     {
       const uint32_t fgrid = (uint32_t)std::min<uint64_t>((n_groups + 7) / 8, (uint64_t)c->sm_count * 8);
-      void (*fill)(const Plain, const uint4*, const uint32_t*, const uint32_t*, uint64_t, const PackMeta*, uint32_t*) =
-          mode == 0 ? (d->q_planes == 6 ? k_pack_fill<0, 6> : k_pack_fill<0, 7>)
-                    : (d->q_planes == 6 ? k_pack_fill<1, 6> : k_pack_fill<1, 7>);
-      fill<<<fgrid, 256, 0, st>>>(P, (const uint4*)d->hdr, (const uint32_t*)src_of, d->vec_off, n, meta, d->planes);
+      FillFn fill = mode == 0 ? (d->q_planes == 6 ? k_pack_fill<0, 6> : k_pack_fill<0, 7>)
+                              : (d->q_planes == 6 ? k_pack_fill<1, 6> : k_pack_fill<1, 7>);
+      fill<<<fgrid, 256, 0, st>>>(P, (const uint4*)d->hdr, (const uint32_t*)src_of, d->vec_off, n, meta, d->planes, 0,
+                                  n_groups);
     }
     c->launches += 1;
   } else {
@@ -738,6 +746,203 @@ int pack_on_device(mb_ctx* c, const mb_plain_reads* in, const mb_layout* L, int 
   MB_CUDA_TRY(cudaEventRecord(c->pack_ev[1], st));
   MB_CUDA_TRY(cudaGetLastError());
   d->bytes = sizeof(mb_read_hdr) * n + 4 * (n + 1) + 4 * n + 4 * n_cig + (uint64_t)d->n_vec * 32 + 4 * (uint64_t)d->n_long;
+  return MB_OK;
+}
+
+}  // namespace mb
+
+namespace mb {
+
+// The host-buffer path of a large batch: the small per-read arrays go first, the analysis and the unit scan run on
+// them while seq / qual cross PCIe on a second stream, a chunk of reads at a time; every chunk is turned into
+// planes as soon as it has landed. Six Phred planes are assumed (Phred <= 63); the OR of the quality bytes is
+// collected on the way and, in the rare batch that needs seven, the caller re-packs (pack_overlapped_verdict).
+int pack_from_host_overlapped(mb_ctx* c, const mb_plain_reads* h, const mb_layout* L, int mode, mb_plain_reads* dev,
+                              mb_dev_reads* d, bool* done) {
+  *done = false;
+  const uint64_t n = h->n_reads;
+  uint64_t min_reads = 1u << 18;
+  if (const char* e = getenv("MB_OVERLAP_MIN_READS")) min_reads = (uint64_t)atoll(e);
+  if (getenv("MB_NO_OVERLAP") || n < min_reads || n < 64 || n >= 0xFFFFFFFFull) return MB_OK;
+  if (mode == 0 && (L->genes_only || !L->identity_order)) return MB_OK;   // contigs would move: sources are not chunk-local
+  {  // only page-locked sources are copied asynchronously; pageable ones would serialise on the host anyway
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, h->qual) != cudaSuccess || at.type != cudaMemoryTypeHost) { cudaGetLastError(); return MB_OK; }
+    if (cudaPointerGetAttributes(&at, h->seq) != cudaSuccess || at.type != cudaMemoryTypeHost) { cudaGetLastError(); return MB_OK; }
+  }
+  memset(d, 0, sizeof(*d));
+  d->owned = false;
+  // all transfers stay on the context stream (one queue, one copy engine, the order the data is needed in); the
+  // re-layout kernels run on the second stream behind events and rejoin the context stream at the end
+  const bool swap = getenv("MB_OVERLAP_KERNELS_ON_MAIN") != nullptr;     // experiment: the other assignment
+  cudaStream_t cs = swap ? c->copy_stream : c->stream;                   // transfers
+  cudaStream_t st = swap ? c->stream : c->copy_stream;                   // kernels
+  PackMeta* meta = (PackMeta*)c->pack_meta;
+  PackMeta* hm = (PackMeta*)c->pack_meta_host;
+  MB_CUDA_TRY(cudaEventRecord(c->pack_ev[0], c->stream));
+  c->pack_timed = true;
+  *dev = *h;
+  const uint64_t n_cig = h->cigar_off[n], n_el = h->seq_off[n];
+  const size_t seq_bytes = h->seq_nibbles ? (size_t)((n_el + 1) / 2) : (size_t)n_el;
+  struct Part { const void** dst; const void* src; size_t bytes; bool bulk; } parts[10] = {
+      {(const void**)&dev->ref_id, h->ref_id, 4 * (size_t)n, false},       {(const void**)&dev->pos, h->pos, 4 * (size_t)n, false},
+      {(const void**)&dev->mapq, h->mapq, (size_t)n, false},               {(const void**)&dev->nm, h->nm, 4 * (size_t)n, false},
+      {(const void**)&dev->l_qseq, h->l_qseq, 4 * (size_t)n, false},       {(const void**)&dev->cigar_off, h->cigar_off, 8 * (size_t)(n + 1), false},
+      {(const void**)&dev->cigar, h->cigar, 4 * (size_t)n_cig, false},     {(const void**)&dev->seq_off, h->seq_off, 8 * (size_t)(n + 1), false},
+      {(const void**)&dev->seq, h->seq, seq_bytes, true},                  {(const void**)&dev->qual, h->qual, (size_t)n_el, true}};
+  int slot = 16;
+  for (auto& p : parts) {
+    void* buf = nullptr;
+    int rc = ctx_reserve(c, slot++, p.bytes + 256, &buf);
+    if (rc) return rc;
+    MB_CUDA_TRY(cudaMemsetAsync((char*)buf + p.bytes, 0, 256, cs));
+    if (!p.bulk && p.bytes) MB_CUDA_TRY(cudaMemcpyAsync(buf, p.src, p.bytes, cudaMemcpyHostToDevice, cs));
+    *p.dst = buf;
+  }
+  // the bulk arrays: behind the small ones on the wire, chunk after chunk on the copy stream
+  const int C = mb_ctx::kChunks;
+  const bool trace = getenv("MB_OVERLAP_TRACE") != nullptr;              // timeline of one call on stderr
+  cudaEvent_t tr[2 * mb_ctx::kChunks + 3];
+  if (trace) { for (auto& e : tr) cudaEventCreate(&e); cudaEventRecord(tr[0], cs); }
+  uint64_t rb[mb_ctx::kChunks + 1];
+  for (int k = 0; k <= C; ++k) rb[k] = k == C ? n : (n * (uint64_t)k / C) & ~(uint64_t)(MB_GROUP - 1);
+  if (trace) cudaEventRecord(tr[1], cs);
+  MB_CUDA_TRY(cudaEventRecord(c->chunk_ev[C], cs));                        // the small arrays are on the device
+  MB_CUDA_TRY(cudaStreamWaitEvent(st, c->chunk_ev[C], 0));
+  for (int k = 0; k < C; ++k) {
+    const uint64_t e0 = h->seq_off[rb[k]], e1 = h->seq_off[rb[k + 1]];
+    if (e1 > e0) {
+      MB_CUDA_TRY(cudaMemcpyAsync((uint8_t*)dev->qual + e0, h->qual + e0, (size_t)(e1 - e0), cudaMemcpyHostToDevice, cs));
+      const uint64_t b0 = h->seq_nibbles ? e0 / 2 : e0, b1 = h->seq_nibbles ? (e1 + 1) / 2 : e1;
+      MB_CUDA_TRY(cudaMemcpyAsync((uint8_t*)dev->seq + b0, h->seq + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, cs));
+    }
+    MB_CUDA_TRY(cudaEventRecord(c->chunk_ev[k], cs));
+    if (trace) cudaEventRecord(tr[2 + k], cs);
+  }
+  // analysis + unit scan on the small arrays (six Phred planes assumed)
+  const uint64_t n_groups = (n + MB_GROUP - 1) / MB_GROUP;
+  const uint32_t n_sblocks = (uint32_t)((n_groups + SCAN_CHUNK - 1) / SCAN_CHUNK);
+  void *src_of = nullptr, *nblk = nullptr, *need = nullptr, *blk_src = nullptr, *blk_dst = nullptr, *g_units = nullptr,
+       *bsum = nullptr;
+  int rc = ctx_reserve(c, 26, 4 * (size_t)n, &src_of);
+  if (!rc) rc = ctx_reserve(c, 27, 2 * (size_t)n, &nblk);
+  if (!rc) rc = ctx_reserve(c, 28, (size_t)n, &need);
+  if (!rc) rc = ctx_reserve(c, 29, 4 * (size_t)std::max<uint32_t>(1, L->n_contigs), &blk_src);
+  if (!rc) rc = ctx_reserve(c, 30, 4 * (size_t)std::max<uint32_t>(1, L->n_contigs), &blk_dst);
+  if (!rc) rc = ctx_reserve(c, 31, 4 * (size_t)n_groups, &g_units);
+  if (!rc) rc = ctx_reserve(c, 32, 8 * (size_t)(n_sblocks + 1), &bsum);
+  if (!rc) rc = pack_alloc(c, true, 33, sizeof(mb_read_hdr) * (size_t)n, (void**)&d->hdr);
+  if (!rc) rc = pack_alloc(c, true, 34, 4 * (size_t)(n + 1), (void**)&d->vec_off);
+  if (!rc) rc = pack_alloc(c, true, 35, 4 * (size_t)n, (void**)&d->cplx);
+  if (rc) return rc;
+  k_pack_meta_init<<<1, 256, 0, st>>>(meta);
+  Plain P;
+  P.n = n;
+  P.ref_id = dev->ref_id; P.pos = dev->pos; P.nm = dev->nm; P.l_qseq = dev->l_qseq; P.mapq = dev->mapq;
+  P.cigar_off = dev->cigar_off; P.seq_off = dev->seq_off; P.cigar = dev->cigar; P.seq = dev->seq; P.qual = dev->qual;
+  P.nib = h->seq_nibbles ? 1u : 0u;
+  P.qual_later = 1;
+  mb_dev_layout dl{};
+  if (mode == 0) { rc = get_dev_layout(c, L, &dl); if (rc) return rc; }
+  const uint32_t grid = (uint32_t)std::min<uint64_t>((n + 255) / 256, (uint64_t)c->sm_count * 8);
+  if (mode == 0) {
+    k_pack_blocks<<<1, 1024, 0, st>>>(P.ref_id, n, L->n_contigs, dl.order, (uint32_t*)blk_src, (uint32_t*)blk_dst);
+    k_pack_analyse<0><<<grid, 256, 0, st>>>(P, L->n_contigs, dl.contig_len, dl.contig_goff, (uint32_t*)blk_src,
+                                            (uint32_t*)blk_dst, (uint4*)d->hdr, d->cplx, (uint32_t*)src_of, (uint16_t*)nblk,
+                                            (uint8_t*)need, meta);
+    c->launches += 2;
+  } else {
+    k_pack_analyse<1><<<grid, 256, 0, st>>>(P, L->n_contigs, nullptr, nullptr, nullptr, nullptr, (uint4*)d->hdr, d->cplx,
+                                            (uint32_t*)src_of, (uint16_t*)nblk, (uint8_t*)need, meta);
+    c->launches += 1;
+  }
+  k_pack_finish<<<1, 32, 0, st>>>(meta, n, mode, P.cigar_off);
+  k_pack_units<<<(uint32_t)std::min<uint64_t>((n_groups + 7) / 8, (uint64_t)c->sm_count * 8), 256, 0, st>>>(
+      (const uint16_t*)nblk, n, n_groups, meta, (uint32_t*)g_units);
+  k_pack_scan1<<<n_sblocks, SCAN_T, 0, st>>>((const uint32_t*)g_units, n_groups, (unsigned long long*)bsum);
+  k_pack_scan2<<<1, SCAN_T, 0, st>>>((unsigned long long*)bsum, n_sblocks, meta);
+  c->launches += 4;
+  MB_CUDA_TRY(cudaMemcpyAsync(hm, meta, sizeof(PackMeta), cudaMemcpyDeviceToHost, st));
+  MB_CUDA_TRY(cudaStreamSynchronize(st));          // the small arrays have landed and are analysed; the bulk is on its way
+  MB_CUDA_TRY(cudaGetLastError());
+  auto drain = [&]() { cudaStreamSynchronize(cs); cudaStreamSynchronize(st); };   // never leave work in flight behind an error
+  if (hm->err != ~0ull) {
+    drain();
+    int status = MB_EINVAL;
+    const char* text = pack_err_text((uint32_t)(hm->err & 0xffu), &status);
+    return mb::fail(status, "read %llu: %s", (unsigned long long)(hm->err >> 8), text);
+  }
+  if (hm->unsorted) {
+    drain();
+    return mb::fail(MB_EUNSORTED, "mb_reads_pack: snps records are not in BAM coordinate order (ref_id, pos); "
+                                  "use mb_pack_reads with sort");
+  }
+  if (hm->n_vec > 0xFFFFFFF0ull) { drain(); return mb::fail(MB_EOVERFLOW, "mb_reads_pack: batch too large for 32-bit unit offsets"); }
+  d->n_reads = n;
+  d->n_vec = hm->n_vec;
+  d->total_bases = hm->total_bases;
+  d->max_ref_span = hm->max_span;
+  d->sorted = mode == 0 ? 1u : 0u;
+  d->row_words = hm->row_words;
+  d->n_long = hm->n_long;
+  d->q_planes = hm->q_planes;           // 6 (assumed)
+  d->n_planes = hm->n_planes;
+  d->max_units = hm->max_units;
+  d->n_cigar_words = hm->n_cig;
+  d->cigar = const_cast<uint32_t*>(dev->cigar);
+  rc = pack_alloc(c, true, 36, (size_t)d->n_vec * 32, (void**)&d->planes);
+  if (!rc) rc = pack_alloc(c, true, 37, 4 * (size_t)d->n_long, (void**)&d->long_idx);
+  if (rc) { drain(); return rc; }
+  k_pack_scan3<<<n_sblocks, SCAN_T, 0, st>>>((const uint32_t*)g_units, n_groups, (const unsigned long long*)bsum, n, meta,
+                                             d->vec_off);
+  c->launches += 1;
+  if (d->n_long) {
+    k_pack_long<<<grid, 256, 0, st>>>((const uint8_t*)need, n, meta, (uint4*)d->hdr, d->long_idx);
+    c->launches += 1;
+  }
+  FillFn fill = mode == 0 ? k_pack_fill<0, 6> : k_pack_fill<1, 6>;
+  for (int k = 0; k < C; ++k) {
+    MB_CUDA_TRY(cudaStreamWaitEvent(st, c->chunk_ev[k], 0));                 // this chunk's seq / qual have landed
+    const uint64_t g_lo = rb[k] / MB_GROUP, g_hi = k == C - 1 ? n_groups : rb[k + 1] / MB_GROUP;
+    if (g_hi <= g_lo) continue;
+    k_pack_qor_flat<<<(uint32_t)c->sm_count * 2, 256, 0, st>>>(P, meta, rb[k], rb[k + 1]);
+    const uint32_t fgrid = (uint32_t)std::min<uint64_t>((g_hi - g_lo + 7) / 8, (uint64_t)c->sm_count * 8);
+    fill<<<fgrid, 256, 0, st>>>(P, (const uint4*)d->hdr, (const uint32_t*)src_of, d->vec_off, n, meta, d->planes, g_lo, g_hi);
+    c->launches += 2;
+    if (trace) cudaEventRecord(tr[2 + C + k], st);
+  }
+  if (trace) {
+    cudaStreamSynchronize(st);
+    cudaStreamSynchronize(cs);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, tr[0], tr[1]);
+    fprintf(stderr, "overlap trace: small arrays landed %.2f ms;", ms);
+    for (int k = 0; k < C; ++k) { cudaEventElapsedTime(&ms, tr[0], tr[2 + k]); fprintf(stderr, " copy%d %.2f", k, ms); }
+    for (int k = 0; k < C; ++k) { cudaEventElapsedTime(&ms, tr[0], tr[2 + C + k]); fprintf(stderr, " fill%d %.2f", k, ms); }
+    fprintf(stderr, "\n");
+    for (auto& e : tr) cudaEventDestroy(e);
+  }
+  MB_CUDA_TRY(cudaMemcpyAsync(hm, meta, sizeof(PackMeta), cudaMemcpyDeviceToHost, st));   // q_or / late errors: read after the caller's sync
+  if (st != c->stream) {                                                   // the context stream continues behind the kernels
+    MB_CUDA_TRY(cudaEventRecord(c->chunk_ev[C], st));
+    MB_CUDA_TRY(cudaStreamWaitEvent(c->stream, c->chunk_ev[C], 0));
+  }
+  MB_CUDA_TRY(cudaEventRecord(c->pack_ev[1], c->stream));
+  MB_CUDA_TRY(cudaGetLastError());
+  d->bytes = sizeof(mb_read_hdr) * n + 4 * (n + 1) + 4 * n + 4 * d->n_cigar_words + (uint64_t)d->n_vec * 32 + 4 * (uint64_t)d->n_long;
+  *done = true;
+  return MB_OK;
+}
+
+int pack_overlapped_verdict(mb_ctx* c, bool* respec) {
+  const PackMeta* hm = (const PackMeta*)c->pack_meta_host;
+  *respec = false;
+  if (hm->err != ~0ull) {
+    int status = MB_EINVAL;
+    const char* text = pack_err_text((uint32_t)(hm->err & 0xffu), &status);
+    return mb::fail(status, "read %llu: %s", (unsigned long long)(hm->err >> 8), text);
+  }
+  if (hm->q_or & 0xC0u) *respec = true;   // Phred > 63 (seven planes) or > 127 (error): the exact path decides
   return MB_OK;
 }
 

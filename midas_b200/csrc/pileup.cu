@@ -1285,23 +1285,43 @@ extern "C" int mb_snps_pileup_plain(mb_ctx* ctx, const mb_plain_reads* plain_hos
   if (!ctx || !plain_host || !L || !f || !counts_host || !stats_host)
     return mb::fail(MB_EINVAL, "mb_snps_pileup_plain: null argument");
   MB_CUDA_TRY(cudaSetDevice(ctx->device));
-  mb_plain_reads dev;
-  int rc = mb::upload_plain(ctx, plain_host, &dev);                     // H2D of the decoded records
-  if (rc) return rc;
-  mb_dev_reads dr;
-  rc = mb::pack_on_device(ctx, &dev, L, 0, /*staged=*/true, &dr);       // k_pack_*: the re-layout, on the GPU
-  if (rc) return rc;
-  void *counts = nullptr, *stats = nullptr;
   const size_t cbytes = sizeof(uint32_t) * 4 * (size_t)L->gpad, sbytes = sizeof(mb_species_stats) * (size_t)L->n_species;
-  rc = mb::ctx_reserve(ctx, 0, cbytes, &counts);
+  void *counts = nullptr, *stats = nullptr;
+  int rc = mb::ctx_reserve(ctx, 0, cbytes, &counts);
   if (!rc) rc = mb::ctx_reserve(ctx, 1, sbytes, &stats);
-  ctx->rng_for = nullptr;
-  if (!rc) rc = mb_snps_pileup_dev(ctx, &dr, L, f, (uint32_t*)counts, (mb_species_stats*)stats);
-  ctx->rng_for = nullptr;
-  if (!rc && cbytes) {
-    cudaError_t e = cudaMemcpyAsync(counts_host, counts, cbytes, cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess && sbytes) e = cudaMemcpyAsync(stats_host, stats, sbytes, cudaMemcpyDeviceToHost, ctx->stream);
-    if (e != cudaSuccess) rc = mb::fail(MB_ECUDA, "mb_snps_pileup_plain: %s", cudaGetErrorString(e));
+  if (rc) return rc;
+  mb_plain_reads dev;
+  mb_dev_reads dr;
+  // large batches: seq / qual cross PCIe in chunks on a second stream while the chunks already there are re-laid
+  bool overlapped = false;
+  rc = mb::pack_from_host_overlapped(ctx, plain_host, L, 0, &dev, &dr, &overlapped);
+  if (rc) return rc;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    if (!overlapped) {
+      if (attempt == 0) {
+        rc = mb::upload_plain(ctx, plain_host, &dev);                   // H2D of the decoded records
+        if (rc) return rc;
+      }
+      rc = mb::pack_on_device(ctx, &dev, L, 0, /*staged=*/true, &dr);   // k_pack_*: the re-layout, on the GPU
+      if (rc) return rc;
+    }
+    ctx->rng_for = nullptr;
+    rc = mb_snps_pileup_dev(ctx, &dr, L, f, (uint32_t*)counts, (mb_species_stats*)stats);
+    ctx->rng_for = nullptr;
+    if (rc) { cudaStreamSynchronize(ctx->copy_stream); return rc; }
+    if (cbytes) {
+      cudaError_t e = cudaMemcpyAsync(counts_host, counts, cbytes, cudaMemcpyDeviceToHost, ctx->stream);
+      if (e == cudaSuccess && sbytes) e = cudaMemcpyAsync(stats_host, stats, sbytes, cudaMemcpyDeviceToHost, ctx->stream);
+      if (e != cudaSuccess) return mb::fail(MB_ECUDA, "mb_snps_pileup_plain: %s", cudaGetErrorString(e));
+    }
+    if (!overlapped) break;
+    // the overlapped pack assumed six Phred planes: its verdict is known once the stream has drained
+    MB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    bool respec = false;
+    rc = mb::pack_overlapped_verdict(ctx, &respec);
+    if (rc) return rc;
+    if (!respec) break;
+    overlapped = false;                                                  // everything is on the device: re-pack exactly
   }
   if (!rc) rc = mb::check_overflow(ctx, "mb_snps_pileup_plain");
   return rc;

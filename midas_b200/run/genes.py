@@ -106,7 +106,7 @@ def pangenome_coverage(args, species, genes, ctx=None):
 def count_mapped_bp(args, species, genes, ctx=None):
     """reference genes.py:171-203: per gene aligned/mapped reads and depth, per species summaries."""
     bam_path = "/".join([args["outdir"], "genes/temp/pangenomes.bam"])
-    names, lens, reads = lib.read_bam(bam_path, int(args.get("threads", 0) or 0), pinned=True)
+    names, lens, reads = lib.read_bam(bam_path, int(args.get("threads", 0) or 0))
     gene_ids = list(genes.keys())
     gindex = {g: k for k, g in enumerate(gene_ids)}
     missing = [n for n in set(names[t] for t in np.unique(reads.ref_id))

@@ -120,8 +120,9 @@ def build_refset(species, contigs, bam_names=None):
     return ref
 
 
-def load_alignments(bampath, species, contigs, threads=0, pinned=True):
-    """Decode the BAM (native reader, page-locked arrays, seq left as in the file) and number its records
+def load_alignments(bampath, species, contigs, threads=0, pinned=False):
+    """Decode the BAM (native reader, seq left as in the file; page-locked arrays only on request: pinning ~0.3 GB per
+    million reads costs more than it saves for a sample that crosses PCIe once) and number its records
     on a RefSet in tid order. Records on references that are not contigs of a selected species are never
     fetched by the reference (snps.py:190-199) and are dropped. Returns (RefSet, PlainReads)."""
     names, lens, reads = lib.read_bam(bampath, threads, pinned=pinned)

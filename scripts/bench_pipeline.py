@@ -2,8 +2,9 @@
 """Stage times of the whole `run_midas.py snps --pileup` stage, from a coordinate-sorted BAM on disk to
 <species>.snps.gz + summary.txt, on a C2-shaped workload scaled down (the BAM writer used to make the
 fixture is pure Python). The stage replaces reference midas/run/snps.py:299-302 (index_bam, pysam_pileup,
-snps_summary); its steps here are: native BAM decode (mb_bam_open), host re-layout (mb_pack_reads), one
-mb_snps_pileup call (H2D + kernels + D2H), native row formatting + threaded multi-member gzip.
+snps_summary); its steps here are: native BAM decode into page-locked arrays (mb_bam_open), one
+mb_snps_pileup_plain call (H2D of the decoded records + re-layout on the GPU + pileup + D2H), native row
+formatting + threaded multi-member gzip.
 
   python scripts/bench_pipeline.py [--scale 0.1] [--threads 16]
 
@@ -76,7 +77,7 @@ def main():
                                       f"BAM {bam_bytes / 1e6:.0f} MB -> snps.gz {gz / 1e6:.0f} MB",
                           "host_threads": a.threads, "seconds": stages,
                           "gbases_per_s_bam_to_files": best["n_bases"] / best["total"] / 1e9,
-                          "gbases_per_s_gpu_call": best["n_bases"] / best["gpu_h2d_kernels_d2h"] / 1e9}))
+                          "gbases_per_s_gpu_call": best["n_bases"] / best["gpu_h2d_pack_kernels_d2h"] / 1e9}))
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
 

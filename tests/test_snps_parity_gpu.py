@@ -135,3 +135,43 @@ def test_full_size_c2(ctx):
     assert np.array_equal(got, exp_counts.astype(np.uint32))
     for k, name in enumerate(lib.STATS_DTYPE.names):
         assert int(stats[name][0]) == int(exp_stats[0, k]), name
+
+
+def test_overlapped_host_path(ctx, monkeypatch):
+    """Page-locked records, batch above the overlap threshold: seq / qual cross PCIe in chunks on a second stream
+    while earlier chunks are re-laid (six Phred planes assumed). Same counts as the oracle; a batch that needs seven
+    planes is re-packed exactly; missing qualities in a late chunk are still reported."""
+    import gen
+    monkeypatch.setenv("MB_OVERLAP_MIN_READS", "2000")
+    ref, reads = synth.synth_snps(seed=31, n_species=1, contigs_per_species=3, contig_len=20_000, n_reads=60_000,
+                                  len_jitter=0.2)
+    lay = lib.Layout.of(ref)
+    exp_counts, exp_stats = oracle.snps_pileup(reads, ref, Filters())
+    for r in (lib.pinned_reads(reads), lib.pinned_reads(reads.nibble_packed())):
+        launches = ctx.launch_count
+        counts, stats = ctx.snps_pileup_plain(r, lay, Filters())
+        assert np.array_equal(lay.unpad(counts).astype(np.uint64), exp_counts)
+        for k, name in enumerate(lib.STATS_DTYPE.names):
+            assert np.array_equal(stats[name], exp_stats[:, k]), name
+        assert ctx.launch_count - launches >= 20          # the chunked path ran (one qor + fill pair per chunk)
+    # Phred 64 in the last read: the speculation fails, the exact re-pack must give the seven-plane answer
+    hi = lib.pinned_reads(reads)
+    hi.qual[-5:] = 70
+    e2, s2 = oracle.snps_pileup(hi, ref, Filters(baseq=65))
+    c2, st2 = ctx.snps_pileup_plain(hi, lay, Filters(baseq=65))
+    assert np.array_equal(lay.unpad(c2).astype(np.uint64), e2) and int(st2["mapped_reads"][0]) == int(s2[0, 4])
+    # qualities missing in a read of the last chunk
+    bad = lib.pinned_reads(reads)
+    bad.qual[int(bad.seq_off[bad.n_reads - 3])] = 0xFF
+    with pytest.raises(lib.MidasB200Error) as e:
+        ctx.snps_pileup_plain(bad, lay, Filters())
+    assert e.value.status == -1
+    # random CIGARs (non-simple reads, long reads) through the chunked path
+    rng = np.random.default_rng(3)
+    ref2 = gen.make_ref(rng, 1, 4, 3000, 9000)
+    rr = gen.random_reads(41, ref2, 5000, max_len=260)
+    rr.qual[rr.qual > 63] = 63
+    lay2 = lib.Layout.of(ref2)
+    e3, s3 = oracle.snps_pileup(rr, ref2, Filters(mapid=0.0, aln_cov=0.0, readq=0, mapq=0, baseq=10))
+    c3, st3 = ctx.snps_pileup_plain(lib.pinned_reads(rr), lay2, Filters(mapid=0.0, aln_cov=0.0, readq=0, mapq=0, baseq=10))
+    assert np.array_equal(lay2.unpad(c3).astype(np.uint64), e3)

@@ -359,6 +359,26 @@ uint32_t mb_bam_ref_len(const mb_bam* b, uint32_t i);
 const mb_plain_reads* mb_bam_reads(const mb_bam* b);
 const uint16_t* mb_bam_flags(const mb_bam* b);   /* [n_reads] SAM flags (informational) */
 
+/* Streaming form of the ingest: the host only inflates the BGZF blocks (n_threads host threads), reads the header
+ * and finds where the records start; the inflated record stream goes to the GPU as it is and the device parses it
+ * (refID, pos, mapq, CIGAR, the NM tag, where seq and qual lie), re-lays it and counts - no host-side record decode.
+ * tid_map[i] = index into the layout's contigs of BAM reference i, or -1 to drop its records (reference
+ * midas/run/snps.py:190-199 only ever fetches the contigs of the selected species). The records must be in BAM
+ * coordinate order and the kept references must keep their relative order in the layout's numbering
+ * (MB_EUNSORTED otherwise: use mb_bam_open + mb_pack_reads with sort). */
+typedef struct mb_bam_stream mb_bam_stream;
+int mb_bam_stream_open(const char* path, int n_threads, mb_bam_stream** out);
+void mb_bam_stream_close(mb_bam_stream* s);
+uint32_t mb_bam_stream_n_ref(const mb_bam_stream* s);
+const char* mb_bam_stream_ref_name(const mb_bam_stream* s, uint32_t i);
+uint32_t mb_bam_stream_ref_len(const mb_bam_stream* s, uint32_t i);
+uint64_t mb_bam_stream_bytes(const mb_bam_stream* s);   /* inflated bytes (what crosses PCIe) */
+/* <- midas/run/snps.py:186-199 + :141-216 from the BAM bytes: H2D of the inflated stream, k_bam_* (parse), k_pack_*
+ * (re-layout), pileup, D2H. n_reads_out / n_bases_out (may be NULL): records kept and their bases. */
+int mb_snps_pileup_bam(mb_ctx* ctx, const mb_bam_stream* s, const int32_t* tid_map, const mb_layout* L,
+                       const mb_filters* f, uint32_t* counts_host, mb_species_stats* stats_host,
+                       uint64_t* n_reads_out, uint64_t* n_bases_out);
+
 /* ------------------------------------------------------------- text output */
 /* Rows of <species>.snps.gz for n_rows consecutive positions of one contig, starting at 0-based
  * position first_pos0 (reference midas/run/snps.py:201-210):

@@ -133,6 +133,9 @@ int upload_plain(mb_ctx* ctx, const mb_plain_reads* host, mb_plain_reads* dev);
 int pack_from_host_overlapped(mb_ctx* ctx, const mb_plain_reads* host, const mb_layout* L, int mode, mb_plain_reads* dev,
                               mb_dev_reads* d, bool* done);
 int pack_overlapped_verdict(mb_ctx* ctx, bool* respec);   // after a stream sync: errors / re-pack needed
+// streaming BAM (host_bam.cpp): the inflated stream and the start of every kept record
+const uint8_t* bam_stream_data(const mb_bam_stream* S, size_t* total);
+int bam_stream_walk(const mb_bam_stream* S, const int32_t* tid_map, std::vector<uint64_t>* rec_off, uint64_t* n_cig_total);
 void free_dev_reads_arrays(mb_dev_reads* d);
 int check_overflow(mb_ctx* ctx, const char* who);   // after a stream sync: MB_EOVERFLOW if the flag is set (and clears it)
 }  // namespace mb

@@ -124,14 +124,19 @@ int32_t find_nm(const uint8_t* p, const uint8_t* end) {
 
 }  // namespace
 
-extern "C" int mb_bam_open(const char* path, int n_threads, int flags, mb_bam** out) {
-  if (!path || !out) return mb::fail(MB_EINVAL, "mb_bam_open: null argument");
-  const bool pin = (flags & MB_BAM_PINNED) != 0, nib = !(flags & MB_BAM_SEQ_BYTES);
-  if (n_threads <= 0) n_threads = (int)std::min<unsigned>(32, std::max(1u, std::thread::hardware_concurrency()));
+// The inflated byte stream of a BAM file and what its header says (steps 1-3 of every reader below).
+struct BamData {
+  RawBuf<uint8_t> data;
+  size_t total = 0, first_record = 0;
+  std::vector<std::string> ref_name;
+  std::vector<uint32_t> ref_len;
+};
+
+static int inflate_bam(const char* path, int n_threads, BamData* B, const char* who) {
   const bool timing = getenv("MB_BAM_TIMING") != nullptr;
   auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   double t_phase = now();
-  auto phase = [&](const char* name) { if (timing) { const double t = now(); fprintf(stderr, "mb_bam_open: %-8s %8.1f ms\n", name, t - t_phase); t_phase = t; } };
+  auto phase = [&](const char* name) { if (timing) { const double t = now(); fprintf(stderr, "%s: %-8s %8.1f ms\n", who, name, t - t_phase); t_phase = t; } };
   // the file is mapped, not copied: the inflate threads read the compressed blocks straight from the page cache
   struct RawFile {
     const uint8_t* p = nullptr;
@@ -144,12 +149,12 @@ extern "C" int mb_bam_open(const char* path, int n_threads, int flags, mb_bam** 
   } raw;
   {
     const int fd = open(path, O_RDONLY);
-    if (fd < 0) return mb::fail(MB_EINVAL, "mb_bam_open: cannot open %s", path);
+    if (fd < 0) return mb::fail(MB_EINVAL, "%s: cannot open %s", who, path);
     struct stat st;
-    if (fstat(fd, &st) != 0) { close(fd); return mb::fail(MB_EINVAL, "mb_bam_open: cannot stat %s", path); }
+    if (fstat(fd, &st) != 0) { close(fd); return mb::fail(MB_EINVAL, "%s: cannot stat %s", who, path); }
     if (st.st_size > 0) {
       void* m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
-      if (m == MAP_FAILED) { close(fd); return mb::fail(MB_EINVAL, "mb_bam_open: cannot map %s", path); }
+      if (m == MAP_FAILED) { close(fd); return mb::fail(MB_EINVAL, "%s: cannot map %s", who, path); }
       madvise(m, (size_t)st.st_size, MADV_WILLNEED);
       raw.p = (const uint8_t*)m;
       raw.n = (size_t)st.st_size;
@@ -164,7 +169,7 @@ extern "C" int mb_bam_open(const char* path, int n_threads, int flags, mb_bam** 
   while (off + 18 <= raw.size()) {
     const uint8_t* b = raw.data() + off;
     if (b[0] != 0x1f || b[1] != 0x8b || b[2] != 8 || !(b[3] & 4))
-      return mb::fail(MB_EMALFORMED, "mb_bam_open: %s: not a BGZF block at offset %zu", path, off);
+      return mb::fail(MB_EMALFORMED, "%s: %s: not a BGZF block at offset %zu", who, path, off);
     const uint16_t xlen = rd16(b + 10);
     size_t x = off + 12, xend = x + xlen, bsize = 0;
     while (x + 4 <= xend && xend <= raw.size()) {
@@ -173,24 +178,24 @@ extern "C" int mb_bam_open(const char* path, int n_threads, int flags, mb_bam** 
       x += 4 + slen;
     }
     if (!bsize || off + bsize > raw.size() || bsize < (size_t)xlen + 20)
-      return mb::fail(MB_EMALFORMED, "mb_bam_open: %s: bad BGZF block size at offset %zu", path, off);
+      return mb::fail(MB_EMALFORMED, "%s: %s: bad BGZF block size at offset %zu", who, path, off);
     Blk k;
     k.off = off;
     k.cbeg = xend;
     k.clen = off + bsize - 8 - xend;
     k.isize = rd32(raw.data() + off + bsize - 4);
     if (k.isize > 65536u)
-      return mb::fail(MB_EMALFORMED, "mb_bam_open: %s: BGZF block at offset %zu claims %u inflated bytes (> 64 KiB)", path, off, k.isize);
+      return mb::fail(MB_EMALFORMED, "%s: %s: BGZF block at offset %zu claims %u inflated bytes (> 64 KiB)", who, path, off, k.isize);
     k.dst = total;
     total += k.isize;
     blks.push_back(k);
     off += bsize;
   }
-  if (off != raw.size()) return mb::fail(MB_EMALFORMED, "mb_bam_open: %s: trailing bytes after the last BGZF block", path);
+  if (off != raw.size()) return mb::fail(MB_EMALFORMED, "%s: %s: trailing bytes after the last BGZF block", who, path);
   phase("blocks");
   // 2. inflate in parallel
-  RawBuf<uint8_t> data;
-  if (!data.resize(total + 8)) return mb::fail(MB_ENOMEM, "mb_bam_open: out of memory");
+  RawBuf<uint8_t>& data = B->data;
+  if (!data.resize(total + 64)) return mb::fail(MB_ENOMEM, "%s: out of memory", who);
   std::atomic<int> bad_flag{0};
   std::atomic<int>* bad = &bad_flag;
   pfor(blks.size(), n_threads, [&](size_t lo, size_t hi) {
@@ -211,26 +216,48 @@ extern "C" int mb_bam_open(const char* path, int n_threads, int flags, mb_bam** 
       if (!ok) { bad->store(1); return; }
     }
   });
-  if (bad->load()) return mb::fail(MB_EMALFORMED, "mb_bam_open: %s: BGZF inflate / CRC failure", path);
+  if (bad->load()) return mb::fail(MB_EMALFORMED, "%s: %s: BGZF inflate / CRC failure", who, path);
   raw.release();
   phase("inflate");
   // 3. header
   const uint8_t* d = data.data();
-  memset(data.data() + total, 0, 8);
-  if (total < 12 || memcmp(d, "BAM\1", 4) != 0) return mb::fail(MB_EMALFORMED, "mb_bam_open: %s: not a BAM file", path);
+  memset(data.data() + total, 0, 64);
+  if (total < 12 || memcmp(d, "BAM\1", 4) != 0) return mb::fail(MB_EMALFORMED, "%s: %s: not a BAM file", who, path);
   size_t o = 8 + (size_t)rd32(d + 4);
-  if (o + 4 > total) return mb::fail(MB_EMALFORMED, "mb_bam_open: %s: truncated header", path);
+  if (o + 4 > total) return mb::fail(MB_EMALFORMED, "%s: %s: truncated header", who, path);
   const uint32_t n_ref = rd32(d + o);
   o += 4;
-  mb_bam* B = new mb_bam();
   for (uint32_t i = 0; i < n_ref; ++i) {
-    if (o + 4 > total) { delete B; return mb::fail(MB_EMALFORMED, "mb_bam_open: %s: truncated reference list", path); }
+    if (o + 4 > total) return mb::fail(MB_EMALFORMED, "%s: %s: truncated reference list", who, path);
     const uint32_t ln = rd32(d + o);
-    if (o + 8 + ln > total || ln == 0) { delete B; return mb::fail(MB_EMALFORMED, "mb_bam_open: %s: truncated reference list", path); }
+    if (o + 8 + ln > total || ln == 0) return mb::fail(MB_EMALFORMED, "%s: %s: truncated reference list", who, path);
     B->ref_name.emplace_back((const char*)d + o + 4, ln - 1);
     B->ref_len.push_back(rd32(d + o + 4 + ln));
     o += 8 + ln;
   }
+  B->total = total;
+  B->first_record = o;
+  return MB_OK;
+}
+
+extern "C" int mb_bam_open(const char* path, int n_threads, int flags, mb_bam** out) {
+  if (!path || !out) return mb::fail(MB_EINVAL, "mb_bam_open: null argument");
+  const bool pin = (flags & MB_BAM_PINNED) != 0, nib = !(flags & MB_BAM_SEQ_BYTES);
+  if (n_threads <= 0) n_threads = (int)std::min<unsigned>(32, std::max(1u, std::thread::hardware_concurrency()));
+  const bool timing = getenv("MB_BAM_TIMING") != nullptr;
+  auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  double t_phase = now();
+  auto phase = [&](const char* name) { if (timing) { const double t = now(); fprintf(stderr, "mb_bam_open: %-8s %8.1f ms\n", name, t - t_phase); t_phase = t; } };
+  BamData bd;
+  { int rc = inflate_bam(path, n_threads, &bd, "mb_bam_open"); if (rc) return rc; }
+  t_phase = now();
+  const uint8_t* d = bd.data.data();
+  const size_t total = bd.total;
+  size_t o = bd.first_record;
+  const uint32_t n_ref = (uint32_t)bd.ref_name.size();
+  mb_bam* B = new mb_bam();
+  B->ref_name = bd.ref_name;
+  B->ref_len = bd.ref_len;
   // 4. record table (sequential: 4 bytes per record decide the next offset)
   std::vector<size_t> rec;
   std::vector<uint64_t> coff(1, 0), soff(1, 0);
@@ -314,3 +341,64 @@ extern "C" const char* mb_bam_ref_name(const mb_bam* B, uint32_t i) { return B &
 extern "C" uint32_t mb_bam_ref_len(const mb_bam* B, uint32_t i) { return B && i < B->ref_len.size() ? B->ref_len[i] : 0; }
 extern "C" const mb_plain_reads* mb_bam_reads(const mb_bam* B) { return B ? &B->pub : nullptr; }
 extern "C" const uint16_t* mb_bam_flags(const mb_bam* B) { return B ? B->flag.data() : nullptr; }
+
+// ------------------------------------------------------------------------------------------- streaming form
+// The inflated record stream goes to the GPU as it is; the device parses the records (csrc/pack.cu k_bam_*). The
+// host only inflates, reads the header and walks the 4-byte block_size chain to find where the records start.
+struct mb_bam_stream {
+  BamData bd;
+};
+
+extern "C" int mb_bam_stream_open(const char* path, int n_threads, mb_bam_stream** out) {
+  if (!path || !out) return mb::fail(MB_EINVAL, "mb_bam_stream_open: null argument");
+  if (n_threads <= 0) n_threads = (int)std::min<unsigned>(32, std::max(1u, std::thread::hardware_concurrency()));
+  mb_bam_stream* S = new mb_bam_stream();
+  const int rc = inflate_bam(path, n_threads, &S->bd, "mb_bam_stream_open");
+  if (rc) { delete S; return rc; }
+  *out = S;
+  return MB_OK;
+}
+extern "C" void mb_bam_stream_close(mb_bam_stream* S) { delete S; }
+extern "C" uint32_t mb_bam_stream_n_ref(const mb_bam_stream* S) { return S ? (uint32_t)S->bd.ref_name.size() : 0; }
+extern "C" const char* mb_bam_stream_ref_name(const mb_bam_stream* S, uint32_t i) {
+  return S && i < S->bd.ref_name.size() ? S->bd.ref_name[i].c_str() : "";
+}
+extern "C" uint32_t mb_bam_stream_ref_len(const mb_bam_stream* S, uint32_t i) {
+  return S && i < S->bd.ref_len.size() ? S->bd.ref_len[i] : 0;
+}
+extern "C" uint64_t mb_bam_stream_bytes(const mb_bam_stream* S) { return S ? (uint64_t)S->bd.total : 0; }
+
+namespace mb {
+const uint8_t* bam_stream_data(const mb_bam_stream* S, size_t* total) {
+  *total = S->bd.total;
+  return S->bd.data.data();
+}
+
+// Offsets (of the refID field, i.e. 4 bytes behind block_size) of the records on references that tid_map keeps
+// (tid_map[refID] >= 0; records with refID < 0 - unplaced - are dropped like in mb_bam_open), in file order.
+int bam_stream_walk(const mb_bam_stream* S, const int32_t* tid_map, std::vector<uint64_t>* rec_off, uint64_t* n_cig_total) {
+  const uint8_t* d = S->bd.data.data();
+  const size_t total = S->bd.total;
+  const uint32_t n_ref = (uint32_t)S->bd.ref_name.size();
+  size_t o = S->bd.first_record;
+  uint64_t ncig = 0;
+  rec_off->clear();
+  rec_off->reserve((total - o) / 256 + 16);
+  while (o + 4 <= total) {
+    const uint32_t bs = rd32(d + o);
+    if (bs < 32 || o + 4 + bs > total) return mb::fail(MB_EMALFORMED, "mb_bam_stream: truncated record at %zu", o);
+    const uint8_t* r = d + o + 4;
+    const int32_t rid = (int32_t)rd32(r);
+    const uint32_t l_name = r[8], n_cig = rd16(r + 12), l_seq = rd32(r + 16);
+    if (32 + (size_t)l_name + 4 * (size_t)n_cig + (l_seq + 1) / 2 + (size_t)l_seq > bs)
+      return mb::fail(MB_EMALFORMED, "mb_bam_stream: record fields exceed block_size at %zu", o);
+    if (rid >= 0) {
+      if ((uint32_t)rid >= n_ref) return mb::fail(MB_EMALFORMED, "mb_bam_stream: refID %d out of range", rid);
+      if (tid_map[rid] >= 0) { rec_off->push_back((uint64_t)(o + 4)); ncig += n_cig; }
+    }
+    o += 4 + bs;
+  }
+  *n_cig_total = ncig;
+  return MB_OK;
+}
+}  // namespace mb

@@ -97,7 +97,7 @@ struct mb_ctx {
   bool ftab_valid;
   std::unordered_map<uint64_t, mb_dev_layout> layouts;
   // staging for the host-buffer convenience calls
-  static constexpr int kStage = 40;
+  static constexpr int kStage = 48;
   void* stage[kStage];
   size_t stage_cap[kStage];
   // device packer (pack.cu)
@@ -124,7 +124,8 @@ int ctx_reserve(mb_ctx* ctx, int slot, size_t bytes, void** out);
 int get_dev_layout(mb_ctx* ctx, const mb_layout* L, mb_dev_layout* out);
 int get_filter_tables(mb_ctx* ctx, const mb_filters* f, const int32_t** t_pid, const int32_t** t_cov);
 // device packer: plain arrays already on the device -> packed batch `d`; staged: into context staging buffers
-int pack_on_device(mb_ctx* ctx, const mb_plain_reads* dev, const mb_layout* L, int mode, bool staged, mb_dev_reads* d);
+int pack_on_device(mb_ctx* ctx, const mb_plain_reads* dev, const mb_layout* L, int mode, bool staged, mb_dev_reads* d,
+                   const uint64_t* qual_off_dev = nullptr);   // qual_off_dev: qualities not at seq_off (BAM stream)
 // copy the plain arrays of `host` into context staging buffers (slots from `slot0`), `dev` gets the device pointers
 int upload_plain(mb_ctx* ctx, const mb_plain_reads* host, mb_plain_reads* dev);
 // host records -> packed batch in context staging buffers with the transfer of seq / qual overlapped with the
@@ -135,7 +136,8 @@ int pack_from_host_overlapped(mb_ctx* ctx, const mb_plain_reads* host, const mb_
 int pack_overlapped_verdict(mb_ctx* ctx, bool* respec);   // after a stream sync: errors / re-pack needed
 // streaming BAM (host_bam.cpp): the inflated stream and the start of every kept record
 const uint8_t* bam_stream_data(const mb_bam_stream* S, size_t* total);
-int bam_stream_walk(const mb_bam_stream* S, const int32_t* tid_map, std::vector<uint64_t>* rec_off, uint64_t* n_cig_total);
+int bam_stream_walk(const mb_bam_stream* S, const int32_t* tid_map, std::vector<uint64_t>* rec_off,
+                    std::vector<uint64_t>* cigar_off);
 void free_dev_reads_arrays(mb_dev_reads* d);
 int check_overflow(mb_ctx* ctx, const char* who);   // after a stream sync: MB_EOVERFLOW if the flag is set (and clears it)
 }  // namespace mb

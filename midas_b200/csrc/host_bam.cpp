@@ -376,14 +376,17 @@ const uint8_t* bam_stream_data(const mb_bam_stream* S, size_t* total) {
 
 // Offsets (of the refID field, i.e. 4 bytes behind block_size) of the records on references that tid_map keeps
 // (tid_map[refID] >= 0; records with refID < 0 - unplaced - are dropped like in mb_bam_open), in file order.
-int bam_stream_walk(const mb_bam_stream* S, const int32_t* tid_map, std::vector<uint64_t>* rec_off, uint64_t* n_cig_total) {
+int bam_stream_walk(const mb_bam_stream* S, const int32_t* tid_map, std::vector<uint64_t>* rec_off,
+                    std::vector<uint64_t>* cigar_off) {
   const uint8_t* d = S->bd.data.data();
   const size_t total = S->bd.total;
   const uint32_t n_ref = (uint32_t)S->bd.ref_name.size();
   size_t o = S->bd.first_record;
   uint64_t ncig = 0;
   rec_off->clear();
+  cigar_off->clear();
   rec_off->reserve((total - o) / 256 + 16);
+  cigar_off->reserve((total - o) / 256 + 17);
   while (o + 4 <= total) {
     const uint32_t bs = rd32(d + o);
     if (bs < 32 || o + 4 + bs > total) return mb::fail(MB_EMALFORMED, "mb_bam_stream: truncated record at %zu", o);
@@ -394,11 +397,11 @@ int bam_stream_walk(const mb_bam_stream* S, const int32_t* tid_map, std::vector<
       return mb::fail(MB_EMALFORMED, "mb_bam_stream: record fields exceed block_size at %zu", o);
     if (rid >= 0) {
       if ((uint32_t)rid >= n_ref) return mb::fail(MB_EMALFORMED, "mb_bam_stream: refID %d out of range", rid);
-      if (tid_map[rid] >= 0) { rec_off->push_back((uint64_t)(o + 4)); ncig += n_cig; }
+      if (tid_map[rid] >= 0) { rec_off->push_back((uint64_t)(o + 4)); cigar_off->push_back(ncig); ncig += n_cig; }
     }
     o += 4 + bs;
   }
-  *n_cig_total = ncig;
+  cigar_off->push_back(ncig);
   return MB_OK;
 }
 }  // namespace mb

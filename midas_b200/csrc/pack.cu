@@ -18,8 +18,12 @@
 //   k_pack_long      MB_RF_LONG flags + their index list
 //   k_pack_fill      one warp per read, one lane per base: every plane word of a 32-base block is one
 //                    __ballot_sync (sequence low / high bit, candidate, Phred bits), zero padding included
+#include <chrono>
 #include <cstdio>
 #include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
 
 #include "common.h"
 
@@ -44,6 +48,7 @@ struct Plain {  // device view of mb_plain_reads
   const int32_t *ref_id, *pos, *nm, *l_qseq;
   const uint8_t* mapq;
   const uint64_t *cigar_off, *seq_off;
+  const uint64_t* qual_off;   // where a read's qualities start in qual[] (= seq_off, except for records parsed out of a BAM stream)
   const uint32_t* cigar;
   const uint8_t *seq, *qual;
   uint32_t nib;
@@ -130,7 +135,7 @@ __global__ void __launch_bounds__(256) k_pack_analyse(const Plain in, const uint
     if (in.nib && (so & 1)) { report(meta, i, PE_SEQALIGN); continue; }
     const int32_t nm_raw = in.nm[i];
     if (nm_raw < 0) { report(meta, i, PE_NM); continue; }
-    if (!in.qual_later && in.qual[so] == 0xFF) { report(meta, i, PE_NOQUAL); continue; }
+    if (!in.qual_later && in.qual[in.qual_off[i]] == 0xFF) { report(meta, i, PE_NOQUAL); continue; }
     const uint64_t co = in.cigar_off[i];
     const int64_t n_cig = (int64_t)(in.cigar_off[i + 1] - co);
     if (n_cig > 65535) { report(meta, i, PE_NCIG); continue; }
@@ -268,7 +273,7 @@ __global__ void __launch_bounds__(256) k_pack_qor(const Plain in, PackMeta* meta
   for (uint64_t i = wg; i < in.n; i += nw) {
     const int64_t lq = in.l_qseq[i];
     if (lq <= 0 || lq > 65535) continue;
-    const uintptr_t a0 = (uintptr_t)(in.qual + in.seq_off[i]), a1 = a0 + (uintptr_t)lq;
+    const uintptr_t a0 = (uintptr_t)(in.qual + in.qual_off[i]), a1 = a0 + (uintptr_t)lq;
     const uintptr_t w0 = a0 & ~(uintptr_t)3, w1 = (a1 + 3) & ~(uintptr_t)3;
     for (uintptr_t w = w0 + 4 * (uintptr_t)lane; w < w1; w += 128) {
       uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(w));
@@ -460,11 +465,12 @@ __global__ void __launch_bounds__(256) k_pack_fill(const Plain in, const uint4* 
     // my read's metadata (lane l <-> read g0 + l)
     const uint64_t jm = g0 + lane;
     uint4 hm = make_uint4(0, 0, 0, 0);
-    uint64_t so_m = 0, co_m = 0;
+    uint64_t so_m = 0, co_m = 0, qo_m = 0;
     if (jm < n) {
       hm = __ldg(&hdr[jm]);
       const uint64_t im = src_of[jm];
       so_m = in.seq_off[im];
+      qo_m = in.qual_off[im];
       co_m = in.cigar_off[im];
     }
     for (uint32_t rr = 0; rr < MB_GROUP; ++rr) {
@@ -477,12 +483,13 @@ __global__ void __launch_bounds__(256) k_pack_fill(const Plain in, const uint4* 
       const uint32_t hy = __shfl_sync(0xffffffffu, hm.y, rr), hz = __shfl_sync(0xffffffffu, hm.z, rr);
       const uint32_t hw = __shfl_sync(0xffffffffu, hm.w, rr);
       const uint64_t so = __shfl_sync(0xffffffffu, so_m, rr), co = __shfl_sync(0xffffffffu, co_m, rr);
+      const uint64_t qo = __shfl_sync(0xffffffffu, qo_m, rr);
       const uint32_t lq = hy & 0xffffu, qstart = hz & 0xffffu, span = hw & 0xffffu, fl = hw >> 24;
       const uint32_t n_blk = (lq + MB_BLOCK - 1) / MB_BLOCK;
       // my base of every block: quality byte at qb[32 b], sequence nibble in byte sb[16 b] (seq_off is even with nibble
       // packing, so the nibble within the byte depends on the lane alone)
-      if (in.qual_later && lane == 0 && in.qual[so] == 0xFF) report(meta, src_of[g0 + rr], PE_NOQUAL);
-      const uint8_t* __restrict__ qb = in.qual + so + lane;
+      if (in.qual_later && lane == 0 && in.qual[qo] == 0xFF) report(meta, src_of[g0 + rr], PE_NOQUAL);
+      const uint8_t* __restrict__ qb = in.qual + qo + lane;
       const uint8_t* __restrict__ sb = in.nib ? in.seq + ((so + lane) >> 1) : in.seq + so + lane;
       const uint32_t sb_step = in.nib ? 16u : 32u, nib_shift = (in.nib && !(lane & 1u)) ? 4u : 0u;
       const bool simple = (fl & MB_RF_SIMPLE) != 0;
@@ -616,7 +623,8 @@ int upload_plain(mb_ctx* c, const mb_plain_reads* h, mb_plain_reads* d) {
   return MB_OK;
 }
 
-int pack_on_device(mb_ctx* c, const mb_plain_reads* in, const mb_layout* L, int mode, bool staged, mb_dev_reads* d) {
+int pack_on_device(mb_ctx* c, const mb_plain_reads* in, const mb_layout* L, int mode, bool staged, mb_dev_reads* d,
+                   const uint64_t* qual_off_dev) {
   memset(d, 0, sizeof(*d));
   d->owned = !staged;
   const uint64_t n = in->n_reads;
@@ -649,6 +657,7 @@ int pack_on_device(mb_ctx* c, const mb_plain_reads* in, const mb_layout* L, int 
   P.cigar_off = in->cigar_off; P.seq_off = in->seq_off; P.cigar = in->cigar; P.seq = in->seq; P.qual = in->qual;
   P.nib = in->seq_nibbles ? 1u : 0u;
   P.qual_later = 0;
+  P.qual_off = qual_off_dev ? qual_off_dev : P.seq_off;
   mb_dev_layout dl{};
   if (mode == 0) { rc = get_dev_layout(c, L, &dl); if (rc) return rc; }
   const uint32_t grid = (uint32_t)std::min<uint64_t>((n + 255) / 256, (uint64_t)c->sm_count * 8);
@@ -668,7 +677,7 @@ int pack_on_device(mb_ctx* c, const mb_plain_reads* in, const mb_layout* L, int 
   }
   for (int pass = 0; pass < 2; ++pass) {
     if (n) {
-      if (pass == 0) {
+      if (pass == 0 && !qual_off_dev) {
         k_pack_qor_flat<<<(uint32_t)c->sm_count * 8, 256, 0, st>>>(P, meta, 0, n);
       } else {   // Phred > 63 somewhere (or garbage in padding): the exact per-record pass decides
         MB_CUDA_TRY(cudaMemsetAsync(&meta->q_or, 0, sizeof(uint32_t), st));
@@ -842,6 +851,7 @@ int pack_from_host_overlapped(mb_ctx* c, const mb_plain_reads* h, const mb_layou
   P.cigar_off = dev->cigar_off; P.seq_off = dev->seq_off; P.cigar = dev->cigar; P.seq = dev->seq; P.qual = dev->qual;
   P.nib = h->seq_nibbles ? 1u : 0u;
   P.qual_later = 1;
+  P.qual_off = P.seq_off;
   mb_dev_layout dl{};
   if (mode == 0) { rc = get_dev_layout(c, L, &dl); if (rc) return rc; }
   const uint32_t grid = (uint32_t)std::min<uint64_t>((n + 255) / 256, (uint64_t)c->sm_count * 8);
@@ -968,6 +978,200 @@ extern "C" int mb_reads_pack(mb_ctx* c, const mb_plain_reads* plain_host, const 
   int rc = mb::upload_plain(c, plain_host, &dev);
   if (rc) return rc;
   return mb_reads_pack_dev(c, &dev, L, mode, out);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// BAM record stream on the device: the inflated bytes as they lie in the file; one thread parses one record
+// (SAM/BAM specification v1 section 4.2: refID, pos, l_read_name, mapq, bin, n_cigar_op, flag, l_seq, next_refID,
+// next_pos, tlen, read_name, cigar, seq, qual, aux). Nothing is copied except the CIGAR words (to an aligned
+// array): seq and qual stay in the stream and the packer reads them where they are.
+namespace {
+
+__device__ __forceinline__ uint32_t ld_u16(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8); }
+__device__ __forceinline__ uint32_t ld_u32(const uint8_t* p) {
+  return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+}
+
+// integer value of the NM aux tag, or -1 when absent / malformed (as host_bam.cpp::find_nm)
+__device__ int32_t bam_find_nm(const uint8_t* p, const uint8_t* end) {
+  while (p + 3 <= end) {
+    const uint8_t t0 = p[0], t1 = p[1], ty = p[2];
+    p += 3;
+    uint32_t sz = 0;
+    switch (ty) {
+      case 'A': case 'c': case 'C': sz = 1; break;
+      case 's': case 'S': sz = 2; break;
+      case 'i': case 'I': case 'f': sz = 4; break;
+      case 'd': sz = 8; break;
+      case 'Z': case 'H': {
+        while (p < end && *p) ++p;
+        if (p >= end) return -1;
+        ++p;
+        continue;
+      }
+      case 'B': {
+        if (p + 5 > end) return -1;
+        const uint8_t sub = p[0];
+        const uint32_t cnt = ld_u32(p + 1);
+        const uint32_t es = (sub == 'c' || sub == 'C') ? 1u : (sub == 's' || sub == 'S') ? 2u : 4u;
+        const size_t remaining = (size_t)(end - p);
+        if ((size_t)cnt > (remaining - 5) / es) return -1;
+        p += 5 + (size_t)cnt * es;
+        continue;
+      }
+      default: return -1;
+    }
+    if (p + sz > end) return -1;
+    if (t0 == 'N' && t1 == 'M') {
+      switch (ty) {
+        case 'c': return (int32_t)(int8_t)p[0];
+        case 'C': return (int32_t)p[0];
+        case 's': return (int32_t)(int16_t)ld_u16(p);
+        case 'S': return (int32_t)ld_u16(p);
+        case 'i': return (int32_t)ld_u32(p);
+        case 'I': { const uint32_t v = ld_u32(p); return v > 0x7fffffffu ? 0x7fffffff : (int32_t)v; }
+        default: return -1;
+      }
+    }
+    p += sz;
+  }
+  return -1;
+}
+
+__global__ void __launch_bounds__(256) k_bam_parse(const uint8_t* __restrict__ data, uint64_t total,
+                                                   const uint64_t* __restrict__ rec_off, uint64_t n,
+                                                   const int32_t* __restrict__ tid_map, const uint64_t* __restrict__ cigar_off,
+                                                   int32_t* ref_id, int32_t* pos, uint8_t* mapq, int32_t* nm, int32_t* l_qseq,
+                                                   uint32_t* cigar, uint64_t* seq_off, uint64_t* qual_off) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const uint64_t ro = rec_off[i];
+    const uint8_t* __restrict__ r = data + ro;
+    const uint32_t bs = ld_u32(r - 4);
+    const uint32_t l_name = r[8], n_cig = ld_u16(r + 12), l_seq = ld_u32(r + 16);
+    ref_id[i] = tid_map[(int32_t)ld_u32(r)];
+    pos[i] = (int32_t)ld_u32(r + 4);
+    mapq[i] = r[9];
+    l_qseq[i] = (int32_t)l_seq;
+    const uint8_t* __restrict__ cg = r + 32 + l_name;
+    uint32_t* __restrict__ dst = cigar + cigar_off[i];
+    for (uint32_t k = 0; k < n_cig; ++k) dst[k] = ld_u32(cg + 4 * k);
+    const uint64_t so = ro + 32 + l_name + 4ull * n_cig;            // seq: two bases per byte, first base in the high nibble
+    seq_off[i] = 2 * so;
+    qual_off[i] = so + (l_seq + 1) / 2;
+    nm[i] = bam_find_nm(r + 32 + l_name + 4ull * n_cig + (l_seq + 1) / 2 + l_seq, r + bs);
+    if (i == n - 1) seq_off[n] = 2 * total;
+  }
+}
+
+}  // namespace
+
+extern "C" int mb_snps_pileup_bam(mb_ctx* c, const mb_bam_stream* s, const int32_t* tid_map, const mb_layout* L,
+                                  const mb_filters* f, uint32_t* counts_host, mb_species_stats* stats_host,
+                                  uint64_t* n_reads_out, uint64_t* n_bases_out) {
+  if (!c || !s || !tid_map || !L || !f || !counts_host || !stats_host)
+    return mb::fail(MB_EINVAL, "mb_snps_pileup_bam: null argument");
+  MB_CUDA_TRY(cudaSetDevice(c->device));
+  const uint32_t n_ref = mb_bam_stream_n_ref(s);
+  for (uint32_t t = 0; t < n_ref; ++t)
+    if (tid_map[t] >= (int32_t)L->n_contigs) return mb::fail(MB_EINVAL, "mb_snps_pileup_bam: tid_map[%u] outside the layout", t);
+  size_t total = 0;
+  const uint8_t* data = mb::bam_stream_data(s, &total);
+  cudaStream_t st = c->stream;
+  const bool timing = getenv("MB_BAM_TIMING") != nullptr;
+  auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  double t_phase = now();
+  auto phase = [&](const char* name) {
+    if (timing) { cudaStreamSynchronize(st); const double t = now(); fprintf(stderr, "mb_snps_pileup_bam: %-10s %8.1f ms\n", name, t - t_phase); t_phase = t; }
+  };
+  // the record walk (host, sequential: 4 bytes per record decide where the next one starts) runs while the stream
+  // itself crosses PCIe
+  std::vector<uint64_t> rec_off, cig_off;
+  int walk_rc = MB_OK;
+  std::string walk_msg;
+  double walk_ms = 0;
+  std::thread walker([&] {
+    const double t0 = now();
+    walk_rc = mb::bam_stream_walk(s, tid_map, &rec_off, &cig_off);
+    if (walk_rc) walk_msg = mb_last_error();
+    walk_ms = now() - t0;
+  });
+  void* d_data = nullptr;
+  int rc = mb::ctx_reserve(c, 24, total + 512, &d_data);
+  cudaError_t e = cudaSuccess;
+  if (!rc) {
+    e = cudaMemsetAsync((char*)d_data + total, 0, 512, st);
+    if (e == cudaSuccess && total) e = cudaMemcpyAsync(d_data, data, total, cudaMemcpyHostToDevice, st);
+  }
+  phase("h2d stream");
+  walker.join();
+  if (timing) fprintf(stderr, "mb_snps_pileup_bam: walk (thread) %6.1f ms\n", walk_ms);
+  phase("walk join");
+  if (rc) return rc;
+  if (e != cudaSuccess) return mb::fail(MB_ECUDA, "mb_snps_pileup_bam: %s", cudaGetErrorString(e));
+  if (walk_rc) return mb::fail(walk_rc, "%s", walk_msg.c_str());
+  const uint64_t n = rec_off.size();
+  if (n >= 0xFFFFFFFFull) return mb::fail(MB_EOVERFLOW, "mb_snps_pileup_bam: more than 2^32-2 records");
+  const uint64_t n_cig = cig_off.empty() ? 0 : cig_off.back();
+  void *d_rec = nullptr, *d_tid = nullptr, *d_qoff = nullptr;
+  mb_plain_reads dev;
+  memset(&dev, 0, sizeof(dev));
+  dev.n_reads = n;
+  dev.seq_nibbles = 1;
+  struct A { const void** p; int slot; size_t bytes; } arrs[8] = {
+      {(const void**)&dev.ref_id, 16, 4 * (size_t)n}, {(const void**)&dev.pos, 17, 4 * (size_t)n},
+      {(const void**)&dev.mapq, 18, (size_t)n},       {(const void**)&dev.nm, 19, 4 * (size_t)n},
+      {(const void**)&dev.l_qseq, 20, 4 * (size_t)n}, {(const void**)&dev.cigar_off, 21, 8 * (size_t)(n + 1)},
+      {(const void**)&dev.cigar, 22, 4 * (size_t)n_cig}, {(const void**)&dev.seq_off, 23, 8 * (size_t)(n + 1)}};
+  for (auto& a : arrs) {
+    void* buf = nullptr;
+    rc = mb::ctx_reserve(c, a.slot, a.bytes + 256, &buf);
+    if (rc) return rc;
+    MB_CUDA_TRY(cudaMemsetAsync((char*)buf + a.bytes, 0, 256, st));
+    *a.p = buf;
+  }
+  rc = mb::ctx_reserve(c, 40, 8 * (size_t)n + 256, &d_rec);
+  if (!rc) rc = mb::ctx_reserve(c, 41, 4 * (size_t)n_ref + 256, &d_tid);
+  if (!rc) rc = mb::ctx_reserve(c, 42, 8 * (size_t)n + 256, &d_qoff);
+  if (rc) return rc;
+  dev.seq = (const uint8_t*)d_data;
+  dev.qual = (const uint8_t*)d_data;
+  if (n) {
+    MB_CUDA_TRY(cudaMemcpyAsync(d_rec, rec_off.data(), 8 * (size_t)n, cudaMemcpyHostToDevice, st));
+    MB_CUDA_TRY(cudaMemcpyAsync((void*)dev.cigar_off, cig_off.data(), 8 * (size_t)(n + 1), cudaMemcpyHostToDevice, st));
+    MB_CUDA_TRY(cudaMemcpyAsync(d_tid, tid_map, 4 * (size_t)n_ref, cudaMemcpyHostToDevice, st));
+    const uint32_t grid = (uint32_t)std::min<uint64_t>((n + 255) / 256, (uint64_t)c->sm_count * 8);
+    k_bam_parse<<<grid, 256, 0, st>>>((const uint8_t*)d_data, (uint64_t)total, (const uint64_t*)d_rec, n, (const int32_t*)d_tid,
+                                      dev.cigar_off, (int32_t*)dev.ref_id, (int32_t*)dev.pos, (uint8_t*)dev.mapq,
+                                      (int32_t*)dev.nm, (int32_t*)dev.l_qseq, (uint32_t*)dev.cigar, (uint64_t*)dev.seq_off,
+                                      (uint64_t*)d_qoff);
+    c->launches += 1;
+    MB_CUDA_TRY(cudaStreamSynchronize(st));      // the host vectors above are read by the copies: keep them alive until here
+  }
+  phase("parse");
+  mb_dev_reads dr;
+  rc = mb::pack_on_device(c, &dev, L, 0, /*staged=*/true, &dr, (const uint64_t*)d_qoff);
+  if (rc) return rc;
+  phase("pack");
+  if (n_reads_out) *n_reads_out = n;
+  if (n_bases_out) *n_bases_out = dr.total_bases;
+  void *counts = nullptr, *stats = nullptr;
+  const size_t cbytes = sizeof(uint32_t) * 4 * (size_t)L->gpad, sbytes = sizeof(mb_species_stats) * (size_t)L->n_species;
+  rc = mb::ctx_reserve(c, 0, cbytes, &counts);
+  if (!rc) rc = mb::ctx_reserve(c, 1, sbytes, &stats);
+  if (rc) return rc;
+  c->rng_for = nullptr;
+  rc = mb_snps_pileup_dev(c, &dr, L, f, (uint32_t*)counts, (mb_species_stats*)stats);
+  c->rng_for = nullptr;
+  if (rc) return rc;
+  if (cbytes) {
+    e = cudaMemcpyAsync(counts_host, counts, cbytes, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && sbytes) e = cudaMemcpyAsync(stats_host, stats, sbytes, cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) return mb::fail(MB_ECUDA, "mb_snps_pileup_bam: %s", cudaGetErrorString(e));
+  }
+  rc = mb::check_overflow(c, "mb_snps_pileup_bam");
+  phase("pileup+d2h");
+  return rc;
 }
 
 extern "C" int mb_ctx_last_pack_ms(mb_ctx* c, float* ms) {

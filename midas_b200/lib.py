@@ -85,6 +85,8 @@ EXPORTS = [
     "mb_format_snps_bound", "mb_format_snps_rows",
     "mb_merge_sites_dev", "mb_format_merge_bound", "mb_format_merge_freq_rows", "mb_format_merge_depth_rows",
     "mb_bam_open", "mb_bam_close", "mb_bam_n_ref", "mb_bam_ref_name", "mb_bam_ref_len", "mb_bam_reads", "mb_bam_flags",
+    "mb_bam_stream_open", "mb_bam_stream_close", "mb_bam_stream_n_ref", "mb_bam_stream_ref_name", "mb_bam_stream_ref_len",
+    "mb_bam_stream_bytes", "mb_snps_pileup_bam",
 ]
 
 _lib = None
@@ -181,6 +183,19 @@ def load():
     L.mb_bam_reads.restype = C.POINTER(CPlainReads)
     L.mb_bam_flags.argtypes = [C.c_void_p]
     L.mb_bam_flags.restype = C.c_void_p
+    L.mb_bam_stream_open.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
+    L.mb_bam_stream_close.argtypes = [C.c_void_p]
+    L.mb_bam_stream_close.restype = None
+    L.mb_bam_stream_n_ref.argtypes = [C.c_void_p]
+    L.mb_bam_stream_n_ref.restype = C.c_uint32
+    L.mb_bam_stream_ref_name.argtypes = [C.c_void_p, C.c_uint32]
+    L.mb_bam_stream_ref_name.restype = C.c_char_p
+    L.mb_bam_stream_ref_len.argtypes = [C.c_void_p, C.c_uint32]
+    L.mb_bam_stream_ref_len.restype = C.c_uint32
+    L.mb_bam_stream_bytes.argtypes = [C.c_void_p]
+    L.mb_bam_stream_bytes.restype = C.c_uint64
+    L.mb_snps_pileup_bam.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(CFilters), C.c_void_p,
+                                     C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     _lib = L
     return L
 
@@ -458,6 +473,22 @@ class Context:
         _check(load().mb_snps_pileup_plain(self._h, C.byref(cin), layout._h, C.byref(f), _ptr(counts), _ptr(stats)))
         return counts, stats
 
+    def snps_pileup_bam(self, stream: "BamStream", tid_map, layout: Layout, filters: Filters,
+                        counts_out: np.ndarray | None = None):
+        """From the inflated BAM record stream (mb_snps_pileup_bam): the bytes go to the GPU as they are, the device
+        parses the records, re-lays them and counts. tid_map: int32 [n_ref] BAM reference -> layout contig (-1 = drop).
+        Returns (counts, stats, n_reads, n_bases)."""
+        counts = counts_out if counts_out is not None else np.empty((4, layout.gpad), np.uint32)
+        assert counts.dtype == np.uint32 and counts.shape == (4, layout.gpad) and counts.flags.c_contiguous
+        stats = np.zeros(layout.n_species, STATS_DTYPE)
+        tid_map = np.ascontiguousarray(tid_map, np.int32)
+        assert len(tid_map) == len(stream.names)
+        f = CFilters.of(filters)
+        nr, nb = C.c_uint64(), C.c_uint64()
+        _check(load().mb_snps_pileup_bam(self._h, stream._h, _ptr(tid_map), layout._h, C.byref(f), _ptr(counts),
+                                         _ptr(stats), C.byref(nr), C.byref(nb)))
+        return counts, stats, int(nr.value), int(nb.value)
+
     # ---- merge (snps)
     def merge_sites(self, counts, mean_depth, snp_freq=0.01, site_depth=1, site_ratio=2.0):
         """Pooled allele call across samples (reference midas/merge/snps.py GenomicSite).
@@ -598,6 +629,28 @@ def read_bam(path: str, threads: int = 0, pinned: bool = False, seq_bytes: bool 
                        arr(r.qual, int(soff[-1]), np.uint8), arr(L.mb_bam_flags(h), n, np.uint16),
                        bool(r.seq_nibbles))
     return names, lens, reads
+
+
+class BamStream:
+    """A BAM file inflated on the host threads (mb_bam_stream_open): header + the raw record stream, which the GPU
+    parses (Context.snps_pileup_bam). No host-side record decode."""
+
+    def __init__(self, path: str, threads: int = 0):
+        L = load()
+        h = C.c_void_p()
+        _check(L.mb_bam_stream_open(os.fsencode(path), int(threads), C.byref(h)))
+        self._h = h
+        n = int(L.mb_bam_stream_n_ref(h))
+        self.names = [L.mb_bam_stream_ref_name(h, i).decode() for i in range(n)]
+        self.lens = [int(L.mb_bam_stream_ref_len(h, i)) for i in range(n)]
+        self.nbytes = int(L.mb_bam_stream_bytes(h))
+
+    def close(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h and _lib is not None:
+            _lib.mb_bam_stream_close(h)
+
+    __del__ = close
 
 
 class _Pinned:

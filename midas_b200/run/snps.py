@@ -212,15 +212,42 @@ def pysam_pileup(args, species, contigs, ctx=None):
         t = time()
         threads = int(args.get("threads", 1) or 1)
         bampath = "%s/snps/temp/genomes.bam" % args["outdir"]
-        ref, reads = load_alignments(bampath, species, contigs, threads=threads)
-        if timing is not None:
-            timing["n_reads"], timing["n_bases"] = int(reads.n_reads), int(reads.l_qseq.sum(dtype=np.int64))
-        t = lap("bam_decode", t)
         filters = _filters(args)
+        streamed = None
+        if world == 1 and not args.get("host_decode"):
+            # the streaming ingest: host threads only inflate the BGZF blocks; the record stream goes to the GPU as it
+            # is and the device parses, re-lays and counts it (mb_snps_pileup_bam)
+            stream = lib.BamStream(bampath, threads)
+            ref = build_refset(species, contigs, stream.names)
+            index = {n: k for k, n in enumerate(ref.contig_names)}
+            tid_map = np.array([index.get(n, -1) for n in stream.names], np.int32)
+            for n, l in zip(stream.names, stream.lens):
+                k = index.get(n)
+                if k is not None and int(ref.contig_len[k]) != int(l):
+                    raise lib.MidasB200Error(-5, f"BAM header length of {n} ({l}) != FASTA length ({int(ref.contig_len[k])})")
+            t = lap("bam_inflate", t)
+            layout = lib.Layout.of(ref)
+            try:
+                counts, stats, n_reads, n_bases = ctx.snps_pileup_bam(stream, tid_map, layout, filters)
+                streamed = True
+                if timing is not None:
+                    timing["n_reads"], timing["n_bases"] = n_reads, n_bases
+                t = lap("gpu_h2d_parse_pack_kernels_d2h", t)
+            except lib.MidasB200Error as e:
+                if e.status != -6:          # not coordinate-sorted: decode and sort on the host below
+                    raise
+            finally:
+                stream.close()
+        if not streamed:
+            ref, reads = load_alignments(bampath, species, contigs, threads=threads)
+            if timing is not None:
+                timing["n_reads"], timing["n_bases"] = int(reads.n_reads), int(reads.l_qseq.sum(dtype=np.int64))
+            t = lap("bam_decode", t)
         if world == 1:
             layout = lib.Layout.of(ref)
-            counts, stats = _run_batch(ctx, reads, layout, filters, threads)
-            t = lap("gpu_h2d_pack_kernels_d2h", t)
+            if not streamed:
+                counts, stats = _run_batch(ctx, reads, layout, filters, threads)
+                t = lap("gpu_h2d_pack_kernels_d2h", t)
             mine, writes = np.arange(ref.n_species), np.ones(ref.n_species, bool)
             sub_ref = ref
             rows = np.stack([stats[name].astype(np.int64) for name in lib.STATS_DTYPE.names], 1)

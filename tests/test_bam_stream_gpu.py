@@ -1,0 +1,83 @@
+"""GPU: the streaming ingest (mb_bam_stream_open + mb_snps_pileup_bam: the inflated BAM record stream parsed on the
+device) gives the counts of the host-decoded path and of the oracle, on BAM files with arbitrary CIGARs, unplaced
+records, references that are dropped, missing NM / qualities."""
+import numpy as np
+import pytest
+
+import gen
+from midas_b200 import bam, lib, synth
+from midas_b200.soa import Filters, RefSet
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _via_stream(ctx, path, ref, filters, tid_map=None, threads=4):
+    st = lib.BamStream(path, threads)
+    index = {n: k for k, n in enumerate(ref.contig_names)}
+    tm = np.array([index.get(n, -1) for n in st.names], np.int32) if tid_map is None else tid_map
+    lay = lib.Layout.of(ref)
+    counts, stats, n_reads, n_bases = ctx.snps_pileup_bam(st, tm, lay, filters)
+    st.close()
+    return lay, counts, stats, n_reads, n_bases
+
+
+@pytest.mark.parametrize("seed,n_species,cps,lo,hi,n_reads,max_len", [
+    (301, 3, 2, 500, 6000, 3000, 300), (302, 1, 1, 5000, 5000, 4000, 150), (303, 2, 3, 40, 900, 2500, 120)])
+def test_random_cigars_from_a_bam_file(ctx, tmp_path, seed, n_species, cps, lo, hi, n_reads, max_len):
+    rng = np.random.default_rng(seed)
+    ref = gen.make_ref(rng, n_species, cps, lo, hi)
+    reads = gen.random_reads(seed, ref, n_reads, max_len=max_len)
+    reads.ref_id[::97] = -1                                     # unplaced records: dropped
+    p = str(tmp_path / "x.bam")
+    bam.write_bam(p, ref.contig_names, ref.contig_len, reads)
+    kept = reads.select(np.nonzero(reads.ref_id >= 0)[0])
+    for filters in (Filters(), Filters(mapid=0.0, aln_cov=0.0, readq=0, mapq=0, baseq=0)):
+        exp_counts, exp_stats = oracle.snps_pileup(kept, ref, filters)
+        lay, counts, stats, n, nb = _via_stream(ctx, p, ref, filters)
+        assert n == kept.n_reads and nb == kept.total_bases
+        assert np.array_equal(lay.unpad(counts).astype(np.uint64), exp_counts)
+        for k, name in enumerate(lib.STATS_DTYPE.names):
+            assert np.array_equal(stats[name], exp_stats[:, k]), name
+
+
+def test_dropped_references_and_c2_shape(ctx, tmp_path):
+    ref, reads = synth.synth_snps(seed=5, n_species=3, contigs_per_species=2, contig_len=15_000, n_reads=80_000,
+                                  len_jitter=0.2, abundance="lognormal")
+    p = str(tmp_path / "y.bam")
+    bam.write_bam(p, ref.contig_names, ref.contig_len, reads)
+    # only species 0 and 2 are selected: the records of species 1's contigs are never fetched by the reference
+    keep_c = np.nonzero(ref.contig_species != 1)[0]
+    sub = RefSet([ref.contig_names[c] for c in keep_c], ref.contig_len[keep_c],
+                 np.searchsorted([0, 2], ref.contig_species[keep_c]).astype(np.int32), [ref.species_ids[0], ref.species_ids[2]], None)
+    cmap = -np.ones(ref.n_contigs, np.int32)
+    cmap[keep_c] = np.arange(len(keep_c), dtype=np.int32)
+    kept = reads.select(np.nonzero(cmap[reads.ref_id] >= 0)[0])
+    kept.ref_id = np.ascontiguousarray(cmap[kept.ref_id], np.int32)
+    exp_counts, exp_stats = oracle.snps_pileup(kept, sub, Filters())
+    lay, counts, stats, n, nb = _via_stream(ctx, p, sub, Filters())
+    assert n == kept.n_reads
+    assert np.array_equal(lay.unpad(counts).astype(np.uint64), exp_counts)
+    for k, name in enumerate(lib.STATS_DTYPE.names):
+        assert np.array_equal(stats[name], exp_stats[:, k]), name
+
+
+def test_errors_and_unsorted(ctx, tmp_path):
+    rng = np.random.default_rng(1)
+    ref = gen.make_ref(rng, 1, 2, 800, 900)
+    reads = gen.random_reads(3, ref, 300, max_len=80)
+    bad = reads.select(slice(0, 300))
+    bad.nm[200] = -1                                            # no NM tag: KeyError in the reference
+    p = str(tmp_path / "nm.bam")
+    bam.write_bam(p, ref.contig_names, ref.contig_len, bad, extra_tags=False)
+    with pytest.raises(lib.MidasB200Error) as e:
+        _via_stream(ctx, p, ref, Filters())
+    assert e.value.status == -1
+    uns = gen.random_reads(4, ref, 300, max_len=80, sort=False)
+    p2 = str(tmp_path / "uns.bam")
+    bam.write_bam(p2, ref.contig_names, ref.contig_len, uns)
+    with pytest.raises(lib.MidasB200Error) as e:
+        _via_stream(ctx, p2, ref, Filters())
+    assert e.value.status == -6
+    with pytest.raises(lib.MidasB200Error):
+        lib.BamStream(str(tmp_path / "missing.bam"))

@@ -378,6 +378,10 @@ uint64_t mb_bam_stream_bytes(const mb_bam_stream* s);   /* inflated bytes (what 
 int mb_snps_pileup_bam(mb_ctx* ctx, const mb_bam_stream* s, const int32_t* tid_map, const mb_layout* L,
                        const mb_filters* f, uint32_t* counts_host, mb_species_stats* stats_host,
                        uint64_t* n_reads_out, uint64_t* n_bases_out);
+/* <- midas/run/genes.py:175-189 from the BAM bytes (file order kept; tid_map[i] = gene index of BAM reference i or -1) */
+int mb_genes_coverage_bam(mb_ctx* ctx, const mb_bam_stream* s, const int32_t* tid_map, const uint32_t* gene_len_host,
+                          uint32_t n_genes, const mb_filters* f, int exact_order, mb_gene_out* out_host,
+                          uint64_t* n_reads_out);
 
 /* ------------------------------------------------------------- text output */
 /* Rows of <species>.snps.gz for n_rows consecutive positions of one contig, starting at 0-based

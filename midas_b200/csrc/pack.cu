@@ -1066,15 +1066,13 @@ __global__ void __launch_bounds__(256) k_bam_parse(const uint8_t* __restrict__ d
 
 }  // namespace
 
-extern "C" int mb_snps_pileup_bam(mb_ctx* c, const mb_bam_stream* s, const int32_t* tid_map, const mb_layout* L,
-                                  const mb_filters* f, uint32_t* counts_host, mb_species_stats* stats_host,
-                                  uint64_t* n_reads_out, uint64_t* n_bases_out) {
-  if (!c || !s || !tid_map || !L || !f || !counts_host || !stats_host)
-    return mb::fail(MB_EINVAL, "mb_snps_pileup_bam: null argument");
-  MB_CUDA_TRY(cudaSetDevice(c->device));
+namespace mb {
+// BAM record stream -> packed batch in context staging buffers (H2D of the stream, k_bam_parse, k_pack_*).
+int pack_from_bam_stream(mb_ctx* c, const mb_bam_stream* s, const int32_t* tid_map, uint32_t n_targets, const mb_layout* L,
+                         int mode, mb_dev_reads* dr, const char* who) {
   const uint32_t n_ref = mb_bam_stream_n_ref(s);
   for (uint32_t t = 0; t < n_ref; ++t)
-    if (tid_map[t] >= (int32_t)L->n_contigs) return mb::fail(MB_EINVAL, "mb_snps_pileup_bam: tid_map[%u] outside the layout", t);
+    if (tid_map[t] >= (int32_t)n_targets) return mb::fail(MB_EINVAL, "%s: tid_map[%u] outside the layout", who, t);
   size_t total = 0;
   const uint8_t* data = mb::bam_stream_data(s, &total);
   cudaStream_t st = c->stream;
@@ -1082,7 +1080,7 @@ extern "C" int mb_snps_pileup_bam(mb_ctx* c, const mb_bam_stream* s, const int32
   auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   double t_phase = now();
   auto phase = [&](const char* name) {
-    if (timing) { cudaStreamSynchronize(st); const double t = now(); fprintf(stderr, "mb_snps_pileup_bam: %-10s %8.1f ms\n", name, t - t_phase); t_phase = t; }
+    if (timing) { cudaStreamSynchronize(st); const double t = now(); fprintf(stderr, "%s: %-10s %8.1f ms\n", who, name, t - t_phase); t_phase = t; }
   };
   // the record walk (host, sequential: 4 bytes per record decide where the next one starts) runs while the stream
   // itself crosses PCIe
@@ -1105,13 +1103,13 @@ extern "C" int mb_snps_pileup_bam(mb_ctx* c, const mb_bam_stream* s, const int32
   }
   phase("h2d stream");
   walker.join();
-  if (timing) fprintf(stderr, "mb_snps_pileup_bam: walk (thread) %6.1f ms\n", walk_ms);
+  if (timing) fprintf(stderr, "%s: walk (thread) %6.1f ms\n", who, walk_ms);
   phase("walk join");
   if (rc) return rc;
-  if (e != cudaSuccess) return mb::fail(MB_ECUDA, "mb_snps_pileup_bam: %s", cudaGetErrorString(e));
+  if (e != cudaSuccess) return mb::fail(MB_ECUDA, "%s: %s", who, cudaGetErrorString(e));
   if (walk_rc) return mb::fail(walk_rc, "%s", walk_msg.c_str());
   const uint64_t n = rec_off.size();
-  if (n >= 0xFFFFFFFFull) return mb::fail(MB_EOVERFLOW, "mb_snps_pileup_bam: more than 2^32-2 records");
+  if (n >= 0xFFFFFFFFull) return mb::fail(MB_EOVERFLOW, "%s: more than 2^32-2 records", who);
   const uint64_t n_cig = cig_off.empty() ? 0 : cig_off.back();
   void *d_rec = nullptr, *d_tid = nullptr, *d_qoff = nullptr;
   mb_plain_reads dev;
@@ -1149,11 +1147,24 @@ extern "C" int mb_snps_pileup_bam(mb_ctx* c, const mb_bam_stream* s, const int32
     MB_CUDA_TRY(cudaStreamSynchronize(st));      // the host vectors above are read by the copies: keep them alive until here
   }
   phase("parse");
-  mb_dev_reads dr;
-  rc = mb::pack_on_device(c, &dev, L, 0, /*staged=*/true, &dr, (const uint64_t*)d_qoff);
+  rc = mb::pack_on_device(c, &dev, L, mode, /*staged=*/true, dr, (const uint64_t*)d_qoff);
   if (rc) return rc;
   phase("pack");
-  if (n_reads_out) *n_reads_out = n;
+  return MB_OK;
+}
+}  // namespace mb
+
+extern "C" int mb_snps_pileup_bam(mb_ctx* c, const mb_bam_stream* s, const int32_t* tid_map, const mb_layout* L,
+                                  const mb_filters* f, uint32_t* counts_host, mb_species_stats* stats_host,
+                                  uint64_t* n_reads_out, uint64_t* n_bases_out) {
+  if (!c || !s || !tid_map || !L || !f || !counts_host || !stats_host)
+    return mb::fail(MB_EINVAL, "mb_snps_pileup_bam: null argument");
+  MB_CUDA_TRY(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  mb_dev_reads dr;
+  int rc = mb::pack_from_bam_stream(c, s, tid_map, L->n_contigs, L, 0, &dr, "mb_snps_pileup_bam");
+  if (rc) return rc;
+  if (n_reads_out) *n_reads_out = dr.n_reads;
   if (n_bases_out) *n_bases_out = dr.total_bases;
   void *counts = nullptr, *stats = nullptr;
   const size_t cbytes = sizeof(uint32_t) * 4 * (size_t)L->gpad, sbytes = sizeof(mb_species_stats) * (size_t)L->n_species;
@@ -1165,13 +1176,37 @@ extern "C" int mb_snps_pileup_bam(mb_ctx* c, const mb_bam_stream* s, const int32
   c->rng_for = nullptr;
   if (rc) return rc;
   if (cbytes) {
-    e = cudaMemcpyAsync(counts_host, counts, cbytes, cudaMemcpyDeviceToHost, st);
+    cudaError_t e = cudaMemcpyAsync(counts_host, counts, cbytes, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess && sbytes) e = cudaMemcpyAsync(stats_host, stats, sbytes, cudaMemcpyDeviceToHost, st);
     if (e != cudaSuccess) return mb::fail(MB_ECUDA, "mb_snps_pileup_bam: %s", cudaGetErrorString(e));
   }
-  rc = mb::check_overflow(c, "mb_snps_pileup_bam");
-  phase("pileup+d2h");
-  return rc;
+  return mb::check_overflow(c, "mb_snps_pileup_bam");
+}
+
+extern "C" int mb_genes_coverage_bam(mb_ctx* c, const mb_bam_stream* s, const int32_t* tid_map, const uint32_t* gene_len_host,
+                                     uint32_t n_genes, const mb_filters* f, int exact_order, mb_gene_out* out_host,
+                                     uint64_t* n_reads_out) {
+  if (!c || !s || !tid_map || !gene_len_host || !f || !out_host)
+    return mb::fail(MB_EINVAL, "mb_genes_coverage_bam: null argument");
+  MB_CUDA_TRY(cudaSetDevice(c->device));
+  mb_layout* L = nullptr;
+  int rc = mb_layout_create_genes(n_genes, &L);
+  if (rc) return rc;
+  mb_dev_reads dr;
+  rc = mb::pack_from_bam_stream(c, s, tid_map, n_genes, L, 1, &dr, "mb_genes_coverage_bam");
+  mb_layout_destroy(L);
+  if (rc) return rc;
+  if (n_reads_out) *n_reads_out = dr.n_reads;
+  void *gl = nullptr, *out = nullptr;
+  rc = mb::ctx_reserve(c, 2, sizeof(uint32_t) * (size_t)n_genes, &gl);
+  if (!rc) rc = mb::ctx_reserve(c, 3, sizeof(mb_gene_out) * (size_t)n_genes, &out);
+  if (rc) return rc;
+  if (n_genes) MB_CUDA_TRY(cudaMemcpyAsync(gl, gene_len_host, sizeof(uint32_t) * (size_t)n_genes, cudaMemcpyHostToDevice, c->stream));
+  rc = mb_genes_coverage_dev(c, &dr, (const uint32_t*)gl, n_genes, f, exact_order, (mb_gene_out*)out);
+  if (rc) return rc;
+  if (n_genes) MB_CUDA_TRY(cudaMemcpyAsync(out_host, out, sizeof(mb_gene_out) * (size_t)n_genes, cudaMemcpyDeviceToHost, c->stream));
+  MB_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return MB_OK;
 }
 
 extern "C" int mb_ctx_last_pack_ms(mb_ctx* c, float* ms) {

@@ -86,7 +86,7 @@ EXPORTS = [
     "mb_merge_sites_dev", "mb_format_merge_bound", "mb_format_merge_freq_rows", "mb_format_merge_depth_rows",
     "mb_bam_open", "mb_bam_close", "mb_bam_n_ref", "mb_bam_ref_name", "mb_bam_ref_len", "mb_bam_reads", "mb_bam_flags",
     "mb_bam_stream_open", "mb_bam_stream_close", "mb_bam_stream_n_ref", "mb_bam_stream_ref_name", "mb_bam_stream_ref_len",
-    "mb_bam_stream_bytes", "mb_snps_pileup_bam",
+    "mb_bam_stream_bytes", "mb_snps_pileup_bam", "mb_genes_coverage_bam",
 ]
 
 _lib = None
@@ -194,6 +194,8 @@ def load():
     L.mb_bam_stream_ref_len.restype = C.c_uint32
     L.mb_bam_stream_bytes.argtypes = [C.c_void_p]
     L.mb_bam_stream_bytes.restype = C.c_uint64
+    L.mb_genes_coverage_bam.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(CFilters),
+                                        C.c_int, C.c_void_p, C.POINTER(C.c_uint64)]
     L.mb_snps_pileup_bam.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(CFilters), C.c_void_p,
                                      C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     _lib = L
@@ -531,6 +533,19 @@ class Context:
         _check(load().mb_genes_coverage_plain(self._h, C.byref(cin), _ptr(gene_len), len(gene_len), C.byref(f),
                                               int(exact_order), _ptr(out)))
         return out
+
+    def genes_coverage_bam(self, stream: "BamStream", tid_map, gene_len: np.ndarray, filters: Filters, exact_order=False):
+        """From the inflated BAM record stream (mb_genes_coverage_bam); tid_map: int32 [n_ref] BAM reference -> gene
+        index (-1 = drop). Returns (per-gene outputs, n_reads)."""
+        gene_len = np.ascontiguousarray(gene_len, np.uint32)
+        tid_map = np.ascontiguousarray(tid_map, np.int32)
+        assert len(tid_map) == len(stream.names)
+        out = np.zeros(len(gene_len), GENE_OUT_DTYPE)
+        f = CFilters.of(filters)
+        nr = C.c_uint64()
+        _check(load().mb_genes_coverage_bam(self._h, stream._h, _ptr(tid_map), _ptr(gene_len), len(gene_len), C.byref(f),
+                                            int(exact_order), _ptr(out), C.byref(nr)))
+        return out, int(nr.value)
 
     def genes_coverage(self, packed: PackedReads, gene_len: np.ndarray, filters: Filters, exact_order=False):
         gene_len = np.ascontiguousarray(gene_len, np.uint32)

@@ -106,30 +106,41 @@ def pangenome_coverage(args, species, genes, ctx=None):
 def count_mapped_bp(args, species, genes, ctx=None):
     """reference genes.py:171-203: per gene aligned/mapped reads and depth, per species summaries."""
     bam_path = "/".join([args["outdir"], "genes/temp/pangenomes.bam"])
-    names, lens, reads = lib.read_bam(bam_path, int(args.get("threads", 0) or 0))
+    threads = int(args.get("threads", 0) or 0)
     gene_ids = list(genes.keys())
     gindex = {g: k for k, g in enumerate(gene_ids)}
-    missing = [n for n in set(names[t] for t in np.unique(reads.ref_id))
-               if n not in gindex] if reads.n_reads else []
-    if missing:
-        raise KeyError(missing[0])                                   # genes[...] KeyError, genes.py:180
-    tid_map = np.array([gindex.get(n, -1) for n in names], np.int32) if names else np.zeros(0, np.int32)
-    if reads.n_reads and not np.array_equal(tid_map, np.arange(len(names), dtype=np.int32)):
-        reads.ref_id[...] = tid_map[reads.ref_id]
     gene_len = np.array([genes[g].length for g in gene_ids], np.uint32)
-    if reads.n_reads:
-        hit = np.unique(reads.ref_id)
-        if (gene_len[hit] == 0).any():
-            raise ZeroDivisionError("float division by zero")    # alen / float(gene.length), genes.py:189
+    f = Filters(float(args["mapid"]), float(args["aln_cov"]), int(args["readq"]), int(args["mapq"]), 0)
+    exact = bool(args.get("exact_order", False))
     own_ctx = ctx is None
     if own_ctx:
         ctx = lib.Context(int(args.get("device", 0)), use_torch_stream=False)
     try:
-        # decoded records -> H2D -> re-layout on the GPU -> coverage kernel -> D2H. depth is one division of
-        # the integer sum (within 1e-12 of the reference's running float sum); --exact_order reproduces the
-        # running sum bit for bit at the price of a device sort
-        f = Filters(float(args["mapid"]), float(args["aln_cov"]), int(args["readq"]), int(args["mapq"]), 0)
-        out = ctx.genes_coverage_plain(reads, gene_len, f, exact_order=bool(args.get("exact_order", False)))
+        # depth is one division of the integer sum (within 1e-12 of the reference's running float sum);
+        # --exact_order reproduces the running sum bit for bit at the price of a device sort
+        stream = lib.BamStream(bam_path, threads)
+        tid_map = np.array([gindex.get(n, -1) for n in stream.names], np.int32)
+        if len(tid_map) and (tid_map >= 0).all() and not (gene_len[tid_map] == 0).any() and not args.get("host_decode"):
+            # the streaming ingest: the host only inflates; the record stream is parsed, re-laid and counted on the GPU
+            out, _ = ctx.genes_coverage_bam(stream, tid_map, gene_len, f, exact_order=exact)
+            stream.close()
+        else:
+            # a BAM reference that is not a gene of the selected pangenomes, or a zero-length gene: the reference raises
+            # only if a record actually hits it (genes.py:180,189) - decode on the host and look
+            stream.close()
+            names, lens, reads = lib.read_bam(bam_path, threads)
+            missing = [n for n in set(names[t] for t in np.unique(reads.ref_id))
+                       if n not in gindex] if reads.n_reads else []
+            if missing:
+                raise KeyError(missing[0])                                   # genes[...] KeyError, genes.py:180
+            tid_map = np.array([gindex.get(n, -1) for n in names], np.int32) if names else np.zeros(0, np.int32)
+            if reads.n_reads and not np.array_equal(tid_map, np.arange(len(names), dtype=np.int32)):
+                reads.ref_id[...] = tid_map[reads.ref_id]
+            if reads.n_reads:
+                hit = np.unique(reads.ref_id)
+                if (gene_len[hit] == 0).any():
+                    raise ZeroDivisionError("float division by zero")    # alen / float(gene.length), genes.py:189
+            out = ctx.genes_coverage_plain(reads, gene_len, f, exact_order=exact)
     finally:
         if own_ctx:
             ctx.close()

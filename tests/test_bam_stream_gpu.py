@@ -81,3 +81,24 @@ def test_errors_and_unsorted(ctx, tmp_path):
     assert e.value.status == -6
     with pytest.raises(lib.MidasB200Error):
         lib.BamStream(str(tmp_path / "missing.bam"))
+
+
+def test_genes_coverage_from_a_bam_file(ctx, tmp_path):
+    gref, greads, _ = synth.synth_genes(seed=12, n_species=3, genes_per_species=150, n_reads=40_000, read_len=110)
+    p = str(tmp_path / "g.bam")
+    bam.write_bam(p, gref.contig_names, gref.contig_len, greads)
+    st = lib.BamStream(p, 4)
+    assert st.names == gref.contig_names
+    tid_map = np.arange(len(st.names), dtype=np.int32)
+    for filters in (Filters.genes_defaults(), Filters(mapid=97.0, aln_cov=0.9, readq=30, mapq=30, baseq=0)):
+        exp = oracle.genes_coverage(greads, gref.contig_len, filters)
+        for exact in (False, True):
+            out, n = ctx.genes_coverage_bam(st, tid_map, gref.contig_len, filters, exact_order=exact)
+            assert n == greads.n_reads
+            assert np.array_equal(out["aligned_reads"], exp["aligned"]) and np.array_equal(out["mapped_reads"], exp["mapped"])
+            assert np.array_equal(out["mapped_bp"], exp["mapped_bp"])
+            if exact:
+                assert np.array_equal(out["depth"].view(np.uint64), exp["depth"].view(np.uint64))
+            else:
+                assert np.allclose(out["depth"], exp["depth"], rtol=1e-12, atol=0)
+    st.close()

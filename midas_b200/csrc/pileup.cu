@@ -196,6 +196,7 @@ __global__ void __launch_bounds__(256) k_tile_ranges(const uint4* __restrict__ h
 // short loop; taken only by heavily clipped reads and by indels that push a run across a word boundary)
 #define MB_SLIDE(d, wshift, A, B, C)                                                        \
   do {                                                                                      \
+    if ((d) == -1) break;                                                                   \
     while ((d) > -1) {                                                                      \
       _Pragma("unroll") for (int w = 0; w <= WT; ++w) { A[w] = A[w + 1]; B[w] = B[w + 1]; C[w] = C[w + 1]; } \
       A[WT + 1] = 0; B[WT + 1] = 0; C[WT + 1] = 0;                                          \
@@ -220,6 +221,8 @@ __global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : 2) k_pi
   constexpr bool PFL2 = (VAR & 8) != 0;         // bit 3: the next round's arrays are prefetched into L2 during COUNT
   constexpr bool SORTED = (VAR & 16) != 0;      // bit 4: the rows of a round are dealt to the threads by class (below)
   constexpr int KMAX = 3;                       // SORTED: rows per thread and round (rmax <= KMAX * NT)
+  constexpr bool DEFER = (VAR & 32) != 0;       // bit 5: reads with an indel are placed after the warp's simple ones (below)
+  constexpr int DCAP = 16, DWORDS = 3 * WT + 6; // DEFER: entries per warp and round; words per entry
   extern __shared__ __align__(128) uint32_t smem[];
   constexpr uint32_t W = (uint32_t)WT;          // row words (compile time: every per-lane loop below unrolls)
   constexpr int NP = 3 + NQ;                    // words per 32-base block: seq lo, seq hi, candidate, Phred bits
@@ -247,7 +250,11 @@ __global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : 2) k_pi
   uint32_t mb_phase = 0;                                               // parity of my warp's next wait
   // SORTED: the round's headers (bit 31 of .w = the read passed the header filters and touches the tile), the
   // rows in processing order, the unit offsets of the round's groups
-  uint4* const s_hdr = reinterpret_cast<uint4*>(const_cast<uint32_t*>(s_zero) + 8);
+  // DEFER: per warp, the converted planes + header of the reads whose placement is put off: the indel code then runs
+  // once per warp and round over those reads only, instead of in every iteration that holds one of them
+  uint32_t* const s_defer = const_cast<uint32_t*>(s_zero) + 8;
+  uint32_t wdefer = 0;                                                 // DEFER: entries of my warp's list (warp-uniform)
+  uint4* const s_hdr = reinterpret_cast<uint4*>(s_defer + (DEFER ? (NT / 32) * DCAP * DWORDS : 0));
   uint16_t* const s_perm = reinterpret_cast<uint16_t*>(s_hdr + p.rmax);
   uint32_t* const s_goff = reinterpret_cast<uint32_t*>(s_perm + p.rmax);
   __shared__ uint32_t s_cnt[2];                                        // SORTED: simple / complex rows of the round
@@ -360,126 +367,14 @@ __global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : 2) k_pi
       col_rows = 0;
     };
 
-    // ---- STAGE of one read (row i of a round of n rows): header filters (snps.py:148,154,157), row index
-    // table, the read's bit planes, bit-sliced base-quality test, mean-quality filter, CIGAR placement, row store
-    auto stage_one = [&](const int i, const int n, const uint4 h, const uint32_t b0, const uint32_t cw,
-                         const uint32_t prev_loc, const uint32_t* __restrict__ raw_in) {
-        const uint32_t loc = h.x, lq = h.y & 0xffffu, alen = h.y >> 16, qstart = h.z & 0xffffu, nm = h.z >> 16;
-        const uint32_t span = h.w & 0xffffu, mq = (h.w >> 16) & 0xffu, fl = (h.w >> 24) & 0x7fu;
-        bool needq = false, ovl = false, owner = false;
-        if (SORTED) {                              // classified before (bit 31 of the stashed header)
-          if (!(fl & MB_RF_LONG)) {
-            owner = loc >= ts;
-            ovl = span > 0 && loc + span > ts;
-            if (owner) ++my_aligned;                                                                // snps.py:143
-            needq = (h.w >> 31) != 0;
-          }
-        } else if (!(fl & MB_RF_LONG)) {
-          owner = loc >= ts;
-          ovl = span > 0 && loc + span > ts;
-          // exact integer forms of the two double-precision tests (tables built in ctx.cu)
-          bool hk = (fl & MB_RF_NMSAT) ? (p.pid_always != 0)
-                                       : (100 * ((int)alen - (int)nm) >= __ldg(p.t_pid + alen));   // snps.py:148
-          hk = hk && (int)mq >= p.mapq;                                                             // snps.py:154
-          hk = hk && (int)alen >= __ldg(p.t_cov + lq);                                              // snps.py:157
-          if (owner) ++my_aligned;                                                                  // snps.py:143
-          needq = hk && (ovl || owner);
-        }
-        const int rel = (int)(loc >> 5) - (int)tcol;                      // start column, in [-W, NCOL)
-        {  // s_first[x] = first row of this round whose start column + (W-1) >= x
-          const int kmax = NCOL + (int)W - 1;
-          int xi = rel + (int)W - 1;
-          xi = xi < 0 ? 0 : (xi > kmax ? kmax : xi);
-          int xlo = 0;
-          if (i > 0) {
-            int xp = (int)(prev_loc >> 5) - (int)tcol + (int)W - 1;
-            xp = xp < 0 ? 0 : (xp > kmax ? kmax : xp);
-            xlo = xp + 1;
-          }
-          for (int x = xlo; x <= xi; ++x) s_first[x] = (uint32_t)i;
-          if (i == n - 1)
-            for (int x = xi + 1; x <= kmax + 1; ++x) s_first[x] = (uint32_t)n;
-        }
-        // query bit planes, 32 bases per word: low / high bit of the base code, countable mask
-        // (query word w lives at index w + 1; index 0 is "word -1", zero until the planes are slid)
-        // (words 1..WT are all written by the conversion below; the planes are only read under `keep`)
-        uint32_t ql[WT + 2], qh[WT + 2], qv[WT + 2];
-        ql[0] = 0; qh[0] = 0; qv[0] = 0;
-        ql[WT + 1] = 0; qh[WT + 1] = 0; qv[WT + 1] = 0;
-        const uint32_t slot0 = s_mod[(int)tb + rel + (int)W];
-        uint4* __restrict__ dst = s_rows + (uint32_t)i * W;
-        bool keep = false, placed = false;
-        if (needq) {
-          uint32_t pc[NQ];
-#pragma unroll
-          for (int k = 0; k < NQ; ++k) pc[k] = 0;
-          // one 32-base block -> query word w of the three planes
-          auto convert = [&](const int w, const uint32_t* __restrict__ blk) {
-            // Phred >= baseq, bit-sliced over 32 bases: from the low bit up, "greater or equal so far"
-            uint32_t ge = 0xffffffffu;
-#pragma unroll
-            for (int k = 0; k < NQ; ++k) {
-              const uint32_t pk = blk[3 + k];
-              // threshold bit set: ge &= plane, clear: ge |= plane - one LOP3 (lut 0xD4 = c ? a & b : a | b)
-              asm("lop3.b32 %0, %1, %0, %2, 0xD4;" : "+r"(ge) : "r"(pk), "r"(tmk[k]));
-              pc[k] += __popc(pk);
-            }
-            ql[w + 1] = blk[0];
-            qh[w + 1] = blk[1];
-            qv[w + 1] = blk[2] & ge & q_allow;
-          };
-          constexpr bool LD256 = WT <= 8 && !(VAR & 1);
-          if (LD256) {
-            // the whole read at once: ceil(9 W / 8) independent 256-bit loads; the units of the 32 reads of a
-            // group are interleaved, so the lanes of a warp (consecutive reads) read consecutive sectors
-            constexpr int NV8 = (WT * NP + 7) / 8;
-            const uint32_t nv8 = (((lq + 31u) >> 5) * (uint32_t)NP + 7u) >> 3;
-            const uint32_t* __restrict__ vp = p.planes + (size_t)b0 * 8;
-            uint32_t raw_ld[TMA ? 1 : 8 * NV8];
-            if (!TMA) {
-#pragma unroll
-              for (int u = 0; u < NV8; ++u) {
-                // every read has a block, i.e. at least NP > 8 words: its first two units always exist; units
-                // past the read's end come from one shared all-zero unit (no predicated loads, no zeroed defaults)
-                ldg256((u < 2 || (uint32_t)u < nv8) ? vp + 8 * MB_GROUP * u : p.zero_unit, raw_ld + 8 * u);
-              }
-            }
-            const uint32_t* __restrict__ raw = TMA ? raw_in : raw_ld;   // TMA: already copied out of the warp's slot
-#pragma unroll
-            for (int bl = 0; bl < WT; ++bl) convert(bl, raw + bl * NP);
-          } else {
-            // wide rows: steps of four blocks = NP independent 128-bit loads
-            const uint32_t nvec = (((lq + 31u) >> 5) * (uint32_t)NP + 3u) >> 2;
-            const uint32_t* __restrict__ vp = p.planes + (size_t)b0 * 8;
-#pragma unroll
-            for (int s4 = 0; s4 < WT; s4 += 4) {
-              const int nb = WT - s4 < 4 ? WT - s4 : 4;
-              const int nv = (nb * NP + 3) / 4;
-              uint32_t raw[4 * NP];
-#pragma unroll
-              for (int u = 0; u < NP; ++u) {
-                uint4 t = make_uint4(0, 0, 0, 0);
-                const int v = s4 / 4 * NP + u;                    // 16-byte half of unit v / 2
-                if (u < nv && (uint32_t)v < nvec)
-                  t = __ldg(reinterpret_cast<const uint4*>(vp + (size_t)(v >> 1) * (8 * MB_GROUP)) + (v & 1));
-                raw[4 * u] = t.x; raw[4 * u + 1] = t.y; raw[4 * u + 2] = t.z; raw[4 * u + 3] = t.w;
-              }
-#pragma unroll
-              for (int bl = 0; bl < 4; ++bl)
-                if (bl < nb) convert(s4 + bl, raw + bl * NP);
-            }
-          }
-          // mean-quality filter (snps.py:151): mean(q) < readq  <=>  sum(q) < readq * l_qseq (exact)
-          uint32_t qsum = 0;
-#pragma unroll
-          for (int k = 0; k < NQ; ++k) qsum += pc[k] << k;
-          keep = qsum >= p.readq_eff * lq;
-          if (keep && owner) ++my_mapped;                                    // snps.py:161
-        // ---- CIGAR: every M/=/X run is one funnel-shifted copy of the query planes. Query bit q of a run
-        // (q0, x0) lies at row bit q - dq with dq = q0 - o - x0 = 32 d + sh, sh in [1, 32]: row word j is
-        // query words (j + d, j + d + 1) funnel-shifted by sh; d is -1 for every read that is not heavily
-        // clipped, other d first slide the planes by whole words so that the per-word code is static.
-        if (keep && ovl) {
+    // ---- placement + row store of one read whose query planes are converted (ql / qh / qv: query word w at index
+    // w + 1, indices 0 and WT + 1 zero); every class of read
+    auto place_store = [&](uint32_t (&ql)[WT + 2], uint32_t (&qh)[WT + 2], uint32_t (&qv)[WT + 2], const uint32_t loc,
+                           const uint32_t qstart, const uint32_t lq, const uint32_t span, const uint32_t cw,
+                           const uint32_t fl, const int i) {
+          const int rel = (int)(loc >> 5) - (int)tcol;
+          const uint32_t slot0 = s_mod[(int)tb + rel + (int)W];
+          uint4* __restrict__ dst = s_rows + (uint32_t)i * W;
           uint32_t rl[WT], rh[WT], rv[WT];
           const int o = (int)(loc & 31u);
           const bool simple = (fl & MB_RF_SIMPLE) != 0;
@@ -573,8 +468,165 @@ __global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : 2) k_pi
             dst[slot] = make_uint4(rv[j] & ~rh[j] & ~rl[j], rv[j] & ~rh[j] & rl[j], rv[j] & rh[j] & ~rl[j],
                                    rv[j] & rh[j] & rl[j]);
           }
-          placed = true;
+    };
+
+    // ---- STAGE of one read (row i of a round of n rows): header filters (snps.py:148,154,157), row index
+    // table, the read's bit planes, bit-sliced base-quality test, mean-quality filter, CIGAR placement, row store
+    auto stage_one = [&](const int i, const int n, const uint4 h, const uint32_t b0, const uint32_t cw,
+                         const uint32_t prev_loc, const uint32_t* __restrict__ raw_in, const bool defer_ok = false,
+                         const uint32_t row_mask = 0xffffffffu) {
+        const uint32_t loc = h.x, lq = h.y & 0xffffu, alen = h.y >> 16, qstart = h.z & 0xffffu, nm = h.z >> 16;
+        const uint32_t span = h.w & 0xffffu, mq = (h.w >> 16) & 0xffu, fl = (h.w >> 24) & 0x7fu;
+        bool needq = false, ovl = false, owner = false;
+        if (SORTED) {                              // classified before (bit 31 of the stashed header)
+          if (!(fl & MB_RF_LONG)) {
+            owner = loc >= ts;
+            ovl = span > 0 && loc + span > ts;
+            if (owner) ++my_aligned;                                                                // snps.py:143
+            needq = (h.w >> 31) != 0;
+          }
+        } else if (!(fl & MB_RF_LONG)) {
+          owner = loc >= ts;
+          ovl = span > 0 && loc + span > ts;
+          // exact integer forms of the two double-precision tests (tables built in ctx.cu)
+          bool hk = (fl & MB_RF_NMSAT) ? (p.pid_always != 0)
+                                       : (100 * ((int)alen - (int)nm) >= __ldg(p.t_pid + alen));   // snps.py:148
+          hk = hk && (int)mq >= p.mapq;                                                             // snps.py:154
+          hk = hk && (int)alen >= __ldg(p.t_cov + lq);                                              // snps.py:157
+          if (owner) ++my_aligned;                                                                  // snps.py:143
+          needq = hk && (ovl || owner);
         }
+        const int rel = (int)(loc >> 5) - (int)tcol;                      // start column, in [-W, NCOL)
+        {  // s_first[x] = first row of this round whose start column + (W-1) >= x
+          const int kmax = NCOL + (int)W - 1;
+          int xi = rel + (int)W - 1;
+          xi = xi < 0 ? 0 : (xi > kmax ? kmax : xi);
+          int xlo = 0;
+          if (i > 0) {
+            int xp = (int)(prev_loc >> 5) - (int)tcol + (int)W - 1;
+            xp = xp < 0 ? 0 : (xp > kmax ? kmax : xp);
+            xlo = xp + 1;
+          }
+          for (int x = xlo; x <= xi; ++x) s_first[x] = (uint32_t)i;
+          if (i == n - 1)
+            for (int x = xi + 1; x <= kmax + 1; ++x) s_first[x] = (uint32_t)n;
+        }
+        // query bit planes, 32 bases per word: low / high bit of the base code, countable mask
+        // (query word w lives at index w + 1; index 0 is "word -1", zero until the planes are slid)
+        // (words 1..WT are all written by the conversion below; the planes are only read under `keep`)
+        uint32_t ql[WT + 2], qh[WT + 2], qv[WT + 2];
+        ql[0] = 0; qh[0] = 0; qv[0] = 0;
+        ql[WT + 1] = 0; qh[WT + 1] = 0; qv[WT + 1] = 0;
+        const uint32_t slot0 = s_mod[(int)tb + rel + (int)W];
+        uint4* __restrict__ dst = s_rows + (uint32_t)i * W;
+        bool keep = false, placed = false;
+        if (needq) {
+          uint32_t pc[NQ];
+#pragma unroll
+          for (int k = 0; k < NQ; ++k) pc[k] = 0;
+          constexpr bool LD256 = WT <= 8 && !(VAR & 1);
+          // mean-quality filter (snps.py:151): mean(q) < readq  <=>  sum(q) < readq * l_qseq (exact). QUICK: the sum of
+          // the two top Phred planes alone is a lower bound of sum(q); for all but poor reads it already reaches the
+          // threshold and the four (five) lower planes need not be counted at all
+          constexpr bool QUICK = LD256;
+          const uint32_t q_thr = p.readq_eff * lq;
+          // one 32-base block -> query word w of the three planes
+          auto convert = [&](const int w, const uint32_t* __restrict__ blk) {
+            // Phred >= baseq, bit-sliced over 32 bases: from the low bit up, "greater or equal so far"
+            uint32_t ge = 0xffffffffu;
+#pragma unroll
+            for (int k = 0; k < NQ; ++k) {
+              const uint32_t pk = blk[3 + k];
+              // threshold bit set: ge &= plane, clear: ge |= plane - one LOP3 (lut 0xD4 = c ? a & b : a | b)
+              asm("lop3.b32 %0, %1, %0, %2, 0xD4;" : "+r"(ge) : "r"(pk), "r"(tmk[k]));
+              if (!QUICK || k >= NQ - 2) pc[k] += __popc(pk);          // QUICK: the two top planes first (below)
+            }
+            ql[w + 1] = blk[0];
+            qh[w + 1] = blk[1];
+            qv[w + 1] = blk[2] & ge & q_allow;
+          };
+          if (LD256) {
+            // the whole read at once: ceil(9 W / 8) independent 256-bit loads; the units of the 32 reads of a
+            // group are interleaved, so the lanes of a warp (consecutive reads) read consecutive sectors
+            constexpr int NV8 = (WT * NP + 7) / 8;
+            const uint32_t nv8 = (((lq + 31u) >> 5) * (uint32_t)NP + 7u) >> 3;
+            const uint32_t* __restrict__ vp = p.planes + (size_t)b0 * 8;
+            uint32_t raw_ld[TMA ? 1 : 8 * NV8];
+            if (!TMA) {
+#pragma unroll
+              for (int u = 0; u < NV8; ++u) {
+                // every read has a block, i.e. at least NP > 8 words: its first two units always exist; units
+                // past the read's end come from one shared all-zero unit (no predicated loads, no zeroed defaults)
+                ldg256((u < 2 || (uint32_t)u < nv8) ? vp + 8 * MB_GROUP * u : p.zero_unit, raw_ld + 8 * u);
+              }
+            }
+            const uint32_t* __restrict__ raw = TMA ? raw_in : raw_ld;   // TMA: already copied out of the warp's slot
+#pragma unroll
+            for (int bl = 0; bl < WT; ++bl) convert(bl, raw + bl * NP);
+            if (QUICK) {
+              keep = (pc[NQ - 1] << (NQ - 1)) + (pc[NQ - 2] << (NQ - 2)) >= q_thr;
+              if (!keep) {                                         // a poor read: the exact sum
+#pragma unroll
+                for (int bl = 0; bl < WT; ++bl)
+#pragma unroll
+                  for (int k = 0; k < NQ - 2; ++k) pc[k] += __popc(raw[bl * NP + 3 + k]);
+              }
+            }
+          } else {
+            // wide rows: steps of four blocks = NP independent 128-bit loads
+            const uint32_t nvec = (((lq + 31u) >> 5) * (uint32_t)NP + 3u) >> 2;
+            const uint32_t* __restrict__ vp = p.planes + (size_t)b0 * 8;
+#pragma unroll
+            for (int s4 = 0; s4 < WT; s4 += 4) {
+              const int nb = WT - s4 < 4 ? WT - s4 : 4;
+              const int nv = (nb * NP + 3) / 4;
+              uint32_t raw[4 * NP];
+#pragma unroll
+              for (int u = 0; u < NP; ++u) {
+                uint4 t = make_uint4(0, 0, 0, 0);
+                const int v = s4 / 4 * NP + u;                    // 16-byte half of unit v / 2
+                if (u < nv && (uint32_t)v < nvec)
+                  t = __ldg(reinterpret_cast<const uint4*>(vp + (size_t)(v >> 1) * (8 * MB_GROUP)) + (v & 1));
+                raw[4 * u] = t.x; raw[4 * u + 1] = t.y; raw[4 * u + 2] = t.z; raw[4 * u + 3] = t.w;
+              }
+#pragma unroll
+              for (int bl = 0; bl < 4; ++bl)
+                if (bl < nb) convert(s4 + bl, raw + bl * NP);
+            }
+          }
+          if (!keep) {
+            uint32_t qsum = 0;
+#pragma unroll
+            for (int k = 0; k < NQ; ++k) qsum += pc[k] << k;
+            keep = qsum >= q_thr;
+          }
+          if (keep && owner) ++my_mapped;                                    // snps.py:161
+        }
+        // ---- CIGAR: every M/=/X run is one funnel-shifted copy of the query planes. Query bit q of a run
+        // (q0, x0) lies at row bit q - dq with dq = q0 - o - x0 = 32 d + sh, sh in [1, 32]: row word j is
+        // query words (j + d, j + d + 1) funnel-shifted by sh; d is -1 for every read that is not heavily
+        // clipped, other d first slide the planes by whole words so that the per-word code is static.
+        bool now = keep && ovl;
+        if (DEFER && defer_ok) {
+          // the lanes of this warp that hold a read with an indel take consecutive entries of the warp's list (all
+          // lanes of the iteration meet here: row_mask names them)
+          const bool want = now && !(fl & MB_RF_SIMPLE);
+          const uint32_t dm = __ballot_sync(row_mask, want);
+          const uint32_t pos = wdefer + (uint32_t)__popc(dm & ((1u << lane) - 1u));
+          wdefer += (uint32_t)__popc(dm);
+          if (want && pos < (uint32_t)DCAP) {
+            uint32_t* e = s_defer + ((uint32_t)(tid >> 5) * DCAP + pos) * DWORDS;
+#pragma unroll
+            for (int w = 0; w < WT; ++w) { e[w] = ql[w + 1]; e[WT + w] = qh[w + 1]; e[2 * WT + w] = qv[w + 1]; }
+            e[3 * WT] = h.x; e[3 * WT + 1] = h.y; e[3 * WT + 2] = h.z; e[3 * WT + 3] = h.w;
+            e[3 * WT + 4] = cw; e[3 * WT + 5] = (uint32_t)i;
+            now = false;
+            placed = true;
+          }
+        }
+        if (now) {
+          place_store(ql, qh, qv, loc, qstart, lq, span, cw, fl, i);
+          placed = true;
         }
         if (!placed) {                                          // filtered out, or not on this tile: an empty row
 #pragma unroll
@@ -768,7 +820,27 @@ __global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : 2) k_pi
           ncw = __ldg(&p.cplx[r + NT]);
           nprev = __ldg(&p.hdr[r + NT - 1].x);
         }
-        stage_one(i, n, h, b0, cw, prev_loc, nullptr);
+        // the lanes of my warp in this iteration: rows i - lane .. i - lane + 31 below n
+        const int left = n - (i - lane);
+        stage_one(i, n, h, b0, cw, prev_loc, nullptr, true, left >= 32 ? 0xffffffffu : ((1u << left) - 1u));
+      }
+      if (DEFER) {
+        // the reads this warp put off: one pass (their number rarely exceeds the lanes), all lanes in the indel code
+        __syncwarp();
+        const uint32_t nd = min(__shfl_sync(0xffffffffu, wdefer, 0), (uint32_t)DCAP);   // lane 0 was in every iteration
+        wdefer = 0;
+        for (uint32_t k = (uint32_t)lane; k < nd; k += 32) {
+          const uint32_t* e = s_defer + ((uint32_t)(tid >> 5) * DCAP + k) * DWORDS;
+          uint32_t ql[WT + 2], qh[WT + 2], qv[WT + 2];
+          ql[0] = 0; qh[0] = 0; qv[0] = 0;
+          ql[WT + 1] = 0; qh[WT + 1] = 0; qv[WT + 1] = 0;
+#pragma unroll
+          for (int w = 0; w < WT; ++w) { ql[w + 1] = e[w]; qh[w + 1] = e[WT + w]; qv[w + 1] = e[2 * WT + w]; }
+          const uint32_t hx = e[3 * WT], hy = e[3 * WT + 1], hz = e[3 * WT + 2], hw = e[3 * WT + 3];
+          place_store(ql, qh, qv, hx, hz & 0xffffu, hy & 0xffffu, hw & 0xffffu, e[3 * WT + 4], (hw >> 24) & 0x7fu,
+                      (int)e[3 * WT + 5]);
+        }
+        __syncwarp();
       }
       if (rb + p.rmax < r1) {   // the first read of my next round: requested now, in flight during COUNT
         const uint32_t nr = rb + p.rmax + (uint32_t)tid;
@@ -1056,7 +1128,7 @@ __global__ void __launch_bounds__(256) k_restat(const uint32_t* __restrict__ cou
 
 // the row widths (and Phred plane counts) the tile kernel is instantiated for; a batch runs at the smallest
 // width >= its row_words
-struct PileKernel { uint32_t W; void (*fn)(const PileParams); uint32_t kt; bool tma; bool sorted; };   // kt: positions per tile
+struct PileKernel { uint32_t W; void (*fn)(const PileParams); uint32_t kt; bool tma; bool sorted; bool defer = false; };   // kt: positions per tile
 PileKernel pick_kernel(uint32_t row_words, uint32_t q_planes, bool want_tma) {
 #define MB_PT(W, Q) {W, k_pileup_v2<W, Q, 4>, 2048, true, false}
   static const PileKernel t6[] = {MB_PT(3, 6), MB_PT(4, 6), MB_PT(5, 6), MB_PT(6, 6), MB_PT(7, 6), MB_PT(8, 6)};
@@ -1078,11 +1150,13 @@ PileKernel pick_kernel(uint32_t row_words, uint32_t q_planes, bool want_tma) {
                                    {6, k_pileup_v2<6, 6, 2>, 1024, false, false}, {6, k_pileup_v2<6, 6, 3>, 1024, false, false}};
   static const PileKernel kpf = {6, k_pileup_v2<6, 6, 8>, 2048, false, false};
   static const PileKernel kso = {6, k_pileup_v2<6, 6, 24>, 2048, false, true};
+  static const PileKernel kdf = {6, k_pileup_v2<6, 6, 40>, 2048, false, false, true};
   if (const char* e = getenv("MB_PILE_VAR")) {
     const long v = atol(e);
     if (v >= 0 && v < 4 && q_planes == 6 && row_words > 5 && row_words <= 6) return kx[v];
     if (v == 8 && q_planes == 6 && row_words > 5 && row_words <= 6) return kpf;
     if (v == 24 && q_planes == 6 && row_words > 5 && row_words <= 6) return kso;
+    if (v == 40 && q_planes == 6 && row_words > 5 && row_words <= 6) return kdf;
   }
   const PileKernel* k = q_planes == 6 ? k6 : k7;
   for (int i = 0; i < 9; ++i)
@@ -1091,9 +1165,12 @@ PileKernel pick_kernel(uint32_t row_words, uint32_t q_planes, bool want_tma) {
 }
 
 size_t sorted_smem_bytes(uint32_t rmax) { return (size_t)rmax * 18 + 4 * ((size_t)(rmax >> 5) + 4) + 32; }
-size_t pile_smem_bytes(uint32_t W, uint32_t rmax, uint32_t ncol, uint32_t slot_units, uint32_t n_warps, bool sorted) {
+size_t defer_smem_bytes(uint32_t W, uint32_t n_warps) { return (size_t)n_warps * 16 * (3 * W + 6) * 4; }
+size_t pile_smem_bytes(uint32_t W, uint32_t rmax, uint32_t ncol, uint32_t slot_units, uint32_t n_warps, bool sorted,
+                       bool defer) {
   return sizeof(uint4) * ((size_t)VCL * ncol + ((size_t)rmax + 1) * W)     // + the empty padding row
          + (slot_units ? (size_t)n_warps * slot_units * 1024 : 0) + 32     // TMA: one slot per warp; a zero unit
+         + (defer ? defer_smem_bytes(W, n_warps) : 0)                      // DEFER: the warps' lists of put-off reads
          + (sorted ? sorted_smem_bytes(rmax) : 0);                         // SORTED: header stash, order, group offsets
 }
 
@@ -1164,9 +1241,10 @@ extern "C" int mb_snps_pileup_dev(mb_ctx* ctx, const mb_dev_reads* reads, const 
     if (rmax == 0) return mb::fail(MB_EINVAL, "mb_snps_pileup_dev: no shared memory left for rows (W=%u)", W);
   } else if (kern.sorted) {
     rmax = 3u * NT;                                                              // KMAX rows per thread
-    while (rmax > NT && pile_smem_bytes(W, rmax, NCOL, 0, NT / 32, true) > ctx->pile_smem) rmax -= NT;
+    while (rmax > NT && pile_smem_bytes(W, rmax, NCOL, 0, NT / 32, true, false) > ctx->pile_smem) rmax -= NT;
   } else {
-    rmax = (uint32_t)((ctx->pile_smem - fixed) / (sizeof(uint4) * W)) - 1u;   // one row is the empty padding row
+    const size_t extra = 32 + (kern.defer ? defer_smem_bytes(W, NT / 32) : 0);
+    rmax = (uint32_t)((ctx->pile_smem - fixed - extra) / (sizeof(uint4) * W)) - 1u;   // one row is the empty padding row
     if (rmax > (uint32_t)LANE_ROWS_MAX * KSUB) rmax = LANE_ROWS_MAX * KSUB;
     if (rmax >= 2u * NT && !getenv("MB_PILE_RAGGED")) rmax = rmax / NT * NT;   // the same number of reads for every thread
     rmax &= ~7u;
@@ -1224,7 +1302,7 @@ extern "C" int mb_snps_pileup_dev(mb_ctx* ctx, const mb_dev_reads* reads, const 
   p.n_species = ns;
   const uint32_t grid = min(n_ktiles, (uint32_t)(ctx->sm_count * ctx->pile_occ));
   { int trc = mb::timing_begin(ctx); if (trc) return trc; }
-  kern.fn<<<grid, NT, pile_smem_bytes(W, rmax, NCOL, slot_units, NT / 32, kern.sorted), st>>>(p);
+  kern.fn<<<grid, NT, pile_smem_bytes(W, rmax, NCOL, slot_units, NT / 32, kern.sorted, kern.defer), st>>>(p);
   { int trc = mb::timing_end(ctx); if (trc) return trc; }
   ctx->launches++;
   if (reads->n_long) {

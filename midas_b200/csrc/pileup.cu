@@ -243,6 +243,10 @@ __global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : 2) k_pi
   __shared__ uint8_t s_mod[NCOL + 2 * WMAX + 1];                      // x % W for small x
   __shared__ __align__(8) unsigned long long s_mbar[NT / 32];         // TMA: one per warp
   __shared__ uint32_t s_pf[4];                                         // PFL2: first read, last read, first unit, units
+  // the two filter tables for the lengths a row of W words can hold (a read that is staged has l_qseq <= 32 W)
+  constexpr int NTAB = 32 * WT + 1;
+  __shared__ int32_t s_tpid[NTAB], s_tcov[NTAB];
+  for (int i = threadIdx.x; i < NTAB; i += NT) { s_tpid[i] = p.t_pid[i]; s_tcov[i] = p.t_cov[i]; }
   // TMA: slot of warp w = slot_units x {32 lanes x 32 bytes}, as the group lies in HBM; then one all-zero unit
   uint32_t* const s_slots = reinterpret_cast<uint32_t*>(s_rows + ((size_t)p.rmax + 1) * W);
   uint32_t* const my_slot = s_slots + (size_t)(threadIdx.x >> 5) * p.slot_units * (8 * MB_GROUP);
@@ -490,9 +494,9 @@ __global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : 2) k_pi
           ovl = span > 0 && loc + span > ts;
           // exact integer forms of the two double-precision tests (tables built in ctx.cu)
           bool hk = (fl & MB_RF_NMSAT) ? (p.pid_always != 0)
-                                       : (100 * ((int)alen - (int)nm) >= __ldg(p.t_pid + alen));   // snps.py:148
+                                       : (100 * ((int)alen - (int)nm) >= s_tpid[alen]);   // snps.py:148
           hk = hk && (int)mq >= p.mapq;                                                             // snps.py:154
-          hk = hk && (int)alen >= __ldg(p.t_cov + lq);                                              // snps.py:157
+          hk = hk && (int)alen >= s_tcov[lq];                                              // snps.py:157
           if (owner) ++my_aligned;                                                                  // snps.py:143
           needq = hk && (ovl || owner);
         }
@@ -756,9 +760,9 @@ __global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : 2) k_pi
             if (!(fl & MB_RF_LONG)) {
               const bool owner = loc >= ts, ovl = span > 0 && loc + span > ts;
               bool hk = (fl & MB_RF_NMSAT) ? (p.pid_always != 0)
-                                           : (100 * ((int)alen - (int)nm) >= __ldg(p.t_pid + alen));   // snps.py:148
+                                           : (100 * ((int)alen - (int)nm) >= s_tpid[alen]);   // snps.py:148
               hk = hk && (int)mq >= p.mapq;                                                             // snps.py:154
-              hk = hk && (int)alen >= __ldg(p.t_cov + lq);                                              // snps.py:157
+              hk = hk && (int)alen >= s_tcov[lq];                                              // snps.py:157
               if (hk && (ovl || owner)) {
                 cls = (fl & MB_RF_SIMPLE) ? 0 : 1;
                 h.w |= 0x80000000u;

@@ -90,6 +90,12 @@ struct mb_ctx {
   size_t tile_rng_cap;
   const mb_dev_reads* rng_for;  // resident batch the tile index in tile_rng was built for (null: none)
   uint32_t rng_W, rng_ntiles;
+  // work units of the pileup kernel: (first position, positions) of every unit, per species region; rebuilt when the
+  // layout, the unit length or the kernel tile changes
+  uint2* units;
+  size_t units_cap;
+  uint64_t units_layout;
+  uint32_t units_len, n_units;
   uint32_t* sched;     // dynamic tile scheduler counters
   // exact integer thresholds of the two floating-point read filters, per alen / l_qseq (see ctx.cu)
   int32_t* ftab;       // device: [2][65536]

@@ -159,6 +159,11 @@ extern "C" int mb_ctx_create(int device, mb_ctx** out) {
   c->rng_for = nullptr;
   c->rng_W = 0;
   c->rng_ntiles = 0;
+  c->units = nullptr;
+  c->units_cap = 0;
+  c->units_layout = ~0ull;
+  c->units_len = 0;
+  c->n_units = 0;
   c->sched = nullptr;
   c->ftab = nullptr;
   c->ftab_valid = false;
@@ -213,6 +218,7 @@ extern "C" void mb_ctx_destroy(mb_ctx* c) {
   if (c->ovf) cudaFree(c->ovf);
   if (c->ovf_host) cudaFreeHost(c->ovf_host);
   if (c->tile_rng) cudaFree(c->tile_rng);
+  if (c->units) cudaFree(c->units);
   if (c->sched) cudaFree(c->sched);
   if (c->ftab) cudaFree(c->ftab);
   for (int i = 0; i < mb_ctx::kRing; ++i) {

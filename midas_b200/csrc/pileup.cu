@@ -38,6 +38,7 @@
 #include <cstdlib>
 #include <cmath>
 #include <algorithm>
+#include <type_traits>
 
 #include "common.h"
 
@@ -64,6 +65,7 @@ struct PileParams {
   const uint32_t* planes;     // bit-planar read data (mb_packed_reads), regions in 32-byte units
   const uint32_t* zero_unit;  // 32 bytes of zeros (the slack behind planes[]): what a load past a read's end fetches
   const uint32_t* tile_rng;   // [2 * n_ktiles]
+  const uint2* units;         // [n_ktiles] (first position, positions) of the work units ("tiles" of at most KT positions)
   const int32_t* tile_species;  // per MB_TILE tile
   uint32_t* counts;
   unsigned long long* stats;
@@ -85,6 +87,29 @@ struct PileParams {
   unsigned long long* mirror; // peer-memory copy of the stats rows (multi-GPU), written by the last CTA; or null
   uint32_t n_species;
 };
+
+// Phase clocks of the tile kernel (a separate build, `make prof`: -DMB_PROF): per CTA and warp, cycles spent in
+// STAGE / COUNT / EXPAND and at the barriers behind them, read back by mb_debug_prof (scripts/phase_prof.py)
+#ifdef MB_PROF
+constexpr int PROF_K = 8;                // 0 other, 1 stage, 2 wait after stage, 3 count, 4 wait after count, 5 expand, 6 start ns, 7 end ns
+constexpr int PROF_CTAS = 1024, PROF_WARPS = 8;
+__device__ unsigned long long g_prof[PROF_CTAS * PROF_WARPS * PROF_K];
+#define PROF_DECL __shared__ uint32_t s_prof[PROF_WARPS][PROF_K]; __shared__ uint32_t s_prof_t[PROF_WARPS];
+#define PROF_INIT do { if ((threadIdx.x & 31) == 0) { for (int k_ = 0; k_ < PROF_K; ++k_) s_prof[threadIdx.x >> 5][k_] = 0; \
+    s_prof_t[threadIdx.x >> 5] = (uint32_t)clock(); unsigned long long ns_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns_)); \
+    if (blockIdx.x < PROF_CTAS) g_prof[(blockIdx.x * PROF_WARPS + (threadIdx.x >> 5)) * PROF_K + 6] = ns_; } } while (0)
+#define PROF_MARK(k) do { if ((threadIdx.x & 31) == 0) { const uint32_t t_ = (uint32_t)clock(); \
+    s_prof[threadIdx.x >> 5][k] += t_ - s_prof_t[threadIdx.x >> 5]; s_prof_t[threadIdx.x >> 5] = t_; } } while (0)
+#define PROF_FINI do { if ((threadIdx.x & 31) == 0 && blockIdx.x < PROF_CTAS) { unsigned long long ns_; \
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns_)); \
+    unsigned long long* o_ = g_prof + (blockIdx.x * PROF_WARPS + (threadIdx.x >> 5)) * PROF_K; \
+    for (int k_ = 0; k_ < 6; ++k_) o_[k_] = s_prof[threadIdx.x >> 5][k_]; o_[7] = ns_; } } while (0)
+#else
+#define PROF_DECL
+#define PROF_INIT do {} while (0)
+#define PROF_MARK(k) do {} while (0)
+#define PROF_FINI do {} while (0)
+#endif
 
 __device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
 #pragma unroll
@@ -182,11 +207,13 @@ __device__ __forceinline__ uint32_t warp_lower_bound(const uint4* __restrict__ h
 }
 
 __global__ void __launch_bounds__(256) k_tile_ranges(const uint4* __restrict__ hdr, uint32_t n_reads, uint32_t back,
-                                                     uint32_t n_tiles, uint32_t kt, uint32_t* __restrict__ rng) {
+                                                     uint32_t n_tiles, const uint2* __restrict__ units,
+                                                     uint32_t* __restrict__ rng) {
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (t >= n_tiles) return;
-  const uint32_t ts = t * kt, te = ts + kt;
+  const uint2 un = units[t];
+  const uint32_t ts = un.x, te = ts + un.y;
   const uint32_t r0 = warp_lower_bound(hdr, 0u, n_reads, ts > back ? ts - back : 0u, lane);
   const uint32_t r1 = warp_lower_bound(hdr, r0, n_reads, te, lane);
   if (lane == 0) { rng[2 * t] = r0; rng[2 * t + 1] = r1; }
@@ -212,7 +239,7 @@ __global__ void __launch_bounds__(256) k_tile_ranges(const uint4* __restrict__ h
 // VAR: bit 0: 128-bit plane loads in steps of four blocks instead of 256-bit loads (experiment switch);
 //      bit 1: 1024-position tiles, 128 threads, 4 CTAs per SM instead of 2048 / 256 / 2
 template <int WT, int NQ, int VAR>
-__global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : 2) k_pileup_v2(const PileParams p) {
+__global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : ((VAR & 128) ? 3 : 2)) k_pileup_v2(const PileParams p) {
   constexpr int KT = (VAR & 2) ? 1024 : 2048;
   constexpr int NCOL = KT / 32;            // 32-position columns per tile
   constexpr int NT = NCOL * KSUB;          // threads per CTA
@@ -223,6 +250,8 @@ __global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : 2) k_pi
   constexpr int KMAX = 3;                       // SORTED: rows per thread and round (rmax <= KMAX * NT)
   constexpr bool DEFER = (VAR & 32) != 0;       // bit 5: reads with an indel are placed after the warp's simple ones (below)
   constexpr int DCAP = 16, DWORDS = 3 * WT + 6; // DEFER: entries per warp and round; words per entry
+  constexpr bool BAL = (VAR & 64) != 0;         // bit 6: COUNT deals the round's active columns over all threads (below)
+  constexpr int NLB = 10;                       // BAL: register counter levels of a lane (a round has < 1024 rows)
   extern __shared__ __align__(128) uint32_t smem[];
   constexpr uint32_t W = (uint32_t)WT;          // row words (compile time: every per-lane loop below unrolls)
   constexpr int NP = 3 + NQ;                    // words per 32-base block: seq lo, seq hi, candidate, Phred bits
@@ -243,6 +272,8 @@ __global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : 2) k_pi
   __shared__ uint8_t s_mod[NCOL + 2 * WMAX + 1];                      // x % W for small x
   __shared__ __align__(8) unsigned long long s_mbar[NT / 32];         // TMA: one per warp
   __shared__ uint32_t s_pf[4];                                         // PFL2: first read, last read, first unit, units
+  __shared__ uint32_t s_cr[2];                                         // BAL: first / past-the-last column the round's rows touch
+  __shared__ uint32_t s_colrows[NCOL];                                 // BAL: rows folded into a column since the last expansion
   // the two filter tables for the lengths a row of W words can hold (a read that is staged has l_qseq <= 32 W)
   constexpr int NTAB = 32 * WT + 1;
   __shared__ int32_t s_tpid[NTAB], s_tcov[NTAB];
@@ -268,10 +299,13 @@ __global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : 2) k_pi
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int col = tid >> 2, ksub = tid & 3;                           // COUNT role
+  PROF_DECL
+  PROF_INIT;
 
   for (int i = tid; i < VCL * NCOL; i += NT) s_vc[i] = make_uint4(0, 0, 0, 0);
   if (tid < (int)W) s_rows[p.rmax * W + tid] = make_uint4(0, 0, 0, 0);   // row rmax stays empty: COUNT reads it for padding
   for (int i = tid; i < NCOL + 2 * WMAX + 1; i += NT) s_mod[i] = (uint8_t)((uint32_t)i % W);
+  if (BAL && tid < NCOL) s_colrows[tid] = 0;
   if (TMA) {
     if (tid < NT / 32) mbar_init(&s_mbar[tid], 1);
     if (tid < 8) const_cast<uint32_t*>(s_zero)[tid] = 0;
@@ -288,7 +322,9 @@ __global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : 2) k_pi
     const uint32_t tile = s_tile;
     if (tile >= p.n_ktiles) break;
     if (tid == 0) next_tile = atomicAdd(p.sched, 1u);                 // its latency hides behind this tile's work
-    const uint32_t ts = tile * KT;
+    const uint2 unit = p.units[tile];
+    const uint32_t ts = unit.x;
+    const int ucol = (int)(unit.y >> 5);                                // columns of this unit (<= NCOL)
     const uint32_t r0 = p.tile_rng[2 * tile], r1 = p.tile_rng[2 * tile + 1];
     const uint32_t r0a = TMA ? (r0 & ~31u) : r0;                       // TMA: rounds start on a group boundary
     const uint32_t n_groups = r1 > r0a ? (r1 - r0a + 31u) >> 5 : 0u;   // (the leading reads end before the tile: empty rows)
@@ -315,12 +351,16 @@ __global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : 2) k_pi
 
     // transpose the shared vertical counters to u32 counts and write the tile (or add to it)
     auto expand = [&](const bool accumulate, const bool last) {
+      PROF_MARK(0);
       __syncthreads();
-      if (ksub == 0 && col_rows) atomicMax(&s_nmax, col_rows);
+      PROF_MARK(4);
+      if (BAL) {
+        if (tid < NCOL && s_colrows[tid]) atomicMax(&s_nmax, s_colrows[tid]);
+      } else if (ksub == 0 && col_rows) atomicMax(&s_nmax, col_rows);
       __syncthreads();
       const int nl = 32 - __clz(s_nmax);
       const int nlo = nl < 8 ? nl : 8;
-      for (int q = tid; q < KT / 4; q += NT) {
+      for (int q = tid; q < ucol * 8; q += NT) {
         const int c4 = q >> 3, sh = (q & 7) * 4;
         uint32_t lo[4] = {0, 0, 0, 0}, hi[4] = {0, 0, 0, 0};
         for (int l = 0; l < nlo; ++l) {
@@ -368,7 +408,9 @@ __global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : 2) k_pi
       __syncthreads();
       for (int i = tid; i < (nl < VCL ? nl + 1 : VCL) * NCOL; i += NT) s_vc[i] = make_uint4(0, 0, 0, 0);
       if (tid == 0) s_nmax = 0;
+      if (BAL && tid < NCOL) s_colrows[tid] = 0;
       col_rows = 0;
+      PROF_MARK(5);
     };
 
     // ---- placement + row store of one read whose query planes are converted (ql / qh / qv: query word w at index
@@ -514,6 +556,10 @@ __global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : 2) k_pi
           for (int x = xlo; x <= xi; ++x) s_first[x] = (uint32_t)i;
           if (i == n - 1)
             for (int x = xi + 1; x <= kmax + 1; ++x) s_first[x] = (uint32_t)n;
+          if (BAL) {   // rows are sorted by start: the first and the last row bound the columns of the round
+            if (i == 0) s_cr[0] = (uint32_t)max(rel, 0);
+            if (i == n - 1) s_cr[1] = (uint32_t)min(rel + (int)W, ucol);
+          }
         }
         // query bit planes, 32 bases per word: low / high bit of the base code, countable mask
         // (query word w lives at index w + 1; index 0 is "word -1", zero until the planes are slid)
@@ -658,7 +704,9 @@ __global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : 2) k_pi
         pass_rows = 0;
       }
       pass_rows += (uint32_t)n;
+      PROF_MARK(0);
       __syncthreads();
+      PROF_MARK(4);
       // ---- STAGE: one thread per read, everything in registers: header filters (snps.py:148,154,157),
       // row index table, the read's bit planes as independent 256-bit loads, bit-sliced base-quality test,
       // mean-quality filter, CIGAR placement, row store
@@ -859,7 +907,9 @@ __global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : 2) k_pi
       if (PFL2 && tid == 0) { s_pf[0] = pf_r0; s_pf[1] = pf_r1; s_pf[2] = pf_u0; s_pf[3] = pf_u1 > pf_u0 ? pf_u1 - pf_u0 : 0u; }
       }
       }
+      PROF_MARK(1);
       __syncthreads();
+      PROF_MARK(2);
       if (SORTED) {
         // my rows' headers of the coming round (this tile's next round or the next tile's first one): in flight
         // during COUNT; the class counters are free again
@@ -892,8 +942,86 @@ __global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : 2) k_pi
       // ---- COUNT: my column's rows of this round, KSUB-strided, 8 rows per carry-save tree into
       // bit-sliced register counters; then the KSUB lanes of a column are merged by a shuffle
       // butterfly of bit-sliced adders and lane ksub folds class ksub into the shared counters
-      {
-        const uint32_t lo = s_first[col], hi = s_first[col + (int)W];
+      if (BAL) {
+        // A round of rmax coordinate-sorted rows touches only part of the tile's columns (C2: ~27 of 64), so with a
+        // fixed thread -> column map most warps would idle through COUNT. Here the columns [c0, c1) the round touches
+        // are dealt over all threads: L = 4 NS lanes per column, lane = (class A/C/G/T, sub): a lane adds one class
+        // word of every NS-th row of its column with a 16-row carry-save tree; the NS partial counters are merged by
+        // a shuffle butterfly and sub 0 folds its class into the shared counters.
+        const uint32_t c0 = s_cr[0], c1 = s_cr[1];
+        const uint32_t nc = c1 > c0 ? c1 - c0 : 0u;
+        auto count_bal = [&](auto lns_tag) {
+          constexpr int LNS = decltype(lns_tag)::value, NS = 1 << LNS, L = 4 * NS;
+          const uint32_t cb = c0 + (uint32_t)(tid / L);
+          const bool act = cb < c1;
+          const uint32_t colb = act ? cb : c0;
+          const int cls = tid & 3, sub = (tid >> 2) & (NS - 1);
+          const uint32_t lo = act ? s_first[colb] : 0u, hi = act ? s_first[colb + W] : 0u;
+          if (!__any_sync(0xffffffffu, hi > lo)) return;
+          uint32_t cnt[NLB];
+#pragma unroll
+          for (int l = 0; l < NLB; ++l) cnt[l] = 0;
+          const uint32_t* __restrict__ base = reinterpret_cast<const uint32_t*>(s_rows + s_mod[tb + colb]) + cls;
+          auto add16 = [&](const uint32_t (&in)[16]) {
+            uint32_t t[8], f[4], g0, g1, e;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) CSA(cnt[0], t[k], cnt[0], in[2 * k], in[2 * k + 1]);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) CSA(cnt[1], f[k], cnt[1], t[2 * k], t[2 * k + 1]);
+            CSA(cnt[2], g0, cnt[2], f[0], f[1]);
+            CSA(cnt[2], g1, cnt[2], f[2], f[3]);
+            CSA(cnt[3], e, cnt[3], g0, g1);
+#pragma unroll
+            for (int l = 4; l < NLB; ++l) {
+              const uint32_t tt = cnt[l] & e;
+              cnt[l] ^= e;
+              e = tt;
+            }
+          };
+          uint32_t r = lo + (uint32_t)sub;
+          const uint32_t* __restrict__ rp = base + r * (W * 4);
+          for (; r + 15u * NS < hi; r += 16 * NS, rp += 16 * NS * (W * 4)) {      // whole batches: constant offsets
+            uint32_t in[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) in[u] = rp[u * NS * (int)(W * 4)];
+            add16(in);
+          }
+          if (r < hi) {                                                            // the last, partial batch
+            uint32_t in[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) in[u] = r + (uint32_t)(u * NS) < hi ? rp[u * NS * (int)(W * 4)] : 0u;
+            add16(in);
+          }
+#pragma unroll
+          for (int step = 0; step < LNS; ++step) {       // the sum over the subs is a round's row count at most: NLB levels hold it
+            uint32_t carry = 0;
+#pragma unroll
+            for (int l = 0; l < NLB; ++l) {
+              const uint32_t y = __shfl_xor_sync(0xffffffffu, cnt[l], 4 << step);
+              CSA(cnt[l], carry, cnt[l], y, carry);
+            }
+          }
+          const bool folder = act && sub == 0 && hi > lo;
+          if (folder && cls == 0) s_colrows[colb] += hi - lo;
+          uint32_t* vc = reinterpret_cast<uint32_t*>(s_vc) + colb * 4 + cls;
+          uint32_t carry = 0;
+#pragma unroll
+          for (int l = 0; l < VCL; ++l) {
+            if (l >= NLB && !__any_sync(0xffffffffu, folder && carry != 0)) break;
+            if (folder) {
+              const uint32_t a = vc[l * NCOL * 4];
+              uint32_t sum;
+              CSA(sum, carry, a, l < NLB ? cnt[l < NLB ? l : 0] : 0u, carry);
+              vc[l * NCOL * 4] = sum;
+            }
+          }
+        };
+        if (nc <= (uint32_t)(NT / 32)) count_bal(std::integral_constant<int, 3>());
+        else if (nc <= (uint32_t)(NT / 16)) count_bal(std::integral_constant<int, 2>());
+        else if (nc <= (uint32_t)(NT / 8)) count_bal(std::integral_constant<int, 1>());
+        else count_bal(std::integral_constant<int, 0>());
+      } else {
+        const uint32_t lo = s_first[col], hi = col < ucol ? s_first[col + (int)W] : lo;
         if (__any_sync(0xffffffffu, hi > lo)) {
           if (ksub == 0) col_rows += hi - lo;
           uint32_t cnt[4][XLEV];
@@ -959,6 +1087,7 @@ __global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : 2) k_pi
           }
         }
       }
+      PROF_MARK(3);
     }
     expand(accumulate, true);
 
@@ -976,11 +1105,13 @@ __global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : 2) k_pi
     }
     __syncthreads();
     if (tid < 4) {
-      const int sp = p.tile_species[tile / (MB_TILE / KT)];
+      const int sp = p.tile_species[ts / MB_TILE];
       const unsigned long long v = s_red[tid];
       if (sp >= 0 && v && !(p.defer_restat && tid < 2)) atomicAdd(&p.stats[5 * sp + 1 + tid], v);
     }
   }
+  PROF_MARK(0);
+  PROF_FINI;
   // ---- multi-GPU: the last CTA to finish copies the finished stats rows into the peer buffer (e.g. rank 0's
   // table over NVLink), so gathering the per-species rows needs no collective
   if (p.mirror) {
@@ -1132,7 +1263,7 @@ __global__ void __launch_bounds__(256) k_restat(const uint32_t* __restrict__ cou
 
 // the row widths (and Phred plane counts) the tile kernel is instantiated for; a batch runs at the smallest
 // width >= its row_words
-struct PileKernel { uint32_t W; void (*fn)(const PileParams); uint32_t kt; bool tma; bool sorted; bool defer = false; };   // kt: positions per tile
+struct PileKernel { uint32_t W; void (*fn)(const PileParams); uint32_t kt; bool tma; bool sorted; bool defer = false; bool cta3 = false; };   // kt: positions per tile
 PileKernel pick_kernel(uint32_t row_words, uint32_t q_planes, bool want_tma) {
 #define MB_PT(W, Q) {W, k_pileup_v2<W, Q, 4>, 2048, true, false}
   static const PileKernel t6[] = {MB_PT(3, 6), MB_PT(4, 6), MB_PT(5, 6), MB_PT(6, 6), MB_PT(7, 6), MB_PT(8, 6)};
@@ -1143,7 +1274,7 @@ PileKernel pick_kernel(uint32_t row_words, uint32_t q_planes, bool want_tma) {
     for (int i = 0; i < 6; ++i)
       if (k[i].W >= row_words) return k[i];
   }
-#define MB_PK(W, Q) {W, k_pileup_v2<W, Q, 8>, 2048, false, false}
+#define MB_PK(W, Q) {W, k_pileup_v2<W, Q, 72>, 2048, false, false}
   static const PileKernel k6[] = {MB_PK(3, 6), MB_PK(4, 6), MB_PK(5, 6),  MB_PK(6, 6),  MB_PK(7, 6),
                                   MB_PK(8, 6), MB_PK(10, 6), MB_PK(12, 6), MB_PK(16, 6)};
   static const PileKernel k7[] = {MB_PK(3, 7), MB_PK(4, 7), MB_PK(5, 7),  MB_PK(6, 7),  MB_PK(7, 7),
@@ -1155,12 +1286,16 @@ PileKernel pick_kernel(uint32_t row_words, uint32_t q_planes, bool want_tma) {
   static const PileKernel kpf = {6, k_pileup_v2<6, 6, 8>, 2048, false, false};
   static const PileKernel kso = {6, k_pileup_v2<6, 6, 24>, 2048, false, true};
   static const PileKernel kdf = {6, k_pileup_v2<6, 6, 40>, 2048, false, false, true};
+  static const PileKernel kbl = {6, k_pileup_v2<6, 6, 72>, 2048, false, false};
+  static const PileKernel kb3 = {6, k_pileup_v2<6, 6, 200>, 2048, false, false, false, true};
   if (const char* e = getenv("MB_PILE_VAR")) {
     const long v = atol(e);
     if (v >= 0 && v < 4 && q_planes == 6 && row_words > 5 && row_words <= 6) return kx[v];
     if (v == 8 && q_planes == 6 && row_words > 5 && row_words <= 6) return kpf;
     if (v == 24 && q_planes == 6 && row_words > 5 && row_words <= 6) return kso;
     if (v == 40 && q_planes == 6 && row_words > 5 && row_words <= 6) return kdf;
+    if (v == 72 && q_planes == 6 && row_words > 5 && row_words <= 6) return kbl;
+    if (v == 200 && q_planes == 6 && row_words > 5 && row_words <= 6) return kb3;
   }
   const PileKernel* k = q_planes == 6 ? k6 : k7;
   for (int i = 0; i < 9; ++i)
@@ -1179,6 +1314,16 @@ size_t pile_smem_bytes(uint32_t W, uint32_t rmax, uint32_t ncol, uint32_t slot_u
 }
 
 }  // namespace
+
+#ifdef MB_PROF
+extern "C" int mb_debug_prof(unsigned long long* out, size_t n_words) {
+  const size_t all = sizeof(g_prof) / sizeof(g_prof[0]);
+  if (!out || n_words > all) return MB_EINVAL;
+  MB_CUDA_TRY(cudaDeviceSynchronize());
+  MB_CUDA_TRY(cudaMemcpyFromSymbol(out, g_prof, n_words * sizeof(unsigned long long)));
+  return MB_OK;
+}
+#endif
 
 extern "C" int mb_snps_pileup_dev(mb_ctx* ctx, const mb_dev_reads* reads, const mb_layout* L, const mb_filters* f,
                                   uint32_t* counts_dev, mb_species_stats* stats_dev) {
@@ -1204,17 +1349,8 @@ extern "C" int mb_snps_pileup_dev(mb_ctx* ctx, const mb_dev_reads* reads, const 
   const PileKernel kern = pick_kernel(reads->row_words, reads->q_planes, want_tma);
   const uint32_t W = kern.W;                                          // instantiated row width >= row_words
   const uint32_t KT = kern.kt, NCOL = KT / 32, NT = NCOL * KSUB;
-  const uint32_t n_ktiles = L->n_tiles * (MB_TILE / KT);
-  if (ctx->tile_rng_cap < (size_t)2 * n_ktiles + 2) {
-    if (ctx->tile_rng) { MB_CUDA_TRY(cudaStreamSynchronize(ctx->stream)); MB_CUDA_TRY(cudaFree(ctx->tile_rng)); }
-    ctx->tile_rng = nullptr;
-    ctx->tile_rng_cap = 0;
-    ctx->rng_for = nullptr;
-    MB_CUDA_TRY(cudaMalloc(&ctx->tile_rng, sizeof(uint32_t) * ((size_t)2 * n_ktiles + 2)));
-    ctx->tile_rng_cap = (size_t)2 * n_ktiles + 2;
-  }
   {
-    size_t kb = (kern.tma || kern.sorted) ? 112 : (KT == 2048 ? 100 : 50);            // 2 / 4 CTAs per SM
+    size_t kb = (kern.tma || kern.sorted) ? 112 : (kern.cta3 ? 72 : (KT == 2048 ? 100 : 50));   // 2 / 3 / 4 CTAs per SM
     if (const char* e = getenv("MB_PILE_SMEM_KB")) { long v = atol(e); if (v >= 24 && v <= 220) kb = (size_t)v; }
     ctx->pile_smem = kb * 1024;
   }
@@ -1227,6 +1363,61 @@ extern "C" int mb_snps_pileup_dev(mb_ctx* ctx, const mb_dev_reads* reads, const 
     int occ = 0;
     MB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern.fn, NT, ctx->pile_smem));
     ctx->pile_occ = occ > 0 ? occ : 1;
+  }
+  // ---- work units. A unit is at most KT positions of one species region; the persistent grid takes them in genome
+  // order from an atomic counter. Phase clocks (profiles/r02r_phase.log) show the CTAs of a C2 launch finishing up to
+  // one unit time apart (6.6 units of 2048 positions per CTA, SMs differ in speed by a few per cent): 7-10 % of the
+  // CTA time idle at the tail. So the units get shorter towards the end of the genome - half length over the last
+  // 15 % of the positions, quarter length over the last 5 % - and the last claims are small. Shorter units stage more
+  // reads twice (those that straddle a boundary), which is why only the tail gets them. MB_PILE_UNIT overrides the
+  // (then uniform) length (tests, sweeps).
+  const uint32_t P = (uint32_t)(ctx->sm_count * ctx->pile_occ);
+  uint32_t unit_len = KT;
+  bool guided = L->gpad / KT > 2ull * P;
+  if (const char* e = getenv("MB_PILE_UNIT")) {
+    const long v = atol(e);
+    if (v >= 32 && v <= (long)KT && v % 32 == 0) { unit_len = (uint32_t)v; guided = false; }
+    if (v == 0) guided = false;
+  }
+  if (guided) unit_len |= 1u;                                    // cache key: the guided table of this tile length
+  if (ctx->units_layout != L->id || ctx->units_len != unit_len) {
+    std::vector<uint2> tab;
+    const uint32_t base_len = unit_len & ~31u;
+    const uint64_t half_from = guided ? L->gpad / 100 * 85 : L->gpad, quarter_from = guided ? L->gpad / 100 * 95 : L->gpad;
+    tab.reserve((size_t)(L->gpad / base_len + L->n_species + 16));
+    for (uint32_t sp = 0; sp < L->n_species; ++sp) {
+      const uint32_t end = L->species_goff[sp + 1];
+      for (uint32_t x = L->species_goff[sp]; x < end;) {
+        uint32_t len = x >= quarter_from ? base_len / 4 : (x >= half_from ? base_len / 2 : base_len);
+        len = std::max(32u, len & ~31u);
+        len = std::min(len, end - x);
+        tab.push_back(make_uint2(x, len));
+        x += len;
+      }
+    }
+    MB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));            // a launch in flight may still read the old table
+    if (ctx->units_cap < tab.size() + 1) {
+      if (ctx->units) MB_CUDA_TRY(cudaFree(ctx->units));
+      ctx->units = nullptr;
+      ctx->units_cap = 0;
+      MB_CUDA_TRY(cudaMalloc(&ctx->units, sizeof(uint2) * (tab.size() + 1)));
+      ctx->units_cap = tab.size() + 1;
+    }
+    if (!tab.empty())
+      MB_CUDA_TRY(cudaMemcpy(ctx->units, tab.data(), sizeof(uint2) * tab.size(), cudaMemcpyHostToDevice));
+    ctx->units_layout = L->id;
+    ctx->units_len = unit_len;
+    ctx->n_units = (uint32_t)tab.size();
+    ctx->rng_for = nullptr;
+  }
+  const uint32_t n_ktiles = ctx->n_units;
+  if (ctx->tile_rng_cap < (size_t)2 * n_ktiles + 2) {
+    if (ctx->tile_rng) { MB_CUDA_TRY(cudaStreamSynchronize(ctx->stream)); MB_CUDA_TRY(cudaFree(ctx->tile_rng)); }
+    ctx->tile_rng = nullptr;
+    ctx->tile_rng_cap = 0;
+    ctx->rng_for = nullptr;
+    MB_CUDA_TRY(cudaMalloc(&ctx->tile_rng, sizeof(uint32_t) * ((size_t)2 * n_ktiles + 2)));
+    ctx->tile_rng_cap = (size_t)2 * n_ktiles + 2;
   }
   const size_t fixed = sizeof(uint4) * (size_t)VCL * NCOL;
   uint32_t rmax, slot_units = 0;
@@ -1270,7 +1461,7 @@ extern "C" int mb_snps_pileup_dev(mb_ctx* ctx, const mb_dev_reads* reads, const 
   // the tile -> read-range index depends only on the resident batch: built once per (batch, row width)
   if (ctx->rng_for != reads || ctx->rng_W != W || ctx->rng_ntiles != n_ktiles) {
     k_tile_ranges<<<(n_ktiles + 7) / 8, 256, 0, st>>>(reinterpret_cast<const uint4*>(reads->hdr),
-                                                          (uint32_t)reads->n_reads, 32u * W, n_ktiles, KT, ctx->tile_rng);
+                                                          (uint32_t)reads->n_reads, 32u * W, n_ktiles, ctx->units, ctx->tile_rng);
     ctx->launches++;
     ctx->rng_for = reads;
     ctx->rng_W = W;
@@ -1284,6 +1475,7 @@ extern "C" int mb_snps_pileup_dev(mb_ctx* ctx, const mb_dev_reads* reads, const 
   p.planes = reads->planes;
   p.zero_unit = reads->planes + (size_t)reads->n_vec * 8;       // upload_reads keeps 256 zero bytes behind every array
   p.tile_rng = ctx->tile_rng;
+  p.units = ctx->units;
   p.tile_species = dl.tile_species;
   p.counts = counts_dev;
   p.stats = reinterpret_cast<unsigned long long*>(stats_dev);
@@ -1304,7 +1496,7 @@ extern "C" int mb_snps_pileup_dev(mb_ctx* ctx, const mb_dev_reads* reads, const 
   p.ovf = ctx->ovf;
   p.mirror = reads->n_long ? nullptr : reinterpret_cast<unsigned long long*>(ctx->stats_mirror);
   p.n_species = ns;
-  const uint32_t grid = min(n_ktiles, (uint32_t)(ctx->sm_count * ctx->pile_occ));
+  const uint32_t grid = min(n_ktiles, P);
   { int trc = mb::timing_begin(ctx); if (trc) return trc; }
   kern.fn<<<grid, NT, pile_smem_bytes(W, rmax, NCOL, slot_units, NT / 32, kern.sorted, kern.defer), st>>>(p);
   { int trc = mb::timing_end(ctx); if (trc) return trc; }

@@ -15,7 +15,8 @@ import numpy as np
 from .soa import CFilters, Filters, PlainReads, RefSet
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmidas_b200.so")
+# MB_LIB_PATH: another build of the same library (the phase-clock build of `make prof`), for scripts/phase_prof.py
+LIB_PATH = os.environ.get("MB_LIB_PATH") or os.path.join(_HERE, "libmidas_b200.so")
 
 MB_TILE = 4096
 MB_BLOCK = 32

@@ -87,6 +87,34 @@ def test_random_cigars(ctx, seed, n_species, cps, lo, hi, n_reads, max_len):
         _check(ctx, ref, reads, filters)
 
 
+@pytest.mark.parametrize("unit", [32, 96, 480, 1056, 1952])
+def test_work_unit_lengths(ctx, monkeypatch, unit):
+    """The kernel's work units are any multiple of 32 positions up to its tile (the library shortens them so that
+    the units divide evenly over the persistent grid): every length gives the oracle's counts, reads that straddle a
+    unit boundary included, on single- and multi-species layouts with W = 6 and wider rows."""
+    import gen
+    monkeypatch.setenv("MB_PILE_UNIT", str(unit))
+    ref, reads = synth.synth_snps(seed=21, n_species=3, contigs_per_species=2, contig_len=7_000, n_reads=30_000,
+                                  read_len=150, len_jitter=0.3, abundance="lognormal")
+    _check(ctx, ref, reads, Filters())
+    rng = np.random.default_rng(300 + unit)
+    ref = gen.make_ref(rng, 2, 2, 3000, 9000)
+    reads = gen.random_reads(301 + unit, ref, 5000, max_len=300)
+    _check(ctx, ref, reads, Filters(mapid=0.0, aln_cov=0.0, readq=0, mapq=0, baseq=0))
+
+
+@pytest.mark.parametrize("var", ["8", "72", "200"])
+def test_count_variants(ctx, monkeypatch, var):
+    """The COUNT variants of the W = 6 instance (fixed column map, columns dealt over all threads, the latter at three
+    CTAs per SM) against the oracle, at two unit lengths."""
+    monkeypatch.setenv("MB_PILE_VAR", var)
+    ref, reads = synth.synth_snps(seed=22, n_species=2, contigs_per_species=1, contig_len=60_000, n_reads=120_000,
+                                  read_len=150, len_jitter=0.0, abundance="lognormal")
+    _check(ctx, ref, reads, Filters())
+    monkeypatch.setenv("MB_PILE_UNIT", "736")
+    _check(ctx, ref, reads, Filters())
+
+
 def test_unsorted_input_is_sorted_by_the_packer(ctx):
     import gen
     rng = np.random.default_rng(7)

@@ -132,6 +132,13 @@ __device__ __forceinline__ void ldg256(const uint32_t* __restrict__ p, uint32_t*
       : "l"(p));
 }
 
+// the same, pinned where it is written (the software pipeline issues it long before the data is used)
+__device__ __forceinline__ void ldg256_at(const uint32_t* __restrict__ p, uint32_t* r) {
+  asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "l"(p));
+}
+
 // ---- asynchronous staging (VAR & 4): one bulk copy (TMA, UBLKCP) per warp and group, completion on an mbarrier
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
@@ -251,6 +258,7 @@ __global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : ((VAR &
   constexpr bool DEFER = (VAR & 32) != 0;       // bit 5: reads with an indel are placed after the warp's simple ones (below)
   constexpr int DCAP = 16, DWORDS = 3 * WT + 6; // DEFER: entries per warp and round; words per entry
   constexpr bool BAL = (VAR & 64) != 0;         // bit 6: COUNT deals the round's active columns over all threads (below)
+  constexpr bool PIPE = (VAR & 256) != 0 && WT <= 8;   // bit 8: a thread's plane loads run one row ahead of its placement (below)
   constexpr int NLB = 10;                       // BAL: register counter levels of a lane (a round has < 1024 rows)
   extern __shared__ __align__(128) uint32_t smem[];
   constexpr uint32_t W = (uint32_t)WT;          // row words (compile time: every per-lane loop below unrolls)
@@ -688,6 +696,11 @@ __global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : ((VAR &
     bool accumulate = false;
     uint4 nh = make_uint4(0, 0, 0, 0);                         // header, block offset, run word and predecessor
     uint32_t nb0 = 0, ncw = 0, nprev = 0;                       // of this thread's next read: one step ahead
+    // PIPE: the planes of my next row, first / second half of its 32-byte units; whether the first half of my first
+    // row of the coming round is already on its way
+    constexpr int PV8 = (WT * NP + 7) / 8, PVA = (PV8 + 1) / 2, PVB = PV8 - PVA;
+    uint32_t rawA[PIPE ? 8 * PVA : 1], rawB[PIPE ? 8 * PVB : 1];
+    bool pre_ok = false;
     if (TMA) {                                                  // my read of the warp's first group of this tile
       const uint32_t rf = r0a + 32u * (uint32_t)(tid >> 5) + (uint32_t)lane;
       if ((uint32_t)(tid >> 5) < n_groups && rf < r1) {
@@ -763,8 +776,8 @@ __global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : ((VAR &
           if (i < n) stage_one(i, n, h_cur, 0u, cw_cur, prev_cur, raw);
         }
       } else {
-      uint32_t pf_r0 = 0, pf_r1 = 0, pf_u0 = 0, pf_u1 = 0;
       if ((PFL2 || SORTED) && tid == 0) {
+        uint32_t pf_r0 = 0, pf_r1 = 0, pf_u0 = 0, pf_u1 = 0;
         // the reads of the next round (or of the next tile's first round) and their unit range: asked for now,
         // needed when this round's STAGE ends
         pf_r0 = rb + p.rmax;
@@ -780,6 +793,8 @@ __global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : ((VAR &
           pf_u0 = __ldg(&p.vec_off[pf_r0 & ~31u]);
           pf_u1 = __ldg(&p.vec_off[min((pf_r1 + 31u) & ~31u, p.n_reads)]);
         }
+        // (the readers of the previous round's values are past the barrier above)
+        s_pf[0] = pf_r0; s_pf[1] = pf_r1; s_pf[2] = pf_u0; s_pf[3] = pf_u1 > pf_u0 ? pf_u1 - pf_u0 : 0u;
       }
       if (SORTED) {
         // ---- phase A: my rows' headers (requested before the previous COUNT) are classified - simple (one run),
@@ -851,7 +866,147 @@ __global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : ((VAR &
           const uint32_t cw = ((h.w >> 24) & MB_RF_SIMPLE) ? 0xffffffffu : __ldg(&p.cplx[r]);
           stage_one(i, n, h, b0, cw, i > 0 ? s_hdr[i - 1].x : 0u, nullptr);
         }
-        if (tid == 0) { s_pf[0] = pf_r0; s_pf[1] = pf_r1; s_pf[2] = pf_u0; s_pf[3] = pf_u1 > pf_u0 ? pf_u1 - pf_u0 : 0u; }
+      } else {
+      if (PIPE) {
+        // ---- software pipeline over my rows. Per row: header -> filters -> plane loads -> conversion -> placement.
+        // The warps of a CTA leave the barrier together, so without this they all wait for their plane loads at the
+        // same moment (23 % of the warp time in profiles/r02t_k_pileup_v2_bal.txt). Here the first half of the next
+        // row's units is requested before the current row is placed (the registers of the converted row's raw words
+        // are free by then), the second half when its turn starts (in flight while the first three blocks are
+        // converted), and the first row of the coming round before COUNT.
+#define MB_RAWW(w) ((w) < 8 * PVA ? rawA[(w) < 8 * PVA ? (w) : 0] : rawB[(w) >= 8 * PVA ? (w) - 8 * PVA : 0])
+        auto filt = [&](const uint4 h, bool& needq, bool& ovl, bool& owner) {
+          const uint32_t loc = h.x, lq = h.y & 0xffffu, alen = h.y >> 16, nm = h.z >> 16;
+          const uint32_t span = h.w & 0xffffu, mq = (h.w >> 16) & 0xffu, fl = (h.w >> 24) & 0x7fu;
+          needq = false; ovl = false; owner = false;
+          if (!(fl & MB_RF_LONG)) {
+            owner = loc >= ts;
+            ovl = span > 0 && loc + span > ts;
+            bool hk = (fl & MB_RF_NMSAT) ? (p.pid_always != 0)
+                                         : (100 * ((int)alen - (int)nm) >= s_tpid[alen]);   // snps.py:148
+            hk = hk && (int)mq >= p.mapq;                                                             // snps.py:154
+            hk = hk && (int)alen >= s_tcov[lq];                                                      // snps.py:157
+            needq = hk && (ovl || owner);
+          }
+        };
+        auto issue = [&](const bool second, const uint4 h, const uint32_t b0, const bool needq) {
+          if (!needq) return;
+          const uint32_t nv8 = ((((h.y & 0xffffu) + 31u) >> 5) * (uint32_t)NP + 7u) >> 3;
+          const uint32_t* __restrict__ vp = p.planes + (size_t)b0 * 8;
+          if (!second) {
+#pragma unroll
+            for (int u = 0; u < PVA; ++u)
+              ldg256_at((u < 2 || (uint32_t)u < nv8) ? vp + 8 * MB_GROUP * u : p.zero_unit, rawA + 8 * u);
+          } else {
+#pragma unroll
+            for (int u = PVA; u < PV8; ++u)
+              ldg256_at((u < 2 || (uint32_t)u < nv8) ? vp + 8 * MB_GROUP * u : p.zero_unit, rawB + 8 * (u - PVA));
+          }
+        };
+        if (rb == r0) {                                        // first round of the unit: nothing is in flight yet
+          pre_ok = false;
+          nh = make_uint4(0, 0, 0, 0); nb0 = 0; ncw = 0; nprev = 0;
+          if (tid < n) {
+            nh = __ldg(&p.hdr[rb + tid]);
+            nb0 = __ldg(&p.vec_off[rb + tid]);
+            ncw = __ldg(&p.cplx[rb + tid]);
+            if (tid > 0) nprev = __ldg(&p.hdr[rb + tid - 1].x);
+          }
+        }
+        if (tid < n) {
+          int i = tid;
+          uint4 h = nh;
+          uint32_t b0 = nb0, cw = ncw, prev_loc = nprev;
+          bool needq, ovl, owner;
+          filt(h, needq, ovl, owner);
+          if (!pre_ok) issue(false, h, b0, needq);
+          for (;;) {
+            const uint32_t r = rb + (uint32_t)i;
+            // my next row: in this round, else my first row of the coming round
+            const bool more = i + NT < n;
+            const uint32_t rn = more ? r + NT : rb + p.rmax + (uint32_t)tid;
+            const bool hasn = more || (rb + p.rmax < r1 && rn < r1);
+            if (hasn) {
+              nh = __ldg(&p.hdr[rn]);
+              nb0 = __ldg(&p.vec_off[rn]);
+              ncw = __ldg(&p.cplx[rn]);
+              nprev = (more || tid > 0) ? __ldg(&p.hdr[rn - 1].x) : 0u;
+            }
+            issue(true, h, b0, needq);
+            const uint32_t loc = h.x, lq = h.y & 0xffffu, qstart = h.z & 0xffffu;
+            const uint32_t span = h.w & 0xffffu, fl = (h.w >> 24) & 0x7fu;
+            if (owner) ++my_aligned;                                                                  // snps.py:143
+            const int rel = (int)(loc >> 5) - (int)tcol;                      // start column, in [-W, NCOL)
+            {  // s_first[x] = first row of this round whose start column + (W-1) >= x
+              const int kmax = NCOL + (int)W - 1;
+              int xi = rel + (int)W - 1;
+              xi = xi < 0 ? 0 : (xi > kmax ? kmax : xi);
+              int xlo = 0;
+              if (i > 0) {
+                int xp = (int)(prev_loc >> 5) - (int)tcol + (int)W - 1;
+                xp = xp < 0 ? 0 : (xp > kmax ? kmax : xp);
+                xlo = xp + 1;
+              }
+              for (int x = xlo; x <= xi; ++x) s_first[x] = (uint32_t)i;
+              if (i == n - 1)
+                for (int x = xi + 1; x <= kmax + 1; ++x) s_first[x] = (uint32_t)n;
+              if (BAL) {
+                if (i == 0) s_cr[0] = (uint32_t)max(rel, 0);
+                if (i == n - 1) s_cr[1] = (uint32_t)min(rel + (int)W, ucol);
+              }
+            }
+            uint32_t ql[WT + 2], qh[WT + 2], qv[WT + 2];
+            ql[0] = 0; qh[0] = 0; qv[0] = 0;
+            ql[WT + 1] = 0; qh[WT + 1] = 0; qv[WT + 1] = 0;
+            bool keep = false;
+            if (needq) {
+              uint32_t pc1 = 0, pc2 = 0;                       // set bits of the two top Phred planes
+#pragma unroll
+              for (int bl = 0; bl < WT; ++bl) {
+                uint32_t ge = 0xffffffffu;                     // Phred >= baseq, bit-sliced over 32 bases (as in stage_one)
+#pragma unroll
+                for (int k = 0; k < NQ; ++k) {
+                  const uint32_t pk = MB_RAWW(bl * NP + 3 + k);
+                  asm("lop3.b32 %0, %1, %0, %2, 0xD4;" : "+r"(ge) : "r"(pk), "r"(tmk[k]));
+                  if (k == NQ - 1) pc1 += __popc(pk);
+                  if (k == NQ - 2) pc2 += __popc(pk);
+                }
+                ql[bl + 1] = MB_RAWW(bl * NP);
+                qh[bl + 1] = MB_RAWW(bl * NP + 1);
+                qv[bl + 1] = MB_RAWW(bl * NP + 2) & ge & q_allow;
+              }
+              // mean-quality filter (snps.py:151): the two top planes bound the sum from below, the exact sum otherwise
+              const uint32_t q_thr = p.readq_eff * lq;
+              uint32_t qsum = (pc1 << (NQ - 1)) + (pc2 << (NQ - 2));
+              keep = qsum >= q_thr;
+              if (!keep) {
+#pragma unroll
+                for (int bl = 0; bl < WT; ++bl)
+#pragma unroll
+                  for (int k = 0; k < NQ - 2; ++k) qsum += (uint32_t)__popc(MB_RAWW(bl * NP + 3 + k)) << k;
+                keep = qsum >= q_thr;
+              }
+              if (keep && owner) ++my_mapped;                                    // snps.py:161
+            }
+            bool needq_n = false, ovl_n = false, owner_n = false;
+            if (hasn) {
+              filt(nh, needq_n, ovl_n, owner_n);
+              issue(false, nh, nb0, needq_n);
+            }
+            if (keep && ovl) {
+              place_store(ql, qh, qv, loc, qstart, lq, span, cw, fl, i);
+            } else {
+              uint4* __restrict__ dst = s_rows + (uint32_t)i * W;
+#pragma unroll
+              for (int j = 0; j < WT; ++j) dst[j] = make_uint4(0, 0, 0, 0);
+            }
+            if (!more) { pre_ok = hasn; break; }
+            i += NT;
+            h = nh; b0 = nb0; cw = ncw; prev_loc = nprev;
+            needq = needq_n; ovl = ovl_n; owner = owner_n;
+          }
+        }
+#undef MB_RAWW
       } else {
       if (rb == r0) {                                          // later rounds: requested before the previous COUNT
         nh = make_uint4(0, 0, 0, 0); nb0 = 0; ncw = 0; nprev = 0;
@@ -904,7 +1059,7 @@ __global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : ((VAR &
           if (tid > 0) nprev = __ldg(&p.hdr[nr - 1].x);
         }
       }
-      if (PFL2 && tid == 0) { s_pf[0] = pf_r0; s_pf[1] = pf_r1; s_pf[2] = pf_u0; s_pf[3] = pf_u1 > pf_u0 ? pf_u1 - pf_u0 : 0u; }
+      }
       }
       }
       PROF_MARK(1);
@@ -1288,6 +1443,8 @@ PileKernel pick_kernel(uint32_t row_words, uint32_t q_planes, bool want_tma) {
   static const PileKernel kdf = {6, k_pileup_v2<6, 6, 40>, 2048, false, false, true};
   static const PileKernel kbl = {6, k_pileup_v2<6, 6, 72>, 2048, false, false};
   static const PileKernel kb3 = {6, k_pileup_v2<6, 6, 200>, 2048, false, false, false, true};
+  static const PileKernel kpp = {6, k_pileup_v2<6, 6, 328>, 2048, false, false};
+  static const PileKernel kb1 = {6, k_pileup_v2<6, 6, 74>, 1024, false, false};
   if (const char* e = getenv("MB_PILE_VAR")) {
     const long v = atol(e);
     if (v >= 0 && v < 4 && q_planes == 6 && row_words > 5 && row_words <= 6) return kx[v];
@@ -1296,6 +1453,8 @@ PileKernel pick_kernel(uint32_t row_words, uint32_t q_planes, bool want_tma) {
     if (v == 40 && q_planes == 6 && row_words > 5 && row_words <= 6) return kdf;
     if (v == 72 && q_planes == 6 && row_words > 5 && row_words <= 6) return kbl;
     if (v == 200 && q_planes == 6 && row_words > 5 && row_words <= 6) return kb3;
+    if (v == 328 && q_planes == 6 && row_words > 5 && row_words <= 6) return kpp;
+    if (v == 74 && q_planes == 6 && row_words > 5 && row_words <= 6) return kb1;
   }
   const PileKernel* k = q_planes == 6 ? k6 : k7;
   for (int i = 0; i < 9; ++i)

@@ -84,7 +84,7 @@ struct mb_ctx {
   uint64_t launches;
   size_t pile_smem;   // dynamic shared memory per CTA of the pileup kernel (0 = not configured yet)
   int pile_occ;       // resident CTAs per SM at that size
-  uint32_t pile_attr_mask;  // row widths whose kernel instance already has its shared-memory attribute set
+  std::unordered_map<const void*, size_t> pile_attr;  // kernel instances whose shared-memory attribute is set, and to what
   // scratch (grown on demand)
   uint32_t* tile_rng;  // [2*n_tiles]
   size_t tile_rng_cap;

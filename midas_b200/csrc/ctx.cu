@@ -153,7 +153,6 @@ extern "C" int mb_ctx_create(int device, mb_ctx** out) {
   c->launches = 0;
   c->pile_smem = 0;
   c->pile_occ = 1;
-  c->pile_attr_mask = 0;
   c->tile_rng = nullptr;
   c->tile_rng_cap = 0;
   c->rng_for = nullptr;

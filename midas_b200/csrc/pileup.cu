@@ -132,13 +132,6 @@ __device__ __forceinline__ void ldg256(const uint32_t* __restrict__ p, uint32_t*
       : "l"(p));
 }
 
-// the same, pinned where it is written (the software pipeline issues it long before the data is used)
-__device__ __forceinline__ void ldg256_at(const uint32_t* __restrict__ p, uint32_t* r) {
-  asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-               : "l"(p));
-}
-
 // ---- asynchronous staging (VAR & 4): one bulk copy (TMA, UBLKCP) per warp and group, completion on an mbarrier
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
@@ -258,7 +251,11 @@ __global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : ((VAR &
   constexpr bool DEFER = (VAR & 32) != 0;       // bit 5: reads with an indel are placed after the warp's simple ones (below)
   constexpr int DCAP = 16, DWORDS = 3 * WT + 6; // DEFER: entries per warp and round; words per entry
   constexpr bool BAL = (VAR & 64) != 0;         // bit 6: COUNT deals the round's active columns over all threads (below)
-  constexpr bool PIPE = (VAR & 256) != 0 && WT <= 8;   // bit 8: a thread's plane loads run one row ahead of its placement (below)
+  constexpr bool BQ30 = (VAR & 512) != 0;       // bit 9: instance for baseq = 30, the CLI default (comparator below)
+  // bit 10: a row's plane loads are issued as soon as its header is there, before the header filters are evaluated
+  constexpr bool SPEC = (VAR & 1024) != 0 && WT <= 8 && !(VAR & 1) && !TMA && !SORTED;
+  // the next unit's table entries and my first header of it are requested during the current unit's last round
+  constexpr bool XU = PFL2 && !TMA && !SORTED;
   constexpr int NLB = 10;                       // BAL: register counter levels of a lane (a round has < 1024 rows)
   extern __shared__ __align__(128) uint32_t smem[];
   constexpr uint32_t W = (uint32_t)WT;          // row words (compile time: every per-lane loop below unrolls)
@@ -266,6 +263,7 @@ __global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : ((VAR &
   uint32_t tmk[NQ];                             // bit k of baseq, spread over a word (warp-uniform)
 #pragma unroll
   for (int k = 0; k < NQ; ++k) {
+    if (BQ30) { tmk[k] = 0; continue; }
     tmk[k] = ((p.baseq >> k) & 1u) ? 0xffffffffu : 0u;
     // kept as a plain register operand: seen as a known-uniform value the compiler turns every comparator
     // step into an AND plus a predicated OR (two instructions) instead of one three-input LOP3
@@ -280,6 +278,7 @@ __global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : ((VAR &
   __shared__ uint8_t s_mod[NCOL + 2 * WMAX + 1];                      // x % W for small x
   __shared__ __align__(8) unsigned long long s_mbar[NT / 32];         // TMA: one per warp
   __shared__ uint32_t s_pf[4];                                         // PFL2: first read, last read, first unit, units
+  __shared__ uint32_t s_nx[5];                                         // XU: the next unit (start, positions, reads r0, r1, its index)
   __shared__ uint32_t s_cr[2];                                         // BAL: first / past-the-last column the round's rows touch
   __shared__ uint32_t s_colrows[NCOL];                                 // BAL: rows folded into a column since the last expansion
   // the two filter tables for the lengths a row of W words can hold (a read that is staged has l_qseq <= 32 W)
@@ -321,7 +320,10 @@ __global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : ((VAR &
   }
 
   uint32_t next_tile = 0;                                             // thread 0: the tile after the current one
-  if (tid == 0) next_tile = atomicAdd(p.sched, 1u);
+  if (tid == 0) { next_tile = atomicAdd(p.sched, 1u); s_nx[4] = 0xffffffffu; }
+  uint4 nh = make_uint4(0, 0, 0, 0);                                  // header, block offset, run word and predecessor
+  uint32_t nb0 = 0, ncw = 0, nprev = 0;                                // of this thread's next read: one step ahead
+  uint32_t pre_tile = 0xffffffffu;                                     // XU: the unit they were requested for, if it is the next one
   for (;;) {
     __syncthreads();
     if (tid == 0) { s_tile = next_tile; s_nmax = 0; }
@@ -330,10 +332,19 @@ __global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : ((VAR &
     const uint32_t tile = s_tile;
     if (tile >= p.n_ktiles) break;
     if (tid == 0) next_tile = atomicAdd(p.sched, 1u);                 // its latency hides behind this tile's work
-    const uint2 unit = p.units[tile];
+    uint2 unit;
+    uint32_t r0, r1;
+    if (XU && s_nx[4] == tile) {                                        // published during the previous unit's last round
+      unit = make_uint2(s_nx[0], s_nx[1]);
+      r0 = s_nx[2];
+      r1 = s_nx[3];
+    } else {
+      unit = p.units[tile];
+      r0 = p.tile_rng[2 * tile];
+      r1 = p.tile_rng[2 * tile + 1];
+    }
     const uint32_t ts = unit.x;
     const int ucol = (int)(unit.y >> 5);                                // columns of this unit (<= NCOL)
-    const uint32_t r0 = p.tile_rng[2 * tile], r1 = p.tile_rng[2 * tile + 1];
     const uint32_t r0a = TMA ? (r0 & ~31u) : r0;                       // TMA: rounds start on a group boundary
     const uint32_t n_groups = r1 > r0a ? (r1 - r0a + 31u) >> 5 : 0u;   // (the leading reads end before the tile: empty rows)
     const uint32_t GR = p.rmax >> 5;                                   // groups per round
@@ -515,12 +526,15 @@ __global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : ((VAR &
               x0 += oplen;
             }
           }
+          // row word j lives in slot (slot0 + j) mod W: two bases, one compare per word
+          uint4* __restrict__ const dA = dst + slot0;
+          uint4* __restrict__ const dB = dA - W;
+          const int wrap = (int)W - (int)slot0;                      // the first j that wraps
 #pragma unroll
           for (int j = 0; j < WT; ++j) {
-            uint32_t slot = slot0 + (uint32_t)j;
-            if (slot >= W) slot -= W;
-            dst[slot] = make_uint4(rv[j] & ~rh[j] & ~rl[j], rv[j] & ~rh[j] & rl[j], rv[j] & rh[j] & ~rl[j],
-                                   rv[j] & rh[j] & rl[j]);
+            uint4* __restrict__ const d = j < wrap ? dA : dB;
+            d[j] = make_uint4(rv[j] & ~rh[j] & ~rl[j], rv[j] & ~rh[j] & rl[j], rv[j] & rh[j] & ~rl[j],
+                              rv[j] & rh[j] & rl[j]);
           }
     };
 
@@ -531,6 +545,17 @@ __global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : ((VAR &
                          const uint32_t row_mask = 0xffffffffu) {
         const uint32_t loc = h.x, lq = h.y & 0xffffu, alen = h.y >> 16, qstart = h.z & 0xffffu, nm = h.z >> 16;
         const uint32_t span = h.w & 0xffffu, mq = (h.w >> 16) & 0xffu, fl = (h.w >> 24) & 0x7fu;
+        constexpr int NV8S = (WT * NP + 7) / 8;
+        uint32_t raw_sp[SPEC ? 8 * NV8S : 1];
+        if (SPEC) {
+          // the loads do not wait for the filters (a filtered read's planes are fetched and dropped: the byte model of
+          // the kernel counts every read's planes anyway); the filter code and the index table run under their latency
+          const uint32_t nv8 = (((lq + 31u) >> 5) * (uint32_t)NP + 7u) >> 3;
+          const uint32_t* __restrict__ vp = p.planes + (size_t)b0 * 8;
+#pragma unroll
+          for (int u = 0; u < NV8S; ++u)
+            ldg256((u < 2 || (uint32_t)u < nv8) ? vp + 8 * MB_GROUP * u : p.zero_unit, raw_sp + 8 * u);
+        }
         bool needq = false, ovl = false, owner = false;
         if (SORTED) {                              // classified before (bit 31 of the stashed header)
           if (!(fl & MB_RF_LONG)) {
@@ -551,7 +576,9 @@ __global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : ((VAR &
           needq = hk && (ovl || owner);
         }
         const int rel = (int)(loc >> 5) - (int)tcol;                      // start column, in [-W, NCOL)
-        {  // s_first[x] = first row of this round whose start column + (W-1) >= x
+        // s_first[x] = first row of this round whose start column + (W-1) >= x. Rows are sorted by start: only a row
+        // that starts in a later 32-position column than its predecessor (or the first / last row) has entries to write
+        if (i == 0 || i == n - 1 || (loc >> 5) != (prev_loc >> 5)) {
           const int kmax = NCOL + (int)W - 1;
           int xi = rel + (int)W - 1;
           xi = xi < 0 ? 0 : (xi > kmax ? kmax : xi);
@@ -592,16 +619,27 @@ __global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : ((VAR &
           auto convert = [&](const int w, const uint32_t* __restrict__ blk) {
             // Phred >= baseq, bit-sliced over 32 bases: from the low bit up, "greater or equal so far"
             uint32_t ge = 0xffffffffu;
+            if (BQ30) {
+              // 30 = 0b011110: plane 0 cannot change an all-ones start, planes 1-4 are ANDed, the planes above ORed - two
+              // LOP3 per block instead of one per plane, no threshold registers
+              ge = blk[3 + 1] & blk[3 + 2] & blk[3 + 3] & blk[3 + 4];
 #pragma unroll
-            for (int k = 0; k < NQ; ++k) {
-              const uint32_t pk = blk[3 + k];
-              // threshold bit set: ge &= plane, clear: ge |= plane - one LOP3 (lut 0xD4 = c ? a & b : a | b)
-              asm("lop3.b32 %0, %1, %0, %2, 0xD4;" : "+r"(ge) : "r"(pk), "r"(tmk[k]));
-              if (!QUICK || k >= NQ - 2) pc[k] += __popc(pk);          // QUICK: the two top planes first (below)
+              for (int k = 5; k < NQ; ++k) ge |= blk[3 + k];
+#pragma unroll
+              for (int k = 0; k < NQ; ++k)
+                if (!QUICK || k >= NQ - 2) pc[k] += __popc(blk[3 + k]);
+            } else {
+#pragma unroll
+              for (int k = 0; k < NQ; ++k) {
+                const uint32_t pk = blk[3 + k];
+                // threshold bit set: ge &= plane, clear: ge |= plane - one LOP3 (lut 0xD4 = c ? a & b : a | b)
+                asm("lop3.b32 %0, %1, %0, %2, 0xD4;" : "+r"(ge) : "r"(pk), "r"(tmk[k]));
+                if (!QUICK || k >= NQ - 2) pc[k] += __popc(pk);          // QUICK: the two top planes first (below)
+              }
             }
             ql[w + 1] = blk[0];
             qh[w + 1] = blk[1];
-            qv[w + 1] = blk[2] & ge & q_allow;
+            qv[w + 1] = BQ30 ? (blk[2] & ge) : (blk[2] & ge & q_allow);
           };
           if (LD256) {
             // the whole read at once: ceil(9 W / 8) independent 256-bit loads; the units of the 32 reads of a
@@ -609,8 +647,8 @@ __global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : ((VAR &
             constexpr int NV8 = (WT * NP + 7) / 8;
             const uint32_t nv8 = (((lq + 31u) >> 5) * (uint32_t)NP + 7u) >> 3;
             const uint32_t* __restrict__ vp = p.planes + (size_t)b0 * 8;
-            uint32_t raw_ld[TMA ? 1 : 8 * NV8];
-            if (!TMA) {
+            uint32_t raw_ld[(TMA || SPEC) ? 1 : 8 * NV8];
+            if (!TMA && !SPEC) {
 #pragma unroll
               for (int u = 0; u < NV8; ++u) {
                 // every read has a block, i.e. at least NP > 8 words: its first two units always exist; units
@@ -618,7 +656,7 @@ __global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : ((VAR &
                 ldg256((u < 2 || (uint32_t)u < nv8) ? vp + 8 * MB_GROUP * u : p.zero_unit, raw_ld + 8 * u);
               }
             }
-            const uint32_t* __restrict__ raw = TMA ? raw_in : raw_ld;   // TMA: already copied out of the warp's slot
+            const uint32_t* __restrict__ raw = TMA ? raw_in : (SPEC ? raw_sp : raw_ld);   // TMA: already copied out of the warp's slot
 #pragma unroll
             for (int bl = 0; bl < WT; ++bl) convert(bl, raw + bl * NP);
             if (QUICK) {
@@ -694,13 +732,6 @@ __global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : ((VAR &
 
     uint32_t pass_rows = 0;
     bool accumulate = false;
-    uint4 nh = make_uint4(0, 0, 0, 0);                         // header, block offset, run word and predecessor
-    uint32_t nb0 = 0, ncw = 0, nprev = 0;                       // of this thread's next read: one step ahead
-    // PIPE: the planes of my next row, first / second half of its 32-byte units; whether the first half of my first
-    // row of the coming round is already on its way
-    constexpr int PV8 = (WT * NP + 7) / 8, PVA = (PV8 + 1) / 2, PVB = PV8 - PVA;
-    uint32_t rawA[PIPE ? 8 * PVA : 1], rawB[PIPE ? 8 * PVB : 1];
-    bool pre_ok = false;
     if (TMA) {                                                  // my read of the warp's first group of this tile
       const uint32_t rf = r0a + 32u * (uint32_t)(tid >> 5) + (uint32_t)lane;
       if ((uint32_t)(tid >> 5) < n_groups && rf < r1) {
@@ -785,8 +816,15 @@ __global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : ((VAR &
         if (pf_r0 >= r1) {
           pf_r0 = pf_r1 = 0;
           if (next_tile < p.n_ktiles) {
-            pf_r0 = __ldg(&p.tile_rng[2 * next_tile]);
-            pf_r1 = min(pf_r0 + p.rmax, __ldg(&p.tile_rng[2 * next_tile + 1]));
+            const uint32_t a = __ldg(&p.tile_rng[2 * next_tile]), b = __ldg(&p.tile_rng[2 * next_tile + 1]);
+            pf_r0 = a;
+            pf_r1 = min(a + p.rmax, b);
+            if (XU) {
+              const uint2 nu = __ldg(&p.units[next_tile]);
+              s_nx[0] = nu.x; s_nx[1] = nu.y; s_nx[2] = a; s_nx[3] = b; s_nx[4] = next_tile;
+            }
+          } else if (XU) {
+            s_nx[4] = 0xffffffffu;
           }
         }
         if (pf_r1 > pf_r0) {
@@ -867,151 +905,11 @@ __global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : ((VAR &
           stage_one(i, n, h, b0, cw, i > 0 ? s_hdr[i - 1].x : 0u, nullptr);
         }
       } else {
-      if (PIPE) {
-        // ---- software pipeline over my rows. Per row: header -> filters -> plane loads -> conversion -> placement.
-        // The warps of a CTA leave the barrier together, so without this they all wait for their plane loads at the
-        // same moment (23 % of the warp time in profiles/r02t_k_pileup_v2_bal.txt). Here the first half of the next
-        // row's units is requested before the current row is placed (the registers of the converted row's raw words
-        // are free by then), the second half when its turn starts (in flight while the first three blocks are
-        // converted), and the first row of the coming round before COUNT.
-#define MB_RAWW(w) ((w) < 8 * PVA ? rawA[(w) < 8 * PVA ? (w) : 0] : rawB[(w) >= 8 * PVA ? (w) - 8 * PVA : 0])
-        auto filt = [&](const uint4 h, bool& needq, bool& ovl, bool& owner) {
-          const uint32_t loc = h.x, lq = h.y & 0xffffu, alen = h.y >> 16, nm = h.z >> 16;
-          const uint32_t span = h.w & 0xffffu, mq = (h.w >> 16) & 0xffu, fl = (h.w >> 24) & 0x7fu;
-          needq = false; ovl = false; owner = false;
-          if (!(fl & MB_RF_LONG)) {
-            owner = loc >= ts;
-            ovl = span > 0 && loc + span > ts;
-            bool hk = (fl & MB_RF_NMSAT) ? (p.pid_always != 0)
-                                         : (100 * ((int)alen - (int)nm) >= s_tpid[alen]);   // snps.py:148
-            hk = hk && (int)mq >= p.mapq;                                                             // snps.py:154
-            hk = hk && (int)alen >= s_tcov[lq];                                                      // snps.py:157
-            needq = hk && (ovl || owner);
-          }
-        };
-        auto issue = [&](const bool second, const uint4 h, const uint32_t b0, const bool needq) {
-          if (!needq) return;
-          const uint32_t nv8 = ((((h.y & 0xffffu) + 31u) >> 5) * (uint32_t)NP + 7u) >> 3;
-          const uint32_t* __restrict__ vp = p.planes + (size_t)b0 * 8;
-          if (!second) {
-#pragma unroll
-            for (int u = 0; u < PVA; ++u)
-              ldg256_at((u < 2 || (uint32_t)u < nv8) ? vp + 8 * MB_GROUP * u : p.zero_unit, rawA + 8 * u);
-          } else {
-#pragma unroll
-            for (int u = PVA; u < PV8; ++u)
-              ldg256_at((u < 2 || (uint32_t)u < nv8) ? vp + 8 * MB_GROUP * u : p.zero_unit, rawB + 8 * (u - PVA));
-          }
-        };
-        if (rb == r0) {                                        // first round of the unit: nothing is in flight yet
-          pre_ok = false;
-          nh = make_uint4(0, 0, 0, 0); nb0 = 0; ncw = 0; nprev = 0;
-          if (tid < n) {
-            nh = __ldg(&p.hdr[rb + tid]);
-            nb0 = __ldg(&p.vec_off[rb + tid]);
-            ncw = __ldg(&p.cplx[rb + tid]);
-            if (tid > 0) nprev = __ldg(&p.hdr[rb + tid - 1].x);
-          }
-        }
-        if (tid < n) {
-          int i = tid;
-          uint4 h = nh;
-          uint32_t b0 = nb0, cw = ncw, prev_loc = nprev;
-          bool needq, ovl, owner;
-          filt(h, needq, ovl, owner);
-          if (!pre_ok) issue(false, h, b0, needq);
-          for (;;) {
-            const uint32_t r = rb + (uint32_t)i;
-            // my next row: in this round, else my first row of the coming round
-            const bool more = i + NT < n;
-            const uint32_t rn = more ? r + NT : rb + p.rmax + (uint32_t)tid;
-            const bool hasn = more || (rb + p.rmax < r1 && rn < r1);
-            if (hasn) {
-              nh = __ldg(&p.hdr[rn]);
-              nb0 = __ldg(&p.vec_off[rn]);
-              ncw = __ldg(&p.cplx[rn]);
-              nprev = (more || tid > 0) ? __ldg(&p.hdr[rn - 1].x) : 0u;
-            }
-            issue(true, h, b0, needq);
-            const uint32_t loc = h.x, lq = h.y & 0xffffu, qstart = h.z & 0xffffu;
-            const uint32_t span = h.w & 0xffffu, fl = (h.w >> 24) & 0x7fu;
-            if (owner) ++my_aligned;                                                                  // snps.py:143
-            const int rel = (int)(loc >> 5) - (int)tcol;                      // start column, in [-W, NCOL)
-            {  // s_first[x] = first row of this round whose start column + (W-1) >= x
-              const int kmax = NCOL + (int)W - 1;
-              int xi = rel + (int)W - 1;
-              xi = xi < 0 ? 0 : (xi > kmax ? kmax : xi);
-              int xlo = 0;
-              if (i > 0) {
-                int xp = (int)(prev_loc >> 5) - (int)tcol + (int)W - 1;
-                xp = xp < 0 ? 0 : (xp > kmax ? kmax : xp);
-                xlo = xp + 1;
-              }
-              for (int x = xlo; x <= xi; ++x) s_first[x] = (uint32_t)i;
-              if (i == n - 1)
-                for (int x = xi + 1; x <= kmax + 1; ++x) s_first[x] = (uint32_t)n;
-              if (BAL) {
-                if (i == 0) s_cr[0] = (uint32_t)max(rel, 0);
-                if (i == n - 1) s_cr[1] = (uint32_t)min(rel + (int)W, ucol);
-              }
-            }
-            uint32_t ql[WT + 2], qh[WT + 2], qv[WT + 2];
-            ql[0] = 0; qh[0] = 0; qv[0] = 0;
-            ql[WT + 1] = 0; qh[WT + 1] = 0; qv[WT + 1] = 0;
-            bool keep = false;
-            if (needq) {
-              uint32_t pc1 = 0, pc2 = 0;                       // set bits of the two top Phred planes
-#pragma unroll
-              for (int bl = 0; bl < WT; ++bl) {
-                uint32_t ge = 0xffffffffu;                     // Phred >= baseq, bit-sliced over 32 bases (as in stage_one)
-#pragma unroll
-                for (int k = 0; k < NQ; ++k) {
-                  const uint32_t pk = MB_RAWW(bl * NP + 3 + k);
-                  asm("lop3.b32 %0, %1, %0, %2, 0xD4;" : "+r"(ge) : "r"(pk), "r"(tmk[k]));
-                  if (k == NQ - 1) pc1 += __popc(pk);
-                  if (k == NQ - 2) pc2 += __popc(pk);
-                }
-                ql[bl + 1] = MB_RAWW(bl * NP);
-                qh[bl + 1] = MB_RAWW(bl * NP + 1);
-                qv[bl + 1] = MB_RAWW(bl * NP + 2) & ge & q_allow;
-              }
-              // mean-quality filter (snps.py:151): the two top planes bound the sum from below, the exact sum otherwise
-              const uint32_t q_thr = p.readq_eff * lq;
-              uint32_t qsum = (pc1 << (NQ - 1)) + (pc2 << (NQ - 2));
-              keep = qsum >= q_thr;
-              if (!keep) {
-#pragma unroll
-                for (int bl = 0; bl < WT; ++bl)
-#pragma unroll
-                  for (int k = 0; k < NQ - 2; ++k) qsum += (uint32_t)__popc(MB_RAWW(bl * NP + 3 + k)) << k;
-                keep = qsum >= q_thr;
-              }
-              if (keep && owner) ++my_mapped;                                    // snps.py:161
-            }
-            bool needq_n = false, ovl_n = false, owner_n = false;
-            if (hasn) {
-              filt(nh, needq_n, ovl_n, owner_n);
-              issue(false, nh, nb0, needq_n);
-            }
-            if (keep && ovl) {
-              place_store(ql, qh, qv, loc, qstart, lq, span, cw, fl, i);
-            } else {
-              uint4* __restrict__ dst = s_rows + (uint32_t)i * W;
-#pragma unroll
-              for (int j = 0; j < WT; ++j) dst[j] = make_uint4(0, 0, 0, 0);
-            }
-            if (!more) { pre_ok = hasn; break; }
-            i += NT;
-            h = nh; b0 = nb0; cw = ncw; prev_loc = nprev;
-            needq = needq_n; ovl = ovl_n; owner = owner_n;
-          }
-        }
-#undef MB_RAWW
-      } else {
-      if (rb == r0) {                                          // later rounds: requested before the previous COUNT
+      const bool hdr_here = rb == r0 && !(XU && pre_tile == tile);   // else requested before the previous COUNT
+      if (hdr_here) {
         nh = make_uint4(0, 0, 0, 0); nb0 = 0; ncw = 0; nprev = 0;
       }
-      if (rb == r0 && tid < n) {
+      if (hdr_here && tid < n) {
         nh = __ldg(&p.hdr[rb + tid]);
         nb0 = __ldg(&p.vec_off[rb + tid]);
         ncw = __ldg(&p.cplx[rb + tid]);
@@ -1061,7 +959,6 @@ __global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : ((VAR &
       }
       }
       }
-      }
       PROF_MARK(1);
       __syncthreads();
       PROF_MARK(2);
@@ -1076,6 +973,18 @@ __global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : ((VAR &
           hq[k] = rr < b ? __ldg(&p.hdr[rr]) : make_uint4(0, 0, 0, 0);
         }
         if (tid < 2) s_cnt[tid] = 0;
+      }
+      if (XU && rb + p.rmax >= r1) {
+        // the unit's last round: my first read of the next unit, in flight during COUNT, EXPAND and the hand-over
+        pre_tile = s_nx[4];
+        nh = make_uint4(0, 0, 0, 0); nb0 = 0; ncw = 0; nprev = 0;
+        const uint32_t nr = s_nx[2] + (uint32_t)tid;
+        if (pre_tile != 0xffffffffu && nr < s_nx[3]) {
+          nh = __ldg(&p.hdr[nr]);
+          nb0 = __ldg(&p.vec_off[nr]);
+          ncw = __ldg(&p.cplx[nr]);
+          if (tid > 0) nprev = __ldg(&p.hdr[nr - 1].x);
+        }
       }
       if (PFL2 && !TMA) {
         // HBM -> L2 traffic of the next round runs under this round's COUNT: 8 KB pieces of the plane range, then the
@@ -1418,8 +1327,8 @@ __global__ void __launch_bounds__(256) k_restat(const uint32_t* __restrict__ cou
 
 // the row widths (and Phred plane counts) the tile kernel is instantiated for; a batch runs at the smallest
 // width >= its row_words
-struct PileKernel { uint32_t W; void (*fn)(const PileParams); uint32_t kt; bool tma; bool sorted; bool defer = false; bool cta3 = false; };   // kt: positions per tile
-PileKernel pick_kernel(uint32_t row_words, uint32_t q_planes, bool want_tma) {
+struct PileKernel { uint32_t W; void (*fn)(const PileParams); uint32_t kt; bool tma; bool sorted; bool defer = false; bool cta3 = false; bool bal = false; };   // kt: positions per tile
+PileKernel pick_kernel(uint32_t row_words, uint32_t q_planes, bool want_tma, int baseq) {
 #define MB_PT(W, Q) {W, k_pileup_v2<W, Q, 4>, 2048, true, false}
   static const PileKernel t6[] = {MB_PT(3, 6), MB_PT(4, 6), MB_PT(5, 6), MB_PT(6, 6), MB_PT(7, 6), MB_PT(8, 6)};
   static const PileKernel t7[] = {MB_PT(3, 7), MB_PT(4, 7), MB_PT(5, 7), MB_PT(6, 7), MB_PT(7, 7), MB_PT(8, 7)};
@@ -1429,22 +1338,26 @@ PileKernel pick_kernel(uint32_t row_words, uint32_t q_planes, bool want_tma) {
     for (int i = 0; i < 6; ++i)
       if (k[i].W >= row_words) return k[i];
   }
-#define MB_PK(W, Q) {W, k_pileup_v2<W, Q, 72>, 2048, false, false}
+#define MB_PK(W, Q) {W, k_pileup_v2<W, Q, 1096>, 2048, false, false, false, false, true}
   static const PileKernel k6[] = {MB_PK(3, 6), MB_PK(4, 6), MB_PK(5, 6),  MB_PK(6, 6),  MB_PK(7, 6),
                                   MB_PK(8, 6), MB_PK(10, 6), MB_PK(12, 6), MB_PK(16, 6)};
   static const PileKernel k7[] = {MB_PK(3, 7), MB_PK(4, 7), MB_PK(5, 7),  MB_PK(6, 7),  MB_PK(7, 7),
                                   MB_PK(8, 7), MB_PK(10, 7), MB_PK(12, 7), MB_PK(16, 7)};
 #undef MB_PK
+  // baseq = 30 (the default of run_midas.py snps) with six Phred planes: the comparator is specialised
+#define MB_PB(W) {W, k_pileup_v2<W, 6, 1608>, 2048, false, false, false, false, true}
+  static const PileKernel k6b[] = {MB_PB(3), MB_PB(4), MB_PB(5), MB_PB(6), MB_PB(7), MB_PB(8), MB_PB(10), MB_PB(12), MB_PB(16)};
+#undef MB_PB
   // experiment switches (MB_PILE_VAR, W = 6 with 6 Phred planes only)
   static const PileKernel kx[4] = {{6, k_pileup_v2<6, 6, 0>, 2048, false, false}, {6, k_pileup_v2<6, 6, 1>, 2048, false, false},
                                    {6, k_pileup_v2<6, 6, 2>, 1024, false, false}, {6, k_pileup_v2<6, 6, 3>, 1024, false, false}};
   static const PileKernel kpf = {6, k_pileup_v2<6, 6, 8>, 2048, false, false};
   static const PileKernel kso = {6, k_pileup_v2<6, 6, 24>, 2048, false, true};
   static const PileKernel kdf = {6, k_pileup_v2<6, 6, 40>, 2048, false, false, true};
-  static const PileKernel kbl = {6, k_pileup_v2<6, 6, 72>, 2048, false, false};
-  static const PileKernel kb3 = {6, k_pileup_v2<6, 6, 200>, 2048, false, false, false, true};
-  static const PileKernel kpp = {6, k_pileup_v2<6, 6, 328>, 2048, false, false};
-  static const PileKernel kb1 = {6, k_pileup_v2<6, 6, 74>, 1024, false, false};
+  static const PileKernel kbl = {6, k_pileup_v2<6, 6, 72>, 2048, false, false, false, false, true};
+  static const PileKernel kb3 = {6, k_pileup_v2<6, 6, 200>, 2048, false, false, false, true, true};
+  static const PileKernel kb1 = {6, k_pileup_v2<6, 6, 74>, 1024, false, false, false, false, true};
+  static const PileKernel knsp = {6, k_pileup_v2<6, 6, 584>, 2048, false, false, false, false, true};
   if (const char* e = getenv("MB_PILE_VAR")) {
     const long v = atol(e);
     if (v >= 0 && v < 4 && q_planes == 6 && row_words > 5 && row_words <= 6) return kx[v];
@@ -1453,10 +1366,10 @@ PileKernel pick_kernel(uint32_t row_words, uint32_t q_planes, bool want_tma) {
     if (v == 40 && q_planes == 6 && row_words > 5 && row_words <= 6) return kdf;
     if (v == 72 && q_planes == 6 && row_words > 5 && row_words <= 6) return kbl;
     if (v == 200 && q_planes == 6 && row_words > 5 && row_words <= 6) return kb3;
-    if (v == 328 && q_planes == 6 && row_words > 5 && row_words <= 6) return kpp;
     if (v == 74 && q_planes == 6 && row_words > 5 && row_words <= 6) return kb1;
+    if (v == 584 && q_planes == 6 && row_words > 5 && row_words <= 6) return knsp;
   }
-  const PileKernel* k = q_planes == 6 ? k6 : k7;
+  const PileKernel* k = q_planes == 6 ? (baseq == 30 && !getenv("MB_PILE_GENERIC_BASEQ") ? k6b : k6) : k7;
   for (int i = 0; i < 9; ++i)
     if (k[i].W >= row_words) return k[i];
   return k[8];
@@ -1505,18 +1418,23 @@ extern "C" int mb_snps_pileup_dev(mb_ctx* ctx, const mb_dev_reads* reads, const 
   bool want_tma = false;
   if (const char* e = getenv("MB_PILE_TMA")) want_tma = atol(e) != 0;
   if (getenv("MB_PILE_VAR")) want_tma = false;
-  const PileKernel kern = pick_kernel(reads->row_words, reads->q_planes, want_tma);
+  const PileKernel kern = pick_kernel(reads->row_words, reads->q_planes, want_tma, f->baseq);
   const uint32_t W = kern.W;                                          // instantiated row width >= row_words
   const uint32_t KT = kern.kt, NCOL = KT / 32, NT = NCOL * KSUB;
   {
     size_t kb = (kern.tma || kern.sorted) ? 112 : (kern.cta3 ? 72 : (KT == 2048 ? 100 : 50));   // 2 / 3 / 4 CTAs per SM
     if (const char* e = getenv("MB_PILE_SMEM_KB")) { long v = atol(e); if (v >= 24 && v <= 220) kb = (size_t)v; }
     ctx->pile_smem = kb * 1024;
+    if (const char* e = getenv("MB_PILE_SMEM_B")) { long v = atol(e); if (v >= 24 * 1024 && v <= 220 * 1024) ctx->pile_smem = (size_t)v; }
   }
-  const uint32_t attr_bit = 1u << (W + (reads->q_planes == 7 ? 16u : 0u) + (kern.tma ? 8u : 0u));
-  if (!(ctx->pile_attr_mask & attr_bit) || getenv("MB_PILE_VAR") || getenv("MB_PILE_SMEM_KB")) {
-    MB_CUDA_TRY(cudaFuncSetAttribute(kern.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->pile_smem));
-    ctx->pile_attr_mask |= attr_bit;
+  // the shared-memory attribute is per kernel instance: set once per (instance, size)
+  {
+    const void* fn = reinterpret_cast<const void*>(kern.fn);
+    auto it = ctx->pile_attr.find(fn);
+    if (it == ctx->pile_attr.end() || it->second != ctx->pile_smem) {
+      MB_CUDA_TRY(cudaFuncSetAttribute(kern.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->pile_smem));
+      ctx->pile_attr[fn] = ctx->pile_smem;
+    }
   }
   {
     int occ = 0;
@@ -1539,10 +1457,16 @@ extern "C" int mb_snps_pileup_dev(mb_ctx* ctx, const mb_dev_reads* reads, const 
     if (v == 0) guided = false;
   }
   if (guided) unit_len |= 1u;                                    // cache key: the guided table of this tile length
-  if (ctx->units_layout != L->id || ctx->units_len != unit_len) {
+  if (ctx->units_layout != L->id || ctx->units_len != unit_len || getenv("MB_PILE_GUIDE")) {
     std::vector<uint2> tab;
     const uint32_t base_len = unit_len & ~31u;
-    const uint64_t half_from = guided ? L->gpad / 100 * 85 : L->gpad, quarter_from = guided ? L->gpad / 100 * 95 : L->gpad;
+    uint64_t pct_half = 85, pct_quarter = 95;                       // MB_PILE_GUIDE="half,quarter" (per cent): sweeps
+    if (const char* e = getenv("MB_PILE_GUIDE")) {
+      unsigned a = 0, b = 0;
+      if (sscanf(e, "%u,%u", &a, &b) == 2 && a <= b && b <= 100) { pct_half = a; pct_quarter = b; }
+    }
+    const uint64_t half_from = guided ? L->gpad / 100 * pct_half : L->gpad;
+    const uint64_t quarter_from = guided ? L->gpad / 100 * pct_quarter : L->gpad;
     tab.reserve((size_t)(L->gpad / base_len + L->n_species + 16));
     for (uint32_t sp = 0; sp < L->n_species; ++sp) {
       const uint32_t end = L->species_goff[sp + 1];
@@ -1599,7 +1523,8 @@ extern "C" int mb_snps_pileup_dev(mb_ctx* ctx, const mb_dev_reads* reads, const 
   } else {
     const size_t extra = 32 + (kern.defer ? defer_smem_bytes(W, NT / 32) : 0);
     rmax = (uint32_t)((ctx->pile_smem - fixed - extra) / (sizeof(uint4) * W)) - 1u;   // one row is the empty padding row
-    if (rmax > (uint32_t)LANE_ROWS_MAX * KSUB) rmax = LANE_ROWS_MAX * KSUB;
+    const uint32_t cap = kern.bal ? 1016u : (uint32_t)LANE_ROWS_MAX * KSUB;             // what a lane's register counters hold
+    if (rmax > cap) rmax = cap;
     if (rmax >= 2u * NT && !getenv("MB_PILE_RAGGED")) rmax = rmax / NT * NT;   // the same number of reads for every thread
     rmax &= ~7u;
   }

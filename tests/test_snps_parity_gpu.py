@@ -103,7 +103,7 @@ def test_work_unit_lengths(ctx, monkeypatch, unit):
     _check(ctx, ref, reads, Filters(mapid=0.0, aln_cov=0.0, readq=0, mapq=0, baseq=0))
 
 
-@pytest.mark.parametrize("var", ["8", "72", "74", "200", "328"])
+@pytest.mark.parametrize("var", ["8", "72", "74", "200", "584"])
 def test_count_variants(ctx, monkeypatch, var):
     """The COUNT variants of the W = 6 instance (fixed column map, columns dealt over all threads, the latter at three
     CTAs per SM) against the oracle, at two unit lengths."""

@@ -252,6 +252,9 @@ __global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : ((VAR &
   constexpr int DCAP = 16, DWORDS = 3 * WT + 6; // DEFER: entries per warp and round; words per entry
   constexpr bool BAL = (VAR & 64) != 0;         // bit 6: COUNT deals the round's active columns over all threads (below)
   constexpr bool BQ30 = (VAR & 512) != 0;       // bit 9: instance for baseq = 30, the CLI default (comparator below)
+  // bit 12: no read of the batch has more than WT - 1 blocks of 32 bases (150-base reads: 5 blocks, while a row needs
+  // 6 words for any alignment of the start): one block less to load, convert and carry in registers
+  constexpr int QB = ((VAR & 4096) != 0 && WT <= 8 && WT > 2) ? WT - 1 : WT;
   // bit 10: a row's plane loads are issued as soon as its header is there, before the header filters are evaluated
   constexpr bool SPEC = (VAR & 1024) != 0 && WT <= 8 && !(VAR & 1) && !TMA && !SORTED;
   // the next unit's table entries and my first header of it are requested during the current unit's last round
@@ -545,7 +548,7 @@ __global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : ((VAR &
                          const uint32_t row_mask = 0xffffffffu) {
         const uint32_t loc = h.x, lq = h.y & 0xffffu, alen = h.y >> 16, qstart = h.z & 0xffffu, nm = h.z >> 16;
         const uint32_t span = h.w & 0xffffu, mq = (h.w >> 16) & 0xffu, fl = (h.w >> 24) & 0x7fu;
-        constexpr int NV8S = (WT * NP + 7) / 8;
+        constexpr int NV8S = (QB * NP + 7) / 8;
         uint32_t raw_sp[SPEC ? 8 * NV8S : 1];
         if (SPEC) {
           // the loads do not wait for the filters (a filtered read's planes are fetched and dropped: the byte model of
@@ -644,7 +647,7 @@ __global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : ((VAR &
           if (LD256) {
             // the whole read at once: ceil(9 W / 8) independent 256-bit loads; the units of the 32 reads of a
             // group are interleaved, so the lanes of a warp (consecutive reads) read consecutive sectors
-            constexpr int NV8 = (WT * NP + 7) / 8;
+            constexpr int NV8 = (QB * NP + 7) / 8;
             const uint32_t nv8 = (((lq + 31u) >> 5) * (uint32_t)NP + 7u) >> 3;
             const uint32_t* __restrict__ vp = p.planes + (size_t)b0 * 8;
             uint32_t raw_ld[(TMA || SPEC) ? 1 : 8 * NV8];
@@ -658,12 +661,14 @@ __global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : ((VAR &
             }
             const uint32_t* __restrict__ raw = TMA ? raw_in : (SPEC ? raw_sp : raw_ld);   // TMA: already copied out of the warp's slot
 #pragma unroll
-            for (int bl = 0; bl < WT; ++bl) convert(bl, raw + bl * NP);
+            for (int bl = 0; bl < QB; ++bl) convert(bl, raw + bl * NP);
+#pragma unroll
+            for (int bl = QB; bl < WT; ++bl) { ql[bl + 1] = 0; qh[bl + 1] = 0; qv[bl + 1] = 0; }
             if (QUICK) {
               keep = (pc[NQ - 1] << (NQ - 1)) + (pc[NQ - 2] << (NQ - 2)) >= q_thr;
               if (!keep) {                                         // a poor read: the exact sum
 #pragma unroll
-                for (int bl = 0; bl < WT; ++bl)
+                for (int bl = 0; bl < QB; ++bl)
 #pragma unroll
                   for (int k = 0; k < NQ - 2; ++k) pc[k] += __popc(raw[bl * NP + 3 + k]);
               }
@@ -748,6 +753,7 @@ __global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : ((VAR &
         pass_rows = 0;
       }
       pass_rows += (uint32_t)n;
+      const bool hdr_here = rb == r0 && !(XU && pre_tile == tile);   // else my first header was requested a round ago
       PROF_MARK(0);
       __syncthreads();
       PROF_MARK(4);
@@ -905,7 +911,6 @@ __global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : ((VAR &
           stage_one(i, n, h, b0, cw, i > 0 ? s_hdr[i - 1].x : 0u, nullptr);
         }
       } else {
-      const bool hdr_here = rb == r0 && !(XU && pre_tile == tile);   // else requested before the previous COUNT
       if (hdr_here) {
         nh = make_uint4(0, 0, 0, 0); nb0 = 0; ncw = 0; nprev = 0;
       }
@@ -1328,7 +1333,7 @@ __global__ void __launch_bounds__(256) k_restat(const uint32_t* __restrict__ cou
 // the row widths (and Phred plane counts) the tile kernel is instantiated for; a batch runs at the smallest
 // width >= its row_words
 struct PileKernel { uint32_t W; void (*fn)(const PileParams); uint32_t kt; bool tma; bool sorted; bool defer = false; bool cta3 = false; bool bal = false; };   // kt: positions per tile
-PileKernel pick_kernel(uint32_t row_words, uint32_t q_planes, bool want_tma, int baseq) {
+PileKernel pick_kernel(uint32_t row_words, uint32_t q_planes, bool want_tma, int baseq, uint32_t max_units) {
 #define MB_PT(W, Q) {W, k_pileup_v2<W, Q, 4>, 2048, true, false}
   static const PileKernel t6[] = {MB_PT(3, 6), MB_PT(4, 6), MB_PT(5, 6), MB_PT(6, 6), MB_PT(7, 6), MB_PT(8, 6)};
   static const PileKernel t7[] = {MB_PT(3, 7), MB_PT(4, 7), MB_PT(5, 7), MB_PT(6, 7), MB_PT(7, 7), MB_PT(8, 7)};
@@ -1369,7 +1374,21 @@ PileKernel pick_kernel(uint32_t row_words, uint32_t q_planes, bool want_tma, int
     if (v == 74 && q_planes == 6 && row_words > 5 && row_words <= 6) return kb1;
     if (v == 584 && q_planes == 6 && row_words > 5 && row_words <= 6) return knsp;
   }
-  const PileKernel* k = q_planes == 6 ? (baseq == 30 && !getenv("MB_PILE_GENERIC_BASEQ") ? k6b : k6) : k7;
+  const bool b30 = baseq == 30 && !getenv("MB_PILE_GENERIC_BASEQ");
+  if (q_planes == 6 && max_units && !getenv("MB_PILE_FULL_BLOCKS")) {
+    // instances for batches whose reads all have at most W - 1 blocks of 32 bases
+#define MB_PQ(W, V) {W, k_pileup_v2<W, 6, V>, 2048, false, false, false, false, true}
+    static const PileKernel k6q[] = {MB_PQ(3, 5192), MB_PQ(4, 5192), MB_PQ(5, 5192), MB_PQ(6, 5192), MB_PQ(7, 5192), MB_PQ(8, 5192)};
+    static const PileKernel k6bq[] = {MB_PQ(3, 5704), MB_PQ(4, 5704), MB_PQ(5, 5704), MB_PQ(6, 5704), MB_PQ(7, 5704), MB_PQ(8, 5704)};
+#undef MB_PQ
+    const PileKernel* kq = b30 ? k6bq : k6q;
+    for (int i = 0; i < 6; ++i)
+      if (kq[i].W >= row_words) {
+        if (max_units <= ((kq[i].W - 1) * 9 + 7) / 8) return kq[i];
+        break;
+      }
+  }
+  const PileKernel* k = q_planes == 6 ? (b30 ? k6b : k6) : k7;
   for (int i = 0; i < 9; ++i)
     if (k[i].W >= row_words) return k[i];
   return k[8];
@@ -1418,7 +1437,7 @@ extern "C" int mb_snps_pileup_dev(mb_ctx* ctx, const mb_dev_reads* reads, const 
   bool want_tma = false;
   if (const char* e = getenv("MB_PILE_TMA")) want_tma = atol(e) != 0;
   if (getenv("MB_PILE_VAR")) want_tma = false;
-  const PileKernel kern = pick_kernel(reads->row_words, reads->q_planes, want_tma, f->baseq);
+  const PileKernel kern = pick_kernel(reads->row_words, reads->q_planes, want_tma, f->baseq, reads->max_units);
   const uint32_t W = kern.W;                                          // instantiated row width >= row_words
   const uint32_t KT = kern.kt, NCOL = KT / 32, NT = NCOL * KSUB;
   {

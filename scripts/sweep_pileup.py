@@ -17,7 +17,7 @@ import bench  # noqa: E402
 from midas_b200 import lib  # noqa: E402
 from midas_b200.soa import Filters  # noqa: E402
 
-KNOBS = ("MB_PILE_VAR", "MB_PILE_SMEM_KB", "MB_PILE_RAGGED", "MB_PILE_TMA", "MB_PILE_UNIT", "MB_PILE_GUIDE", "MB_PILE_GENERIC_BASEQ", "MB_PILE_SMEM_B")
+KNOBS = ("MB_PILE_VAR", "MB_PILE_SMEM_KB", "MB_PILE_RAGGED", "MB_PILE_TMA", "MB_PILE_UNIT", "MB_PILE_GUIDE", "MB_PILE_GENERIC_BASEQ", "MB_PILE_SMEM_B", "MB_PILE_FULL_BLOCKS")
 
 
 def main():

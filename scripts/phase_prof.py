@@ -62,6 +62,7 @@ def main():
         out = {"setting": setting, "kernel_ms_with_clocks": round(ms / max(1, n), 4),
                "share": {k: round(float(v), 4) for k, v in zip(NAMES, share)},
                "cycles_per_warp": {k: int(v) for k, v in zip(NAMES, cyc.mean(axis=(0, 1)))},
+               "per_warp_stage_share": [round(float(x), 3) for x in (cyc[:, :, 1].sum(axis=0) / tot.sum(axis=0))],
                "per_warp_count_share": [round(float(x), 3) for x in (cyc[:, :, 3].sum(axis=0) / tot.sum(axis=0))],
                "per_warp_wait_after_stage": [round(float(x), 3) for x in (cyc[:, :, 2].sum(axis=0) / tot.sum(axis=0))],
                "cta_end_us": {"min": round(float(end.min()), 1), "p10": round(float(np.percentile(end, 10)), 1),

@@ -368,6 +368,11 @@ const uint16_t* mb_bam_flags(const mb_bam* b);   /* [n_reads] SAM flags (informa
  * (MB_EUNSORTED otherwise: use mb_bam_open + mb_pack_reads with sort). */
 typedef struct mb_bam_stream mb_bam_stream;
 int mb_bam_stream_open(const char* path, int n_threads, mb_bam_stream** out);
+/* The same, with the transfer under the inflate: the blocks are inflated front to back and every 16 MB of the stream
+ * that is complete crosses PCIe (on ctx's stream, into ctx's staging memory) while the host threads inflate the
+ * rest; a following mb_snps_pileup_bam / mb_genes_coverage_bam on the same ctx finds the stream on the device. One
+ * resident stream per context: opening another one, or passing a different stream to those calls, replaces it. */
+int mb_bam_stream_open_dev(mb_ctx* ctx, const char* path, int n_threads, mb_bam_stream** out);
 void mb_bam_stream_close(mb_bam_stream* s);
 uint32_t mb_bam_stream_n_ref(const mb_bam_stream* s);
 const char* mb_bam_stream_ref_name(const mb_bam_stream* s, uint32_t i);

@@ -90,6 +90,7 @@ struct mb_ctx {
   size_t tile_rng_cap;
   const mb_dev_reads* rng_for;  // resident batch the tile index in tile_rng was built for (null: none)
   uint32_t rng_W, rng_ntiles;
+  const mb_bam_stream* bam_resident;   // the BAM stream whose inflated bytes lie in staging slot 24 (mb_bam_stream_open_dev)
   // work units of the pileup kernel: (first position, positions) of every unit, per species region; rebuilt when the
   // layout, the unit length or the kernel tile changes
   uint2* units;

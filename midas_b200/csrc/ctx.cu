@@ -3,6 +3,8 @@
 #include <cstring>
 #include <climits>
 
+#include <chrono>
+
 #include "common.h"
 
 namespace mb {
@@ -158,6 +160,7 @@ extern "C" int mb_ctx_create(int device, mb_ctx** out) {
   c->rng_for = nullptr;
   c->rng_W = 0;
   c->rng_ntiles = 0;
+  c->bam_resident = nullptr;
   c->units = nullptr;
   c->units_cap = 0;
   c->units_layout = ~0ull;
@@ -199,6 +202,10 @@ extern "C" void mb_ctx_destroy(mb_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  const bool timing = getenv("MB_CTX_TIMING") != nullptr;
+  auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  double t0 = now();
+  auto phase = [&](const char* what) { if (timing) { const double t = now(); fprintf(stderr, "mb_ctx_destroy: %-10s %8.1f ms\n", what, t - t0); t0 = t; } };
   for (auto& kv : c->layouts) {
     cudaFree(kv.second.tile_species);
     cudaFree(kv.second.species_len);
@@ -206,8 +213,12 @@ extern "C" void mb_ctx_destroy(mb_ctx* c) {
     cudaFree(kv.second.contig_goff);
     cudaFree(kv.second.order);
   }
+  phase("layouts");
   for (int i = 0; i < mb_ctx::kStage; ++i)
-    if (c->stage[i]) cudaFree(c->stage[i]);
+    if (c->stage[i]) {
+      cudaFree(c->stage[i]);
+      if (timing) { const double t = now(); fprintf(stderr, "mb_ctx_destroy: stage %2d (%7.1f MB) %8.1f ms\n", i, c->stage_cap[i] / 1e6, t - t0); t0 = t; }
+    }
   cudaStreamDestroy(c->copy_stream);
   for (int i = 0; i <= mb_ctx::kChunks; ++i) cudaEventDestroy(c->chunk_ev[i]);
   if (c->pack_meta) cudaFree(c->pack_meta);
@@ -225,6 +236,7 @@ extern "C" void mb_ctx_destroy(mb_ctx* c) {
     cudaEventDestroy(c->ring[i][1]);
   }
   cudaStreamDestroy(c->own_stream);
+  phase("rest");
   delete c;
 }
 

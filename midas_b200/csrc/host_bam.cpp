@@ -17,6 +17,11 @@
 #include <chrono>
 #include <vector>
 
+#include <functional>
+#include <thread>
+#include <atomic>
+#include <chrono>
+
 #include "common.h"
 
 // a buffer whose pages are first touched by the threads that fill it (std::vector would zero it on one thread)
@@ -130,9 +135,72 @@ struct BamData {
   size_t total = 0, first_record = 0;
   std::vector<std::string> ref_name;
   std::vector<uint32_t> ref_len;
+  // mb_bam_stream_open_dev: every record's start (of its refID field), refID and CIGAR length, found by a walker
+  // thread that trails the inflate; bam_stream_walk then only applies the tid_map
+  bool walked = false, header_ok = false;
+  int walk_rc = 0;
+  std::string walk_msg;
+  std::vector<uint64_t> all_off;
+  std::vector<int32_t> all_rid;
+  std::vector<uint32_t> all_ncig;
 };
 
-static int inflate_bam(const char* path, int n_threads, BamData* B, const char* who) {
+// BAM header of the first `avail` inflated bytes: 0 = parsed (ref_name / ref_len / first_record set), 1 = the header
+// runs past `avail` (call again with more), < 0 = mb_status
+static int parse_bam_header(const uint8_t* d, size_t avail, BamData* B, const char* who, const char* path) {
+  B->ref_name.clear();
+  B->ref_len.clear();
+  if (avail < 12) return 1;
+  if (memcmp(d, "BAM\1", 4) != 0) return mb::fail(MB_EMALFORMED, "%s: %s: not a BAM file", who, path);
+  size_t o = 8 + (size_t)rd32(d + 4);
+  if (o + 4 > avail) return 1;
+  const uint32_t n_ref = rd32(d + o);
+  o += 4;
+  for (uint32_t i = 0; i < n_ref; ++i) {
+    if (o + 4 > avail) return 1;
+    const uint32_t ln = rd32(d + o);
+    if (ln == 0) return mb::fail(MB_EMALFORMED, "%s: %s: truncated reference list", who, path);
+    if (o + 8 + ln > avail) return 1;
+    B->ref_name.emplace_back((const char*)d + o + 4, ln - 1);
+    B->ref_len.push_back(rd32(d + o + 4 + ln));
+    o += 8 + ln;
+  }
+  B->first_record = o;
+  return 0;
+}
+
+// One step of the record walk: records that lie entirely below `avail`, from *o on. < 0 = mb_status.
+static int walk_records(const uint8_t* d, size_t avail, size_t total, uint32_t n_ref, size_t* o_io, BamData* B) {
+  size_t o = *o_io;
+  while (o + 4 <= avail) {
+    const uint32_t bs = rd32(d + o);
+    if (bs < 32 || o + 4 + bs > total) return mb::fail(MB_EMALFORMED, "mb_bam_stream: truncated record at %zu", o);
+    if (o + 4 + 32 > avail) break;                               // its fixed fields are not all there yet
+    const uint8_t* r = d + o + 4;
+    const int32_t rid = (int32_t)rd32(r);
+    const uint32_t l_name = r[8], n_cig = rd16(r + 12), l_seq = rd32(r + 16);
+    if (32 + (size_t)l_name + 4 * (size_t)n_cig + (l_seq + 1) / 2 + (size_t)l_seq > bs)
+      return mb::fail(MB_EMALFORMED, "mb_bam_stream: record fields exceed block_size at %zu", o);
+    if (rid >= 0 && (uint32_t)rid >= n_ref) return mb::fail(MB_EMALFORMED, "mb_bam_stream: refID %d out of range", rid);
+    B->all_off.push_back((uint64_t)(o + 4));
+    B->all_rid.push_back(rid);
+    B->all_ncig.push_back(n_cig);
+    o += 4 + bs;
+  }
+  *o_io = o;
+  return MB_OK;
+}
+
+// Optional consumer of the inflated stream while it is being produced (mb_bam_stream_open_dev): `total` is called once
+// the block table says how long the stream is, `ready` for consecutive chunks, in order, as soon as every block of a
+// chunk is inflated - on the calling thread, while the worker threads go on inflating.
+struct ChunkSink {
+  size_t chunk_bytes = 16u << 20;
+  std::function<int(size_t)> total;
+  std::function<int(size_t, size_t, const uint8_t*)> ready;
+};
+
+static int inflate_bam(const char* path, int n_threads, BamData* B, const char* who, ChunkSink* sink = nullptr) {
   const bool timing = getenv("MB_BAM_TIMING") != nullptr;
   auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   double t_phase = now();
@@ -198,45 +266,118 @@ static int inflate_bam(const char* path, int n_threads, BamData* B, const char* 
   if (!data.resize(total + 64)) return mb::fail(MB_ENOMEM, "%s: out of memory", who);
   std::atomic<int> bad_flag{0};
   std::atomic<int>* bad = &bad_flag;
-  pfor(blks.size(), n_threads, [&](size_t lo, size_t hi) {
-    for (size_t i = lo; i < hi; ++i) {
-      const Blk& k = blks[i];
+  auto inflate_block = [&](size_t i) {
+    const Blk& k = blks[i];
+    if (!k.isize) return true;
+    z_stream zs;
+    memset(&zs, 0, sizeof(zs));
+    if (inflateInit2(&zs, -15) != Z_OK) return false;
+    zs.next_in = const_cast<uint8_t*>(raw.data()) + k.cbeg;
+    zs.avail_in = (uInt)k.clen;
+    zs.next_out = data.data() + k.dst;
+    zs.avail_out = k.isize;
+    const int rc = inflate(&zs, Z_FINISH);
+    const bool ok = rc == Z_STREAM_END && zs.total_out == k.isize &&
+                    (crc32(0L, data.data() + k.dst, k.isize) == rd32(raw.data() + k.off + (k.cbeg - k.off) + k.clen));
+    inflateEnd(&zs);
+    return ok;
+  };
+  if (!sink) {
+    pfor(blks.size(), n_threads, [&](size_t lo, size_t hi) {
+      for (size_t i = lo; i < hi; ++i)
+        if (!inflate_block(i)) { bad->store(1); return; }
+    });
+  } else {
+    // blocks are handed out in file order (an atomic cursor), so the stream completes front to back; a chunk is the
+    // blocks that END inside [k C, (k + 1) C): when their count reaches zero the bytes up to the last one's end are
+    // final, and the calling thread passes them on while the workers carry on
+    int src = sink->total(total);
+    if (src) return src;
+    const size_t C = sink->chunk_bytes;
+    const size_t n_chunks = total ? (total + C - 1) / C : 0;
+    std::vector<std::atomic<uint32_t>> left(n_chunks ? n_chunks : 1);
+    for (auto& a : left) a.store(0);
+    std::vector<size_t> chunk_end(n_chunks, 0);
+    for (const Blk& k : blks) {
       if (!k.isize) continue;
-      z_stream zs;
-      memset(&zs, 0, sizeof(zs));
-      if (inflateInit2(&zs, -15) != Z_OK) { bad->store(1); return; }
-      zs.next_in = const_cast<uint8_t*>(raw.data()) + k.cbeg;
-      zs.avail_in = (uInt)k.clen;
-      zs.next_out = data.data() + k.dst;
-      zs.avail_out = k.isize;
-      const int rc = inflate(&zs, Z_FINISH);
-      const bool ok = rc == Z_STREAM_END && zs.total_out == k.isize &&
-                      (crc32(0L, data.data() + k.dst, k.isize) == rd32(raw.data() + k.off + (k.cbeg - k.off) + k.clen));
-      inflateEnd(&zs);
-      if (!ok) { bad->store(1); return; }
+      const size_t c = (k.dst + k.isize - 1) / C;
+      left[c].fetch_add(1);
+      chunk_end[c] = std::max(chunk_end[c], k.dst + (size_t)k.isize);
     }
-  });
+    std::atomic<size_t> cursor{0};
+    std::atomic<size_t> avail{0};          // the stream is final up to here
+    std::atomic<int> done{0};              // 1: every chunk is through (or the inflate failed)
+    B->all_off.reserve(total / 256 + 16);
+    B->all_rid.reserve(total / 256 + 16);
+    B->all_ncig.reserve(total / 256 + 16);
+    // the walker: header as soon as it is complete, then the block_size chain behind the inflate front
+    std::thread walker([&] {
+      bool have_header = false;
+      size_t o = 0;
+      int rc = MB_OK;
+      for (;;) {
+        const bool last = done.load(std::memory_order_acquire) != 0;
+        const size_t a = avail.load(std::memory_order_acquire);
+        if (!have_header) {
+          const int h = parse_bam_header(data.data(), a, B, who, path);
+          if (h < 0) { rc = h; break; }
+          if (h == 0) { have_header = true; B->header_ok = true; o = B->first_record; }
+        }
+        if (have_header) {
+          rc = walk_records(data.data(), a, total, (uint32_t)B->ref_name.size(), &o, B);
+          if (rc) break;
+        }
+        if (last && a == avail.load(std::memory_order_acquire)) {
+          if (!have_header && !bad->load()) rc = mb::fail(MB_EMALFORMED, "%s: %s: truncated header", who, path);
+          break;
+        }
+        if (a == avail.load(std::memory_order_acquire)) std::this_thread::sleep_for(std::chrono::microseconds(100));
+      }
+      B->walk_rc = rc;
+      if (rc) B->walk_msg = mb_last_error();
+      B->walked = true;
+    });
+    std::vector<std::thread> workers;
+    const int nw = std::max(1, n_threads);
+    for (int t = 0; t < nw; ++t)
+      workers.emplace_back([&] {
+        for (;;) {
+          const size_t i = cursor.fetch_add(1);
+          if (i >= blks.size() || bad->load()) return;
+          if (!inflate_block(i)) { bad->store(1); return; }
+          if (blks[i].isize) left[(blks[i].dst + blks[i].isize - 1) / C].fetch_sub(1, std::memory_order_release);
+        }
+      });
+    size_t sent = 0;
+    for (size_t c = 0; c < n_chunks && !src; ++c) {
+      while (left[c].load(std::memory_order_acquire) != 0 && !bad->load()) std::this_thread::sleep_for(std::chrono::microseconds(50));
+      if (bad->load()) break;
+      const size_t end = std::max(chunk_end[c], sent);      // a chunk no block ends in adds nothing
+      avail.store(end, std::memory_order_release);
+      if (end > sent) src = sink->ready(sent, end - sent, data.data() + sent);
+      sent = end;
+    }
+    if (src) bad->store(2);
+    for (auto& w : workers) w.join();
+    done.store(1, std::memory_order_release);
+    walker.join();
+    if (src) return src;
+  }
   if (bad->load()) return mb::fail(MB_EMALFORMED, "%s: %s: BGZF inflate / CRC failure", who, path);
   raw.release();
   phase("inflate");
   // 3. header
-  const uint8_t* d = data.data();
   memset(data.data() + total, 0, 64);
-  if (total < 12 || memcmp(d, "BAM\1", 4) != 0) return mb::fail(MB_EMALFORMED, "%s: %s: not a BAM file", who, path);
-  size_t o = 8 + (size_t)rd32(d + 4);
-  if (o + 4 > total) return mb::fail(MB_EMALFORMED, "%s: %s: truncated header", who, path);
-  const uint32_t n_ref = rd32(d + o);
-  o += 4;
-  for (uint32_t i = 0; i < n_ref; ++i) {
-    if (o + 4 > total) return mb::fail(MB_EMALFORMED, "%s: %s: truncated reference list", who, path);
-    const uint32_t ln = rd32(d + o);
-    if (o + 8 + ln > total || ln == 0) return mb::fail(MB_EMALFORMED, "%s: %s: truncated reference list", who, path);
-    B->ref_name.emplace_back((const char*)d + o + 4, ln - 1);
-    B->ref_len.push_back(rd32(d + o + 4 + ln));
-    o += 8 + ln;
-  }
   B->total = total;
-  B->first_record = o;
+  if (B->walked) {                          // the walker has read it (and the records) already
+    if (!B->header_ok) return mb::fail(B->walk_rc ? B->walk_rc : MB_EMALFORMED, "%s", B->walk_msg.c_str());
+    return MB_OK;                            // (a malformed record is reported by the call that uses the stream)
+  }
+  {
+    const int h = parse_bam_header(data.data(), total, B, who, path);
+    if (h < 0) return h;
+    if (h > 0) return mb::fail(MB_EMALFORMED, "%s: %s: truncated header", who, path);
+  }
   return MB_OK;
 }
 
@@ -347,6 +488,7 @@ extern "C" const uint16_t* mb_bam_flags(const mb_bam* B) { return B ? B->flag.da
 // host only inflates, reads the header and walks the 4-byte block_size chain to find where the records start.
 struct mb_bam_stream {
   BamData bd;
+  mb_ctx* dev_ctx = nullptr;     // mb_bam_stream_open_dev: the context whose staging buffer holds a copy of the stream
 };
 
 extern "C" int mb_bam_stream_open(const char* path, int n_threads, mb_bam_stream** out) {
@@ -358,7 +500,38 @@ extern "C" int mb_bam_stream_open(const char* path, int n_threads, mb_bam_stream
   *out = S;
   return MB_OK;
 }
-extern "C" void mb_bam_stream_close(mb_bam_stream* S) { delete S; }
+extern "C" int mb_bam_stream_open_dev(mb_ctx* c, const char* path, int n_threads, mb_bam_stream** out) {
+  if (!c || !path || !out) return mb::fail(MB_EINVAL, "mb_bam_stream_open_dev: null argument");
+  if (n_threads <= 0) n_threads = (int)std::min<unsigned>(32, std::max(1u, std::thread::hardware_concurrency()));
+  MB_CUDA_TRY(cudaSetDevice(c->device));
+  mb_bam_stream* S = new mb_bam_stream();
+  uint8_t* dev = nullptr;
+  ChunkSink sink;
+  sink.total = [&](size_t total) {
+    void* d = nullptr;
+    c->bam_resident = nullptr;
+    const int rc = mb::ctx_reserve(c, 24, total + 512, &d);
+    if (rc) return rc;
+    dev = (uint8_t*)d;
+    MB_CUDA_TRY(cudaMemsetAsync(dev + total, 0, 512, c->stream));
+    return (int)MB_OK;
+  };
+  sink.ready = [&](size_t off, size_t len, const uint8_t* src) {
+    // pageable memory: the call returns when the driver has staged the chunk; the DMA itself runs under the next one
+    MB_CUDA_TRY(cudaMemcpyAsync(dev + off, src, len, cudaMemcpyHostToDevice, c->stream));
+    return (int)MB_OK;
+  };
+  const int rc = inflate_bam(path, n_threads, &S->bd, "mb_bam_stream_open_dev", &sink);
+  if (rc) { delete S; return rc; }
+  S->dev_ctx = c;
+  c->bam_resident = S;
+  *out = S;
+  return MB_OK;
+}
+extern "C" void mb_bam_stream_close(mb_bam_stream* S) {
+  if (S && S->dev_ctx && S->dev_ctx->bam_resident == S) S->dev_ctx->bam_resident = nullptr;
+  delete S;
+}
 extern "C" uint32_t mb_bam_stream_n_ref(const mb_bam_stream* S) { return S ? (uint32_t)S->bd.ref_name.size() : 0; }
 extern "C" const char* mb_bam_stream_ref_name(const mb_bam_stream* S, uint32_t i) {
   return S && i < S->bd.ref_name.size() ? S->bd.ref_name[i].c_str() : "";
@@ -385,6 +558,22 @@ int bam_stream_walk(const mb_bam_stream* S, const int32_t* tid_map, std::vector<
   uint64_t ncig = 0;
   rec_off->clear();
   cigar_off->clear();
+  if (S->bd.walked) {                       // mb_bam_stream_open_dev walked the chain behind the inflate
+    if (S->bd.walk_rc) return mb::fail(S->bd.walk_rc, "%s", S->bd.walk_msg.c_str());
+    const size_t n = S->bd.all_off.size();
+    rec_off->reserve(n + 1);
+    cigar_off->reserve(n + 2);
+    for (size_t i = 0; i < n; ++i) {
+      const int32_t rid = S->bd.all_rid[i];
+      if (rid >= 0 && tid_map[rid] >= 0) {
+        rec_off->push_back(S->bd.all_off[i]);
+        cigar_off->push_back(ncig);
+        ncig += S->bd.all_ncig[i];
+      }
+    }
+    cigar_off->push_back(ncig);
+    return MB_OK;
+  }
   rec_off->reserve((total - o) / 256 + 16);
   cigar_off->reserve((total - o) / 256 + 17);
   while (o + 4 <= total) {

@@ -1095,9 +1095,11 @@ int pack_from_bam_stream(mb_ctx* c, const mb_bam_stream* s, const int32_t* tid_m
     walk_ms = now() - t0;
   });
   void* d_data = nullptr;
+  const bool resident = c->bam_resident == s;          // mb_bam_stream_open_dev sent it while the host inflated
   int rc = mb::ctx_reserve(c, 24, total + 512, &d_data);
   cudaError_t e = cudaSuccess;
-  if (!rc) {
+  if (!rc && !resident) {
+    c->bam_resident = nullptr;
     e = cudaMemsetAsync((char*)d_data + total, 0, 512, st);
     if (e == cudaSuccess && total) e = cudaMemcpyAsync(d_data, data, total, cudaMemcpyHostToDevice, st);
   }
@@ -1134,10 +1136,12 @@ int pack_from_bam_stream(mb_ctx* c, const mb_bam_stream* s, const int32_t* tid_m
   if (rc) return rc;
   dev.seq = (const uint8_t*)d_data;
   dev.qual = (const uint8_t*)d_data;
+  phase("reserve");
   if (n) {
     MB_CUDA_TRY(cudaMemcpyAsync(d_rec, rec_off.data(), 8 * (size_t)n, cudaMemcpyHostToDevice, st));
     MB_CUDA_TRY(cudaMemcpyAsync((void*)dev.cigar_off, cig_off.data(), 8 * (size_t)(n + 1), cudaMemcpyHostToDevice, st));
     MB_CUDA_TRY(cudaMemcpyAsync(d_tid, tid_map, 4 * (size_t)n_ref, cudaMemcpyHostToDevice, st));
+    phase("h2d index");
     const uint32_t grid = (uint32_t)std::min<uint64_t>((n + 255) / 256, (uint64_t)c->sm_count * 8);
     k_bam_parse<<<grid, 256, 0, st>>>((const uint8_t*)d_data, (uint64_t)total, (const uint64_t*)d_rec, n, (const int32_t*)d_tid,
                                       dev.cigar_off, (int32_t*)dev.ref_id, (int32_t*)dev.pos, (uint8_t*)dev.mapq,

@@ -86,7 +86,7 @@ EXPORTS = [
     "mb_format_snps_bound", "mb_format_snps_rows",
     "mb_merge_sites_dev", "mb_format_merge_bound", "mb_format_merge_freq_rows", "mb_format_merge_depth_rows",
     "mb_bam_open", "mb_bam_close", "mb_bam_n_ref", "mb_bam_ref_name", "mb_bam_ref_len", "mb_bam_reads", "mb_bam_flags",
-    "mb_bam_stream_open", "mb_bam_stream_close", "mb_bam_stream_n_ref", "mb_bam_stream_ref_name", "mb_bam_stream_ref_len",
+    "mb_bam_stream_open", "mb_bam_stream_open_dev", "mb_bam_stream_close", "mb_bam_stream_n_ref", "mb_bam_stream_ref_name", "mb_bam_stream_ref_len",
     "mb_bam_stream_bytes", "mb_snps_pileup_bam", "mb_genes_coverage_bam",
 ]
 
@@ -185,6 +185,7 @@ def load():
     L.mb_bam_flags.argtypes = [C.c_void_p]
     L.mb_bam_flags.restype = C.c_void_p
     L.mb_bam_stream_open.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
+    L.mb_bam_stream_open_dev.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
     L.mb_bam_stream_close.argtypes = [C.c_void_p]
     L.mb_bam_stream_close.restype = None
     L.mb_bam_stream_n_ref.argtypes = [C.c_void_p]
@@ -651,10 +652,15 @@ class BamStream:
     """A BAM file inflated on the host threads (mb_bam_stream_open): header + the raw record stream, which the GPU
     parses (Context.snps_pileup_bam). No host-side record decode."""
 
-    def __init__(self, path: str, threads: int = 0):
+    def __init__(self, path: str, threads: int = 0, ctx: "Context" = None):
+        """With `ctx` (mb_bam_stream_open_dev) the inflated stream crosses PCIe while the host threads are still
+        inflating, and ctx.snps_pileup_bam / ctx.genes_coverage_bam find it on the device."""
         L = load()
         h = C.c_void_p()
-        _check(L.mb_bam_stream_open(os.fsencode(path), int(threads), C.byref(h)))
+        if ctx is not None:
+            _check(L.mb_bam_stream_open_dev(ctx._h, os.fsencode(path), int(threads), C.byref(h)))
+        else:
+            _check(L.mb_bam_stream_open(os.fsencode(path), int(threads), C.byref(h)))
         self._h = h
         n = int(L.mb_bam_stream_n_ref(h))
         self.names = [L.mb_bam_stream_ref_name(h, i).decode() for i in range(n)]

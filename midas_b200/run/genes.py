@@ -118,7 +118,7 @@ def count_mapped_bp(args, species, genes, ctx=None):
     try:
         # depth is one division of the integer sum (within 1e-12 of the reference's running float sum);
         # --exact_order reproduces the running sum bit for bit at the price of a device sort
-        stream = lib.BamStream(bam_path, threads)
+        stream = lib.BamStream(bam_path, threads, ctx=None if args.get("host_decode") else ctx)
         tid_map = np.array([gindex.get(n, -1) for n in stream.names], np.int32)
         if len(tid_map) and (tid_map >= 0).all() and not (gene_len[tid_map] == 0).any() and not args.get("host_decode"):
             # the streaming ingest: the host only inflates; the record stream is parsed, re-laid and counted on the GPU

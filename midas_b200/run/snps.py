@@ -199,14 +199,17 @@ def pysam_pileup(args, species, contigs, ctx=None):
     args["log"].write("\nCounting alleles\n")
     rank, world = _world()
     own_ctx = ctx is None
-    if own_ctx:
-        ctx = lib.Context(int(args.get("device", 0)), use_torch_stream=False)
     timing = args.get("timing")                     # optional dict: stage -> seconds (scripts/bench_pipeline.py)
 
     def lap(stage, t0):
         if timing is not None:
             timing[stage] = timing.get(stage, 0.0) + (time() - t0)
         return time()
+
+    if own_ctx:
+        t = time()
+        ctx = lib.Context(int(args.get("device", 0)), use_torch_stream=False)
+        lap("context_create", t)
 
     try:
         t = time()
@@ -217,7 +220,8 @@ def pysam_pileup(args, species, contigs, ctx=None):
         if world == 1 and not args.get("host_decode"):
             # the streaming ingest: host threads only inflate the BGZF blocks; the record stream goes to the GPU as it
             # is and the device parses, re-lays and counts it (mb_snps_pileup_bam)
-            stream = lib.BamStream(bampath, threads)
+            # (the stream crosses PCIe in chunks while the host threads inflate the rest: mb_bam_stream_open_dev)
+            stream = lib.BamStream(bampath, threads, ctx=ctx)
             ref = build_refset(species, contigs, stream.names)
             index = {n: k for k, n in enumerate(ref.contig_names)}
             tid_map = np.array([index.get(n, -1) for n in stream.names], np.int32)
@@ -282,7 +286,9 @@ def pysam_pileup(args, species, contigs, ctx=None):
         lap("tsv_gzip", t)
     finally:
         if own_ctx:
+            t = time()
             ctx.close()
+            lap("context_close", t)
     print("  %s minutes" % round((time() - start) / 60, 2))
 
 
@@ -311,6 +317,8 @@ def run_pipeline(args):
     start = time()
     species = initialize_species(args)
     contigs = initialize_contigs(species)
+    if args.get("timing") is not None:
+        args["timing"]["read_reference"] = time() - start
     print("  %s minutes" % round((time() - start) / 60, 2))
     if args.get("align"):
         sys.exit("\nError: the --align stage (bowtie2 | samtools) is not part of midas_b200; "

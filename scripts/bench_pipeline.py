@@ -1,14 +1,16 @@
 #!/usr/bin/env python
 """Stage times of the whole `run_midas.py snps --pileup` stage, from a coordinate-sorted BAM on disk to
-<species>.snps.gz + summary.txt, on a C2-shaped workload scaled down (the BAM writer used to make the
-fixture is pure Python). The stage replaces reference midas/run/snps.py:299-302 (index_bam, pysam_pileup,
-snps_summary); its steps here are: native BAM decode into page-locked arrays (mb_bam_open), one
-mb_snps_pileup_plain call (H2D of the decoded records + re-layout on the GPU + pileup + D2H), native row
-formatting + threaded multi-member gzip.
+<species>.snps.gz + summary.txt, on a C2-shaped workload (scaled by --scale; the BAM writer used to make the fixture
+is pure Python). The stage replaces reference midas/run/snps.py:299-302 (index_bam, pysam_pileup, snps_summary); its
+steps here are: BGZF inflate on the host threads with the inflated record stream crossing PCIe behind the inflate
+front and the record walk trailing it (mb_bam_stream_open_dev), one mb_snps_pileup_bam call (records parsed and
+re-laid on the GPU, pileup, D2H), native row formatting + threaded multi-member gzip. --host-decode times the
+round-1 path (records decoded on the host, mb_snps_pileup_plain) instead.
 
   python scripts/bench_pipeline.py [--scale 0.1] [--threads 16]
 
-One JSON line: seconds per stage, bases per second from BAM to the finished files."""
+One JSON line: seconds per stage (of the last of PIPE_REPS passes, default 2), bases per second from BAM to the
+finished files."""
 import argparse
 import gzip
 import io
@@ -60,7 +62,7 @@ def main():
                 "baseq": 30, "build_db": False, "align": False, "call": True, "remove_temp": False,
                 "log": io.StringIO(), "species_id": None, "device": 0, "host_decode": a.host_decode}
         best = None
-        for rep in range(2):                        # first pass pays CUDA context creation and page-cache misses
+        for rep in range(int(os.environ.get("PIPE_REPS", "2"))):   # first pass pays CUDA context creation and page-cache misses
             timing = {}
             args["timing"] = timing
             with open(os.devnull, "w") as devnull:

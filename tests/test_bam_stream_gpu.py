@@ -13,12 +13,27 @@ pytestmark = pytest.mark.gpu
 
 
 def _via_stream(ctx, path, ref, filters, tid_map=None, threads=4):
-    st = lib.BamStream(path, threads)
-    index = {n: k for k, n in enumerate(ref.contig_names)}
-    tm = np.array([index.get(n, -1) for n in st.names], np.int32) if tid_map is None else tid_map
+    """Both forms of the open: the stream uploaded by the pileup call, and uploaded chunk by chunk while the host
+    threads inflate (mb_bam_stream_open_dev); a second call on the resident stream, and a call with another stream
+    in between, must not disturb the result."""
     lay = lib.Layout.of(ref)
-    counts, stats, n_reads, n_bases = ctx.snps_pileup_bam(st, tm, lay, filters)
-    st.close()
+    out = []
+    for dev in (False, True, True):
+        st = lib.BamStream(path, threads, ctx=ctx if dev else None)
+        index = {n: k for k, n in enumerate(ref.contig_names)}
+        tm = np.array([index.get(n, -1) for n in st.names], np.int32) if tid_map is None else tid_map
+        if dev and len(out) == 2:
+            other = lib.BamStream(path, threads)              # replaces the resident copy: st is uploaded again
+            ctx.snps_pileup_bam(other, tm, lay, filters)
+            other.close()
+        out.append(ctx.snps_pileup_bam(st, tm, lay, filters))
+        if dev:
+            again = ctx.snps_pileup_bam(st, tm, lay, filters)
+            assert np.array_equal(again[0], out[-1][0]) and np.array_equal(again[1], out[-1][1])
+        st.close()
+    for o in out[1:]:
+        assert np.array_equal(o[0], out[0][0]) and np.array_equal(o[1], out[0][1]) and o[2:] == out[0][2:]
+    counts, stats, n_reads, n_bases = out[0]
     return lay, counts, stats, n_reads, n_bases
 
 
@@ -102,3 +117,46 @@ def test_genes_coverage_from_a_bam_file(ctx, tmp_path):
             else:
                 assert np.allclose(out["depth"], exp["depth"], rtol=1e-12, atol=0)
     st.close()
+
+
+@pytest.mark.parametrize("dev", [False, True])
+def test_malformed_streams(ctx, tmp_path, dev):
+    """Both forms of the open refuse what is not a BAM; a record whose block_size runs past the end of the stream or
+    whose fields exceed it is MB_EMALFORMED from the call that walks the records - never a crash."""
+    import struct
+    ref, reads = synth.synth_snps(seed=31, n_species=1, contigs_per_species=2, contig_len=4_000, n_reads=3_000)
+    good = str(tmp_path / "good.bam")
+    bam.write_bam(good, ref.contig_names, ref.contig_len, reads)
+    data = bytearray(bam.bgzf_decompress(open(good, "rb").read()))
+    lay = lib.Layout.of(ref)
+    tm = np.arange(ref.n_contigs, dtype=np.int32)
+
+    def run(payload, name):
+        p = str(tmp_path / name)
+        with open(p, "wb") as fh:
+            fh.write(bam.bgzf_compress(bytes(payload)))
+        st = lib.BamStream(p, 4, ctx=ctx if dev else None)
+        try:
+            return ctx.snps_pileup_bam(st, tm, lay, Filters())
+        finally:
+            st.close()
+
+    assert run(data, "ok.bam")[2] == reads.n_reads
+    with pytest.raises(lib.MidasB200Error) as e:
+        run(b"NOT\1" + bytes(data[4:]), "magic.bam")
+    assert e.value.status == -5
+    with pytest.raises(lib.MidasB200Error) as e:
+        run(data[:40], "header.bam")                      # the reference list is cut
+    assert e.value.status == -5
+    # first record: block_size far past the end
+    off = bam.read_bam_header(bytes(data))[3]
+    bad = bytearray(data)
+    struct.pack_into("<I", bad, off, 0x7FFFFFFF)
+    with pytest.raises(lib.MidasB200Error) as e:
+        run(bad, "trunc.bam")
+    assert e.value.status == -5
+    bad = bytearray(data)
+    struct.pack_into("<I", bad, off + 4 + 16, 0x00FFFFFF)   # l_seq larger than the record
+    with pytest.raises(lib.MidasB200Error) as e:
+        run(bad, "fields.bam")
+    assert e.value.status == -5

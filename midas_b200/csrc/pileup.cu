@@ -1334,15 +1334,9 @@ __global__ void __launch_bounds__(256) k_restat(const uint32_t* __restrict__ cou
 // width >= its row_words
 struct PileKernel { uint32_t W; void (*fn)(const PileParams); uint32_t kt; bool tma; bool sorted; bool defer = false; bool cta3 = false; bool bal = false; };   // kt: positions per tile
 PileKernel pick_kernel(uint32_t row_words, uint32_t q_planes, bool want_tma, int baseq, uint32_t max_units) {
-#define MB_PT(W, Q) {W, k_pileup_v2<W, Q, 4>, 2048, true, false}
-  static const PileKernel t6[] = {MB_PT(3, 6), MB_PT(4, 6), MB_PT(5, 6), MB_PT(6, 6), MB_PT(7, 6), MB_PT(8, 6)};
-  static const PileKernel t7[] = {MB_PT(3, 7), MB_PT(4, 7), MB_PT(5, 7), MB_PT(6, 7), MB_PT(7, 7), MB_PT(8, 7)};
-#undef MB_PT
-  if (want_tma && row_words <= 8) {
-    const PileKernel* k = q_planes == 6 ? t6 : t7;
-    for (int i = 0; i < 6; ++i)
-      if (k[i].W >= row_words) return k[i];
-  }
+  // the bulk-copy staging experiment (MB_PILE_TMA=1): the W = 6, six-plane instance only
+  static const PileKernel ktma = {6, k_pileup_v2<6, 6, 4>, 2048, true, false};
+  if (want_tma && q_planes == 6 && row_words > 5 && row_words <= 6) return ktma;
 #define MB_PK(W, Q) {W, k_pileup_v2<W, Q, 1096>, 2048, false, false, false, false, true}
   static const PileKernel k6[] = {MB_PK(3, 6), MB_PK(4, 6), MB_PK(5, 6),  MB_PK(6, 6),  MB_PK(7, 6),
                                   MB_PK(8, 6), MB_PK(10, 6), MB_PK(12, 6), MB_PK(16, 6)};

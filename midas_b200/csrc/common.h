@@ -98,6 +98,10 @@ struct mb_ctx {
   uint64_t units_layout;
   uint32_t units_len, n_units;
   uint32_t* sched;     // dynamic tile scheduler counters
+  // per-species stats of the launch in flight: zero between launches (the kernel's last CTA moves them to the
+  // caller's rows and clears them), so that no launch is spent on initialising the rows
+  unsigned long long* stats_acc;
+  size_t stats_acc_cap;
   // exact integer thresholds of the two floating-point read filters, per alen / l_qseq (see ctx.cu)
   int32_t* ftab;       // device: [2][65536]
   double ftab_mapid, ftab_cov;

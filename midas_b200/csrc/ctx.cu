@@ -167,6 +167,8 @@ extern "C" int mb_ctx_create(int device, mb_ctx** out) {
   c->units_len = 0;
   c->n_units = 0;
   c->sched = nullptr;
+  c->stats_acc = nullptr;
+  c->stats_acc_cap = 0;
   c->ftab = nullptr;
   c->ftab_valid = false;
   memset(c->stage, 0, sizeof(c->stage));
@@ -194,6 +196,7 @@ extern "C" int mb_ctx_create(int device, mb_ctx** out) {
     MB_CUDA_TRY(cudaEventCreate(&c->ring[i][1]));
   }
   MB_CUDA_TRY(cudaMalloc(&c->sched, 256));
+  MB_CUDA_TRY(cudaMemset(c->sched, 0, 256));        // the pileup kernel's last CTA leaves the counters at zero again
   *out = c;
   return MB_OK;
 }
@@ -230,6 +233,7 @@ extern "C" void mb_ctx_destroy(mb_ctx* c) {
   if (c->tile_rng) cudaFree(c->tile_rng);
   if (c->units) cudaFree(c->units);
   if (c->sched) cudaFree(c->sched);
+  if (c->stats_acc) cudaFree(c->stats_acc);
   if (c->ftab) cudaFree(c->ftab);
   for (int i = 0; i < mb_ctx::kRing; ++i) {
     cudaEventDestroy(c->ring[i][0]);

@@ -85,6 +85,8 @@ struct PileParams {
   uint32_t n_reads;
   uint32_t* ovf;              // set to 1 when a u32 counter saturates (MB_EOVERFLOW)
   unsigned long long* mirror; // peer-memory copy of the stats rows (multi-GPU), written by the last CTA; or null
+  unsigned long long* acc;    // [5 * n_species] the launch's running stats (zero before and after the launch)
+  const uint64_t* species_len;
   uint32_t n_species;
 };
 
@@ -1176,14 +1178,16 @@ __global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : ((VAR &
     if (tid < 4) {
       const int sp = p.tile_species[ts / MB_TILE];
       const unsigned long long v = s_red[tid];
-      if (sp >= 0 && v && !(p.defer_restat && tid < 2)) atomicAdd(&p.stats[5 * sp + 1 + tid], v);
+      if (sp >= 0 && v && !(p.defer_restat && tid < 2)) atomicAdd(&p.acc[5 * sp + 1 + tid], v);
     }
   }
   PROF_MARK(0);
   PROF_FINI;
-  // ---- multi-GPU: the last CTA to finish copies the finished stats rows into the peer buffer (e.g. rank 0's
-  // table over NVLink), so gathering the per-species rows needs no collective
-  if (p.mirror) {
+  // ---- the last CTA to finish moves the stats from the running rows to the caller's (genome_length: snps.py:211),
+  // clears the running rows and the scheduler counters for the next launch - no separate initialisation launch - and,
+  // multi-GPU, copies the finished rows into the peer buffer (e.g. rank 0's table over NVLink), so that gathering the
+  // per-species rows needs no collective
+  {
     __shared__ uint32_t s_last;
     __threadfence();
     __syncthreads();
@@ -1191,8 +1195,14 @@ __global__ void __launch_bounds__((VAR & 2) ? 128 : 256, (VAR & 2) ? 4 : ((VAR &
     __syncthreads();
     if (s_last) {
       __threadfence();
-      for (uint32_t i = tid; i < 5u * p.n_species; i += NT) p.mirror[i] = __ldcg(p.stats + i);
-      __threadfence_system();
+      for (uint32_t i = tid; i < 5u * p.n_species; i += NT) {
+        const unsigned long long v = i % 5u == 0 ? (unsigned long long)p.species_len[i / 5u] : __ldcg(p.acc + i);
+        p.stats[i] = v;
+        if (p.mirror) p.mirror[i] = v;
+        p.acc[i] = 0;
+      }
+      if (tid == 0) { p.sched[0] = 0; p.sched[1] = 0; }
+      if (p.mirror) __threadfence_system();
     }
   }
 }
@@ -1543,10 +1553,20 @@ extern "C" int mb_snps_pileup_dev(mb_ctx* ctx, const mb_dev_reads* reads, const 
   }
   cudaStream_t st = ctx->stream;
   const uint32_t ns = L->n_species;
-  k_init_stats<<<ns ? (ns + 255) / 256 : 1, 256, 0, st>>>(
-      reinterpret_cast<unsigned long long*>(stats_dev), dl.species_len, ns, ctx->sched);
-  ctx->launches++;
+  if (ctx->stats_acc_cap < 5 * (size_t)ns + 8) {
+    if (ctx->stats_acc) { MB_CUDA_TRY(cudaStreamSynchronize(st)); MB_CUDA_TRY(cudaFree(ctx->stats_acc)); }
+    ctx->stats_acc = nullptr;
+    ctx->stats_acc_cap = 0;
+    const size_t cap = 5 * (size_t)ns + 64;
+    MB_CUDA_TRY(cudaMalloc(&ctx->stats_acc, sizeof(unsigned long long) * cap));
+    MB_CUDA_TRY(cudaMemsetAsync(ctx->stats_acc, 0, sizeof(unsigned long long) * cap, st));
+    ctx->stats_acc_cap = cap;
+  }
   if (n_ktiles == 0) {
+    // nothing to count: the rows are initialised by a launch of their own (genome_length, zeros)
+    k_init_stats<<<ns ? (ns + 255) / 256 : 1, 256, 0, st>>>(
+        reinterpret_cast<unsigned long long*>(stats_dev), dl.species_len, ns, ctx->sched);
+    ctx->launches++;
     if (ctx->stats_mirror && ns) {
       k_mirror_stats<<<1, 256, 0, st>>>(reinterpret_cast<unsigned long long*>(stats_dev),
                                         reinterpret_cast<unsigned long long*>(ctx->stats_mirror), 5u * ns);
@@ -1593,6 +1613,8 @@ extern "C" int mb_snps_pileup_dev(mb_ctx* ctx, const mb_dev_reads* reads, const 
   p.ovf = ctx->ovf;
   p.mirror = reads->n_long ? nullptr : reinterpret_cast<unsigned long long*>(ctx->stats_mirror);
   p.n_species = ns;
+  p.acc = ctx->stats_acc;
+  p.species_len = dl.species_len;
   const uint32_t grid = min(n_ktiles, P);
   { int trc = mb::timing_begin(ctx); if (trc) return trc; }
   kern.fn<<<grid, NT, pile_smem_bytes(W, rmax, NCOL, slot_units, NT / 32, kern.sorted, kern.defer), st>>>(p);

@@ -30,6 +30,7 @@ struct GeneParams {
   const uint4* hdr;
   const uint32_t* vec_off;
   const uint32_t* planes;   // genes-mode packing: q_planes words per 32-base block, regions in 32-byte units
+  const uint32_t* zero_unit;  // 32 bytes of zeros (the slack behind planes[]): what a load past a read's end fetches
   uint64_t n_reads;
   unsigned long long* out;  // mb_gene_out as 3 x u64: [aligned|mapped<<32], mapped_bp, depth bits
   uint32_t* key;            // exact order: per read, gene index if kept else 0xFFFFFFFF (may be null)
@@ -46,12 +47,26 @@ __global__ void __launch_bounds__(GENE_THREADS) k_genes_v2(const GeneParams p) {
   // One thread per read: its Phred planes are up to NQ independent 256-bit loads per step (a 150-base
   // read is 4 of them, all in flight at once); the units of 32 consecutive reads are interleaved in
   // memory, so each of a warp's loads reads 1 KB of consecutive bytes.
+  // Per read three dependent round trips would be exposed (header -> filter tables -> planes); instead the header
+  // of the thread's next read is requested one iteration ahead and the first NQ units of the planes are requested as
+  // soon as the header is there, before the filter tables are consulted (a filtered read's planes are fetched and
+  // dropped: the byte model counts every read's planes anyway).
   const uint64_t stride = (uint64_t)gridDim.x * GENE_THREADS;
-  for (uint64_t r = (uint64_t)blockIdx.x * GENE_THREADS + threadIdx.x; r < p.n_reads; r += stride) {
-    const uint4 h = __ldg(&p.hdr[r]);
-    const uint32_t v0 = __ldg(&p.vec_off[r]);
+  uint64_t r = (uint64_t)blockIdx.x * GENE_THREADS + threadIdx.x;
+  uint4 nh = make_uint4(0, 0, 0, 0);
+  uint32_t nv0 = 0;
+  if (r < p.n_reads) { nh = __ldg(&p.hdr[r]); nv0 = __ldg(&p.vec_off[r]); }
+  for (; r < p.n_reads; r += stride) {
+    const uint4 h = nh;
+    const uint32_t v0 = nv0;
+    if (r + stride < p.n_reads) { nh = __ldg(&p.hdr[r + stride]); nv0 = __ldg(&p.vec_off[r + stride]); }
     const uint32_t gene = h.x, lq = h.y & 0xffffu, alen = h.y >> 16;
     const uint32_t nm = h.z >> 16, mq = (h.w >> 16) & 0xffu, fl = h.w >> 24;
+    const uint32_t nv8 = (((lq + 31u) >> 5) * (uint32_t)NQ + 7u) >> 3;
+    const uint32_t* __restrict__ q = p.planes + (size_t)v0 * 8;
+    uint32_t v[8 * NQ];                                   // NQ 256-bit loads = 8 blocks: plane of word i is i % NQ
+#pragma unroll
+    for (int u = 0; u < NQ; ++u) ldg256((uint32_t)u < nv8 ? q + (size_t)u * (8 * MB_GROUP) : p.zero_unit, v + 8 * u);
     // exact integer forms of the two double-precision tests of keep_read (tables built in ctx.cu)
     bool ok = (fl & MB_RF_NMSAT) ? (p.pid_always != 0)
                                  : (100 * ((int)alen - (int)nm) >= __ldg(p.t_pid + alen));   // genes.py:157
@@ -59,29 +74,31 @@ __global__ void __launch_bounds__(GENE_THREADS) k_genes_v2(const GeneParams p) {
     ok = ok && (int)alen >= __ldg(p.t_cov + lq);                                              // genes.py:166
     bool keep = false;
     if (ok) {
-      // mean-quality test genes.py:160: mean(q) < readq  <=>  sum(q) < readq * l_qseq (exact)
-      const uint32_t nv8 = (((lq + 31u) >> 5) * (uint32_t)NQ + 7u) >> 3;
-      const uint32_t* __restrict__ q = p.planes + (size_t)v0 * 8;
+      // mean-quality test genes.py:160: mean(q) < readq  <=>  sum(q) < readq * l_qseq (exact). The two top planes
+      // alone bound the sum from below and settle all but poor reads.
+      const uint32_t thr = p.readq_eff * lq;
       uint32_t pc[NQ];
 #pragma unroll
       for (int k = 0; k < NQ; ++k) pc[k] = 0;
-      for (uint32_t b = 0; b < nv8; b += NQ) {            // NQ 256-bit loads = 8 blocks: plane of word i is i % NQ
-        uint32_t v[8 * NQ];
 #pragma unroll
-        for (int u = 0; u < NQ; ++u) {
-          if (b + (uint32_t)u < nv8) ldg256(q + (size_t)(b + u) * (8 * MB_GROUP), v + 8 * u);
-          else {
+      for (int i = 0; i < 8 * NQ; ++i)
+        if (i % NQ >= NQ - 2) pc[i % NQ] += __popc(v[i]);
+      keep = (pc[NQ - 1] << (NQ - 1)) + (pc[NQ - 2] << (NQ - 2)) >= thr;   // (of the first 256 bases: still a lower bound)
+      if (!keep) {
 #pragma unroll
-            for (int c = 0; c < 8; ++c) v[8 * u + c] = 0;
-          }
+        for (int i = 0; i < 8 * NQ; ++i)
+          if (i % NQ < NQ - 2) pc[i % NQ] += __popc(v[i]);
+        for (uint32_t b = NQ; b < nv8; b += NQ) {          // reads longer than 256 bases
+#pragma unroll
+          for (int u = 0; u < NQ; ++u) ldg256(b + (uint32_t)u < nv8 ? q + (size_t)(b + u) * (8 * MB_GROUP) : p.zero_unit, v + 8 * u);
+#pragma unroll
+          for (int i = 0; i < 8 * NQ; ++i) pc[i % NQ] += __popc(v[i]);
         }
+        uint32_t s = 0;
 #pragma unroll
-        for (int i = 0; i < 8 * NQ; ++i) pc[i % NQ] += __popc(v[i]);
+        for (int k = 0; k < NQ; ++k) s += pc[k] << k;
+        keep = s >= thr;
       }
-      uint32_t s = 0;
-#pragma unroll
-      for (int k = 0; k < NQ; ++k) s += pc[k] << k;
-      keep = s >= p.readq_eff * lq;
     }
     if (gene < p.n_genes) {
       unsigned long long* o = p.out + (size_t)gene * 3;
@@ -157,6 +174,7 @@ extern "C" int mb_genes_coverage_dev(mb_ctx* ctx, const mb_dev_reads* reads, con
   p.hdr = reinterpret_cast<const uint4*>(reads->hdr);
   p.vec_off = reads->vec_off;
   p.planes = reads->planes;
+  p.zero_unit = reads->planes + (size_t)reads->n_vec * 8;       // the uploads keep 256 zero bytes behind every array
   p.n_reads = reads->n_reads;
   p.out = reinterpret_cast<unsigned long long*>(out_dev);
   p.key = key;

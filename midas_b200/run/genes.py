@@ -195,9 +195,14 @@ def write_results(args, species, genes):
     for gene_id in sorted(genes):
         g = genes[gene_id]
         rows[g.species_id].append(_tsv((g.id, g.mapped_reads, g.depth, g.copies)))
+    threads = int(args.get("threads", 1) or 1)
     for sid, lines in rows.items():
-        out = mio.iopen("%s/genes/output/%s.genes.gz" % (args["outdir"], sid), "w")
-        out.write("".join(lines))
+        # independent gzip members compressed on the host threads (gzip.open() at level 9 on one thread would be
+        # the slowest step of the stage at pangenome scale)
+        out = mio.GzipMembersWriter("%s/genes/output/%s.genes.gz" % (args["outdir"], sid),
+                                    level=args.get("gzip_level"), threads=threads)
+        for lo in range(0, len(lines), 1 << 15):
+            out.write("".join(lines[lo:lo + (1 << 15)]).encode())
         out.close()
     with open("%s/genes/summary.txt" % args["outdir"], "w") as fh:
         fh.write(_tsv(SUMMARY_HEADER))

@@ -146,9 +146,9 @@ def load_alignments(bampath, species, contigs, threads=0, pinned=False):
     return ref, reads
 
 
-def write_species_tsv(path, ref: RefSet, contigs, layout, counts, species_index, threads=8):
+def write_species_tsv(path, ref: RefSet, contigs, layout, counts, species_index, threads=8, level=None):
     """<species>.snps.gz (reference snps.py:179-182 header, :201-210 rows)."""
-    out = mio.GzipMembersWriter(path, threads=threads)
+    out = mio.GzipMembersWriter(path, level=level, threads=threads)
     out.write(b"ref_id\tref_pos\tref_allele\tdepth\tcount_a\tcount_c\tcount_g\tcount_t\n")
     index = {cid: c for c, cid in enumerate(ref.contig_names)}
     for cid in sorted(index):                                      # species_pileup's order, snps.py:187
@@ -275,7 +275,8 @@ def pysam_pileup(args, species, contigs, ctx=None):
         for k, g in enumerate(mine):
             if writes[k]:
                 out_path = "%s/snps/output/%s.snps.gz" % (args["outdir"], ref.species_ids[g])
-                write_species_tsv(out_path, sub_ref, contigs, layout, counts, k, threads=threads)
+                write_species_tsv(out_path, sub_ref, contigs, layout, counts, k, threads=threads,
+                                  level=args.get("gzip_level"))
         for g, species_id in enumerate(ref.species_ids):
             sp = species[species_id]
             sp.genome_length, sp.covered_bases, sp.total_depth, sp.aligned_reads, sp.mapped_reads = (int(x) for x in rows[g])

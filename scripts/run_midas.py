@@ -53,6 +53,8 @@ def _common(parser):
     parser.add_argument("-n", type=int, dest="max_reads")
     parser.add_argument("-t", dest="threads", default=1)
     parser.add_argument("--device", type=int, default=0, help="CUDA device (this package only)")
+    parser.add_argument("--gzip_level", type=int, default=None, choices=range(1, 10), metavar="1-9",
+                        help="zlib level of the .gz outputs (this package only; default 1: the stage is zlib-bound)")
     parser.add_argument("--build_db", action="store_true", default=False)
     parser.add_argument("--align", action="store_true", default=False)
 

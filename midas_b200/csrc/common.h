@@ -150,5 +150,6 @@ const uint8_t* bam_stream_data(const mb_bam_stream* S, size_t* total);
 int bam_stream_walk(const mb_bam_stream* S, const int32_t* tid_map, std::vector<uint64_t>* rec_off,
                     std::vector<uint64_t>* cigar_off);
 void free_dev_reads_arrays(mb_dev_reads* d);
+bool fast_inflate(const uint8_t* in, size_t in_len, size_t in_slack, uint8_t* out, size_t out_len);
 int check_overflow(mb_ctx* ctx, const char* who);   // after a stream sync: MB_EOVERFLOW if the flag is set (and clears it)
 }  // namespace mb

@@ -266,9 +266,17 @@ static int inflate_bam(const char* path, int n_threads, BamData* B, const char* 
   if (!data.resize(total + 64)) return mb::fail(MB_ENOMEM, "%s: out of memory", who);
   std::atomic<int> bad_flag{0};
   std::atomic<int>* bad = &bad_flag;
+  static const bool use_zlib_only = [] { const char* e = getenv("MB_INFLATE"); return e && !strcmp(e, "zlib"); }();
+  std::atomic<uint64_t> n_fallback{0};
   auto inflate_block = [&](size_t i) {
     const Blk& k = blks[i];
     if (!k.isize) return true;
+    // the block decoder of host_inflate.cpp first (the 8-byte CRC / ISIZE footer behind the data is its read slack);
+    // whatever it refuses, or whatever fails the CRC after it, goes through zlib
+    if (!use_zlib_only && mb::fast_inflate(raw.data() + k.cbeg, k.clen, 8, data.data() + k.dst, k.isize) &&
+        crc32(0L, data.data() + k.dst, k.isize) == rd32(raw.data() + k.cbeg + k.clen))
+      return true;
+    n_fallback.fetch_add(1, std::memory_order_relaxed);
     z_stream zs;
     memset(&zs, 0, sizeof(zs));
     if (inflateInit2(&zs, -15) != Z_OK) return false;
@@ -365,6 +373,7 @@ static int inflate_bam(const char* path, int n_threads, BamData* B, const char* 
   }
   if (bad->load()) return mb::fail(MB_EMALFORMED, "%s: %s: BGZF inflate / CRC failure", who, path);
   raw.release();
+  if (timing) fprintf(stderr, "%s: %llu of %zu blocks through zlib\n", who, (unsigned long long)n_fallback.load(), blks.size());
   phase("inflate");
   // 3. header
   memset(data.data() + total, 0, 64);

@@ -3,6 +3,7 @@ import os
 import sys
 
 import numpy as np
+import pytest
 
 import gen
 from midas_b200 import bam
@@ -88,3 +89,26 @@ def test_native_reader_rejects_garbage(tmp_path):
     assert e.value.status == -5
     with pytest.raises(lib.MidasB200Error):
         lib.read_bam(str(tmp_path / "missing.bam"))
+
+
+@pytest.mark.parametrize("level", [0, 1, 4, 9])
+def test_native_reader_inflates_every_kind_of_block(tmp_path, level, capfd, monkeypatch):
+    """The library's own DEFLATE decoder (csrc/host_inflate.cpp; CRC-checked, zlib behind it for whatever it refuses)
+    on BGZF blocks written at several zlib levels - stored blocks at level 0, fixed-Huffman blocks for tiny members,
+    dynamic ones otherwise - must hand the readers the same bytes as Python's zlib, and must be the path taken."""
+    from midas_b200 import lib
+    monkeypatch.setenv("MB_BAM_TIMING", "1")
+    for seed, n_reads, max_len in ((1, 2500, 150), (2, 12, 40), (3, 9000, 300)):
+        rng = np.random.default_rng(100 + seed)
+        ref = gen.make_ref(rng, 2, 2, 3000, 9000)
+        reads = gen.random_reads(seed, ref, n_reads, max_len=max_len)
+        p = str(tmp_path / f"l{level}_{seed}.bam")
+        bam.write_bam(p, ref.contig_names, ref.contig_len, reads, level=level)
+        n1, l1, r1 = bam.read_bam(p)
+        capfd.readouterr()
+        n2, l2, r2 = lib.read_bam(p, 3, seq_bytes=True)
+        err = capfd.readouterr().err
+        assert n1 == n2
+        for f in ("ref_id", "pos", "mapq", "nm", "l_qseq", "cigar_off", "cigar", "seq_off", "seq", "qual"):
+            assert np.array_equal(getattr(r1, f), getattr(r2, f)), f
+        assert " 0 of " in err and "blocks through zlib" in err, err          # no block needed the fallback

@@ -587,18 +587,38 @@ int bam_stream_walk(const mb_bam_stream* S, const int32_t* tid_map, std::vector<
   cigar_off->clear();
   if (S->bd.walked) {                       // mb_bam_stream_open_dev walked the chain behind the inflate
     if (S->bd.walk_rc) return mb::fail(S->bd.walk_rc, "%s", S->bd.walk_msg.c_str());
+    // keep the records of the references tid_map keeps; their CIGAR offsets are the running sum of n_cigar. Two
+    // passes over slices of the record list on the host threads (count, then fill behind the slices' prefix sums).
     const size_t n = S->bd.all_off.size();
-    rec_off->reserve(n + 1);
-    cigar_off->reserve(n + 2);
-    for (size_t i = 0; i < n; ++i) {
-      const int32_t rid = S->bd.all_rid[i];
-      if (rid >= 0 && tid_map[rid] >= 0) {
-        rec_off->push_back(S->bd.all_off[i]);
-        cigar_off->push_back(ncig);
-        ncig += S->bd.all_ncig[i];
+    const int T = (int)std::min<size_t>(std::max(1u, std::min(16u, std::thread::hardware_concurrency())), n / 65536 + 1);
+    const size_t per = (n + (size_t)T - 1) / (size_t)T;
+    std::vector<uint64_t> kept(T + 1, 0), cig(T + 1, 0);
+    const int32_t* rid = S->bd.all_rid.data();
+    const uint32_t* nc = S->bd.all_ncig.data();
+    const uint64_t* off = S->bd.all_off.data();
+    pfor((size_t)T, T, [&](size_t lo, size_t hi) {
+      for (size_t t = lo; t < hi; ++t) {
+        uint64_t k = 0, c = 0;
+        for (size_t i = t * per, e = std::min(n, i + per); i < e; ++i)
+          if (rid[i] >= 0 && tid_map[rid[i]] >= 0) { ++k; c += nc[i]; }
+        kept[t + 1] = k;
+        cig[t + 1] = c;
       }
-    }
-    cigar_off->push_back(ncig);
+    });
+    for (int t = 0; t < T; ++t) { kept[t + 1] += kept[t]; cig[t + 1] += cig[t]; }
+    rec_off->resize(kept[T]);
+    cigar_off->resize(kept[T] + 1);
+    uint64_t* ro = rec_off->data();
+    uint64_t* co = cigar_off->data();
+    pfor((size_t)T, T, [&](size_t lo, size_t hi) {
+      for (size_t t = lo; t < hi; ++t) {
+        uint64_t k = kept[t], c = cig[t];
+        for (size_t i = t * per, e = std::min(n, i + per); i < e; ++i)
+          if (rid[i] >= 0 && tid_map[rid[i]] >= 0) { ro[k] = off[i]; co[k] = c; ++k; c += nc[i]; }
+      }
+    });
+    co[kept[T]] = cig[T];
+    (void)ncig;
     return MB_OK;
   }
   rec_off->reserve((total - o) / 256 + 16);

@@ -14,6 +14,8 @@ Flags, defaults, directory layout, log.txt and the on-disk outputs follow the re
     the species are dealt to the ranks (midas_b200.shard.plan: the reference's own unit of parallelism, one worker
     per species, midas/run/snps.py:225-228), every rank writes its species' .snps.gz, rank 0 writes summary.txt,
     log.txt and readme.txt. Without torchrun, --device picks the GPU.
+  * --gzip_level N: zlib level of the .gz outputs (default 1; the reference's gzip.open() uses 9). The files hold the
+    same bytes once decompressed.
 log.txt (opened 'w', parameter block) and readme.txt follow the reference (:432-481, :290-336, :630-746).
 """
 import argparse

@@ -1468,7 +1468,7 @@ extern "C" int mb_snps_pileup_dev(mb_ctx* ctx, const mb_dev_reads* reads, const 
   // order from an atomic counter. Phase clocks (profiles/r02r_phase.log) show the CTAs of a C2 launch finishing up to
   // one unit time apart (6.6 units of 2048 positions per CTA, SMs differ in speed by a few per cent): 7-10 % of the
   // CTA time idle at the tail. So the units get shorter towards the end of the genome - half length over the last
-  // 15 % of the positions, quarter length over the last 5 % - and the last claims are small. Shorter units stage more
+  // 10 % of the positions, quarter length over the last 3 % - and the last claims are small. Shorter units stage more
   // reads twice (those that straddle a boundary), which is why only the tail gets them. MB_PILE_UNIT overrides the
   // (then uniform) length (tests, sweeps).
   const uint32_t P = (uint32_t)(ctx->sm_count * ctx->pile_occ);
@@ -1483,7 +1483,7 @@ extern "C" int mb_snps_pileup_dev(mb_ctx* ctx, const mb_dev_reads* reads, const 
   if (ctx->units_layout != L->id || ctx->units_len != unit_len || getenv("MB_PILE_GUIDE")) {
     std::vector<uint2> tab;
     const uint32_t base_len = unit_len & ~31u;
-    uint64_t pct_half = 85, pct_quarter = 95;                       // MB_PILE_GUIDE="half,quarter" (per cent): sweeps
+    uint64_t pct_half = 90, pct_quarter = 97;                       // MB_PILE_GUIDE="half,quarter" (per cent): sweeps
     if (const char* e = getenv("MB_PILE_GUIDE")) {
       unsigned a = 0, b = 0;
       if (sscanf(e, "%u,%u", &a, &b) == 2 && a <= b && b <= 100) { pct_half = a; pct_quarter = b; }

@@ -9,26 +9,30 @@
 // The count is integer and HBM-bound (about 1.4 B per base in, 16 B per position out), so the
 // design removes every per-base atomic and every per-base scalar operation that it can:
 //
-//   * the padded genome is cut into KT-position tiles; reads are sorted by coordinate, so the reads
-//     overlapping a tile are one contiguous index range (k_tile_ranges) and a CTA owns a tile;
+//   * the padded genome is cut into work units of at most KT positions (shorter towards the end of the genome, so that
+//     the last claims of the persistent grid are small); reads are sorted by coordinate, so the reads overlapping a
+//     unit are one contiguous index range (k_tile_ranges) and a CTA owns a unit;
 //   * STAGE: one thread turns one read into a *bit-plane row in reference coordinates*, entirely in
 //     registers: the read's bit planes (mb_packed_reads: 32 bases per word) arrive as independent
 //     256-bit loads (the 32-byte units of 32 consecutive reads are interleaved, so each load of a warp
-//     is 1 KB of consecutive memory), Phred >= baseq is a bit-sliced comparator (one LOP3 per Phred bit per 32 bases,
-//     no per-base work at all), the Phred sum is one POPC per plane word, the two sequence planes are
+//     is 1 KB of consecutive memory), issued as soon as the read's header is there and before its filters are
+//     evaluated; Phred >= baseq is a bit-sliced comparator (one LOP3 per Phred bit per 32 bases, two per 32 bases in
+//     the instance for baseq = 30; no per-base work at all), the Phred sum is one POPC per plane word (and the two top
+//     planes alone settle the mean-quality test for all but poor reads), the two sequence planes are
 //     taken as they lie in HBM, and each CIGAR run is one funnel shift per plane per 32-position
 //     word (the packer has already cleared the candidate bit of every base outside an M/=/X run, so
 //     single-run reads need no masks). The row is stored in shared memory as W x {A,C,G,T} 32-bit
 //     masks aligned to the global 32-position grid;
-//   * COUNT: a lane owns a 32-position column and adds the rows covering it with carry-save adders
-//     into bit-sliced ("vertical") counters held in registers: one LOP3 works on 32 positions at
-//     once, ~0.6 instructions per aligned base instead of one shared-memory atomic per base;
-//     KSUB lanes share a column (rows strided) and are merged by a shuffle butterfly of bit-sliced
-//     adders into shared-memory vertical counters;
+//   * COUNT: the 32-position columns a round of rows touches are dealt over all threads of the CTA (4 NS lanes per
+//     column: a lane adds one class word of every NS-th row of its column with a 16-row carry-save tree into
+//     bit-sliced ("vertical") counters held in registers: one LOP3 works on 32 positions at once); the NS partial
+//     counters are merged by a shuffle butterfly of bit-sliced adders into shared-memory vertical counters.
+//     (The round-1 form - a fixed lane -> column map, KSUB lanes per column - is kept behind MB_PILE_VAR=8.)
 //   * EXPAND: the vertical counters are transposed to u32 counts (4 positions per thread, multiply
 //     spread), depth / covered_bases / total_depth are reduced on the way, and the four planes are
 //     written with coalesced 128-bit stores. Every output element is written exactly once, no
-//     pre-zeroing, no global atomics on counters.
+//     pre-zeroing, no global atomics on counters. The last CTA to finish hands the per-species stats rows to the
+//     caller and clears the running rows and the scheduler counters: a call is one launch.
 //
 // Reads that straddle a tile boundary are staged by both tiles (each counts only its own columns);
 // the tile containing a read's start owns it for aligned_reads / mapped_reads. Reads that do not

@@ -263,69 +263,79 @@ bool fast_inflate(const uint8_t* in, size_t in_len, size_t in_slack, uint8_t* ou
     // fast loop: while a whole refill word can be read and the longest match plus the copy overshoot fits, nothing
     // inside needs a bounds check but the match distance
     constexpr uint32_t LMASK = (1u << LIT_BITS) - 1, DMASK = (1u << DIST_BITS) - 1;
-    while (fast_ok && ip <= in_fast_end && (size_t)(out_end - op) >= 258 + 16) {
-      bb |= load64(ip) << bc;
-      ip += (63 - bc) >> 3;
-      bc |= 56;
+    // Invariant at the top: the bit buffer has just been refilled (>= 56 bits) and `e` is the entry its low bits select,
+    // looked up before the previous symbol's output was written - the table load runs under the copy.
+    if (fast_ok && ip <= in_fast_end && (size_t)(out_end - op) >= 258 + 16) {
+#define MB_REFILL() do { bb |= load64(ip) << bc; ip += (63 - bc) >> 3; bc |= 56; } while (0)
+      MB_REFILL();
       uint32_t e = lt[bb & LMASK];
-      if (e & F_LITERAL) {                                   // up to three literals per refill (<= 45 bits)
-        bb >>= e_len(e); bc -= (int)e_len(e);
-        *op++ = (uint8_t)e_value(e);
-        e = lt[bb & LMASK];
-        if (e & F_LITERAL) {
+      while (ip <= in_fast_end && (size_t)(out_end - op) >= 258 + 16) {
+        if (e & F_LITERAL) {                                 // up to three literals (<= 30 bits), then the next entry
           bb >>= e_len(e); bc -= (int)e_len(e);
           *op++ = (uint8_t)e_value(e);
           e = lt[bb & LMASK];
           if (e & F_LITERAL) {
             bb >>= e_len(e); bc -= (int)e_len(e);
             *op++ = (uint8_t)e_value(e);
+            e = lt[bb & LMASK];
+            if (e & F_LITERAL) {
+              bb >>= e_len(e); bc -= (int)e_len(e);
+              *op++ = (uint8_t)e_value(e);
+              e = lt[bb & LMASK];
+            }
           }
-        }
-        continue;
-      }
-      if (e & F_SUB) {
-        bb >>= LIT_BITS; bc -= LIT_BITS;
-        e = lt[e_value(e) + (uint32_t)(bb & ((1u << e_extra(e)) - 1))];
-        if (e & F_LITERAL) {
-          bb >>= e_len(e); bc -= (int)e_len(e);
-          *op++ = (uint8_t)e_value(e);
+          MB_REFILL();                                       // (the low bits `e` was selected by are unchanged)
           continue;
         }
-      }
-      bb >>= e_len(e); bc -= (int)e_len(e);
-      if (e & (F_EOB | F_BAD)) {
-        if (e & F_BAD) return false;
-        eob = true;
-        break;
-      }
-      const uint32_t length = e_value(e) + (uint32_t)(bb & ((1u << e_extra(e)) - 1));
-      bb >>= e_extra(e); bc -= (int)e_extra(e);
-      uint32_t d = dt[bb & DMASK];
-      if (d & F_SUB) {
-        bb >>= DIST_BITS; bc -= DIST_BITS;
-        d = dt[e_value(d) + (uint32_t)(bb & ((1u << e_extra(d)) - 1))];
-      }
-      if (d & F_BAD) return false;
-      bb >>= e_len(d); bc -= (int)e_len(d);
-      const uint32_t dist = e_value(d) + (uint32_t)(bb & ((1u << e_extra(d)) - 1));
-      bb >>= e_extra(d); bc -= (int)e_extra(d);
-      if (dist > (size_t)(op - out)) return false;
-      const uint8_t* src = op - dist;
-      uint8_t* const stop = op + length;
-      if (dist >= 8) {
-        memcpy(op, src, 8); memcpy(op + 8, src + 8, 8);      // most matches are short: two words, then the rest
-        if (length > 16) {
-          op += 16; src += 16;
-          do { memcpy(op, src, 8); op += 8; src += 8; } while (op < stop);
+        if (e & F_SUB) {
+          bb >>= LIT_BITS; bc -= LIT_BITS;
+          e = lt[e_value(e) + (uint32_t)(bb & ((1u << e_extra(e)) - 1))];
+          if (e & F_LITERAL) {
+            bb >>= e_len(e); bc -= (int)e_len(e);
+            *op++ = (uint8_t)e_value(e);
+            e = lt[bb & LMASK];
+            MB_REFILL();
+            continue;
+          }
         }
-      } else if (dist == 1) {
-        uint64_t v = *src;
-        v *= 0x0101010101010101ull;
-        do { memcpy(op, &v, 8); op += 8; } while (op < stop);
-      } else {
-        do { *op++ = *src++; } while (op < stop);
+        bb >>= e_len(e); bc -= (int)e_len(e);
+        if (e & (F_EOB | F_BAD)) {
+          if (e & F_BAD) return false;
+          eob = true;
+          break;
+        }
+        const uint32_t length = e_value(e) + (uint32_t)(bb & ((1u << e_extra(e)) - 1));
+        bb >>= e_extra(e); bc -= (int)e_extra(e);
+        uint32_t d = dt[bb & DMASK];
+        if (d & F_SUB) {
+          bb >>= DIST_BITS; bc -= DIST_BITS;
+          d = dt[e_value(d) + (uint32_t)(bb & ((1u << e_extra(d)) - 1))];
+        }
+        if (d & F_BAD) return false;
+        bb >>= e_len(d); bc -= (int)e_len(d);
+        const uint32_t dist = e_value(d) + (uint32_t)(bb & ((1u << e_extra(d)) - 1));
+        bb >>= e_extra(d); bc -= (int)e_extra(d);
+        MB_REFILL();
+        e = lt[bb & LMASK];                                  // the next symbol's entry: in flight during the copy
+        if (dist > (size_t)(op - out)) return false;
+        const uint8_t* src = op - dist;
+        uint8_t* const stop = op + length;
+        if (dist >= 8) {
+          memcpy(op, src, 8); memcpy(op + 8, src + 8, 8);    // most matches are short: two words, then the rest
+          if (length > 16) {
+            op += 16; src += 16;
+            do { memcpy(op, src, 8); op += 8; src += 8; } while (op < stop);
+          }
+        } else if (dist == 1) {
+          uint64_t v = *src;
+          v *= 0x0101010101010101ull;
+          do { memcpy(op, &v, 8); op += 8; } while (op < stop);
+        } else {
+          do { *op++ = *src++; } while (op < stop);
+        }
+        op = stop;
       }
-      op = stop;
+#undef MB_REFILL
     }
     if (!eob && bc < 64) bb &= ((uint64_t)1 << bc) - 1;      // the careful loop below ORs bytes in: clear what lies above
     if (!eob) for (;;) {

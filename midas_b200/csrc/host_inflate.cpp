@@ -287,31 +287,36 @@ bool fast_inflate(const uint8_t* in, size_t in_len, size_t in_slack, uint8_t* ou
           MB_REFILL();                                       // (the low bits `e` was selected by are unchanged)
           continue;
         }
-        if (e & F_SUB) {
-          bb >>= LIT_BITS; bc -= LIT_BITS;
-          e = lt[e_value(e) + (uint32_t)(bb & ((1u << e_extra(e)) - 1))];
-          if (e & F_LITERAL) {
+        if (e & (F_SUB | F_EOB | F_BAD)) {                   // the rare cases behind one test: a length code is none of them
+          if (e & F_SUB) {
+            bb >>= LIT_BITS; bc -= LIT_BITS;
+            e = lt[e_value(e) + (uint32_t)(bb & ((1u << e_extra(e)) - 1))];
+            if (e & F_LITERAL) {
+              bb >>= e_len(e); bc -= (int)e_len(e);
+              *op++ = (uint8_t)e_value(e);
+              e = lt[bb & LMASK];
+              MB_REFILL();
+              continue;
+            }
+          }
+          if (e & (F_EOB | F_BAD)) {
+            if (e & F_BAD) return false;
             bb >>= e_len(e); bc -= (int)e_len(e);
-            *op++ = (uint8_t)e_value(e);
-            e = lt[bb & LMASK];
-            MB_REFILL();
-            continue;
+            eob = true;
+            break;
           }
         }
         bb >>= e_len(e); bc -= (int)e_len(e);
-        if (e & (F_EOB | F_BAD)) {
-          if (e & F_BAD) return false;
-          eob = true;
-          break;
-        }
         const uint32_t length = e_value(e) + (uint32_t)(bb & ((1u << e_extra(e)) - 1));
         bb >>= e_extra(e); bc -= (int)e_extra(e);
         uint32_t d = dt[bb & DMASK];
-        if (d & F_SUB) {
-          bb >>= DIST_BITS; bc -= DIST_BITS;
-          d = dt[e_value(d) + (uint32_t)(bb & ((1u << e_extra(d)) - 1))];
+        if (d & (F_SUB | F_BAD)) {
+          if (d & F_SUB) {
+            bb >>= DIST_BITS; bc -= DIST_BITS;
+            d = dt[e_value(d) + (uint32_t)(bb & ((1u << e_extra(d)) - 1))];
+          }
+          if (d & F_BAD) return false;
         }
-        if (d & F_BAD) return false;
         bb >>= e_len(d); bc -= (int)e_len(d);
         const uint32_t dist = e_value(d) + (uint32_t)(bb & ((1u << e_extra(d)) - 1));
         bb >>= e_extra(d); bc -= (int)e_extra(d);
